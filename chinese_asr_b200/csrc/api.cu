@@ -1,0 +1,687 @@
+// C ABI of libasr_b200.so (see include/asr_b200.h for the contract and the reference call each
+// entry point replaces).  Host-side orchestration only: metadata, weight packing, launch order.
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+
+#include "asr_internal.cuh"
+
+namespace asr {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+static int dev_alloc(std::vector<void*>& pool, void** p, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    ASR_CUDA(cudaMalloc(p, bytes));
+    pool.push_back(*p);
+    return ASR_OK;
+}
+template <typename T>
+static int dev_alloc_t(std::vector<void*>& pool, T** p, size_t count) {
+    return dev_alloc(pool, reinterpret_cast<void**>(p), count * sizeof(T));
+}
+template <typename T>
+static int dev_upload(std::vector<void*>& pool, T** p, const std::vector<T>& v) {
+    ASR_TRY(dev_alloc_t(pool, p, v.size()));
+    ASR_CUDA(cudaMemcpy(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return ASR_OK;
+}
+
+// ---- stage timing ----------------------------------------------------------------------------
+enum Stage { kStFeat = 0, kStEncGemm, kStEncRec, kStKeys, kStCell, kStAttn, kStProj, kStTopk };
+
+struct StageScope {
+    asr_handle* h; cudaStream_t st; int idx;
+    StageScope(asr_handle* h_, int stage, cudaStream_t st_) : h(h_), st(st_), idx(-1) {
+        if (!h->timing) return;
+        const int cap = (int)(sizeof(h->ev_stage) / sizeof(h->ev_stage[0]));
+        if (h->n_ev >= cap) return;
+        idx = h->n_ev++;
+        h->ev_stage[idx] = stage;
+        if (!h->ev[2 * idx]) { cudaEventCreate(&h->ev[2 * idx]); cudaEventCreate(&h->ev[2 * idx + 1]); }
+        cudaEventRecord(h->ev[2 * idx], st);
+    }
+    ~StageScope() { if (idx >= 0) cudaEventRecord(h->ev[2 * idx + 1], st); }
+};
+
+// ---- batch metadata --------------------------------------------------------------------------
+static int prepare_batch(asr_handle* h, const int32_t* h_L, int B, cudaStream_t st) {
+    BatchMeta& m = h->meta;
+    Workspace& w = h->ws;
+    if (B <= 0) { set_error("empty batch"); return ASR_ERR_ARG; }
+    if (B > w.max_utts) { set_error("batch %d > reserved %d utterances", B, w.max_utts); return ASR_ERR_CAPACITY; }
+    int64_t rows = 0;
+    int lmax = 0;
+    for (int i = 0; i < B; ++i) {
+        if (h_L[i] <= 0) { set_error("utterance %d has %d frames", i, h_L[i]); return ASR_ERR_ARG; }
+        rows += h_L[i];
+        lmax = std::max(lmax, (int)h_L[i]);
+    }
+    if (rows > w.max_rows) { set_error("batch has %lld frames > reserved %lld", (long long)rows, (long long)w.max_rows); return ASR_ERR_CAPACITY; }
+    m.B = B; m.Lmax = lmax; m.rows = rows;
+    m.order.resize(B);
+    std::iota(m.order.begin(), m.order.end(), 0);
+    std::stable_sort(m.order.begin(), m.order.end(), [&](int a, int b) { return h_L[a] > h_L[b]; });
+    m.len_sorted.resize(B);
+    m.uoff_sorted.assign(B + 1, 0);
+    m.foff_orig.assign(B + 1, 0);
+    for (int r = 0; r < B; ++r) {
+        m.len_sorted[r] = h_L[m.order[r]];
+        m.uoff_sorted[r + 1] = m.uoff_sorted[r] + m.len_sorted[r];
+    }
+    for (int i = 0; i < B; ++i) m.foff_orig[i + 1] = m.foff_orig[i] + h_L[i];
+    m.toff.assign(lmax + 1, 0);
+    {
+        int nact = B;
+        for (int t = 0; t < lmax; ++t) {
+            while (nact > 0 && m.len_sorted[nact - 1] <= t) --nact;
+            m.toff[t + 1] = m.toff[t] + nact;
+        }
+    }
+    std::vector<int> pack_src(rows), feat2packed(rows);
+    for (int r = 0; r < B; ++r) {
+        const int f0 = m.foff_orig[m.order[r]];
+        for (int t = 0; t < m.len_sorted[r]; ++t) {
+            const int prow = m.toff[t] + r;
+            pack_src[prow] = f0 + t;
+            feat2packed[f0 + t] = prow;
+        }
+    }
+    // one staging buffer, one H2D copy
+    const size_t n_int = (size_t)B + B + (lmax + 1) + (B + 1) + (B + 1) + 2 * (size_t)rows;
+    if (n_int * sizeof(int) > w.h_stage_bytes) { set_error("staging buffer too small"); return ASR_ERR_CAPACITY; }
+    int* hs = reinterpret_cast<int*>(w.h_stage);
+    size_t o = 0;
+    auto put = [&](const std::vector<int>& v, int** dptr, int* dbase) {
+        memcpy(hs + o, v.data(), v.size() * sizeof(int));
+        *dptr = dbase + o;
+        o += v.size();
+    };
+    int* dbase = m.d_order;   // base of the device metadata block (allocated in asr_reserve)
+    int* d0 = dbase;
+    put(m.order, &m.d_order, d0);
+    put(m.len_sorted, &m.d_len_sorted, d0);
+    put(m.toff, &m.d_toff, d0);
+    put(m.uoff_sorted, &m.d_uoff_sorted, d0);
+    put(m.foff_orig, &m.d_foff_orig, d0);
+    put(pack_src, &m.d_pack_src, d0);
+    put(feat2packed, &m.d_feat2packed, d0);
+    // the pinned staging buffer is reused by the next batch: wait for this copy before returning
+    ASR_CUDA(cudaMemcpyAsync(d0, hs, o * sizeof(int), cudaMemcpyHostToDevice, st));
+    ASR_CUDA(cudaStreamSynchronize(st));
+    h->encoded = false;
+    return ASR_OK;
+}
+
+static int run_encoder(asr_handle* h, int upto_layer, cudaStream_t st) {
+    Workspace& w = h->ws;
+    const BatchMeta& m = h->meta;
+    const int M = (int)m.rows;
+    const float* x = w.xpack;
+    int K = kFeat;
+    for (int layer = 0; layer <= upto_layer; ++layer) {
+        {
+            StageScope sc(h, kStEncGemm, st);
+            GemmEpilogue e{};
+            e.kind = Epi::kBias;
+            e.bias = h->w.enc_bias[layer];
+            e.C = w.xg;
+            e.ldc = 2 * kGates;
+            ASR_TRY(launch_gemm(plain_a(x, K, K), h->w.enc_w_ih[layer], M, 2 * kGates, K, e, st, &h->launches));
+        }
+        {
+            StageScope sc(h, kStEncRec, st);
+            const bool last = layer == 3;
+            float* y = w.act[layer & 1];
+            ASR_TRY(launch_lstm_recurrence(h, layer, w.xg, layer == 0 ? nullptr : x, y,
+                                           last ? w.enc : nullptr, w.h0, w.c0, st));
+            x = y;
+            K = kEnc;
+        }
+    }
+    return ASR_OK;
+}
+
+static int run_keys(asr_handle* h, cudaStream_t st) {
+    Workspace& w = h->ws;
+    StageScope sc(h, kStKeys, st);
+    GemmEpilogue e{};
+    e.kind = Epi::kBias;
+    e.bias = h->w.att_b;
+    e.C = w.keys;
+    e.ldc = kAtt;
+    return launch_gemm(plain_a(w.enc, kEnc, kEnc), h->w.att_w_enc_t, (int)h->meta.rows, kAtt, kEnc, e, st,
+                       &h->launches);
+}
+
+// one decoder step up to the logits: LSTM cell -> attention -> vocabulary projection
+static int decoder_step(asr_handle* h, int k, int step, int cur, float temperature,
+                        float* d_align_step, cudaStream_t st) {
+    Workspace& w = h->ws;
+    const int R = h->meta.B * k;
+    const int nxt = cur ^ 1;
+    {
+        StageScope sc(h, kStCell, st);
+        AOperand A{};
+        A.nseg = 3;
+        A.seg[0] = ASeg{h->w.emb, w.tok_hist + (size_t)step * R, kEmb, kEmb};
+        A.seg[1] = ASeg{w.dctx[cur], w.src_row, kEnc, kEmb + kEnc};
+        A.seg[2] = ASeg{w.dh[cur], w.src_row, kDecH, kDecK};
+        GemmEpilogue e{};
+        e.kind = Epi::kLstmCell;
+        e.bias = h->w.dec_b;
+        e.c_prev = w.dc[cur];
+        e.c_rowidx = w.src_row;
+        e.h_out = w.dh[nxt];
+        e.c_out = w.dc[nxt];
+        e.H = kDecH;
+        e.stop_flag = w.ctrl;
+        ASR_TRY(launch_gemm(A, h->w.dec_w, R, 4 * kDecH, kDecK, e, st, &h->launches));
+    }
+    {
+        StageScope sc(h, kStAttn, st);
+        ASR_TRY(launch_attention(h, k, step, nxt, d_align_step, st));
+    }
+    {
+        StageScope sc(h, kStProj, st);
+        AOperand A{};
+        A.nseg = 2;
+        A.seg[0] = ASeg{w.dh[nxt], nullptr, kDecH, kDecH};
+        A.seg[1] = ASeg{w.dctx[nxt], nullptr, kEnc, kProjK};
+        GemmEpilogue e{};
+        e.kind = temperature == 1.f ? Epi::kBias : Epi::kBiasScale;
+        e.bias = h->w.proj_b;
+        e.C = w.logits;
+        e.ldc = kVocab;
+        e.scale = temperature;
+        e.stop_flag = w.ctrl;
+        ASR_TRY(launch_gemm(A, h->w.proj_w, R, kVocab, kProjK, e, st, &h->launches));
+    }
+    return ASR_OK;
+}
+
+// After the early stop (model.py:578, 897-901) every kernel of the remaining steps returns at its
+// first instruction (ctrl[0] >= 0): no host synchronisation is needed inside the loop.
+
+static int check_decode_ready(asr_handle* h, int k, int max_len) {
+    if (!h->encoded) { set_error("decode called before asr_encode"); return ASR_ERR_STATE; }
+    if (k < 1 || k > kMaxBeam) { set_error("beam width %d outside 1..%d", k, kMaxBeam); return ASR_ERR_ARG; }
+    if (k > h->ws.max_beam) { set_error("beam width %d > reserved %d", k, h->ws.max_beam); return ASR_ERR_CAPACITY; }
+    if (max_len < 1 || max_len > h->ws.max_len) { set_error("max_len %d > reserved %d", max_len, h->ws.max_len); return ASR_ERR_CAPACITY; }
+    return ASR_OK;
+}
+
+static int beam_decode_device(asr_handle* h, int k, int max_len, float temperature, int second_pass,
+                              double lm_weight, double length_weight, cudaStream_t st) {
+    ASR_TRY(check_decode_ready(h, k, max_len));
+    if (second_pass && !h->lm.loaded) { set_error("second_pass requires asr_set_lm"); return ASR_ERR_STATE; }
+    ASR_TRY(decode_init(h, k, max_len, false, st));
+    int cur = 0;
+    for (int step = 0; step < max_len; ++step) {
+        ASR_TRY(decoder_step(h, k, step, cur, temperature, nullptr, st));
+        StageScope sc(h, kStTopk, st);
+        ASR_TRY(launch_row_topk(h, k, step, st));
+        ASR_TRY(launch_beam_bookkeep(h, k, step, max_len, st));
+        cur ^= 1;
+    }
+    {
+        StageScope sc(h, kStTopk, st);
+        ASR_TRY(launch_beam_finalise(h, k, max_len, second_pass, lm_weight, length_weight, st));
+    }
+    h->last_k = k;
+    h->last_B = h->meta.B;
+    return ASR_OK;
+}
+
+static int greedy_decode_device(asr_handle* h, int max_len, float* d_align, float* d_logits,
+                                cudaStream_t st) {
+    ASR_TRY(check_decode_ready(h, 1, max_len));
+    ASR_TRY(decode_init(h, 1, max_len, true, st));
+    const int B = h->meta.B;
+    int cur = 0;
+    for (int step = 0; step < max_len; ++step) {
+        float* al = d_align ? d_align + (size_t)step * h->meta.Lmax * B : nullptr;
+        ASR_TRY(decoder_step(h, 1, step, cur, 1.f, al, st));
+        if (d_logits) {
+            // logits are in sorted order; export in original order
+            ASR_TRY(launch_unsort_rows(h, h->ws.logits, kVocab, d_logits + (size_t)step * B * kVocab, st));
+        }
+        StageScope sc(h, kStTopk, st);
+        ASR_TRY(launch_greedy_pick(h, step, max_len, st));
+        cur ^= 1;
+    }
+    ASR_TRY(launch_greedy_finalise(h, max_len, st));
+    return ASR_OK;
+}
+
+static int fetch_results(asr_handle* h, int B, int max_len, int32_t* h_tokens, int32_t* h_len,
+                         float* h_score, int32_t* h_info, cudaStream_t st) {
+    Workspace& w = h->ws;
+    if (h_tokens) ASR_CUDA(cudaMemcpyAsync(h_tokens, w.out_tokens, sizeof(int) * (size_t)B * max_len, cudaMemcpyDeviceToHost, st));
+    if (h_len) ASR_CUDA(cudaMemcpyAsync(h_len, w.out_len, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+    if (h_score) ASR_CUDA(cudaMemcpyAsync(h_score, w.out_score, sizeof(float) * B, cudaMemcpyDeviceToHost, st));
+    int info[4];
+    ASR_CUDA(cudaMemcpyAsync(info, w.out_info, sizeof(info), cudaMemcpyDeviceToHost, st));
+    ASR_CUDA(cudaStreamSynchronize(st));
+    h->last_steps = info[0];
+    if (h_info) memcpy(h_info, info, sizeof(info));
+    return ASR_OK;
+}
+
+static int features_device(asr_handle* h, const float* d_pcm, const int64_t* h_pcm_off, int B,
+                           int32_t* h_L, int normalise, bool packed_out, float* d_out,
+                           cudaStream_t st) {
+    Workspace& w = h->ws;
+    if (B <= 0 || B > w.max_utts) { set_error("batch %d outside 1..%d", B, w.max_utts); return ASR_ERR_CAPACITY; }
+    if (h_pcm_off[B] - h_pcm_off[0] > w.max_samples) { set_error("batch has more samples than reserved"); return ASR_ERR_CAPACITY; }
+    std::vector<long long> poff(B + 1);
+    std::vector<int> foff(B + 1, 0), roff(B + 1, 0);
+    for (int i = 0; i <= B; ++i) poff[i] = h_pcm_off[i];
+    for (int i = 0; i < B; ++i) {
+        const int64_t n = h_pcm_off[i + 1] - h_pcm_off[i] - 1;
+        const int T = n < kNfft ? 0 : (int)(1 + (n - kNfft) / kHop);
+        if (T < 3) { set_error("utterance %d too short (%lld samples)", i, (long long)(n + 1)); return ASR_ERR_ARG; }
+        foff[i + 1] = foff[i] + T;
+        roff[i + 1] = roff[i] + T / 3;
+        h_L[i] = T / 3;
+    }
+    if (foff[B] > w.max_frames || roff[B] > w.max_rows) { set_error("batch has more frames than reserved"); return ASR_ERR_CAPACITY; }
+    if (packed_out) ASR_TRY(prepare_batch(h, h_L, B, st));
+    // upload offsets through the pinned staging area (synchronous: buffers are reused)
+    char* hs = reinterpret_cast<char*>(w.h_stage);
+    memcpy(hs, poff.data(), sizeof(long long) * (B + 1));
+    memcpy(hs + sizeof(long long) * (B + 1), foff.data(), sizeof(int) * (B + 1));
+    memcpy(hs + sizeof(long long) * (B + 1) + sizeof(int) * (B + 1), roff.data(), sizeof(int) * (B + 1));
+    ASR_CUDA(cudaMemcpyAsync(w.d_pcm_off, hs, sizeof(long long) * (B + 1), cudaMemcpyHostToDevice, st));
+    ASR_CUDA(cudaMemcpyAsync(w.d_frame_off, hs + sizeof(long long) * (B + 1), sizeof(int) * (B + 1), cudaMemcpyHostToDevice, st));
+    ASR_CUDA(cudaMemcpyAsync(w.d_featrow_off, hs + sizeof(long long) * (B + 1) + sizeof(int) * (B + 1), sizeof(int) * (B + 1), cudaMemcpyHostToDevice, st));
+    ASR_CUDA(cudaStreamSynchronize(st));
+    StageScope sc(h, kStFeat, st);
+    ASR_TRY(launch_logmel(h, d_pcm, w.d_pcm_off, w.d_frame_off, B, foff[B], w.mel, st));
+    ASR_TRY(launch_delta_cmvn(h, w.mel, w.d_frame_off, w.d_featrow_off, B, normalise,
+                              packed_out ? h->meta.d_feat2packed : nullptr, d_out, st));
+    return ASR_OK;
+}
+
+}  // namespace asr
+
+using namespace asr;
+
+// =============================================================================================
+extern "C" {
+
+const char* asr_last_error(void) { return g_err; }
+int asr_version(void) { return 100; }
+
+int asr_num_frames(int64_t n_samples) {
+    const int64_t n = n_samples - 1;
+    if (n < kNfft) return 0;
+    return (int)((1 + (n - kNfft) / kHop) / 3);
+}
+
+int asr_create(asr_handle** out, const asr_weights* wt, const asr_feature_consts* fc) {
+    if (!out || !wt || !fc) { set_error("asr_create: NULL argument"); return ASR_ERR_ARG; }
+    int dev = 0, cc_major = 0;
+    ASR_CUDA(cudaGetDevice(&dev));
+    ASR_CUDA(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (cc_major != 10) { set_error("asr_b200 requires an sm_100 device (found sm_%d x)", cc_major); return ASR_ERR_CUDA; }
+    asr_handle* h = new asr_handle();
+    h->device = dev;
+    std::vector<void*>& pool = h->weight_allocs;
+    int rc = build_feature_consts(h, fc);
+    if (rc != ASR_OK) { delete h; return rc; }
+
+    // encoder weights, permuted: n' = dir*1024 + j*128 + gate*32 + uu  <-  gate*256 + 32*j + uu
+    for (int layer = 0; layer < 4; ++layer) {
+        const int K = layer == 0 ? kFeat : kEnc;
+        std::vector<float> wih((size_t)2 * kGates * K), bias(2 * kGates), whh((size_t)2 * kGates * kEncH);
+        for (int dir = 0; dir < 2; ++dir) {
+            const int s = layer * 2 + dir;
+            for (int j = 0; j < 8; ++j)
+                for (int g = 0; g < 4; ++g)
+                    for (int uu = 0; uu < 32; ++uu) {
+                        const int src = g * kEncH + 32 * j + uu;
+                        const int dst = dir * kGates + j * 128 + g * 32 + uu;
+                        memcpy(&wih[(size_t)dst * K], wt->enc_w_ih[s] + (size_t)src * K, sizeof(float) * K);
+                        memcpy(&whh[(size_t)dst * kEncH], wt->enc_w_hh[s] + (size_t)src * kEncH, sizeof(float) * kEncH);
+                        bias[dst] = wt->enc_b_ih[s][src] + wt->enc_b_hh[s][src];
+                    }
+        }
+        if ((rc = dev_upload(pool, &h->w.enc_w_ih[layer], wih)) != ASR_OK) return rc;
+        if ((rc = dev_upload(pool, &h->w.enc_bias[layer], bias)) != ASR_OK) return rc;
+        if ((rc = dev_upload(pool, &h->w.enc_w_hh[layer], whh)) != ASR_OK) return rc;
+    }
+    // decoder cell: [2048, 1280] = [W_ih | W_hh], rows interleaved n' = 4*u + gate
+    {
+        std::vector<float> dw((size_t)4 * kDecH * kDecK), db(4 * kDecH);
+        for (int g = 0; g < 4; ++g)
+            for (int u = 0; u < kDecH; ++u) {
+                const int src = g * kDecH + u, dst = 4 * u + g;
+                memcpy(&dw[(size_t)dst * kDecK], wt->dec_w_ih + (size_t)src * (kEmb + kEnc), sizeof(float) * (kEmb + kEnc));
+                memcpy(&dw[(size_t)dst * kDecK + kEmb + kEnc], wt->dec_w_hh + (size_t)src * kDecH, sizeof(float) * kDecH);
+                db[dst] = wt->dec_b_ih[src] + wt->dec_b_hh[src];
+            }
+        if ((rc = dev_upload(pool, &h->w.dec_w, dw)) != ASR_OK) return rc;
+        if ((rc = dev_upload(pool, &h->w.dec_b, db)) != ASR_OK) return rc;
+    }
+    auto up = [&](float** dst, const float* src, size_t n) {
+        std::vector<float> v(src, src + n);
+        return dev_upload(pool, dst, v);
+    };
+    if ((rc = up(&h->w.emb, wt->embedding, (size_t)kVocab * kEmb)) != ASR_OK) return rc;
+    if ((rc = up(&h->w.proj_w, wt->proj_w, (size_t)kVocab * kProjK)) != ASR_OK) return rc;
+    if ((rc = up(&h->w.proj_b, wt->proj_b, kVocab)) != ASR_OK) return rc;
+    if ((rc = up(&h->w.att_b, wt->att_b, kAtt)) != ASR_OK) return rc;
+    if ((rc = up(&h->w.att_w_hidden, wt->att_w_hidden, (size_t)kDecH * kAtt)) != ASR_OK) return rc;
+    if ((rc = up(&h->w.att_v, wt->att_v, kAtt)) != ASR_OK) return rc;
+    {
+        std::vector<float> t((size_t)kAtt * kEnc);
+        for (int c = 0; c < kEnc; ++c)
+            for (int d = 0; d < kAtt; ++d) t[(size_t)d * kEnc + c] = wt->att_w_enc[(size_t)c * kAtt + d];
+        if ((rc = dev_upload(pool, &h->w.att_w_enc_t, t)) != ASR_OK) return rc;
+    }
+    *out = h;
+    return ASR_OK;
+}
+
+int asr_destroy(asr_handle* h) {
+    if (!h) return ASR_OK;
+    cudaDeviceSynchronize();
+    for (void* p : h->weight_allocs) cudaFree(p);
+    for (void* p : h->ws.allocs) cudaFree(p);
+    if (h->ws.h_stage) cudaFreeHost(h->ws.h_stage);
+    for (cudaEvent_t e : h->ev) if (e) cudaEventDestroy(e);
+    delete h;
+    return ASR_OK;
+}
+
+int asr_reserve(asr_handle* h, int max_utts, int64_t max_rows, int max_beam, int64_t max_samples,
+                int max_len) {
+    if (!h || max_utts <= 0 || max_rows <= 0 || max_beam < 1 || max_beam > kMaxBeam || max_len < 1 || max_len > 64) {
+        set_error("asr_reserve: bad argument");
+        return ASR_ERR_ARG;
+    }
+    Workspace& w = h->ws;
+    cudaDeviceSynchronize();
+    for (void* p : w.allocs) cudaFree(p);
+    w.allocs.clear();
+    if (w.h_stage) { cudaFreeHost(w.h_stage); w.h_stage = nullptr; }
+    w.max_utts = max_utts; w.max_rows = max_rows; w.max_beam = max_beam; w.max_len = max_len;
+    w.max_samples = max_samples;
+    w.max_frames = 3 * max_rows + 2 * (int64_t)max_utts;
+    std::vector<void*>& pool = w.allocs;
+    const size_t R = (size_t)max_utts * max_beam;
+    const size_t K2 = 2 * (size_t)max_beam;
+    if (max_samples > 0) {
+        ASR_TRY(dev_alloc_t(pool, &w.pcm, (size_t)max_samples));
+        ASR_TRY(dev_alloc_t(pool, &w.mel, (size_t)w.max_frames * kMel));
+    }
+    ASR_TRY(dev_alloc_t(pool, &w.xpack, (size_t)max_rows * kFeat));
+    ASR_TRY(dev_alloc_t(pool, &w.d_pcm_off, (size_t)max_utts + 1));
+    ASR_TRY(dev_alloc_t(pool, &w.d_frame_off, (size_t)max_utts + 1));
+    ASR_TRY(dev_alloc_t(pool, &w.d_featrow_off, (size_t)max_utts + 1));
+    ASR_TRY(dev_alloc_t(pool, &w.xg, (size_t)max_rows * 2 * kGates));
+    ASR_TRY(dev_alloc_t(pool, &w.act[0], (size_t)max_rows * kEnc));
+    ASR_TRY(dev_alloc_t(pool, &w.act[1], (size_t)max_rows * kEnc));
+    ASR_TRY(dev_alloc_t(pool, &w.enc, (size_t)max_rows * kEnc));
+    ASR_TRY(dev_alloc_t(pool, &w.keys, (size_t)max_rows * kAtt));
+    ASR_TRY(dev_alloc_t(pool, &w.h0, (size_t)max_utts * kEnc));
+    ASR_TRY(dev_alloc_t(pool, &w.c0, (size_t)max_utts * kEnc));
+    for (int i = 0; i < 2; ++i) {
+        ASR_TRY(dev_alloc_t(pool, &w.dh[i], R * kDecH));
+        ASR_TRY(dev_alloc_t(pool, &w.dc[i], R * kDecH));
+        ASR_TRY(dev_alloc_t(pool, &w.dctx[i], R * kEnc));
+    }
+    ASR_TRY(dev_alloc_t(pool, &w.logits, R * kVocab));
+    ASR_TRY(dev_alloc_t(pool, &w.att_part, (size_t)max_utts * 8 * max_beam * 514));
+    // raw attention scores are only exported by the greedy path (k = 1)
+    w.att_score_ld = std::min<int64_t>(max_rows, 4096);
+    ASR_TRY(dev_alloc_t(pool, &w.att_score, (size_t)max_utts * w.att_score_ld));
+    ASR_TRY(dev_alloc_t(pool, &w.att_ticket, (size_t)max_utts));
+    ASR_TRY(dev_alloc_t(pool, &w.tok_hist, (size_t)(max_len + 1) * R));
+    ASR_TRY(dev_alloc_t(pool, &w.prev_hist, (size_t)(max_len + 1) * R));
+    ASR_TRY(dev_alloc_t(pool, &w.src_row, R));
+    ASR_TRY(dev_alloc_t(pool, &w.beam_score, R));
+    ASR_TRY(dev_alloc_t(pool, &w.rowcand_s, R * K2));
+    ASR_TRY(dev_alloc_t(pool, &w.rowcand_t, R * K2));
+    ASR_TRY(dev_alloc_t(pool, &w.fin_score, (size_t)max_len * R));
+    ASR_TRY(dev_alloc_t(pool, &w.fin_row, (size_t)max_len * R));
+    ASR_TRY(dev_alloc_t(pool, &w.tr_cand_s, (size_t)max_len * max_utts * K2));
+    ASR_TRY(dev_alloc_t(pool, &w.tr_cand_b, (size_t)max_len * max_utts * K2));
+    ASR_TRY(dev_alloc_t(pool, &w.tr_cand_t, (size_t)max_len * max_utts * K2));
+    ASR_TRY(dev_alloc_t(pool, &w.tr_bp, (size_t)max_len * R));
+    ASR_TRY(dev_alloc_t(pool, &w.tr_tok, (size_t)max_len * R));
+    ASR_TRY(dev_alloc_t(pool, &w.top_done, (size_t)max_utts));
+    ASR_TRY(dev_alloc_t(pool, &w.ctrl, 8));
+    ASR_TRY(dev_alloc_t(pool, &w.g_accum, (size_t)max_utts));
+    ASR_TRY(dev_alloc_t(pool, &w.g_finished, (size_t)max_utts));
+    ASR_TRY(dev_alloc_t(pool, &w.g_len, (size_t)max_utts));
+    ASR_TRY(dev_alloc_t(pool, &w.g_tokens, (size_t)max_len * max_utts));
+    ASR_TRY(dev_alloc_t(pool, &w.out_tokens, (size_t)max_utts * max_len));
+    ASR_TRY(dev_alloc_t(pool, &w.out_len, (size_t)max_utts));
+    ASR_TRY(dev_alloc_t(pool, &w.out_score, (size_t)max_utts));
+    ASR_TRY(dev_alloc_t(pool, &w.out_info, 4));
+    // device metadata block + pinned staging
+    const size_t meta_ints = 4 * (size_t)max_utts + 8 + 2 * (size_t)max_rows + (size_t)max_rows + 8;
+    int* meta_block = nullptr;
+    ASR_TRY(dev_alloc_t(pool, &meta_block, meta_ints));
+    h->meta.d_order = meta_block;
+    w.h_stage_bytes = std::max(meta_ints * sizeof(int), (size_t)(max_utts + 1) * 16 + 64);
+    ASR_CUDA(cudaMallocHost(&w.h_stage, w.h_stage_bytes));
+    h->encoded = false;
+    return ASR_OK;
+}
+
+int asr_features(asr_handle* h, const float* d_pcm, const int64_t* h_pcm_off, int B, float* d_feats,
+                 int32_t* h_L, int normalise, void* stream) {
+    if (!h || !d_pcm || !h_pcm_off || !d_feats || !h_L) { set_error("asr_features: NULL argument"); return ASR_ERR_ARG; }
+    if (h->ws.max_samples <= 0) { set_error("asr_features: reserve with max_samples > 0"); return ASR_ERR_STATE; }
+    cudaStream_t st = (cudaStream_t)stream;
+    ASR_TRY(features_device(h, d_pcm, h_pcm_off, B, h_L, normalise, false, d_feats, st));
+    ASR_CUDA(cudaStreamSynchronize(st));
+    return ASR_OK;
+}
+
+int asr_encode(asr_handle* h, const float* d_feats, const int32_t* h_L, int B, void* stream) {
+    if (!h || !d_feats || !h_L) { set_error("asr_encode: NULL argument"); return ASR_ERR_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    ASR_TRY(prepare_batch(h, h_L, B, st));
+    ASR_TRY(launch_pack_rows(h, d_feats, h->meta.d_pack_src, h->meta.rows, kFeat, h->ws.xpack, st));
+    ASR_TRY(run_encoder(h, 3, st));
+    ASR_TRY(run_keys(h, st));
+    h->encoded = true;
+    return ASR_OK;
+}
+
+int asr_encode_layers(asr_handle* h, const float* d_feats, const int32_t* h_L, int B, int upto_layer,
+                      float* d_layer_out, void* stream) {
+    if (!h || !d_feats || !h_L || !d_layer_out || upto_layer < 0 || upto_layer > 3) { set_error("asr_encode_layers: bad argument"); return ASR_ERR_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    ASR_TRY(prepare_batch(h, h_L, B, st));
+    ASR_TRY(launch_pack_rows(h, d_feats, h->meta.d_pack_src, h->meta.rows, kFeat, h->ws.xpack, st));
+    ASR_TRY(run_encoder(h, upto_layer, st));
+    ASR_TRY(launch_export_packed_padded(h, h->ws.act[upto_layer & 1], kEnc, d_layer_out, st));
+    ASR_CUDA(cudaStreamSynchronize(st));
+    return ASR_OK;
+}
+
+int asr_export_encoder(asr_handle* h, float* d_enc_out, float* d_keys, float* d_h, float* d_c, void* stream) {
+    if (!h || !h->encoded) { set_error("asr_export_encoder before asr_encode"); return ASR_ERR_STATE; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const BatchMeta& m = h->meta;
+    if (d_enc_out) ASR_TRY(launch_export_padded(h, h->ws.enc, kEnc, d_enc_out, m.Lmax, m.B, nullptr, st));
+    if (d_keys) ASR_TRY(launch_export_padded(h, h->ws.keys, kAtt, d_keys, m.Lmax, m.B, h->w.att_b, st));
+    if (d_h) ASR_TRY(launch_unsort_rows(h, h->ws.h0, kEnc, d_h, st));
+    if (d_c) ASR_TRY(launch_unsort_rows(h, h->ws.c0, kEnc, d_c, st));
+    ASR_CUDA(cudaStreamSynchronize(st));
+    return ASR_OK;
+}
+
+int asr_decode_greedy(asr_handle* h, int max_len, int32_t* h_tokens, int32_t* h_len, float* h_score_sum,
+                      int32_t* h_finished, int32_t* h_steps, float* d_align, float* d_logits, void* stream) {
+    if (!h) { set_error("NULL handle"); return ASR_ERR_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    ASR_TRY(greedy_decode_device(h, max_len, d_align, d_logits, st));
+    if (h_finished) ASR_CUDA(cudaMemcpyAsync(h_finished, h->ws.top_done, sizeof(int) * h->meta.B, cudaMemcpyDeviceToHost, st));
+    int info[4];
+    ASR_TRY(fetch_results(h, h->meta.B, max_len, h_tokens, h_len, h_score_sum, info, st));
+    if (h_steps) *h_steps = info[0];
+    return ASR_OK;
+}
+
+int asr_set_lm(asr_handle* h, const asr_lm_tables* t) {
+    if (!h || !t || t->vocab <= 0 || (t->bi_cap & (t->bi_cap - 1)) || (t->tri_cap & (t->tri_cap - 1))) {
+        set_error("asr_set_lm: bad tables");
+        return ASR_ERR_ARG;
+    }
+    std::vector<void*>& pool = h->weight_allocs;
+    LmTables& lm = h->lm;
+    auto upf = [&](float** d, const float* s, size_t n) { std::vector<float> v(s, s + n); return dev_upload(pool, d, v); };
+    auto upl = [&](long long** d, const int64_t* s, size_t n) { std::vector<long long> v(s, s + n); return dev_upload(pool, d, v); };
+    ASR_TRY(upf(&lm.uni_logp, t->uni_logp, t->vocab));
+    ASR_TRY(upf(&lm.uni_bo, t->uni_bo, t->vocab));
+    ASR_TRY(upl(&lm.bi_keys, t->bi_keys, t->bi_cap));
+    ASR_TRY(upf(&lm.bi_vals, t->bi_vals, 2 * (size_t)t->bi_cap));
+    ASR_TRY(upl(&lm.tri_keys, t->tri_keys, t->tri_cap));
+    ASR_TRY(upf(&lm.tri_vals, t->tri_vals, t->tri_cap));
+    lm.bi_cap = t->bi_cap; lm.tri_cap = t->tri_cap; lm.vocab = t->vocab; lm.skip_id = t->skip_id;
+    lm.loaded = true;
+    return ASR_OK;
+}
+
+int asr_lm_score(asr_handle* h, const int32_t* h_ids, const int32_t* h_n, int n, int max_n, float* h_scores, void* stream) {
+    if (!h || !h->lm.loaded) { set_error("asr_lm_score: no LM loaded"); return ASR_ERR_STATE; }
+    if (n <= 0) return ASR_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int *d_ids = nullptr, *d_n = nullptr; float* d_s = nullptr;
+    ASR_CUDA(cudaMalloc(&d_ids, sizeof(int) * (size_t)n * max_n));
+    ASR_CUDA(cudaMalloc(&d_n, sizeof(int) * n));
+    ASR_CUDA(cudaMalloc(&d_s, sizeof(float) * n));
+    ASR_CUDA(cudaMemcpyAsync(d_ids, h_ids, sizeof(int) * (size_t)n * max_n, cudaMemcpyHostToDevice, st));
+    ASR_CUDA(cudaMemcpyAsync(d_n, h_n, sizeof(int) * n, cudaMemcpyHostToDevice, st));
+    int rc = launch_lm_score(h, d_ids, d_n, n, max_n, d_s, st);
+    if (rc == ASR_OK) {
+        cudaMemcpyAsync(h_scores, d_s, sizeof(float) * n, cudaMemcpyDeviceToHost, st);
+        cudaStreamSynchronize(st);
+    }
+    cudaFree(d_ids); cudaFree(d_n); cudaFree(d_s);
+    return rc;
+}
+
+int asr_decode_beam(asr_handle* h, int k, int max_len, float temperature, int second_pass, double lm_weight,
+                    double length_weight, int32_t* h_tokens, int32_t* h_len, float* h_score, int32_t* h_info,
+                    void* stream) {
+    if (!h) { set_error("NULL handle"); return ASR_ERR_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    ASR_TRY(beam_decode_device(h, k, max_len, temperature, second_pass, lm_weight, length_weight, st));
+    return fetch_results(h, h->meta.B, max_len, h_tokens, h_len, h_score, h_info, st);
+}
+
+int asr_beam_trace(asr_handle* h, float* h_cand_score, int32_t* h_cand_beam, int32_t* h_cand_tok,
+                   int32_t* h_backptr, int32_t* h_active_tok, float* h_fin_score) {
+    if (!h || h->last_k <= 0) { set_error("asr_beam_trace: no beam decode yet"); return ASR_ERR_STATE; }
+    ASR_CUDA(cudaDeviceSynchronize());
+    const int B = h->last_B, k = h->last_k, K = 2 * k, steps = h->last_steps;
+    const Workspace& w = h->ws;
+    const std::vector<int>& order = h->meta.order;
+    auto fetch = [&](auto* dst, const auto* src, int width, bool is_fin) -> int {
+        using T = std::remove_pointer_t<decltype(dst)>;
+        if (!dst) return ASR_OK;
+        std::vector<T> tmp((size_t)steps * B * width);
+        ASR_CUDA(cudaMemcpy(tmp.data(), src, sizeof(T) * tmp.size(), cudaMemcpyDeviceToHost));
+        for (int s = 0; s < steps; ++s)
+            for (int u = 0; u < B; ++u)
+                memcpy(dst + ((size_t)s * B + order[u]) * width, tmp.data() + ((size_t)s * B + u) * width, sizeof(T) * width);
+        (void)is_fin;
+        return ASR_OK;
+    };
+    ASR_TRY(fetch(h_cand_score, w.tr_cand_s, K, false));
+    ASR_TRY(fetch(h_cand_beam, w.tr_cand_b, K, false));
+    ASR_TRY(fetch(h_cand_tok, w.tr_cand_t, K, false));
+    ASR_TRY(fetch(h_backptr, w.tr_bp, k, false));
+    ASR_TRY(fetch(h_active_tok, w.tr_tok, k, false));
+    if (h_fin_score) {
+        std::vector<float> fs((size_t)steps * B * k);
+        std::vector<int> fr((size_t)steps * B * k);
+        ASR_CUDA(cudaMemcpy(fs.data(), w.fin_score, sizeof(float) * fs.size(), cudaMemcpyDeviceToHost));
+        ASR_CUDA(cudaMemcpy(fr.data(), w.fin_row, sizeof(int) * fr.size(), cudaMemcpyDeviceToHost));
+        for (int s = 0; s < steps; ++s)
+            for (int u = 0; u < B; ++u)
+                for (int j = 0; j < k; ++j) {
+                    const size_t i = ((size_t)s * B + u) * k + j;
+                    h_fin_score[((size_t)s * B + order[u]) * k + j] = fr[i] >= 0 ? fs[i] : NAN;
+                }
+    }
+    return ASR_OK;
+}
+
+int asr_transcribe_device(asr_handle* h, const float* d_pcm, const int64_t* h_pcm_off, int B, int k, int max_len,
+                          float temperature, int second_pass, double lm_weight, double length_weight,
+                          int32_t* h_tokens, int32_t* h_len, float* h_score, void* stream) {
+    if (!h || !d_pcm || !h_pcm_off) { set_error("asr_transcribe: NULL argument"); return ASR_ERR_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    std::vector<int32_t> L(B);
+    ASR_TRY(features_device(h, d_pcm, h_pcm_off, B, L.data(), 1, true, h->ws.xpack, st));
+    ASR_TRY(run_encoder(h, 3, st));
+    ASR_TRY(run_keys(h, st));
+    h->encoded = true;
+    if (k <= 0) {
+        ASR_TRY(greedy_decode_device(h, max_len, nullptr, nullptr, st));
+    } else {
+        ASR_TRY(beam_decode_device(h, k, max_len, temperature, second_pass, lm_weight, length_weight, st));
+    }
+    return fetch_results(h, B, max_len, h_tokens, h_len, h_score, nullptr, st);
+}
+
+int asr_transcribe(asr_handle* h, const float* h_pcm, const int64_t* h_pcm_off, int B, int k, int max_len,
+                   float temperature, int second_pass, double lm_weight, double length_weight,
+                   int32_t* h_tokens, int32_t* h_len, float* h_score, void* stream) {
+    if (!h || !h_pcm || !h_pcm_off) { set_error("asr_transcribe: NULL argument"); return ASR_ERR_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = h_pcm_off[B] - h_pcm_off[0];
+    if (n > h->ws.max_samples) { set_error("batch has more samples than reserved"); return ASR_ERR_CAPACITY; }
+    ASR_CUDA(cudaMemcpyAsync(h->ws.pcm, h_pcm + h_pcm_off[0], sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, st));
+    std::vector<int64_t> off(B + 1);
+    for (int i = 0; i <= B; ++i) off[i] = h_pcm_off[i] - h_pcm_off[0];
+    return asr_transcribe_device(h, h->ws.pcm, off.data(), B, k, max_len, temperature, second_pass, lm_weight,
+                                 length_weight, h_tokens, h_len, h_score, stream);
+}
+
+int64_t asr_launch_count(asr_handle* h, int reset) {
+    if (!h) return 0;
+    const int64_t n = h->launches;
+    if (reset) h->launches = 0;
+    return n;
+}
+
+int asr_stage_timing(asr_handle* h, int enable) {
+    if (!h) return ASR_ERR_ARG;
+    h->timing = enable != 0;
+    h->n_ev = 0;
+    return ASR_OK;
+}
+
+int asr_stage_times(asr_handle* h, float* h_ms, int n) {
+    if (!h || !h_ms) return ASR_ERR_ARG;
+    ASR_CUDA(cudaDeviceSynchronize());
+    float acc[kStages] = {};
+    for (int i = 0; i < h->n_ev; ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->ev[2 * i], h->ev[2 * i + 1]) == cudaSuccess) acc[h->ev_stage[i]] += ms;
+    }
+    for (int i = 0; i < n && i < kStages; ++i) h_ms[i] = acc[i];
+    h->n_ev = 0;
+    return ASR_OK;
+}
+
+}  // extern "C"

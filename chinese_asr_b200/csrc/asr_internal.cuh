@@ -1,0 +1,285 @@
+// Internal declarations shared by the translation units of libasr_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/asr_b200.h"
+
+namespace asr {
+
+constexpr int kFeat = ASR_FEAT_DIM;     // 720
+constexpr int kMel = ASR_N_MELS;        // 80
+constexpr int kEncH = 256;              // per direction
+constexpr int kEnc = ASR_ENC_OUT;       // 512
+constexpr int kGates = 1024;            // 4 * kEncH, per direction
+constexpr int kAtt = ASR_ATT;           // 128
+constexpr int kDecH = ASR_DEC_H;        // 512
+constexpr int kEmb = ASR_EMB;           // 256
+constexpr int kVocab = ASR_VOCAB;       // 5004
+constexpr int kDecK = kEmb + kEnc + kDecH;   // 1280: [emb | ctx_prev | h_prev]
+constexpr int kProjK = kDecH + kEnc;    // 1024: [h | ctx]
+constexpr int kPad = 0, kSos = 1, kEos = 2;
+constexpr int kNfft = 512, kHop = 160, kWin = 400, kBins = 257, kWinOff = 56;
+constexpr int kMaxBeam = ASR_MAX_BEAM;
+constexpr int kNumSMs = 148;
+constexpr int kStages = 8;
+
+void set_error(const char* fmt, ...);
+
+#define ASR_CUDA(call)                                                                        \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) {                                                              \
+            asr::set_error("%s:%d CUDA error %s: %s", __FILE__, __LINE__, #call,              \
+                           cudaGetErrorString(e_));                                           \
+            return ASR_ERR_CUDA;                                                              \
+        }                                                                                     \
+    } while (0)
+
+#define ASR_CHECK_LAUNCH()                                                                    \
+    do {                                                                                      \
+        cudaError_t e_ = cudaGetLastError();                                                  \
+        if (e_ != cudaSuccess) {                                                              \
+            asr::set_error("%s:%d kernel launch failed: %s", __FILE__, __LINE__,              \
+                           cudaGetErrorString(e_));                                           \
+            return ASR_ERR_CUDA;                                                              \
+        }                                                                                     \
+    } while (0)
+
+#define ASR_TRY(expr)                                                                         \
+    do {                                                                                      \
+        int rc_ = (expr);                                                                     \
+        if (rc_ != ASR_OK) return rc_;                                                        \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// A operand of the GEMMs: up to three K-segments, each optionally row-gathered.  This is how the
+// decoder reads [emb[tok] | ctx[src] | h[src]] without materialising the concatenation or the
+// reference's reorder-by-backpointer copies (model.py:913-925).
+struct ASeg {
+    const float* base;
+    const int* rowidx;   // nullptr -> identity
+    int ld;              // row stride in floats
+    int kend;            // exclusive end of this segment along K
+};
+struct AOperand {
+    ASeg seg[3];
+    int nseg;
+};
+inline AOperand plain_a(const float* a, int ld, int K) {
+    AOperand o{};
+    o.nseg = 1;
+    o.seg[0] = ASeg{a, nullptr, ld, K};
+    return o;
+}
+
+enum class Epi : int {
+    kBias = 0,      // C = acc + bias[n]
+    kBiasScale,     // C = (acc + bias[n]) / scale      (logit /= temperature, model.py:834)
+    kLstmCell       // N is gate-interleaved (n = 4*u + gate): writes h, c  (nn.LSTMCell)
+};
+
+struct GemmEpilogue {
+    Epi kind;
+    const float* bias;     // [N]
+    float* C;              // [M, ldc]        (kBias / kBiasScale)
+    int ldc;
+    float scale;
+    // kLstmCell
+    const float* c_prev;   // [*, H] gathered through c_rowidx
+    const int* c_rowidx;
+    float* h_out;          // [M, H]
+    float* c_out;          // [M, H]
+    int H;
+    const int* stop_flag;  // optional: kernel returns immediately when *stop_flag >= 0
+};
+
+// C[M,N] = A[M,K] * W[N,K]^T (+ epilogue).  fp32 in, fp32 accumulate.
+int launch_gemm(const AOperand& A, const float* W, int M, int N, int K, const GemmEpilogue& epi,
+                cudaStream_t st, int64_t* launches);
+
+// ---------------------------------------------------------------------------------------------
+struct FeatureConsts {
+    float* window = nullptr;     // [400]
+    float2* tw256 = nullptr;     // [256] exp(-2 pi i k / 256)
+    float2* tw512 = nullptr;     // [257] exp(-2 pi i k / 512)
+    int* mel_start = nullptr;    // [80]
+    int* mel_len = nullptr;      // [80]
+    float* mel_w = nullptr;      // [80, mel_maxw]
+    int mel_maxw = 0;
+    float taps[27];
+    float preemph = 0.97f;
+};
+
+struct PackedWeights {
+    // encoder: per layer, both directions concatenated along N and permuted so that the 128
+    // gate pre-activations a recurrence CTA needs are contiguous:
+    //   n' = dir*1024 + j*128 + gate*32 + uu   <->  reference row gate*256 + 32*j + uu
+    float* enc_w_ih[4] = {};     // [2048, K_l]
+    float* enc_bias[4] = {};     // [2048]  b_ih + b_hh, same permutation
+    float* enc_w_hh[4] = {};     // [2, 1024, 256] same permutation per direction
+    // decoder cell: [2048, 1280] = [W_ih | W_hh], rows interleaved n' = 4*u + gate
+    float* dec_w = nullptr;
+    float* dec_b = nullptr;      // [2048] b_ih + b_hh interleaved
+    float* emb = nullptr;        // [5004, 256]
+    float* proj_w = nullptr;     // [5004, 1024]
+    float* proj_b = nullptr;     // [5004]
+    float* att_w_enc_t = nullptr;    // [128, 512]  (W_enc transposed -> [N, K])
+    float* att_b = nullptr;          // [128]
+    float* att_w_hidden = nullptr;   // [512, 128]  as stored (k-major rows, coalesced over d)
+    float* att_v = nullptr;          // [128]
+};
+
+struct LmTables {
+    float* uni_logp = nullptr;
+    float* uni_bo = nullptr;
+    long long* bi_keys = nullptr;
+    float* bi_vals = nullptr;
+    long long bi_cap = 0;
+    long long* tri_keys = nullptr;
+    float* tri_vals = nullptr;
+    long long tri_cap = 0;
+    int vocab = 0;
+    int skip_id = -1;
+    bool loaded = false;
+};
+
+// Per-batch metadata (host copy + device copy).  Utterances are processed in "sorted order"
+// (descending length, like encoder.py:47); `order[r]` is the original index of sorted rank r.
+struct BatchMeta {
+    int B = 0;
+    int Lmax = 0;
+    int64_t rows = 0;                 // sum of L
+    std::vector<int> order;           // [B] sorted rank -> original index
+    std::vector<int> len_sorted;      // [B]
+    std::vector<int> toff;            // [Lmax+1] packed time-major offsets (rows with len > t come first)
+    std::vector<int> uoff_sorted;     // [B+1] utterance-major offsets in sorted order
+    std::vector<int> foff_orig;       // [B+1] utterance-major offsets in original order (d_feats)
+    // device mirrors
+    int* d_order = nullptr;
+    int* d_len_sorted = nullptr;
+    int* d_toff = nullptr;
+    int* d_uoff_sorted = nullptr;
+    int* d_foff_orig = nullptr;
+    int* d_pack_src = nullptr;        // [rows] packed row -> row of d_feats (original order)
+    int* d_feat2packed = nullptr;     // [rows] row of d_feats -> packed row
+};
+
+struct Workspace {
+    int max_utts = 0, max_beam = 0, max_len = 0;
+    int64_t max_rows = 0, max_samples = 0, max_frames = 0;
+    // features
+    float* pcm = nullptr;        // [max_samples] staging for asr_transcribe
+    float* mel = nullptr;        // [max_frames, 80]
+    float* xpack = nullptr;      // [max_rows, 720] packed time-major encoder input
+    long long* d_pcm_off = nullptr;  // [max_utts + 1]
+    int* d_frame_off = nullptr;      // [max_utts + 1]  STFT frames prefix
+    int* d_featrow_off = nullptr;    // [max_utts + 1]  feature rows prefix (original order)
+    // encoder
+    float* xg = nullptr;         // [max_rows, 2048]
+    float* act[2] = {};          // [max_rows, 512] packed time-major residual stream
+    float* enc = nullptr;        // [max_rows, 512] utterance-major, sorted order
+    float* keys = nullptr;       // [max_rows, 128]
+    float* h0 = nullptr;         // [max_utts, 512] last-layer final h (fwd|bwd), sorted order
+    float* c0 = nullptr;
+    // decoder
+    float* dh[2] = {};           // [R, 512]
+    float* dc[2] = {};
+    float* dctx[2] = {};
+    float* logits = nullptr;     // [R, 5004]
+    float* att_part = nullptr;   // [B, S, k, 2 + 512] partial (max, sum, ctx)
+    float* att_score = nullptr;  // [R, Lmax_cap] raw scores (alignment export)
+    int* att_ticket = nullptr;   // [B]
+    int* tok_hist = nullptr;     // [max_len + 1, R]
+    int* prev_hist = nullptr;    // [max_len + 1, R]
+    int* src_row = nullptr;      // [R] source row of the current step's state
+    float* beam_score = nullptr; // [R]
+    float* rowcand_s = nullptr;  // [R, 2k]
+    int* rowcand_t = nullptr;    // [R, 2k]
+    float* fin_score = nullptr;  // [max_len, B, k]  (NaN = none)
+    int* fin_row = nullptr;      // [max_len, B, k]
+    float* tr_cand_s = nullptr;  // [max_len, B, 2k]
+    int* tr_cand_b = nullptr;
+    int* tr_cand_t = nullptr;
+    int* tr_bp = nullptr;        // [max_len, B, k]
+    int* tr_tok = nullptr;       // [max_len, B, k]
+    int* top_done = nullptr;     // [B]
+    int* ctrl = nullptr;         // [8]: 0 stop_step(-1), 1 done_count, 2 ticket, 3 steps_run
+    // greedy
+    float* g_accum = nullptr;    // [B]
+    int* g_finished = nullptr;   // [B]
+    int* g_len = nullptr;        // [B]
+    int* g_tokens = nullptr;     // [max_len, B]
+    // results
+    int* out_tokens = nullptr;   // [B, max_len]
+    int* out_len = nullptr;      // [B]
+    float* out_score = nullptr;  // [B]
+    int* out_info = nullptr;     // [4]
+    int64_t att_score_ld = 0;
+    // pinned host staging
+    void* h_stage = nullptr;
+    size_t h_stage_bytes = 0;
+    std::vector<void*> allocs;
+};
+
+}  // namespace asr
+
+struct asr_handle {
+    int device = 0;
+    asr::FeatureConsts fc;
+    asr::PackedWeights w;
+    asr::LmTables lm;
+    asr::Workspace ws;
+    asr::BatchMeta meta;
+    bool encoded = false;
+    int last_k = 0, last_steps = 0, last_B = 0;
+    int64_t launches = 0;
+    bool timing = false;
+    cudaEvent_t ev[2 * asr::kStages * 64] = {};
+    int n_ev = 0;
+    int ev_stage[asr::kStages * 64] = {};
+    float stage_ms[asr::kStages] = {};
+    std::vector<void*> weight_allocs;
+};
+
+namespace asr {
+
+// ---- features.cu -----------------------------------------------------------------------------
+int build_feature_consts(asr_handle* h, const asr_feature_consts* fc);
+int launch_logmel(asr_handle* h, const float* d_pcm, const long long* d_pcm_off,
+                  const int* d_frame_off, int B, int total_frames, float* d_mel, cudaStream_t st);
+// out_rowmap: feature row (utterance-major, original order) -> output row; nullptr = identity
+int launch_delta_cmvn(asr_handle* h, const float* d_mel, const int* d_frame_off,
+                      const int* d_featrow_off, int B, int normalise, const int* out_rowmap,
+                      float* d_out, cudaStream_t st);
+
+// ---- encoder.cu ------------------------------------------------------------------------------
+int launch_pack_rows(asr_handle* h, const float* src, const int* rowmap, int64_t rows, int width,
+                     float* dst, cudaStream_t st);
+// one bidirectional layer recurrence.  xg [rows, 2048]; x_in residual input (nullptr for layer 0)
+// y_packed: packed time-major output (or nullptr); y_utt: utterance-major output (or nullptr)
+int launch_lstm_recurrence(asr_handle* h, int layer, const float* xg, const float* x_in,
+                           float* y_packed, float* y_utt, float* h_fin, float* c_fin,
+                           cudaStream_t st);
+int launch_export_padded(asr_handle* h, const float* src_utt, int width, float* dst, int Lmax, int B,
+                         const float* pad_row, cudaStream_t st);
+int launch_export_packed_padded(asr_handle* h, const float* src_packed, int width, float* dst,
+                                cudaStream_t st);
+int launch_unsort_rows(asr_handle* h, const float* src, int width, float* dst, cudaStream_t st);
+
+// ---- decoder.cu ------------------------------------------------------------------------------
+int decode_init(asr_handle* h, int k, int max_len, bool greedy, cudaStream_t st);
+int launch_attention(asr_handle* h, int k, int step, int cur, float* d_align_step, cudaStream_t st);
+int launch_row_topk(asr_handle* h, int k, int step, cudaStream_t st);
+int launch_beam_bookkeep(asr_handle* h, int k, int step, int max_len, cudaStream_t st);
+int launch_beam_finalise(asr_handle* h, int k, int max_len, int second_pass, double lm_weight,
+                         double length_weight, cudaStream_t st);
+int launch_greedy_pick(asr_handle* h, int step, int max_len, cudaStream_t st);
+int launch_greedy_finalise(asr_handle* h, int max_len, cudaStream_t st);
+int launch_lm_score(asr_handle* h, const int* d_ids, const int* d_n, int n, int max_n,
+                    float* d_scores, cudaStream_t st);
+
+}  // namespace asr

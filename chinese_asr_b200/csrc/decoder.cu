@@ -1,0 +1,926 @@
+// Decoder-side kernels of the greedy / beam loop (reference model.py:503-602, 604-987,
+// attention.py:91-95, decoder.py:94-137).  The two GEMMs of a step (LSTM cell, vocabulary
+// projection) are in gemm.cu; this file holds everything between and after them:
+//
+//   attention_kernel   : query projection h*W_hidden, additive scores v.tanh(keys + q), masked
+//                        softmax over time and the context reduction, for all k beams of an
+//                        utterance at once.  The encoder memory and keys of an utterance are read
+//                        ONCE per step and shared by its k beams (the reference tiles them k times
+//                        and re-gathers them every step, model.py:660-669, 913-916).  Long
+//                        utterances are split over several CTAs (flash-decoding style partial
+//                        softmax), the last CTA to finish combines the partials.
+//   row_topk_kernel    : per row: logsumexp (model.py:835), log-prob + beam score (model.py:836)
+//                        and an exact top-2k by 4-pass radix select on registers.
+//   beam_bookkeep_kernel: per utterance: merge the k rows' candidates into the top-2k over k*V
+//                        (model.py:860-867), EOS/finished bookkeeping (model.py:876-889), early
+//                        stop flag (model.py:897-901), active-set selection, back-pointers and
+//                        history (model.py:904-929).  No host sync: the stop decision is a device
+//                        flag every later kernel checks.
+//   beam_finalise_kernel: parse_finished_tensors + second-pass LM rescoring + un-finished
+//                        fallback (model.py:708-765, 945-987), n-gram LM lookups on device.
+//   greedy_pick_kernel : argmax / score / length bookkeeping of the greedy loop (model.py:554-578).
+#include <math_constants.h>
+
+#include "asr_internal.cuh"
+
+namespace asr {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// init
+struct InitParams {
+    const float* h0; const float* c0;
+    float* dh; float* dc; float* dctx;
+    int* src_row; float* beam_score; int* tok_hist; int* prev_hist; int* top_done;
+    int* ctrl; int* att_ticket;
+    float* g_accum; int* g_finished; int* g_len;
+    int B, k, R;
+};
+
+__global__ void decode_init_kernel(InitParams p) {
+    const int r = blockIdx.x;
+    const int u = r / p.k;
+    for (int c = threadIdx.x; c < kDecH; c += blockDim.x) {
+        p.dh[(size_t)r * kDecH + c] = p.h0[(size_t)u * kEnc + c];
+        p.dc[(size_t)r * kDecH + c] = p.c0[(size_t)u * kEnc + c];
+        p.dctx[(size_t)r * kEnc + c] = 0.f;
+    }
+    if (threadIdx.x == 0) {
+        p.src_row[r] = r;
+        p.beam_score[r] = 0.f;
+        p.tok_hist[r] = kSos;
+        p.prev_hist[r] = r;
+        if (r % p.k == 0) {
+            p.top_done[u] = 0;
+            p.att_ticket[u] = 0;
+            p.g_accum[u] = 0.f;
+            p.g_finished[u] = 0;
+            p.g_len[u] = 0;
+        }
+        if (r == 0) {
+            p.ctrl[0] = -1;   // stop step
+            p.ctrl[1] = 0;
+            p.ctrl[2] = 0;    // ticket
+            p.ctrl[3] = 0;    // steps run
+        }
+    }
+}
+
+int decode_init(asr_handle* h, int k, int max_len, bool greedy, cudaStream_t st) {
+    Workspace& w = h->ws;
+    const int B = h->meta.B, R = B * k;
+    InitParams p{w.h0, w.c0, w.dh[0], w.dc[0], w.dctx[0], w.src_row, w.beam_score, w.tok_hist,
+                 w.prev_hist, w.top_done, w.ctrl, w.att_ticket, w.g_accum, w.g_finished, w.g_len,
+                 B, k, R};
+    ASR_CUDA(cudaMemsetAsync(w.tok_hist, 0, sizeof(int) * (size_t)(max_len + 1) * R, st));
+    decode_init_kernel<<<R, 128, 0, st>>>(p);
+    ASR_CHECK_LAUNCH();
+    h->launches++;
+    if (!greedy) {
+        ASR_CUDA(cudaMemsetAsync(w.fin_row, 0xff, sizeof(int) * (size_t)max_len * B * k, st));
+    }
+    return ASR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// attention
+struct AttnParams {
+    const float* h;         // [R, 512] new decoder hidden state
+    const float* keys;      // [rows, 128] utterance-major sorted
+    const float* enc;       // [rows, 512]
+    const float* w_hidden;  // [512, 128]
+    const float* v;         // [128]
+    const int* uoff;        // [B + 1]
+    float* ctx_out;         // [R, 512]
+    float* part;            // [B, S, k, 514]
+    int* ticket;            // [B]
+    float* raw_score;       // [R, score_ld] or nullptr (alignment export)
+    float* align_out;       // [Lmax, B] original order for this step, or nullptr
+    const int* order;       // [B]
+    const int* ctrl;
+    int k, S, B, Lmax, sc_ld;
+    long long score_ld;
+};
+
+template <int K>
+__global__ void __launch_bounds__(256)
+attention_kernel(AttnParams p) {
+    if (p.ctrl[0] >= 0) return;
+    extern __shared__ __align__(16) float sm[];
+    float* s_q = sm;                        // [K][128]
+    float* s_sc = sm + K * kAtt;            // [K][sc_ld]
+    float* s_h = s_sc + K * p.sc_ld;        // [K][512]
+    __shared__ float s_m[K], s_sum[K];
+    __shared__ int s_last;
+
+    const int u = blockIdx.x, sp = blockIdx.y;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int k = p.k;
+    const int row0 = p.uoff[u];
+    const int L = p.uoff[u + 1] - row0;
+    const int Lc = (L + p.S - 1) / p.S;
+    const int lbeg = min(L, sp * Lc), lend = min(L, lbeg + Lc);
+    const int nl = lend - lbeg;
+
+    // ---- phase A: q = h * W_hidden ------------------------------------------------------------
+    for (int i = tid; i < k * kDecH; i += 256) s_h[i] = p.h[(size_t)u * k * kDecH + i];
+    __syncthreads();
+    {
+        const int d = tid & 127, half = tid >> 7;
+        const int kb0 = half == 0 ? 0 : (k + 1) / 2;
+        const int kb1 = half == 0 ? (k + 1) / 2 : k;
+        float acc[(K + 1) / 2];
+#pragma unroll
+        for (int i = 0; i < (K + 1) / 2; ++i) acc[i] = 0.f;
+        for (int c = 0; c < kDecH; c += 4) {
+            const float w0 = __ldg(p.w_hidden + (size_t)(c + 0) * kAtt + d);
+            const float w1 = __ldg(p.w_hidden + (size_t)(c + 1) * kAtt + d);
+            const float w2 = __ldg(p.w_hidden + (size_t)(c + 2) * kAtt + d);
+            const float w3 = __ldg(p.w_hidden + (size_t)(c + 3) * kAtt + d);
+#pragma unroll
+            for (int i = 0; i < (K + 1) / 2; ++i) {
+                const int kb = kb0 + i;
+                if (kb < kb1) {
+                    const float4 hv = *reinterpret_cast<const float4*>(s_h + kb * kDecH + c);
+                    acc[i] = fmaf(hv.x, w0, acc[i]);
+                    acc[i] = fmaf(hv.y, w1, acc[i]);
+                    acc[i] = fmaf(hv.z, w2, acc[i]);
+                    acc[i] = fmaf(hv.w, w3, acc[i]);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < (K + 1) / 2; ++i)
+            if (kb0 + i < kb1) s_q[(kb0 + i) * kAtt + d] = acc[i];
+    }
+    __syncthreads();
+
+    // ---- phase B: scores e[l][kb] = sum_d v_d tanh(key[l][d] + q[kb][d]) ----------------------
+    {
+        const float4 v4 = *reinterpret_cast<const float4*>(p.v + 4 * lane);
+        float4 q4[K];
+#pragma unroll
+        for (int kb = 0; kb < K; ++kb)
+            q4[kb] = kb < k ? *reinterpret_cast<const float4*>(s_q + kb * kAtt + 4 * lane)
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int l = lbeg + warp; l < lend; l += 8) {
+            const float4 key = __ldg(reinterpret_cast<const float4*>(p.keys + (size_t)(row0 + l) * kAtt) + lane);
+#pragma unroll
+            for (int kb = 0; kb < K; ++kb) {
+                if (kb < k) {
+                    float e = v4.x * tanhf(key.x + q4[kb].x);
+                    e = fmaf(v4.y, tanhf(key.y + q4[kb].y), e);
+                    e = fmaf(v4.z, tanhf(key.z + q4[kb].z), e);
+                    e = fmaf(v4.w, tanhf(key.w + q4[kb].w), e);
+                    e = warp_sum(e);
+                    if (lane == 0) s_sc[kb * p.sc_ld + (l - lbeg)] = e;
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase C: local softmax statistics -----------------------------------------------------
+    for (int kb = warp; kb < k; kb += 8) {
+        float* sc = s_sc + kb * p.sc_ld;
+        float m = -CUDART_INF_F;
+        for (int l = lane; l < nl; l += 32) m = fmaxf(m, sc[l]);
+        m = warp_max(m);
+        float sum = 0.f;
+        for (int l = lane; l < nl; l += 32) {
+            const float e = sc[l];
+            if (p.raw_score) p.raw_score[(size_t)(u * k + kb) * p.score_ld + lbeg + l] = e;
+            const float pe = expf(e - m);
+            sc[l] = pe;
+            sum += pe;
+        }
+        sum = warp_sum(sum);
+        if (lane == 0) { s_m[kb] = m; s_sum[kb] = sum; }
+    }
+    __syncthreads();
+
+    // ---- phase D: context partial: ctx[kb][c] = sum_l p[l][kb] * enc[l][c] ---------------------
+    float2 acc[K];
+#pragma unroll
+    for (int kb = 0; kb < K; ++kb) acc[kb] = make_float2(0.f, 0.f);
+    {
+        const float2* encp = reinterpret_cast<const float2*>(p.enc + (size_t)(row0 + lbeg) * kEnc) + tid;
+        int l = 0;
+        for (; l + 4 <= nl; l += 4) {
+            const float2 e0 = __ldg(encp + (size_t)(l + 0) * (kEnc / 2));
+            const float2 e1 = __ldg(encp + (size_t)(l + 1) * (kEnc / 2));
+            const float2 e2 = __ldg(encp + (size_t)(l + 2) * (kEnc / 2));
+            const float2 e3 = __ldg(encp + (size_t)(l + 3) * (kEnc / 2));
+#pragma unroll
+            for (int kb = 0; kb < K; ++kb) {
+                if (kb < k) {
+                    const float* sc = s_sc + kb * p.sc_ld + l;
+                    acc[kb].x = fmaf(sc[0], e0.x, acc[kb].x); acc[kb].y = fmaf(sc[0], e0.y, acc[kb].y);
+                    acc[kb].x = fmaf(sc[1], e1.x, acc[kb].x); acc[kb].y = fmaf(sc[1], e1.y, acc[kb].y);
+                    acc[kb].x = fmaf(sc[2], e2.x, acc[kb].x); acc[kb].y = fmaf(sc[2], e2.y, acc[kb].y);
+                    acc[kb].x = fmaf(sc[3], e3.x, acc[kb].x); acc[kb].y = fmaf(sc[3], e3.y, acc[kb].y);
+                }
+            }
+        }
+        for (; l < nl; ++l) {
+            const float2 e0 = __ldg(encp + (size_t)l * (kEnc / 2));
+#pragma unroll
+            for (int kb = 0; kb < K; ++kb) {
+                if (kb < k) {
+                    const float pe = s_sc[kb * p.sc_ld + l];
+                    acc[kb].x = fmaf(pe, e0.x, acc[kb].x); acc[kb].y = fmaf(pe, e0.y, acc[kb].y);
+                }
+            }
+        }
+    }
+
+    if (p.S == 1) {
+#pragma unroll
+        for (int kb = 0; kb < K; ++kb) {
+            if (kb < k) {
+                const float inv = s_sum[kb];
+                float2 o = make_float2(acc[kb].x / inv, acc[kb].y / inv);
+                reinterpret_cast<float2*>(p.ctx_out + (size_t)(u * k + kb) * kEnc)[tid] = o;
+            }
+        }
+        if (p.align_out) {       // greedy only (k == 1)
+            const float inv = s_sum[0];
+            for (int l = tid; l < p.Lmax; l += 256)
+                p.align_out[(size_t)l * p.B + p.order[u]] = l < L ? s_sc[l] / inv : 0.f;
+        }
+        return;
+    }
+
+    // ---- phase E: write partials; the last CTA of the utterance combines -----------------------
+    float* part = p.part + ((size_t)(u * p.S + sp) * k) * 514;
+#pragma unroll
+    for (int kb = 0; kb < K; ++kb) {
+        if (kb < k) {
+            reinterpret_cast<float2*>(part + (size_t)kb * 514 + 2)[tid] = acc[kb];
+            if (tid == 0) { part[(size_t)kb * 514] = s_m[kb]; part[(size_t)kb * 514 + 1] = s_sum[kb]; }
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const int t = atomicAdd(p.ticket + u, 1);
+        s_last = (t == p.S - 1);
+        if (s_last) p.ticket[u] = 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const float* pu = p.part + (size_t)u * p.S * k * 514;
+    for (int kb = 0; kb < k; ++kb) {
+        float M = -CUDART_INF_F;
+        for (int s = 0; s < p.S; ++s) M = fmaxf(M, __ldcg(pu + ((size_t)s * k + kb) * 514));
+        float denom = 0.f;
+        float2 o = make_float2(0.f, 0.f);
+        for (int s = 0; s < p.S; ++s) {
+            const float* ps = pu + ((size_t)s * k + kb) * 514;
+            const float ms = __ldcg(ps);
+            const float wgt = ms == -CUDART_INF_F ? 0.f : expf(ms - M);
+            denom = fmaf(wgt, __ldcg(ps + 1), denom);
+            const float2 c = __ldcg(reinterpret_cast<const float2*>(ps + 2) + tid);
+            o.x = fmaf(wgt, c.x, o.x);
+            o.y = fmaf(wgt, c.y, o.y);
+        }
+        o.x /= denom; o.y /= denom;
+        reinterpret_cast<float2*>(p.ctx_out + (size_t)(u * k + kb) * kEnc)[tid] = o;
+        if (p.align_out && kb == 0) {
+            const float* rs = p.raw_score + (size_t)(u * k) * p.score_ld;
+            for (int l = tid; l < p.Lmax; l += 256)
+                p.align_out[(size_t)l * p.B + p.order[u]] = l < L ? expf(__ldcg(rs + l) - M) / denom : 0.f;
+        }
+    }
+}
+
+int launch_attention(asr_handle* h, int k, int step, int nxt, float* d_align_step, cudaStream_t st) {
+    (void)step;
+    Workspace& w = h->ws;
+    const BatchMeta& m = h->meta;
+    AttnParams p{};
+    p.h = w.dh[nxt];
+    p.keys = w.keys;
+    p.enc = w.enc;
+    p.w_hidden = h->w.att_w_hidden;
+    p.v = h->w.att_v;
+    p.uoff = m.d_uoff_sorted;
+    p.ctx_out = w.dctx[nxt];
+    p.part = w.att_part;
+    p.ticket = w.att_ticket;
+    p.order = m.d_order;
+    p.ctrl = w.ctrl;
+    p.k = k;
+    p.B = m.B;
+    p.Lmax = m.Lmax;
+    int S = (2 * kNumSMs + m.B - 1) / m.B;
+    if (S > 8) S = 8;
+    if (S < 1) S = 1;
+    while (S > 1 && (m.Lmax + S - 1) / S < 16) --S;
+    p.S = S;
+    p.sc_ld = ((m.Lmax + S - 1) / S + 3) & ~3;
+    p.score_ld = w.att_score_ld;
+    p.align_out = d_align_step;
+    p.raw_score = (d_align_step && S > 1) ? w.att_score : nullptr;
+    const int K = k == 1 ? 1 : (k <= 4 ? 4 : (k <= 8 ? 8 : 16));
+    const size_t smem = sizeof(float) * ((size_t)K * kAtt + (size_t)K * p.sc_ld + (size_t)K * kDecH);
+    dim3 grid(m.B, S);
+#define ASR_LAUNCH_ATT(KK)                                                                      \
+    do {                                                                                        \
+        static size_t cur_max = 48 * 1024;                                                      \
+        if (smem > cur_max) {                                                                   \
+            ASR_CUDA(cudaFuncSetAttribute(attention_kernel<KK>,                                 \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            cur_max = smem;                                                                     \
+        }                                                                                       \
+        attention_kernel<KK><<<grid, 256, smem, st>>>(p);                                       \
+    } while (0)
+    if (smem > 200 * 1024) { set_error("attention: utterance too long (%d frames)", m.Lmax); return ASR_ERR_CAPACITY; }
+    switch (K) {
+        case 1: ASR_LAUNCH_ATT(1); break;
+        case 4: ASR_LAUNCH_ATT(4); break;
+        case 8: ASR_LAUNCH_ATT(8); break;
+        default: ASR_LAUNCH_ATT(16); break;
+    }
+#undef ASR_LAUNCH_ATT
+    ASR_CHECK_LAUNCH();
+    h->launches++;
+    return ASR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-row logsumexp + exact top-K (K = 2k <= 32)
+__device__ __forceinline__ unsigned ordered_key(float f) {
+    const unsigned b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+constexpr int kRowElems = 20;   // 256 threads * 20 >= 5004
+constexpr int kCandCap = 1024;
+
+struct RowTopkParams {
+    const float* logits;      // [R, V]
+    const float* beam_score;  // [R]
+    float* cand_s;            // [R, K]
+    int* cand_t;              // [R, K]
+    const int* ctrl;
+    int k, K, step;
+};
+
+__device__ __forceinline__ float block_reduce_max(float v, float* s_red) {
+    v = warp_max(v);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = s_red[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) r = fmaxf(r, s_red[i]);
+    __syncthreads();
+    return r;
+}
+__device__ __forceinline__ float block_reduce_sum(float v, float* s_red) {
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = s_red[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) r += s_red[i];
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(256)
+row_topk_kernel(RowTopkParams p) {
+    if (p.ctrl[0] >= 0) return;
+    const int r = blockIdx.x;
+    if (p.step == 0 && (r % p.k) != 0) return;      // step 0: only the first beam (model.py:862)
+    __shared__ float s_red[8];
+    __shared__ int s_hist[256];
+    __shared__ unsigned s_prefix;
+    __shared__ int s_krem;
+    __shared__ int s_cnt;
+    __shared__ float s_cs[kCandCap];
+    __shared__ int s_ct[kCandCap];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    const float* row = p.logits + (size_t)r * kVocab;
+    float v[kRowElems];
+    float m = -CUDART_INF_F;
+#pragma unroll
+    for (int i = 0; i < kRowElems; ++i) {
+        const int e = tid + 256 * i;
+        v[i] = e < kVocab ? row[e] : -CUDART_INF_F;
+        m = fmaxf(m, v[i]);
+    }
+    m = block_reduce_max(m, s_red);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kRowElems; ++i) s += expf(v[i] - m);      // exp(-inf) = 0 for padding
+    s = block_reduce_sum(s, s_red);
+    const float lse = m + logf(s);
+    const float bs = p.beam_score[r];
+    unsigned key[kRowElems];
+#pragma unroll
+    for (int i = 0; i < kRowElems; ++i) {
+        const int e = tid + 256 * i;
+        v[i] = __fadd_rn(__fsub_rn(v[i], lse), bs);               // model.py:835-836
+        key[i] = e < kVocab ? ordered_key(v[i]) : 0u;
+    }
+
+    // radix select: find the K-th largest key, 8 bits per pass from the top
+    if (tid == 0) { s_prefix = 0u; s_krem = p.K; s_cnt = 0; }
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        s_hist[tid] = 0;
+        __syncthreads();
+        const unsigned prefix = s_prefix;
+        const unsigned mask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+#pragma unroll
+        for (int i = 0; i < kRowElems; ++i) {
+            const int e = tid + 256 * i;
+            if (e < kVocab && (key[i] & mask) == prefix) atomicAdd(&s_hist[(key[i] >> shift) & 255], 1);
+        }
+        __syncthreads();
+        if (warp == 0) {
+            // lane owns bins [8*lane, 8*lane+8); suffix sums from the top
+            int loc[8], tot = 0;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) { loc[b] = s_hist[8 * lane + b]; tot += loc[b]; }
+            int above = 0;     // elements in lanes that own larger bins
+            for (int src = 31; src > 0; --src) {
+                const int t = __shfl_sync(0xffffffffu, tot, src);
+                if (lane < src) above += t;
+            }
+            const int krem = s_krem;
+            // the crossing lane: above < krem <= above + tot
+            if (above < krem && krem <= above + tot) {
+                int cum = above;
+                for (int b = 7; b >= 0; --b) {
+                    if (cum + loc[b] >= krem) {
+                        s_prefix = prefix | ((unsigned)(8 * lane + b) << shift);
+                        s_krem = krem - cum;
+                        break;
+                    }
+                    cum += loc[b];
+                }
+            }
+        }
+        __syncthreads();
+    }
+    const unsigned kth = s_prefix;
+    // collect every element >= kth (count = K - krem + #ties at kth), capped
+#pragma unroll
+    for (int i = 0; i < kRowElems; ++i) {
+        const int e = tid + 256 * i;
+        if (e < kVocab && key[i] >= kth) {
+            const int slot = atomicAdd(&s_cnt, 1);
+            if (slot < kCandCap) { s_cs[slot] = v[i]; s_ct[slot] = e; }
+        }
+    }
+    __syncthreads();
+    const int n = min(s_cnt, kCandCap);
+    // rank by counting: order (score desc, token asc)
+    for (int i = tid; i < n; i += 256) {
+        const float si = s_cs[i];
+        const int ti = s_ct[i];
+        int rank = 0;
+        for (int j = 0; j < n; ++j) {
+            const float sj = s_cs[j];
+            rank += (sj > si || (sj == si && s_ct[j] < ti)) ? 1 : 0;
+        }
+        if (rank < p.K) {
+            p.cand_s[(size_t)r * p.K + rank] = si;
+            p.cand_t[(size_t)r * p.K + rank] = ti;
+        }
+    }
+}
+
+int launch_row_topk(asr_handle* h, int k, int step, cudaStream_t st) {
+    Workspace& w = h->ws;
+    RowTopkParams p{w.logits, w.beam_score, w.rowcand_s, w.rowcand_t, w.ctrl, k, 2 * k, step};
+    row_topk_kernel<<<h->meta.B * k, 256, 0, st>>>(p);
+    ASR_CHECK_LAUNCH();
+    h->launches++;
+    return ASR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-utterance merge + beam bookkeeping
+struct BookParams {
+    const float* cand_s; const int* cand_t;     // [R, K]
+    float* beam_score; int* src_row;            // [R]
+    int* tok_hist; int* prev_hist;              // [max_len + 1, R]
+    float* fin_score; int* fin_row;             // [max_len, B, k]
+    float* tr_cand_s; int* tr_cand_b; int* tr_cand_t;   // [max_len, B, K]
+    int* tr_bp; int* tr_tok;                    // [max_len, B, k]
+    int* top_done; int* ctrl;
+    int B, k, K, step;
+};
+
+__global__ void __launch_bounds__(512)
+beam_bookkeep_kernel(BookParams p) {
+    if (p.ctrl[0] >= 0) return;
+    __shared__ float s_s[512];
+    __shared__ int s_f[512];
+    __shared__ float s_cs[32];
+    __shared__ int s_cf[32];
+    const int u = blockIdx.x, tid = threadIdx.x;
+    const int k = p.k, K = p.K, R = p.B * k;
+    const int nrow = p.step == 0 ? 1 : k;
+    const int n = nrow * K;
+    if (tid < n) {
+        const int b = tid / K, j = tid - b * K;
+        s_s[tid] = p.cand_s[(size_t)(u * k + b) * K + j];
+        s_f[tid] = b * kVocab + p.cand_t[(size_t)(u * k + b) * K + j];
+    }
+    __syncthreads();
+    if (tid < n) {
+        const float si = s_s[tid];
+        const int fi = s_f[tid];
+        int rank = 0;
+        for (int j = 0; j < n; ++j) {
+            const float sj = s_s[j];
+            rank += (sj > si || (sj == si && s_f[j] < fi)) ? 1 : 0;
+        }
+        if (rank < K) { s_cs[rank] = si; s_cf[rank] = fi; }
+    }
+    __syncthreads();
+    if (tid < K) {
+        const size_t o = ((size_t)p.step * p.B + u) * K + tid;
+        p.tr_cand_s[o] = s_cs[tid];
+        p.tr_cand_b[o] = s_cf[tid] / kVocab;
+        p.tr_cand_t[o] = s_cf[tid] % kVocab;
+    }
+    if (tid == 0) {
+        // finished hypotheses: </s> among the top k (model.py:876-889)
+        for (int j = 0; j < k; ++j) {
+            const int tok = s_cf[j] % kVocab;
+            const size_t o = ((size_t)p.step * p.B + u) * k + j;
+            if (tok == kEos) {
+                p.fin_score[o] = s_cs[j];
+                p.fin_row[o] = u * k + s_cf[j] / kVocab;
+            }
+        }
+        int done = p.top_done[u];
+        if (s_cf[0] % kVocab == kEos) done = 1;
+        p.top_done[u] = done;
+        // active set: first k non-EOS candidates in rank order (model.py:904-929)
+        int i = 0;
+        for (int j = 0; j < K && i < k; ++j) {
+            const int tok = s_cf[j] % kVocab;
+            if (tok == kEos) continue;
+            const int beam = s_cf[j] / kVocab;
+            const int r = u * k + i;
+            p.src_row[r] = u * k + beam;
+            p.beam_score[r] = s_cs[j];
+            p.tok_hist[(size_t)(p.step + 1) * R + r] = tok;
+            p.prev_hist[(size_t)(p.step + 1) * R + r] = u * k + beam;
+            const size_t o = ((size_t)p.step * p.B + u) * k + i;
+            p.tr_bp[o] = beam;
+            p.tr_tok[o] = tok;
+            ++i;
+        }
+        // early stop (model.py:897-901): decided by the last utterance to arrive
+        __threadfence();
+        const int t = atomicAdd(p.ctrl + 2, 1);
+        if (t == p.B - 1) {
+            __threadfence();
+            int all = 1;
+            for (int b = 0; b < p.B; ++b) all &= (*((volatile int*)p.top_done + b) != 0);
+            p.ctrl[2] = 0;
+            p.ctrl[3] = p.step + 1;
+            if (all) p.ctrl[0] = p.step;
+        }
+    }
+}
+
+int launch_beam_bookkeep(asr_handle* h, int k, int step, int max_len, cudaStream_t st) {
+    (void)max_len;
+    Workspace& w = h->ws;
+    BookParams p{w.rowcand_s, w.rowcand_t, w.beam_score, w.src_row, w.tok_hist, w.prev_hist,
+                 w.fin_score, w.fin_row, w.tr_cand_s, w.tr_cand_b, w.tr_cand_t, w.tr_bp, w.tr_tok,
+                 w.top_done, w.ctrl, h->meta.B, k, 2 * k, step};
+    beam_bookkeep_kernel<<<h->meta.B, 512, 0, st>>>(p);
+    ASR_CHECK_LAUNCH();
+    h->launches++;
+    return ASR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// n-gram LM on device (tables from asr_set_lm; semantics of oracle NGramLM / kenlm .score)
+struct LmDev {
+    const float* uni_logp; const float* uni_bo;
+    const long long* bi_keys; const float* bi_vals; long long bi_cap;
+    const long long* tri_keys; const float* tri_vals; long long tri_cap;
+    int vocab, skip_id;
+};
+
+__device__ __forceinline__ long long hash_slot(long long key, long long cap) {
+    unsigned long long z = (unsigned long long)key + 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z = z ^ (z >> 31);
+    return (long long)(z & (unsigned long long)(cap - 1));
+}
+__device__ long long lm_find(const long long* keys, long long cap, long long key) {
+    long long s = hash_slot(key, cap);
+    while (true) {
+        const long long kk = keys[s];
+        if (kk == key) return s;
+        if (kk == -1) return -1;
+        s = (s + 1) & (cap - 1);
+    }
+}
+__device__ float lm_uni_or_bi(const LmDev& lm, int c, int w) {
+    const long long s = lm_find(lm.bi_keys, lm.bi_cap, (long long)c * lm.vocab + w);
+    if (s >= 0) return lm.bi_vals[2 * s];
+    return __fadd_rn(lm.uni_bo[c], lm.uni_logp[w]);
+}
+__device__ float lm_word(const LmDev& lm, int c0, int c1, int nctx, int w) {
+    if (nctx == 2) {
+        const long long s = lm_find(lm.tri_keys, lm.tri_cap, ((long long)c0 * lm.vocab + c1) * lm.vocab + w);
+        if (s >= 0) return lm.tri_vals[s];
+        const long long b = lm_find(lm.bi_keys, lm.bi_cap, (long long)c0 * lm.vocab + c1);
+        const float bo = b >= 0 ? lm.bi_vals[2 * b + 1] : 0.f;
+        return __fadd_rn(bo, lm_uni_or_bi(lm, c1, w));
+    }
+    if (nctx == 1) return lm_uni_or_bi(lm, c1, w);
+    return lm.uni_logp[w];
+}
+// total log10 probability of ids[0..n) with <s> context and </s> appended, float32 accumulation
+__device__ float lm_score_ids(const LmDev& lm, const int* ids, int n) {
+    int c0 = 0, c1 = kSos, nctx = 1;
+    float total = 0.f;
+    for (int i = 0; i <= n; ++i) {
+        const int w = i < n ? ids[i] : kEos;
+        if (i < n && w == lm.skip_id) continue;
+        total = __fadd_rn(total, lm_word(lm, c0, c1, nctx, w));
+        c0 = c1; c1 = w; nctx = 2;
+    }
+    return total;
+}
+
+__global__ void lm_score_kernel(LmDev lm, const int* __restrict__ ids, const int* __restrict__ n,
+                                int count, int max_n, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    out[i] = lm_score_ids(lm, ids + (size_t)i * max_n, n[i]);
+}
+
+static LmDev lm_dev(const asr_handle* h) {
+    const LmTables& t = h->lm;
+    return LmDev{t.uni_logp, t.uni_bo, t.bi_keys, t.bi_vals, t.bi_cap, t.tri_keys, t.tri_vals,
+                 t.tri_cap, t.vocab, t.skip_id};
+}
+
+int launch_lm_score(asr_handle* h, const int* d_ids, const int* d_n, int n, int max_n,
+                    float* d_scores, cudaStream_t st) {
+    lm_score_kernel<<<(n + 127) / 128, 128, 0, st>>>(lm_dev(h), d_ids, d_n, n, max_n, d_scores);
+    ASR_CHECK_LAUNCH();
+    h->launches++;
+    return ASR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// finalisation
+struct FinalParams {
+    const float* fin_score; const int* fin_row;   // [max_len, B, k]
+    const int* tok_hist; const int* prev_hist;    // [max_len + 1, R]
+    const float* beam_score;                      // [R]
+    const int* ctrl; const int* order;
+    int* out_tokens; int* out_len; float* out_score; int* out_info;
+    LmDev lm;
+    int B, k, max_len, second_pass;
+    double lm_weight, length_weight;
+};
+
+constexpr int kMaxDecodeLen = 64;
+
+__device__ int backtrace(const FinalParams& p, int row, int len, int* toks) {
+    // tokens at history positions 1..len along the back-pointer chain ending in `row` at `len`
+    const int R = p.B * p.k;
+    for (int pos = len; pos >= 1; --pos) {
+        toks[pos - 1] = p.tok_hist[(size_t)pos * R + row];
+        row = p.prev_hist[(size_t)pos * R + row];
+    }
+    return len;
+}
+
+__global__ void __launch_bounds__(256)
+beam_finalise_kernel(FinalParams p) {
+    __shared__ double s_best[256];
+    __shared__ int s_idx[256];
+    __shared__ int s_cnt[256];
+    const int u = blockIdx.x, tid = threadIdx.x;
+    const int k = p.k;
+    const int steps = p.ctrl[3];
+    const int n = steps * k;                      // entry e = l*k + j, (step, rank) order
+    int cnt = 0;
+    for (int e = tid; e < n; e += 256) {
+        const int l = e / k, j = e - l * k;
+        cnt += p.fin_row[((size_t)l * p.B + u) * k + j] >= 0 ? 1 : 0;
+    }
+    s_cnt[tid] = cnt;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if (tid < o) s_cnt[tid] += s_cnt[tid + o]; __syncthreads(); }
+    const int nfin = s_cnt[0];
+    __syncthreads();
+
+    int toks[kMaxDecodeLen];
+    double best = -CUDART_INF;
+    int best_e = 0x7fffffff;
+    if (nfin > 0) {
+        for (int e = tid; e < n; e += 256) {
+            const int l = e / k, j = e - l * k;
+            const size_t o = ((size_t)l * p.B + u) * k + j;
+            const int row = p.fin_row[o];
+            if (row < 0) continue;
+            double sc = (double)p.fin_score[o];
+            if (p.second_pass && nfin > 1) {
+                backtrace(p, row, l, toks);
+                const float lm = lm_score_ids(p.lm, toks, l);
+                sc = __dadd_rn(__dadd_rn(sc, __dmul_rn(p.lm_weight, (double)lm)),
+                               __dmul_rn(p.length_weight, (double)l));      // model.py:758-759
+            }
+            if (sc > best || (sc == best && e < best_e)) { best = sc; best_e = e; }
+        }
+    }
+    s_best[tid] = best;
+    s_idx[tid] = best_e;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (tid < o) {
+            const double b2 = s_best[tid + o];
+            const int e2 = s_idx[tid + o];
+            if (b2 > s_best[tid] || (b2 == s_best[tid] && e2 < s_idx[tid])) { s_best[tid] = b2; s_idx[tid] = e2; }
+        }
+        __syncthreads();
+    }
+    if (tid != 0) return;
+    const int uo = p.order[u];
+    int* ot = p.out_tokens + (size_t)uo * p.max_len;
+    int len = 0;
+    float score;
+    if (nfin > 0) {
+        const int e = s_idx[0];
+        const int l = e / k, j = e - l * k;
+        const size_t o = ((size_t)l * p.B + u) * k + j;
+        len = backtrace(p, p.fin_row[o], l, toks);
+        score = p.fin_score[o];                    // the un-rescored log-prob (model.py:762)
+        atomicAdd(p.out_info + 3, nfin);
+    } else {
+        // un-finished fallback (model.py:961-972): best active beam with the length bonus
+        const float bonus = (float)(p.length_weight * (double)steps);
+        int bi = 0;
+        float bv = -CUDART_INF_F;
+        for (int i = 0; i < k; ++i) {
+            const float v = __fadd_rn(p.beam_score[u * k + i], bonus);
+            if (v > bv) { bv = v; bi = i; }
+        }
+        len = backtrace(p, u * k + bi, steps, toks);
+        score = bv;
+        atomicAdd(p.out_info + 2, 1);
+    }
+    for (int i = 0; i < p.max_len; ++i) ot[i] = i < len ? toks[i] : kPad;
+    p.out_len[uo] = len;
+    p.out_score[uo] = score;
+    if (u == 0) { p.out_info[0] = steps; p.out_info[1] = p.ctrl[0]; }
+}
+
+int launch_beam_finalise(asr_handle* h, int k, int max_len, int second_pass, double lm_weight,
+                         double length_weight, cudaStream_t st) {
+    Workspace& w = h->ws;
+    if (max_len > kMaxDecodeLen) { set_error("max_len %d > %d", max_len, kMaxDecodeLen); return ASR_ERR_ARG; }
+    ASR_CUDA(cudaMemsetAsync(w.out_info, 0, 4 * sizeof(int), st));
+    FinalParams p{w.fin_score, w.fin_row, w.tok_hist, w.prev_hist, w.beam_score, w.ctrl,
+                  h->meta.d_order, w.out_tokens, w.out_len, w.out_score, w.out_info, lm_dev(h),
+                  h->meta.B, k, max_len, second_pass, lm_weight, length_weight};
+    beam_finalise_kernel<<<h->meta.B, 256, 0, st>>>(p);
+    ASR_CHECK_LAUNCH();
+    h->launches++;
+    return ASR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// greedy
+struct GreedyParams {
+    const float* logits;   // [B, V]
+    int* tok_hist;         // [max_len + 1, B]
+    int* g_tokens;         // [max_len, B]
+    float* g_accum; int* g_finished; int* g_len;
+    int* ctrl;
+    int B, step;
+};
+
+__global__ void __launch_bounds__(256)
+greedy_pick_kernel(GreedyParams p) {
+    if (p.ctrl[0] >= 0) return;
+    __shared__ float s_red[8];
+    __shared__ float s_v[8];
+    __shared__ int s_i[8];
+    const int u = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* row = p.logits + (size_t)u * kVocab;
+    float v[kRowElems];
+    float m = -CUDART_INF_F;
+    int mi = 0x7fffffff;
+#pragma unroll
+    for (int i = 0; i < kRowElems; ++i) {
+        const int e = tid + 256 * i;
+        v[i] = e < kVocab ? row[e] : -CUDART_INF_F;
+        if (v[i] > m) { m = v[i]; mi = e; }          // ascending e per thread: first max kept
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float m2 = __shfl_xor_sync(0xffffffffu, m, o);
+        const int i2 = __shfl_xor_sync(0xffffffffu, mi, o);
+        if (m2 > m || (m2 == m && i2 < mi)) { m = m2; mi = i2; }
+    }
+    if (lane == 0) { s_v[warp] = m; s_i[warp] = mi; }
+    __syncthreads();
+    m = s_v[0]; mi = s_i[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i)
+        if (s_v[i] > m || (s_v[i] == m && s_i[i] < mi)) { m = s_v[i]; mi = s_i[i]; }
+    __syncthreads();
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kRowElems; ++i) s += expf(v[i] - m);
+    s = block_reduce_sum(s, s_red);
+    if (tid != 0) return;
+    const float lse = m + logf(s);
+    const float logp = __fsub_rn(m, lse);            // model.py:554,563
+    const int tok = mi;
+    p.g_tokens[(size_t)p.step * p.B + u] = tok;
+    p.tok_hist[(size_t)(p.step + 1) * p.B + u] = tok;
+    int fin = p.g_finished[u];
+    float acc = p.g_accum[u];
+    const int now = tok == kEos;
+    if (!fin && now) acc = __fadd_rn(acc, logp);     // model.py:569
+    fin |= now;
+    if (!fin) { p.g_len[u] += 1; acc = __fadd_rn(acc, logp); }   // model.py:572-575
+    p.g_finished[u] = fin;
+    p.g_accum[u] = acc;
+    __threadfence();
+    const int t = atomicAdd(p.ctrl + 2, 1);
+    if (t == p.B - 1) {
+        __threadfence();
+        int all = 1;
+        for (int b = 0; b < p.B; ++b) all &= (*((volatile int*)p.g_finished + b) != 0);
+        p.ctrl[2] = 0;
+        p.ctrl[3] = p.step + 1;
+        if (all) p.ctrl[0] = p.step;                 // model.py:578
+    }
+}
+
+int launch_greedy_pick(asr_handle* h, int step, int max_len, cudaStream_t st) {
+    (void)max_len;
+    Workspace& w = h->ws;
+    GreedyParams p{w.logits, w.tok_hist, w.g_tokens, w.g_accum, w.g_finished, w.g_len, w.ctrl,
+                   h->meta.B, step};
+    greedy_pick_kernel<<<h->meta.B, 256, 0, st>>>(p);
+    ASR_CHECK_LAUNCH();
+    h->launches++;
+    return ASR_OK;
+}
+
+__global__ void greedy_finalise_kernel(const int* __restrict__ g_tokens, const int* __restrict__ g_len,
+                                       const float* __restrict__ g_accum,
+                                       const int* __restrict__ g_finished,
+                                       const int* __restrict__ order, const int* __restrict__ ctrl,
+                                       int B, int max_len, int* out_tokens, int* out_len,
+                                       float* out_score, int* out_fin, int* out_info) {
+    const int u = blockIdx.x;
+    const int uo = order[u];
+    const int steps = ctrl[3];
+    for (int s = threadIdx.x; s < max_len; s += blockDim.x)
+        out_tokens[(size_t)uo * max_len + s] = s < steps ? g_tokens[(size_t)s * B + u] : kPad;
+    if (threadIdx.x == 0) {
+        out_len[uo] = g_len[u];
+        out_score[uo] = g_accum[u];
+        out_fin[uo] = g_finished[u];
+        if (u == 0) { out_info[0] = steps; out_info[1] = ctrl[0]; out_info[2] = 0; out_info[3] = 0; }
+    }
+}
+
+int launch_greedy_finalise(asr_handle* h, int max_len, cudaStream_t st) {
+    Workspace& w = h->ws;
+    greedy_finalise_kernel<<<h->meta.B, 64, 0, st>>>(w.g_tokens, w.g_len, w.g_accum, w.g_finished,
+                                                     h->meta.d_order, w.ctrl, h->meta.B, max_len,
+                                                     w.out_tokens, w.out_len, w.out_score,
+                                                     w.top_done, w.out_info);
+    ASR_CHECK_LAUNCH();
+    h->launches++;
+    return ASR_OK;
+}
+
+}  // namespace asr

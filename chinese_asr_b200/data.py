@@ -1,0 +1,122 @@
+"""Feature front end: the reference's data.py hot-path surface on B200.
+
+Same names and argument meaning as the reference (data.py:21-57 create_fb_matrix, :84-106 MelScale,
+:109-121 fast_read, :167-280 get_log_mel, :371-382 AudioBase), but get_log_mel runs the fused
+CUDA kernels (csrc/features.cu) through the C ABI and returns a CUDA tensor.  The host only builds
+the constant tables (filterbank, window, delta taps) once, exactly as AudioBase does."""
+import math
+import os
+import pickle
+import wave
+
+import numpy as np
+import torch
+
+from .gpd import gpd
+
+
+def create_fb_matrix(n_stft, f_min, f_max, n_mels):
+    """Triangular mel filterbank [n_stft, n_mels] (data.py:21-57): HTK mel scale, un-normalised,
+    with the reference's quirk that STFT bin j is assigned frequency linspace(f_min, f_max)[j]."""
+    def to_mel(f):
+        return 2595. * torch.log10(torch.tensor(1.) + (f / 700.))
+
+    def to_hz(m):
+        return 700. * (10 ** (m / 2595.) - 1.)
+
+    freqs = torch.linspace(f_min, f_max, n_stft)
+    m_lo = 0. if f_min == 0 else to_mel(f_min)
+    pts = to_hz(torch.linspace(m_lo, to_mel(f_max), n_mels + 2))
+    gap = pts[1:] - pts[:-1]
+    delta = pts.unsqueeze(0) - freqs.unsqueeze(1)
+    down = (-1. * delta[:, :-2]) / gap[:-1]
+    up = delta[:, 2:] / gap[1:]
+    return torch.max(torch.tensor(0.), torch.min(down, up))
+
+
+class MelScale(object):
+    """Holder of the filterbank (data.py:84-106).  Calling it on a spectrogram is not part of the
+    B200 path (the mel projection is fused into the log-mel kernel); `fb` is what is consumed."""
+
+    def __init__(self, n_mels=128, sr=16000, f_max=None, f_min=0., n_stft=None):
+        self.n_mels = n_mels
+        self.sr = sr
+        self.f_max = f_max if f_max is not None else sr // 2
+        self.f_min = f_min
+        self.fb = create_fb_matrix(n_stft, self.f_min, self.f_max, self.n_mels) if n_stft is not None else None
+
+
+def delta_filter_stack():
+    """[3, 9] identity / delta / delta-delta taps, L2-normalised per filter (data.py:138-149)."""
+    d = np.array([2, 1, 0, -1, -2])
+    dd = np.convolve(d, d, "full")
+    f = np.array([[0] * 4 + [1] + [0] * 4, [0] * 2 + list(d) + [0] * 2, list(dd)], dtype=np.float32)
+    f /= np.sqrt(np.sum(f ** 2, axis=1, keepdims=True))
+    return np.ascontiguousarray(f, dtype=np.float32)
+
+
+def fast_read(path):
+    """16-bit PCM / float32 WAV -> float32 in [-1, 1) (data.py:109-121; soundfile is replaced by
+    the stdlib wave module)."""
+    with wave.open(path, 'rb') as w:
+        rate, width, ch, n = w.getframerate(), w.getsampwidth(), w.getnchannels(), w.getnframes()
+        raw = w.readframes(n)
+    if width == 2:
+        data = np.frombuffer(raw, dtype='<i2').astype(np.float32) / 32768.0
+    elif width == 4:
+        data = np.frombuffer(raw, dtype='<i4').astype(np.float32) / 2147483648.0
+    else:
+        raise ValueError(f"unsupported sample width {width} in {path}")
+    if ch > 1:
+        data = data.reshape(-1, ch)[:, 0].copy()
+    if rate != gpd['sample_rate']:
+        print(f'[WARN] rate={rate}, dtype={data.dtype}, path={path}')
+    return data
+
+
+class AudioBase(object):
+    """Vocabulary + feature constants (data.py:371-382).  dict.pkl is read from `dict_path`
+    (default: ./dict.pkl like the reference, then $ASR_DICT_PKL)."""
+
+    def __init__(self, dict_path=None):
+        path = dict_path or ('dict.pkl' if os.path.exists('dict.pkl') else os.environ.get('ASR_DICT_PKL', 'dict.pkl'))
+        with open(path, 'rb') as f:
+            self.word2int, self.int2word = pickle.load(f)
+        self.ms = MelScale(n_mels=gpd['n_mels'], sr=gpd['sample_rate'], f_max=7600, f_min=80, n_stft=257)
+        self.window = torch.hann_window(int(gpd['window_len'] * gpd['sample_rate']))
+
+
+def feature_consts(ms=None, window=None):
+    """numpy constant tables handed to asr_create (kept alive by the caller)."""
+    if ms is None:
+        ms = MelScale(n_mels=gpd['n_mels'], sr=gpd['sample_rate'], f_max=7600, f_min=80, n_stft=257)
+    if window is None:
+        window = torch.hann_window(int(gpd['window_len'] * gpd['sample_rate']))
+    return {
+        "mel_fb": np.ascontiguousarray(ms.fb.numpy(), dtype=np.float32),
+        "window": np.ascontiguousarray(window.numpy(), dtype=np.float32),
+        "taps": delta_filter_stack(),
+        "preemphasis": float(gpd['preemphasis']),
+    }
+
+
+_default_engine = None
+
+
+def set_default_engine(engine):
+    """The Model whose handle get_log_mel uses (set by Model.load / Model.load_state)."""
+    global _default_engine
+    _default_engine = engine
+
+
+def get_log_mel(training, file_path, ms, window, data_aug=False, engine=None):
+    """data.py:167-280 on the device: WAV path (or float32 array) -> CUDA tensor [L, 720]
+    (un-normalised, like the reference; main.py:37 applies the CMVN).  training / data_aug must
+    be False: dither and augmentation are training-only (data.py:181-200) and out of scope."""
+    if training or data_aug:
+        raise NotImplementedError("training-time dither / augmentation is outside the inference path")
+    eng = engine or _default_engine
+    if eng is None:
+        raise RuntimeError("get_log_mel needs a loaded Model (Model.load) to own the device handle")
+    pcm = fast_read(file_path) if isinstance(file_path, str) else np.asarray(file_path, dtype=np.float32)
+    return eng.features([pcm], normalise=False)[0]

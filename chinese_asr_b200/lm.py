@@ -1,0 +1,98 @@
+"""Second-pass language model with device-resident tables (replaces kenlm at model.py:749-763).
+
+The reference calls kenlm.LanguageModel(lm_path).score(' '.join(chars), bos=True).  KenLM and its
+binary model are not available here, so the B200 path takes a back-off n-gram (order <= 3) in ARPA
+semantics: log10 probabilities, back-off weights, <s> context when bos, </s> appended when eos,
+OOV -> <unk>.  Scoring of the finished hypotheses runs on the GPU (csrc/decoder.cu); this class
+only builds / uploads the tables.  `.score()` is provided for API compatibility and evaluates the
+same tables through the device kernel (asr_lm_score) - there is no host scoring path."""
+import numpy as np
+
+SPACE_ID = 781      # dict.pkl's literal ' ' token: vanishes under str.split()
+UNK = 3
+
+
+def _hash_slot(key, cap):
+    m = (1 << 64) - 1
+    z = (key + 0x9E3779B97F4A7C15) & m
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & m
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & m
+    z = z ^ (z >> 31)
+    return int(z & (cap - 1))
+
+
+def _build_table(items, nvals):
+    cap = 1
+    while cap < 2 * len(items) + 8:
+        cap *= 2
+    keys = np.full(cap, -1, dtype=np.int64)
+    vals = np.zeros((cap, nvals), dtype=np.float32)
+    for k, v in items:
+        s = _hash_slot(k, cap)
+        while keys[s] != -1:
+            s = (s + 1) & (cap - 1)
+        keys[s] = k
+        vals[s] = v
+    return keys, vals
+
+
+class NGramLM:
+    def __init__(self, tables, word2int=None, skip_id=SPACE_ID):
+        """tables: dict with uni_logp[V], uni_bo[V], bi_keys, bi_vals[cap,2], tri_keys, tri_vals."""
+        self.t = {k: np.ascontiguousarray(v) for k, v in tables.items()}
+        self.t["bi_vals"] = self.t["bi_vals"].reshape(-1, 2).astype(np.float32)
+        self.t["tri_vals"] = self.t["tri_vals"].reshape(-1).astype(np.float32)
+        self.vocab = int(self.t["uni_logp"].shape[0])
+        self.word2int = word2int
+        self.skip_id = skip_id
+        self._engine = None
+
+    def tables(self):
+        return self.t
+
+    @classmethod
+    def from_arpa(cls, path, word2int, skip_id=SPACE_ID):
+        """Load an ARPA file (order <= 3) whose words are dict.pkl strings."""
+        V = len(word2int)
+        uni_logp = np.full(V, -99.0, dtype=np.float32)
+        uni_bo = np.zeros(V, dtype=np.float32)
+        bi, tri = [], []
+        order = 0
+        with open(path, encoding='utf-8') as f:
+            for line in f:
+                line = line.rstrip('\n')
+                if line.startswith('\\') and line.endswith('-grams:'):
+                    order = int(line[1])
+                    continue
+                if not line or line.startswith('\\') or line.startswith('ngram '):
+                    continue
+                parts = line.split('\t') if '\t' in line else line.split(' ')
+                if order == 0 or len(parts) < order + 1:
+                    continue
+                lp = float(parts[0])
+                words = parts[1].split(' ') if '\t' in line else parts[1:1 + order]
+                ids = [word2int.get(w, UNK) for w in words]
+                bo = float(parts[-1]) if len(parts) > (2 if '\t' in line else order + 1) else 0.0
+                if order == 1:
+                    uni_logp[ids[0]] = lp
+                    uni_bo[ids[0]] = bo
+                elif order == 2:
+                    bi.append((ids[0] * V + ids[1], (lp, bo)))
+                elif order == 3:
+                    tri.append(((ids[0] * V + ids[1]) * V + ids[2], (lp,)))
+        bk, bv = _build_table(bi, 2)
+        tk, tv = _build_table(tri, 1)
+        return cls({"uni_logp": uni_logp, "uni_bo": uni_bo, "bi_keys": bk, "bi_vals": bv,
+                    "tri_keys": tk, "tri_vals": tv.reshape(-1)}, word2int, skip_id)
+
+    def bind(self, engine):
+        self._engine = engine
+
+    def score(self, sentence, bos=True, eos=True):
+        """kenlm-style total log10 probability, evaluated by the device kernel."""
+        if not (bos and eos):
+            raise NotImplementedError("the device scorer implements bos=True, eos=True (model.py:755)")
+        if self._engine is None or self.word2int is None:
+            raise RuntimeError("NGramLM.score needs bind(model) and word2int")
+        ids = [self.word2int.get(w, UNK) for w in sentence.split()]
+        return float(self._engine.lm_score([ids])[0])

@@ -1,0 +1,187 @@
+/*
+ * asr_b200.h - C ABI of the B200-native (sm_100a) inference hot path of shawnthu/chinese-asr.
+ *
+ * The reference has no FFI/plugin interface (it is pure Python); the drop-in boundary is a set
+ * of Python signatures.  Every entry point below names the reference
+ * call it replaces (file:line into the reference tree).  The Python mirror of the reference
+ * interface (chinese_asr_b200/model.py, data.py, main.py) binds exactly these symbols with
+ * ctypes; torch tensors are used only as buffer carriers (their data_ptr() is passed here).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative asr_status otherwise; nothing throws
+ *     across the ABI.  asr_last_error() gives a human-readable message for the last failure
+ *     on the calling thread.
+ *   - "d_" pointers are device pointers owned by the caller, "h_" pointers are host pointers.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  All work is
+ *     enqueued on it; functions that return host-side results synchronise that stream.
+ *   - one handle per GPU (created on the current device), not shared between threads.
+ *   - utterances are identified by their position in the caller's batch ("original order");
+ *     the library sorts by length internally (encoder.py:47) and un-sorts every output.
+ */
+#ifndef ASR_B200_H_
+#define ASR_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct asr_handle asr_handle;
+
+enum asr_status {
+    ASR_OK = 0,
+    ASR_ERR_ARG = -1,      /* bad argument (shape, NULL, k not in 1..16, ...)               */
+    ASR_ERR_CUDA = -2,     /* a CUDA call failed                                            */
+    ASR_ERR_STATE = -3,    /* call order violated (decode before encode, LM not loaded ...) */
+    ASR_ERR_CAPACITY = -4  /* batch exceeds what asr_reserve() provisioned                   */
+};
+
+/* architecture constants of the path (gpd.py:4-133; frozen at import time in the reference) */
+#define ASR_FEAT_DIM 720
+#define ASR_N_MELS 80
+#define ASR_ENC_OUT 512
+#define ASR_ATT 128
+#define ASR_DEC_H 512
+#define ASR_EMB 256
+#define ASR_VOCAB 5004
+#define ASR_MAX_BEAM 16
+
+/* Weights in the reference checkpoint layout (Model.load, model.py:357-369; tensor names in
+ * SURVEY.md section 8b).  All host pointers, float32, row-major, copied during asr_create.
+ * enc_*[layer*2 + dir], dir 0 = forward, 1 = reverse. */
+typedef struct asr_weights {
+    const float* enc_w_ih[8];   /* [1024, 720] for layer 0, [1024, 512] otherwise */
+    const float* enc_w_hh[8];   /* [1024, 256]                                     */
+    const float* enc_b_ih[8];   /* [1024]                                          */
+    const float* enc_b_hh[8];   /* [1024]                                          */
+    const float* embedding;     /* [5004, 256]   decoder.embedding.weight          */
+    const float* dec_w_ih;      /* [2048, 768]   cell.cell.0.weight_ih             */
+    const float* dec_w_hh;      /* [2048, 512]   cell.cell.0.weight_hh             */
+    const float* dec_b_ih;      /* [2048]                                          */
+    const float* dec_b_hh;      /* [2048]                                          */
+    const float* proj_w;        /* [5004, 1024]  proj_linear.weight                */
+    const float* proj_b;        /* [5004]                                          */
+    const float* att_w_enc;     /* [512, 128]    attn_mechanism.W_enc  ([in,out])  */
+    const float* att_b;         /* [128]                                           */
+    const float* att_w_hidden;  /* [512, 128]    attn_mechanism.W_hidden ([in,out])*/
+    const float* att_v;         /* [128]                                           */
+} asr_weights;
+
+/* Feature constants computed by the host mirror of AudioBase (data.py:371-382). */
+typedef struct asr_feature_consts {
+    const float* mel_fb;   /* [257, 80] triangular filterbank (data.py:21-57)   */
+    const float* window;   /* [400] periodic Hann (data.py:381-382)             */
+    const float* taps;     /* [3, 9] identity / delta / delta-delta taps (data.py:138-149) */
+    float preemphasis;     /* gpd['preemphasis'] = 0.97                         */
+} asr_feature_consts;
+
+const char* asr_last_error(void);
+int asr_version(void);
+
+/* Model() + Model.load()  (model.py:18-82, 357-369) and AudioBase() (data.py:371-382). */
+int asr_create(asr_handle** out, const asr_weights* w, const asr_feature_consts* fc);
+int asr_destroy(asr_handle* h);
+
+/* Provision device workspaces: at most max_utts utterances per batch, max_rows encoder frames
+ * summed over the batch, beam width <= max_beam, max_samples PCM samples per batch (0 if the
+ * feature kernels are not used), decode length <= max_len. */
+int asr_reserve(asr_handle* h, int max_utts, int64_t max_rows, int max_beam, int64_t max_samples,
+                int max_len);
+
+/* get_log_mel() + CMVN  (data.py:167-280, main.py:37).
+ * d_pcm: concatenated float32 waveforms; h_pcm_off[B+1]: sample offsets of each utterance.
+ * d_feats: [sum L_u, 720], utterance-major in original order (what the reference returns per
+ * utterance, concatenated).  h_L[B] receives L_u = T_u / 3.  normalise=0 skips the CMVN. */
+int asr_features(asr_handle* h, const float* d_pcm, const int64_t* h_pcm_off, int B,
+                 float* d_feats, int32_t* h_L, int normalise, void* stream);
+/* frame count helper: L for an utterance of n samples */
+int asr_num_frames(int64_t n_samples);
+
+/* RNNEncoder.forward + get_mask_for_softmax + get_initial_state + compute_key_value
+ * (encoder.py:36-81, util.py:131-142, decoder.py:56-59, attention.py:67-78).
+ * d_feats as produced by asr_features (utterance-major, original order).  The encoder memory,
+ * attention keys and the decoder initial state stay inside the handle for the decode calls. */
+int asr_encode(asr_handle* h, const float* d_feats, const int32_t* h_L, int B, void* stream);
+
+/* Export the encoder results in the reference's layouts (tests / debugging):
+ * d_enc_out [Lmax, B, 512] zero padded, d_keys [Lmax, B, 128] (padded rows = b_attn, as
+ * attention.py:77 produces on zero rows), d_h / d_c [B, 512].  Any pointer may be NULL. */
+int asr_export_encoder(asr_handle* h, float* d_enc_out, float* d_keys, float* d_h, float* d_c,
+                       void* stream);
+/* Per-layer residual-stream output of layer `layer` (0..3): [Lmax, B, 512] zero padded. */
+int asr_encode_layers(asr_handle* h, const float* d_feats, const int32_t* h_L, int B,
+                      int upto_layer, float* d_layer_out, void* stream);
+
+/* Model.eval_one_batch_with_greedy (model.py:503-602) after asr_encode.
+ * h_tokens [B, max_len] (argmax token of every executed step), h_len[B] = text_len,
+ * h_score_sum[B] = accumulated log-prob, h_finished[B]; *h_steps = number of executed steps.
+ * d_align (optional, may be NULL): [max_len, Lmax, B] alignments (EvalOutput.alignment).
+ * d_logits (optional): [max_len, B, 5004] raw logits of each step (parity tests). */
+int asr_decode_greedy(asr_handle* h, int max_len, int32_t* h_tokens, int32_t* h_len,
+                      float* h_score_sum, int32_t* h_finished, int32_t* h_steps, float* d_align,
+                      float* d_logits, void* stream);
+
+/* Second-pass LM tables (builder-defined back-off trigram with KenLM scoring semantics; the
+ * reference calls kenlm.LanguageModel.score at model.py:755).  Host pointers, copied. */
+typedef struct asr_lm_tables {
+    const float* uni_logp;    /* [vocab]                       */
+    const float* uni_bo;      /* [vocab]                       */
+    const int64_t* bi_keys;   /* [bi_cap]  a*V+b or -1         */
+    const float* bi_vals;     /* [bi_cap, 2] logp, backoff     */
+    int64_t bi_cap;           /* power of two                  */
+    const int64_t* tri_keys;  /* [tri_cap] (a*V+b)*V+c or -1   */
+    const float* tri_vals;    /* [tri_cap] logp                */
+    int64_t tri_cap;          /* power of two                  */
+    int32_t vocab;
+    int32_t skip_id;          /* token that vanishes under str.split(): id 781 ' ' */
+} asr_lm_tables;
+int asr_set_lm(asr_handle* h, const asr_lm_tables* t);
+/* kenlm-style score of token-id sequences on the device (tests): h_ids [n, max_n], h_n[n] */
+int asr_lm_score(asr_handle* h, const int32_t* h_ids, const int32_t* h_n, int n, int max_n,
+                 float* h_scores, void* stream);
+
+/* Model.eval_one_batch_with_beam (model.py:604-987) after asr_encode.
+ * k = bmsz (1..16).  second_pass != 0 requires asr_set_lm.  Results on the host:
+ * h_tokens [B, max_len], h_len[B], h_score[B] (the reference's EvalOutput.score),
+ * h_info[4] = {steps executed, stop step or -1, #utterances that took the un-finished
+ * fallback, #finished hypotheses}. */
+int asr_decode_beam(asr_handle* h, int k, int max_len, float temperature, int second_pass,
+                    double lm_weight, double length_weight, int32_t* h_tokens, int32_t* h_len,
+                    float* h_score, int32_t* h_info, void* stream);
+
+/* Per-step internals of the last asr_decode_beam call (parity tests; original utterance order):
+ * h_cand_score/h_cand_beam/h_cand_tok [steps, B, 2k] (model.py:863-867),
+ * h_backptr/h_active_tok [steps, B, k] (model.py:907-909),
+ * h_fin_score [steps, B, k] (score of the EOS candidates among the top k, NaN where none).
+ * Any pointer may be NULL. */
+int asr_beam_trace(asr_handle* h, float* h_cand_score, int32_t* h_cand_beam, int32_t* h_cand_tok,
+                   int32_t* h_backptr, int32_t* h_active_tok, float* h_fin_score);
+
+/* Whole path for one batch, host buffers in / host buffers out (parse() in main.py:27-65 for a
+ * batch): H2D copy of the PCM, features, encoder, greedy (k = 0) or beam decode, D2H of the
+ * hypotheses.  h_pcm should be pinned for the copy to be asynchronous. */
+int asr_transcribe(asr_handle* h, const float* h_pcm, const int64_t* h_pcm_off, int B, int k,
+                   int max_len, float temperature, int second_pass, double lm_weight,
+                   double length_weight, int32_t* h_tokens, int32_t* h_len, float* h_score,
+                   void* stream);
+/* Same, PCM already resident on the device (d_pcm); used for the HBM-resident throughput. */
+int asr_transcribe_device(asr_handle* h, const float* d_pcm, const int64_t* h_pcm_off, int B,
+                          int k, int max_len, float temperature, int second_pass, double lm_weight,
+                          double length_weight, int32_t* h_tokens, int32_t* h_len, float* h_score,
+                          void* stream);
+
+/* Number of kernels this library launched since the handle was created / last reset. */
+int64_t asr_launch_count(asr_handle* h, int reset);
+
+/* Stage timing with CUDA events on `stream` for the next transcribe/decode call:
+ * h_ms[8] = {features, encoder input GEMMs, encoder recurrence, keys+init, decoder cell,
+ * attention, vocab projection, top-k + bookkeeping + finalise}.  enable=1 records events
+ * around every stage (adds event overhead); asr_stage_times reads them after a sync. */
+int asr_stage_timing(asr_handle* h, int enable);
+int asr_stage_times(asr_handle* h, float* h_ms, int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ASR_B200_H_ */

@@ -1,0 +1,262 @@
+"""Parity checks of the CUDA path (through the C ABI / Python mirror) against the oracle and the
+committed reference goldens.  Each check returns a dict of metrics; tests/test_gpu_parity.py asserts
+on them and tools/gpu_diag.py prints them all (first-run diagnostics)."""
+import os
+import pickle
+
+import numpy as np
+import torch
+
+from oracle import asr_oracle as O
+from tests.cases import CASES, case_inputs, case_weights, load_golden
+
+GOLD_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+_vocab = None
+_models = {}
+
+
+def vocab():
+    global _vocab
+    if _vocab is None:
+        with open(os.path.join(GOLD_DIR, "dict.pkl"), "rb") as f:
+            _vocab = pickle.load(f)
+    return _vocab
+
+
+def get_model(weights_key, weights):
+    """One engine per distinct weight set (handle creation uploads ~64 MB)."""
+    from chinese_asr_b200.model import Model
+    from chinese_asr_b200.gpd import gpd
+    gpd['verbose'] = False
+    if weights_key not in _models:
+        m = Model()
+        m.load_state(weights)
+        _models[weights_key] = m
+    return _models[weights_key]
+
+
+def wkey(cs):
+    return (cs["wseed"], cs["variant"], cs.get("eos_bias"))
+
+
+def maxabs(a, b):
+    return float((torch.as_tensor(a).float().cpu() - torch.as_tensor(b).float().cpu()).abs().max())
+
+
+# ---------------------------------------------------------------------------------------------
+def check_features():
+    g = load_golden()
+    w = O.make_weights(1234, "plain")
+    m = get_model((1234, "plain", None), w)
+    res = {}
+    pcms = {"feat_2s": O.synth_pcm(11, 32000), "feat_5s": O.synth_pcm(12, 80000),
+            "feat_odd": O.synth_pcm(13, 20011)}
+    names = list(pcms)
+    raw = m.features([pcms[n] for n in names], normalise=False)
+    nrm = m.features([pcms[n] for n in names], normalise=True)
+    for n, fr, fn in zip(names, raw, nrm):
+        rows = g[n + "_rows"]
+        res[n + "_L_ok"] = int(fr.size(0) == int(g[n + "_L"]))
+        res[n + "_raw_vs_ref"] = maxabs(fr[rows], g[n + "_raw"])
+        res[n + "_cmvn_vs_ref"] = maxabs(fn[rows], g[n + "_cmvn"])
+        res[n + "_raw_vs_oracle"] = maxabs(fr, O.features(pcms[n], normalise=False))
+        res[n + "_cmvn_vs_oracle"] = maxabs(fn, O.features(pcms[n], normalise=True))
+    z = m.features([np.zeros(8000, dtype=np.float32)], normalise=False)[0]
+    res["zero_raw_vs_ref"] = maxabs(z, g["feat_zero_raw"])
+    return res
+
+
+def check_encoder(cname):
+    g = load_golden()
+    cs = CASES[cname]
+    weights = case_weights(cs)
+    m = get_model(wkey(cs), weights)
+    pcms, feats, lens = case_inputs(cs)
+    res = {}
+    o_out, _, (o_h, o_c), o_layers = O.encoder_forward(weights, feats, lens, return_layers=True)
+    for layer in range(4):
+        y = m.encode_layer(feats, lens, layer)
+        res[f"layer{layer}_vs_oracle"] = maxabs(y, o_layers[layer])
+    enc, keys, h, c = m.encode_export(feats, lens)
+    res["enc_vs_oracle"] = maxabs(enc, o_out)
+    res["enc_vs_ref"] = maxabs(enc, g[cname + "_enc_out"])
+    res["h_vs_ref"] = maxabs(h, g[cname + "_enc_h"])
+    res["c_vs_ref"] = maxabs(c, g[cname + "_enc_c"])
+    res["keys_vs_ref"] = maxabs(keys, g[cname + "_keys"])
+    # padded rows must be exactly zero (pad_packed_sequence, encoder.py:63-64)
+    pad_ok = 1
+    for b, n in enumerate(lens.tolist()):
+        if n < enc.size(0) and float(enc[n:, b].abs().max()) != 0.0:
+            pad_ok = 0
+    res["pad_exact_zero"] = pad_ok
+    return res
+
+
+def check_encoder_kat():
+    """The reference's only reproducible known answer (encoder.py:636-652): all-ones weights and
+    inputs, lens [10, 8, 23, 14] -> out.sum()=110345.43, h.sum()=2048, c.sum()=28160."""
+    g = load_golden()
+    w = O.make_weights(1, "plain")
+    for d in (w["encoder_state_dict"],):
+        for k in d:
+            d[k] = torch.ones_like(d[k])
+    m = get_model(("ones",), w)
+    lens = torch.tensor([10, 8, 23, 14])
+    feats = [torch.ones(n, 720) for n in lens.tolist()]
+    enc, _, h, c = m.encode_export(feats, lens)
+    want = g["kat_rnn_sums"]
+    return {"out_sum": float(enc.double().sum()), "h_sum": float(h.double().sum()),
+            "c_sum": float(c.double().sum()), "want_out": float(want[0]), "want_h": float(want[1]),
+            "want_c": float(want[2])}
+
+
+def check_greedy(cname):
+    g = load_golden()
+    cs = CASES[cname]
+    weights = case_weights(cs)
+    m = get_model(wkey(cs), weights)
+    _, i2w = vocab()
+    pcms, feats, lens = case_inputs(cs)
+    tr = {}
+    o = O.greedy_decode(weights, feats, lens, i2w, trace=tr)
+    out, logits, toks = m.eval_one_batch_with_greedy(m.device, feats, lens, i2w, None, return_logits=True)
+    res = {"steps": int(logits.size(0)), "oracle_steps": o["steps"]}
+    res["text_vs_ref"] = int(list(out.pred_text) == list(g[cname + "_text"]))
+    res["text_vs_oracle"] = int(list(out.pred_text) == o["pred_text"])
+    res["len_vs_ref"] = int(out.text_len.tolist() == g[cname + "_text_len"].tolist())
+    ref_s = g[cname + "_score"]
+    res["score_rel_vs_ref"] = float(max(abs(a - b) / max(1e-6, abs(b)) for a, b in zip(out.score, ref_s)))
+    n = min(logits.size(0), len(tr["logit"]))
+    res["logit0_vs_oracle"] = maxabs(logits[0], tr["logit"][0])
+    # later steps only comparable while the fed-back tokens agree
+    res["logit_all_vs_oracle"] = max(maxabs(logits[s], tr["logit"][s]) for s in range(n))
+    res["align0_vs_ref"] = maxabs(out.alignment[0], g[cname + "_align0"])
+    top2 = torch.stack(tr["logit"]).topk(2, dim=2)[0]
+    res["oracle_min_margin"] = float((top2[..., 0] - top2[..., 1]).min())
+    return res
+
+
+def check_beam(cname):
+    from chinese_asr_b200.gpd import gpd
+    from chinese_asr_b200.lm import NGramLM
+    g = load_golden()
+    cs = CASES[cname]
+    weights = case_weights(cs)
+    m = get_model(wkey(cs), weights)
+    w2i, i2w = vocab()
+    pcms, feats, lens = case_inputs(cs)
+    k = cs["bw"]
+    lm_o = O.NGramLM(seed=cs["lm"], word2int=w2i) if cs.get("lm") else None
+    lm_d = NGramLM(lm_o.tables(), w2i) if lm_o is not None else None
+    tr = {}
+    o = O.beam_decode(weights, k, feats, lens, i2w, second_pass=lm_o is not None, lm_model=lm_o,
+                      lm_weight=cs.get("lm_weight", 0.0), length_weight=cs.get("length_weight", 0.0),
+                      temperature=cs.get("temperature", 1), trace=tr)
+    gpd['temperature'] = cs.get("temperature", 1)
+    try:
+        out = m.eval_one_batch_with_beam(m.device, k, feats, lens, None, i2w,
+                                         second_pass=lm_d is not None, lm_model=lm_d,
+                                         lm_weight=cs.get("lm_weight", 0.0),
+                                         length_weight=cs.get("length_weight", 0.0))
+    finally:
+        gpd['temperature'] = 1.
+    info = m.last_beam_info
+    t = m.beam_trace(len(feats), k)
+    res = {"steps": info["steps"], "oracle_steps": o["steps"], "stopped_at": info["stopped_at"],
+           "oracle_stopped_at": -1 if o["stopped_at"] is None else o["stopped_at"],
+           "fallback": info["fallback"], "oracle_fallback": len(o["fallback"]),
+           "finished": info["finished"], "oracle_finished": sum(len(v) for v in o["nbest"].values()),
+           "oracle_min_margin": min(tr["min_margin"])}
+    res["text_vs_ref"] = int(list(out.pred_text) == list(g[cname + "_text"]))
+    res["tokens_vs_oracle"] = int(info["tokens"] == o["tokens"])
+    ref_s = g[cname + "_score"]
+    res["score_rel_vs_ref"] = float(max(abs(a - b) / max(1e-6, abs(b)) for a, b in zip(out.score, ref_s)))
+    # per-step internals against the reference's recorded torch.topk outputs
+    ns = min(info["steps"], g[cname + "_cand_scores"].shape[0])
+    res["cand_scores_vs_ref"] = float(np.abs(t["cand_scores"][:ns] - g[cname + "_cand_scores"][:ns]).max())
+    flat = t["cand_beams"][:ns].astype(np.int64) * O.VOCAB + t["cand_tokens"][:ns]
+    res["cand_index_mismatch_vs_ref"] = int((flat != g[cname + "_cand_index"][:ns]).sum())
+    nb = len(tr.get("backptr", []))
+    if nb:
+        bp = torch.stack(tr["backptr"]).numpy()
+        at = torch.stack(tr["active_tokens"]).numpy()
+        res["backptr_mismatch"] = int((t["backptr"][:nb] != bp).sum())
+        res["active_tok_mismatch"] = int((t["active_tokens"][:nb] != at).sum())
+        act_ref = g[cname + "_active"]
+        if act_ref.shape[0]:
+            # reference active_hypos index into the 2k candidates -> beams via its cand_index
+            na = min(nb, act_ref.shape[0])
+            ref_beam = np.take_along_axis(g[cname + "_cand_index"][:na] // O.VOCAB, act_ref[:na], axis=2)
+            res["backptr_mismatch_vs_ref"] = int((t["backptr"][:na] != ref_beam).sum())
+    return res
+
+
+def check_lm():
+    from chinese_asr_b200.lm import NGramLM
+    w2i, i2w = vocab()
+    lm_o = O.NGramLM(seed=7, word2int=w2i)
+    m = get_model((1234, "plain", None), O.make_weights(1234, "plain"))
+    lm_d = NGramLM(lm_o.tables(), w2i)
+    m.set_lm(lm_d)
+    rng = np.random.default_rng(5)
+    seqs = [[]]
+    for _ in range(300):
+        n = int(rng.integers(0, 40))
+        hot = rng.random() < 0.6
+        s = rng.integers(0, 48 if hot else O.VOCAB, n).tolist()
+        if n and rng.random() < 0.3:
+            s[int(rng.integers(0, n))] = O.SPACE_ID
+        seqs.append(s)
+    dev = m.lm_score(seqs)
+    ref = np.array([lm_o.score_ids(s) for s in seqs], dtype=np.float32)
+    sent = " ".join(i2w[t] for t in seqs[5])
+    return {"n": len(seqs), "mismatch": int((dev != ref).sum()), "maxabs": float(np.abs(dev - ref).max()),
+            "string_api": float(abs(lm_d.score(sent) - lm_o.score(sent)))}
+
+
+def check_fused(cname="beam4"):
+    """asr_transcribe (PCM in, hypotheses out, one call) == staged features/encode/decode."""
+    cs = CASES[cname]
+    weights = case_weights(cs)
+    m = get_model(wkey(cs), weights)
+    _, i2w = vocab()
+    pcms, feats, lens = case_inputs(cs)
+    dfeats = m.features(pcms, normalise=True)
+    staged = m.eval_one_batch_with_beam(m.device, cs["bw"], dfeats, lens, None, i2w, second_pass=False)
+    off = np.zeros(len(pcms) + 1, dtype=np.int64)
+    off[1:] = np.cumsum([len(p) for p in pcms])
+    pin = torch.from_numpy(np.concatenate(pcms)).pin_memory()
+    tok, ln, sc, texts = m.transcribe(pin, off, bw=cs["bw"], int2word=i2w)
+    dev = torch.from_numpy(np.concatenate(pcms)).cuda()
+    tok2, ln2, sc2, texts2 = m.transcribe(dev, off, bw=cs["bw"], int2word=i2w, resident=True)
+    tokg, lng, scg, textsg = m.transcribe(pin, off, bw=None, int2word=i2w)
+    greedy = m.eval_one_batch_with_greedy(m.device, dfeats, lens, i2w, None)
+    return {"fused_eq_staged": int(texts == list(staged.pred_text)),
+            "resident_eq_host": int(texts2 == texts and np.array_equal(sc, sc2)),
+            "score_eq": int(np.allclose(sc, np.array(staged.score, dtype=np.float32), rtol=0, atol=0)),
+            "greedy_fused_eq_staged": int(textsg == list(greedy.pred_text))}
+
+
+def check_batch_invariance(B=12, k=4, seconds=3.0, seed=900):
+    """Size-independent property: an utterance's hypothesis does not depend on what else is in
+    the batch (no cross-utterance reduction anywhere on the path)."""
+    weights = O.make_weights(1234, "sharp", eos_bias=8.0)
+    m = get_model((1234, "sharp", 8.0), weights)
+    _, i2w = vocab()
+    rng = np.random.default_rng(seed)
+    ns = [int(16000 * seconds * (0.5 + rng.random())) for _ in range(B)]
+    pcms = [O.synth_pcm(seed + i, n) for i, n in enumerate(ns)]
+    off = np.zeros(B + 1, dtype=np.int64)
+    off[1:] = np.cumsum(ns)
+    tok, ln, sc, texts = m.transcribe(np.concatenate(pcms), off, bw=k, int2word=i2w)
+    same = 0
+    for i in (0, B // 2, B - 1):
+        o1 = np.array([0, ns[i]], dtype=np.int64)
+        t1, l1, s1, x1 = m.transcribe(pcms[i], o1, bw=k, int2word=i2w)
+        same += int(x1[0] == texts[i] and abs(float(s1[0]) - float(sc[i])) <= 1e-4 * max(1.0, abs(float(sc[i]))))
+    perm = rng.permutation(B)
+    offp = np.zeros(B + 1, dtype=np.int64)
+    offp[1:] = np.cumsum([ns[j] for j in perm])
+    tp, lp, sp, xp = m.transcribe(np.concatenate([pcms[j] for j in perm]), offp, bw=k, int2word=i2w)
+    perm_ok = int(all(xp[i] == texts[j] for i, j in enumerate(perm)))
+    return {"single_eq_batch": same, "of": 3, "perm_invariant": perm_ok}
