@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py - beam=8 utterances/s of the chinese-asr inference hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # CPU port of the reference path
+
+A "step" is one pass of the whole hot path (log-mel features -> BiLSTM encoder -> bw=8 beam decode,
+40 steps -> finalisation) over one batch of synthetic 10 s / 16 kHz utterances per GPU.  Workload =
+BASELINE.json configs[4] (the one the metric is quoted on): 4096 utterances sharded over 8 GPUs =
+512 utterances per GPU per step; per-GPU work is fixed as N grows (weak scaling), utterances are
+independent so there is no data-path collective, only the final gather of hypotheses.
+Prints ONE JSON line (rank 0)."""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SECONDS = 10.0
+SR = 16000
+MAX_LEN = 40
+V = 5004
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--batch", type=int, default=512, help="utterances per GPU per step")
+    ap.add_argument("--bw", type=int, default=8)
+    ap.add_argument("--seconds", type=float, default=SECONDS)
+    ap.add_argument("--cpu-sample", type=int, default=16, help="utterances in the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def synth_batch(B, n, seed):
+    rng = np.random.default_rng(seed)
+    return (0.1 * rng.standard_normal((B, n))).astype(np.float32)
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for nme, val in zip(names, r[3:7]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_port_rate(n_utts, bw, seconds, threads=None, reps=1, warm=0):
+    """The oracle (CPU port of the reference path, same torch CPU library ops the reference calls)
+    on a bounded sample: features + encoder + beam decode, batch = n_utts.  Returns utt/s."""
+    import torch
+    from oracle import asr_oracle as O
+    if threads:
+        torch.set_num_threads(threads)
+    weights = O.make_weights(1234, "plain")
+    n = int(seconds * SR)
+    pcm = synth_batch(n_utts, n, 4242)
+    best = None
+    for it in range(warm + reps):
+        t0 = time.perf_counter()
+        feats = [O.features(pcm[i]) for i in range(n_utts)]
+        lens = torch.tensor([f.size(0) for f in feats])
+        O.beam_decode(weights, bw, feats, lens, None)
+        dt = time.perf_counter() - t0
+        if it >= warm:
+            best = dt if best is None else min(best, dt)
+    return n_utts / best, best, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    cores = os.cpu_count()
+    n_utts = args.cpu_sample
+    times = []
+    for it in range(args.warmup + args.steps):
+        rate, dt, threads = cpu_port_rate(n_utts, args.bw, args.seconds)
+        if it >= args.warmup:
+            times.append(dt)
+    ms = 1000.0 * float(np.mean(times))
+    value = n_utts / (ms / 1000.0)
+    sample = f"{n_utts} utterances x {args.seconds:g} s per step (one batch), features+encoder+beam bw={args.bw}"
+    line = {
+        "impl": "reference", "metric": "utterances_per_sec_beam8", "value": value, "unit": "utt/s",
+        "rtfx": value * args.seconds, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"bw={args.bw} beam decode of {args.seconds:g} s 16 kHz utterances "
+                               f"(BASELINE.json configs[4]); CPU arm runs a bounded sample per step",
+                   "beam": args.bw, "utt_seconds": args.seconds, "max_len": MAX_LEN},
+        "cpu_baseline": {"value": value, "unit": "utt/s", "cores": threads, "kind": "port", "sample": sample,
+                         "host_cpus": cores},
+        "e2e": {"value": value, "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+def decoder_step_bytes(B, k, L):
+    """algorithmic HBM bytes of one decoder step (fp32 storage)."""
+    w_dec = 4 * (2625536 + 65536 + 128 + 5129100)
+    return w_dec + B * L * 2560 + B * k * 12288 + B * k * 1024 + 2 * 4 * B * k * V
+
+
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+    from oracle import asr_oracle as O          # weights / synthetic inputs only (not on the timed path)
+    from chinese_asr_b200.model import Model
+    from chinese_asr_b200.gpd import gpd
+    from chinese_asr_b200 import parallel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    gpd["verbose"] = False
+    gpd["temperature"] = 1.0
+    B, k = args.batch, args.bw
+    n = int(args.seconds * SR)
+    L = (1 + (n - 1 - 512) // 160) // 3
+
+    m = Model()
+    m.load_state(O.make_weights(1234, "plain"))
+    m.reserve(B, B * L, k, B * n, MAX_LEN)
+    off = (np.arange(B + 1, dtype=np.int64) * n)
+    host = torch.from_numpy(synth_batch(B, n, 1000 + rank).reshape(-1)).pin_memory()
+    resident = host.to(dev)
+    total = B * world
+
+    def step(e2e):
+        if e2e:
+            tok, ln, sc = m.transcribe(host, off, bw=k)
+        else:
+            tok, ln, sc = m.transcribe(resident, off, bw=k, resident=True)
+        if world > 1:   # the one collective of the path: gather the hypotheses
+            rec = parallel.pack_records(np.arange(B) + rank * B, tok, ln, sc, MAX_LEN)
+            tok, ln, sc = parallel.gather_hypotheses(rec, total, MAX_LEN, device=dev)
+        return tok, ln, sc
+
+    def timed(e2e, steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(steps):
+            step(e2e)
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            dist.barrier()
+        return float(ms.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step(False)
+    step(True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    m.launch_count(reset=True)
+    ms_dev = timed(False, args.steps)
+    launches = m.launch_count(reset=True)
+    ms_e2e = timed(True, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # instrumented repeat of the same step: per-stage CUDA-event durations on the launch stream
+    m.stage_timing(True)
+    step(False)
+    stages = m.stage_times()
+    m.stage_timing(False)
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    ms_step = ms_dev / args.steps
+    value = total / (ms_step / 1000.0)
+    e2e_val = total / (ms_e2e / args.steps / 1000.0)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    tf_peak = float(peaks.get("bf16_tflops_sustained", 1590.0))
+    peak_src = "measured" if peaks else "fallback"
+
+    # roofline of the dominant stage (kernel group), from the instrumented step
+    dom = max(stages, key=stages.get)
+    R = B * k
+    flops = {
+        "enc_input_gemm": 2.0 * B * L * 2048 * (720 + 3 * 512),
+        "enc_recurrence": 2.0 * B * L * 4 * 2 * 1024 * 256,
+        "dec_cell": 2.0 * R * 2048 * 1280 * MAX_LEN,
+        "vocab_proj": 2.0 * R * V * 1024 * MAX_LEN,
+        "attn_keys": 2.0 * B * L * 512 * 128,
+    }
+    nlaunch = {"enc_input_gemm": 4, "enc_recurrence": 4, "dec_cell": MAX_LEN, "vocab_proj": MAX_LEN,
+               "attn_keys": 1, "attention": MAX_LEN, "topk_bookkeep": 2 * MAX_LEN + 1, "features": 2}
+    if dom in flops:
+        ach = flops[dom] / (stages[dom] / 1000.0) / 1e12
+        roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s",
+                "frac": ach / tf_peak, "traffic": None, "peak_source": peak_src + " (cuBLAS bf16, sustained)",
+                "ms_per_launch": stages[dom] / nlaunch[dom], "launches_per_step": nlaunch[dom]}
+    else:
+        if dom == "attention":
+            byts = MAX_LEN * (B * L * 2560 + R * 3 * 2048 + 4 * (65536 + 128))
+        elif dom == "features":
+            byts = B * (4 * n + 4 * 720 * L + 2 * 4 * 80 * 3 * L)
+        else:
+            byts = MAX_LEN * (2 * 4 * R * V)
+        ach = byts / (stages[dom] / 1000.0) / 1e9
+        roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "ms_per_launch": stages[dom] / nlaunch[dom], "launches_per_step": nlaunch[dom]}
+    # the north-star group: one decoder step (cell + attention + projection + top-k) vs HBM roofline
+    dec_ms = (stages["dec_cell"] + stages["attention"] + stages["vocab_proj"] + stages["topk_bookkeep"]) / MAX_LEN
+    dec_bytes = decoder_step_bytes(B, k, L)
+    dec_roof = {"ms_per_decoder_step": dec_ms, "algorithmic_bytes": dec_bytes,
+                "achieved_gbs": dec_bytes / (dec_ms / 1000.0) / 1e9,
+                "frac_of_hbm_peak": dec_bytes / (dec_ms / 1000.0) / 1e9 / hbm_peak}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        rate, dt, threads = cpu_port_rate(args.cpu_sample, k, args.seconds)
+        cpu = {"value": rate, "unit": "utt/s", "cores": threads, "kind": "port", "host_cpus": os.cpu_count(),
+               "sample": f"{args.cpu_sample} utterances x {args.seconds:g} s, one batch, features+encoder+beam "
+                         f"bw={k}, {dt:.1f} s wall"}
+    line = {
+        "metric": "utterances_per_sec_beam8", "value": value, "unit": "utt/s", "rtfx": value * args.seconds,
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"bw={k} beam decode of {args.seconds:g} s 16 kHz utterances, {B} per GPU per step "
+                               f"(BASELINE.json configs[4]: 4096 utterances over 8 GPUs)",
+                   "beam": k, "utts_per_gpu_per_step": B, "utt_seconds": args.seconds, "max_len": MAX_LEN,
+                   "enc_frames_per_utt": L, "weights": "random-init (reference initialisers), fp32",
+                   "l2_policy": "inputs larger than L2 (PCM %.0f MB, gate pre-activations %.0f MB per step)"
+                                % (B * n * 4 / 1e6, B * L * 8192 / 1e6)},
+        "e2e": {"value": e2e_val, "unit": "utt/s", "rtfx": e2e_val * args.seconds,
+                "h2d_bytes_per_step": int(B * n * 4 + (B + 1) * 16 + 3 * B * L * 4),
+                "d2h_bytes_per_step": int(B * (MAX_LEN + 2) * 4 + 16),
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roof,
+        "decoder_step_roofline": dec_roof,
+        "stage_ms": stages,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -123,6 +123,25 @@ static int prepare_batch(asr_handle* h, const int32_t* h_L, int B, cudaStream_t 
     return ASR_OK;
 }
 
+// GEMM dispatch: CUDA-core fp32 (mode 0) or tcgen05 3xTF32 with a fused gather + hi/lo split of
+// the A operand (mode 1).  Both produce fp32-faithful results; mode 1 runs on the tensor cores.
+static int gemm(asr_handle* h, const AOperand& A, const float* W, const float* W_hi, const float* W_lo,
+                int M, int N, int K, const GemmEpilogue& epi, cudaStream_t st) {
+    if (h->gemm_mode == 1 && W_hi && W_lo && h->ws.a_hi) {
+        ASR_TRY(split_operand(A, M, K, h->ws.a_hi, h->ws.a_lo, epi.stop_flag, st, &h->launches));
+        return launch_gemm_tc(h->ws.a_hi, h->ws.a_lo, W_hi, W_lo, M, N, K, epi, st, &h->launches);
+    }
+    return launch_gemm(A, W, M, N, K, epi, st, &h->launches);
+}
+
+static int split_weight(asr_handle* h, const float* w, int N, int K, float** hi, float** lo) {
+    ASR_TRY(dev_alloc_t(h->weight_allocs, hi, (size_t)N * K));
+    ASR_TRY(dev_alloc_t(h->weight_allocs, lo, (size_t)N * K));
+    ASR_TRY(split_operand(plain_a(w, K, K), N, K, *hi, *lo, nullptr, 0, nullptr));
+    ASR_CUDA(cudaDeviceSynchronize());
+    return ASR_OK;
+}
+
 static int run_encoder(asr_handle* h, int upto_layer, cudaStream_t st) {
     Workspace& w = h->ws;
     const BatchMeta& m = h->meta;
@@ -137,7 +156,8 @@ static int run_encoder(asr_handle* h, int upto_layer, cudaStream_t st) {
             e.bias = h->w.enc_bias[layer];
             e.C = w.xg;
             e.ldc = 2 * kGates;
-            ASR_TRY(launch_gemm(plain_a(x, K, K), h->w.enc_w_ih[layer], M, 2 * kGates, K, e, st, &h->launches));
+            ASR_TRY(gemm(h, plain_a(x, K, K), h->w.enc_w_ih[layer], h->w.enc_w_ih_hi[layer],
+                         h->w.enc_w_ih_lo[layer], M, 2 * kGates, K, e, st));
         }
         {
             StageScope sc(h, kStEncRec, st);
@@ -160,8 +180,8 @@ static int run_keys(asr_handle* h, cudaStream_t st) {
     e.bias = h->w.att_b;
     e.C = w.keys;
     e.ldc = kAtt;
-    return launch_gemm(plain_a(w.enc, kEnc, kEnc), h->w.att_w_enc_t, (int)h->meta.rows, kAtt, kEnc, e, st,
-                       &h->launches);
+    return gemm(h, plain_a(w.enc, kEnc, kEnc), h->w.att_w_enc_t, h->w.att_w_enc_t_hi, h->w.att_w_enc_t_lo,
+                (int)h->meta.rows, kAtt, kEnc, e, st);
 }
 
 // one decoder step up to the logits: LSTM cell -> attention -> vocabulary projection
@@ -186,7 +206,7 @@ static int decoder_step(asr_handle* h, int k, int step, int cur, float temperatu
         e.c_out = w.dc[nxt];
         e.H = kDecH;
         e.stop_flag = w.ctrl;
-        ASR_TRY(launch_gemm(A, h->w.dec_w, R, 4 * kDecH, kDecK, e, st, &h->launches));
+        ASR_TRY(gemm(h, A, h->w.dec_w, h->w.dec_w_hi, h->w.dec_w_lo, R, 4 * kDecH, kDecK, e, st));
     }
     {
         StageScope sc(h, kStAttn, st);
@@ -205,7 +225,7 @@ static int decoder_step(asr_handle* h, int k, int step, int cur, float temperatu
         e.ldc = kVocab;
         e.scale = temperature;
         e.stop_flag = w.ctrl;
-        ASR_TRY(launch_gemm(A, h->w.proj_w, R, kVocab, kProjK, e, st, &h->launches));
+        ASR_TRY(gemm(h, A, h->w.proj_w, h->w.proj_w_hi, h->w.proj_w_lo, R, kVocab, kProjK, e, st));
     }
     return ASR_OK;
 }
@@ -390,7 +410,53 @@ int asr_create(asr_handle** out, const asr_weights* wt, const asr_feature_consts
             for (int d = 0; d < kAtt; ++d) t[(size_t)d * kEnc + c] = wt->att_w_enc[(size_t)c * kAtt + d];
         if ((rc = dev_upload(pool, &h->w.att_w_enc_t, t)) != ASR_OK) return rc;
     }
+    // tf32 hi / lo copies for the tcgen05 path
+    for (int layer = 0; layer < 4; ++layer) {
+        const int K = layer == 0 ? kFeat : kEnc;
+        if ((rc = split_weight(h, h->w.enc_w_ih[layer], 2 * kGates, K, &h->w.enc_w_ih_hi[layer], &h->w.enc_w_ih_lo[layer])) != ASR_OK) return rc;
+    }
+    if ((rc = split_weight(h, h->w.dec_w, 4 * kDecH, kDecK, &h->w.dec_w_hi, &h->w.dec_w_lo)) != ASR_OK) return rc;
+    if ((rc = split_weight(h, h->w.proj_w, kVocab, kProjK, &h->w.proj_w_hi, &h->w.proj_w_lo)) != ASR_OK) return rc;
+    if ((rc = split_weight(h, h->w.att_w_enc_t, kAtt, kEnc, &h->w.att_w_enc_t_hi, &h->w.att_w_enc_t_lo)) != ASR_OK) return rc;
+    const char* env = getenv("ASR_B200_GEMM");
+    h->gemm_mode = (env && strcmp(env, "simt") == 0) ? 0 : (env && strcmp(env, "tc") == 0) ? 1 : 0;
     *out = h;
+    return ASR_OK;
+}
+
+int asr_set_gemm_mode(asr_handle* h, int mode) {
+    if (!h || mode < 0 || mode > 1) { set_error("asr_set_gemm_mode: bad argument"); return ASR_ERR_ARG; }
+    h->gemm_mode = mode;
+    return ASR_OK;
+}
+
+// Standalone GEMM for tests: d_C[M,N] = d_A[M,K] * d_W[N,K]^T + d_bias[N] with either path.
+int asr_test_gemm(asr_handle* h, const float* d_A, const float* d_W, const float* d_bias, float* d_C, int M,
+                  int N, int K, int mode, void* stream) {
+    if (!h || !d_A || !d_W || !d_bias || !d_C) { set_error("asr_test_gemm: NULL argument"); return ASR_ERR_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    GemmEpilogue e{};
+    e.kind = Epi::kBias;
+    e.bias = d_bias;
+    e.C = d_C;
+    e.ldc = N;
+    if (mode == 0) {
+        ASR_TRY(launch_gemm(plain_a(d_A, K, K), d_W, M, N, K, e, st, &h->launches));
+    } else {
+        float *a_hi, *a_lo, *w_hi, *w_lo;
+        ASR_CUDA(cudaMalloc(&a_hi, sizeof(float) * (size_t)M * K));
+        ASR_CUDA(cudaMalloc(&a_lo, sizeof(float) * (size_t)M * K));
+        ASR_CUDA(cudaMalloc(&w_hi, sizeof(float) * (size_t)N * K));
+        ASR_CUDA(cudaMalloc(&w_lo, sizeof(float) * (size_t)N * K));
+        int rc = split_operand(plain_a(d_A, K, K), M, K, a_hi, a_lo, nullptr, st, &h->launches);
+        if (rc == ASR_OK) rc = split_operand(plain_a(d_W, K, K), N, K, w_hi, w_lo, nullptr, st, &h->launches);
+        if (rc == ASR_OK) rc = launch_gemm_tc(a_hi, a_lo, w_hi, w_lo, M, N, K, e, st, &h->launches);
+        cudaError_t ce = cudaStreamSynchronize(st);
+        cudaFree(a_hi); cudaFree(a_lo); cudaFree(w_hi); cudaFree(w_lo);
+        if (rc != ASR_OK) return rc;
+        if (ce != cudaSuccess) { set_error("asr_test_gemm: %s", cudaGetErrorString(ce)); return ASR_ERR_CUDA; }
+    }
+    ASR_CUDA(cudaStreamSynchronize(st));
     return ASR_OK;
 }
 
@@ -471,6 +537,11 @@ int asr_reserve(asr_handle* h, int max_utts, int64_t max_rows, int max_beam, int
     ASR_TRY(dev_alloc_t(pool, &w.out_len, (size_t)max_utts));
     ASR_TRY(dev_alloc_t(pool, &w.out_score, (size_t)max_utts));
     ASR_TRY(dev_alloc_t(pool, &w.out_info, 4));
+    {
+        const size_t split_elems = std::max((size_t)max_rows * kFeat, R * (size_t)kDecK);
+        ASR_TRY(dev_alloc_t(pool, &w.a_hi, split_elems));
+        ASR_TRY(dev_alloc_t(pool, &w.a_lo, split_elems));
+    }
     // device metadata block + pinned staging
     const size_t meta_ints = 4 * (size_t)max_utts + 8 + 2 * (size_t)max_rows + (size_t)max_rows + 8;
     int* meta_block = nullptr;

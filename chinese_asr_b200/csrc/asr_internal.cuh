@@ -100,6 +100,17 @@ struct GemmEpilogue {
 // C[M,N] = A[M,K] * W[N,K]^T (+ epilogue).  fp32 in, fp32 accumulate.
 int launch_gemm(const AOperand& A, const float* W, int M, int N, int K, const GemmEpilogue& epi,
                 cudaStream_t st, int64_t* launches);
+// tcgen05 3xTF32 path (gemm_tc.cu): operands pre-split into tf32 hi / lo parts
+int split_operand(const AOperand& A, int M, int K, float* hi, float* lo, const int* stop_flag,
+                  cudaStream_t st, int64_t* launches);
+int launch_gemm_tc(const float* a_hi, const float* a_lo, const float* w_hi, const float* w_lo, int M,
+                   int N, int K, const GemmEpilogue& epi, cudaStream_t st, int64_t* launches);
+// a weight matrix with its pre-split copies
+struct SplitW {
+    float* w = nullptr;    // [N, K] fp32
+    float* hi = nullptr;   // rn_tf32(w)
+    float* lo = nullptr;   // rn_tf32(w - hi)
+};
 
 // ---------------------------------------------------------------------------------------------
 struct FeatureConsts {
@@ -131,6 +142,15 @@ struct PackedWeights {
     float* att_b = nullptr;          // [128]
     float* att_w_hidden = nullptr;   // [512, 128]  as stored (k-major rows, coalesced over d)
     float* att_v = nullptr;          // [128]
+    // tf32 hi / lo splits of the GEMM weights (tcgen05 3xTF32 path), same shapes as the originals
+    float* enc_w_ih_hi[4] = {};
+    float* enc_w_ih_lo[4] = {};
+    float* dec_w_hi = nullptr;
+    float* dec_w_lo = nullptr;
+    float* proj_w_hi = nullptr;
+    float* proj_w_lo = nullptr;
+    float* att_w_enc_t_hi = nullptr;
+    float* att_w_enc_t_lo = nullptr;
 };
 
 struct LmTables {
@@ -222,6 +242,8 @@ struct Workspace {
     // pinned host staging
     void* h_stage = nullptr;
     size_t h_stage_bytes = 0;
+    float* a_hi = nullptr;       // split A operand of the tcgen05 GEMMs: max(rows*720, R*1280) floats
+    float* a_lo = nullptr;
     std::vector<void*> allocs;
 };
 
@@ -238,6 +260,7 @@ struct asr_handle {
     int last_k = 0, last_steps = 0, last_B = 0;
     int64_t launches = 0;
     bool timing = false;
+    int gemm_mode = 0;           // 0 = CUDA-core fp32 FMA, 1 = tcgen05 3xTF32
     cudaEvent_t ev[2 * asr::kStages * 64] = {};
     int n_ev = 0;
     int ev_stage[asr::kStages * 64] = {};

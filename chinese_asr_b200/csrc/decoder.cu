@@ -634,12 +634,13 @@ __device__ __forceinline__ long long hash_slot(long long key, long long cap) {
 }
 __device__ long long lm_find(const long long* keys, long long cap, long long key) {
     long long s = hash_slot(key, cap);
-    while (true) {
+    for (long long probes = 0; probes < cap; ++probes) {    // bounded: a corrupt table cannot hang
         const long long kk = keys[s];
         if (kk == key) return s;
         if (kk == -1) return -1;
         s = (s + 1) & (cap - 1);
     }
+    return -1;
 }
 __device__ float lm_uni_or_bi(const LmDev& lm, int c, int w) {
     const long long s = lm_find(lm.bi_keys, lm.bi_cap, (long long)c * lm.vocab + w);

@@ -1,0 +1,369 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a:  C[M,N] = A[M,K] * W[N,K]^T  in "3xTF32".
+//
+// Why 3xTF32: parity with the fp32 reference must be token-exact (BASELINE.json north_star), and
+// bf16 / single-pass tf32 tensor-core products (8 / 11 significant bits) flip beam decisions
+// (hard part 1).  Every fp32 operand x is split once into
+//     x_hi = rn_tf32(x)          (cvt.rna.tf32.f32, exact in tf32)
+//     x_lo = rn_tf32(x - x_hi)   (the residual, |x_lo| <= 2^-11 |x|)
+// and the product is accumulated in fp32 in TMEM as  a_hi*w_hi + a_lo*w_hi + a_hi*w_lo
+// (the dropped a_lo*w_lo term and the rounding of the residuals are ~2^-22 relative), i.e.
+// fp32-faithful products at 1/3 of the tf32 tensor rate instead of the CUDA-core fp32 rate.
+//
+// Kernel anatomy (one 128 x BN output tile per CTA, cta_group::1):
+//   warp 0   : TMA producer - cp.async.bulk.tensor.2d of the A_hi/A_lo/W_hi/W_lo K-slabs
+//              (32 fp32 = 128 B rows, SWIZZLE_128B) into a 3-stage shared-memory ring,
+//              completion on `full` mbarriers (expect_tx); out-of-bounds rows / K are zero-filled
+//              by TMA, so M, N and K tails need no special code.
+//   warp 1   : allocates TMEM (BN fp32 columns), issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8)
+//              from one elected lane: 4 K-steps x 3 products per stage, tcgen05.commit releases
+//              the stage (`empty` mbarrier) and finally signals `tmem_full`.
+//   warps 2-5: epilogue - tcgen05.ld 32x32b.x32 of the accumulator rows (one row per thread),
+//              fused bias / temperature / LSTM-cell non-linearities, direct global stores.
+// SASS evidence: UTCHMMA-class (UTC*MMA), UTMALDG, LDTM, UTCBAR in `cuobjdump -sass`.
+#include <cuda.h>
+
+#include "asr_internal.cuh"
+
+namespace asr {
+
+namespace tc {
+
+constexpr int BM = 128;
+constexpr int BKF = 32;             // fp32 elements per K-slab row = 128 bytes
+constexpr int STAGES = 3;
+constexpr int UMMA_K = 8;
+constexpr unsigned kSpinLimit = 1u << 28;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    unsigned spins = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (!done && ++spins > kSpinLimit) __trap();      // turn a protocol bug into an error, not a hang
+    }
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int x, int y) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y)
+        : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (one 128-byte swizzle atom along K):
+// start address >> 4 | SBO (8 rows * 128 B = 1024 B) >> 4 at [32,46) | version 1 at [46,48) |
+// layout SWIZZLE_128B (2) at [61,64).  LBO is unused for swizzled K-major operands.
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(const void* smem) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_u32(smem) & 0x3FFFF) >> 4);
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// instruction descriptor, kind::tf32: D=f32 (1<<4), A=B=TF32 (2<<7, 2<<10), both K-major,
+// N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ float sigm(float x) { return 1.f / (1.f + expf(-x)); }
+
+template <int BN>
+struct SmemLayout {
+    static constexpr int kATile = BM * BKF * 4;      // 16 KB
+    static constexpr int kBTile = BN * BKF * 4;
+    static constexpr int kStage = 2 * kATile + 2 * kBTile;
+    static constexpr int kBytes = STAGES * kStage + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                   const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+                   int M, int N, int K, GemmEpilogue epi) {
+    if (epi.stop_flag && *epi.stop_flag >= 0) return;
+    using L = SmemLayout<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * L::kStage);
+    uint64_t* full = bars;                 // [STAGES]
+    uint64_t* empty = bars + STAGES;       // [STAGES]
+    uint64_t* tmem_full = bars + 2 * STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int nkb = (K + BKF - 1) / BKF;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w_hi) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "n"(BN)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                uint8_t* st = smem + s * L::kStage;
+                mbar_expect_tx(&full[s], L::kStage);
+                tma_load_2d(&map_a_hi, &full[s], st, kb * BKF, m0);
+                tma_load_2d(&map_a_lo, &full[s], st + L::kATile, kb * BKF, m0);
+                tma_load_2d(&map_w_hi, &full[s], st + 2 * L::kATile, kb * BKF, n0);
+                tma_load_2d(&map_w_lo, &full[s], st + 2 * L::kATile + L::kBTile, kb * BKF, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&full[s], ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                uint8_t* st = smem + s * L::kStage;
+                const uint64_t d_ah = make_kmajor_sw128_desc(st);
+                const uint64_t d_al = make_kmajor_sw128_desc(st + L::kATile);
+                const uint64_t d_wh = make_kmajor_sw128_desc(st + 2 * L::kATile);
+                const uint64_t d_wl = make_kmajor_sw128_desc(st + 2 * L::kATile + L::kBTile);
+#pragma unroll
+                for (int kk = 0; kk < BKF / UMMA_K; ++kk) {
+                    const uint64_t adv = (uint64_t)((kk * UMMA_K * 4) >> 4);      // +32 B per K-step
+                    umma_tf32(tmem_base, d_al + adv, d_wh + adv, idesc, (kb | kk) ? 1u : 0u);
+                    umma_tf32(tmem_base, d_ah + adv, d_wl + adv, idesc, 1u);
+                    umma_tf32(tmem_base, d_ah + adv, d_wh + adv, idesc, 1u);
+                }
+                umma_commit(&empty[s]);            // frees the stage when these MMAs have read it
+            }
+            umma_commit(tmem_full);                // accumulator complete
+        }
+    } else {
+        // ---- epilogue: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32) ------------------------
+        const int q = warp & 3;
+        const int row = m0 + q * 32 + lane;
+        mbar_wait(tmem_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const bool row_ok = row < M;
+        int crow = row;
+        if (epi.kind == Epi::kLstmCell && row_ok && epi.c_rowidx) crow = epi.c_rowidx[row];
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+            const int n = n0 + c0;
+            if (!row_ok || n >= N) continue;
+            if (epi.kind == Epi::kLstmCell) {
+                // 32 columns = 8 hidden units x (i, f, g, o)
+                float hv[8], cv[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int nn = n + 4 * j;
+                    const float gi = __uint_as_float(r[4 * j]) + epi.bias[nn];
+                    const float gf = __uint_as_float(r[4 * j + 1]) + epi.bias[nn + 1];
+                    const float gg = __uint_as_float(r[4 * j + 2]) + epi.bias[nn + 2];
+                    const float go = __uint_as_float(r[4 * j + 3]) + epi.bias[nn + 3];
+                    const float cp = epi.c_prev[(size_t)crow * epi.H + (nn >> 2)];
+                    cv[j] = sigm(gf) * cp + sigm(gi) * tanhf(gg);
+                    hv[j] = sigm(go) * tanhf(cv[j]);
+                }
+                float4* ho = reinterpret_cast<float4*>(epi.h_out + (size_t)row * epi.H + (n >> 2));
+                float4* co = reinterpret_cast<float4*>(epi.c_out + (size_t)row * epi.H + (n >> 2));
+                ho[0] = make_float4(hv[0], hv[1], hv[2], hv[3]);
+                ho[1] = make_float4(hv[4], hv[5], hv[6], hv[7]);
+                co[0] = make_float4(cv[0], cv[1], cv[2], cv[3]);
+                co[1] = make_float4(cv[4], cv[5], cv[6], cv[7]);
+            } else {
+                float* crowp = epi.C + (size_t)row * epi.ldc + n;
+                const bool sc = epi.kind == Epi::kBiasScale;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    if (n + j + 3 < N) {
+                        float4 v;
+                        v.x = __uint_as_float(r[j]) + epi.bias[n + j];
+                        v.y = __uint_as_float(r[j + 1]) + epi.bias[n + j + 1];
+                        v.z = __uint_as_float(r[j + 2]) + epi.bias[n + j + 2];
+                        v.w = __uint_as_float(r[j + 3]) + epi.bias[n + j + 3];
+                        if (sc) { v.x /= epi.scale; v.y /= epi.scale; v.z /= epi.scale; v.w /= epi.scale; }
+                        *reinterpret_cast<float4*>(crowp + j) = v;
+                    } else {
+                        for (int jj = 0; jj < 4; ++jj)
+                            if (n + j + jj < N) {
+                                float v = __uint_as_float(r[j + jj]) + epi.bias[n + j + jj];
+                                if (sc) v /= epi.scale;
+                                crowp[j + jj] = v;
+                            }
+                    }
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// operand split: x -> (rn_tf32(x), rn_tf32(x - rn_tf32(x))), with the AOperand gather fused
+__device__ __forceinline__ float rn_tf32(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+
+__global__ void split_operand_kernel(AOperand A, int M, int K, float* __restrict__ hi, float* __restrict__ lo,
+                                     const int* stop_flag) {
+    if (stop_flag && *stop_flag >= 0) return;
+    const int k4n = K >> 2;
+    const long long total = (long long)M * k4n;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int row = (int)(i / k4n);
+        const int k = (int)(i - (long long)row * k4n) * 4;
+        int g = 0;
+        if (A.nseg > 1 && k >= A.seg[0].kend) g = 1;
+        if (A.nseg > 2 && k >= A.seg[1].kend) g = 2;
+        const ASeg& s = A.seg[g];
+        const int kstart = g == 0 ? 0 : A.seg[g - 1].kend;
+        const int r = s.rowidx ? s.rowidx[row] : row;
+        const float4 v = *reinterpret_cast<const float4*>(s.base + (size_t)r * s.ld + (k - kstart));
+        float4 h, l;
+        h.x = rn_tf32(v.x); l.x = rn_tf32(v.x - h.x);
+        h.y = rn_tf32(v.y); l.y = rn_tf32(v.y - h.y);
+        h.z = rn_tf32(v.z); l.z = rn_tf32(v.z - h.z);
+        h.w = rn_tf32(v.w); l.w = rn_tf32(v.w - h.w);
+        *reinterpret_cast<float4*>(hi + (size_t)row * K + k) = h;
+        *reinterpret_cast<float4*>(lo + (size_t)row * K + k) = l;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2-D fp32 tensor [rows, K] row-major -> box [box_rows, 32] with 128-byte swizzle
+static int make_map(CUtensorMap* map, const float* base, int rows, int K, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return ASR_ERR_CUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)K * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)BKF, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) rows=%d K=%d", (int)r, rows, K); return ASR_ERR_CUDA; }
+    return ASR_OK;
+}
+
+}  // namespace tc
+
+int split_operand(const AOperand& A, int M, int K, float* hi, float* lo, const int* stop_flag, cudaStream_t st,
+                  int64_t* launches) {
+    if (M <= 0) return ASR_OK;
+    if (K % 4) { set_error("split: K %% 4"); return ASR_ERR_ARG; }
+    long long total = (long long)M * (K / 4);
+    int grid = (int)std::min<long long>((total + 255) / 256, (long long)kNumSMs * 16);
+    tc::split_operand_kernel<<<grid, 256, 0, st>>>(A, M, K, hi, lo, stop_flag);
+    ASR_CHECK_LAUNCH();
+    if (launches) ++*launches;
+    return ASR_OK;
+}
+
+// C = A * W^T with pre-split operands (a_hi/a_lo [M,K], w_hi/w_lo [N,K], all dense row-major)
+int launch_gemm_tc(const float* a_hi, const float* a_lo, const float* w_hi, const float* w_lo, int M, int N, int K,
+                   const GemmEpilogue& epi, cudaStream_t st, int64_t* launches) {
+    if (M <= 0) return ASR_OK;
+    if ((K * 4) % 16) { set_error("gemm_tc: K*4 must be a multiple of 16"); return ASR_ERR_ARG; }
+    if (epi.kind == Epi::kLstmCell && (N % 32)) { set_error("gemm_tc: LSTM epilogue needs N %% 32 == 0"); return ASR_ERR_ARG; }
+    constexpr int BN = 128;
+    CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
+    ASR_TRY(tc::make_map(&ma_hi, a_hi, M, K, tc::BM));
+    ASR_TRY(tc::make_map(&ma_lo, a_lo, M, K, tc::BM));
+    ASR_TRY(tc::make_map(&mw_hi, w_hi, N, K, BN));
+    ASR_TRY(tc::make_map(&mw_lo, w_lo, N, K, BN));
+    static bool attr = false;
+    const int smem = tc::SmemLayout<BN>::kBytes;
+    if (!attr) {
+        ASR_CUDA(cudaFuncSetAttribute(tc::gemm_tf32x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr = true;
+    }
+    dim3 grid((N + BN - 1) / BN, (M + tc::BM - 1) / tc::BM);
+    tc::gemm_tf32x3_kernel<BN><<<grid, 192, smem, st>>>(ma_hi, ma_lo, mw_hi, mw_lo, M, N, K, epi);
+    ASR_CHECK_LAUNCH();
+    if (launches) ++*launches;
+    return ASR_OK;
+}
+
+}  // namespace asr

@@ -66,13 +66,20 @@ class NGramLM:
                     continue
                 if not line or line.startswith('\\') or line.startswith('ngram '):
                     continue
-                parts = line.split('\t') if '\t' in line else line.split(' ')
-                if order == 0 or len(parts) < order + 1:
+                if order == 0:
+                    continue
+                if '\t' in line:
+                    parts = line.split('\t')
+                    words = parts[1].split(' ')
+                    bo = float(parts[2]) if len(parts) > 2 else 0.0
+                else:
+                    parts = line.split(' ')
+                    words = parts[1:1 + order]
+                    bo = float(parts[1 + order]) if len(parts) > 1 + order else 0.0
+                if len(words) != order:
                     continue
                 lp = float(parts[0])
-                words = parts[1].split(' ') if '\t' in line else parts[1:1 + order]
                 ids = [word2int.get(w, UNK) for w in words]
-                bo = float(parts[-1]) if len(parts) > (2 if '\t' in line else order + 1) else 0.0
                 if order == 1:
                     uni_logp[ids[0]] = lp
                     uni_bo[ids[0]] = bo

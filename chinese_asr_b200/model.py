@@ -263,14 +263,19 @@ class Model(object):
         if self._lm is lm_model:
             return
         t = lm_model.tables()
-        a = {k: np.ascontiguousarray(t[k]) for k in t}
+        # typed, contiguous host copies that stay alive until asr_set_lm has copied them
+        uni_logp = np.ascontiguousarray(t["uni_logp"], dtype=np.float32)
+        uni_bo = np.ascontiguousarray(t["uni_bo"], dtype=np.float32)
+        bi_keys = np.ascontiguousarray(t["bi_keys"], dtype=np.int64)
+        bi_vals = np.ascontiguousarray(t["bi_vals"], dtype=np.float32).reshape(-1)
+        tri_keys = np.ascontiguousarray(t["tri_keys"], dtype=np.int64)
+        tri_vals = np.ascontiguousarray(t["tri_vals"], dtype=np.float32).reshape(-1)
+        assert bi_vals.shape[0] == 2 * bi_keys.shape[0] and tri_vals.shape[0] == tri_keys.shape[0]
         tb = _cabi.AsrLmTables(
-            _cabi.fptr(a["uni_logp"].astype(np.float32)), _cabi.fptr(a["uni_bo"].astype(np.float32)),
-            a["bi_keys"].astype(np.int64).ctypes.data_as(_cabi.c_int64_p),
-            _cabi.fptr(np.ascontiguousarray(a["bi_vals"], dtype=np.float32).reshape(-1)), int(a["bi_keys"].shape[0]),
-            a["tri_keys"].astype(np.int64).ctypes.data_as(_cabi.c_int64_p),
-            _cabi.fptr(np.ascontiguousarray(a["tri_vals"], dtype=np.float32).reshape(-1)), int(a["tri_keys"].shape[0]),
-            int(a["uni_logp"].shape[0]), int(getattr(lm_model, 'skip_id', 781)))
+            _cabi.fptr(uni_logp), _cabi.fptr(uni_bo),
+            bi_keys.ctypes.data_as(_cabi.c_int64_p), _cabi.fptr(bi_vals), int(bi_keys.shape[0]),
+            tri_keys.ctypes.data_as(_cabi.c_int64_p), _cabi.fptr(tri_vals), int(tri_keys.shape[0]),
+            int(uni_logp.shape[0]), int(getattr(lm_model, 'skip_id', 781)))
         check(lib.asr_set_lm(self._h, C.byref(tb)), "asr_set_lm")
         self._lm = lm_model
         if hasattr(lm_model, 'bind'):
@@ -373,6 +378,23 @@ class Model(object):
             texts = [''.join(int2word[t] for t in tokens[i, :tlen[i]].tolist()) for i in range(B)]
             return tokens, tlen, score, texts
         return tokens, tlen, score
+
+    # ---- GEMM engine ---------------------------------------------------------------------------------
+    def set_gemm_mode(self, mode):
+        """'simt' (CUDA-core fp32) or 'tc' (tcgen05 3xTF32 tensor cores)."""
+        self._need()
+        check(lib.asr_set_gemm_mode(self._h, {'simt': 0, 'tc': 1}[mode]), "asr_set_gemm_mode")
+
+    def test_gemm(self, A, W, bias, mode):
+        """C = A @ W.T + bias on the device through one GEMM engine (tests)."""
+        self._need()
+        M, K = A.shape
+        N = W.shape[0]
+        Cout = torch.empty(M, N, dtype=torch.float32, device=self.device)
+        check(lib.asr_test_gemm(self._h, C.c_void_p(A.data_ptr()), C.c_void_p(W.data_ptr()),
+                                C.c_void_p(bias.data_ptr()), C.c_void_p(Cout.data_ptr()), M, N, K,
+                                {'simt': 0, 'tc': 1}[mode], self._stream()), "asr_test_gemm")
+        return Cout
 
     # ---- instrumentation ---------------------------------------------------------------------------
     def launch_count(self, reset=False):

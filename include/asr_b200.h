@@ -171,6 +171,15 @@ int asr_transcribe_device(asr_handle* h, const float* d_pcm, const int64_t* h_pc
                           double length_weight, int32_t* h_tokens, int32_t* h_len, float* h_score,
                           void* stream);
 
+/* GEMM engine of the four GEMM-shaped stages (nn.LSTM input projections util.py:1259, attention
+ * keys attention.py:77, nn.LSTMCell util.py:1650-1661, vocabulary projection decoder.py:133):
+ * 0 = CUDA-core fp32 FMA, 1 = tcgen05/TMEM/TMA tensor cores in 3xTF32 (fp32-faithful).  The
+ * default can also be chosen with the environment variable ASR_B200_GEMM=simt|tc. */
+int asr_set_gemm_mode(asr_handle* h, int mode);
+/* Standalone GEMM for tests: d_C[M,N] = d_A[M,K] * d_W[N,K]^T + d_bias[N] through engine `mode`. */
+int asr_test_gemm(asr_handle* h, const float* d_A, const float* d_W, const float* d_bias, float* d_C,
+                  int M, int N, int K, int mode, void* stream);
+
 /* Number of kernels this library launched since the handle was created / last reset. */
 int64_t asr_launch_count(asr_handle* h, int reset);
 

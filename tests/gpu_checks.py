@@ -191,6 +191,22 @@ def check_beam(cname):
     return res
 
 
+def check_gemm(mode):
+    """Both GEMM engines against a float64 product: fp32-faithful means ~1e-6 relative error."""
+    m = get_model((1234, "plain", None), O.make_weights(1234, "plain"))
+    g = torch.Generator().manual_seed(3)
+    res = {}
+    for (M, N, K) in ((300, 2048, 720), (256, 5004, 1024), (129, 128, 512), (2500, 2048, 512)):
+        A = torch.randn(M, K, generator=g)
+        W = torch.randn(N, K, generator=g) * 0.05
+        b = torch.randn(N, generator=g)
+        ref = (A.double() @ W.double().t() + b.double())
+        out = m.test_gemm(A.cuda(), W.cuda(), b.cuda(), mode).cpu().double()
+        scale = float(ref.abs().max())
+        res[f"{M}x{N}x{K}_relerr"] = float((out - ref).abs().max()) / scale
+    return res
+
+
 def check_lm():
     from chinese_asr_b200.lm import NGramLM
     w2i, i2w = vocab()

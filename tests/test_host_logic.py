@@ -1,0 +1,98 @@
+"""Host-side logic of the product (CPU only): constant tables, WAV ingest, ARPA loader, sharding
+and the N>1 gather over gloo."""
+import os
+import wave
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from tests.cases import load_golden
+from oracle import asr_oracle as O
+
+
+def test_feature_constants_match_reference():
+    from chinese_asr_b200 import data
+    g = load_golden()
+    fc = data.feature_consts()
+    assert np.array_equal(fc["mel_fb"], g["fb"])           # data.py:21-57, bit-exact
+    assert np.array_equal(fc["window"], g["window"])       # data.py:381-382
+    assert np.array_equal(fc["taps"], O.delta_taps())
+    assert int((fc["mel_fb"] != 0).sum()) == 504
+
+
+def test_fast_read_wav(tmp_path):
+    from chinese_asr_b200 import data
+    x = (np.random.default_rng(0).standard_normal(4000) * 3000).astype(np.int16)
+    p = str(tmp_path / "a.wav")
+    with wave.open(p, "wb") as w:
+        w.setnchannels(1); w.setsampwidth(2); w.setframerate(16000)
+        w.writeframes(x.tobytes())
+    y = data.fast_read(p)
+    assert y.dtype == np.float32 and np.array_equal(y, x.astype(np.float32) / 32768.0)
+
+
+def test_arpa_loader_matches_tables(tmp_path):
+    from chinese_asr_b200.lm import NGramLM
+    import pickle
+    w2i, i2w = pickle.load(open(os.path.join(os.path.dirname(__file__), "golden", "dict.pkl"), "rb"))
+    words = [i2w[i] for i in (4, 5, 6, 7, 8)]
+    arpa = tmp_path / "t.arpa"
+    lines = ["\\data\\", "ngram 1=7", "ngram 2=2", "ngram 3=1", "", "\\1-grams:"]
+    for i, wd in enumerate(["<s>", "</s>", "<unk>"] + words[:4]):
+        lines.append(f"{-1.0 - 0.1 * i}\t{wd}\t{-0.2 - 0.01 * i}")
+    lines += ["", "\\2-grams:", f"-0.5\t{words[0]} {words[1]}\t-0.3", f"-0.7\t<s> {words[0]}\t-0.1", "",
+              "\\3-grams:", f"-0.25\t<s> {words[0]} {words[1]}", "", "\\end\\"]
+    arpa.write_text("\n".join(lines), encoding="utf-8")
+    lm = NGramLM.from_arpa(str(arpa), w2i)
+    t = lm.tables()
+    assert t["uni_logp"][w2i[words[0]]] == np.float32(-1.3)
+    V = len(w2i)
+    key = w2i[words[0]] * V + w2i[words[1]]
+    assert key in t["bi_keys"].tolist()
+    assert ((w2i["<s>"] * V + w2i[words[0]]) * V + w2i[words[1]]) in t["tri_keys"].tolist()
+
+
+def test_shard_utterances_balanced():
+    from chinese_asr_b200.parallel import shard_utterances
+    rng = np.random.default_rng(1)
+    n = rng.integers(32000, 320000, 257)
+    for world in (1, 2, 4, 8):
+        sh = shard_utterances(n, world)
+        assert sorted(i for s in sh for i in s) == list(range(257))
+        counts = [len(s) for s in sh]
+        assert max(counts) - min(counts) <= 1
+        tot = [int(n[s].sum()) for s in sh]
+        assert max(tot) / min(tot) < 1.05
+
+
+def _gather_worker(rank, world, port, total, max_len, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from chinese_asr_b200.parallel import shard_utterances, pack_records, gather_hypotheses
+    n = np.arange(total) * 7 % 13 + 5
+    mine = shard_utterances(n, world)[rank]
+    toks = np.stack([np.full(max_len, i, dtype=np.int32) for i in mine]) if mine else np.zeros((0, max_len), np.int32)
+    rec = pack_records(mine, toks, [i % max_len for i in mine], [-(i + 0.5) for i in mine], max_len)
+    t, l, s = gather_hypotheses(rec, total, max_len)
+    ok = all((t[i] == i).all() and l[i] == i % max_len and s[i] == np.float32(-(i + 0.5)) for i in range(total))
+    q.put((rank, bool(ok)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2])
+def test_gather_hypotheses_gloo(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 500)
+    procs = [ctx.Process(target=_gather_worker, args=(r, world, port, 11, 40, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res) and len(res) == world

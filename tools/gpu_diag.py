@@ -20,6 +20,8 @@ def main():
               ("encoder_kat", G.check_encoder_kat, ()),
               ("encoder_greedy3", G.check_encoder, ("greedy3",)),
               ("encoder_beam4", G.check_encoder, ("beam4",)),
+              ("gemm_simt", G.check_gemm, ("simt",)),
+              ("gemm_tc", G.check_gemm, ("tc",)),
               ("lm", G.check_lm, ()),
               ("greedy1", G.check_greedy, ("greedy1",)),
               ("greedy3", G.check_greedy, ("greedy3",)),
@@ -47,7 +49,8 @@ def main():
             print(f"   {k}: {v}")
         sys.stdout.flush()
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    with open(os.path.join(ROOT, "gpurun_out", "diag.json"), "w") as f:
+    tag = "_".join(sel) if sel else "all"
+    with open(os.path.join(ROOT, "gpurun_out", f"diag_{tag}.json"), "w") as f:
         json.dump(out, f, indent=1)
 
 
