@@ -210,6 +210,15 @@ static int decoder_step(asr_handle* h, int k, int step, int cur, float temperatu
     }
     {
         StageScope sc(h, kStAttn, st);
+        // query projection q = h_new * W_hidden (attention.py:92) on the GEMM engine
+        GemmEpilogue e{};
+        e.kind = Epi::kBias;
+        e.bias = h->w.zero_bias;
+        e.C = w.att_q;
+        e.ldc = kAtt;
+        e.stop_flag = w.ctrl;
+        ASR_TRY(gemm(h, plain_a(w.dh[nxt], kDecH, kDecH), h->w.att_w_hidden_t, h->w.att_w_hidden_t_hi,
+                     h->w.att_w_hidden_t_lo, R, kAtt, kDecH, e, st));
         ASR_TRY(launch_attention(h, k, step, nxt, d_align_step, st));
     }
     {
@@ -410,6 +419,14 @@ int asr_create(asr_handle** out, const asr_weights* wt, const asr_feature_consts
             for (int d = 0; d < kAtt; ++d) t[(size_t)d * kEnc + c] = wt->att_w_enc[(size_t)c * kAtt + d];
         if ((rc = dev_upload(pool, &h->w.att_w_enc_t, t)) != ASR_OK) return rc;
     }
+    {
+        std::vector<float> t((size_t)kAtt * kDecH), z(kAtt, 0.f);
+        for (int c = 0; c < kDecH; ++c)
+            for (int d = 0; d < kAtt; ++d) t[(size_t)d * kDecH + c] = wt->att_w_hidden[(size_t)c * kAtt + d];
+        if ((rc = dev_upload(pool, &h->w.att_w_hidden_t, t)) != ASR_OK) return rc;
+        if ((rc = dev_upload(pool, &h->w.zero_bias, z)) != ASR_OK) return rc;
+    }
+    if ((rc = split_weight(h, h->w.att_w_hidden_t, kAtt, kDecH, &h->w.att_w_hidden_t_hi, &h->w.att_w_hidden_t_lo)) != ASR_OK) return rc;
     // tf32 hi / lo copies for the tcgen05 path
     for (int layer = 0; layer < 4; ++layer) {
         const int K = layer == 0 ? kFeat : kEnc;
@@ -509,6 +526,7 @@ int asr_reserve(asr_handle* h, int max_utts, int64_t max_rows, int max_beam, int
         ASR_TRY(dev_alloc_t(pool, &w.dctx[i], R * kEnc));
     }
     ASR_TRY(dev_alloc_t(pool, &w.logits, R * kVocab));
+    ASR_TRY(dev_alloc_t(pool, &w.att_q, R * kAtt));
     ASR_TRY(dev_alloc_t(pool, &w.att_part, (size_t)max_utts * 8 * max_beam * 514));
     // raw attention scores are only exported by the greedy path (k = 1)
     w.att_score_ld = std::min<int64_t>(max_rows, 4096);

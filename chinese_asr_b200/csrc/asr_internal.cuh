@@ -151,6 +151,10 @@ struct PackedWeights {
     float* proj_w_lo = nullptr;
     float* att_w_enc_t_hi = nullptr;
     float* att_w_enc_t_lo = nullptr;
+    float* att_w_hidden_t = nullptr;     // [128, 512] (W_hidden transposed -> [N, K]) for the query GEMM
+    float* att_w_hidden_t_hi = nullptr;
+    float* att_w_hidden_t_lo = nullptr;
+    float* zero_bias = nullptr;          // [128] zeros
 };
 
 struct LmTables {
@@ -210,6 +214,7 @@ struct Workspace {
     float* dc[2] = {};
     float* dctx[2] = {};
     float* logits = nullptr;     // [R, 5004]
+    float* att_q = nullptr;      // [R, 128] query projection of the current step
     float* att_part = nullptr;   // [B, S, k, 2 + 512] partial (max, sum, ctx)
     float* att_score = nullptr;  // [R, Lmax_cap] raw scores (alignment export)
     int* att_ticket = nullptr;   // [B]

@@ -30,6 +30,12 @@ __device__ __forceinline__ float warp_sum(float v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+// tanh(x) = 1 - 2 / (1 + e^{2x}) with ex2.approx / rcp-based division: absolute error < 1e-6
+// (libdevice tanhf costs ~3x the instructions; tanh.approx.f32 is only 2^-11 accurate)
+__device__ __forceinline__ float tanh_acc(float x) {
+    const float e = __expf(2.f * x);
+    return 1.f - __fdividef(2.f, e + 1.f);
+}
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -95,10 +101,9 @@ int decode_init(asr_handle* h, int k, int max_len, bool greedy, cudaStream_t st)
 // ---------------------------------------------------------------------------------------------
 // attention
 struct AttnParams {
-    const float* h;         // [R, 512] new decoder hidden state
+    const float* q;         // [R, 128] query projection h_new * W_hidden (GEMM engine)
     const float* keys;      // [rows, 128] utterance-major sorted
     const float* enc;       // [rows, 512]
-    const float* w_hidden;  // [512, 128]
     const float* v;         // [128]
     const int* uoff;        // [B + 1]
     float* ctx_out;         // [R, 512]
@@ -119,7 +124,6 @@ attention_kernel(AttnParams p) {
     extern __shared__ __align__(16) float sm[];
     float* s_q = sm;                        // [K][128]
     float* s_sc = sm + K * kAtt;            // [K][sc_ld]
-    float* s_h = s_sc + K * p.sc_ld;        // [K][512]
     __shared__ float s_m[K], s_sum[K];
     __shared__ int s_last;
 
@@ -132,40 +136,13 @@ attention_kernel(AttnParams p) {
     const int lbeg = min(L, sp * Lc), lend = min(L, lbeg + Lc);
     const int nl = lend - lbeg;
 
-    // ---- phase A: q = h * W_hidden ------------------------------------------------------------
-    for (int i = tid; i < k * kDecH; i += 256) s_h[i] = p.h[(size_t)u * k * kDecH + i];
-    __syncthreads();
-    {
-        const int d = tid & 127, half = tid >> 7;
-        const int kb0 = half == 0 ? 0 : (k + 1) / 2;
-        const int kb1 = half == 0 ? (k + 1) / 2 : k;
-        float acc[(K + 1) / 2];
-#pragma unroll
-        for (int i = 0; i < (K + 1) / 2; ++i) acc[i] = 0.f;
-        for (int c = 0; c < kDecH; c += 4) {
-            const float w0 = __ldg(p.w_hidden + (size_t)(c + 0) * kAtt + d);
-            const float w1 = __ldg(p.w_hidden + (size_t)(c + 1) * kAtt + d);
-            const float w2 = __ldg(p.w_hidden + (size_t)(c + 2) * kAtt + d);
-            const float w3 = __ldg(p.w_hidden + (size_t)(c + 3) * kAtt + d);
-#pragma unroll
-            for (int i = 0; i < (K + 1) / 2; ++i) {
-                const int kb = kb0 + i;
-                if (kb < kb1) {
-                    const float4 hv = *reinterpret_cast<const float4*>(s_h + kb * kDecH + c);
-                    acc[i] = fmaf(hv.x, w0, acc[i]);
-                    acc[i] = fmaf(hv.y, w1, acc[i]);
-                    acc[i] = fmaf(hv.z, w2, acc[i]);
-                    acc[i] = fmaf(hv.w, w3, acc[i]);
-                }
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < (K + 1) / 2; ++i)
-            if (kb0 + i < kb1) s_q[(kb0 + i) * kAtt + d] = acc[i];
-    }
+    // ---- phase A: the query projection q = h * W_hidden was computed by the GEMM engine --------
+    for (int i = tid; i < k * kAtt; i += 256) s_q[i] = p.q[(size_t)u * k * kAtt + i];
     __syncthreads();
 
     // ---- phase B: scores e[l][kb] = sum_d v_d tanh(key[l][d] + q[kb][d]) ----------------------
+    // one warp per frame, lane owns 4 of the 128 attention dims for all K beams; the K partial
+    // sums are reduced with a transposed butterfly (K/2 + K/4 + .. shuffles instead of 5 K)
     {
         const float4 v4 = *reinterpret_cast<const float4*>(p.v + 4 * lane);
         float4 q4[K];
@@ -173,19 +150,34 @@ attention_kernel(AttnParams p) {
         for (int kb = 0; kb < K; ++kb)
             q4[kb] = kb < k ? *reinterpret_cast<const float4*>(s_q + kb * kAtt + 4 * lane)
                             : make_float4(0.f, 0.f, 0.f, 0.f);
+        constexpr int kGroup = 32 / K;                 // lanes that end up holding the same beam
         for (int l = lbeg + warp; l < lend; l += 8) {
             const float4 key = __ldg(reinterpret_cast<const float4*>(p.keys + (size_t)(row0 + l) * kAtt) + lane);
+            float e[K];
 #pragma unroll
             for (int kb = 0; kb < K; ++kb) {
-                if (kb < k) {
-                    float e = v4.x * tanhf(key.x + q4[kb].x);
-                    e = fmaf(v4.y, tanhf(key.y + q4[kb].y), e);
-                    e = fmaf(v4.z, tanhf(key.z + q4[kb].z), e);
-                    e = fmaf(v4.w, tanhf(key.w + q4[kb].w), e);
-                    e = warp_sum(e);
-                    if (lane == 0) s_sc[kb * p.sc_ld + (l - lbeg)] = e;
-                }
+                float t = v4.x * tanh_acc(key.x + q4[kb].x);
+                t = fmaf(v4.y, tanh_acc(key.y + q4[kb].y), t);
+                t = fmaf(v4.z, tanh_acc(key.z + q4[kb].z), t);
+                t = fmaf(v4.w, tanh_acc(key.w + q4[kb].w), t);
+                e[kb] = t;
             }
+            int off = 16;
+#pragma unroll
+            for (int n = K; n > 1; n >>= 1) {
+                const int half = n >> 1;
+                const bool up = (lane & off) != 0;
+#pragma unroll
+                for (int j = 0; j < half; ++j) {
+                    const float send = up ? e[j] : e[j + half];
+                    const float keep = up ? e[j + half] : e[j];
+                    e[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                }
+                off >>= 1;
+            }
+            for (; off > 0; off >>= 1) e[0] += __shfl_xor_sync(0xffffffffu, e[0], off);
+            const int kb = lane / kGroup;
+            if ((lane % kGroup) == 0 && kb < k) s_sc[kb * p.sc_ld + (l - lbeg)] = e[0];
         }
     }
     __syncthreads();
@@ -210,6 +202,7 @@ attention_kernel(AttnParams p) {
     __syncthreads();
 
     // ---- phase D: context partial: ctx[kb][c] = sum_l p[l][kb] * enc[l][c] ---------------------
+    // thread owns 2 of the 512 encoder columns for all K beams; packed fp32x2 FMAs (FFMA2)
     float2 acc[K];
 #pragma unroll
     for (int kb = 0; kb < K; ++kb) acc[kb] = make_float2(0.f, 0.f);
@@ -224,11 +217,11 @@ attention_kernel(AttnParams p) {
 #pragma unroll
             for (int kb = 0; kb < K; ++kb) {
                 if (kb < k) {
-                    const float* sc = s_sc + kb * p.sc_ld + l;
-                    acc[kb].x = fmaf(sc[0], e0.x, acc[kb].x); acc[kb].y = fmaf(sc[0], e0.y, acc[kb].y);
-                    acc[kb].x = fmaf(sc[1], e1.x, acc[kb].x); acc[kb].y = fmaf(sc[1], e1.y, acc[kb].y);
-                    acc[kb].x = fmaf(sc[2], e2.x, acc[kb].x); acc[kb].y = fmaf(sc[2], e2.y, acc[kb].y);
-                    acc[kb].x = fmaf(sc[3], e3.x, acc[kb].x); acc[kb].y = fmaf(sc[3], e3.y, acc[kb].y);
+                    const float4 w = *reinterpret_cast<const float4*>(s_sc + kb * p.sc_ld + l);
+                    acc[kb] = __ffma2_rn(make_float2(w.x, w.x), e0, acc[kb]);
+                    acc[kb] = __ffma2_rn(make_float2(w.y, w.y), e1, acc[kb]);
+                    acc[kb] = __ffma2_rn(make_float2(w.z, w.z), e2, acc[kb]);
+                    acc[kb] = __ffma2_rn(make_float2(w.w, w.w), e3, acc[kb]);
                 }
             }
         }
@@ -238,7 +231,7 @@ attention_kernel(AttnParams p) {
             for (int kb = 0; kb < K; ++kb) {
                 if (kb < k) {
                     const float pe = s_sc[kb * p.sc_ld + l];
-                    acc[kb].x = fmaf(pe, e0.x, acc[kb].x); acc[kb].y = fmaf(pe, e0.y, acc[kb].y);
+                    acc[kb] = __ffma2_rn(make_float2(pe, pe), e0, acc[kb]);
                 }
             }
         }
@@ -310,10 +303,9 @@ int launch_attention(asr_handle* h, int k, int step, int nxt, float* d_align_ste
     Workspace& w = h->ws;
     const BatchMeta& m = h->meta;
     AttnParams p{};
-    p.h = w.dh[nxt];
+    p.q = w.att_q;
     p.keys = w.keys;
     p.enc = w.enc;
-    p.w_hidden = h->w.att_w_hidden;
     p.v = h->w.att_v;
     p.uoff = m.d_uoff_sorted;
     p.ctx_out = w.dctx[nxt];
@@ -334,7 +326,7 @@ int launch_attention(asr_handle* h, int k, int step, int nxt, float* d_align_ste
     p.align_out = d_align_step;
     p.raw_score = (d_align_step && S > 1) ? w.att_score : nullptr;
     const int K = k == 1 ? 1 : (k <= 4 ? 4 : (k <= 8 ? 8 : 16));
-    const size_t smem = sizeof(float) * ((size_t)K * kAtt + (size_t)K * p.sc_ld + (size_t)K * kDecH);
+    const size_t smem = sizeof(float) * ((size_t)K * kAtt + (size_t)K * p.sc_ld);
     dim3 grid(m.B, S);
 #define ASR_LAUNCH_ATT(KK)                                                                      \
     do {                                                                                        \
@@ -406,6 +398,7 @@ row_topk_kernel(RowTopkParams p) {
     if (p.step == 0 && (r % p.k) != 0) return;      // step 0: only the first beam (model.py:862)
     __shared__ float s_red[8];
     __shared__ int s_hist[256];
+    __shared__ unsigned s_tmax[256];
     __shared__ unsigned s_prefix;
     __shared__ int s_krem;
     __shared__ int s_cnt;
@@ -437,57 +430,85 @@ row_topk_kernel(RowTopkParams p) {
         key[i] = e < kVocab ? ordered_key(v[i]) : 0u;
     }
 
-    // radix select: find the K-th largest key, 8 bits per pass from the top
-    if (tid == 0) { s_prefix = 0u; s_krem = p.K; s_cnt = 0; }
-    for (int pass = 0; pass < 4; ++pass) {
-        const int shift = 24 - 8 * pass;
-        s_hist[tid] = 0;
-        __syncthreads();
-        const unsigned prefix = s_prefix;
-        const unsigned mask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+    // Fast path: the K-th largest of the 256 per-thread maxima is a lower bound of the K-th
+    // largest element (they are K distinct elements), so {key >= that} holds >= K candidates and,
+    // for any non-degenerate row, only a few more than K.
+    unsigned tm = 0u;
+#pragma unroll
+    for (int i = 0; i < kRowElems; ++i) tm = max(tm, key[i]);
+    s_tmax[tid] = tm;
+    if (tid == 0) s_cnt = 0;
+    __syncthreads();
+    {
+        int rk = 0;
+#pragma unroll 8
+        for (int j = 0; j < 256; ++j) {
+            const unsigned o = s_tmax[j];
+            rk += (o > tm || (o == tm && j < tid)) ? 1 : 0;
+        }
+        if (rk == p.K - 1) s_prefix = tm;
+    }
+    __syncthreads();
+    unsigned kth = s_prefix;
+    auto collect = [&]() {
 #pragma unroll
         for (int i = 0; i < kRowElems; ++i) {
             const int e = tid + 256 * i;
-            if (e < kVocab && (key[i] & mask) == prefix) atomicAdd(&s_hist[(key[i] >> shift) & 255], 1);
-        }
-        __syncthreads();
-        if (warp == 0) {
-            // lane owns bins [8*lane, 8*lane+8); suffix sums from the top
-            int loc[8], tot = 0;
-#pragma unroll
-            for (int b = 0; b < 8; ++b) { loc[b] = s_hist[8 * lane + b]; tot += loc[b]; }
-            int above = 0;     // elements in lanes that own larger bins
-            for (int src = 31; src > 0; --src) {
-                const int t = __shfl_sync(0xffffffffu, tot, src);
-                if (lane < src) above += t;
+            if (e < kVocab && key[i] >= kth) {
+                const int slot = atomicAdd(&s_cnt, 1);
+                if (slot < kCandCap) { s_cs[slot] = v[i]; s_ct[slot] = e; }
             }
-            const int krem = s_krem;
-            // the crossing lane: above < krem <= above + tot
-            if (above < krem && krem <= above + tot) {
-                int cum = above;
-                for (int b = 7; b >= 0; --b) {
-                    if (cum + loc[b] >= krem) {
-                        s_prefix = prefix | ((unsigned)(8 * lane + b) << shift);
-                        s_krem = krem - cum;
-                        break;
+        }
+    };
+    collect();
+    __syncthreads();
+    if (s_cnt > kCandCap) {
+        // Slow path (degenerate rows with > kCandCap near-ties): exact 4-pass radix select of the
+        // K-th largest key, 8 bits per pass from the top
+        __syncthreads();
+        if (tid == 0) { s_prefix = 0u; s_krem = p.K; s_cnt = 0; }
+        for (int pass = 0; pass < 4; ++pass) {
+            const int shift = 24 - 8 * pass;
+            s_hist[tid] = 0;
+            __syncthreads();
+            const unsigned prefix = s_prefix;
+            const unsigned mask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+    #pragma unroll
+            for (int i = 0; i < kRowElems; ++i) {
+                const int e = tid + 256 * i;
+                if (e < kVocab && (key[i] & mask) == prefix) atomicAdd(&s_hist[(key[i] >> shift) & 255], 1);
+            }
+            __syncthreads();
+            if (warp == 0) {
+                // lane owns bins [8*lane, 8*lane+8); suffix sums from the top
+                int loc[8], tot = 0;
+    #pragma unroll
+                for (int b = 0; b < 8; ++b) { loc[b] = s_hist[8 * lane + b]; tot += loc[b]; }
+                int above = 0;     // elements in lanes that own larger bins
+                for (int src = 31; src > 0; --src) {
+                    const int t = __shfl_sync(0xffffffffu, tot, src);
+                    if (lane < src) above += t;
+                }
+                const int krem = s_krem;
+                // the crossing lane: above < krem <= above + tot
+                if (above < krem && krem <= above + tot) {
+                    int cum = above;
+                    for (int b = 7; b >= 0; --b) {
+                        if (cum + loc[b] >= krem) {
+                            s_prefix = prefix | ((unsigned)(8 * lane + b) << shift);
+                            s_krem = krem - cum;
+                            break;
+                        }
+                        cum += loc[b];
                     }
-                    cum += loc[b];
                 }
             }
+            __syncthreads();
         }
+        kth = s_prefix;
+        collect();
         __syncthreads();
     }
-    const unsigned kth = s_prefix;
-    // collect every element >= kth (count = K - krem + #ties at kth), capped
-#pragma unroll
-    for (int i = 0; i < kRowElems; ++i) {
-        const int e = tid + 256 * i;
-        if (e < kVocab && key[i] >= kth) {
-            const int slot = atomicAdd(&s_cnt, 1);
-            if (slot < kCandCap) { s_cs[slot] = v[i]; s_ct[slot] = e; }
-        }
-    }
-    __syncthreads();
     const int n = min(s_cnt, kCandCap);
     // rank by counting: order (score desc, token asc)
     for (int i = tid; i < n; i += 256) {
