@@ -163,8 +163,13 @@ static int run_encoder(asr_handle* h, int upto_layer, cudaStream_t st) {
             StageScope sc(h, kStEncRec, st);
             const bool last = layer == 3;
             float* y = w.act[layer & 1];
-            ASR_TRY(launch_lstm_recurrence(h, layer, w.xg, layer == 0 ? nullptr : x, y,
-                                           last ? w.enc : nullptr, w.h0, w.c0, st));
+            if (h->rec_mode == 1) {
+                ASR_TRY(launch_lstm_recurrence_tc(h, layer, w.xg, layer == 0 ? nullptr : x, y,
+                                                  last ? w.enc : nullptr, w.h0, w.c0, st));
+            } else {
+                ASR_TRY(launch_lstm_recurrence(h, layer, w.xg, layer == 0 ? nullptr : x, y,
+                                               last ? w.enc : nullptr, w.h0, w.c0, st));
+            }
             x = y;
             K = kEnc;
         }
@@ -431,19 +436,23 @@ int asr_create(asr_handle** out, const asr_weights* wt, const asr_feature_consts
     for (int layer = 0; layer < 4; ++layer) {
         const int K = layer == 0 ? kFeat : kEnc;
         if ((rc = split_weight(h, h->w.enc_w_ih[layer], 2 * kGates, K, &h->w.enc_w_ih_hi[layer], &h->w.enc_w_ih_lo[layer])) != ASR_OK) return rc;
+        if ((rc = split_weight(h, h->w.enc_w_hh[layer], 2 * kGates, kEncH, &h->w.enc_w_hh_hi[layer], &h->w.enc_w_hh_lo[layer])) != ASR_OK) return rc;
     }
     if ((rc = split_weight(h, h->w.dec_w, 4 * kDecH, kDecK, &h->w.dec_w_hi, &h->w.dec_w_lo)) != ASR_OK) return rc;
     if ((rc = split_weight(h, h->w.proj_w, kVocab, kProjK, &h->w.proj_w_hi, &h->w.proj_w_lo)) != ASR_OK) return rc;
     if ((rc = split_weight(h, h->w.att_w_enc_t, kAtt, kEnc, &h->w.att_w_enc_t_hi, &h->w.att_w_enc_t_lo)) != ASR_OK) return rc;
     const char* env = getenv("ASR_B200_GEMM");
     h->gemm_mode = (env && strcmp(env, "simt") == 0) ? 0 : (env && strcmp(env, "tc") == 0) ? 1 : 0;
+    const char* env_rec = getenv("ASR_B200_REC");
+    h->rec_mode = (env_rec && strcmp(env_rec, "tc") == 0) ? 1 : 0;
     *out = h;
     return ASR_OK;
 }
 
 int asr_set_gemm_mode(asr_handle* h, int mode) {
-    if (!h || mode < 0 || mode > 1) { set_error("asr_set_gemm_mode: bad argument"); return ASR_ERR_ARG; }
-    h->gemm_mode = mode;
+    if (!h || mode < 0 || mode > 3) { set_error("asr_set_gemm_mode: bad argument"); return ASR_ERR_ARG; }
+    h->gemm_mode = mode & 1;          // bit 0: GEMM stages on tcgen05
+    h->rec_mode = (mode >> 1) & 1;    // bit 1: encoder recurrence on tcgen05
     return ASR_OK;
 }
 

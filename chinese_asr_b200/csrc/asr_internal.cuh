@@ -151,6 +151,8 @@ struct PackedWeights {
     float* proj_w_lo = nullptr;
     float* att_w_enc_t_hi = nullptr;
     float* att_w_enc_t_lo = nullptr;
+    float* enc_w_hh_hi[4] = {};          // [2, 1024, 256] tf32 split of enc_w_hh (tensor-core recurrence)
+    float* enc_w_hh_lo[4] = {};
     float* att_w_hidden_t = nullptr;     // [128, 512] (W_hidden transposed -> [N, K]) for the query GEMM
     float* att_w_hidden_t_hi = nullptr;
     float* att_w_hidden_t_lo = nullptr;
@@ -266,6 +268,7 @@ struct asr_handle {
     int64_t launches = 0;
     bool timing = false;
     int gemm_mode = 0;           // 0 = CUDA-core fp32 FMA, 1 = tcgen05 3xTF32
+    int rec_mode = 0;            // encoder recurrence: 0 = CUDA-core (register-stationary W_hh), 1 = tcgen05
     cudaEvent_t ev[2 * asr::kStages * 64] = {};
     int n_ev = 0;
     int ev_stage[asr::kStages * 64] = {};
@@ -292,6 +295,10 @@ int launch_pack_rows(asr_handle* h, const float* src, const int* rowmap, int64_t
 int launch_lstm_recurrence(asr_handle* h, int layer, const float* xg, const float* x_in,
                            float* y_packed, float* y_utt, float* h_fin, float* c_fin,
                            cudaStream_t st);
+// tensor-core (tcgen05 3xTF32) variant, encoder_tc.cu
+int launch_lstm_recurrence_tc(asr_handle* h, int layer, const float* xg, const float* x_in,
+                              float* y_packed, float* y_utt, float* h_fin, float* c_fin,
+                              cudaStream_t st);
 int launch_export_padded(asr_handle* h, const float* src_utt, int width, float* dst, int Lmax, int B,
                          const float* pad_row, cudaStream_t st);
 int launch_export_packed_padded(asr_handle* h, const float* src_packed, int width, float* dst,

@@ -391,16 +391,13 @@ __device__ __forceinline__ float block_reduce_sum(float v, float* s_red) {
     return r;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 row_topk_kernel(RowTopkParams p) {
     if (p.ctrl[0] >= 0) return;
     const int r = blockIdx.x;
     if (p.step == 0 && (r % p.k) != 0) return;      // step 0: only the first beam (model.py:862)
     __shared__ float s_red[8];
-    __shared__ int s_hist[256];
-    __shared__ unsigned s_tmax[256];
-    __shared__ unsigned s_prefix;
-    __shared__ int s_krem;
+    __shared__ int s_wcnt[8];
     __shared__ int s_cnt;
     __shared__ float s_cs[kCandCap];
     __shared__ int s_ct[kCandCap];
@@ -412,7 +409,7 @@ row_topk_kernel(RowTopkParams p) {
 #pragma unroll
     for (int i = 0; i < kRowElems; ++i) {
         const int e = tid + 256 * i;
-        v[i] = e < kVocab ? row[e] : -CUDART_INF_F;
+        v[i] = e < kVocab ? __ldg(row + e) : -CUDART_INF_F;
         m = fmaxf(m, v[i]);
     }
     m = block_reduce_max(m, s_red);
@@ -422,90 +419,58 @@ row_topk_kernel(RowTopkParams p) {
     s = block_reduce_sum(s, s_red);
     const float lse = m + logf(s);
     const float bs = p.beam_score[r];
-    unsigned key[kRowElems];
+    float tmf = -CUDART_INF_F;
 #pragma unroll
     for (int i = 0; i < kRowElems; ++i) {
-        const int e = tid + 256 * i;
-        v[i] = __fadd_rn(__fsub_rn(v[i], lse), bs);               // model.py:835-836
-        key[i] = e < kVocab ? ordered_key(v[i]) : 0u;
+        v[i] = __fadd_rn(__fsub_rn(v[i], lse), bs);               // model.py:835-836 (padding stays -inf)
+        tmf = fmaxf(tmf, v[i]);
     }
-
-    // Fast path: the K-th largest of the 256 per-thread maxima is a lower bound of the K-th
-    // largest element (they are K distinct elements), so {key >= that} holds >= K candidates and,
-    // for any non-degenerate row, only a few more than K.
-    unsigned tm = 0u;
-#pragma unroll
-    for (int i = 0; i < kRowElems; ++i) tm = max(tm, key[i]);
-    s_tmax[tid] = tm;
+    // Threshold: the K-th largest of the 256 per-thread maxima is a lower bound of the K-th largest
+    // element (they are K distinct elements), so {x >= threshold} holds >= K candidates and, for
+    // any non-degenerate row, only a few more.  Found by a 32-step bisection on the ordered key
+    // with __syncthreads_count (one barrier-with-popcount per bit, almost no instructions).
+    const unsigned tm = ordered_key(tmf);
+    unsigned kth = 0u;
+#pragma unroll 1
+    for (int bit = 31; bit >= 0; --bit) {
+        const unsigned cand = kth | (1u << bit);
+        if (__syncthreads_count(tm >= cand) >= p.K) kth = cand;
+    }
     if (tid == 0) s_cnt = 0;
     __syncthreads();
-    {
-        int rk = 0;
-#pragma unroll 8
-        for (int j = 0; j < 256; ++j) {
-            const unsigned o = s_tmax[j];
-            rk += (o > tm || (o == tm && j < tid)) ? 1 : 0;
-        }
-        if (rk == p.K - 1) s_prefix = tm;
-    }
-    __syncthreads();
-    unsigned kth = s_prefix;
     auto collect = [&]() {
 #pragma unroll
         for (int i = 0; i < kRowElems; ++i) {
-            const int e = tid + 256 * i;
-            if (e < kVocab && key[i] >= kth) {
+            if (ordered_key(v[i]) >= kth && v[i] != -CUDART_INF_F) {
                 const int slot = atomicAdd(&s_cnt, 1);
-                if (slot < kCandCap) { s_cs[slot] = v[i]; s_ct[slot] = e; }
+                if (slot < kCandCap) { s_cs[slot] = v[i]; s_ct[slot] = tid + 256 * i; }
             }
         }
     };
     collect();
     __syncthreads();
     if (s_cnt > kCandCap) {
-        // Slow path (degenerate rows with > kCandCap near-ties): exact 4-pass radix select of the
-        // K-th largest key, 8 bits per pass from the top
-        __syncthreads();
-        if (tid == 0) { s_prefix = 0u; s_krem = p.K; s_cnt = 0; }
-        for (int pass = 0; pass < 4; ++pass) {
-            const int shift = 24 - 8 * pass;
-            s_hist[tid] = 0;
+        // Degenerate row (more than kCandCap values above the threshold): exact K-th largest by
+        // bisection over all elements, then collect again (ties beyond the cap are truncated).
+        kth = 0u;
+#pragma unroll 1
+        for (int bit = 31; bit >= 0; --bit) {
+            const unsigned cand = kth | (1u << bit);
+            int c = 0;
+#pragma unroll
+            for (int i = 0; i < kRowElems; ++i) c += (ordered_key(v[i]) >= cand && v[i] != -CUDART_INF_F) ? 1 : 0;
+            c = __reduce_add_sync(0xffffffffu, c);
             __syncthreads();
-            const unsigned prefix = s_prefix;
-            const unsigned mask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
-    #pragma unroll
-            for (int i = 0; i < kRowElems; ++i) {
-                const int e = tid + 256 * i;
-                if (e < kVocab && (key[i] & mask) == prefix) atomicAdd(&s_hist[(key[i] >> shift) & 255], 1);
-            }
+            if (lane == 0) s_wcnt[warp] = c;
             __syncthreads();
-            if (warp == 0) {
-                // lane owns bins [8*lane, 8*lane+8); suffix sums from the top
-                int loc[8], tot = 0;
-    #pragma unroll
-                for (int b = 0; b < 8; ++b) { loc[b] = s_hist[8 * lane + b]; tot += loc[b]; }
-                int above = 0;     // elements in lanes that own larger bins
-                for (int src = 31; src > 0; --src) {
-                    const int t = __shfl_sync(0xffffffffu, tot, src);
-                    if (lane < src) above += t;
-                }
-                const int krem = s_krem;
-                // the crossing lane: above < krem <= above + tot
-                if (above < krem && krem <= above + tot) {
-                    int cum = above;
-                    for (int b = 7; b >= 0; --b) {
-                        if (cum + loc[b] >= krem) {
-                            s_prefix = prefix | ((unsigned)(8 * lane + b) << shift);
-                            s_krem = krem - cum;
-                            break;
-                        }
-                        cum += loc[b];
-                    }
-                }
-            }
-            __syncthreads();
+            int tot = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) tot += s_wcnt[w];
+            if (tot >= p.K) kth = cand;
         }
-        kth = s_prefix;
+        __syncthreads();
+        if (tid == 0) s_cnt = 0;
+        __syncthreads();
         collect();
         __syncthreads();
     }
