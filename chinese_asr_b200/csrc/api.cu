@@ -534,6 +534,11 @@ int asr_reserve(asr_handle* h, int max_utts, int64_t max_rows, int max_beam, int
         ASR_TRY(dev_alloc_t(pool, &w.dc[i], R * kDecH));
         ASR_TRY(dev_alloc_t(pool, &w.dctx[i], R * kEnc));
     }
+    {
+        // tensor-core recurrence staging: 2 directions x ceil(max_utts / 16) chunks x 8 CTAs x 8 KB
+        w.rec_stage_ctas = (size_t)2 * ((max_utts + 15) / 16) * 8;
+        ASR_TRY(dev_alloc_t(pool, &w.rec_stage, w.rec_stage_ctas * 2048));
+    }
     ASR_TRY(dev_alloc_t(pool, &w.logits, R * kVocab));
     ASR_TRY(dev_alloc_t(pool, &w.att_q, R * kAtt));
     ASR_TRY(dev_alloc_t(pool, &w.att_part, (size_t)max_utts * 8 * max_beam * 514));

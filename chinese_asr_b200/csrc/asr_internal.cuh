@@ -235,6 +235,8 @@ struct Workspace {
     int* tr_tok = nullptr;       // [max_len, B, k]
     int* top_done = nullptr;     // [B]
     int* ctrl = nullptr;         // [8]: 0 stop_step(-1), 1 done_count, 2 ticket, 3 steps_run
+    float* rec_stage = nullptr;  // tensor-core recurrence: per CTA 8 KB image of its new h slice (hi | lo)
+    size_t rec_stage_ctas = 0;
     // greedy
     float* g_accum = nullptr;    // [B]
     int* g_finished = nullptr;   // [B]

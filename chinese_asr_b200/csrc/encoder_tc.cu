@@ -5,17 +5,20 @@
 // [32j, 32j+32) = 128 gate columns), but the per-step product runs on the 5th-gen tensor cores with
 // the operands "swapped" so that the 128 gate columns fill the MMA M dimension and the batch rows
 // are the (small) N dimension:
-//        D[128 gate cols, NB rows] = W_slice[128, 256] * h[NB, 256]^T
-//   * W_hi (tf32-rounded W_hh slice) is STATIONARY IN SHARED MEMORY (128 KB, K-major SWIZZLE_128B),
+//        D[128 gate cols, rows] = W_slice[128, 256] * h[rows, 256]^T
+//   * W_hi (tf32-rounded W_hh slice) is STATIONARY IN SHARED MEMORY (128 KB, K-major SWIZZLE_128B);
 //     W_lo (the tf32 residual) is STATIONARY IN TENSOR MEMORY (128 lanes x 256 columns) and is fed
-//     as the TMEM A operand; both are loaded once per layer.
-//   * h_hi / h_lo (NB x 256 each) live in shared memory in the UMMA K-major layout; every step each
-//     CTA writes its 32-unit slice of the new h (already split into hi / lo) straight into the
-//     operand tiles of all 8 CTAs through DSMEM, so the next step's MMA needs no repacking.
-//   * per step: 32 K-steps x 3 products (W_lo*h_hi, W_hi*h_lo, W_hi*h_hi) accumulate in TMEM (fp32),
-//     tcgen05.commit -> mbarrier, tcgen05.ld -> gate non-linearities / cell update in registers.
-//   * two split-phase cluster barriers per step: (A) every CTA's MMAs have finished reading h_t,
-//     (B) every CTA's slice of h_{t+1} has landed everywhere.
+//     as the TMEM A operand.  Both are loaded once per layer.
+//   * the B operand tile holds [h_hi rows | h_lo rows] (2*NB rows x 256, UMMA K-major layout), so per
+//     K-step one N=2*NB MMA gives W_hi*h_hi and W_hi*h_lo in adjacent accumulator column blocks and
+//     one N=NB MMA (A from TMEM) adds W_lo*h_hi: 64 tcgen05.mma per step, fp32 accumulation in TMEM.
+//   * exchange of the new h: every CTA writes the 2*NB x 32 image of its slice (already split
+//     into hi / lo and already in the swizzled operand layout) to a small global staging buffer and
+//     issues ONE multicast bulk copy (cp.async.bulk ... .multicast::cluster) that lands it in the
+//     operand tiles of all 8 CTAs and signals their `h_ready` mbarriers (complete_tx).
+//   * no cluster-wide barrier in the loop: "every CTA's MMAs of this step are done" is a multicast
+//     tcgen05.commit onto an mbarrier with count 8; "h_{t+1} is complete" is the tx-count of
+//     `h_ready`.
 #include <cooperative_groups.h>
 
 #include "asr_internal.cuh"
@@ -28,8 +31,25 @@ namespace asr {
 using namespace tcx;
 
 __device__ __forceinline__ float sigmoid_tc(float x) { return 1.f / (1.f + expf(-x)); }
-__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
-__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(smem_u32(bar)), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_multicast(void* dst_smem, const void* src_gmem, uint32_t bytes,
+                                                   uint64_t* bar, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+        "[%0], [%1], %2, [%3], %4;"
+        ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+        : "memory");
+}
 
 struct RecTcParams {
     const float* xg;        // [rows, 2048] permuted gate pre-activations (bias included)
@@ -40,6 +60,7 @@ struct RecTcParams {
     float* y_utt;
     float* h_fin;
     float* c_fin;
+    float* stage;           // [gridDim.x][2048] global staging images
     const int* len_sorted;
     const int* toff;
     const int* uoff;
@@ -52,18 +73,18 @@ constexpr int kSlabA = 128 * 128;          // bytes: 128 rows x 32 fp32
 template <int NB>
 __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(256, 1)
 lstm_rec_tc_kernel(RecTcParams p) {
-    constexpr int kSlabB = NB * 128;        // bytes
+    constexpr int kSlabB = 2 * NB * 128;    // bytes: [NB hi rows | NB lo rows] x 32 fp32
     constexpr int P = NB / 8;               // rows per gate thread (all 8 warps run the gate phase)
     constexpr int HC = NB / 2;              // accumulator columns read per warp
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* A_hi = smem;                                   // 8 slabs x 16 KB
-    uint8_t* B_hi = A_hi + 8 * kSlabA;                      // 8 slabs x NB*128 B
-    uint8_t* B_lo = B_hi + 8 * kSlabB;
-    float* red = reinterpret_cast<float*>(B_lo + 8 * kSlabB);    // [NB][128]
-    uint64_t* mbar_done = reinterpret_cast<uint64_t*>(red + NB * 128);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar_done + 1);
-    int* s_len = reinterpret_cast<int*>(tmem_slot + 1);           // [NB]
+    uint8_t* Bt = A_hi + 8 * kSlabA;                        // 8 slabs x kSlabB
+    float* red = reinterpret_cast<float*>(Bt + 8 * kSlabB); // [NB][128]
+    uint64_t* mma_done = reinterpret_cast<uint64_t*>(red + NB * 128);
+    uint64_t* h_ready = mma_done + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h_ready + 1);
+    int* s_len = reinterpret_cast<int*>(tmem_slot + 1);     // [NB]
 
     cg::cluster_group cluster = cg::this_cluster();
     const int j = (int)cluster.block_rank();
@@ -73,10 +94,13 @@ lstm_rec_tc_kernel(RecTcParams p) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int r0 = chunk * NB;
     const int nrows = min(NB, p.B - r0);
+    float* stage = p.stage + (size_t)blockIdx.x * 2048;     // this CTA's slice image (kSlabB bytes used)
 
     // ---- one-time setup ------------------------------------------------------------------------
-    for (int i = tid; i < (2 * 8 * kSlabB) / 16; i += 256)
-        reinterpret_cast<float4*>(B_hi)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < (8 * kSlabB) / 16; i += 256)
+        reinterpret_cast<float4*>(Bt)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < kSlabB / 16; i += 256)
+        reinterpret_cast<float4*>(stage)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     {
         const float* wsrc = p.whh_hi + ((size_t)dir * kGates + j * 128) * kEncH;
         for (int idx = tid; idx < 128 * 64; idx += 256) {
@@ -86,13 +110,17 @@ lstm_rec_tc_kernel(RecTcParams p) {
         }
     }
     if (tid < NB) s_len[tid] = tid < nrows ? p.len_sorted[r0 + tid] : 0;
-    if (tid == 0) { mbar_init(mbar_done, 1); mbar_fence_init(); }
+    if (tid == 0) {
+        mbar_init(mma_done, 8);        // one multicast commit from each CTA of the cluster
+        mbar_init(h_ready, 1);         // one arrive.expect_tx by this CTA + 8 multicast bulk copies
+        mbar_fence_init();
+    }
     if (warp == 4) tmem_alloc<512>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_d = tmem_base + 256;               // accumulator columns [256, 256 + NB)
+    const uint32_t tmem_d = tmem_base + 256;               // accumulator columns [256, 256 + 2*NB)
     if (warp < 4) {
         // W_lo slice -> TMEM lanes (gate column m = 32*warp + lane), columns [0, 256)
         const float* wsrc = p.whh_lo + ((size_t)dir * kGates + j * 128 + 32 * warp + lane) * kEncH;
@@ -109,6 +137,7 @@ lstm_rec_tc_kernel(RecTcParams p) {
         }
         tmem_wait_st();
     }
+    __threadfence();
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -120,10 +149,11 @@ lstm_rec_tc_kernel(RecTcParams p) {
 #pragma unroll
     for (int q = 0; q < P; ++q) { c_reg[q] = 0.f; h_reg[q] = 0.f; }
 
-    cluster.sync();
+    cluster.sync();      // every CTA's barriers / tiles are initialised before any multicast arrives
 
-    const uint32_t a_base = smem_u32(A_hi), bh_base = smem_u32(B_hi), bl_base = smem_u32(B_lo);
-    constexpr uint32_t idesc = idesc_tf32(128, NB);
+    const uint32_t a_base = smem_u32(A_hi), bt_base = smem_u32(Bt);
+    constexpr uint32_t idesc2 = idesc_tf32(128, 2 * NB);
+    constexpr uint32_t idesc1 = idesc_tf32(128, NB);
 
     for (int s = 0; s < Lc; ++s) {
         const int t = dir == 0 ? s : Lc - 1 - s;
@@ -131,125 +161,107 @@ lstm_rec_tc_kernel(RecTcParams p) {
         for (int i = 0; i < nrows; ++i) nact += (s_len[i] > t) ? 1 : 0;
         const int row_t = p.toff[t] + r0;
 
-        // (a) one thread issues the 96 MMAs of this step
+        // (a) one thread issues the 64 MMAs of this step once h_t has landed
         if (warp == 4) {
             if (lane == 0) {
-                fence_proxy_async();
+                if (s > 0) mbar_wait(h_ready, (uint32_t)((s - 1) & 1));
                 tc_fence_after();
 #pragma unroll 4
                 for (int kk = 0; kk < 32; ++kk) {
                     const int sl = kk >> 2, q = kk & 3;
                     const uint64_t dA = kmajor_sw128_desc(a_base + sl * kSlabA) + (uint64_t)(2 * q);
-                    const uint64_t dBh = kmajor_sw128_desc(bh_base + sl * kSlabB) + (uint64_t)(2 * q);
-                    const uint64_t dBl = kmajor_sw128_desc(bl_base + sl * kSlabB) + (uint64_t)(2 * q);
-                    umma_tf32_ts(tmem_d, tmem_base + (uint32_t)(8 * kk), dBh, idesc, kk > 0 ? 1u : 0u);
-                    umma_tf32_ss(tmem_d, dA, dBl, idesc, 1u);
-                    umma_tf32_ss(tmem_d, dA, dBh, idesc, 1u);
+                    const uint64_t dB = kmajor_sw128_desc(bt_base + sl * kSlabB) + (uint64_t)(2 * q);
+                    umma_tf32_ss(tmem_d, dA, dB, idesc2, kk > 0 ? 1u : 0u);          // W_hi * [h_hi | h_lo]
+                    umma_tf32_ts(tmem_d, tmem_base + (uint32_t)(8 * kk), dB, idesc1, 1u);   // + W_lo * h_hi
                 }
-                umma_commit(mbar_done);
+                umma_commit_mc(mma_done, (uint16_t)0xFF);
             }
             __syncwarp();
         }
 
-        // (b) gate threads prefetch this step's input-projection pre-activations
+        // (b) prefetch this step's input-projection pre-activations
         float xi[P], xf[P], xgg[P], xo[P];
-        {
-#pragma unroll
-            for (int q = 0; q < P; ++q) {
-                const int i = warp + 8 * q;
-                xi[q] = xf[q] = xgg[q] = xo[q] = 0.f;
-                if (i < nact) {
-                    const float* g = p.xg + (size_t)(row_t + i) * (2 * kGates) + dir * kGates + j * 128 + uu;
-                    xi[q] = __ldg(g);
-                    xf[q] = __ldg(g + 32);
-                    xgg[q] = __ldg(g + 64);
-                    xo[q] = __ldg(g + 96);
-                }
-            }
-        }
-
-        // (c) wait for this CTA's accumulator, then tell the cluster our MMAs are done reading h_t
-        mbar_wait(mbar_done, (uint32_t)(s & 1));
-        tc_fence_after();
-        cluster_arrive();                                           // barrier A (arrive)
-
-        float hn[P];
-        {
-            // accumulator rows (gate column m = 32*(warp&3) + lane), columns [half*HC, half*HC + HC)
-            // -> red[row][m]; warps w and w+4 share a TMEM lane quarter and split the columns
-            uint32_t d[HC];
-            const int qd = warp & 3, half = warp >> 2;
-            const uint32_t taddr = tmem_d + ((uint32_t)(32 * qd) << 16) + (uint32_t)(half * HC);
-            if (HC == 16) tmem_ld16(taddr, d);
-            else tmem_ld8(taddr, d);
-            const int m = 32 * qd + lane;
-#pragma unroll
-            for (int n = 0; n < HC; ++n) red[(half * HC + n) * 128 + m] = __uint_as_float(d[n]);
-            tc_fence_before();
-            __syncthreads();
-#pragma unroll
-            for (int q = 0; q < P; ++q) {
-                const int i = warp + 8 * q;
-                hn[q] = 0.f;
-                if (i < nact) {
-                    const float* rr = red + i * 128 + uu;
-                    const float gi = xi[q] + rr[0];
-                    const float gf = xf[q] + rr[32];
-                    const float gg = xgg[q] + rr[64];
-                    const float go = xo[q] + rr[96];
-                    const float c = sigmoid_tc(gf) * c_reg[q] + sigmoid_tc(gi) * tanhf(gg);
-                    const float hh = sigmoid_tc(go) * tanhf(c);
-                    c_reg[q] = c;
-                    h_reg[q] = hh;
-                    hn[q] = hh;
-                    const size_t row = (size_t)(row_t + i);
-                    const int ocol = dir * kEncH + 32 * j + uu;
-                    float y = hh;
-                    if (p.x_in) y += p.x_in[row * kEnc + ocol];
-                    if (p.y_packed) p.y_packed[row * kEnc + ocol] = y;
-                    if (p.y_utt) p.y_utt[(size_t)(p.uoff[r0 + i] + t) * kEnc + ocol] = y;
-                }
-            }
-        }
-        cluster_wait();                                             // barrier A (wait)
-
-        {
-            // broadcast the new h slice (split hi / lo) into the operand tiles of all 8 CTAs
-#pragma unroll
-            for (int q = 0; q < P; ++q) {
-                const int i = warp + 8 * q;
-                if (i < nact) {
-                    const float hi = rn_tf32(hn[q]);
-                    const float lo = rn_tf32(hn[q] - hi);
-                    const uint32_t off = (uint32_t)(j * kSlabB) + sw128_offset(i, uu);
-                    float* ph = reinterpret_cast<float*>(B_hi + off);
-                    float* pl = reinterpret_cast<float*>(B_lo + off);
-#pragma unroll
-                    for (int rk = 0; rk < 8; ++rk) {
-                        *cluster.map_shared_rank(ph, rk) = hi;
-                        *cluster.map_shared_rank(pl, rk) = lo;
-                    }
-                }
-            }
-            fence_proxy_async();
-        }
-        cluster_arrive();                                           // barrier B
-        cluster_wait();
-    }
-
-    {
 #pragma unroll
         for (int q = 0; q < P; ++q) {
             const int i = warp + 8 * q;
-            if (i < nrows) {
+            xi[q] = xf[q] = xgg[q] = xo[q] = 0.f;
+            if (i < nact) {
+                const float* g = p.xg + (size_t)(row_t + i) * (2 * kGates) + dir * kGates + j * 128 + uu;
+                xi[q] = __ldg(g);
+                xf[q] = __ldg(g + 32);
+                xgg[q] = __ldg(g + 64);
+                xo[q] = __ldg(g + 96);
+            }
+        }
+
+        // (c) all 8 CTAs' MMAs of this step are complete: the accumulator is final and every
+        //     operand tile of the cluster may be overwritten
+        mbar_wait(mma_done, (uint32_t)(s & 1));
+        tc_fence_after();
+        {
+            // accumulator rows (gate column m = 32*(warp&3) + lane); warps w and w+4 share a TMEM lane
+            // quarter and split the columns.  D = cols[n] (W_hi h_hi + W_lo h_hi) + cols[NB+n] (W_hi h_lo)
+            uint32_t d1[HC], d2[HC];
+            const int qd = warp & 3, half = warp >> 2;
+            const uint32_t taddr = tmem_d + ((uint32_t)(32 * qd) << 16) + (uint32_t)(half * HC);
+            if (HC == 16) { tmem_ld16(taddr, d1); tmem_ld16(taddr + NB, d2); }
+            else { tmem_ld8(taddr, d1); tmem_ld8(taddr + NB, d2); }
+            const int m = 32 * qd + lane;
+#pragma unroll
+            for (int n = 0; n < HC; ++n)
+                red[(half * HC + n) * 128 + m] = __uint_as_float(d1[n]) + __uint_as_float(d2[n]);
+        }
+        tc_fence_before();
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < P; ++q) {
+            const int i = warp + 8 * q;
+            if (i < nact) {
+                const float* rr = red + i * 128 + uu;
+                const float gi = xi[q] + rr[0];
+                const float gf = xf[q] + rr[32];
+                const float gg = xgg[q] + rr[64];
+                const float go = xo[q] + rr[96];
+                const float c = sigmoid_tc(gf) * c_reg[q] + sigmoid_tc(gi) * tanhf(gg);
+                const float hh = sigmoid_tc(go) * tanhf(c);
+                c_reg[q] = c;
+                h_reg[q] = hh;
+                // slice image in the operand layout: hi row i, lo row NB + i, column uu of K-slab j
+                const float hi = rn_tf32(hh);
+                const float lo = rn_tf32(hh - hi);
+                const uint32_t off = sw128_offset(i, uu) >> 2;
+                stage[off] = hi;
+                stage[NB * 32 + off] = lo;
+                const size_t row = (size_t)(row_t + i);
                 const int ocol = dir * kEncH + 32 * j + uu;
-                p.h_fin[(size_t)(r0 + i) * kEnc + ocol] = h_reg[q];
-                p.c_fin[(size_t)(r0 + i) * kEnc + ocol] = c_reg[q];
+                float y = hh;
+                if (p.x_in) y += p.x_in[row * kEnc + ocol];
+                if (p.y_packed) p.y_packed[row * kEnc + ocol] = y;
+                if (p.y_utt) p.y_utt[(size_t)(p.uoff[r0 + i] + t) * kEnc + ocol] = y;
+            }
+        }
+        if (s + 1 < Lc) {
+            __threadfence();           // the image is visible at L2 ...
+            fence_proxy_async();       // ... and ordered before the async-proxy bulk read
+            __syncthreads();
+            if (tid == 0) {
+                mbar_expect_tx(h_ready, 8u * (uint32_t)kSlabB);
+                bulk_g2s_multicast(Bt + j * kSlabB, stage, (uint32_t)kSlabB, h_ready, (uint16_t)0xFF);
             }
         }
     }
+
+#pragma unroll
+    for (int q = 0; q < P; ++q) {
+        const int i = warp + 8 * q;
+        if (i < nrows) {
+            const int ocol = dir * kEncH + 32 * j + uu;
+            p.h_fin[(size_t)(r0 + i) * kEnc + ocol] = h_reg[q];
+            p.c_fin[(size_t)(r0 + i) * kEnc + ocol] = c_reg[q];
+        }
+    }
     tc_fence_before();
-    cluster.sync();                                     // nobody may exit while peers can still write to it
+    cluster.sync();                                     // nobody exits while peers may still signal it
     if (warp == 4) {
         tc_fence_after();
         tmem_dealloc<512>(tmem_base);
@@ -258,7 +270,7 @@ lstm_rec_tc_kernel(RecTcParams p) {
 
 template <int NB>
 static int launch_tc(const RecTcParams& p, cudaStream_t st) {
-    const size_t smem = 8 * (size_t)kSlabA + 16 * (size_t)NB * 128 + (size_t)NB * 128 * 4 + 1024 + 64 + NB * 4;
+    const size_t smem = 8 * (size_t)kSlabA + 8 * (size_t)(2 * NB * 128) + (size_t)NB * 128 * 4 + 1024 + 64 + NB * 4;
     static bool attr = false;
     if (!attr) {
         ASR_CUDA(cudaFuncSetAttribute(lstm_rec_tc_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -281,12 +293,14 @@ int launch_lstm_recurrence_tc(asr_handle* h, int layer, const float* xg, const f
     p.y_utt = y_utt;
     p.h_fin = h_fin;
     p.c_fin = c_fin;
+    p.stage = h->ws.rec_stage;
     p.len_sorted = m.d_len_sorted;
     p.toff = m.d_toff;
     p.uoff = m.d_uoff_sorted;
     p.B = m.B;
     const int NB = m.B > 128 ? 32 : 16;
     p.nchunks = (m.B + NB - 1) / NB;
+    if ((size_t)2 * p.nchunks * 8 > h->ws.rec_stage_ctas) { set_error("recurrence staging too small"); return ASR_ERR_CAPACITY; }
     if (NB == 32) ASR_TRY(launch_tc<32>(p, st));
     else ASR_TRY(launch_tc<16>(p, st));
     h->launches++;
