@@ -20,6 +20,7 @@
 //     tcgen05.commit onto an mbarrier with count 8; "h_{t+1} is complete" is the tx-count of
 //     `h_ready`.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "asr_internal.cuh"
 #include "tc_common.cuh"
@@ -30,7 +31,10 @@ namespace asr {
 
 using namespace tcx;
 
-__device__ __forceinline__ float sigmoid_tc(float x) { return 1.f / (1.f + expf(-x)); }
+// fast activations: ex2.approx + approximate division, absolute error < 1e-6 (the 3xTF32 products
+// bound the overall accuracy of this kernel at ~1e-5)
+__device__ __forceinline__ float sigmoid_tc(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float tanh_tc(float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); }
 
 __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
     asm volatile(
@@ -66,6 +70,7 @@ struct RecTcParams {
     const int* uoff;
     int B;
     int nchunks;
+    long long* dbg;         // optional [steps][8] clock64 timeline of CTA 0 (nullptr = off)
 };
 
 constexpr int kSlabA = 128 * 128;          // bytes: 128 rows x 32 fp32
@@ -120,7 +125,7 @@ lstm_rec_tc_kernel(RecTcParams p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_d = tmem_base + 256;               // accumulator columns [256, 256 + 2*NB)
+    const uint32_t tmem_d = tmem_base + 256;               // accumulator columns [256, 256 + 4*NB): two (hi | lo) sets
     if (warp < 4) {
         // W_lo slice -> TMEM lanes (gate column m = 32*warp + lane), columns [0, 256)
         const float* wsrc = p.whh_lo + ((size_t)dir * kGates + j * 128 + 32 * warp + lane) * kEncH;
@@ -151,7 +156,7 @@ lstm_rec_tc_kernel(RecTcParams p) {
 
     cluster.sync();      // every CTA's barriers / tiles are initialised before any multicast arrives
 
-    const uint32_t a_base = smem_u32(A_hi), bt_base = smem_u32(Bt);
+    const uint64_t dA0 = kmajor_sw128_desc(smem_u32(A_hi)), dB0 = kmajor_sw128_desc(smem_u32(Bt));
     constexpr uint32_t idesc2 = idesc_tf32(128, 2 * NB);
     constexpr uint32_t idesc1 = idesc_tf32(128, NB);
 
@@ -166,26 +171,32 @@ lstm_rec_tc_kernel(RecTcParams p) {
             if (lane == 0) {
                 if (s > 0) mbar_wait(h_ready, (uint32_t)((s - 1) & 1));
                 tc_fence_after();
-#pragma unroll 4
+                if (p.dbg && blockIdx.x == 0) p.dbg[s * 8 + 0] = clock64();
+#pragma unroll
                 for (int kk = 0; kk < 32; ++kk) {
-                    const int sl = kk >> 2, q = kk & 3;
-                    const uint64_t dA = kmajor_sw128_desc(a_base + sl * kSlabA) + (uint64_t)(2 * q);
-                    const uint64_t dB = kmajor_sw128_desc(bt_base + sl * kSlabB) + (uint64_t)(2 * q);
-                    umma_tf32_ss(tmem_d, dA, dB, idesc2, kk > 0 ? 1u : 0u);          // W_hi * [h_hi | h_lo]
-                    umma_tf32_ts(tmem_d, tmem_base + (uint32_t)(8 * kk), dB, idesc1, 1u);   // + W_lo * h_hi
+                    // descriptors differ from the slab-0 ones by compile-time constants only
+                    const uint64_t dA = dA0 + (uint64_t)(((kk >> 2) * kSlabA + (kk & 3) * 32) >> 4);
+                    const uint64_t dB = dB0 + (uint64_t)(((kk >> 2) * kSlabB + (kk & 3) * 32) >> 4);
+                    // two independent accumulators (even / odd K-steps) halve the dependent-MMA chain
+                    const uint32_t dacc = tmem_d + (uint32_t)((kk & 1) * 2 * NB);
+                    umma_tf32_ss(dacc, dA, dB, idesc2, kk > 1 ? 1u : 0u);            // W_hi * [h_hi | h_lo]
+                    umma_tf32_ts(dacc, tmem_base + (uint32_t)(8 * kk), dB, idesc1, 1u);     // + W_lo * h_hi
                 }
                 umma_commit_mc(mma_done, (uint16_t)0xFF);
+                if (p.dbg && blockIdx.x == 0) p.dbg[s * 8 + 1] = clock64();
             }
             __syncwarp();
         }
 
         // (b) prefetch this step's input-projection pre-activations
-        float xi[P], xf[P], xgg[P], xo[P];
+        float xi[P], xf[P], xgg[P], xo[P], xres[P], yv[P];
+        const int ocol = dir * kEncH + 32 * j + uu;
 #pragma unroll
         for (int q = 0; q < P; ++q) {
             const int i = warp + 8 * q;
-            xi[q] = xf[q] = xgg[q] = xo[q] = 0.f;
+            xi[q] = xf[q] = xgg[q] = xo[q] = xres[q] = yv[q] = 0.f;
             if (i < nact) {
+                if (p.x_in) xres[q] = __ldg(p.x_in + (size_t)(row_t + i) * kEnc + ocol);
                 const float* g = p.xg + (size_t)(row_t + i) * (2 * kGates) + dir * kGates + j * 128 + uu;
                 xi[q] = __ldg(g);
                 xf[q] = __ldg(g + 32);
@@ -198,21 +209,29 @@ lstm_rec_tc_kernel(RecTcParams p) {
         //     operand tile of the cluster may be overwritten
         mbar_wait(mma_done, (uint32_t)(s & 1));
         tc_fence_after();
+        if (p.dbg && blockIdx.x == 0 && tid == 0) p.dbg[s * 8 + 2] = clock64();
         {
             // accumulator rows (gate column m = 32*(warp&3) + lane); warps w and w+4 share a TMEM lane
             // quarter and split the columns.  D = cols[n] (W_hi h_hi + W_lo h_hi) + cols[NB+n] (W_hi h_lo)
-            uint32_t d1[HC], d2[HC];
+            uint32_t d1[HC], d2[HC], d3[HC], d4[HC];
             const int qd = warp & 3, half = warp >> 2;
             const uint32_t taddr = tmem_d + ((uint32_t)(32 * qd) << 16) + (uint32_t)(half * HC);
-            if (HC == 16) { tmem_ld16(taddr, d1); tmem_ld16(taddr + NB, d2); }
-            else { tmem_ld8(taddr, d1); tmem_ld8(taddr + NB, d2); }
+            if (HC == 16) {
+                tmem_ld16(taddr, d1); tmem_ld16(taddr + NB, d2);
+                tmem_ld16(taddr + 2 * NB, d3); tmem_ld16(taddr + 3 * NB, d4);
+            } else {
+                tmem_ld8(taddr, d1); tmem_ld8(taddr + NB, d2);
+                tmem_ld8(taddr + 2 * NB, d3); tmem_ld8(taddr + 3 * NB, d4);
+            }
             const int m = 32 * qd + lane;
 #pragma unroll
             for (int n = 0; n < HC; ++n)
-                red[(half * HC + n) * 128 + m] = __uint_as_float(d1[n]) + __uint_as_float(d2[n]);
+                red[(half * HC + n) * 128 + m] = (__uint_as_float(d1[n]) + __uint_as_float(d3[n])) +
+                                                 (__uint_as_float(d2[n]) + __uint_as_float(d4[n]));
         }
         tc_fence_before();
         __syncthreads();
+        if (p.dbg && blockIdx.x == 0 && tid == 0) p.dbg[s * 8 + 3] = clock64();
 #pragma unroll
         for (int q = 0; q < P; ++q) {
             const int i = warp + 8 * q;
@@ -222,8 +241,8 @@ lstm_rec_tc_kernel(RecTcParams p) {
                 const float gf = xf[q] + rr[32];
                 const float gg = xgg[q] + rr[64];
                 const float go = xo[q] + rr[96];
-                const float c = sigmoid_tc(gf) * c_reg[q] + sigmoid_tc(gi) * tanhf(gg);
-                const float hh = sigmoid_tc(go) * tanhf(c);
+                const float c = sigmoid_tc(gf) * c_reg[q] + sigmoid_tc(gi) * tanh_tc(gg);
+                const float hh = sigmoid_tc(go) * tanh_tc(c);
                 c_reg[q] = c;
                 h_reg[q] = hh;
                 // slice image in the operand layout: hi row i, lo row NB + i, column uu of K-slab j
@@ -232,21 +251,29 @@ lstm_rec_tc_kernel(RecTcParams p) {
                 const uint32_t off = sw128_offset(i, uu) >> 2;
                 stage[off] = hi;
                 stage[NB * 32 + off] = lo;
-                const size_t row = (size_t)(row_t + i);
-                const int ocol = dir * kEncH + 32 * j + uu;
-                float y = hh;
-                if (p.x_in) y += p.x_in[row * kEnc + ocol];
-                if (p.y_packed) p.y_packed[row * kEnc + ocol] = y;
-                if (p.y_utt) p.y_utt[(size_t)(p.uoff[r0 + i] + t) * kEnc + ocol] = y;
+                yv[q] = hh + xres[q];                  // residual add (util.py:1284-1291)
             }
         }
+        if (p.dbg && blockIdx.x == 0 && tid == 0) p.dbg[s * 8 + 4] = clock64();
         if (s + 1 < Lc) {
             __threadfence();           // the image is visible at L2 ...
             fence_proxy_async();       // ... and ordered before the async-proxy bulk read
             __syncthreads();
+            if (p.dbg && blockIdx.x == 0 && tid == 0) p.dbg[s * 8 + 5] = clock64();
             if (tid == 0) {
                 mbar_expect_tx(h_ready, 8u * (uint32_t)kSlabB);
                 bulk_g2s_multicast(Bt + j * kSlabB, stage, (uint32_t)kSlabB, h_ready, (uint16_t)0xFF);
+                if (p.dbg && blockIdx.x == 0) p.dbg[s * 8 + 6] = clock64();
+            }
+        }
+        // layer output stores are off the critical path: issued after the exchange has been started
+#pragma unroll
+        for (int q = 0; q < P; ++q) {
+            const int i = warp + 8 * q;
+            if (i < nact) {
+                const size_t row = (size_t)(row_t + i);
+                if (p.y_packed) p.y_packed[row * kEnc + ocol] = yv[q];
+                if (p.y_utt) p.y_utt[(size_t)(p.uoff[r0 + i] + t) * kEnc + ocol] = yv[q];
             }
         }
     }
@@ -301,8 +328,33 @@ int launch_lstm_recurrence_tc(asr_handle* h, int layer, const float* xg, const f
     const int NB = m.B > 128 ? 32 : 16;
     p.nchunks = (m.B + NB - 1) / NB;
     if ((size_t)2 * p.nchunks * 8 > h->ws.rec_stage_ctas) { set_error("recurrence staging too small"); return ASR_ERR_CAPACITY; }
+    static const bool want_dbg = getenv("ASR_B200_REC_DBG") != nullptr;
+    long long* dbg = nullptr;
+    if (want_dbg) { ASR_CUDA(cudaMalloc(&dbg, sizeof(long long) * 8 * 4096)); ASR_CUDA(cudaMemset(dbg, 0, sizeof(long long) * 8 * 4096)); }
+    p.dbg = dbg;
     if (NB == 32) ASR_TRY(launch_tc<32>(p, st));
     else ASR_TRY(launch_tc<16>(p, st));
+    if (dbg) {
+        std::vector<long long> hbuf(8 * 4096);
+        ASR_CUDA(cudaStreamSynchronize(st));
+        ASR_CUDA(cudaMemcpy(hbuf.data(), dbg, sizeof(long long) * hbuf.size(), cudaMemcpyDeviceToHost));
+        cudaFree(dbg);
+        const int L = m.len_sorted[0];
+        double acc[7] = {};
+        int cnt = 0;
+        for (int s2 = 2; s2 + 1 < L; ++s2, ++cnt) {
+            const long long* a = &hbuf[s2 * 8];
+            acc[0] += (double)(a[1] - a[0]);         // MMA issue
+            acc[1] += (double)(a[2] - a[1]);         // MMA exec + multicast commit
+            acc[2] += (double)(a[3] - a[2]);         // TMEM ld + red + sync
+            acc[3] += (double)(a[4] - a[3]);         // gates + stores
+            acc[4] += (double)(a[5] - a[4]);         // fences + sync
+            acc[5] += (double)(a[6] - a[5]);         // bulk issue
+            acc[6] += (double)(hbuf[(s2 + 1) * 8] - a[6]);   // exchange latency until next h_ready
+        }
+        fprintf(stderr, "[rec_tc dbg] layer %d NB=%d steps=%d cycles/step: issue %.0f mma+commit %.0f ld+red %.0f gates %.0f fences %.0f bulk-issue %.0f exchange %.0f\n",
+                layer, NB, L, acc[0] / cnt, acc[1] / cnt, acc[2] / cnt, acc[3] / cnt, acc[4] / cnt, acc[5] / cnt, acc[6] / cnt);
+    }
     h->launches++;
     return ASR_OK;
 }
