@@ -163,7 +163,10 @@ static int run_encoder(asr_handle* h, int upto_layer, cudaStream_t st) {
             StageScope sc(h, kStEncRec, st);
             const bool last = layer == 3;
             float* y = w.act[layer & 1];
-            if (h->rec_mode == 1) {
+            if (h->rec_mode == 2) {
+                ASR_TRY(launch_lstm_recurrence_tc3(h, layer, w.xg, layer == 0 ? nullptr : x, y,
+                                                   last ? w.enc : nullptr, w.h0, w.c0, st));
+            } else if (h->rec_mode == 1) {
                 ASR_TRY(launch_lstm_recurrence_tc(h, layer, w.xg, layer == 0 ? nullptr : x, y,
                                                   last ? w.enc : nullptr, w.h0, w.c0, st));
             } else {
@@ -437,6 +440,8 @@ int asr_create(asr_handle** out, const asr_weights* wt, const asr_feature_consts
         const int K = layer == 0 ? kFeat : kEnc;
         if ((rc = split_weight(h, h->w.enc_w_ih[layer], 2 * kGates, K, &h->w.enc_w_ih_hi[layer], &h->w.enc_w_ih_lo[layer])) != ASR_OK) return rc;
         if ((rc = split_weight(h, h->w.enc_w_hh[layer], 2 * kGates, kEncH, &h->w.enc_w_hh_hi[layer], &h->w.enc_w_hh_lo[layer])) != ASR_OK) return rc;
+        if ((rc = dev_alloc_t(pool, &h->w.enc_w_hh_lo_bf[layer], (size_t)2 * kGates * kEncH / 2)) != ASR_OK) return rc;
+        if ((rc = pack_bf16_pairs(h->w.enc_w_hh_lo[layer], h->w.enc_w_hh_lo_bf[layer], (long long)2 * kGates * kEncH / 2)) != ASR_OK) return rc;
     }
     if ((rc = split_weight(h, h->w.dec_w, 4 * kDecH, kDecK, &h->w.dec_w_hi, &h->w.dec_w_lo)) != ASR_OK) return rc;
     if ((rc = split_weight(h, h->w.proj_w, kVocab, kProjK, &h->w.proj_w_hi, &h->w.proj_w_lo)) != ASR_OK) return rc;
@@ -444,15 +449,16 @@ int asr_create(asr_handle** out, const asr_weights* wt, const asr_feature_consts
     const char* env = getenv("ASR_B200_GEMM");
     h->gemm_mode = (env && strcmp(env, "simt") == 0) ? 0 : (env && strcmp(env, "tc") == 0) ? 1 : 0;
     const char* env_rec = getenv("ASR_B200_REC");
-    h->rec_mode = (env_rec && strcmp(env_rec, "tc") == 0) ? 1 : 0;
+    h->rec_mode = (env_rec && strcmp(env_rec, "tc") == 0) ? 1 : (env_rec && strcmp(env_rec, "tc3") == 0) ? 2 : 0;
     *out = h;
     return ASR_OK;
 }
 
 int asr_set_gemm_mode(asr_handle* h, int mode) {
-    if (!h || mode < 0 || mode > 3) { set_error("asr_set_gemm_mode: bad argument"); return ASR_ERR_ARG; }
+    if (!h || mode < 0 || mode > 7) { set_error("asr_set_gemm_mode: bad argument"); return ASR_ERR_ARG; }
     h->gemm_mode = mode & 1;          // bit 0: GEMM stages on tcgen05
-    h->rec_mode = (mode >> 1) & 1;    // bit 1: encoder recurrence on tcgen05
+    // bit 1: encoder recurrence on tcgen05 (W_hi in smem); bit 2: weights fully TMEM-resident
+    h->rec_mode = (mode & 4) ? 2 : ((mode & 2) ? 1 : 0);
     return ASR_OK;
 }
 
@@ -536,7 +542,10 @@ int asr_reserve(asr_handle* h, int max_utts, int64_t max_rows, int max_beam, int
     }
     {
         // tensor-core recurrence staging: 2 directions x ceil(max_utts / 16) chunks x 8 CTAs x 8 KB
-        w.rec_stage_ctas = (size_t)2 * ((max_utts + 15) / 16) * 8;
+        // (encoder_tc.cu), or 2 x max(7, ceil(max_utts / 80)) chunks x 8 CTAs x 25 KB (encoder_tc3.cu)
+        const size_t v2 = (size_t)2 * ((max_utts + 15) / 16) * 8 * 8192;
+        const size_t v3 = (size_t)2 * std::max(7, (max_utts + 79) / 80) * 8 * rec3_stage_bytes_per_cta();
+        w.rec_stage_ctas = (std::max(v2, v3) + 8191) / 8192;      // capacity in 8 KB units
         ASR_TRY(dev_alloc_t(pool, &w.rec_stage, w.rec_stage_ctas * 2048));
     }
     ASR_TRY(dev_alloc_t(pool, &w.logits, R * kVocab));

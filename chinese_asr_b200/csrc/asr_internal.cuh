@@ -153,6 +153,7 @@ struct PackedWeights {
     float* att_w_enc_t_lo = nullptr;
     float* enc_w_hh_hi[4] = {};          // [2, 1024, 256] tf32 split of enc_w_hh (tensor-core recurrence)
     float* enc_w_hh_lo[4] = {};
+    uint32_t* enc_w_hh_lo_bf[4] = {};    // [2, 1024, 128] bf16 pairs of the residual (TMEM-resident recurrence)
     float* att_w_hidden_t = nullptr;     // [128, 512] (W_hidden transposed -> [N, K]) for the query GEMM
     float* att_w_hidden_t_hi = nullptr;
     float* att_w_hidden_t_lo = nullptr;
@@ -301,6 +302,12 @@ int launch_lstm_recurrence(asr_handle* h, int layer, const float* xg, const floa
 int launch_lstm_recurrence_tc(asr_handle* h, int layer, const float* xg, const float* x_in,
                               float* y_packed, float* y_utt, float* h_fin, float* c_fin,
                               cudaStream_t st);
+// weights fully TMEM-resident variant, encoder_tc3.cu
+int launch_lstm_recurrence_tc3(asr_handle* h, int layer, const float* xg, const float* x_in,
+                               float* y_packed, float* y_utt, float* h_fin, float* c_fin,
+                               cudaStream_t st);
+int pack_bf16_pairs(const float* src, uint32_t* dst, long long n_pairs);
+size_t rec3_stage_bytes_per_cta();
 int launch_export_padded(asr_handle* h, const float* src_utt, int width, float* dst, int Lmax, int B,
                          const float* pad_row, cudaStream_t st);
 int launch_export_packed_padded(asr_handle* h, const float* src_packed, int width, float* dst,

@@ -1,0 +1,433 @@
+// Tensor-core LSTM recurrence, weights fully resident in TENSOR MEMORY (rec_mode 2).
+//
+// encoder_tc.cu keeps W_hi in shared memory and re-reads its 128 KB through the UMMA operand path
+// every step (measured: the 64 MMAs of a step are bound by ~64 B/clk of shared-memory operand
+// fetch, ~3.9k cycles).  Here the whole recurrent weight slice of a CTA lives in TMEM:
+//     columns [  0,256) : W_hi  = rn_tf32(W_hh slice)            128 lanes x 256 tf32
+//     columns [256,384) : W_lo  = bf16(W_hh - W_hi), 2 per column 128 lanes x 256 bf16
+//     columns [384,512) : fp32 accumulator D[128 gate cols, NB rows]
+// so shared memory only holds the h operand tiles, which lets one cluster carry up to NB = 80
+// sequences (one round of <= 15 clusters covers 2 directions x 512 sequences).  Per K-step:
+//     D += W_hi (TMEM, tf32) * h_hi^T        tcgen05.mma kind::tf32, A from TMEM
+//     D += W_hi (TMEM, tf32) * h_lo^T        tcgen05.mma kind::tf32, A from TMEM
+//     D += W_lo (TMEM, bf16) * bf16(h)^T     tcgen05.mma kind::f16  (K = 16 per instruction)
+// The W_lo term only needs ~2^-9 relative accuracy (it is 2^-11 of the product), which bf16 gives.
+// Exchange of h_{t+1}: as in encoder_tc.cu - each CTA writes the image of its 32-unit slice
+// ([hi | lo | bf16] rows, already in the swizzled UMMA layouts) to global staging and multicasts it
+// with one cp.async.bulk into the tiles of all 8 CTAs; mbarriers only, no cluster barrier per step.
+#include <cooperative_groups.h>
+#include <cuda_bf16.h>
+#include <stdlib.h>
+
+#include "asr_internal.cuh"
+#include "tc_common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace asr {
+
+using namespace tcx;
+
+namespace rec3 {
+
+__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float tanh_f(float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); }
+
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(smem_u32(bar)), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_multicast(void* dst_smem, const void* src_gmem, uint32_t bytes,
+                                                   uint64_t* bar, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+        "[%0], [%1], %2, [%3], %4;"
+        ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+        : "memory");
+}
+// D[tmem] += A[tmem, bf16] * B[smem desc, bf16]
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// K-major SWIZZLE_64B descriptor (rows of 64 bytes, 8-row / 512-byte atoms)
+__device__ __forceinline__ uint64_t kmajor_sw64_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;
+    return d;
+}
+// byte offset of bf16 element (row, kk in 0..31) inside a [rows x 32 bf16] SWIZZLE_64B K-major slab
+__device__ __forceinline__ uint32_t sw64_offset(int row, int kk) {
+    return (uint32_t)(row * 64 + ((((kk >> 3) ^ ((row >> 1) & 3)) << 4) | ((kk & 7) << 1)));
+}
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+template <int N>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t* r);
+template <>
+__device__ __forceinline__ void tmem_ld_cols<8>(uint32_t taddr, uint32_t* r) { tmem_ld8(taddr, r); }
+template <>
+__device__ __forceinline__ void tmem_ld_cols<16>(uint32_t taddr, uint32_t* r) { tmem_ld16(taddr, r); }
+template <>
+__device__ __forceinline__ void tmem_ld_cols<32>(uint32_t taddr, uint32_t* r) { tmem_ld32(taddr, r); }
+template <>
+__device__ __forceinline__ void tmem_ld_cols<20>(uint32_t taddr, uint32_t* r) {
+    tmem_ld16(taddr, r);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19])
+                 : "r"(taddr + 16));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct Params {
+    const float* xg;            // [rows, 2048] permuted gate pre-activations (bias included)
+    const float* whh_hi;        // [2, 1024, 256] permuted, rn_tf32(W_hh)
+    const uint32_t* whh_lo_bf;  // [2, 1024, 128] permuted, bf16 pairs of (W_hh - hi)
+    const float* x_in;
+    float* y_packed;
+    float* y_utt;
+    float* h_fin;
+    float* c_fin;
+    uint8_t* stage;             // [gridDim.x][kStageBytes] global staging images
+    const int* len_sorted;
+    const int* toff;
+    const int* uoff;
+    int B;
+    int rows_per_chunk;
+    int nchunks;
+    long long* dbg;
+};
+
+constexpr int kStageBytes = 80 * 320;    // per-CTA staging slot (largest NB)
+
+template <int NB>
+__global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(256, 1)
+lstm_rec_tc3_kernel(Params p) {
+    constexpr int PASSES = NB > 64 ? 2 : 1;
+    constexpr int RB = NB / PASSES;          // rows transposed through `red` per pass
+    constexpr int HC = RB / 2;               // accumulator columns read per warp per pass
+    constexpr int P = NB / 8;                // rows per gate thread
+    constexpr int PP = P / PASSES;           // rows per gate thread per pass
+    constexpr int kHi = NB * 128;            // bytes of one hi (or lo) slab
+    constexpr int kBf = NB * 64;             // bytes of one bf16 slab
+    constexpr int kSlab = 2 * kHi + kBf;     // [hi | lo | bf16] of one 32-wide K range
+    static_assert(NB % 16 == 0 && P % PASSES == 0, "NB");
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* T = smem;                                             // 8 slabs x kSlab
+    float* red = reinterpret_cast<float*>(T + 8 * kSlab);          // [RB][128]
+    uint64_t* mma_done = reinterpret_cast<uint64_t*>(red + RB * 128);
+    uint64_t* h_ready = mma_done + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h_ready + 1);
+    int* s_len = reinterpret_cast<int*>(tmem_slot + 1);            // [NB]
+
+    cg::cluster_group cluster = cg::this_cluster();
+    const int j = (int)cluster.block_rank();
+    const int cid = blockIdx.x / 8;
+    const int dir = cid / p.nchunks;
+    const int chunk = cid - dir * p.nchunks;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int r0 = chunk * p.rows_per_chunk;
+    const int nrows = min(p.rows_per_chunk, p.B - r0);
+    uint8_t* stage = p.stage + (size_t)blockIdx.x * kStageBytes;
+
+    // ---- one-time setup ------------------------------------------------------------------------
+    for (int i = tid; i < (8 * kSlab) / 16; i += 256) reinterpret_cast<float4*>(T)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < kSlab / 16; i += 256) reinterpret_cast<float4*>(stage)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid < NB) s_len[tid] = tid < nrows ? p.len_sorted[r0 + tid] : 0;
+    if (tid == 0) {
+        mbar_init(mma_done, 8);
+        mbar_init(h_ready, 1);
+        mbar_fence_init();
+    }
+    if (warp == 4) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_alo = tmem_base + 256;
+    const uint32_t tmem_d = tmem_base + 384;
+    if (warp < 4) {
+        const size_t wrow = (size_t)dir * kGates + j * 128 + 32 * warp + lane;   // gate column of this lane
+        const float* whi = p.whh_hi + wrow * kEncH;
+#pragma unroll 1
+        for (int c0 = 0; c0 < kEncH; c0 += 32) {
+            uint32_t r[32];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 v = *reinterpret_cast<const float4*>(whi + c0 + 4 * q);
+                r[4 * q] = __float_as_uint(v.x); r[4 * q + 1] = __float_as_uint(v.y);
+                r[4 * q + 2] = __float_as_uint(v.z); r[4 * q + 3] = __float_as_uint(v.w);
+            }
+            tmem_st32(tmem_base + ((uint32_t)(32 * warp) << 16) + (uint32_t)c0, r);
+        }
+        const uint32_t* wlo = p.whh_lo_bf + wrow * (kEncH / 2);
+#pragma unroll 1
+        for (int c0 = 0; c0 < kEncH / 2; c0 += 32) {
+            uint32_t r[32];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const uint4 v = *reinterpret_cast<const uint4*>(wlo + c0 + 4 * q);
+                r[4 * q] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
+            }
+            tmem_st32(tmem_alo + ((uint32_t)(32 * warp) << 16) + (uint32_t)c0, r);
+        }
+        tmem_wait_st();
+    }
+    __threadfence();
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const int Lc = s_len[0];
+
+    const int uu = lane;
+    const int ocol = dir * kEncH + 32 * j + uu;
+    float c_reg[P], h_reg[P];
+#pragma unroll
+    for (int q = 0; q < P; ++q) { c_reg[q] = 0.f; h_reg[q] = 0.f; }
+
+    cluster.sync();
+
+    const uint32_t t_base = smem_u32(T);
+    constexpr uint32_t idesc_t = idesc_tf32(128, NB);
+    constexpr uint32_t idesc_b = idesc_bf16(128, NB);
+
+    for (int s = 0; s < Lc; ++s) {
+        const int t = dir == 0 ? s : Lc - 1 - s;
+        int nact = 0;
+        for (int i = 0; i < nrows; ++i) nact += (s_len[i] > t) ? 1 : 0;
+        const int row_t = p.toff[t] + r0;
+
+        if (warp == 4) {
+            if (lane == 0) {
+                if (s > 0) mbar_wait(h_ready, (uint32_t)((s - 1) & 1));
+                tc_fence_after();
+                if (p.dbg && blockIdx.x == 0) p.dbg[s * 8 + 0] = clock64();
+                const uint64_t dHi0 = kmajor_sw128_desc(t_base);
+                const uint64_t dLo0 = kmajor_sw128_desc(t_base + kHi);
+                const uint64_t dBf0 = kmajor_sw64_desc(t_base + 2 * kHi);
+#pragma unroll
+                for (int kk = 0; kk < 32; ++kk) {
+                    const uint64_t adv = (uint64_t)(((kk >> 2) * kSlab + (kk & 3) * 32) >> 4);
+                    umma_tf32_ts(tmem_d, tmem_base + (uint32_t)(8 * kk), dHi0 + adv, idesc_t, kk > 0 ? 1u : 0u);
+                    umma_tf32_ts(tmem_d, tmem_base + (uint32_t)(8 * kk), dLo0 + adv, idesc_t, 1u);
+                    if ((kk & 1) == 0) {
+                        // bf16 K-step kb = kk/2: 16 k's = 8 TMEM columns, 32 bytes of the 64-byte row
+                        const int kb = kk >> 1;
+                        const uint64_t advb = (uint64_t)(((kb >> 1) * kSlab + (kb & 1) * 32) >> 4);
+                        umma_bf16_ts(tmem_d, tmem_alo + (uint32_t)(8 * kb), dBf0 + advb, idesc_b, 1u);
+                    }
+                }
+                umma_commit_mc(mma_done, (uint16_t)0xFF);
+                if (p.dbg && blockIdx.x == 0) p.dbg[s * 8 + 1] = clock64();
+            }
+            __syncwarp();
+        }
+
+        float xi[P], xf[P], xgg[P], xo[P], xres[P], yv[P];
+#pragma unroll
+        for (int q = 0; q < P; ++q) {
+            const int i = warp + 8 * q;
+            xi[q] = xf[q] = xgg[q] = xo[q] = xres[q] = yv[q] = 0.f;
+            if (i < nact) {
+                if (p.x_in) xres[q] = __ldg(p.x_in + (size_t)(row_t + i) * kEnc + ocol);
+                const float* g = p.xg + (size_t)(row_t + i) * (2 * kGates) + dir * kGates + j * 128 + uu;
+                xi[q] = __ldg(g);
+                xf[q] = __ldg(g + 32);
+                xgg[q] = __ldg(g + 64);
+                xo[q] = __ldg(g + 96);
+            }
+        }
+
+        mbar_wait(mma_done, (uint32_t)(s & 1));
+        tc_fence_after();
+        if (p.dbg && blockIdx.x == 0 && tid == 0) p.dbg[s * 8 + 2] = clock64();
+#pragma unroll
+        for (int pass = 0; pass < PASSES; ++pass) {
+            {
+                uint32_t d[HC];
+                const int qd = warp & 3, half = warp >> 2;
+                tmem_ld_cols<HC>(tmem_d + ((uint32_t)(32 * qd) << 16) + (uint32_t)(pass * RB + half * HC), d);
+                const int m = 32 * qd + lane;
+#pragma unroll
+                for (int n = 0; n < HC; ++n) red[(half * HC + n) * 128 + m] = __uint_as_float(d[n]);
+            }
+            tc_fence_before();
+            __syncthreads();
+#pragma unroll
+            for (int qq = 0; qq < PP; ++qq) {
+                const int q = pass * PP + qq;
+                const int i = warp + 8 * q;              // rows [pass*RB, pass*RB + RB)
+                if (i < nact) {
+                    const float* rr = red + (i - pass * RB) * 128 + uu;
+                    const float gi = xi[q] + rr[0];
+                    const float gf = xf[q] + rr[32];
+                    const float gg = xgg[q] + rr[64];
+                    const float go = xo[q] + rr[96];
+                    const float c = sigmoid_f(gf) * c_reg[q] + sigmoid_f(gi) * tanh_f(gg);
+                    const float hh = sigmoid_f(go) * tanh_f(c);
+                    c_reg[q] = c;
+                    h_reg[q] = hh;
+                    const float hi = rn_tf32(hh);
+                    const float lo = rn_tf32(hh - hi);
+                    *reinterpret_cast<float*>(stage + sw128_offset(i, uu)) = hi;
+                    *reinterpret_cast<float*>(stage + kHi + sw128_offset(i, uu)) = lo;
+                    *reinterpret_cast<__nv_bfloat16*>(stage + 2 * kHi + sw64_offset(i, uu)) = __float2bfloat16_rn(hh);
+                    yv[q] = hh + xres[q];
+                }
+            }
+            if (PASSES > 1 && pass + 1 < PASSES) __syncthreads();
+        }
+        if (p.dbg && blockIdx.x == 0 && tid == 0) p.dbg[s * 8 + 4] = clock64();
+        if (s + 1 < Lc) {
+            __threadfence();
+            fence_proxy_async();
+            __syncthreads();
+            if (p.dbg && blockIdx.x == 0 && tid == 0) p.dbg[s * 8 + 5] = clock64();
+            if (tid == 0) {
+                mbar_expect_tx(h_ready, 8u * (uint32_t)kSlab);
+                bulk_g2s_multicast(T + j * kSlab, stage, (uint32_t)kSlab, h_ready, (uint16_t)0xFF);
+                if (p.dbg && blockIdx.x == 0) p.dbg[s * 8 + 6] = clock64();
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < P; ++q) {
+            const int i = warp + 8 * q;
+            if (i < nact) {
+                const size_t row = (size_t)(row_t + i);
+                if (p.y_packed) p.y_packed[row * kEnc + ocol] = yv[q];
+                if (p.y_utt) p.y_utt[(size_t)(p.uoff[r0 + i] + t) * kEnc + ocol] = yv[q];
+            }
+        }
+    }
+
+#pragma unroll
+    for (int q = 0; q < P; ++q) {
+        const int i = warp + 8 * q;
+        if (i < nrows) {
+            p.h_fin[(size_t)(r0 + i) * kEnc + ocol] = h_reg[q];
+            p.c_fin[(size_t)(r0 + i) * kEnc + ocol] = c_reg[q];
+        }
+    }
+    tc_fence_before();
+    cluster.sync();
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+// W_lo (fp32 residual) -> bf16 pairs (k even in the low half-word)
+__global__ void pack_bf16_pairs_kernel(const float* __restrict__ src, uint32_t* __restrict__ dst, long long n2) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n2) return;
+    const __nv_bfloat16 a = __float2bfloat16_rn(src[2 * i]);
+    const __nv_bfloat16 b = __float2bfloat16_rn(src[2 * i + 1]);
+    dst[i] = (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
+template <int NB>
+static int launch(const Params& p, cudaStream_t st) {
+    constexpr int PASSES = NB > 64 ? 2 : 1;
+    const size_t smem = 8 * (size_t)(NB * 320) + (size_t)(NB / PASSES) * 128 * 4 + 1024 + 64 + NB * 4;
+    static bool attr = false;
+    if (!attr) {
+        ASR_CUDA(cudaFuncSetAttribute(lstm_rec_tc3_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    lstm_rec_tc3_kernel<NB><<<2 * p.nchunks * 8, 256, smem, st>>>(p);
+    ASR_CHECK_LAUNCH();
+    return ASR_OK;
+}
+
+}  // namespace rec3
+
+int pack_bf16_pairs(const float* src, uint32_t* dst, long long n_pairs) {
+    rec3::pack_bf16_pairs_kernel<<<(unsigned)((n_pairs + 255) / 256), 256>>>(src, dst, n_pairs);
+    ASR_CHECK_LAUNCH();
+    ASR_CUDA(cudaDeviceSynchronize());
+    return ASR_OK;
+}
+
+size_t rec3_stage_bytes_per_cta() { return rec3::kStageBytes; }
+
+int launch_lstm_recurrence_tc3(asr_handle* h, int layer, const float* xg, const float* x_in, float* y_packed,
+                               float* y_utt, float* h_fin, float* c_fin, cudaStream_t st) {
+    const BatchMeta& m = h->meta;
+    rec3::Params p{};
+    p.xg = xg;
+    p.whh_hi = h->w.enc_w_hh_hi[layer];
+    p.whh_lo_bf = h->w.enc_w_hh_lo_bf[layer];
+    p.x_in = x_in;
+    p.y_packed = y_packed;
+    p.y_utt = y_utt;
+    p.h_fin = h_fin;
+    p.c_fin = c_fin;
+    p.stage = reinterpret_cast<uint8_t*>(h->ws.rec_stage);
+    p.len_sorted = m.d_len_sorted;
+    p.toff = m.d_toff;
+    p.uoff = m.d_uoff_sorted;
+    p.B = m.B;
+    // <= 15 clusters of 8 CTAs are co-resident on a B200 (measured): aim at one round, i.e. at most
+    // 7 chunks per direction, with the smallest operand tile that holds the chunk.
+    int rows = (m.B + 6) / 7;
+    int NB = rows <= 16 ? 16 : rows <= 32 ? 32 : rows <= 64 ? 64 : 80;
+    if (rows > 80) rows = 80;
+    p.rows_per_chunk = rows;
+    p.nchunks = (m.B + rows - 1) / rows;
+    if ((size_t)2 * p.nchunks * 8 * rec3::kStageBytes > h->ws.rec_stage_ctas * 8192) {
+        set_error("recurrence staging too small");
+        return ASR_ERR_CAPACITY;
+    }
+    static const bool want_dbg = getenv("ASR_B200_REC_DBG") != nullptr;
+    long long* dbg = nullptr;
+    if (want_dbg) { ASR_CUDA(cudaMalloc(&dbg, sizeof(long long) * 8 * 4096)); ASR_CUDA(cudaMemset(dbg, 0, sizeof(long long) * 8 * 4096)); }
+    p.dbg = dbg;
+    switch (NB) {
+        case 16: ASR_TRY(rec3::launch<16>(p, st)); break;
+        case 32: ASR_TRY(rec3::launch<32>(p, st)); break;
+        case 64: ASR_TRY(rec3::launch<64>(p, st)); break;
+        default: ASR_TRY(rec3::launch<80>(p, st)); break;
+    }
+    if (dbg) {
+        std::vector<long long> hb(8 * 4096);
+        ASR_CUDA(cudaStreamSynchronize(st));
+        ASR_CUDA(cudaMemcpy(hb.data(), dbg, sizeof(long long) * hb.size(), cudaMemcpyDeviceToHost));
+        cudaFree(dbg);
+        const int L = m.len_sorted[0];
+        double acc[6] = {};
+        int cnt = 0;
+        for (int s2 = 2; s2 + 1 < L; ++s2, ++cnt) {
+            const long long* a = &hb[s2 * 8];
+            acc[0] += (double)(a[1] - a[0]);
+            acc[1] += (double)(a[2] - a[1]);
+            acc[2] += (double)(a[4] - a[2]);
+            acc[3] += (double)(a[5] - a[4]);
+            acc[4] += (double)(a[6] - a[5]);
+            acc[5] += (double)(hb[(s2 + 1) * 8] - a[6]);
+        }
+        fprintf(stderr, "[rec_tc3 dbg] layer %d NB=%d rows/chunk=%d chunks=%d steps=%d cycles/step: issue %.0f mma+commit %.0f "
+                        "ld+gates %.0f fences %.0f bulk-issue %.0f exchange %.0f\n",
+                layer, NB, rows, p.nchunks, L, acc[0] / cnt, acc[1] / cnt, acc[2] / cnt, acc[3] / cnt, acc[4] / cnt, acc[5] / cnt);
+    }
+    h->launches++;
+    return ASR_OK;
+}
+
+}  // namespace asr

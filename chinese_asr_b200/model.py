@@ -384,7 +384,7 @@ class Model(object):
         """'simt' (CUDA-core fp32), 'tc' (GEMM stages on tcgen05 3xTF32), 'rec' (only the encoder
         recurrence on tcgen05) or 'tc+rec' (both)."""
         self._need()
-        check(lib.asr_set_gemm_mode(self._h, {'simt': 0, 'tc': 1, 'rec': 2, 'tc+rec': 3}[mode]), "asr_set_gemm_mode")
+        check(lib.asr_set_gemm_mode(self._h, {'simt': 0, 'tc': 1, 'rec': 2, 'tc+rec': 3, 'rec3': 4, 'tc+rec3': 5}[mode]), "asr_set_gemm_mode")
 
     def test_gemm(self, A, W, bias, mode):
         """C = A @ W.T + bias on the device through one GEMM engine (tests)."""
