@@ -447,9 +447,11 @@ int asr_create(asr_handle** out, const asr_weights* wt, const asr_feature_consts
     if ((rc = split_weight(h, h->w.proj_w, kVocab, kProjK, &h->w.proj_w_hi, &h->w.proj_w_lo)) != ASR_OK) return rc;
     if ((rc = split_weight(h, h->w.att_w_enc_t, kAtt, kEnc, &h->w.att_w_enc_t_hi, &h->w.att_w_enc_t_lo)) != ASR_OK) return rc;
     const char* env = getenv("ASR_B200_GEMM");
-    h->gemm_mode = (env && strcmp(env, "simt") == 0) ? 0 : (env && strcmp(env, "tc") == 0) ? 1 : 0;
+    // defaults: every GEMM-shaped stage and the recurrence on the tcgen05 tensor cores (3xTF32);
+    // ASR_B200_GEMM=simt / ASR_B200_REC=simt|tc select the CUDA-core / smem-resident variants
+    h->gemm_mode = (env && strcmp(env, "simt") == 0) ? 0 : 1;
     const char* env_rec = getenv("ASR_B200_REC");
-    h->rec_mode = (env_rec && strcmp(env_rec, "tc") == 0) ? 1 : (env_rec && strcmp(env_rec, "tc3") == 0) ? 2 : 0;
+    h->rec_mode = (env_rec && strcmp(env_rec, "simt") == 0) ? 0 : (env_rec && strcmp(env_rec, "tc") == 0) ? 1 : 2;
     *out = h;
     return ASR_OK;
 }

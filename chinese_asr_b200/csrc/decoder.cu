@@ -36,6 +36,13 @@ __device__ __forceinline__ float tanh_acc(float x) {
     const float e = __expf(2.f * x);
     return 1.f - __fdividef(2.f, e + 1.f);
 }
+// r = 1 / (1 + 2^x) on the MUFU pipe (ex2.approx + rcp.approx); 2^x = inf -> 0, 2^x = 0 -> 1
+__device__ __forceinline__ float rcp1p_ex2(float x) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.f));
+    return r;
+}
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -143,24 +150,32 @@ attention_kernel(AttnParams p) {
     // ---- phase B: scores e[l][kb] = sum_d v_d tanh(key[l][d] + q[kb][d]) ----------------------
     // one warp per frame, lane owns 4 of the 128 attention dims for all K beams; the K partial
     // sums are reduced with a transposed butterfly (K/2 + K/4 + .. shuffles instead of 5 K)
+    // tanh(x) = 1 - 2 r with r = 1 / (1 + 2^(x * 2 log2 e)):  e = V - 2 * sum_d v_d r_d, V = sum_d v_d.
+    // Keys and queries are pre-scaled by 2 log2(e) (once per frame / per beam), so one element costs
+    // FADD, MUFU.EX2, FADD, MUFU.RCP, FFMA - the kernel is bound by the 16 lanes/clk MUFU pipe.
     {
+        constexpr float kScale = 2.885390081777927f;       // 2 * log2(e)
         const float4 v4 = *reinterpret_cast<const float4*>(p.v + 4 * lane);
+        const float vsum = (v4.x + v4.y) + (v4.z + v4.w);
         float4 q4[K];
 #pragma unroll
-        for (int kb = 0; kb < K; ++kb)
+        for (int kb = 0; kb < K; ++kb) {
             q4[kb] = kb < k ? *reinterpret_cast<const float4*>(s_q + kb * kAtt + 4 * lane)
                             : make_float4(0.f, 0.f, 0.f, 0.f);
+            q4[kb].x *= kScale; q4[kb].y *= kScale; q4[kb].z *= kScale; q4[kb].w *= kScale;
+        }
         constexpr int kGroup = 32 / K;                 // lanes that end up holding the same beam
         for (int l = lbeg + warp; l < lend; l += 8) {
-            const float4 key = __ldg(reinterpret_cast<const float4*>(p.keys + (size_t)(row0 + l) * kAtt) + lane);
+            float4 key = __ldg(reinterpret_cast<const float4*>(p.keys + (size_t)(row0 + l) * kAtt) + lane);
+            key.x *= kScale; key.y *= kScale; key.z *= kScale; key.w *= kScale;
             float e[K];
 #pragma unroll
             for (int kb = 0; kb < K; ++kb) {
-                float t = v4.x * tanh_acc(key.x + q4[kb].x);
-                t = fmaf(v4.y, tanh_acc(key.y + q4[kb].y), t);
-                t = fmaf(v4.z, tanh_acc(key.z + q4[kb].z), t);
-                t = fmaf(v4.w, tanh_acc(key.w + q4[kb].w), t);
-                e[kb] = t;
+                float t = v4.x * rcp1p_ex2(key.x + q4[kb].x);
+                t = fmaf(v4.y, rcp1p_ex2(key.y + q4[kb].y), t);
+                t = fmaf(v4.z, rcp1p_ex2(key.z + q4[kb].z), t);
+                t = fmaf(v4.w, rcp1p_ex2(key.w + q4[kb].w), t);
+                e[kb] = fmaf(-2.f, t, vsum);
             }
             int off = 16;
 #pragma unroll
