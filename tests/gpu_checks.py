@@ -173,7 +173,9 @@ def check_beam(cname):
     res["score_rel_vs_ref"] = float(max(abs(a - b) / max(1e-6, abs(b)) for a, b in zip(out.score, ref_s)))
     # per-step internals against the reference's recorded torch.topk outputs
     ns = min(info["steps"], g[cname + "_cand_scores"].shape[0])
-    res["cand_scores_vs_ref"] = float(np.abs(t["cand_scores"][:ns] - g[cname + "_cand_scores"][:ns]).max())
+    ref_cs = g[cname + "_cand_scores"][:ns]
+    res["cand_scores_vs_ref"] = float(np.abs(t["cand_scores"][:ns] - ref_cs).max())
+    res["cand_scores_rel_vs_ref"] = float((np.abs(t["cand_scores"][:ns] - ref_cs) / np.maximum(1.0, np.abs(ref_cs))).max())
     flat = t["cand_beams"][:ns].astype(np.int64) * O.VOCAB + t["cand_tokens"][:ns]
     res["cand_index_mismatch_vs_ref"] = int((flat != g[cname + "_cand_index"][:ns]).sum())
     nb = len(tr.get("backptr", []))
