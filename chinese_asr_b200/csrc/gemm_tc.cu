@@ -21,6 +21,9 @@
 //              fused bias / temperature / LSTM-cell non-linearities, direct global stores.
 // SASS evidence: UTCHMMA-class (UTC*MMA), UTMALDG, LDTM, UTCBAR in `cuobjdump -sass`.
 #include <cuda.h>
+#include <stdlib.h>
+
+#include <algorithm>
 
 #include "asr_internal.cuh"
 
@@ -29,8 +32,6 @@ namespace asr {
 namespace tc {
 
 constexpr int BM = 128;
-constexpr int BKF = 32;             // fp32 elements per K-slab row = 128 bytes
-constexpr int STAGES = 3;
 constexpr int UMMA_K = 8;
 constexpr unsigned kSpinLimit = 1u << 28;
 
@@ -93,12 +94,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (one 128-byte swizzle atom along K):
 // start address >> 4 | SBO (8 rows * 128 B = 1024 B) >> 4 at [32,46) | version 1 at [46,48) |
 // layout SWIZZLE_128B (2) at [61,64).  LBO is unused for swizzled K-major operands.
-__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(const void* smem) {
+template <int BKF>
+__device__ __forceinline__ uint64_t make_kmajor_desc(const void* smem) {
+    // BKF = 32: 128-byte rows, SWIZZLE_128B (2), 1024-byte atoms; BKF = 16: 64-byte rows, SWIZZLE_64B (4),
+    // 512-byte atoms
     uint64_t d = 0;
     d |= (uint64_t)((smem_u32(smem) & 0x3FFFF) >> 4);
-    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)((BKF == 32 ? 1024 : 512) >> 4) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= (uint64_t)(BKF == 32 ? 2 : 4) << 61;
     return d;
 }
 
@@ -110,7 +114,7 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
 
 __device__ __forceinline__ float sigm(float x) { return 1.f / (1.f + expf(-x)); }
 
-template <int BN>
+template <int BN, int BKF, int STAGES>
 struct SmemLayout {
     static constexpr int kATile = BM * BKF * 4;      // 16 KB
     static constexpr int kBTile = BN * BKF * 4;
@@ -118,13 +122,13 @@ struct SmemLayout {
     static constexpr int kBytes = STAGES * kStage + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN>
+template <int BN, int BKF, int STAGES>
 __global__ void __launch_bounds__(192, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                    const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                    int M, int N, int K, GemmEpilogue epi) {
     if (epi.stop_flag && *epi.stop_flag >= 0) return;
-    using L = SmemLayout<BN>;
+    using L = SmemLayout<BN, BKF, STAGES>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * L::kStage);
@@ -178,10 +182,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                 mbar_wait(&full[s], ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 uint8_t* st = smem + s * L::kStage;
-                const uint64_t d_ah = make_kmajor_sw128_desc(st);
-                const uint64_t d_al = make_kmajor_sw128_desc(st + L::kATile);
-                const uint64_t d_wh = make_kmajor_sw128_desc(st + 2 * L::kATile);
-                const uint64_t d_wl = make_kmajor_sw128_desc(st + 2 * L::kATile + L::kBTile);
+                const uint64_t d_ah = make_kmajor_desc<BKF>(st);
+                const uint64_t d_al = make_kmajor_desc<BKF>(st + L::kATile);
+                const uint64_t d_wh = make_kmajor_desc<BKF>(st + 2 * L::kATile);
+                const uint64_t d_wl = make_kmajor_desc<BKF>(st + 2 * L::kATile + L::kBTile);
 #pragma unroll
                 for (int kk = 0; kk < BKF / UMMA_K; ++kk) {
                     const uint64_t adv = (uint64_t)((kk * UMMA_K * 4) >> 4);      // +32 B per K-step
@@ -313,7 +317,7 @@ static EncodeTiledFn get_encode() {
 }
 
 // 2-D fp32 tensor [rows, K] row-major -> box [box_rows, 32] with 128-byte swizzle
-static int make_map(CUtensorMap* map, const float* base, int rows, int K, int box_rows) {
+static int make_map(CUtensorMap* map, const float* base, int rows, int K, int box_rows, int BKF) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return ASR_ERR_CUDA; }
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
@@ -321,7 +325,8 @@ static int make_map(CUtensorMap* map, const float* base, int rows, int K, int bo
     cuuint32_t box[2] = {(cuuint32_t)BKF, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, BKF == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) rows=%d K=%d", (int)r, rows, K); return ASR_ERR_CUDA; }
     return ASR_OK;
@@ -342,26 +347,40 @@ int split_operand(const AOperand& A, int M, int K, float* hi, float* lo, const i
 }
 
 // C = A * W^T with pre-split operands (a_hi/a_lo [M,K], w_hi/w_lo [N,K], all dense row-major)
+template <int BN, int BKF, int STAGES>
+static int launch_tc_cfg(const float* a_hi, const float* a_lo, const float* w_hi, const float* w_lo, int M, int N,
+                         int K, const GemmEpilogue& epi, cudaStream_t st) {
+    CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
+    ASR_TRY(tc::make_map(&ma_hi, a_hi, M, K, tc::BM, BKF));
+    ASR_TRY(tc::make_map(&ma_lo, a_lo, M, K, tc::BM, BKF));
+    ASR_TRY(tc::make_map(&mw_hi, w_hi, N, K, BN, BKF));
+    ASR_TRY(tc::make_map(&mw_lo, w_lo, N, K, BN, BKF));
+    static bool attr = false;
+    const int smem = tc::SmemLayout<BN, BKF, STAGES>::kBytes;
+    if (!attr) {
+        ASR_CUDA(cudaFuncSetAttribute(tc::gemm_tf32x3_kernel<BN, BKF, STAGES>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr = true;
+    }
+    dim3 grid((N + BN - 1) / BN, (M + tc::BM - 1) / tc::BM);
+    tc::gemm_tf32x3_kernel<BN, BKF, STAGES><<<grid, 192, smem, st>>>(ma_hi, ma_lo, mw_hi, mw_lo, M, N, K, epi);
+    ASR_CHECK_LAUNCH();
+    return ASR_OK;
+}
+
 int launch_gemm_tc(const float* a_hi, const float* a_lo, const float* w_hi, const float* w_lo, int M, int N, int K,
                    const GemmEpilogue& epi, cudaStream_t st, int64_t* launches) {
     if (M <= 0) return ASR_OK;
     if ((K * 4) % 16) { set_error("gemm_tc: K*4 must be a multiple of 16"); return ASR_ERR_ARG; }
     if (epi.kind == Epi::kLstmCell && (N % 32)) { set_error("gemm_tc: LSTM epilogue needs N %% 32 == 0"); return ASR_ERR_ARG; }
-    constexpr int BN = 128;
-    CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
-    ASR_TRY(tc::make_map(&ma_hi, a_hi, M, K, tc::BM));
-    ASR_TRY(tc::make_map(&ma_lo, a_lo, M, K, tc::BM));
-    ASR_TRY(tc::make_map(&mw_hi, w_hi, N, K, BN));
-    ASR_TRY(tc::make_map(&mw_lo, w_lo, N, K, BN));
-    static bool attr = false;
-    const int smem = tc::SmemLayout<BN>::kBytes;
-    if (!attr) {
-        ASR_CUDA(cudaFuncSetAttribute(tc::gemm_tf32x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr = true;
+    static const char* env = getenv("ASR_B200_GEMM_TILE");
+    const bool wide = env ? (atoi(env) == 256) : (N >= 1024);
+    if (wide) {
+        // 128 x 256 tile, 64-byte K slabs, 4 stages: twice the MMA work per byte of A in flight
+        ASR_TRY((launch_tc_cfg<256, 16, 4>(a_hi, a_lo, w_hi, w_lo, M, N, K, epi, st)));
+    } else {
+        ASR_TRY((launch_tc_cfg<128, 32, 3>(a_hi, a_lo, w_hi, w_lo, M, N, K, epi, st)));
     }
-    dim3 grid((N + BN - 1) / BN, (M + tc::BM - 1) / tc::BM);
-    tc::gemm_tf32x3_kernel<BN><<<grid, 192, smem, st>>>(ma_hi, ma_lo, mw_hi, mw_lo, M, N, K, epi);
-    ASR_CHECK_LAUNCH();
     if (launches) ++*launches;
     return ASR_OK;
 }
