@@ -122,12 +122,16 @@ struct SmemLayout {
     static constexpr int kBytes = STAGES * kStage + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
+__device__ long long g_gemm_trace[1024];
+
 template <int BN, int BKF, int STAGES>
 __global__ void __launch_bounds__(192, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                    const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
-                   int M, int N, int K, GemmEpilogue epi) {
+                   int M, int N, int K, GemmEpilogue epi, int dbg) {
     if (epi.stop_flag && *epi.stop_flag >= 0) return;
+    const bool trace = (dbg & 4) && blockIdx.x == 0 && blockIdx.y == gridDim.y / 2;
+    if (trace && threadIdx.x == 0) g_gemm_trace[0] = clock64();
     using L = SmemLayout<BN, BKF, STAGES>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -165,12 +169,20 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                 const int s = kb % STAGES;
                 const uint32_t ph = (kb / STAGES) & 1;
                 mbar_wait(&empty[s], ph ^ 1);
+                if (trace && kb < 200) g_gemm_trace[16 + kb * 4] = clock64();
                 uint8_t* st = smem + s * L::kStage;
+                if (dbg & 2) {     // experiment: load only the hi tiles
+                    mbar_expect_tx(&full[s], L::kATile + L::kBTile);
+                    tma_load_2d(&map_a_hi, &full[s], st, kb * BKF, m0);
+                    tma_load_2d(&map_w_hi, &full[s], st + 2 * L::kATile, kb * BKF, n0);
+                    continue;
+                }
                 mbar_expect_tx(&full[s], L::kStage);
                 tma_load_2d(&map_a_hi, &full[s], st, kb * BKF, m0);
                 tma_load_2d(&map_a_lo, &full[s], st + L::kATile, kb * BKF, m0);
                 tma_load_2d(&map_w_hi, &full[s], st + 2 * L::kATile, kb * BKF, n0);
                 tma_load_2d(&map_w_lo, &full[s], st + 2 * L::kATile + L::kBTile, kb * BKF, n0);
+                if (trace && kb < 200) g_gemm_trace[16 + kb * 4 + 1] = clock64();
             }
         }
     } else if (warp == 1) {
@@ -180,6 +192,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                 const int s = kb % STAGES;
                 const uint32_t ph = (kb / STAGES) & 1;
                 mbar_wait(&full[s], ph);
+                if (trace && kb < 200) g_gemm_trace[16 + kb * 4 + 2] = clock64();
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 uint8_t* st = smem + s * L::kStage;
                 const uint64_t d_ah = make_kmajor_desc<BKF>(st);
@@ -189,75 +202,120 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
 #pragma unroll
                 for (int kk = 0; kk < BKF / UMMA_K; ++kk) {
                     const uint64_t adv = (uint64_t)((kk * UMMA_K * 4) >> 4);      // +32 B per K-step
+                    if (dbg & 1) {   // experiment: one product per K-step
+                        umma_tf32(tmem_base, d_ah + adv, d_wh + adv, idesc, (kb | kk) ? 1u : 0u);
+                        continue;
+                    }
                     umma_tf32(tmem_base, d_al + adv, d_wh + adv, idesc, (kb | kk) ? 1u : 0u);
                     umma_tf32(tmem_base, d_ah + adv, d_wl + adv, idesc, 1u);
                     umma_tf32(tmem_base, d_ah + adv, d_wh + adv, idesc, 1u);
                 }
                 umma_commit(&empty[s]);            // frees the stage when these MMAs have read it
+                if (trace && kb < 200) g_gemm_trace[16 + kb * 4 + 3] = clock64();
             }
             umma_commit(tmem_full);                // accumulator complete
         }
     } else {
         // ---- epilogue: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32) ------------------------
+        // TMEM gives every thread one accumulator ROW; writing rows straight to global memory touches
+        // 32 different 128-byte lines per store instruction (measured: the epilogue took as long as
+        // the main loop).  Instead each warp transposes its 32 x BN block through the (now idle)
+        // pipeline shared memory and stores full rows, 512 contiguous bytes per instruction.
         const int q = warp & 3;
-        const int row = m0 + q * 32 + lane;
         mbar_wait(tmem_full, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const bool row_ok = row < M;
-        int crow = row;
-        if (epi.kind == Epi::kLstmCell && row_ok && epi.c_rowidx) crow = epi.c_rowidx[row];
+        if (trace && warp == 2 && lane == 0) g_gemm_trace[1] = clock64();
+        constexpr int LD = BN + 4;                       // floats; keeps 16-byte alignment, conflict-free
+        float* scr = reinterpret_cast<float*>(smem) + (size_t)q * 32 * LD;
+        const int rbase = m0 + q * 32;
+        if (epi.kind == Epi::kLstmCell) {
+            constexpr int LH = BN / 4 + 4;
+            float* scr_h = scr;
+            float* scr_c = scr + 32 * LH;
+            const int row = rbase + lane;
+            const bool row_ok = row < M;
+            int crow = row;
+            if (row_ok && epi.c_rowidx) crow = epi.c_rowidx[row];
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t r[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-            const int n = n0 + c0;
-            if (!row_ok || n >= N) continue;
-            if (epi.kind == Epi::kLstmCell) {
-                // 32 columns = 8 hidden units x (i, f, g, o)
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+                const int n = n0 + c0;
                 float hv[8], cv[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int nn = n + 4 * j;
-                    const float gi = __uint_as_float(r[4 * j]) + epi.bias[nn];
-                    const float gf = __uint_as_float(r[4 * j + 1]) + epi.bias[nn + 1];
-                    const float gg = __uint_as_float(r[4 * j + 2]) + epi.bias[nn + 2];
-                    const float go = __uint_as_float(r[4 * j + 3]) + epi.bias[nn + 3];
-                    const float cp = epi.c_prev[(size_t)crow * epi.H + (nn >> 2)];
-                    cv[j] = sigm(gf) * cp + sigm(gi) * tanhf(gg);
-                    hv[j] = sigm(go) * tanhf(cv[j]);
-                }
-                float4* ho = reinterpret_cast<float4*>(epi.h_out + (size_t)row * epi.H + (n >> 2));
-                float4* co = reinterpret_cast<float4*>(epi.c_out + (size_t)row * epi.H + (n >> 2));
-                ho[0] = make_float4(hv[0], hv[1], hv[2], hv[3]);
-                ho[1] = make_float4(hv[4], hv[5], hv[6], hv[7]);
-                co[0] = make_float4(cv[0], cv[1], cv[2], cv[3]);
-                co[1] = make_float4(cv[4], cv[5], cv[6], cv[7]);
-            } else {
-                float* crowp = epi.C + (size_t)row * epi.ldc + n;
-                const bool sc = epi.kind == Epi::kBiasScale;
+                for (int j = 0; j < 8; ++j) { hv[j] = 0.f; cv[j] = 0.f; }
+                if (row_ok && n < N) {
+                    // 32 columns = 8 hidden units x (i, f, g, o)
+                    const float4 cp0 = *reinterpret_cast<const float4*>(epi.c_prev + (size_t)crow * epi.H + (n >> 2));
+                    const float4 cp1 = *reinterpret_cast<const float4*>(epi.c_prev + (size_t)crow * epi.H + (n >> 2) + 4);
+                    const float cp[8] = {cp0.x, cp0.y, cp0.z, cp0.w, cp1.x, cp1.y, cp1.z, cp1.w};
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    if (n + j + 3 < N) {
-                        float4 v;
-                        v.x = __uint_as_float(r[j]) + epi.bias[n + j];
-                        v.y = __uint_as_float(r[j + 1]) + epi.bias[n + j + 1];
-                        v.z = __uint_as_float(r[j + 2]) + epi.bias[n + j + 2];
-                        v.w = __uint_as_float(r[j + 3]) + epi.bias[n + j + 3];
-                        if (sc) { v.x /= epi.scale; v.y /= epi.scale; v.z /= epi.scale; v.w /= epi.scale; }
-                        *reinterpret_cast<float4*>(crowp + j) = v;
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(epi.bias + n + 4 * j));
+                        const float gi = __uint_as_float(r[4 * j]) + b4.x;
+                        const float gf = __uint_as_float(r[4 * j + 1]) + b4.y;
+                        const float gg = __uint_as_float(r[4 * j + 2]) + b4.z;
+                        const float go = __uint_as_float(r[4 * j + 3]) + b4.w;
+                        cv[j] = sigm(gf) * cp[j] + sigm(gi) * tanhf(gg);
+                        hv[j] = sigm(go) * tanhf(cv[j]);
+                    }
+                }
+                float* ph = scr_h + lane * LH + (c0 >> 2);
+                float* pc = scr_c + lane * LH + (c0 >> 2);
+                *reinterpret_cast<float4*>(ph) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+                *reinterpret_cast<float4*>(ph + 4) = make_float4(hv[4], hv[5], hv[6], hv[7]);
+                *reinterpret_cast<float4*>(pc) = make_float4(cv[0], cv[1], cv[2], cv[3]);
+                *reinterpret_cast<float4*>(pc + 4) = make_float4(cv[4], cv[5], cv[6], cv[7]);
+            }
+            __syncwarp();
+            const int u0 = (n0 >> 2) + 2 * lane;         // BN/4 = 64 (or 32) units per tile
+            if (2 * lane < BN / 4 && u0 + 1 < epi.H) {
+                for (int rr = 0; rr < 32 && rbase + rr < M; ++rr) {
+                    const float2 hh = *reinterpret_cast<const float2*>(scr_h + rr * LH + 2 * lane);
+                    const float2 cc = *reinterpret_cast<const float2*>(scr_c + rr * LH + 2 * lane);
+                    *reinterpret_cast<float2*>(epi.h_out + (size_t)(rbase + rr) * epi.H + u0) = hh;
+                    *reinterpret_cast<float2*>(epi.c_out + (size_t)(rbase + rr) * epi.H + u0) = cc;
+                }
+            }
+        } else {
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+                float* pr = scr + lane * LD + c0;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(pr + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                     __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+            }
+            __syncwarp();
+            const bool sc = epi.kind == Epi::kBiasScale;
+#pragma unroll
+            for (int i = 0; i < BN / 128; ++i) {
+                const int col = 128 * i + 4 * lane;
+                const int n = n0 + col;
+                if (n >= N) continue;
+                float b4[4];
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) b4[jj] = n + jj < N ? __ldg(epi.bias + n + jj) : 0.f;
+                const bool full4 = n + 3 < N;
+                for (int rr = 0; rr < 32 && rbase + rr < M; ++rr) {
+                    float4 v = *reinterpret_cast<const float4*>(scr + rr * LD + col);
+                    v.x += b4[0]; v.y += b4[1]; v.z += b4[2]; v.w += b4[3];
+                    if (sc) { v.x /= epi.scale; v.y /= epi.scale; v.z /= epi.scale; v.w /= epi.scale; }
+                    float* dst = epi.C + (size_t)(rbase + rr) * epi.ldc + n;
+                    if (full4) {
+                        *reinterpret_cast<float4*>(dst) = v;
                     } else {
-                        for (int jj = 0; jj < 4; ++jj)
-                            if (n + j + jj < N) {
-                                float v = __uint_as_float(r[j + jj]) + epi.bias[n + j + jj];
-                                if (sc) v /= epi.scale;
-                                crowp[j + jj] = v;
-                            }
+                        const float vv[4] = {v.x, v.y, v.z, v.w};
+                        for (int jj = 0; jj < 4; ++jj) if (n + jj < N) dst[jj] = vv[jj];
                     }
                 }
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
+    if (trace && warp == 2 && lane == 0) g_gemm_trace[2] = clock64();
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -362,9 +420,24 @@ static int launch_tc_cfg(const float* a_hi, const float* a_lo, const float* w_hi
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr = true;
     }
+    static const int dbg = getenv("ASR_B200_GEMM_DBG") ? atoi(getenv("ASR_B200_GEMM_DBG")) : 0;
     dim3 grid((N + BN - 1) / BN, (M + tc::BM - 1) / tc::BM);
-    tc::gemm_tf32x3_kernel<BN, BKF, STAGES><<<grid, 192, smem, st>>>(ma_hi, ma_lo, mw_hi, mw_lo, M, N, K, epi);
+    tc::gemm_tf32x3_kernel<BN, BKF, STAGES><<<grid, 192, smem, st>>>(ma_hi, ma_lo, mw_hi, mw_lo, M, N, K, epi, dbg);
     ASR_CHECK_LAUNCH();
+    if ((dbg & 4) && M > 100000 && K == 512) {
+        static int printed = 0;
+        if (printed++ < 1) {
+            long long t[1024];
+            cudaStreamSynchronize(st);
+            cudaMemcpyFromSymbol(t, tc::g_gemm_trace, sizeof(t));
+            const int nkb = (K + BKF - 1) / BKF;
+            fprintf(stderr, "[gemm trace] BN=%d BKF=%d STAGES=%d nkb=%d: start->first full %lld, epilogue %lld, total %lld cycles\n", BN, BKF,
+                    STAGES, nkb, t[16 + 2] - t[0], t[2] - t[1], t[2] - t[0]);
+            for (int kb = 0; kb < nkb; kb += (kb < 8 ? 1 : 4))
+                fprintf(stderr, "  kb %2d: prod wait-done %6lld issued %6lld | mma full-done %6lld issued %6lld\n", kb,
+                        t[16 + kb * 4] - t[0], t[16 + kb * 4 + 1] - t[0], t[16 + kb * 4 + 2] - t[0], t[16 + kb * 4 + 3] - t[0]);
+        }
+    }
     return ASR_OK;
 }
 
