@@ -38,7 +38,8 @@ static int dev_upload(std::vector<void*>& pool, T** p, const std::vector<T>& v) 
 }
 
 // ---- stage timing ----------------------------------------------------------------------------
-enum Stage { kStFeat = 0, kStEncGemm, kStEncRec, kStKeys, kStCell, kStAttn, kStProj, kStTopk };
+enum Stage { kStFeat = 0, kStEncGemm, kStEncRec, kStKeys, kStCell, kStAttn, kStProj, kStTopk,
+             kStGemmKernel /* every GEMM-engine launch, nested in the stages above */, kStSplit /* operand split */ };
 
 struct StageScope {
     asr_handle* h; cudaStream_t st; int idx;
@@ -128,9 +129,16 @@ static int prepare_batch(asr_handle* h, const int32_t* h_L, int B, cudaStream_t 
 static int gemm(asr_handle* h, const AOperand& A, const float* W, const float* W_hi, const float* W_lo,
                 int M, int N, int K, const GemmEpilogue& epi, cudaStream_t st) {
     if (h->gemm_mode == 1 && W_hi && W_lo && h->ws.a_hi) {
-        ASR_TRY(split_operand(A, M, K, h->ws.a_hi, h->ws.a_lo, epi.stop_flag, st, &h->launches));
+        {
+            StageScope sc(h, kStSplit, st);
+            ASR_TRY(split_operand(A, M, K, h->ws.a_hi, h->ws.a_lo, epi.stop_flag, st, &h->launches));
+        }
+        StageScope sc(h, kStGemmKernel, st);
+        h->gemm_flops += 2.0 * M * N * K;
         return launch_gemm_tc(h->ws.a_hi, h->ws.a_lo, W_hi, W_lo, M, N, K, epi, st, &h->launches);
     }
+    StageScope sc(h, kStGemmKernel, st);
+    h->gemm_flops += 2.0 * M * N * K;
     return launch_gemm(A, W, M, N, K, epi, st, &h->launches);
 }
 
@@ -782,6 +790,7 @@ int asr_stage_timing(asr_handle* h, int enable) {
     if (!h) return ASR_ERR_ARG;
     h->timing = enable != 0;
     h->n_ev = 0;
+    h->gemm_flops = 0.0;
     return ASR_OK;
 }
 
@@ -794,7 +803,10 @@ int asr_stage_times(asr_handle* h, float* h_ms, int n) {
         if (cudaEventElapsedTime(&ms, h->ev[2 * i], h->ev[2 * i + 1]) == cudaSuccess) acc[h->ev_stage[i]] += ms;
     }
     for (int i = 0; i < n && i < kStages; ++i) h_ms[i] = acc[i];
+    // slot 10: algorithmic GFLOP (2*M*N*K) of the GEMM-engine launches timed in slot 8
+    if (n > 10) h_ms[10] = (float)(h->gemm_flops * 1e-9);
     h->n_ev = 0;
+    h->gemm_flops = 0.0;
     return ASR_OK;
 }
 

@@ -25,7 +25,7 @@ constexpr int kPad = 0, kSos = 1, kEos = 2;
 constexpr int kNfft = 512, kHop = 160, kWin = 400, kBins = 257, kWinOff = 56;
 constexpr int kMaxBeam = ASR_MAX_BEAM;
 constexpr int kNumSMs = 148;
-constexpr int kStages = 8;
+constexpr int kStages = 12;       // 8 pipeline stages + kernel-level timers (GEMM kernel, operand split)
 
 void set_error(const char* fmt, ...);
 
@@ -272,9 +272,10 @@ struct asr_handle {
     bool timing = false;
     int gemm_mode = 0;           // 0 = CUDA-core fp32 FMA, 1 = tcgen05 3xTF32
     int rec_mode = 0;            // encoder recurrence: 0 = CUDA-core (register-stationary W_hh), 1 = tcgen05
-    cudaEvent_t ev[2 * asr::kStages * 64] = {};
+    double gemm_flops = 0.0;     // algorithmic 2*M*N*K of every GEMM-engine launch since the last reset
+    cudaEvent_t ev[2 * 1024] = {};
     int n_ev = 0;
-    int ev_stage[asr::kStages * 64] = {};
+    int ev_stage[1024] = {};
     float stage_ms[asr::kStages] = {};
     std::vector<void*> weight_allocs;
 };

@@ -161,20 +161,30 @@ delta_cmvn_kernel(const float* __restrict__ mel, const int* __restrict__ frame_o
     const int i_lo = (c == 0) ? 4 : (c == 1 ? 2 : 0);
     const int i_hi = (c == 0) ? 5 : (c == 1 ? 7 : 9);
 
-    double sum = 0.0, sq = 0.0;
-    for (int g = ty; g < L; g += 4) {
+    // the 9-tap correlation is recomputed in the second pass (its log-mel input is L2-resident)
+    // instead of writing raw features and reading them back: the output is written exactly once
+    auto tap = [&](int g) {
         const int t = 3 * g + j;
         float acc = 0.f;
         for (int i = i_lo; i < i_hi; ++i) {
             const int tt = t + i - 4;
-            if (tt >= 0 && tt < T) acc = fmaf(tw[i], mel[(size_t)(f0 + tt) * kMel + m], acc);
+            if (tt >= 0 && tt < T) acc = fmaf(tw[i], __ldg(mel + (size_t)(f0 + tt) * kMel + m), acc);
         }
-        const int row = out_rowmap ? out_rowmap[r0 + g] : (r0 + g);
-        out[(size_t)row * kFeat + col] = acc;
+        return acc;
+    };
+    if (!normalise) {
+        for (int g = ty; g < L; g += 4) {
+            const int row = out_rowmap ? out_rowmap[r0 + g] : (r0 + g);
+            out[(size_t)row * kFeat + col] = tap(g);
+        }
+        return;
+    }
+    double sum = 0.0, sq = 0.0;
+    for (int g = ty; g < L; g += 4) {
+        const float acc = tap(g);
         sum += (double)acc;
         sq += (double)acc * (double)acc;
     }
-    if (!normalise) return;
     s_sum[ty][x] = sum;
     s_sq[ty][x] = sq;
     __syncthreads();
@@ -187,8 +197,7 @@ delta_cmvn_kernel(const float* __restrict__ mel, const int* __restrict__ frame_o
     const float denom = (float)sqrt(var) + 1e-6f;
     for (int g = ty; g < L; g += 4) {
         const int row = out_rowmap ? out_rowmap[r0 + g] : (r0 + g);
-        float* p = out + (size_t)row * kFeat + col;
-        *p = (*p - meanf) / denom;
+        out[(size_t)row * kFeat + col] = (tap(g) - meanf) / denom;
     }
 }
 

@@ -405,8 +405,11 @@ class Model(object):
         check(lib.asr_stage_timing(self._h, 1 if enable else 0), "asr_stage_timing")
 
     def stage_times(self):
-        ms = np.zeros(8, dtype=np.float32)
-        check(lib.asr_stage_times(self._h, _cabi.fptr(ms), 8), "asr_stage_times")
+        """ms per pipeline stage (CUDA events on the launch stream) + kernel-level timers:
+        `gemm_kernel_ms` = all GEMM-engine launches (nested in the stages), `operand_split_ms`,
+        `gemm_gflop` = their algorithmic 2*M*N*K."""
+        ms = np.zeros(12, dtype=np.float32)
+        check(lib.asr_stage_times(self._h, _cabi.fptr(ms), 12), "asr_stage_times")
         names = ("features", "enc_input_gemm", "enc_recurrence", "attn_keys", "dec_cell", "attention",
-                 "vocab_proj", "topk_bookkeep")
+                 "vocab_proj", "topk_bookkeep", "gemm_kernel_ms", "operand_split_ms", "gemm_gflop")
         return dict(zip(names, ms.tolist()))
