@@ -103,8 +103,8 @@ def cpu_port_rate(n_utts, bw, seconds, threads=None, reps=1, warm=0):
     on a bounded sample: features + encoder + beam decode, batch = n_utts.  Returns utt/s."""
     import torch
     from oracle import asr_oracle as O
-    if threads:
-        torch.set_num_threads(threads)
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm must use all the host threads it can
+    torch.set_num_threads(threads or max(1, os.cpu_count() or 1))
     weights = O.make_weights(1234, "plain")
     n = int(seconds * SR)
     pcm = synth_batch(n_utts, n, 4242)

@@ -37,16 +37,12 @@ __device__ __forceinline__ float tanh_acc(float x) {
     return 1.f - __fdividef(2.f, e + 1.f);
 }
 // r = 1 / (1 + 2^x) on the MUFU pipe (ex2.approx + rcp.approx); 2^x = inf -> 0, 2^x = 0 -> 1
-// One MUFU (ex2) per element: the reciprocal runs on the FMA pipe (magic-constant seed + 3 Newton steps,
-// relative error < 1e-7), because the attention scores are bound by the 16 lanes/clk MUFU pipe.
+// (measured: replacing the rcp by a seed + 3 Newton steps on the FMA pipe is slower - the kernel then
+// becomes issue-bound - so both transcendental steps stay on the MUFU pipe)
 __device__ __forceinline__ float rcp1p_ex2(float x) {
-    float e;
+    float e, r;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x));
-    const float d = fminf(e + 1.f, 1e30f);                      // 2^x = inf -> r ~ 0
-    float r = __int_as_float(0x7EF311C7 - __float_as_int(d));  // ~12% accurate seed
-    r = r * fmaf(-d, r, 2.f);
-    r = r * fmaf(-d, r, 2.f);
-    r = r * fmaf(-d, r, 2.f);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.f));
     return r;
 }
 __device__ __forceinline__ float warp_max(float v) {

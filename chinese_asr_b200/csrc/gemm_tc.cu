@@ -324,6 +324,217 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
 }
 
 // ---------------------------------------------------------------------------------------------
+// Persistent variant: one CTA per SM loops over output tiles; the TMA producer and the MMA issuer run
+// ahead across tile boundaries and the accumulator is DOUBLE-BUFFERED in TMEM (2 x BN columns), so
+// the epilogue of tile i (TMEM -> smem transpose -> coalesced stores) overlaps the main loop of tile
+// i+1.  Measured on the one-tile-per-CTA kernel: main loop 27.4k cycles at 90 % tensor-pipe
+// efficiency, but 2.6k cycles of prologue and 7.7k cycles of epilogue per tile were exposed.
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int BN, int BKF, int STAGES>
+struct SmemLayoutP {
+    static constexpr int kATile = BM * BKF * 4;
+    static constexpr int kBTile = BN * BKF * 4;
+    static constexpr int kStage = 2 * kATile + 2 * kBTile;
+    static constexpr int kScratch = 4 * 32 * 36 * 4;      // per epilogue warp: 32 rows x (32 + 4) floats
+    static constexpr int kBytes = STAGES * kStage + kScratch + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, int BKF, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                              const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+                              int M, int N, int K, GemmEpilogue epi, int dbg) {
+    if (epi.stop_flag && *epi.stop_flag >= 0) return;
+    using L = SmemLayoutP<BN, BKF, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    float* scratch = reinterpret_cast<float*>(smem + STAGES * L::kStage);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * L::kStage + L::kScratch);
+    uint64_t* full = bars;                     // [STAGES]
+    uint64_t* empty = bars + STAGES;           // [STAGES]
+    uint64_t* tfull = bars + 2 * STAGES;       // [2] accumulator ready for the epilogue
+    uint64_t* tempty = bars + 2 * STAGES + 2;  // [2] accumulator drained by the 4 epilogue warps
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_n = (N + BN - 1) / BN;
+    const int ntiles = ((M + BM - 1) / BM) * tiles_n;
+    const int nkb = (K + BKF - 1) / BKF;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_lo) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w_lo) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "n"(2 * BN)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int it = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    uint8_t* st = smem + s * L::kStage;
+                    mbar_expect_tx(&full[s], L::kStage);
+                    tma_load_2d(&map_a_hi, &full[s], st, kb * BKF, m0);
+                    tma_load_2d(&map_a_lo, &full[s], st + L::kATile, kb * BKF, m0);
+                    tma_load_2d(&map_w_hi, &full[s], st + 2 * L::kATile, kb * BKF, n0);
+                    tma_load_2d(&map_w_lo, &full[s], st + 2 * L::kATile + L::kBTile, kb * BKF, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
+            int it = 0, lt = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
+                const int acc = lt & 1;
+                const uint32_t aph = (lt >> 1) & 1;
+                mbar_wait(&tempty[acc], aph ^ 1);          // the epilogue has drained this accumulator
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t tacc = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&full[s], ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    uint8_t* st = smem + s * L::kStage;
+                    const uint64_t d_ah = make_kmajor_desc<BKF>(st);
+                    const uint64_t d_al = make_kmajor_desc<BKF>(st + L::kATile);
+                    const uint64_t d_wh = make_kmajor_desc<BKF>(st + 2 * L::kATile);
+                    const uint64_t d_wl = make_kmajor_desc<BKF>(st + 2 * L::kATile + L::kBTile);
+#pragma unroll
+                    for (int kk = 0; kk < BKF / UMMA_K; ++kk) {
+                        const uint64_t adv = (uint64_t)((kk * UMMA_K * 4) >> 4);
+                        umma_tf32(tacc, d_al + adv, d_wh + adv, idesc, (kb | kk) ? 1u : 0u);
+                        umma_tf32(tacc, d_ah + adv, d_wl + adv, idesc, 1u);
+                        umma_tf32(tacc, d_ah + adv, d_wh + adv, idesc, 1u);
+                    }
+                    umma_commit(&empty[s]);
+                }
+                umma_commit(&tfull[acc]);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        float* scr = scratch + q * (32 * 36);
+        int lt = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
+            const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+            const int acc = lt & 1;
+            const uint32_t aph = (lt >> 1) & 1;
+            mbar_wait(&tfull[acc], aph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tacc = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
+            const int rbase = m0 + q * 32;
+            if (epi.kind == Epi::kLstmCell) {
+                const int row = rbase + lane;
+                const bool row_ok = row < M;
+                int crow = row;
+                if (row_ok && epi.c_rowidx) crow = epi.c_rowidx[row];
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    uint32_t r[32];
+                    tmem_ld32(tacc + (uint32_t)c0, r);
+                    const int n = n0 + c0;
+                    if (!row_ok || n >= N) continue;
+                    const float4 cp0 = *reinterpret_cast<const float4*>(epi.c_prev + (size_t)crow * epi.H + (n >> 2));
+                    const float4 cp1 = *reinterpret_cast<const float4*>(epi.c_prev + (size_t)crow * epi.H + (n >> 2) + 4);
+                    const float cp[8] = {cp0.x, cp0.y, cp0.z, cp0.w, cp1.x, cp1.y, cp1.z, cp1.w};
+                    float hv[8], cv[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(epi.bias + n + 4 * j));
+                        const float gi = __uint_as_float(r[4 * j]) + b4.x;
+                        const float gf = __uint_as_float(r[4 * j + 1]) + b4.y;
+                        const float gg = __uint_as_float(r[4 * j + 2]) + b4.z;
+                        const float go = __uint_as_float(r[4 * j + 3]) + b4.w;
+                        cv[j] = sigm(gf) * cp[j] + sigm(gi) * tanhf(gg);
+                        hv[j] = sigm(go) * tanhf(cv[j]);
+                    }
+                    float4* ho = reinterpret_cast<float4*>(epi.h_out + (size_t)row * epi.H + (n >> 2));
+                    float4* co = reinterpret_cast<float4*>(epi.c_out + (size_t)row * epi.H + (n >> 2));
+                    ho[0] = make_float4(hv[0], hv[1], hv[2], hv[3]);
+                    ho[1] = make_float4(hv[4], hv[5], hv[6], hv[7]);
+                    co[0] = make_float4(cv[0], cv[1], cv[2], cv[3]);
+                    co[1] = make_float4(cv[4], cv[5], cv[6], cv[7]);
+                }
+            } else {
+                const bool sc = epi.kind == Epi::kBiasScale;
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    uint32_t r[32];
+                    tmem_ld32(tacc + (uint32_t)c0, r);
+                    float* pr = scr + lane * 36;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(pr + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                         __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                    __syncwarp();
+                    // 8 lanes cover one 128-byte row segment, a warp stores 4 rows per instruction;
+                    // all shared-memory loads are issued before the stores (independent, unrolled)
+                    const int cq = lane & 7, rq = lane >> 3;
+                    const int n = n0 + c0 + 4 * cq;
+                    if (n + 3 < N && !(dbg & 8)) {
+                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(epi.bias + n));
+                        float4 v[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const float4*>(scr + (4 * i + rq) * 36 + 4 * cq);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int row = rbase + 4 * i + rq;
+                            if (row < M) {
+                                float4 o = make_float4(v[i].x + b4.x, v[i].y + b4.y, v[i].z + b4.z, v[i].w + b4.w);
+                                if (sc) { o.x /= epi.scale; o.y /= epi.scale; o.z /= epi.scale; o.w /= epi.scale; }
+                                *reinterpret_cast<float4*>(epi.C + (size_t)row * epi.ldc + n) = o;
+                            }
+                        }
+                    } else if (n < N && !(dbg & 8)) {
+                        for (int i = 0; i < 8; ++i) {
+                            const int row = rbase + 4 * i + rq;
+                            for (int jj = 0; jj < 4 && row < M; ++jj)
+                                if (n + jj < N) {
+                                    float o = scr[(4 * i + rq) * 36 + 4 * cq + jj] + __ldg(epi.bias + n + jj);
+                                    if (sc) o /= epi.scale;
+                                    epi.C[(size_t)row * epi.ldc + n + jj] = o;
+                                }
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // operand split: x -> (rn_tf32(x), rn_tf32(x - rn_tf32(x))), with the AOperand gather fused
 __device__ __forceinline__ float rn_tf32(float x) {
     uint32_t u;
@@ -413,6 +624,26 @@ static int launch_tc_cfg(const float* a_hi, const float* a_lo, const float* w_hi
     ASR_TRY(tc::make_map(&ma_lo, a_lo, M, K, tc::BM, BKF));
     ASR_TRY(tc::make_map(&mw_hi, w_hi, N, K, BN, BKF));
     ASR_TRY(tc::make_map(&mw_lo, w_lo, N, K, BN, BKF));
+    static const bool persist = !(getenv("ASR_B200_GEMM_PERSIST") && atoi(getenv("ASR_B200_GEMM_PERSIST")) == 0);
+    if (persist) {
+        static bool attr_p = false;
+        static int num_sms = 0;
+        const int smem_p = tc::SmemLayoutP<BN, BKF, STAGES>::kBytes;
+        if (!attr_p) {
+            int dev = 0;
+            ASR_CUDA(cudaGetDevice(&dev));
+            ASR_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+            ASR_CUDA(cudaFuncSetAttribute(tc::gemm_tf32x3_persistent_kernel<BN, BKF, STAGES>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem_p));
+            attr_p = true;
+        }
+        static const int dbg_p = getenv("ASR_B200_GEMM_DBG") ? atoi(getenv("ASR_B200_GEMM_DBG")) : 0;
+        const int ntiles = ((N + BN - 1) / BN) * ((M + tc::BM - 1) / tc::BM);
+        const int grid_p = ntiles < num_sms ? ntiles : num_sms;
+        tc::gemm_tf32x3_persistent_kernel<BN, BKF, STAGES><<<grid_p, 192, smem_p, st>>>(ma_hi, ma_lo, mw_hi, mw_lo, M, N, K, epi, dbg_p);
+        ASR_CHECK_LAUNCH();
+        return ASR_OK;
+    }
     static bool attr = false;
     const int smem = tc::SmemLayout<BN, BKF, STAGES>::kBytes;
     if (!attr) {
