@@ -86,13 +86,22 @@ __device__ __forceinline__ void tmem_ld_cols<16>(uint32_t taddr, uint32_t* r) { 
 template <>
 __device__ __forceinline__ void tmem_ld_cols<32>(uint32_t taddr, uint32_t* r) { tmem_ld32(taddr, r); }
 template <>
-__device__ __forceinline__ void tmem_ld_cols<20>(uint32_t taddr, uint32_t* r) {
-    tmem_ld16(taddr, r);
+__device__ __forceinline__ void tmem_ld_cols<4>(uint32_t taddr, uint32_t* r) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19])
-                 : "r"(taddr + 16));
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+template <>
+__device__ __forceinline__ void tmem_ld_cols<10>(uint32_t taddr, uint32_t* r) {
+    tmem_ld8(taddr, r);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];"
+                 : "=r"(r[8]), "=r"(r[9])
+                 : "r"(taddr + 8));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+constexpr int kThreads = 512;
 
 struct Params {
     const float* xg;            // [rows, 2048] permuted gate pre-activations (bias included)
@@ -116,17 +125,17 @@ struct Params {
 constexpr int kStageBytes = 80 * 320;    // per-CTA staging slot (largest NB)
 
 template <int NB>
-__global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(256, 1)
+__global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(kThreads, 1)
 lstm_rec_tc3_kernel(Params p) {
+    constexpr int NW = kThreads / 32;        // 16 warps: 4 TMEM lane quarters x 4 column groups
     constexpr int PASSES = NB > 64 ? 2 : 1;
     constexpr int RB = NB / PASSES;          // rows transposed through `red` per pass
-    constexpr int HC = RB / 2;               // accumulator columns read per warp per pass
-    constexpr int P = NB / 8;                // rows per gate thread
-    constexpr int PP = P / PASSES;           // rows per gate thread per pass
+    constexpr int HC = RB / (NW / 4);        // accumulator columns read per warp per pass
+    constexpr int P = (NB + NW - 1) / NW;    // rows per gate thread (row i = warp + NW * q)
     constexpr int kHi = NB * 128;            // bytes of one hi (or lo) slab
     constexpr int kBf = NB * 64;             // bytes of one bf16 slab
     constexpr int kSlab = 2 * kHi + kBf;     // [hi | lo | bf16] of one 32-wide K range
-    static_assert(NB % 16 == 0 && P % PASSES == 0, "NB");
+    static_assert(NB % 16 == 0 && RB % (NW / 4) == 0, "NB");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* T = smem;                                             // 8 slabs x kSlab
@@ -147,8 +156,8 @@ lstm_rec_tc3_kernel(Params p) {
     uint8_t* stage = p.stage + (size_t)blockIdx.x * kStageBytes;
 
     // ---- one-time setup ------------------------------------------------------------------------
-    for (int i = tid; i < (8 * kSlab) / 16; i += 256) reinterpret_cast<float4*>(T)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int i = tid; i < kSlab / 16; i += 256) reinterpret_cast<float4*>(stage)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < (8 * kSlab) / 16; i += kThreads) reinterpret_cast<float4*>(T)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < kSlab / 16; i += kThreads) reinterpret_cast<float4*>(stage)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (tid < NB) s_len[tid] = tid < nrows ? p.len_sorted[r0 + tid] : 0;
     if (tid == 0) {
         mbar_init(mma_done, 8);
@@ -243,7 +252,7 @@ lstm_rec_tc3_kernel(Params p) {
         float xi[P], xf[P], xgg[P], xo[P], xres[P], yv[P];
 #pragma unroll
         for (int q = 0; q < P; ++q) {
-            const int i = warp + 8 * q;
+            const int i = warp + NW * q;
             xi[q] = xf[q] = xgg[q] = xo[q] = xres[q] = yv[q] = 0.f;
             if (i < nact) {
                 if (p.x_in) xres[q] = __ldg(p.x_in + (size_t)(row_t + i) * kEnc + ocol);
@@ -261,20 +270,20 @@ lstm_rec_tc3_kernel(Params p) {
 #pragma unroll
         for (int pass = 0; pass < PASSES; ++pass) {
             {
+                // warps w, w+4, w+8, w+12 share a TMEM lane quarter and split the columns 4 ways
                 uint32_t d[HC];
-                const int qd = warp & 3, half = warp >> 2;
-                tmem_ld_cols<HC>(tmem_d + ((uint32_t)(32 * qd) << 16) + (uint32_t)(pass * RB + half * HC), d);
+                const int qd = warp & 3, cg4 = warp >> 2;
+                tmem_ld_cols<HC>(tmem_d + ((uint32_t)(32 * qd) << 16) + (uint32_t)(pass * RB + cg4 * HC), d);
                 const int m = 32 * qd + lane;
 #pragma unroll
-                for (int n = 0; n < HC; ++n) red[(half * HC + n) * 128 + m] = __uint_as_float(d[n]);
+                for (int n = 0; n < HC; ++n) red[(cg4 * HC + n) * 128 + m] = __uint_as_float(d[n]);
             }
             tc_fence_before();
             __syncthreads();
 #pragma unroll
-            for (int qq = 0; qq < PP; ++qq) {
-                const int q = pass * PP + qq;
-                const int i = warp + 8 * q;              // rows [pass*RB, pass*RB + RB)
-                if (i < nact) {
+            for (int q = 0; q < P; ++q) {
+                const int i = warp + NW * q;
+                if (i >= pass * RB && i < (pass + 1) * RB && i < nact) {    // rows of this pass
                     const float* rr = red + (i - pass * RB) * 128 + uu;
                     const float gi = xi[q] + rr[0];
                     const float gf = xf[q] + rr[32];
@@ -308,7 +317,7 @@ lstm_rec_tc3_kernel(Params p) {
         }
 #pragma unroll
         for (int q = 0; q < P; ++q) {
-            const int i = warp + 8 * q;
+            const int i = warp + NW * q;
             if (i < nact) {
                 const size_t row = (size_t)(row_t + i);
                 if (p.y_packed) p.y_packed[row * kEnc + ocol] = yv[q];
@@ -319,7 +328,7 @@ lstm_rec_tc3_kernel(Params p) {
 
 #pragma unroll
     for (int q = 0; q < P; ++q) {
-        const int i = warp + 8 * q;
+        const int i = warp + NW * q;
         if (i < nrows) {
             p.h_fin[(size_t)(r0 + i) * kEnc + ocol] = h_reg[q];
             p.c_fin[(size_t)(r0 + i) * kEnc + ocol] = c_reg[q];
@@ -351,7 +360,7 @@ static int launch(const Params& p, cudaStream_t st) {
         ASR_CUDA(cudaFuncSetAttribute(lstm_rec_tc3_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = true;
     }
-    lstm_rec_tc3_kernel<NB><<<2 * p.nchunks * 8, 256, smem, st>>>(p);
+    lstm_rec_tc3_kernel<NB><<<2 * p.nchunks * 8, kThreads, smem, st>>>(p);
     ASR_CHECK_LAUNCH();
     return ASR_OK;
 }
