@@ -278,3 +278,42 @@ def check_batch_invariance(B=12, k=4, seconds=3.0, seed=900):
     tp, lp, sp, xp = m.transcribe(np.concatenate([pcms[j] for j in perm]), offp, bw=k, int2word=i2w)
     perm_ok = int(all(xp[i] == texts[j] for i, j in enumerate(perm)))
     return {"single_eq_batch": same, "of": 3, "perm_invariant": perm_ok}
+
+
+def check_config_shape(B, k, seconds_list, lm_seed=None, wseed=1234, eos_bias=8.0, seed0=3000, lm_weight=0.3,
+                       length_weight=2.0):
+    """BASELINE.json configs at their real utterance lengths, fused path (PCM in) vs the oracle on
+    the same seeded inputs.  Returns exact-match statistics (near-ties below fp32 noise may flip)."""
+    from chinese_asr_b200.lm import NGramLM
+    weights = O.make_weights(wseed, "sharp", eos_bias=eos_bias)
+    m = get_model((wseed, "sharp", eos_bias), weights)
+    w2i, i2w = vocab()
+    ns = [int(16000 * s) for s in seconds_list]
+    pcms = [O.synth_pcm(seed0 + i, n) for i, n in enumerate(ns)]
+    feats = [O.features(p) for p in pcms]
+    lens = torch.tensor([f.size(0) for f in feats])
+    lm_o = O.NGramLM(seed=lm_seed, word2int=w2i) if lm_seed else None
+    lm_d = NGramLM(lm_o.tables(), w2i) if lm_o else None
+    off = np.zeros(B + 1, dtype=np.int64)
+    off[1:] = np.cumsum(ns)
+    pcm = np.concatenate(pcms)
+    if k is None:
+        o = O.greedy_decode(weights, feats, lens, i2w)
+        tok, ln, sc, texts = m.transcribe(pcm, off, bw=None, int2word=i2w)
+        otexts, oscores = o["pred_text"], None
+    else:
+        tr = {}
+        o = O.beam_decode(weights, k, feats, lens, i2w, second_pass=lm_o is not None, lm_model=lm_o,
+                          lm_weight=lm_weight if lm_o else 0.0, length_weight=length_weight if lm_o else 0.0, trace=tr)
+        tok, ln, sc, texts = m.transcribe(pcm, off, bw=k, second_pass=lm_d is not None, lm_model=lm_d,
+                                          lm_weight=lm_weight if lm_o else 0.0,
+                                          length_weight=length_weight if lm_o else 0.0, int2word=i2w)
+        otexts, oscores = o["pred_text"], o["score"]
+    same = [a == b for a, b in zip(texts, otexts)]
+    res = {"B": B, "exact": int(sum(same)), "lens_min": int(lens.min()), "lens_max": int(lens.max())}
+    if oscores is not None:
+        rel = [abs(float(a) - b) / max(1e-6, abs(b)) for a, b, s in zip(sc, oscores, same) if s]
+        res["score_rel_max"] = float(max(rel)) if rel else 0.0
+        res["oracle_min_margin"] = float(min(tr["min_margin"]))
+        res["nonempty"] = int(sum(1 for t in otexts if len(t) > 0))
+    return res

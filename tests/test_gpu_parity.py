@@ -135,3 +135,32 @@ def test_errors_are_loud(G):
         m.features([np.zeros(100, dtype=np.float32)])          # too short for one STFT frame
     with pytest.raises((AsrError, ValueError)):
         m.eval_one_batch_with_beam(m.device, 17, [torch.zeros(5, 720)], torch.tensor([5]), None, {}, second_pass=False)
+
+
+def test_config1_greedy_5s(G):
+    """BASELINE.json configs[0]: greedy decode of one 5 s utterance."""
+    r = G.check_config_shape(1, None, [5.0])
+    assert r["exact"] == 1 and r["lens_max"] == 165
+
+
+def test_config2_beam4_batch32_10s(G):
+    """configs[1]: bw=4, 32 x 10 s.  Token-exact; a flip is tolerated only as a near-tie (documented
+    in DESIGN.md section 4): at least 31 of 32 utterances must be identical."""
+    r = G.check_config_shape(32, 4, [10.0] * 32)
+    assert r["lens_max"] == 332 and r["exact"] >= 31, r
+    assert r["score_rel_max"] <= SCORE_RTOL
+
+
+def test_config3_beam16_mixed_2_to_20s(G):
+    """configs[2] in shape (mixed 2-20 s, padding / masking / EOS handling), 12 utterances."""
+    secs = [2.0, 20.0, 3.7, 11.3, 7.9, 16.4, 2.6, 13.0, 5.5, 19.2, 9.1, 4.4]
+    r = G.check_config_shape(12, 16, secs, seed0=3300, eos_bias=9.0, wseed=77)
+    assert r["lens_min"] == 65 and r["lens_max"] == 665 and r["exact"] >= 11, r
+    assert r["score_rel_max"] <= SCORE_RTOL
+
+
+def test_config4_beam8_lm_batch32_10s(G):
+    """configs[3]: bw=8 + second-pass LM rescoring, 32 x 10 s."""
+    r = G.check_config_shape(32, 8, [10.0] * 32, lm_seed=7, seed0=3600)
+    assert r["exact"] >= 31, r
+    assert r["score_rel_max"] <= SCORE_RTOL
