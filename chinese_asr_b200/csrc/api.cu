@@ -206,6 +206,78 @@ static int decoder_step(asr_handle* h, int k, int step, int cur, float temperatu
     Workspace& w = h->ws;
     const int R = h->meta.B * k;
     const int nxt = cur ^ 1;
+    h->fused_dec = h->gemm_mode == 1 && !(getenv("ASR_B200_FUSED_DEC") && atoi(getenv("ASR_B200_FUSED_DEC")) == 0) &&
+                   !(getenv("ASR_B200_GEMM_PERSIST") && atoi(getenv("ASR_B200_GEMM_PERSIST")) == 0);
+    if (h->fused_dec) {
+        // Tensor-core decoder step with producer-side operand preparation:
+        //   * the embedding part of the LSTM input projection is the pre-multiplied table E' (added in the
+        //     cell GEMM's epilogue), so the cell GEMM runs over K = 1024 = [ctx[src] | h[src]];
+        //   * the cell epilogue and the attention kernel write the tf32 hi / lo splits of h_new / ctx_new
+        //     straight into the [R, 1024] A operand of the query and vocabulary GEMMs.
+        {
+            StageScope sc(h, kStCell, st);
+            AOperand A{};
+            A.nseg = 2;
+            A.seg[0] = ASeg{w.dctx[cur], w.src_row, kEnc, kEnc};
+            A.seg[1] = ASeg{w.dh[cur], w.src_row, kDecH, kProjK};
+            {
+                StageScope sc2(h, kStSplit, st);
+                ASR_TRY(split_operand(A, R, kProjK, w.a_hi, w.a_lo, w.ctrl, st, &h->launches));
+            }
+            GemmEpilogue e{};
+            e.kind = Epi::kLstmCell;
+            e.bias = h->w.dec_b;
+            e.c_prev = w.dc[cur];
+            e.c_rowidx = w.src_row;
+            e.h_out = w.dh[nxt];
+            e.c_out = w.dc[nxt];
+            e.H = kDecH;
+            e.stop_flag = w.ctrl;
+            e.ldw = kDecK;
+            e.addrow = h->w.emb_proj;
+            e.addrow_idx = w.tok_hist + (size_t)step * R;
+            e.addrow_ld = 4 * kDecH;
+            e.split_hi = w.dec_split_hi;
+            e.split_lo = w.dec_split_lo;
+            e.split_ld = kProjK;
+            StageScope sc3(h, kStGemmKernel, st);
+            h->gemm_flops += 2.0 * R * 4 * kDecH * kProjK;
+            ASR_TRY(launch_gemm_tc(w.a_hi, w.a_lo, h->w.dec_w_hi + kEmb, h->w.dec_w_lo + kEmb, R, 4 * kDecH, kProjK, e, st,
+                                   &h->launches));
+        }
+        {
+            StageScope sc(h, kStAttn, st);
+            GemmEpilogue e{};
+            e.kind = Epi::kBias;
+            e.bias = h->w.zero_bias;
+            e.C = w.att_q;
+            e.ldc = kAtt;
+            e.stop_flag = w.ctrl;
+            e.lda = kProjK;
+            {
+                StageScope sc3(h, kStGemmKernel, st);
+                h->gemm_flops += 2.0 * R * kAtt * kDecH;
+                ASR_TRY(launch_gemm_tc(w.dec_split_hi, w.dec_split_lo, h->w.att_w_hidden_t_hi, h->w.att_w_hidden_t_lo, R, kAtt,
+                                       kDecH, e, st, &h->launches));
+            }
+            ASR_TRY(launch_attention(h, k, step, nxt, d_align_step, st));
+        }
+        {
+            StageScope sc(h, kStProj, st);
+            GemmEpilogue e{};
+            e.kind = temperature == 1.f ? Epi::kBias : Epi::kBiasScale;
+            e.bias = h->w.proj_b;
+            e.C = w.logits;
+            e.ldc = kVocab;
+            e.scale = temperature;
+            e.stop_flag = w.ctrl;
+            StageScope sc3(h, kStGemmKernel, st);
+            h->gemm_flops += 2.0 * R * kVocab * kProjK;
+            ASR_TRY(launch_gemm_tc(w.dec_split_hi, w.dec_split_lo, h->w.proj_w_hi, h->w.proj_w_lo, R, kVocab, kProjK, e, st,
+                                   &h->launches));
+        }
+        return ASR_OK;
+    }
     {
         StageScope sc(h, kStCell, st);
         AOperand A{};
@@ -436,7 +508,7 @@ int asr_create(asr_handle** out, const asr_weights* wt, const asr_feature_consts
         if ((rc = dev_upload(pool, &h->w.att_w_enc_t, t)) != ASR_OK) return rc;
     }
     {
-        std::vector<float> t((size_t)kAtt * kDecH), z(kAtt, 0.f);
+        std::vector<float> t((size_t)kAtt * kDecH), z(4 * kDecH, 0.f);
         for (int c = 0; c < kDecH; ++c)
             for (int d = 0; d < kAtt; ++d) t[(size_t)d * kDecH + c] = wt->att_w_hidden[(size_t)c * kAtt + d];
         if ((rc = dev_upload(pool, &h->w.att_w_hidden_t, t)) != ASR_OK) return rc;
@@ -454,6 +526,21 @@ int asr_create(asr_handle** out, const asr_weights* wt, const asr_feature_consts
     if ((rc = split_weight(h, h->w.dec_w, 4 * kDecH, kDecK, &h->w.dec_w_hi, &h->w.dec_w_lo)) != ASR_OK) return rc;
     if ((rc = split_weight(h, h->w.proj_w, kVocab, kProjK, &h->w.proj_w_hi, &h->w.proj_w_lo)) != ASR_OK) return rc;
     if ((rc = split_weight(h, h->w.att_w_enc_t, kAtt, kEnc, &h->w.att_w_enc_t_hi, &h->w.att_w_enc_t_lo)) != ASR_OK) return rc;
+    {
+        // E' = embedding * W_ih[:, :256]^T (gate-interleaved columns): the embedding part of the decoder
+        // LSTM input projection is a table lookup added in the cell GEMM's epilogue, K drops 1280 -> 1024
+        float *e_hi = nullptr, *e_lo = nullptr;
+        if ((rc = split_weight(h, h->w.emb, kVocab, kEmb, &e_hi, &e_lo)) != ASR_OK) return rc;
+        if ((rc = dev_alloc_t(pool, &h->w.emb_proj, (size_t)kVocab * 4 * kDecH)) != ASR_OK) return rc;
+        GemmEpilogue e{};
+        e.kind = Epi::kBias;
+        e.bias = h->w.zero_bias;
+        e.C = h->w.emb_proj;
+        e.ldc = 4 * kDecH;
+        e.ldw = kDecK;                     // first 256 columns of the [2048, 1280] cell weight
+        if ((rc = launch_gemm_tc(e_hi, e_lo, h->w.dec_w_hi, h->w.dec_w_lo, kVocab, 4 * kDecH, kEmb, e, 0, nullptr)) != ASR_OK) return rc;
+        ASR_CUDA(cudaDeviceSynchronize());
+    }
     const char* env = getenv("ASR_B200_GEMM");
     // defaults: every GEMM-shaped stage and the recurrence on the tcgen05 tensor cores (3xTF32);
     // ASR_B200_GEMM=simt / ASR_B200_REC=simt|tc select the CUDA-core / smem-resident variants
@@ -560,6 +647,8 @@ int asr_reserve(asr_handle* h, int max_utts, int64_t max_rows, int max_beam, int
     }
     ASR_TRY(dev_alloc_t(pool, &w.logits, R * kVocab));
     ASR_TRY(dev_alloc_t(pool, &w.att_q, R * kAtt));
+    ASR_TRY(dev_alloc_t(pool, &w.dec_split_hi, R * kProjK));
+    ASR_TRY(dev_alloc_t(pool, &w.dec_split_lo, R * kProjK));
     ASR_TRY(dev_alloc_t(pool, &w.att_part, (size_t)max_utts * 8 * max_beam * 514));
     // raw attention scores are only exported by the greedy path (k = 1)
     w.att_score_ld = std::min<int64_t>(max_rows, 4096);

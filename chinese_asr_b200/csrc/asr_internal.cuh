@@ -95,6 +95,14 @@ struct GemmEpilogue {
     float* c_out;          // [M, H]
     int H;
     const int* stop_flag;  // optional: kernel returns immediately when *stop_flag >= 0
+    // tcgen05 engine only:
+    int lda, ldw;          // row strides (floats) of the pre-split A / W operands; 0 = K (dense)
+    const float* addrow;   // kLstmCell: gate pre-activations += addrow[addrow_idx[row]][n] (the
+    const int* addrow_idx; //   pre-multiplied embedding table E' = emb * W_ih[:, :256]^T, row = token)
+    int addrow_ld;
+    float* split_hi;       // kLstmCell: also write rn_tf32(h) / residual into [M, split_ld] at column u,
+    float* split_lo;       //   the A operand of the query / vocabulary GEMMs (no separate split pass)
+    int split_ld;
 };
 
 // C[M,N] = A[M,K] * W[N,K]^T (+ epilogue).  fp32 in, fp32 accumulate.
@@ -157,7 +165,8 @@ struct PackedWeights {
     float* att_w_hidden_t = nullptr;     // [128, 512] (W_hidden transposed -> [N, K]) for the query GEMM
     float* att_w_hidden_t_hi = nullptr;
     float* att_w_hidden_t_lo = nullptr;
-    float* zero_bias = nullptr;          // [128] zeros
+    float* zero_bias = nullptr;          // [2048] zeros
+    float* emb_proj = nullptr;           // [5004, 2048] E' = embedding * W_ih[:, :256]^T (gate-interleaved columns)
 };
 
 struct LmTables {
@@ -218,6 +227,8 @@ struct Workspace {
     float* dctx[2] = {};
     float* logits = nullptr;     // [R, 5004]
     float* att_q = nullptr;      // [R, 128] query projection of the current step
+    float* dec_split_hi = nullptr;   // [R, 1024] tf32 hi of [h_new | ctx_new], written by the producing kernels
+    float* dec_split_lo = nullptr;
     float* att_part = nullptr;   // [B, S, k, 2 + 512] partial (max, sum, ctx)
     float* att_score = nullptr;  // [R, Lmax_cap] raw scores (alignment export)
     int* att_ticket = nullptr;   // [B]
@@ -272,6 +283,7 @@ struct asr_handle {
     bool timing = false;
     int gemm_mode = 0;           // 0 = CUDA-core fp32 FMA, 1 = tcgen05 3xTF32
     int rec_mode = 0;            // encoder recurrence: 0 = CUDA-core (register-stationary W_hh), 1 = tcgen05
+    bool fused_dec = false;      // decoder step with pre-multiplied embeddings and producer-side operand splits
     double gemm_flops = 0.0;     // algorithmic 2*M*N*K of every GEMM-engine launch since the last reset
     cudaEvent_t ev[2 * 1024] = {};
     int n_ev = 0;

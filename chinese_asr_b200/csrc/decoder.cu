@@ -116,6 +116,9 @@ struct AttnParams {
     const float* v;         // [128]
     const int* uoff;        // [B + 1]
     float* ctx_out;         // [R, 512]
+    float* split_hi;        // optional: tf32 hi / lo split of ctx written at column 512 of the
+    float* split_lo;        //   [R, split_ld] A operand of the vocabulary GEMM
+    int split_ld;
     float* part;            // [B, S, k, 514]
     int* ticket;            // [B]
     float* raw_score;       // [R, score_ld] or nullptr (alignment export)
@@ -126,8 +129,20 @@ struct AttnParams {
     long long score_ld;
 };
 
+__device__ __forceinline__ void write_ctx_split(const AttnParams& p, int row, int tid, float2 o) {
+    if (!p.split_hi) return;
+    float2 hi, lo;
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(o.x)); hi.x = __uint_as_float(u);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(o.y)); hi.y = __uint_as_float(u);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(o.x - hi.x)); lo.x = __uint_as_float(u);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(o.y - hi.y)); lo.y = __uint_as_float(u);
+    reinterpret_cast<float2*>(p.split_hi + (size_t)row * p.split_ld + kDecH)[tid] = hi;
+    reinterpret_cast<float2*>(p.split_lo + (size_t)row * p.split_ld + kDecH)[tid] = lo;
+}
+
 template <int K>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, K <= 8 ? 4 : 2)
 attention_kernel(AttnParams p) {
     if (p.ctrl[0] >= 0) return;
     extern __shared__ __align__(16) float sm[];
@@ -290,6 +305,7 @@ attention_kernel(AttnParams p) {
                 const float inv = s_sum[kb];
                 float2 o = make_float2(acc[kb].x / inv, acc[kb].y / inv);
                 reinterpret_cast<float2*>(p.ctx_out + (size_t)(u * k + kb) * kEnc)[tid] = o;
+                write_ctx_split(p, u * k + kb, tid, o);
             }
         }
         if (p.align_out) {       // greedy only (k == 1)
@@ -336,6 +352,7 @@ attention_kernel(AttnParams p) {
         }
         o.x /= denom; o.y /= denom;
         reinterpret_cast<float2*>(p.ctx_out + (size_t)(u * k + kb) * kEnc)[tid] = o;
+        write_ctx_split(p, u * k + kb, tid, o);
         if (p.align_out && kb == 0) {
             const float* rs = p.raw_score + (size_t)(u * k) * p.score_ld;
             for (int l = tid; l < p.Lmax; l += 256)
@@ -355,6 +372,9 @@ int launch_attention(asr_handle* h, int k, int step, int nxt, float* d_align_ste
     p.v = h->w.att_v;
     p.uoff = m.d_uoff_sorted;
     p.ctx_out = w.dctx[nxt];
+    p.split_hi = h->fused_dec ? w.dec_split_hi : nullptr;
+    p.split_lo = w.dec_split_lo;
+    p.split_ld = kProjK;
     p.part = w.att_part;
     p.ticket = w.att_ticket;
     p.order = m.d_order;

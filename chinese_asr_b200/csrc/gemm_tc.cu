@@ -113,6 +113,11 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
 }
 
 __device__ __forceinline__ float sigm(float x) { return 1.f / (1.f + expf(-x)); }
+__device__ __forceinline__ float rn_tf32_e(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
 
 template <int BN, int BKF, int STAGES>
 struct SmemLayout {
@@ -460,10 +465,15 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, cons
                     const float4 cp0 = *reinterpret_cast<const float4*>(epi.c_prev + (size_t)crow * epi.H + (n >> 2));
                     const float4 cp1 = *reinterpret_cast<const float4*>(epi.c_prev + (size_t)crow * epi.H + (n >> 2) + 4);
                     const float cp[8] = {cp0.x, cp0.y, cp0.z, cp0.w, cp1.x, cp1.y, cp1.z, cp1.w};
+                    const float* arow = epi.addrow ? epi.addrow + (size_t)epi.addrow_idx[row] * epi.addrow_ld + n : nullptr;
                     float hv[8], cv[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(epi.bias + n + 4 * j));
+                        float4 b4 = __ldg(reinterpret_cast<const float4*>(epi.bias + n + 4 * j));
+                        if (arow) {
+                            const float4 e4 = __ldg(reinterpret_cast<const float4*>(arow + 4 * j));
+                            b4.x += e4.x; b4.y += e4.y; b4.z += e4.z; b4.w += e4.w;
+                        }
                         const float gi = __uint_as_float(r[4 * j]) + b4.x;
                         const float gf = __uint_as_float(r[4 * j + 1]) + b4.y;
                         const float gg = __uint_as_float(r[4 * j + 2]) + b4.z;
@@ -477,6 +487,17 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, cons
                     ho[1] = make_float4(hv[4], hv[5], hv[6], hv[7]);
                     co[0] = make_float4(cv[0], cv[1], cv[2], cv[3]);
                     co[1] = make_float4(cv[4], cv[5], cv[6], cv[7]);
+                    if (epi.split_hi) {
+                        float hh[8], hl[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) { hh[j] = rn_tf32_e(hv[j]); hl[j] = rn_tf32_e(hv[j] - hh[j]); }
+                        float4* sh = reinterpret_cast<float4*>(epi.split_hi + (size_t)row * epi.split_ld + (n >> 2));
+                        float4* sl = reinterpret_cast<float4*>(epi.split_lo + (size_t)row * epi.split_ld + (n >> 2));
+                        sh[0] = make_float4(hh[0], hh[1], hh[2], hh[3]);
+                        sh[1] = make_float4(hh[4], hh[5], hh[6], hh[7]);
+                        sl[0] = make_float4(hl[0], hl[1], hl[2], hl[3]);
+                        sl[1] = make_float4(hl[4], hl[5], hl[6], hl[7]);
+                    }
                 }
             } else {
                 const bool sc = epi.kind == Epi::kBiasScale;
@@ -586,11 +607,11 @@ static EncodeTiledFn get_encode() {
 }
 
 // 2-D fp32 tensor [rows, K] row-major -> box [box_rows, 32] with 128-byte swizzle
-static int make_map(CUtensorMap* map, const float* base, int rows, int K, int box_rows, int BKF) {
+static int make_map(CUtensorMap* map, const float* base, int rows, int K, int box_rows, int BKF, int ld = 0) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return ASR_ERR_CUDA; }
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)K * sizeof(float)};
+    cuuint64_t strides[1] = {(cuuint64_t)(ld > 0 ? ld : K) * sizeof(float)};
     cuuint32_t box[2] = {(cuuint32_t)BKF, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
@@ -620,10 +641,10 @@ template <int BN, int BKF, int STAGES>
 static int launch_tc_cfg(const float* a_hi, const float* a_lo, const float* w_hi, const float* w_lo, int M, int N,
                          int K, const GemmEpilogue& epi, cudaStream_t st) {
     CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
-    ASR_TRY(tc::make_map(&ma_hi, a_hi, M, K, tc::BM, BKF));
-    ASR_TRY(tc::make_map(&ma_lo, a_lo, M, K, tc::BM, BKF));
-    ASR_TRY(tc::make_map(&mw_hi, w_hi, N, K, BN, BKF));
-    ASR_TRY(tc::make_map(&mw_lo, w_lo, N, K, BN, BKF));
+    ASR_TRY(tc::make_map(&ma_hi, a_hi, M, K, tc::BM, BKF, epi.lda));
+    ASR_TRY(tc::make_map(&ma_lo, a_lo, M, K, tc::BM, BKF, epi.lda));
+    ASR_TRY(tc::make_map(&mw_hi, w_hi, N, K, BN, BKF, epi.ldw));
+    ASR_TRY(tc::make_map(&mw_lo, w_lo, N, K, BN, BKF, epi.ldw));
     static const bool persist = !(getenv("ASR_B200_GEMM_PERSIST") && atoi(getenv("ASR_B200_GEMM_PERSIST")) == 0);
     if (persist) {
         static bool attr_p = false;
