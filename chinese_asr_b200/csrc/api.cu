@@ -342,15 +342,61 @@ static int beam_decode_device(asr_handle* h, int k, int max_len, float temperatu
                               double lm_weight, double length_weight, cudaStream_t st) {
     ASR_TRY(check_decode_ready(h, k, max_len));
     if (second_pass && !h->lm.loaded) { set_error("second_pass requires asr_set_lm"); return ASR_ERR_STATE; }
-    ASR_TRY(decode_init(h, k, max_len, false, st));
-    int cur = 0;
-    for (int step = 0; step < max_len; ++step) {
-        ASR_TRY(decoder_step(h, k, step, cur, temperature, nullptr, st));
-        StageScope sc(h, kStTopk, st);
-        ASR_TRY(launch_row_topk(h, k, step, st));
-        ASR_TRY(launch_beam_bookkeep(h, k, step, max_len, st));
-        cur ^= 1;
+    // The legacy default stream cannot be captured: a blocking stream of the handle stands in for it
+    // (implicitly ordered with the legacy stream on both sides, so callers see the same semantics).
+    cudaStream_t caller_st = st;
+    static const bool use_graph = !(getenv("ASR_B200_GRAPH") && atoi(getenv("ASR_B200_GRAPH")) == 0);
+    if (use_graph && !h->timing && (st == nullptr || st == cudaStreamLegacy)) {
+        if (!h->graph_stream) ASR_CUDA(cudaStreamCreate(&h->graph_stream));
+        st = h->graph_stream;
     }
+    auto run_loop = [&]() -> int {
+        ASR_TRY(decode_init(h, k, max_len, false, st));
+        int cur = 0;
+        for (int step = 0; step < max_len; ++step) {
+            ASR_TRY(decoder_step(h, k, step, cur, temperature, nullptr, st));
+            StageScope sc(h, kStTopk, st);
+            ASR_TRY(launch_row_topk(h, k, step, st));
+            ASR_TRY(launch_beam_bookkeep(h, k, step, max_len, st));
+            cur ^= 1;
+        }
+        return ASR_OK;
+    };
+    // The 40-step loop is launch-bound at the margins (~6 kernels per step, no host sync): once a
+    // batch shape has been seen, the whole loop is captured into a CUDA graph and replayed.  All
+    // per-batch data (lengths, offsets, tokens) lives at fixed device addresses, so only the shape
+    // (B, k, max_len, Lmax, frames, temperature, engines) keys the graph.
+    int temp_bits = 0;
+    memcpy(&temp_bits, &temperature, sizeof(int));
+    const long long key[8] = {h->meta.B, k, max_len, h->meta.Lmax, (long long)h->meta.rows, temp_bits,
+                              h->gemm_mode, h->rec_mode};
+    if (use_graph && !h->timing) {
+        if (h->graph_exec && memcmp(key, h->graph_key, sizeof(key)) == 0) {
+            ASR_CUDA(cudaGraphLaunch(h->graph_exec, st));
+            h->launches += h->graph_launches;
+        } else if (memcmp(key, h->graph_seen, sizeof(key)) == 0) {
+            // second time this shape is decoded: capture (every lazy attribute / allocation is done)
+            if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+            cudaGraph_t g = nullptr;
+            const int64_t launches_before = h->launches;
+            ASR_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            const int rc = run_loop();
+            const cudaError_t ce = cudaStreamEndCapture(st, &g);
+            if (rc != ASR_OK) { if (g) cudaGraphDestroy(g); return rc; }
+            ASR_CUDA(ce);
+            ASR_CUDA(cudaGraphInstantiate(&h->graph_exec, g, 0));
+            cudaGraphDestroy(g);
+            memcpy(h->graph_key, key, sizeof(key));
+            h->graph_launches = h->launches - launches_before;
+            ASR_CUDA(cudaGraphLaunch(h->graph_exec, st));
+        } else {
+            memcpy(h->graph_seen, key, sizeof(key));
+            ASR_TRY(run_loop());
+        }
+    } else {
+        ASR_TRY(run_loop());
+    }
+    st = caller_st;
     {
         StageScope sc(h, kStTopk, st);
         ASR_TRY(launch_beam_finalise(h, k, max_len, second_pass, lm_weight, length_weight, st));
@@ -592,6 +638,8 @@ int asr_test_gemm(asr_handle* h, const float* d_A, const float* d_W, const float
 int asr_destroy(asr_handle* h) {
     if (!h) return ASR_OK;
     cudaDeviceSynchronize();
+    if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+    if (h->graph_stream) cudaStreamDestroy(h->graph_stream);
     for (void* p : h->weight_allocs) cudaFree(p);
     for (void* p : h->ws.allocs) cudaFree(p);
     if (h->ws.h_stage) cudaFreeHost(h->ws.h_stage);
@@ -610,6 +658,9 @@ int asr_reserve(asr_handle* h, int max_utts, int64_t max_rows, int max_beam, int
     cudaDeviceSynchronize();
     for (void* p : w.allocs) cudaFree(p);
     w.allocs.clear();
+    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }   // captured pointers are stale
+    memset(h->graph_key, 0, sizeof(h->graph_key));
+    memset(h->graph_seen, 0, sizeof(h->graph_seen));
     if (w.h_stage) { cudaFreeHost(w.h_stage); w.h_stage = nullptr; }
     w.max_utts = max_utts; w.max_rows = max_rows; w.max_beam = max_beam; w.max_len = max_len;
     w.max_samples = max_samples;

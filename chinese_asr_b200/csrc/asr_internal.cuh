@@ -283,6 +283,11 @@ struct asr_handle {
     bool timing = false;
     int gemm_mode = 0;           // 0 = CUDA-core fp32 FMA, 1 = tcgen05 3xTF32
     int rec_mode = 0;            // encoder recurrence: 0 = CUDA-core (register-stationary W_hh), 1 = tcgen05
+    cudaGraphExec_t graph_exec = nullptr;   // captured beam-decode loop for the shape in graph_key
+    long long graph_key[8] = {};
+    long long graph_seen[8] = {};
+    int64_t graph_launches = 0;             // kernels inside the captured graph
+    cudaStream_t graph_stream = nullptr;    // blocking stream standing in for the legacy stream (not capturable)
     bool fused_dec = false;      // decoder step with pre-multiplied embeddings and producer-side operand splits
     double gemm_flops = 0.0;     // algorithmic 2*M*N*K of every GEMM-engine launch since the last reset
     cudaEvent_t ev[2 * 1024] = {};

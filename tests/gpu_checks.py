@@ -280,6 +280,31 @@ def check_batch_invariance(B=12, k=4, seconds=3.0, seed=900):
     return {"single_eq_batch": same, "of": 3, "perm_invariant": perm_ok}
 
 
+def check_graph_replay(B=6, k=4, n=40000, seed=700):
+    """The beam loop is replayed from a CUDA graph once a batch shape repeats (eager, capture,
+    replay on calls 1-3).  Batches with the same shape but different audio must give exactly what
+    the eager loop gives (stage timing forces the eager loop), also after another shape intervened."""
+    weights = O.make_weights(1234, "sharp", eos_bias=8.0)
+    m = get_model((1234, "sharp", 8.0), weights)
+    _, i2w = vocab()
+    off = np.arange(B + 1, dtype=np.int64) * n
+    batches = [np.concatenate([O.synth_pcm(seed + 10 * j + i, n) for i in range(B)]) for j in range(4)]
+    other = np.concatenate([O.synth_pcm(seed + 99 + i, n // 2) for i in range(B)])
+    off2 = np.arange(B + 1, dtype=np.int64) * (n // 2)
+    got = [m.transcribe(b, off, bw=k, int2word=i2w) for b in batches[:3]]
+    m.transcribe(other, off2, bw=k, int2word=i2w)
+    got.append(m.transcribe(batches[3], off, bw=k, int2word=i2w))
+    m.stage_timing(True)
+    try:
+        want = [m.transcribe(b, off, bw=k, int2word=i2w) for b in batches]
+    finally:
+        m.stage_timing(False)
+    same = sum(int(np.array_equal(g[0], w[0]) and np.array_equal(g[1], w[1]) and np.array_equal(g[2], w[2]))
+               for g, w in zip(got, want))
+    distinct = int(len({tuple(g[3]) for g in got}) > 1)
+    return {"replay_eq_eager": same, "of": len(batches), "batches_differ": distinct}
+
+
 def check_config_shape(B, k, seconds_list, lm_seed=None, wseed=1234, eos_bias=8.0, seed0=3000, lm_weight=0.3,
                        length_weight=2.0):
     """BASELINE.json configs at their real utterance lengths, fused path (PCM in) vs the oracle on

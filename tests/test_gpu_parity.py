@@ -107,6 +107,11 @@ def test_batch_invariance(G):
     assert r["single_eq_batch"] == r["of"] and r["perm_invariant"] == 1
 
 
+def test_graph_replay_equals_eager_loop(G):
+    r = G.check_graph_replay()
+    assert r["replay_eq_eager"] == r["of"] and r["batches_differ"] == 1, r
+
+
 def test_full_size_properties(G):
     """BASELINE.json configs[1] shape (bw=4, 32 x 10 s) through the fused path: every utterance
     decodes, lengths are within [0, max_len], scores are finite and the result is reproducible
