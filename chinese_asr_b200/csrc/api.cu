@@ -142,10 +142,11 @@ static int gemm(asr_handle* h, const AOperand& A, const float* W, const float* W
     return launch_gemm(A, W, M, N, K, epi, st, &h->launches);
 }
 
-static int split_weight(asr_handle* h, const float* w, int N, int K, float** hi, float** lo) {
+static int split_weight(asr_handle* h, const float* w, int N, int K, float** hi, float** lo,
+                        int fmt = kSplitWeight) {
     ASR_TRY(dev_alloc_t(h->weight_allocs, hi, (size_t)N * K));
     ASR_TRY(dev_alloc_t(h->weight_allocs, lo, (size_t)N * K));
-    ASR_TRY(split_operand(plain_a(w, K, K), N, K, *hi, *lo, nullptr, 0, nullptr));
+    ASR_TRY(split_operand(plain_a(w, K, K), N, K, *hi, *lo, nullptr, 0, nullptr, fmt));
     ASR_CUDA(cudaDeviceSynchronize());
     return ASR_OK;
 }
@@ -206,8 +207,7 @@ static int decoder_step(asr_handle* h, int k, int step, int cur, float temperatu
     Workspace& w = h->ws;
     const int R = h->meta.B * k;
     const int nxt = cur ^ 1;
-    h->fused_dec = h->gemm_mode == 1 && !(getenv("ASR_B200_FUSED_DEC") && atoi(getenv("ASR_B200_FUSED_DEC")) == 0) &&
-                   !(getenv("ASR_B200_GEMM_PERSIST") && atoi(getenv("ASR_B200_GEMM_PERSIST")) == 0);
+    h->fused_dec = h->gemm_mode == 1 && !(getenv("ASR_B200_FUSED_DEC") && atoi(getenv("ASR_B200_FUSED_DEC")) == 0);
     if (h->fused_dec) {
         // Tensor-core decoder step with producer-side operand preparation:
         //   * the embedding part of the LSTM input projection is the pre-multiplied table E' (added in the
@@ -565,7 +565,7 @@ int asr_create(asr_handle** out, const asr_weights* wt, const asr_feature_consts
     for (int layer = 0; layer < 4; ++layer) {
         const int K = layer == 0 ? kFeat : kEnc;
         if ((rc = split_weight(h, h->w.enc_w_ih[layer], 2 * kGates, K, &h->w.enc_w_ih_hi[layer], &h->w.enc_w_ih_lo[layer])) != ASR_OK) return rc;
-        if ((rc = split_weight(h, h->w.enc_w_hh[layer], 2 * kGates, kEncH, &h->w.enc_w_hh_hi[layer], &h->w.enc_w_hh_lo[layer])) != ASR_OK) return rc;
+        if ((rc = split_weight(h, h->w.enc_w_hh[layer], 2 * kGates, kEncH, &h->w.enc_w_hh_hi[layer], &h->w.enc_w_hh_lo[layer], kSplitLegacy)) != ASR_OK) return rc;
         if ((rc = dev_alloc_t(pool, &h->w.enc_w_hh_lo_bf[layer], (size_t)2 * kGates * kEncH / 2)) != ASR_OK) return rc;
         if ((rc = pack_bf16_pairs(h->w.enc_w_hh_lo[layer], h->w.enc_w_hh_lo_bf[layer], (long long)2 * kGates * kEncH / 2)) != ASR_OK) return rc;
     }
@@ -576,7 +576,7 @@ int asr_create(asr_handle** out, const asr_weights* wt, const asr_feature_consts
         // E' = embedding * W_ih[:, :256]^T (gate-interleaved columns): the embedding part of the decoder
         // LSTM input projection is a table lookup added in the cell GEMM's epilogue, K drops 1280 -> 1024
         float *e_hi = nullptr, *e_lo = nullptr;
-        if ((rc = split_weight(h, h->w.emb, kVocab, kEmb, &e_hi, &e_lo)) != ASR_OK) return rc;
+        if ((rc = split_weight(h, h->w.emb, kVocab, kEmb, &e_hi, &e_lo, kSplitAct)) != ASR_OK) return rc;
         if ((rc = dev_alloc_t(pool, &h->w.emb_proj, (size_t)kVocab * 4 * kDecH)) != ASR_OK) return rc;
         GemmEpilogue e{};
         e.kind = Epi::kBias;
@@ -624,7 +624,7 @@ int asr_test_gemm(asr_handle* h, const float* d_A, const float* d_W, const float
         ASR_CUDA(cudaMalloc(&w_hi, sizeof(float) * (size_t)N * K));
         ASR_CUDA(cudaMalloc(&w_lo, sizeof(float) * (size_t)N * K));
         int rc = split_operand(plain_a(d_A, K, K), M, K, a_hi, a_lo, nullptr, st, &h->launches);
-        if (rc == ASR_OK) rc = split_operand(plain_a(d_W, K, K), N, K, w_hi, w_lo, nullptr, st, &h->launches);
+        if (rc == ASR_OK) rc = split_operand(plain_a(d_W, K, K), N, K, w_hi, w_lo, nullptr, st, &h->launches, kSplitWeight);
         if (rc == ASR_OK) rc = launch_gemm_tc(a_hi, a_lo, w_hi, w_lo, M, N, K, e, st, &h->launches);
         cudaError_t ce = cudaStreamSynchronize(st);
         cudaFree(a_hi); cudaFree(a_lo); cudaFree(w_hi); cudaFree(w_lo);
@@ -632,6 +632,48 @@ int asr_test_gemm(asr_handle* h, const float* d_A, const float* d_W, const float
         if (ce != cudaSuccess) { set_error("asr_test_gemm: %s", cudaGetErrorString(ce)); return ASR_ERR_CUDA; }
     }
     ASR_CUDA(cudaStreamSynchronize(st));
+    return ASR_OK;
+}
+
+// Tuning aid: average ms per launch of the tensor-core GEMM engine on an [M,K] x [N,K]^T problem with
+// pre-split operands (events on `stream`, `iters` launches after 2 warm-ups).
+int asr_bench_gemm(asr_handle* h, int M, int N, int K, int iters, float* ms_out, void* stream) {
+    if (!h || !ms_out || M < 1 || N < 1 || K < 8 || iters < 1) { set_error("asr_bench_gemm: bad argument"); return ASR_ERR_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    float *a, *a_hi, *a_lo, *w, *w_hi, *w_lo, *c, *bias;
+    ASR_CUDA(cudaMalloc(&a, sizeof(float) * (size_t)M * K));
+    ASR_CUDA(cudaMalloc(&a_hi, sizeof(float) * (size_t)M * K));
+    ASR_CUDA(cudaMalloc(&a_lo, sizeof(float) * (size_t)M * K));
+    ASR_CUDA(cudaMalloc(&w, sizeof(float) * (size_t)N * K));
+    ASR_CUDA(cudaMalloc(&w_hi, sizeof(float) * (size_t)N * K));
+    ASR_CUDA(cudaMalloc(&w_lo, sizeof(float) * (size_t)N * K));
+    ASR_CUDA(cudaMalloc(&c, sizeof(float) * (size_t)M * N));
+    ASR_CUDA(cudaMalloc(&bias, sizeof(float) * (size_t)N));
+    ASR_CUDA(cudaMemsetAsync(a, 0x3c, sizeof(float) * (size_t)M * K, st));
+    ASR_CUDA(cudaMemsetAsync(w, 0x3c, sizeof(float) * (size_t)N * K, st));
+    ASR_CUDA(cudaMemsetAsync(bias, 0, sizeof(float) * (size_t)N, st));
+    GemmEpilogue e{};
+    e.kind = Epi::kBias;
+    e.bias = bias;
+    e.C = c;
+    e.ldc = N;
+    int rc = split_operand(plain_a(a, K, K), M, K, a_hi, a_lo, nullptr, st, nullptr, kSplitAct);
+    if (rc == ASR_OK) rc = split_operand(plain_a(w, K, K), N, K, w_hi, w_lo, nullptr, st, nullptr, kSplitWeight);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int i = 0; i < iters + 2 && rc == ASR_OK; ++i) {
+        if (i == 2) cudaEventRecord(e0, st);
+        rc = launch_gemm_tc(a_hi, a_lo, w_hi, w_lo, M, N, K, e, st, nullptr);
+    }
+    cudaEventRecord(e1, st);
+    cudaError_t ce = cudaStreamSynchronize(st);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    *ms_out = ms / iters;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(a); cudaFree(a_hi); cudaFree(a_lo); cudaFree(w); cudaFree(w_hi); cudaFree(w_lo); cudaFree(c); cudaFree(bias);
+    if (rc != ASR_OK) return rc;
+    if (ce != cudaSuccess) { set_error("asr_bench_gemm: %s", cudaGetErrorString(ce)); return ASR_ERR_CUDA; }
     return ASR_OK;
 }
 

@@ -108,9 +108,11 @@ struct GemmEpilogue {
 // C[M,N] = A[M,K] * W[N,K]^T (+ epilogue).  fp32 in, fp32 accumulate.
 int launch_gemm(const AOperand& A, const float* W, int M, int N, int K, const GemmEpilogue& epi,
                 cudaStream_t st, int64_t* launches);
-// tcgen05 3xTF32 path (gemm_tc.cu): operands pre-split into tf32 hi / lo parts
+// tcgen05 split-precision path (gemm_tc.cu): operands pre-split into a tf32 `hi` part and a `lo`
+// buffer of the same byte size holding the bf16 cross-term operand (layout: see split_operand_kernel)
+enum { kSplitLegacy = 0, kSplitAct = 1, kSplitWeight = 2 };
 int split_operand(const AOperand& A, int M, int K, float* hi, float* lo, const int* stop_flag,
-                  cudaStream_t st, int64_t* launches);
+                  cudaStream_t st, int64_t* launches, int fmt = kSplitAct);
 int launch_gemm_tc(const float* a_hi, const float* a_lo, const float* w_hi, const float* w_lo, int M,
                    int N, int K, const GemmEpilogue& epi, cudaStream_t st, int64_t* launches);
 // a weight matrix with its pre-split copies

@@ -131,14 +131,18 @@ struct AttnParams {
 
 __device__ __forceinline__ void write_ctx_split(const AttnParams& p, int row, int tid, float2 o) {
     if (!p.split_hi) return;
-    float2 hi, lo;
-    uint32_t u;
+    // thread `tid` owns ctx[2 tid], ctx[2 tid + 1].  hi = rn_tf32(x); the cross operand holds, per
+    // 8-float block, 8 x bf16(x - hi) then 8 x bf16(x) (gemm_tc.cu: kSplitAct)
+    float2 hi;
+    uint32_t u, xl, xx;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(o.x)); hi.x = __uint_as_float(u);
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(o.y)); hi.y = __uint_as_float(u);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(o.x - hi.x)); lo.x = __uint_as_float(u);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(o.y - hi.y)); lo.y = __uint_as_float(u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(xl) : "f"(o.y - hi.y), "f"(o.x - hi.x));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(xx) : "f"(o.y), "f"(o.x));
     reinterpret_cast<float2*>(p.split_hi + (size_t)row * p.split_ld + kDecH)[tid] = hi;
-    reinterpret_cast<float2*>(p.split_lo + (size_t)row * p.split_ld + kDecH)[tid] = lo;
+    uint32_t* cross = reinterpret_cast<uint32_t*>(p.split_lo + (size_t)row * p.split_ld + kDecH) + (tid >> 2) * 8 + (tid & 3);
+    cross[0] = xl;
+    cross[4] = xx;
 }
 
 template <int K>

@@ -74,6 +74,15 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
@@ -112,220 +121,26 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-__device__ __forceinline__ float sigm(float x) { return 1.f / (1.f + expf(-x)); }
+// kind::f16 with bf16 operands: D=f32 (1<<4), A=B=BF16 (1<<7, 1<<10)
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// two floats -> packed bf16x2 (first argument in the low half-word), round to nearest even
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo_half, float hi_half) {
+    uint32_t u;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(u) : "f"(hi_half), "f"(lo_half));
+    return u;
+}
+
+// The epilogue runs on 4 warps per SM: libm expf / tanhf / IEEE division are long dependent chains with
+// slow-path branches that one warp per scheduler cannot overlap (measured: ~10k cycles per 32-column
+// chunk).  ex2.approx / rcp.approx forms (2 ulp) are branch-free; the encoder recurrence uses the same.
+__device__ __forceinline__ float sigm(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float tanh_e(float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); }
 __device__ __forceinline__ float rn_tf32_e(float x) {
     uint32_t u;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
     return __uint_as_float(u);
-}
-
-template <int BN, int BKF, int STAGES>
-struct SmemLayout {
-    static constexpr int kATile = BM * BKF * 4;      // 16 KB
-    static constexpr int kBTile = BN * BKF * 4;
-    static constexpr int kStage = 2 * kATile + 2 * kBTile;
-    static constexpr int kBytes = STAGES * kStage + 1024 /*align slack*/ + 256 /*barriers*/;
-};
-
-__device__ long long g_gemm_trace[1024];
-
-template <int BN, int BKF, int STAGES>
-__global__ void __launch_bounds__(192, 1)
-gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-                   const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
-                   int M, int N, int K, GemmEpilogue epi, int dbg) {
-    if (epi.stop_flag && *epi.stop_flag >= 0) return;
-    const bool trace = (dbg & 4) && blockIdx.x == 0 && blockIdx.y == gridDim.y / 2;
-    if (trace && threadIdx.x == 0) g_gemm_trace[0] = clock64();
-    using L = SmemLayout<BN, BKF, STAGES>;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * L::kStage);
-    uint64_t* full = bars;                 // [STAGES]
-    uint64_t* empty = bars + STAGES;       // [STAGES]
-    uint64_t* tmem_full = bars + 2 * STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-    const int nkb = (K + BKF - 1) / BKF;
-
-    if (warp == 0 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(tmem_full, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_hi) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w_hi) : "memory");
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "n"(BN)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(&empty[s], ph ^ 1);
-                if (trace && kb < 200) g_gemm_trace[16 + kb * 4] = clock64();
-                uint8_t* st = smem + s * L::kStage;
-                if (dbg & 2) {     // experiment: load only the hi tiles
-                    mbar_expect_tx(&full[s], L::kATile + L::kBTile);
-                    tma_load_2d(&map_a_hi, &full[s], st, kb * BKF, m0);
-                    tma_load_2d(&map_w_hi, &full[s], st + 2 * L::kATile, kb * BKF, n0);
-                    continue;
-                }
-                mbar_expect_tx(&full[s], L::kStage);
-                tma_load_2d(&map_a_hi, &full[s], st, kb * BKF, m0);
-                tma_load_2d(&map_a_lo, &full[s], st + L::kATile, kb * BKF, m0);
-                tma_load_2d(&map_w_hi, &full[s], st + 2 * L::kATile, kb * BKF, n0);
-                tma_load_2d(&map_w_lo, &full[s], st + 2 * L::kATile + L::kBTile, kb * BKF, n0);
-                if (trace && kb < 200) g_gemm_trace[16 + kb * 4 + 1] = clock64();
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(&full[s], ph);
-                if (trace && kb < 200) g_gemm_trace[16 + kb * 4 + 2] = clock64();
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                uint8_t* st = smem + s * L::kStage;
-                const uint64_t d_ah = make_kmajor_desc<BKF>(st);
-                const uint64_t d_al = make_kmajor_desc<BKF>(st + L::kATile);
-                const uint64_t d_wh = make_kmajor_desc<BKF>(st + 2 * L::kATile);
-                const uint64_t d_wl = make_kmajor_desc<BKF>(st + 2 * L::kATile + L::kBTile);
-#pragma unroll
-                for (int kk = 0; kk < BKF / UMMA_K; ++kk) {
-                    const uint64_t adv = (uint64_t)((kk * UMMA_K * 4) >> 4);      // +32 B per K-step
-                    if (dbg & 1) {   // experiment: one product per K-step
-                        umma_tf32(tmem_base, d_ah + adv, d_wh + adv, idesc, (kb | kk) ? 1u : 0u);
-                        continue;
-                    }
-                    umma_tf32(tmem_base, d_al + adv, d_wh + adv, idesc, (kb | kk) ? 1u : 0u);
-                    umma_tf32(tmem_base, d_ah + adv, d_wl + adv, idesc, 1u);
-                    umma_tf32(tmem_base, d_ah + adv, d_wh + adv, idesc, 1u);
-                }
-                umma_commit(&empty[s]);            // frees the stage when these MMAs have read it
-                if (trace && kb < 200) g_gemm_trace[16 + kb * 4 + 3] = clock64();
-            }
-            umma_commit(tmem_full);                // accumulator complete
-        }
-    } else {
-        // ---- epilogue: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32) ------------------------
-        // TMEM gives every thread one accumulator ROW; writing rows straight to global memory touches
-        // 32 different 128-byte lines per store instruction (measured: the epilogue took as long as
-        // the main loop).  Instead each warp transposes its 32 x BN block through the (now idle)
-        // pipeline shared memory and stores full rows, 512 contiguous bytes per instruction.
-        const int q = warp & 3;
-        mbar_wait(tmem_full, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (trace && warp == 2 && lane == 0) g_gemm_trace[1] = clock64();
-        constexpr int LD = BN + 4;                       // floats; keeps 16-byte alignment, conflict-free
-        float* scr = reinterpret_cast<float*>(smem) + (size_t)q * 32 * LD;
-        const int rbase = m0 + q * 32;
-        if (epi.kind == Epi::kLstmCell) {
-            constexpr int LH = BN / 4 + 4;
-            float* scr_h = scr;
-            float* scr_c = scr + 32 * LH;
-            const int row = rbase + lane;
-            const bool row_ok = row < M;
-            int crow = row;
-            if (row_ok && epi.c_rowidx) crow = epi.c_rowidx[row];
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-                const int n = n0 + c0;
-                float hv[8], cv[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) { hv[j] = 0.f; cv[j] = 0.f; }
-                if (row_ok && n < N) {
-                    // 32 columns = 8 hidden units x (i, f, g, o)
-                    const float4 cp0 = *reinterpret_cast<const float4*>(epi.c_prev + (size_t)crow * epi.H + (n >> 2));
-                    const float4 cp1 = *reinterpret_cast<const float4*>(epi.c_prev + (size_t)crow * epi.H + (n >> 2) + 4);
-                    const float cp[8] = {cp0.x, cp0.y, cp0.z, cp0.w, cp1.x, cp1.y, cp1.z, cp1.w};
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(epi.bias + n + 4 * j));
-                        const float gi = __uint_as_float(r[4 * j]) + b4.x;
-                        const float gf = __uint_as_float(r[4 * j + 1]) + b4.y;
-                        const float gg = __uint_as_float(r[4 * j + 2]) + b4.z;
-                        const float go = __uint_as_float(r[4 * j + 3]) + b4.w;
-                        cv[j] = sigm(gf) * cp[j] + sigm(gi) * tanhf(gg);
-                        hv[j] = sigm(go) * tanhf(cv[j]);
-                    }
-                }
-                float* ph = scr_h + lane * LH + (c0 >> 2);
-                float* pc = scr_c + lane * LH + (c0 >> 2);
-                *reinterpret_cast<float4*>(ph) = make_float4(hv[0], hv[1], hv[2], hv[3]);
-                *reinterpret_cast<float4*>(ph + 4) = make_float4(hv[4], hv[5], hv[6], hv[7]);
-                *reinterpret_cast<float4*>(pc) = make_float4(cv[0], cv[1], cv[2], cv[3]);
-                *reinterpret_cast<float4*>(pc + 4) = make_float4(cv[4], cv[5], cv[6], cv[7]);
-            }
-            __syncwarp();
-            const int u0 = (n0 >> 2) + 2 * lane;         // BN/4 = 64 (or 32) units per tile
-            if (2 * lane < BN / 4 && u0 + 1 < epi.H) {
-                for (int rr = 0; rr < 32 && rbase + rr < M; ++rr) {
-                    const float2 hh = *reinterpret_cast<const float2*>(scr_h + rr * LH + 2 * lane);
-                    const float2 cc = *reinterpret_cast<const float2*>(scr_c + rr * LH + 2 * lane);
-                    *reinterpret_cast<float2*>(epi.h_out + (size_t)(rbase + rr) * epi.H + u0) = hh;
-                    *reinterpret_cast<float2*>(epi.c_out + (size_t)(rbase + rr) * epi.H + u0) = cc;
-                }
-            }
-        } else {
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-                float* pr = scr + lane * LD + c0;
-#pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<float4*>(pr + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                                                     __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-            }
-            __syncwarp();
-            const bool sc = epi.kind == Epi::kBiasScale;
-#pragma unroll
-            for (int i = 0; i < BN / 128; ++i) {
-                const int col = 128 * i + 4 * lane;
-                const int n = n0 + col;
-                if (n >= N) continue;
-                float b4[4];
-#pragma unroll
-                for (int jj = 0; jj < 4; ++jj) b4[jj] = n + jj < N ? __ldg(epi.bias + n + jj) : 0.f;
-                const bool full4 = n + 3 < N;
-                for (int rr = 0; rr < 32 && rbase + rr < M; ++rr) {
-                    float4 v = *reinterpret_cast<const float4*>(scr + rr * LD + col);
-                    v.x += b4[0]; v.y += b4[1]; v.z += b4[2]; v.w += b4[3];
-                    if (sc) { v.x /= epi.scale; v.y /= epi.scale; v.z /= epi.scale; v.w /= epi.scale; }
-                    float* dst = epi.C + (size_t)(rbase + rr) * epi.ldc + n;
-                    if (full4) {
-                        *reinterpret_cast<float4*>(dst) = v;
-                    } else {
-                        const float vv[4] = {v.x, v.y, v.z, v.w};
-                        for (int jj = 0; jj < 4; ++jj) if (n + jj < N) dst[jj] = vv[jj];
-                    }
-                }
-            }
-        }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    }
-    if (trace && warp == 2 && lane == 0) g_gemm_trace[2] = clock64();
-    __syncthreads();
-    if (warp == 1) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN) : "memory");
-    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -338,6 +153,29 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+__device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* map, uint64_t* bar, void* dst, int x, int y,
+                                               uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+        "[%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(smem_u32(bar)), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 template <int BN, int BKF, int STAGES>
 struct SmemLayoutP {
     static constexpr int kATile = BM * BKF * 4;
@@ -347,7 +185,11 @@ struct SmemLayoutP {
     static constexpr int kBytes = STAGES * kStage + kScratch + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN, int BKF, int STAGES>
+// CL = 2: the CTA pair of a cluster works on two vertically adjacent 128-row tiles of the same N tile;
+// each CTA fetches HALF of the W tile and multicasts it into both CTAs' shared memory (the main loop is
+// bound by L2 -> SM traffic, this removes a third of it).  A stage is reused only after the MMA
+// warps of BOTH CTAs have committed it (multicast tcgen05.commit onto both `empty` barriers).
+template <int BN, int BKF, int STAGES, int CL>
 __global__ void __launch_bounds__(192, 1)
 gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                               const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
@@ -366,11 +208,15 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, cons
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_n = (N + BN - 1) / BN;
-    const int ntiles = ((M + BM - 1) / BM) * tiles_n;
+    const int mgroups = ((M + BM - 1) / BM + CL - 1) / CL;        // groups of CL vertically adjacent tiles
+    const int nwork = mgroups * tiles_n;
     const int nkb = (K + BKF - 1) / BKF;
+    const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
+    const int work0 = blockIdx.x / CL, work_step = gridDim.x / CL;
+    constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1);
 
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_hi) : "memory");
@@ -380,20 +226,20 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, cons
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "n"(2 * BN)
+                     "n"(2 * BN > 256 ? 512 : 2 * BN)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    if (CL > 1) cluster_sync_all(); else __syncthreads();       // peer barriers are initialised too
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
         if (lane == 0) {
             int it = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+            for (int work = work0; work < nwork; work += work_step) {
+                const int m0 = ((work / tiles_n) * CL + crank) * BM, n0 = (work % tiles_n) * BN;
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
@@ -402,16 +248,24 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, cons
                     mbar_expect_tx(&full[s], L::kStage);
                     tma_load_2d(&map_a_hi, &full[s], st, kb * BKF, m0);
                     tma_load_2d(&map_a_lo, &full[s], st + L::kATile, kb * BKF, m0);
-                    tma_load_2d(&map_w_hi, &full[s], st + 2 * L::kATile, kb * BKF, n0);
-                    tma_load_2d(&map_w_lo, &full[s], st + 2 * L::kATile + L::kBTile, kb * BKF, n0);
+                    if (CL == 1) {
+                        tma_load_2d(&map_w_hi, &full[s], st + 2 * L::kATile, kb * BKF, n0);
+                        tma_load_2d(&map_w_lo, &full[s], st + 2 * L::kATile + L::kBTile, kb * BKF, n0);
+                    } else {
+                        const int part = crank * (L::kBTile / CL);
+                        const int nrow = n0 + crank * (BN / CL);
+                        tma_load_2d_mc(&map_w_hi, &full[s], st + 2 * L::kATile + part, kb * BKF, nrow, kMask);
+                        tma_load_2d_mc(&map_w_lo, &full[s], st + 2 * L::kATile + L::kBTile + part, kb * BKF, nrow, kMask);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
+            constexpr uint32_t idesc_x = make_idesc_bf16(BM, BN);
             int it = 0, lt = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
+            for (int work = work0; work < nwork; work += work_step, ++lt) {
                 const int acc = lt & 1;
                 const uint32_t aph = (lt >> 1) & 1;
                 mbar_wait(&tempty[acc], aph ^ 1);          // the epilogue has drained this accumulator
@@ -430,11 +284,10 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, cons
 #pragma unroll
                     for (int kk = 0; kk < BKF / UMMA_K; ++kk) {
                         const uint64_t adv = (uint64_t)((kk * UMMA_K * 4) >> 4);
-                        umma_tf32(tacc, d_al + adv, d_wh + adv, idesc, (kb | kk) ? 1u : 0u);
-                        umma_tf32(tacc, d_ah + adv, d_wl + adv, idesc, 1u);
+                        umma_bf16(tacc, d_al + adv, d_wl + adv, idesc_x, (kb | kk) ? 1u : 0u);   // cross terms
                         umma_tf32(tacc, d_ah + adv, d_wh + adv, idesc, 1u);
                     }
-                    umma_commit(&empty[s]);
+                    if (CL == 1) umma_commit(&empty[s]); else umma_commit_mc(&empty[s], kMask);
                 }
                 umma_commit(&tfull[acc]);
             }
@@ -443,43 +296,60 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, cons
         const int q = warp & 3;
         float* scr = scratch + q * (32 * 36);
         int lt = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
-            const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+        for (int work = work0; work < nwork; work += work_step, ++lt) {
+            const int m0 = ((work / tiles_n) * CL + crank) * BM, n0 = (work % tiles_n) * BN;
             const int acc = lt & 1;
             const uint32_t aph = (lt >> 1) & 1;
-            mbar_wait(&tfull[acc], aph);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t tacc = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
             const int rbase = m0 + q * 32;
             if (epi.kind == Epi::kLstmCell) {
+                // One accumulator row per thread, 32 columns (8 hidden units x i,f,g,o) per chunk.  The
+                // per-row operands of chunk c+1 (previous cell state of the source beam, the E'[token]
+                // row segment) are fetched while chunk c is computed, and those of chunk 0 before the
+                // accumulator is even complete: their DRAM latency used to be exposed 8 times per tile.
                 const int row = rbase + lane;
                 const bool row_ok = row < M;
                 int crow = row;
                 if (row_ok && epi.c_rowidx) crow = epi.c_rowidx[row];
-#pragma unroll 1
+                const float* cbase = epi.c_prev + (size_t)crow * epi.H;
+                const float* abase = (epi.addrow && row_ok) ? epi.addrow + (size_t)epi.addrow_idx[row] * epi.addrow_ld : nullptr;
+                float4 cpn[2], adn[8];
+                auto fetch = [&](int n) {
+                    if (row_ok && n < N) {
+                        cpn[0] = *reinterpret_cast<const float4*>(cbase + (n >> 2));
+                        cpn[1] = *reinterpret_cast<const float4*>(cbase + (n >> 2) + 4);
+                        if (abase) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) adn[j] = __ldg(reinterpret_cast<const float4*>(abase + n + 4 * j));
+                        }
+                    }
+                };
+                fetch(n0);
+                mbar_wait(&tfull[acc], aph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 2
                 for (int c0 = 0; c0 < BN; c0 += 32) {
+                    const int n = n0 + c0;
+                    float4 cpv[2], adv4[8];
+                    cpv[0] = cpn[0]; cpv[1] = cpn[1];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) adv4[j] = adn[j];
+                    if (c0 + 32 < BN) fetch(n + 32);
                     uint32_t r[32];
                     tmem_ld32(tacc + (uint32_t)c0, r);
-                    const int n = n0 + c0;
                     if (!row_ok || n >= N) continue;
-                    const float4 cp0 = *reinterpret_cast<const float4*>(epi.c_prev + (size_t)crow * epi.H + (n >> 2));
-                    const float4 cp1 = *reinterpret_cast<const float4*>(epi.c_prev + (size_t)crow * epi.H + (n >> 2) + 4);
-                    const float cp[8] = {cp0.x, cp0.y, cp0.z, cp0.w, cp1.x, cp1.y, cp1.z, cp1.w};
-                    const float* arow = epi.addrow ? epi.addrow + (size_t)epi.addrow_idx[row] * epi.addrow_ld + n : nullptr;
+                    const float cp[8] = {cpv[0].x, cpv[0].y, cpv[0].z, cpv[0].w, cpv[1].x, cpv[1].y, cpv[1].z, cpv[1].w};
                     float hv[8], cv[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         float4 b4 = __ldg(reinterpret_cast<const float4*>(epi.bias + n + 4 * j));
-                        if (arow) {
-                            const float4 e4 = __ldg(reinterpret_cast<const float4*>(arow + 4 * j));
-                            b4.x += e4.x; b4.y += e4.y; b4.z += e4.z; b4.w += e4.w;
-                        }
+                        if (abase) { b4.x += adv4[j].x; b4.y += adv4[j].y; b4.z += adv4[j].z; b4.w += adv4[j].w; }
                         const float gi = __uint_as_float(r[4 * j]) + b4.x;
                         const float gf = __uint_as_float(r[4 * j + 1]) + b4.y;
                         const float gg = __uint_as_float(r[4 * j + 2]) + b4.z;
                         const float go = __uint_as_float(r[4 * j + 3]) + b4.w;
-                        cv[j] = sigm(gf) * cp[j] + sigm(gi) * tanhf(gg);
-                        hv[j] = sigm(go) * tanhf(cv[j]);
+                        cv[j] = sigm(gf) * cp[j] + sigm(gi) * tanh_e(gg);
+                        hv[j] = sigm(go) * tanh_e(cv[j]);
                     }
                     float4* ho = reinterpret_cast<float4*>(epi.h_out + (size_t)row * epi.H + (n >> 2));
                     float4* co = reinterpret_cast<float4*>(epi.c_out + (size_t)row * epi.H + (n >> 2));
@@ -488,19 +358,24 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, cons
                     co[0] = make_float4(cv[0], cv[1], cv[2], cv[3]);
                     co[1] = make_float4(cv[4], cv[5], cv[6], cv[7]);
                     if (epi.split_hi) {
+                        // the 8 hidden units of this thread are one 8-float block of the split operand
                         float hh[8], hl[8];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) { hh[j] = rn_tf32_e(hv[j]); hl[j] = rn_tf32_e(hv[j] - hh[j]); }
+                        for (int j = 0; j < 8; ++j) { hh[j] = rn_tf32_e(hv[j]); hl[j] = hv[j] - hh[j]; }
                         float4* sh = reinterpret_cast<float4*>(epi.split_hi + (size_t)row * epi.split_ld + (n >> 2));
-                        float4* sl = reinterpret_cast<float4*>(epi.split_lo + (size_t)row * epi.split_ld + (n >> 2));
+                        uint4* sx = reinterpret_cast<uint4*>(epi.split_lo + (size_t)row * epi.split_ld + (n >> 2));
                         sh[0] = make_float4(hh[0], hh[1], hh[2], hh[3]);
                         sh[1] = make_float4(hh[4], hh[5], hh[6], hh[7]);
-                        sl[0] = make_float4(hl[0], hl[1], hl[2], hl[3]);
-                        sl[1] = make_float4(hl[4], hl[5], hl[6], hl[7]);
+                        sx[0] = make_uint4(pack_bf16x2(hl[0], hl[1]), pack_bf16x2(hl[2], hl[3]),
+                                           pack_bf16x2(hl[4], hl[5]), pack_bf16x2(hl[6], hl[7]));
+                        sx[1] = make_uint4(pack_bf16x2(hv[0], hv[1]), pack_bf16x2(hv[2], hv[3]),
+                                           pack_bf16x2(hv[4], hv[5]), pack_bf16x2(hv[6], hv[7]));
                     }
                 }
             } else {
                 const bool sc = epi.kind == Epi::kBiasScale;
+                mbar_wait(&tfull[acc], aph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
                 for (int c0 = 0; c0 < BN; c0 += 32) {
                     uint32_t r[32];
@@ -548,10 +423,10 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, cons
             if (lane == 0) mbar_arrive(&tempty[acc]);
         }
     }
-    __syncthreads();
+    if (CL > 1) cluster_sync_all(); else __syncthreads();       // no CTA leaves while its peer may still signal it
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN > 256 ? 512 : 2 * BN) : "memory");
     }
 }
 
@@ -563,29 +438,47 @@ __device__ __forceinline__ float rn_tf32(float x) {
     return __uint_as_float(u);
 }
 
+// fmt: kSplitLegacy  lo = rn_tf32(x - hi) as fp32 (the encoder recurrence packs its own W_lo from it)
+//      kSplitAct / kSplitWeight  "cross" operand: per 8-float block 16 bf16 values,
+//          activations [bf16(x - hi) x8 | bf16(x) x8],  weights [bf16(w) x8 | bf16(w - hi) x8],
+//      so one kind::f16 MMA (K = 16) over a block adds  x_lo*w + x*w_lo  for 8 values of k.
 __global__ void split_operand_kernel(AOperand A, int M, int K, float* __restrict__ hi, float* __restrict__ lo,
-                                     const int* stop_flag) {
+                                     const int* stop_flag, int fmt) {
     if (stop_flag && *stop_flag >= 0) return;
-    const int k4n = K >> 2;
-    const long long total = (long long)M * k4n;
+    const int k8n = K >> 3;
+    const long long total = (long long)M * k8n;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
-        const int row = (int)(i / k4n);
-        const int k = (int)(i - (long long)row * k4n) * 4;
+        const int row = (int)(i / k8n);
+        const int k = (int)(i - (long long)row * k8n) * 8;
         int g = 0;
         if (A.nseg > 1 && k >= A.seg[0].kend) g = 1;
         if (A.nseg > 2 && k >= A.seg[1].kend) g = 2;
         const ASeg& s = A.seg[g];
         const int kstart = g == 0 ? 0 : A.seg[g - 1].kend;
         const int r = s.rowidx ? s.rowidx[row] : row;
-        const float4 v = *reinterpret_cast<const float4*>(s.base + (size_t)r * s.ld + (k - kstart));
-        float4 h, l;
-        h.x = rn_tf32(v.x); l.x = rn_tf32(v.x - h.x);
-        h.y = rn_tf32(v.y); l.y = rn_tf32(v.y - h.y);
-        h.z = rn_tf32(v.z); l.z = rn_tf32(v.z - h.z);
-        h.w = rn_tf32(v.w); l.w = rn_tf32(v.w - h.w);
-        *reinterpret_cast<float4*>(hi + (size_t)row * K + k) = h;
-        *reinterpret_cast<float4*>(lo + (size_t)row * K + k) = l;
+        const float4* src = reinterpret_cast<const float4*>(s.base + (size_t)r * s.ld + (k - kstart));
+        const float4 v0 = src[0], v1 = src[1];
+        const float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        float h[8], l[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { h[j] = rn_tf32(x[j]); l[j] = x[j] - h[j]; }
+        float4* ph = reinterpret_cast<float4*>(hi + (size_t)row * K + k);
+        ph[0] = make_float4(h[0], h[1], h[2], h[3]);
+        ph[1] = make_float4(h[4], h[5], h[6], h[7]);
+        if (fmt == kSplitLegacy) {
+            float4* pl = reinterpret_cast<float4*>(lo + (size_t)row * K + k);
+            pl[0] = make_float4(rn_tf32(l[0]), rn_tf32(l[1]), rn_tf32(l[2]), rn_tf32(l[3]));
+            pl[1] = make_float4(rn_tf32(l[4]), rn_tf32(l[5]), rn_tf32(l[6]), rn_tf32(l[7]));
+        } else {
+            const uint4 pl = make_uint4(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]),
+                                        pack_bf16x2(l[4], l[5]), pack_bf16x2(l[6], l[7]));
+            const uint4 px = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]),
+                                        pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
+            uint4* pc = reinterpret_cast<uint4*>(lo + (size_t)row * K + k);
+            pc[0] = fmt == kSplitAct ? pl : px;
+            pc[1] = fmt == kSplitAct ? px : pl;
+        }
     }
 }
 
@@ -625,12 +518,14 @@ static int make_map(CUtensorMap* map, const float* base, int rows, int K, int bo
 }  // namespace tc
 
 int split_operand(const AOperand& A, int M, int K, float* hi, float* lo, const int* stop_flag, cudaStream_t st,
-                  int64_t* launches) {
+                  int64_t* launches, int fmt) {
     if (M <= 0) return ASR_OK;
-    if (K % 4) { set_error("split: K %% 4"); return ASR_ERR_ARG; }
-    long long total = (long long)M * (K / 4);
+    if (K % 8) { set_error("split: K %% 8"); return ASR_ERR_ARG; }
+    for (int g = 0; g + 1 < A.nseg; ++g)
+        if (A.seg[g].kend % 8) { set_error("split: segment boundary %% 8"); return ASR_ERR_ARG; }
+    long long total = (long long)M * (K / 8);
     int grid = (int)std::min<long long>((total + 255) / 256, (long long)kNumSMs * 16);
-    tc::split_operand_kernel<<<grid, 256, 0, st>>>(A, M, K, hi, lo, stop_flag);
+    tc::split_operand_kernel<<<grid, 256, 0, st>>>(A, M, K, hi, lo, stop_flag, fmt);
     ASR_CHECK_LAUNCH();
     if (launches) ++*launches;
     return ASR_OK;
@@ -645,64 +540,77 @@ static int launch_tc_cfg(const float* a_hi, const float* a_lo, const float* w_hi
     ASR_TRY(tc::make_map(&ma_lo, a_lo, M, K, tc::BM, BKF, epi.lda));
     ASR_TRY(tc::make_map(&mw_hi, w_hi, N, K, BN, BKF, epi.ldw));
     ASR_TRY(tc::make_map(&mw_lo, w_lo, N, K, BN, BKF, epi.ldw));
-    static const bool persist = !(getenv("ASR_B200_GEMM_PERSIST") && atoi(getenv("ASR_B200_GEMM_PERSIST")) == 0);
-    if (persist) {
+    static const int cl = getenv("ASR_B200_GEMM_CLUSTER") ? atoi(getenv("ASR_B200_GEMM_CLUSTER")) : 2;
+    static const int dbg_p = getenv("ASR_B200_GEMM_DBG") ? atoi(getenv("ASR_B200_GEMM_DBG")) : 0;
+    const int smem_p = tc::SmemLayoutP<BN, BKF, STAGES>::kBytes;
+    const int tiles_m = (M + tc::BM - 1) / tc::BM, tiles_n = (N + BN - 1) / BN;
+    if (cl == 2) {
+        auto kern = tc::gemm_tf32x3_persistent_kernel<BN, BKF, STAGES, 2>;
+        static int max_clusters = 0;
+        cudaLaunchConfig_t cfg = {};
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.blockDim = dim3(192);
+        cfg.dynamicSmemBytes = smem_p;
+        cfg.stream = st;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        if (!max_clusters) {
+            ASR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_p));
+            cfg.gridDim = dim3(2 * kNumSMs);
+            ASR_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
+            if (max_clusters < 1) { set_error("gemm_tc: no co-resident CTA pair"); return ASR_ERR_CUDA; }
+        }
+        CUtensorMap mw_hi2, mw_lo2;       // each CTA of the pair fetches half of the W tile rows
+        ASR_TRY(tc::make_map(&mw_hi2, w_hi, N, K, BN / 2, BKF, epi.ldw));
+        ASR_TRY(tc::make_map(&mw_lo2, w_lo, N, K, BN / 2, BKF, epi.ldw));
+        const int nwork = ((tiles_m + 1) / 2) * tiles_n;
+        cfg.gridDim = dim3(2 * std::min(nwork, max_clusters));
+        ASR_CUDA(cudaLaunchKernelEx(&cfg, kern, ma_hi, ma_lo, mw_hi2, mw_lo2, M, N, K, epi, dbg_p));
+        ASR_CHECK_LAUNCH();
+        return ASR_OK;
+    }
+    {
         static bool attr_p = false;
         static int num_sms = 0;
-        const int smem_p = tc::SmemLayoutP<BN, BKF, STAGES>::kBytes;
         if (!attr_p) {
             int dev = 0;
             ASR_CUDA(cudaGetDevice(&dev));
             ASR_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-            ASR_CUDA(cudaFuncSetAttribute(tc::gemm_tf32x3_persistent_kernel<BN, BKF, STAGES>,
+            ASR_CUDA(cudaFuncSetAttribute(tc::gemm_tf32x3_persistent_kernel<BN, BKF, STAGES, 1>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, smem_p));
             attr_p = true;
         }
-        static const int dbg_p = getenv("ASR_B200_GEMM_DBG") ? atoi(getenv("ASR_B200_GEMM_DBG")) : 0;
-        const int ntiles = ((N + BN - 1) / BN) * ((M + tc::BM - 1) / tc::BM);
+        const int ntiles = tiles_n * tiles_m;
         const int grid_p = ntiles < num_sms ? ntiles : num_sms;
-        tc::gemm_tf32x3_persistent_kernel<BN, BKF, STAGES><<<grid_p, 192, smem_p, st>>>(ma_hi, ma_lo, mw_hi, mw_lo, M, N, K, epi, dbg_p);
+        tc::gemm_tf32x3_persistent_kernel<BN, BKF, STAGES, 1><<<grid_p, 192, smem_p, st>>>(ma_hi, ma_lo, mw_hi, mw_lo, M, N, K, epi, dbg_p);
         ASR_CHECK_LAUNCH();
         return ASR_OK;
     }
-    static bool attr = false;
-    const int smem = tc::SmemLayout<BN, BKF, STAGES>::kBytes;
-    if (!attr) {
-        ASR_CUDA(cudaFuncSetAttribute(tc::gemm_tf32x3_kernel<BN, BKF, STAGES>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr = true;
-    }
-    static const int dbg = getenv("ASR_B200_GEMM_DBG") ? atoi(getenv("ASR_B200_GEMM_DBG")) : 0;
-    dim3 grid((N + BN - 1) / BN, (M + tc::BM - 1) / tc::BM);
-    tc::gemm_tf32x3_kernel<BN, BKF, STAGES><<<grid, 192, smem, st>>>(ma_hi, ma_lo, mw_hi, mw_lo, M, N, K, epi, dbg);
-    ASR_CHECK_LAUNCH();
-    if ((dbg & 4) && M > 100000 && K == 512) {
-        static int printed = 0;
-        if (printed++ < 1) {
-            long long t[1024];
-            cudaStreamSynchronize(st);
-            cudaMemcpyFromSymbol(t, tc::g_gemm_trace, sizeof(t));
-            const int nkb = (K + BKF - 1) / BKF;
-            fprintf(stderr, "[gemm trace] BN=%d BKF=%d STAGES=%d nkb=%d: start->first full %lld, epilogue %lld, total %lld cycles\n", BN, BKF,
-                    STAGES, nkb, t[16 + 2] - t[0], t[2] - t[1], t[2] - t[0]);
-            for (int kb = 0; kb < nkb; kb += (kb < 8 ? 1 : 4))
-                fprintf(stderr, "  kb %2d: prod wait-done %6lld issued %6lld | mma full-done %6lld issued %6lld\n", kb,
-                        t[16 + kb * 4] - t[0], t[16 + kb * 4 + 1] - t[0], t[16 + kb * 4 + 2] - t[0], t[16 + kb * 4 + 3] - t[0]);
-        }
-    }
-    return ASR_OK;
 }
 
 int launch_gemm_tc(const float* a_hi, const float* a_lo, const float* w_hi, const float* w_lo, int M, int N, int K,
                    const GemmEpilogue& epi, cudaStream_t st, int64_t* launches) {
     if (M <= 0) return ASR_OK;
-    if ((K * 4) % 16) { set_error("gemm_tc: K*4 must be a multiple of 16"); return ASR_ERR_ARG; }
+    if (K % 8) { set_error("gemm_tc: K must be a multiple of 8"); return ASR_ERR_ARG; }
     if (epi.kind == Epi::kLstmCell && (N % 32)) { set_error("gemm_tc: LSTM epilogue needs N %% 32 == 0"); return ASR_ERR_ARG; }
     static const char* env = getenv("ASR_B200_GEMM_TILE");
-    const bool wide = env ? (atoi(env) == 256) : (N >= 1024);
-    if (wide) {
+    // tile width: 128 for narrow outputs; otherwise 256 or 224 columns, whichever leaves the smaller
+    // last wave over the 74 CTA pairs (vocabulary GEMM: 5004 = 23 x 224 -> 368 pair tiles = 4.97 waves of
+    // 224 columns instead of 320 = 4.32 -> 5 waves of 256)
+    int bn = N >= 1024 ? 256 : 128;
+    if (bn == 256 && epi.kind != Epi::kLstmCell) {
+        const int mg = ((M + tc::BM - 1) / tc::BM + 1) / 2, ncl = kNumSMs / 2;
+        auto cost = [&](int w) { return (long long)((mg * ((N + w - 1) / w) + ncl - 1) / ncl) * w; };
+        if (cost(224) < cost(256)) bn = 224;
+    }
+    if (env) bn = atoi(env);
+    if (bn == 256) {
         // 128 x 256 tile, 64-byte K slabs, 4 stages: twice the MMA work per byte of A in flight
         ASR_TRY((launch_tc_cfg<256, 16, 4>(a_hi, a_lo, w_hi, w_lo, M, N, K, epi, st)));
+    } else if (bn == 224) {
+        ASR_TRY((launch_tc_cfg<224, 16, 4>(a_hi, a_lo, w_hi, w_lo, M, N, K, epi, st)));
     } else {
         ASR_TRY((launch_tc_cfg<128, 32, 3>(a_hi, a_lo, w_hi, w_lo, M, N, K, epi, st)));
     }

@@ -180,6 +180,10 @@ int asr_set_gemm_mode(asr_handle* h, int mode);
 int asr_test_gemm(asr_handle* h, const float* d_A, const float* d_W, const float* d_bias, float* d_C,
                   int M, int N, int K, int mode, void* stream);
 
+/* Tuning aid: average ms per launch of the tensor-core GEMM engine on an [M,K] x [N,K]^T problem
+ * (operands already split, CUDA events on `stream`, `iters` timed launches after 2 warm-ups). */
+int asr_bench_gemm(asr_handle* h, int M, int N, int K, int iters, float* ms_out, void* stream);
+
 /* Number of kernels this library launched since the handle was created / last reset. */
 int64_t asr_launch_count(asr_handle* h, int reset);
 
