@@ -197,8 +197,9 @@ static int run_keys(asr_handle* h, cudaStream_t st) {
     e.bias = h->w.att_b;
     e.C = w.keys;
     e.ldc = kAtt;
-    return gemm(h, plain_a(w.enc, kEnc, kEnc), h->w.att_w_enc_t, h->w.att_w_enc_t_hi, h->w.att_w_enc_t_lo,
-                (int)h->meta.rows, kAtt, kEnc, e, st);
+    ASR_TRY(gemm(h, plain_a(w.enc, kEnc, kEnc), h->w.att_w_enc_t, h->w.att_w_enc_t_hi, h->w.att_w_enc_t_lo,
+                 (int)h->meta.rows, kAtt, kEnc, e, st));
+    return launch_keys_exp(h, st);
 }
 
 // one decoder step up to the logits: LSTM cell -> attention -> vocabulary projection
@@ -723,6 +724,8 @@ int asr_reserve(asr_handle* h, int max_utts, int64_t max_rows, int max_beam, int
     ASR_TRY(dev_alloc_t(pool, &w.act[1], (size_t)max_rows * kEnc));
     ASR_TRY(dev_alloc_t(pool, &w.enc, (size_t)max_rows * kEnc));
     ASR_TRY(dev_alloc_t(pool, &w.keys, (size_t)max_rows * kAtt));
+    ASR_TRY(dev_alloc_t(pool, &w.keys_exp, (size_t)max_rows * kAtt));
+    ASR_TRY(dev_alloc_t(pool, &w.keys_big, (size_t)max_utts));
     ASR_TRY(dev_alloc_t(pool, &w.h0, (size_t)max_utts * kEnc));
     ASR_TRY(dev_alloc_t(pool, &w.c0, (size_t)max_utts * kEnc));
     for (int i = 0; i < 2; ++i) {

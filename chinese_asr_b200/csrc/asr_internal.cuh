@@ -221,6 +221,8 @@ struct Workspace {
     float* act[2] = {};          // [max_rows, 512] packed time-major residual stream
     float* enc = nullptr;        // [max_rows, 512] utterance-major, sorted order
     float* keys = nullptr;       // [max_rows, 128]
+    float* keys_exp = nullptr;   // [max_rows, 128] e^(2 key), the per-frame factor of the attention scores
+    int* keys_big = nullptr;     // [max_utts] utterance has a key outside the product form's range
     float* h0 = nullptr;         // [max_utts, 512] last-layer final h (fwd|bwd), sorted order
     float* c0 = nullptr;
     // decoder
@@ -336,6 +338,7 @@ int launch_unsort_rows(asr_handle* h, const float* src, int width, float* dst, c
 
 // ---- decoder.cu ------------------------------------------------------------------------------
 int decode_init(asr_handle* h, int k, int max_len, bool greedy, cudaStream_t st);
+int launch_keys_exp(asr_handle* h, cudaStream_t st);
 int launch_attention(asr_handle* h, int k, int step, int cur, float* d_align_step, cudaStream_t st);
 int launch_row_topk(asr_handle* h, int k, int step, cudaStream_t st);
 int launch_beam_bookkeep(asr_handle* h, int k, int step, int max_len, cudaStream_t st);

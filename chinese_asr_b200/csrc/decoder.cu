@@ -45,6 +45,11 @@ __device__ __forceinline__ float rcp1p_ex2(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.f));
     return r;
 }
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -112,6 +117,8 @@ int decode_init(asr_handle* h, int k, int max_len, bool greedy, cudaStream_t st)
 struct AttnParams {
     const float* q;         // [R, 128] query projection h_new * W_hidden (GEMM engine)
     const float* keys;      // [rows, 128] utterance-major sorted
+    const float* keys_exp;  // [rows, 128] 2^(key * 2 log2 e) = e^(2 key)      (keys_exp_kernel)
+    const int* keys_big;    // [B] != 0: some |key| of the utterance is outside the product form's range
     const float* enc;       // [rows, 512]
     const float* v;         // [128]
     const int* uoff;        // [B + 1]
@@ -145,6 +152,40 @@ __device__ __forceinline__ void write_ctx_split(const AttnParams& p, int row, in
     cross[4] = xx;
 }
 
+// e^(2 (key + q)) = e^(2 key) * e^(2 q): with the per-frame factor precomputed once per batch (here)
+// and the per-beam factor once per step (phase A of the attention kernel), one score element costs
+// FFMA, MUFU.RCP, FFMA instead of FADD, MUFU.EX2, FADD, MUFU.RCP, FFMA - half the MUFU work that bounds
+// the kernel.  Both factors are kept inside 2^+-60 so the product cannot overflow or hit inf * 0; an
+// utterance (or a step's queries) with a pre-activation outside that range (|x| > 20.8, where tanh has
+// long been +-1 to fp32) takes the exact sum-then-exp path instead.
+constexpr float kAttScale = 2.885390081777927f;       // 2 * log2(e)
+constexpr float kAttRange = 60.f;
+
+__global__ void keys_exp_kernel(const float* __restrict__ keys, const int* __restrict__ uoff,
+                                float* __restrict__ keys_exp, int* __restrict__ keys_big) {
+    const int u = blockIdx.x;
+    const long long beg = (long long)uoff[u] * (kAtt / 4), end = (long long)uoff[u + 1] * (kAtt / 4);
+    bool big = false;
+    for (long long i = beg + blockIdx.y * blockDim.x + threadIdx.x; i < end; i += (long long)gridDim.y * blockDim.x) {
+        float4 x = reinterpret_cast<const float4*>(keys)[i];
+        x.x *= kAttScale; x.y *= kAttScale; x.z *= kAttScale; x.w *= kAttScale;
+        big |= !(fabsf(x.x) <= kAttRange && fabsf(x.y) <= kAttRange && fabsf(x.z) <= kAttRange && fabsf(x.w) <= kAttRange);
+        reinterpret_cast<float4*>(keys_exp)[i] = make_float4(exp2f(x.x), exp2f(x.y), exp2f(x.z), exp2f(x.w));
+    }
+    if (__syncthreads_or(big) && threadIdx.x == 0) atomicOr(keys_big + u, 1);
+}
+
+int launch_keys_exp(asr_handle* h, cudaStream_t st) {
+    Workspace& w = h->ws;
+    const BatchMeta& m = h->meta;
+    ASR_CUDA(cudaMemsetAsync(w.keys_big, 0, sizeof(int) * (size_t)m.B, st));
+    const int slices = std::max(1, std::min(8, (4 * kNumSMs + m.B - 1) / m.B));
+    keys_exp_kernel<<<dim3(m.B, slices), 256, 0, st>>>(w.keys, m.d_uoff_sorted, w.keys_exp, w.keys_big);
+    ASR_CHECK_LAUNCH();
+    h->launches++;
+    return ASR_OK;
+}
+
 template <int K>
 __global__ void __launch_bounds__(256, K <= 8 ? 4 : 2)
 attention_kernel(AttnParams p) {
@@ -165,8 +206,13 @@ attention_kernel(AttnParams p) {
     const int nl = lend - lbeg;
 
     // ---- phase A: the query projection q = h * W_hidden was computed by the GEMM engine --------
-    for (int i = tid; i < k * kAtt; i += 256) s_q[i] = p.q[(size_t)u * k * kAtt + i];
-    __syncthreads();
+    bool q_big = false;
+    for (int i = tid; i < k * kAtt; i += 256) {
+        const float qv = p.q[(size_t)u * k * kAtt + i];
+        s_q[i] = qv;
+        q_big |= !(fabsf(qv * kAttScale) <= kAttRange);
+    }
+    const bool product_form = !__syncthreads_or(q_big) && p.keys_big[u] == 0;
 
     // ---- phase B: scores e[l][kb] = sum_d v_d tanh(key[l][d] + q[kb][d]) ----------------------
     // one warp per frame, lane owns 4 of the 128 attention dims for all K beams; the K partial
@@ -175,7 +221,7 @@ attention_kernel(AttnParams p) {
     // Keys and queries are pre-scaled by 2 log2(e) (once per frame / per beam), so one element costs
     // FADD, MUFU.EX2, FADD, MUFU.RCP, FFMA - the kernel is bound by the 16 lanes/clk MUFU pipe.
     {
-        constexpr float kScale = 2.885390081777927f;       // 2 * log2(e)
+        constexpr float kScale = kAttScale;
         const float4 v4 = *reinterpret_cast<const float4*>(p.v + 4 * lane);
         const float vsum = (v4.x + v4.y) + (v4.z + v4.w);
         float4 q4[K];
@@ -184,19 +230,35 @@ attention_kernel(AttnParams p) {
             q4[kb] = kb < k ? *reinterpret_cast<const float4*>(s_q + kb * kAtt + 4 * lane)
                             : make_float4(0.f, 0.f, 0.f, 0.f);
             q4[kb].x *= kScale; q4[kb].y *= kScale; q4[kb].z *= kScale; q4[kb].w *= kScale;
+            if (product_form) {      // per-beam factor e^(2 q)
+                q4[kb].x = exp2f(q4[kb].x); q4[kb].y = exp2f(q4[kb].y);
+                q4[kb].z = exp2f(q4[kb].z); q4[kb].w = exp2f(q4[kb].w);
+            }
         }
         constexpr int kGroup = 32 / K;                 // lanes that end up holding the same beam
+        const float* kbase = product_form ? p.keys_exp : p.keys;
         for (int l = lbeg + warp; l < lend; l += 8) {
-            float4 key = __ldg(reinterpret_cast<const float4*>(p.keys + (size_t)(row0 + l) * kAtt) + lane);
-            key.x *= kScale; key.y *= kScale; key.z *= kScale; key.w *= kScale;
+            float4 key = __ldg(reinterpret_cast<const float4*>(kbase + (size_t)(row0 + l) * kAtt) + lane);
             float e[K];
+            if (product_form) {
 #pragma unroll
-            for (int kb = 0; kb < K; ++kb) {
-                float t = v4.x * rcp1p_ex2(key.x + q4[kb].x);
-                t = fmaf(v4.y, rcp1p_ex2(key.y + q4[kb].y), t);
-                t = fmaf(v4.z, rcp1p_ex2(key.z + q4[kb].z), t);
-                t = fmaf(v4.w, rcp1p_ex2(key.w + q4[kb].w), t);
-                e[kb] = fmaf(-2.f, t, vsum);
+                for (int kb = 0; kb < K; ++kb) {
+                    float t = v4.x * rcp_approx(fmaf(key.x, q4[kb].x, 1.f));
+                    t = fmaf(v4.y, rcp_approx(fmaf(key.y, q4[kb].y, 1.f)), t);
+                    t = fmaf(v4.z, rcp_approx(fmaf(key.z, q4[kb].z, 1.f)), t);
+                    t = fmaf(v4.w, rcp_approx(fmaf(key.w, q4[kb].w, 1.f)), t);
+                    e[kb] = fmaf(-2.f, t, vsum);
+                }
+            } else {
+                key.x *= kScale; key.y *= kScale; key.z *= kScale; key.w *= kScale;
+#pragma unroll
+                for (int kb = 0; kb < K; ++kb) {
+                    float t = v4.x * rcp1p_ex2(key.x + q4[kb].x);
+                    t = fmaf(v4.y, rcp1p_ex2(key.y + q4[kb].y), t);
+                    t = fmaf(v4.z, rcp1p_ex2(key.z + q4[kb].z), t);
+                    t = fmaf(v4.w, rcp1p_ex2(key.w + q4[kb].w), t);
+                    e[kb] = fmaf(-2.f, t, vsum);
+                }
             }
             int off = 16;
 #pragma unroll
@@ -372,6 +434,8 @@ int launch_attention(asr_handle* h, int k, int step, int nxt, float* d_align_ste
     AttnParams p{};
     p.q = w.att_q;
     p.keys = w.keys;
+    p.keys_exp = w.keys_exp;
+    p.keys_big = w.keys_big;
     p.enc = w.enc;
     p.v = h->w.att_v;
     p.uoff = m.d_uoff_sorted;
@@ -389,6 +453,8 @@ int launch_attention(asr_handle* h, int k, int step, int nxt, float* d_align_ste
     int S = (2 * kNumSMs + m.B - 1) / m.B;
     if (S > 8) S = 8;
     if (S < 1) S = 1;
+    static const int env_split = getenv("ASR_B200_ATT_SPLIT") ? atoi(getenv("ASR_B200_ATT_SPLIT")) : 0;
+    if (env_split > 0) S = env_split;
     while (S > 1 && (m.Lmax + S - 1) / S < 16) --S;
     p.S = S;
     p.sc_ld = ((m.Lmax + S - 1) / S + 3) & ~3;

@@ -531,6 +531,40 @@ int split_operand(const AOperand& A, int M, int K, float* hi, float* lo, const i
     return ASR_OK;
 }
 
+// CL CTAs of a cluster work on CL vertically adjacent tiles and share the W tile by multicast
+template <int BN, int BKF, int STAGES, int CL>
+static int launch_tc_cluster(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const float* w_hi, const float* w_lo,
+                             int M, int N, int K, const GemmEpilogue& epi, cudaStream_t st, int dbg_p) {
+    auto kern = tc::gemm_tf32x3_persistent_kernel<BN, BKF, STAGES, CL>;
+    const int smem_p = tc::SmemLayoutP<BN, BKF, STAGES>::kBytes;
+    const int tiles_m = (M + tc::BM - 1) / tc::BM, tiles_n = (N + BN - 1) / BN;
+    static int max_clusters = 0;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(192);
+    cfg.dynamicSmemBytes = smem_p;
+    cfg.stream = st;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    if (!max_clusters) {
+        ASR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_p));
+        cfg.gridDim = dim3(CL * kNumSMs);
+        ASR_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
+        if (max_clusters < 1) { set_error("gemm_tc: no co-resident cluster of %d CTAs", CL); return ASR_ERR_CUDA; }
+        if (dbg_p & 16) fprintf(stderr, "[gemm_tc] BN=%d cluster %d: %d co-resident clusters\n", BN, CL, max_clusters);
+    }
+    CUtensorMap mw_hi, mw_lo;       // each CTA of the cluster fetches 1/CL of the W tile rows
+    ASR_TRY(tc::make_map(&mw_hi, w_hi, N, K, BN / CL, BKF, epi.ldw));
+    ASR_TRY(tc::make_map(&mw_lo, w_lo, N, K, BN / CL, BKF, epi.ldw));
+    const int nwork = ((tiles_m + CL - 1) / CL) * tiles_n;
+    cfg.gridDim = dim3(CL * std::min(nwork, max_clusters));
+    ASR_CUDA(cudaLaunchKernelEx(&cfg, kern, ma_hi, ma_lo, mw_hi, mw_lo, M, N, K, epi, dbg_p));
+    ASR_CHECK_LAUNCH();
+    return ASR_OK;
+}
+
 // C = A * W^T with pre-split operands (a_hi/a_lo [M,K], w_hi/w_lo [N,K], all dense row-major)
 template <int BN, int BKF, int STAGES>
 static int launch_tc_cfg(const float* a_hi, const float* a_lo, const float* w_hi, const float* w_lo, int M, int N,
@@ -544,33 +578,8 @@ static int launch_tc_cfg(const float* a_hi, const float* a_lo, const float* w_hi
     static const int dbg_p = getenv("ASR_B200_GEMM_DBG") ? atoi(getenv("ASR_B200_GEMM_DBG")) : 0;
     const int smem_p = tc::SmemLayoutP<BN, BKF, STAGES>::kBytes;
     const int tiles_m = (M + tc::BM - 1) / tc::BM, tiles_n = (N + BN - 1) / BN;
-    if (cl == 2) {
-        auto kern = tc::gemm_tf32x3_persistent_kernel<BN, BKF, STAGES, 2>;
-        static int max_clusters = 0;
-        cudaLaunchConfig_t cfg = {};
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.blockDim = dim3(192);
-        cfg.dynamicSmemBytes = smem_p;
-        cfg.stream = st;
-        cfg.attrs = at;
-        cfg.numAttrs = 1;
-        if (!max_clusters) {
-            ASR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_p));
-            cfg.gridDim = dim3(2 * kNumSMs);
-            ASR_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
-            if (max_clusters < 1) { set_error("gemm_tc: no co-resident CTA pair"); return ASR_ERR_CUDA; }
-        }
-        CUtensorMap mw_hi2, mw_lo2;       // each CTA of the pair fetches half of the W tile rows
-        ASR_TRY(tc::make_map(&mw_hi2, w_hi, N, K, BN / 2, BKF, epi.ldw));
-        ASR_TRY(tc::make_map(&mw_lo2, w_lo, N, K, BN / 2, BKF, epi.ldw));
-        const int nwork = ((tiles_m + 1) / 2) * tiles_n;
-        cfg.gridDim = dim3(2 * std::min(nwork, max_clusters));
-        ASR_CUDA(cudaLaunchKernelEx(&cfg, kern, ma_hi, ma_lo, mw_hi2, mw_lo2, M, N, K, epi, dbg_p));
-        ASR_CHECK_LAUNCH();
-        return ASR_OK;
-    }
+    if (cl == 2) return launch_tc_cluster<BN, BKF, STAGES, 2>(ma_hi, ma_lo, w_hi, w_lo, M, N, K, epi, st, dbg_p);
+    if (cl == 4) return launch_tc_cluster<BN, BKF, STAGES, 4>(ma_hi, ma_lo, w_hi, w_lo, M, N, K, epi, st, dbg_p);
     {
         static bool attr_p = false;
         static int num_sms = 0;
