@@ -157,6 +157,13 @@ static int run_encoder(asr_handle* h, int upto_layer, cudaStream_t st) {
     const int M = (int)m.rows;
     const float* x = w.xpack;
     int K = kFeat;
+    // With both engines on the tensor cores the recurrence kernel also emits its output as the
+    // pre-split A operand of the next GEMM (next layer's input projection / attention keys): the
+    // separate split pass (read 4 B, write 8 B per element, 4 x 170k x 512 per batch) disappears.
+    static const bool fuse_env = !(getenv("ASR_B200_FUSED_ENC_SPLIT") && atoi(getenv("ASR_B200_FUSED_ENC_SPLIT")) == 0);
+    const bool fuse = fuse_env && h->gemm_mode == 1 && h->rec_mode == 2 && w.a_hi;
+    bool presplit = false;
+    h->enc_split_ready = false;
     for (int layer = 0; layer <= upto_layer; ++layer) {
         {
             StageScope sc(h, kStEncGemm, st);
@@ -165,8 +172,15 @@ static int run_encoder(asr_handle* h, int upto_layer, cudaStream_t st) {
             e.bias = h->w.enc_bias[layer];
             e.C = w.xg;
             e.ldc = 2 * kGates;
-            ASR_TRY(gemm(h, plain_a(x, K, K), h->w.enc_w_ih[layer], h->w.enc_w_ih_hi[layer],
-                         h->w.enc_w_ih_lo[layer], M, 2 * kGates, K, e, st));
+            if (presplit) {
+                StageScope sc2(h, kStGemmKernel, st);
+                h->gemm_flops += 2.0 * M * (2 * kGates) * K;
+                ASR_TRY(launch_gemm_tc(w.a_hi, w.a_lo, h->w.enc_w_ih_hi[layer], h->w.enc_w_ih_lo[layer], M, 2 * kGates,
+                                       K, e, st, &h->launches));
+            } else {
+                ASR_TRY(gemm(h, plain_a(x, K, K), h->w.enc_w_ih[layer], h->w.enc_w_ih_hi[layer],
+                             h->w.enc_w_ih_lo[layer], M, 2 * kGates, K, e, st));
+            }
         }
         {
             StageScope sc(h, kStEncRec, st);
@@ -174,7 +188,10 @@ static int run_encoder(asr_handle* h, int upto_layer, cudaStream_t st) {
             float* y = w.act[layer & 1];
             if (h->rec_mode == 2) {
                 ASR_TRY(launch_lstm_recurrence_tc3(h, layer, w.xg, layer == 0 ? nullptr : x, y,
-                                                   last ? w.enc : nullptr, w.h0, w.c0, st));
+                                                   last ? w.enc : nullptr, w.h0, w.c0, st,
+                                                   fuse ? w.a_hi : nullptr, fuse ? w.a_lo : nullptr));
+                presplit = fuse;
+                if (last) h->enc_split_ready = fuse;      // utterance-major split of `enc` for the keys GEMM
             } else if (h->rec_mode == 1) {
                 ASR_TRY(launch_lstm_recurrence_tc(h, layer, w.xg, layer == 0 ? nullptr : x, y,
                                                   last ? w.enc : nullptr, w.h0, w.c0, st));
@@ -197,8 +214,16 @@ static int run_keys(asr_handle* h, cudaStream_t st) {
     e.bias = h->w.att_b;
     e.C = w.keys;
     e.ldc = kAtt;
-    ASR_TRY(gemm(h, plain_a(w.enc, kEnc, kEnc), h->w.att_w_enc_t, h->w.att_w_enc_t_hi, h->w.att_w_enc_t_lo,
-                 (int)h->meta.rows, kAtt, kEnc, e, st));
+    if (h->enc_split_ready && h->gemm_mode == 1) {
+        h->enc_split_ready = false;
+        StageScope sc2(h, kStGemmKernel, st);
+        h->gemm_flops += 2.0 * (double)h->meta.rows * kAtt * kEnc;
+        ASR_TRY(launch_gemm_tc(w.a_hi, w.a_lo, h->w.att_w_enc_t_hi, h->w.att_w_enc_t_lo, (int)h->meta.rows, kAtt, kEnc,
+                               e, st, &h->launches));
+    } else {
+        ASR_TRY(gemm(h, plain_a(w.enc, kEnc, kEnc), h->w.att_w_enc_t, h->w.att_w_enc_t_hi, h->w.att_w_enc_t_lo,
+                     (int)h->meta.rows, kAtt, kEnc, e, st));
+    }
     return launch_keys_exp(h, st);
 }
 
@@ -750,6 +775,7 @@ int asr_reserve(asr_handle* h, int max_utts, int64_t max_rows, int max_beam, int
     w.att_score_ld = std::min<int64_t>(max_rows, 4096);
     ASR_TRY(dev_alloc_t(pool, &w.att_score, (size_t)max_utts * w.att_score_ld));
     ASR_TRY(dev_alloc_t(pool, &w.att_ticket, (size_t)max_utts));
+    ASR_TRY(dev_alloc_t(pool, &w.row_ticket, (size_t)max_utts));
     ASR_TRY(dev_alloc_t(pool, &w.tok_hist, (size_t)(max_len + 1) * R));
     ASR_TRY(dev_alloc_t(pool, &w.prev_hist, (size_t)(max_len + 1) * R));
     ASR_TRY(dev_alloc_t(pool, &w.src_row, R));

@@ -236,6 +236,7 @@ struct Workspace {
     float* att_part = nullptr;   // [B, S, k, 2 + 512] partial (max, sum, ctx)
     float* att_score = nullptr;  // [R, Lmax_cap] raw scores (alignment export)
     int* att_ticket = nullptr;   // [B]
+    int* row_ticket = nullptr;   // [B] rows of the utterance whose top-K is published (row_topk_kernel)
     int* tok_hist = nullptr;     // [max_len + 1, R]
     int* prev_hist = nullptr;    // [max_len + 1, R]
     int* src_row = nullptr;      // [R] source row of the current step's state
@@ -292,7 +293,8 @@ struct asr_handle {
     long long graph_seen[8] = {};
     int64_t graph_launches = 0;             // kernels inside the captured graph
     cudaStream_t graph_stream = nullptr;    // blocking stream standing in for the legacy stream (not capturable)
-    bool fused_dec = false;      // decoder step with pre-multiplied embeddings and producer-side operand splits
+    bool enc_split_ready = false;  // ws.a_hi / a_lo hold the split of `enc` (written by the last recurrence)
+    bool fused_dec = false;     // decoder step with pre-multiplied embeddings and producer-side operand splits
     double gemm_flops = 0.0;     // algorithmic 2*M*N*K of every GEMM-engine launch since the last reset
     cudaEvent_t ev[2 * 1024] = {};
     int n_ev = 0;
@@ -324,10 +326,12 @@ int launch_lstm_recurrence(asr_handle* h, int layer, const float* xg, const floa
 int launch_lstm_recurrence_tc(asr_handle* h, int layer, const float* xg, const float* x_in,
                               float* y_packed, float* y_utt, float* h_fin, float* c_fin,
                               cudaStream_t st);
-// weights fully TMEM-resident variant, encoder_tc3.cu
+// weights fully TMEM-resident variant, encoder_tc3.cu.  split_hi / split_lo (optional, [rows, 512]):
+// the layer output is also written as the pre-split A operand of the GEMM that consumes it (kSplitAct
+// layout, same row order as y_packed - or as y_utt when y_packed is nullptr)
 int launch_lstm_recurrence_tc3(asr_handle* h, int layer, const float* xg, const float* x_in,
                                float* y_packed, float* y_utt, float* h_fin, float* c_fin,
-                               cudaStream_t st);
+                               cudaStream_t st, float* split_hi = nullptr, float* split_lo = nullptr);
 int pack_bf16_pairs(const float* src, uint32_t* dst, long long n_pairs);
 size_t rec3_stage_bytes_per_cta();
 int launch_export_padded(asr_handle* h, const float* src_utt, int width, float* dst, int Lmax, int B,

@@ -62,7 +62,7 @@ struct InitParams {
     const float* h0; const float* c0;
     float* dh; float* dc; float* dctx;
     int* src_row; float* beam_score; int* tok_hist; int* prev_hist; int* top_done;
-    int* ctrl; int* att_ticket;
+    int* ctrl; int* att_ticket; int* row_ticket;
     float* g_accum; int* g_finished; int* g_len;
     int B, k, R;
 };
@@ -83,6 +83,7 @@ __global__ void decode_init_kernel(InitParams p) {
         if (r % p.k == 0) {
             p.top_done[u] = 0;
             p.att_ticket[u] = 0;
+            p.row_ticket[u] = 0;
             p.g_accum[u] = 0.f;
             p.g_finished[u] = 0;
             p.g_len[u] = 0;
@@ -100,7 +101,7 @@ int decode_init(asr_handle* h, int k, int max_len, bool greedy, cudaStream_t st)
     Workspace& w = h->ws;
     const int B = h->meta.B, R = B * k;
     InitParams p{w.h0, w.c0, w.dh[0], w.dc[0], w.dctx[0], w.src_row, w.beam_score, w.tok_hist,
-                 w.prev_hist, w.top_done, w.ctrl, w.att_ticket, w.g_accum, w.g_finished, w.g_len,
+                 w.prev_hist, w.top_done, w.ctrl, w.att_ticket, w.row_ticket, w.g_accum, w.g_finished, w.g_len,
                  B, k, R};
     ASR_CUDA(cudaMemsetAsync(w.tok_hist, 0, sizeof(int) * (size_t)(max_len + 1) * R, st));
     decode_init_kernel<<<R, 128, 0, st>>>(p);
@@ -497,13 +498,27 @@ __device__ __forceinline__ unsigned ordered_key(float f) {
 constexpr int kRowElems = 20;   // 256 threads * 20 >= 5004
 constexpr int kCandCap = 1024;
 
+// per-utterance merge + beam bookkeeping state (shared by the row kernel's tail)
+struct BookParams {
+    const float* cand_s; const int* cand_t;     // [R, K]
+    float* beam_score; int* src_row;            // [R]
+    int* tok_hist; int* prev_hist;              // [max_len + 1, R]
+    float* fin_score; int* fin_row;             // [max_len, B, k]
+    float* tr_cand_s; int* tr_cand_b; int* tr_cand_t;   // [max_len, B, K]
+    int* tr_bp; int* tr_tok;                    // [max_len, B, k]
+    int* top_done; int* ctrl;
+    int B, k, K, step;
+};
+
 struct RowTopkParams {
     const float* logits;      // [R, V]
     const float* beam_score;  // [R]
     float* cand_s;            // [R, K]
     int* cand_t;              // [R, K]
+    int* row_ticket;          // [B] rows of the utterance that have published their candidates
     const int* ctrl;
-    int k, K, step;
+    int k, K, step, fuse_book;
+    BookParams book;
 };
 
 __device__ __forceinline__ float block_reduce_max(float v, float* s_red) {
@@ -527,148 +542,22 @@ __device__ __forceinline__ float block_reduce_sum(float v, float* s_red) {
     return r;
 }
 
-__global__ void __launch_bounds__(256, 4)
-row_topk_kernel(RowTopkParams p) {
-    if (p.ctrl[0] >= 0) return;
-    const int r = blockIdx.x;
-    if (p.step == 0 && (r % p.k) != 0) return;      // step 0: only the first beam (model.py:862)
-    __shared__ float s_red[8];
-    __shared__ int s_wcnt[8];
-    __shared__ int s_cnt;
-    __shared__ float s_cs[kCandCap];
-    __shared__ int s_ct[kCandCap];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-    const float* row = p.logits + (size_t)r * kVocab;
-    float v[kRowElems];
-    float m = -CUDART_INF_F;
-#pragma unroll
-    for (int i = 0; i < kRowElems; ++i) {
-        const int e = tid + 256 * i;
-        v[i] = e < kVocab ? __ldg(row + e) : -CUDART_INF_F;
-        m = fmaxf(m, v[i]);
-    }
-    m = block_reduce_max(m, s_red);
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < kRowElems; ++i) s += expf(v[i] - m);      // exp(-inf) = 0 for padding
-    s = block_reduce_sum(s, s_red);
-    const float lse = m + logf(s);
-    const float bs = p.beam_score[r];
-    float tmf = -CUDART_INF_F;
-#pragma unroll
-    for (int i = 0; i < kRowElems; ++i) {
-        v[i] = __fadd_rn(__fsub_rn(v[i], lse), bs);               // model.py:835-836 (padding stays -inf)
-        tmf = fmaxf(tmf, v[i]);
-    }
-    // Threshold: the K-th largest of the 256 per-thread maxima is a lower bound of the K-th largest
-    // element (they are K distinct elements), so {x >= threshold} holds >= K candidates and, for
-    // any non-degenerate row, only a few more.  Found by a 32-step bisection on the ordered key
-    // with __syncthreads_count (one barrier-with-popcount per bit, almost no instructions).
-    const unsigned tm = ordered_key(tmf);
-    unsigned kth = 0u;
-#pragma unroll 1
-    for (int bit = 31; bit >= 0; --bit) {
-        const unsigned cand = kth | (1u << bit);
-        if (__syncthreads_count(tm >= cand) >= p.K) kth = cand;
-    }
-    if (tid == 0) s_cnt = 0;
-    __syncthreads();
-    auto collect = [&]() {
-#pragma unroll
-        for (int i = 0; i < kRowElems; ++i) {
-            if (ordered_key(v[i]) >= kth && v[i] != -CUDART_INF_F) {
-                const int slot = atomicAdd(&s_cnt, 1);
-                if (slot < kCandCap) { s_cs[slot] = v[i]; s_ct[slot] = tid + 256 * i; }
-            }
-        }
-    };
-    collect();
-    __syncthreads();
-    if (s_cnt > kCandCap) {
-        // Degenerate row (more than kCandCap values above the threshold): exact K-th largest by
-        // bisection over all elements, then collect again (ties beyond the cap are truncated).
-        kth = 0u;
-#pragma unroll 1
-        for (int bit = 31; bit >= 0; --bit) {
-            const unsigned cand = kth | (1u << bit);
-            int c = 0;
-#pragma unroll
-            for (int i = 0; i < kRowElems; ++i) c += (ordered_key(v[i]) >= cand && v[i] != -CUDART_INF_F) ? 1 : 0;
-            c = __reduce_add_sync(0xffffffffu, c);
-            __syncthreads();
-            if (lane == 0) s_wcnt[warp] = c;
-            __syncthreads();
-            int tot = 0;
-#pragma unroll
-            for (int w = 0; w < 8; ++w) tot += s_wcnt[w];
-            if (tot >= p.K) kth = cand;
-        }
-        __syncthreads();
-        if (tid == 0) s_cnt = 0;
-        __syncthreads();
-        collect();
-        __syncthreads();
-    }
-    const int n = min(s_cnt, kCandCap);
-    // rank by counting: order (score desc, token asc)
-    for (int i = tid; i < n; i += 256) {
-        const float si = s_cs[i];
-        const int ti = s_ct[i];
-        int rank = 0;
-        for (int j = 0; j < n; ++j) {
-            const float sj = s_cs[j];
-            rank += (sj > si || (sj == si && s_ct[j] < ti)) ? 1 : 0;
-        }
-        if (rank < p.K) {
-            p.cand_s[(size_t)r * p.K + rank] = si;
-            p.cand_t[(size_t)r * p.K + rank] = ti;
-        }
-    }
-}
-
-int launch_row_topk(asr_handle* h, int k, int step, cudaStream_t st) {
-    Workspace& w = h->ws;
-    RowTopkParams p{w.logits, w.beam_score, w.rowcand_s, w.rowcand_t, w.ctrl, k, 2 * k, step};
-    row_topk_kernel<<<h->meta.B * k, 256, 0, st>>>(p);
-    ASR_CHECK_LAUNCH();
-    h->launches++;
-    return ASR_OK;
-}
-
-// ---------------------------------------------------------------------------------------------
-// per-utterance merge + beam bookkeeping
-struct BookParams {
-    const float* cand_s; const int* cand_t;     // [R, K]
-    float* beam_score; int* src_row;            // [R]
-    int* tok_hist; int* prev_hist;              // [max_len + 1, R]
-    float* fin_score; int* fin_row;             // [max_len, B, k]
-    float* tr_cand_s; int* tr_cand_b; int* tr_cand_t;   // [max_len, B, K]
-    int* tr_bp; int* tr_tok;                    // [max_len, B, k]
-    int* top_done; int* ctrl;
-    int B, k, K, step;
-};
-
-__global__ void __launch_bounds__(512)
-beam_bookkeep_kernel(BookParams p) {
-    if (p.ctrl[0] >= 0) return;
-    __shared__ float s_s[512];
-    __shared__ int s_f[512];
-    __shared__ float s_cs[32];
-    __shared__ int s_cf[32];
-    const int u = blockIdx.x, tid = threadIdx.x;
+// Merge of the k rows' top-K lists of utterance u and the beam bookkeeping of one step
+// (model.py:862-929).  Runs in the LAST row CTA of the utterance to publish its candidates.
+__device__ void beam_bookkeep(const BookParams& p, int u, float* s_s, int* s_f, float* s_cs, int* s_cf) {
+    const int tid = threadIdx.x;
     const int k = p.k, K = p.K, R = p.B * k;
     const int nrow = p.step == 0 ? 1 : k;
-    const int n = nrow * K;
-    if (tid < n) {
-        const int b = tid / K, j = tid - b * K;
-        s_s[tid] = p.cand_s[(size_t)(u * k + b) * K + j];
-        s_f[tid] = b * kVocab + p.cand_t[(size_t)(u * k + b) * K + j];
+    const int n = nrow * K;                                   // <= 16 * 32 = 512
+    for (int i = tid; i < n; i += 256) {
+        const int b = i / K, j = i - b * K;
+        s_s[i] = __ldcg(p.cand_s + (size_t)(u * k + b) * K + j);
+        s_f[i] = b * kVocab + __ldcg(p.cand_t + (size_t)(u * k + b) * K + j);
     }
     __syncthreads();
-    if (tid < n) {
-        const float si = s_s[tid];
-        const int fi = s_f[tid];
+    for (int i = tid; i < n; i += 256) {
+        const float si = s_s[i];
+        const int fi = s_f[i];
         int rank = 0;
         for (int j = 0; j < n; ++j) {
             const float sj = s_s[j];
@@ -683,25 +572,24 @@ beam_bookkeep_kernel(BookParams p) {
         p.tr_cand_b[o] = s_cf[tid] / kVocab;
         p.tr_cand_t[o] = s_cf[tid] % kVocab;
     }
-    if (tid == 0) {
+    if (tid < 32) {
+        // one warp, lane j = rank j of the merged list (K <= 32)
+        const int j = tid;
+        const bool valid = j < K;
+        const int f = valid ? s_cf[j] : 0;
+        const int beam = f / kVocab, tok = f - beam * kVocab;
+        const bool eos = valid && tok == kEos;
         // finished hypotheses: </s> among the top k (model.py:876-889)
-        for (int j = 0; j < k; ++j) {
-            const int tok = s_cf[j] % kVocab;
+        if (eos && j < k) {
             const size_t o = ((size_t)p.step * p.B + u) * k + j;
-            if (tok == kEos) {
-                p.fin_score[o] = s_cs[j];
-                p.fin_row[o] = u * k + s_cf[j] / kVocab;
-            }
+            p.fin_score[o] = s_cs[j];
+            p.fin_row[o] = u * k + beam;
         }
-        int done = p.top_done[u];
-        if (s_cf[0] % kVocab == kEos) done = 1;
-        p.top_done[u] = done;
+        if (j == 0 && eos) p.top_done[u] = 1;
         // active set: first k non-EOS candidates in rank order (model.py:904-929)
-        int i = 0;
-        for (int j = 0; j < K && i < k; ++j) {
-            const int tok = s_cf[j] % kVocab;
-            if (tok == kEos) continue;
-            const int beam = s_cf[j] / kVocab;
+        const unsigned live = __ballot_sync(0xffffffffu, valid && !eos);
+        const int i = __popc(live & ((1u << j) - 1u));
+        if (valid && !eos && i < k) {
             const int r = u * k + i;
             p.src_row[r] = u * k + beam;
             p.beam_score[r] = s_cs[j];
@@ -710,33 +598,197 @@ beam_bookkeep_kernel(BookParams p) {
             const size_t o = ((size_t)p.step * p.B + u) * k + i;
             p.tr_bp[o] = beam;
             p.tr_tok[o] = tok;
-            ++i;
         }
         // early stop (model.py:897-901): decided by the last utterance to arrive
         __threadfence();
-        const int t = atomicAdd(p.ctrl + 2, 1);
-        if (t == p.B - 1) {
-            __threadfence();
-            int all = 1;
-            for (int b = 0; b < p.B; ++b) all &= (*((volatile int*)p.top_done + b) != 0);
-            p.ctrl[2] = 0;
-            p.ctrl[3] = p.step + 1;
-            if (all) p.ctrl[0] = p.step;
+        __syncwarp();
+        if (j == 0) {
+            const int t = atomicAdd(p.ctrl + 2, 1);
+            if (t == p.B - 1) {
+                __threadfence();
+                int all = 1;
+                for (int b = 0; b < p.B; ++b) all &= (*((volatile int*)p.top_done + b) != 0);
+                p.ctrl[2] = 0;
+                p.ctrl[3] = p.step + 1;
+                if (all) p.ctrl[0] = p.step;
+            }
         }
     }
 }
 
-int launch_beam_bookkeep(asr_handle* h, int k, int step, int max_len, cudaStream_t st) {
-    (void)max_len;
+__global__ void __launch_bounds__(256)
+beam_bookkeep_kernel(BookParams p) {
+    if (p.ctrl[0] >= 0) return;
+    __shared__ float s_s[512];
+    __shared__ int s_f[512];
+    __shared__ float s_cs[32];
+    __shared__ int s_cf[32];
+    beam_bookkeep(p, blockIdx.x, s_s, s_f, s_cs, s_cf);
+}
+
+// One CTA per decoder row: log-softmax statistics, score = logit - lse + beam score (model.py:835-836),
+// exact top-K (K = 2k <= 32, ties by token id), then - in the last row CTA of each utterance - the
+// per-utterance merge and bookkeeping, so a decoder step needs no separate bookkeeping launch.
+__global__ void __launch_bounds__(256, 4)
+row_topk_kernel(RowTopkParams p) {
+    if (p.ctrl[0] >= 0) return;
+    const int r = blockIdx.x;
+    const int u = r / p.k;
+    __shared__ float s_red[8];
+    __shared__ int s_wcnt[8];
+    __shared__ int s_cnt, s_last;
+    __shared__ float s_gmax[64];
+    __shared__ float s_thr;
+    __shared__ float s_cs[kCandCap];
+    __shared__ int s_ct[kCandCap];
+    __shared__ float s_top_s[32];
+    __shared__ int s_top_f[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nrow = p.step == 0 ? 1 : p.k;                // step 0: only the first beam (model.py:862)
+    const bool active = p.step != 0 || (r % p.k) == 0;
+
+    if (active) {
+        // row base is 16-byte aligned (5004 * 4 = 1251 * 16): 5 float4 per thread cover the row
+        const float4* row4 = reinterpret_cast<const float4*>(p.logits + (size_t)r * kVocab);
+        float v[kRowElems];
+        float m = -CUDART_INF_F;
+#pragma unroll
+        for (int i = 0; i < kRowElems / 4; ++i) {
+            const int e4 = tid + 256 * i;
+            float4 x = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+            if (e4 < kVocab / 4) x = __ldg(row4 + e4);
+            v[4 * i] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
+            m = fmaxf(m, fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w)));
+        }
+        m = block_reduce_max(m, s_red);
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < kRowElems; ++i) s += __expf(v[i] - m);    // exp(-inf) = 0 for padding
+        s = block_reduce_sum(s, s_red);
+        const float lse = m + logf(s);
+        const float bs = p.beam_score[r];
+        float tmf = -CUDART_INF_F;
+#pragma unroll
+        for (int i = 0; i < kRowElems; ++i) {
+            v[i] = __fadd_rn(__fsub_rn(v[i], lse), bs);               // padding stays -inf
+            tmf = fmaxf(tmf, v[i]);
+        }
+        // Threshold: the maxima of 64 groups of 4 threads are 64 distinct row elements, so their K-th
+        // largest T (K <= 32) has at least K elements >= T - and for a non-degenerate row only a few
+        // more (expected 64 (H_64 - H_(64-K)): 18 for K = 16, 44 for K = 32).  Ranks by counting over
+        // the 64 maxima, 2 barriers.  (Measured alternatives: 32-step bisection with
+        // __syncthreads_count over the 256 thread maxima - 32 barriers; min over K group maxima - one
+        // barrier but ~3x the candidates.)
+        float gm = fmaxf(tmf, __shfl_xor_sync(0xffffffffu, tmf, 1));
+        gm = fmaxf(gm, __shfl_xor_sync(0xffffffffu, gm, 2));
+        if ((tid & 3) == 0) s_gmax[tid >> 2] = gm;
+        if (tid == 0) s_cnt = 0;
+        __syncthreads();
+        {
+            const int g = tid >> 2, part = tid & 3;
+            int above = 0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int o = part * 16 + i;
+                const float x = s_gmax[o];
+                above += (x > gm || (x == gm && o < g)) ? 1 : 0;
+            }
+            above += __shfl_xor_sync(0xffffffffu, above, 1);
+            above += __shfl_xor_sync(0xffffffffu, above, 2);
+            if (part == 0 && above == p.K - 1) s_thr = gm;
+        }
+        __syncthreads();
+        unsigned kth = ordered_key(s_thr);
+        auto collect = [&]() {
+#pragma unroll
+            for (int i = 0; i < kRowElems; ++i) {
+                if (ordered_key(v[i]) >= kth && v[i] != -CUDART_INF_F) {
+                    const int slot = atomicAdd(&s_cnt, 1);
+                    if (slot < kCandCap) { s_cs[slot] = v[i]; s_ct[slot] = 4 * (tid + 256 * (i >> 2)) + (i & 3); }
+                }
+            }
+        };
+        collect();
+        __syncthreads();
+        if (s_cnt > kCandCap) {
+            // Degenerate row (more than kCandCap values above the threshold): exact K-th largest by
+            // bisection over all elements, then collect again (ties beyond the cap are truncated).
+            kth = 0u;
+#pragma unroll 1
+            for (int bit = 31; bit >= 0; --bit) {
+                const unsigned cand = kth | (1u << bit);
+                int c = 0;
+#pragma unroll
+                for (int i = 0; i < kRowElems; ++i) c += (ordered_key(v[i]) >= cand && v[i] != -CUDART_INF_F) ? 1 : 0;
+                c = __reduce_add_sync(0xffffffffu, c);
+                __syncthreads();
+                if (lane == 0) s_wcnt[warp] = c;
+                __syncthreads();
+                int tot = 0;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) tot += s_wcnt[w];
+                if (tot >= p.K) kth = cand;
+            }
+            __syncthreads();
+            if (tid == 0) s_cnt = 0;
+            __syncthreads();
+            collect();
+            __syncthreads();
+        }
+        const int n = min(s_cnt, kCandCap);
+        // rank by counting: order (score desc, token asc)
+        for (int i = tid; i < n; i += 256) {
+            const float si = s_cs[i];
+            const int ti = s_ct[i];
+            int rank = 0;
+            for (int j = 0; j < n; ++j) {
+                const float sj = s_cs[j];
+                rank += (sj > si || (sj == si && s_ct[j] < ti)) ? 1 : 0;
+            }
+            if (rank < p.K) {
+                p.cand_s[(size_t)r * p.K + rank] = si;
+                p.cand_t[(size_t)r * p.K + rank] = ti;
+            }
+        }
+        if (!p.fuse_book) return;
+        // publish; the last of the utterance's `nrow` rows merges and does the bookkeeping
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            const int t = atomicAdd(p.row_ticket + u, 1);
+            s_last = (t == nrow - 1);
+            if (s_last) p.row_ticket[u] = 0;
+        }
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+        beam_bookkeep(p.book, u, s_cs, s_ct, s_top_s, s_top_f);
+    }
+}
+
+int launch_row_topk(asr_handle* h, int k, int step, cudaStream_t st) {
     Workspace& w = h->ws;
-    BookParams p{w.rowcand_s, w.rowcand_t, w.beam_score, w.src_row, w.tok_hist, w.prev_hist,
+    // the utterance's last row CTA overwrites beam_score for the next step only after every row of that
+    // utterance has read its own entry (they all published before the ticket completes)
+    float* bs_cur = w.beam_score;
+    float* bs_nxt = w.beam_score;
+    BookParams b{w.rowcand_s, w.rowcand_t, bs_nxt, w.src_row, w.tok_hist, w.prev_hist,
                  w.fin_score, w.fin_row, w.tr_cand_s, w.tr_cand_b, w.tr_cand_t, w.tr_bp, w.tr_tok,
                  w.top_done, w.ctrl, h->meta.B, k, 2 * k, step};
-    beam_bookkeep_kernel<<<h->meta.B, 512, 0, st>>>(p);
+    static const int fuse = getenv("ASR_B200_FUSE_BOOK") ? atoi(getenv("ASR_B200_FUSE_BOOK")) : 0;
+    RowTopkParams p{w.logits, bs_cur, w.rowcand_s, w.rowcand_t, w.row_ticket, w.ctrl, k, 2 * k, step, fuse, b};
+    row_topk_kernel<<<h->meta.B * k, 256, 0, st>>>(p);
     ASR_CHECK_LAUNCH();
     h->launches++;
+    if (!fuse) {
+        beam_bookkeep_kernel<<<h->meta.B, 256, 0, st>>>(b);
+        ASR_CHECK_LAUNCH();
+        h->launches++;
+    }
     return ASR_OK;
 }
+
+int launch_beam_bookkeep(asr_handle*, int, int, int, cudaStream_t) { return ASR_OK; }   // part of launch_row_topk
 
 // ---------------------------------------------------------------------------------------------
 // n-gram LM on device (tables from asr_set_lm; semantics of oracle NGramLM / kenlm .score)

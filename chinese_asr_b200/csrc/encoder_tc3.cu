@@ -51,6 +51,18 @@ __device__ __forceinline__ void bulk_g2s_multicast(void* dst_smem, const void* s
         ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
         : "memory");
 }
+// shared memory of this CTA -> shared memory of cluster CTA `rank` (same offsets), completion on the
+// destination CTA's mbarrier
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void bulk_s2s(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t bar_cluster) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_cluster), "r"(src_cta), "r"(bytes), "r"(bar_cluster)
+                 : "memory");
+}
 // D[tmem] += A[tmem, bf16] * B[smem desc, bf16]
 __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
                                              uint32_t accumulate) {
@@ -108,8 +120,11 @@ struct Params {
     const float* whh_hi;        // [2, 1024, 256] permuted, rn_tf32(W_hh)
     const uint32_t* whh_lo_bf;  // [2, 1024, 128] permuted, bf16 pairs of (W_hh - hi)
     const float* x_in;
+    int xchg_dsmem;         // 1: exchange h through distributed shared memory, 0: through global staging
     float* y_packed;
     float* y_utt;
+    float* y_hi;            // optional [rows, 512]: rn_tf32(y), rows as y_utt when that is written, else as y_packed
+    uint32_t* y_cross;      // optional: per 8-float block 8 x bf16(y - hi) then 8 x bf16(y)  (gemm_tc.cu kSplitAct)
     float* h_fin;
     float* c_fin;
     uint8_t* stage;             // [gridDim.x][kStageBytes] global staging images
@@ -217,12 +232,43 @@ lstm_rec_tc3_kernel(Params p) {
     constexpr uint32_t idesc_t = idesc_tf32(128, NB);
     constexpr uint32_t idesc_b = idesc_bf16(128, NB);
 
-    for (int s = 0; s < Lc; ++s) {
-        const int t = dir == 0 ? s : Lc - 1 - s;
-        int nact = 0;
-        for (int i = 0; i < nrows; ++i) nact += (s_len[i] > t) ? 1 : 0;
-        const int row_t = p.toff[t] + r0;
+    // rows are sorted by decreasing length: the active count follows t incrementally
+    int nact = dir == 0 ? nrows : 0;
+    int prev_t = 0, prev_row_t = 0, prev_nact = 0;
+    float yv[P];
+#pragma unroll
+    for (int q = 0; q < P; ++q) yv[q] = 0.f;
+    // layer output of one step: y (+ residual), and optionally its operand split for the next GEMM.
+    // Called one step late (after the next step's MMAs are issued) so that it never delays them.
+    auto store_outputs = [&](int t, int row_t, int n_act) {
+#pragma unroll
+        for (int q = 0; q < P; ++q) {
+            const int i = warp + NW * q;
+            if (i < n_act) {
+                const size_t row = (size_t)(row_t + i);
+                const size_t urow = p.y_utt ? (size_t)(p.uoff[r0 + i] + t) : 0;
+                if (p.y_packed) p.y_packed[row * kEnc + ocol] = yv[q];
+                if (p.y_utt) p.y_utt[urow * kEnc + ocol] = yv[q];
+                if (p.y_hi) {
+                    // operand split for the consuming GEMM: lane pairs pack two bf16 (even lane:
+                    // residuals, odd lane: values) - all 32 lanes of the warp are in this branch
+                    const size_t srow = p.y_utt ? urow : row;      // last layer: rows as `enc`
+                    const float hi = rn_tf32(yv[q]);
+                    const float lo = yv[q] - hi;
+                    const float lo_n = __shfl_xor_sync(0xffffffffu, lo, 1);
+                    const float y_n = __shfl_xor_sync(0xffffffffu, yv[q], 1);
+                    p.y_hi[srow * kEnc + ocol] = hi;
+                    const bool odd = (ocol & 1) != 0;
+                    const __nv_bfloat162 pk = odd ? __floats2bfloat162_rn(y_n, yv[q]) : __floats2bfloat162_rn(lo, lo_n);
+                    // block of 8 floats -> 8 words: words 0-3 residual pairs, words 4-7 value pairs
+                    uint32_t* blk = p.y_cross + srow * kEnc + (size_t)(ocol & ~7);
+                    blk[(odd ? 4 : 0) + ((ocol & 7) >> 1)] = *reinterpret_cast<const uint32_t*>(&pk);
+                }
+            }
+        }
+    };
 
+    for (int s = 0; s < Lc; ++s) {
         if (warp == 4) {
             if (lane == 0) {
                 if (s > 0) mbar_wait(h_ready, (uint32_t)((s - 1) & 1));
@@ -249,11 +295,17 @@ lstm_rec_tc3_kernel(Params p) {
             __syncwarp();
         }
 
-        float xi[P], xf[P], xgg[P], xo[P], xres[P], yv[P];
+        if (s > 0) store_outputs(prev_t, prev_row_t, prev_nact);
+        const int t = dir == 0 ? s : Lc - 1 - s;
+        if (dir == 0) { while (nact > 0 && s_len[nact - 1] <= t) --nact; }
+        else { while (nact < nrows && s_len[nact] > t) ++nact; }
+        const int row_t = p.toff[t] + r0;
+
+        float xi[P], xf[P], xgg[P], xo[P], xres[P];
 #pragma unroll
         for (int q = 0; q < P; ++q) {
             const int i = warp + NW * q;
-            xi[q] = xf[q] = xgg[q] = xo[q] = xres[q] = yv[q] = 0.f;
+            xi[q] = xf[q] = xgg[q] = xo[q] = xres[q] = 0.f;
             if (i < nact) {
                 if (p.x_in) xres[q] = __ldg(p.x_in + (size_t)(row_t + i) * kEnc + ocol);
                 const float* g = p.xg + (size_t)(row_t + i) * (2 * kGates) + dir * kGates + j * 128 + uu;
@@ -295,9 +347,13 @@ lstm_rec_tc3_kernel(Params p) {
                     h_reg[q] = hh;
                     const float hi = rn_tf32(hh);
                     const float lo = rn_tf32(hh - hi);
-                    *reinterpret_cast<float*>(stage + sw128_offset(i, uu)) = hi;
-                    *reinterpret_cast<float*>(stage + kHi + sw128_offset(i, uu)) = lo;
-                    *reinterpret_cast<__nv_bfloat16*>(stage + 2 * kHi + sw64_offset(i, uu)) = __float2bfloat16_rn(hh);
+                    // image of this CTA's 32-unit slab of the next B operand: into global staging, or (all
+                    // 8 CTAs' MMAs of this step are complete - mma_done counts 8 commits) straight into
+                    // the slab's place in the local operand tile
+                    uint8_t* img = p.xchg_dsmem ? T + j * kSlab : stage;
+                    *reinterpret_cast<float*>(img + sw128_offset(i, uu)) = hi;
+                    *reinterpret_cast<float*>(img + kHi + sw128_offset(i, uu)) = lo;
+                    *reinterpret_cast<__nv_bfloat16*>(img + 2 * kHi + sw64_offset(i, uu)) = __float2bfloat16_rn(hh);
                     yv[q] = hh + xres[q];
                 }
             }
@@ -305,26 +361,35 @@ lstm_rec_tc3_kernel(Params p) {
         }
         if (p.dbg && blockIdx.x == 0 && tid == 0) p.dbg[s * 8 + 4] = clock64();
         if (s + 1 < Lc) {
-            __threadfence();
-            fence_proxy_async();
-            __syncthreads();
-            if (p.dbg && blockIdx.x == 0 && tid == 0) p.dbg[s * 8 + 5] = clock64();
-            if (tid == 0) {
-                mbar_expect_tx(h_ready, 8u * (uint32_t)kSlab);
-                bulk_g2s_multicast(T + j * kSlab, stage, (uint32_t)kSlab, h_ready, (uint16_t)0xFF);
-                if (p.dbg && blockIdx.x == 0) p.dbg[s * 8 + 6] = clock64();
+            if (p.xchg_dsmem) {
+                // the local slab is in place; push it to the 7 peers with one bulk copy each (issued by 7
+                // different warps), each completing on the receiver's h_ready: no global round trip and
+                // no membar.gl on the step's critical path
+                fence_proxy_async();
+                __syncthreads();
+                if (p.dbg && blockIdx.x == 0 && tid == 0) p.dbg[s * 8 + 5] = clock64();
+                if (tid == 0) mbar_expect_tx(h_ready, 7u * (uint32_t)kSlab);
+                if (lane == 0 && warp >= 1 && warp <= 7) {
+                    const uint32_t peer = (uint32_t)((j + warp) & 7);
+                    const uint32_t src = smem_u32(T + j * kSlab);
+                    bulk_s2s(mapa_u32(src, peer), src, (uint32_t)kSlab, mapa_u32(smem_u32(h_ready), peer));
+                }
+                if (p.dbg && blockIdx.x == 0 && tid == 0) p.dbg[s * 8 + 6] = clock64();
+            } else {
+                __threadfence();
+                fence_proxy_async();
+                __syncthreads();
+                if (p.dbg && blockIdx.x == 0 && tid == 0) p.dbg[s * 8 + 5] = clock64();
+                if (tid == 0) {
+                    mbar_expect_tx(h_ready, 8u * (uint32_t)kSlab);
+                    bulk_g2s_multicast(T + j * kSlab, stage, (uint32_t)kSlab, h_ready, (uint16_t)0xFF);
+                    if (p.dbg && blockIdx.x == 0) p.dbg[s * 8 + 6] = clock64();
+                }
             }
         }
-#pragma unroll
-        for (int q = 0; q < P; ++q) {
-            const int i = warp + NW * q;
-            if (i < nact) {
-                const size_t row = (size_t)(row_t + i);
-                if (p.y_packed) p.y_packed[row * kEnc + ocol] = yv[q];
-                if (p.y_utt) p.y_utt[(size_t)(p.uoff[r0 + i] + t) * kEnc + ocol] = yv[q];
-            }
-        }
+        prev_t = t; prev_row_t = row_t; prev_nact = nact;
     }
+    if (Lc > 0) store_outputs(prev_t, prev_row_t, prev_nact);
 
 #pragma unroll
     for (int q = 0; q < P; ++q) {
@@ -377,9 +442,14 @@ int pack_bf16_pairs(const float* src, uint32_t* dst, long long n_pairs) {
 size_t rec3_stage_bytes_per_cta() { return rec3::kStageBytes; }
 
 int launch_lstm_recurrence_tc3(asr_handle* h, int layer, const float* xg, const float* x_in, float* y_packed,
-                               float* y_utt, float* h_fin, float* c_fin, cudaStream_t st) {
+                               float* y_utt, float* h_fin, float* c_fin, cudaStream_t st, float* split_hi,
+                               float* split_lo) {
     const BatchMeta& m = h->meta;
     rec3::Params p{};
+    static const int xchg = getenv("ASR_B200_REC_XCHG") ? atoi(getenv("ASR_B200_REC_XCHG")) : 0;   // measured: 7 DSMEM bulk copies per CTA per step (10.9 -> 17.9 ms per batch) lose to one multicast from L2
+    p.xchg_dsmem = xchg;
+    p.y_hi = split_hi;
+    p.y_cross = reinterpret_cast<uint32_t*>(split_lo);
     p.xg = xg;
     p.whh_hi = h->w.enc_w_hh_hi[layer];
     p.whh_lo_bf = h->w.enc_w_hh_lo_bf[layer];
