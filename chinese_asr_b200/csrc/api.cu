@@ -497,7 +497,9 @@ static int features_device(asr_handle* h, const float* d_pcm, const int64_t* h_p
     ASR_CUDA(cudaStreamSynchronize(st));
     StageScope sc(h, kStFeat, st);
     ASR_TRY(launch_logmel(h, d_pcm, w.d_pcm_off, w.d_frame_off, B, foff[B], w.mel, st));
-    ASR_TRY(launch_delta_cmvn(h, w.mel, w.d_frame_off, w.d_featrow_off, B, normalise,
+    int lmax = 0;
+    for (int i = 0; i < B; ++i) lmax = std::max(lmax, (int)h_L[i]);
+    ASR_TRY(launch_delta_cmvn(h, w.mel, w.d_frame_off, w.d_featrow_off, B, lmax, normalise,
                               packed_out ? h->meta.d_feat2packed : nullptr, d_out, st));
     return ASR_OK;
 }
@@ -741,6 +743,7 @@ int asr_reserve(asr_handle* h, int max_utts, int64_t max_rows, int max_beam, int
         ASR_TRY(dev_alloc_t(pool, &w.mel, (size_t)w.max_frames * kMel));
     }
     ASR_TRY(dev_alloc_t(pool, &w.xpack, (size_t)max_rows * kFeat));
+    ASR_TRY(dev_alloc_t(pool, &w.feat_partial, (size_t)max_utts * 4 * kFeat * 2));     // [B, 4, 720] double2
     ASR_TRY(dev_alloc_t(pool, &w.d_pcm_off, (size_t)max_utts + 1));
     ASR_TRY(dev_alloc_t(pool, &w.d_frame_off, (size_t)max_utts + 1));
     ASR_TRY(dev_alloc_t(pool, &w.d_featrow_off, (size_t)max_utts + 1));

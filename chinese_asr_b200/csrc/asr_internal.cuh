@@ -213,6 +213,7 @@ struct Workspace {
     float* pcm = nullptr;        // [max_samples] staging for asr_transcribe
     float* mel = nullptr;        // [max_frames, 80]
     float* xpack = nullptr;      // [max_rows, 720] packed time-major encoder input
+    double* feat_partial = nullptr;  // [max_utts, 4, 720] (sum, sum of squares) partials of the CMVN statistics
     long long* d_pcm_off = nullptr;  // [max_utts + 1]
     int* d_frame_off = nullptr;      // [max_utts + 1]  STFT frames prefix
     int* d_featrow_off = nullptr;    // [max_utts + 1]  feature rows prefix (original order)
@@ -311,8 +312,8 @@ int launch_logmel(asr_handle* h, const float* d_pcm, const long long* d_pcm_off,
                   const int* d_frame_off, int B, int total_frames, float* d_mel, cudaStream_t st);
 // out_rowmap: feature row (utterance-major, original order) -> output row; nullptr = identity
 int launch_delta_cmvn(asr_handle* h, const float* d_mel, const int* d_frame_off,
-                      const int* d_featrow_off, int B, int normalise, const int* out_rowmap,
-                      float* d_out, cudaStream_t st);
+                      const int* d_featrow_off, int B, int max_rows_per_utt, int normalise,
+                      const int* out_rowmap, float* d_out, cudaStream_t st);
 
 // ---- encoder.cu ------------------------------------------------------------------------------
 int launch_pack_rows(asr_handle* h, const float* src, const int* rowmap, int64_t rows, int width,

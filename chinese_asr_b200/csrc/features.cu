@@ -25,7 +25,8 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
 
-constexpr int kFramesPerCta = 8;
+constexpr int kFramesPerCta = 8;      // one warp per frame
+constexpr int kFrameRounds = 4;       // frames per warp: the twiddle / window tables are staged once per 32 frames
 
 __global__ void __launch_bounds__(256)
 logmel_kernel(const float* __restrict__ pcm, const long long* __restrict__ pcm_off,
@@ -47,8 +48,10 @@ logmel_kernel(const float* __restrict__ pcm, const long long* __restrict__ pcm_o
     for (int i = tid; i < kWin; i += 256) s_win[i] = g_window[i];
     __syncthreads();
 
-    const int gf = blockIdx.x * kFramesPerCta + warp;
+    for (int round = 0; round < kFrameRounds; ++round) {
+    const int gf = (blockIdx.x * kFrameRounds + round) * kFramesPerCta + warp;
     if (gf >= total_frames) return;
+    __syncwarp();                       // the previous frame's mel pass has finished reading `power`
 
     // utterance of this frame: largest u with frame_off[u] <= gf
     int lo = 0, hi = B;
@@ -136,69 +139,122 @@ logmel_kernel(const float* __restrict__ pcm, const long long* __restrict__ pcm_o
         if (acc == 0.f) acc = 1.1920928955078125e-07f;   // torch.finfo(float32).eps
         out[m] = logf(acc);
     }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
 struct Taps { float w[27]; };
 
-__global__ void __launch_bounds__(960)
-delta_cmvn_kernel(const float* __restrict__ mel, const int* __restrict__ frame_off,
-                  const int* __restrict__ featrow_off, Taps taps, int normalise,
-                  const int* __restrict__ out_rowmap, float* __restrict__ out) {
-    __shared__ double s_sum[4][240];
-    __shared__ double s_sq[4][240];
-    const int u = blockIdx.x;
-    const int c = blockIdx.y;
-    const int x = threadIdx.x;          // 0..239 = j*80 + m
-    const int ty = threadIdx.y;         // 0..3
+constexpr int kSubRows = 32;                       // stacked rows per staged sub-chunk
+constexpr int kSubFrames = 3 * kSubRows + 8;       // log-mel frames they touch (9 taps, stride 3)
+constexpr int kStatChunks = 4;                     // partial CMVN sums per utterance
+
+// Stage log-mel frames [3 g0 - 4, 3 g0 - 4 + kSubFrames) of one utterance in shared memory (zero outside
+// [0, T): the correlation's zero padding, data.py:157-162) and hand every (row g, column group c)
+// value of rows [g0, g1) to `sink(g, c, value)`; thread (x = j*80 + m, ty) owns column c*240 + x of
+// rows g = g0 + ty, g0 + ty + 4, ...  Each mel value is read from global memory once per sub-chunk
+// (coalesced float4) instead of once per tap.
+template <typename Sink>
+__device__ __forceinline__ void delta_rows(const float* __restrict__ mel_u, int T, int g0, int g1,
+                                           const Taps& taps, float* s_mel, Sink&& sink) {
+    const int x = threadIdx.x, ty = threadIdx.y;
     const int j = x / kMel, m = x - j * kMel;
+    const int tid = ty * 240 + x;
+    const int tb = 3 * g0 - 4;
+    __syncthreads();                                // previous sub-chunk fully consumed
+    for (int i = tid; i < kSubFrames * (kMel / 4); i += 960) {
+        const int fr = i / (kMel / 4), q = i - fr * (kMel / 4);
+        const int tt = tb + fr;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tt >= 0 && tt < T) v = __ldg(reinterpret_cast<const float4*>(mel_u + (size_t)tt * kMel) + q);
+        reinterpret_cast<float4*>(s_mel)[i] = v;
+    }
+    __syncthreads();
+    for (int g = g0 + ty; g < g1; g += 4) {
+        const float* base = s_mel + (3 * (g - g0) + j) * kMel + m;     // frame t - 4 of this row / slot
+        // c = 0: identity tap (i = 4); c = 1: taps 2..6; c = 2: taps 0..8  (zero weights skipped as in
+        // the reference's dense 9-tap kernels they are exact zeros)
+        sink(g, 0, taps.w[4] * base[4 * kMel]);
+        float a1 = 0.f;
+#pragma unroll
+        for (int i = 2; i < 7; ++i) a1 = fmaf(taps.w[9 + i], base[i * kMel], a1);
+        sink(g, 1, a1);
+        float a2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) a2 = fmaf(taps.w[18 + i], base[i * kMel], a2);
+        sink(g, 2, a2);
+    }
+}
+
+// pass 1: partial sums of every feature column over a quarter of the utterance's rows
+__global__ void __launch_bounds__(960)
+feat_stats_kernel(const float* __restrict__ mel, const int* __restrict__ frame_off,
+                  const int* __restrict__ featrow_off, Taps taps, double2* __restrict__ partial) {
+    __shared__ __align__(16) float s_mel[kSubFrames * kMel];
+    __shared__ double s_red[2][4][240];
+    const int u = blockIdx.x, ch = blockIdx.y;
+    const int x = threadIdx.x, ty = threadIdx.y;
+    const int f0 = frame_off[u];
+    const int T = frame_off[u + 1] - f0;
+    const int L = featrow_off[u + 1] - featrow_off[u];
+    const int per = (L + kStatChunks - 1) / kStatChunks;
+    const int ga = min(L, ch * per), gb = min(L, ga + per);
+    double sum[3] = {0.0, 0.0, 0.0}, sq[3] = {0.0, 0.0, 0.0};
+    for (int g0 = ga; g0 < gb; g0 += kSubRows) {
+        delta_rows(mel + (size_t)f0 * kMel, T, g0, min(gb, g0 + kSubRows), taps, s_mel,
+                   [&](int, int c, float v) { sum[c] += (double)v; sq[c] += (double)v * (double)v; });
+    }
+    for (int c = 0; c < 3; ++c) {
+        __syncthreads();
+        s_red[0][ty][x] = sum[c];
+        s_red[1][ty][x] = sq[c];
+        __syncthreads();
+        if (ty == 0) {
+            const double a = (s_red[0][0][x] + s_red[0][1][x]) + (s_red[0][2][x] + s_red[0][3][x]);
+            const double b = (s_red[1][0][x] + s_red[1][1][x]) + (s_red[1][2][x] + s_red[1][3][x]);
+            partial[((size_t)u * kStatChunks + ch) * kFeat + c * 240 + x] = make_double2(a, b);
+        }
+    }
+}
+
+// pass 2: recompute the taps from the staged log-mel rows, normalise, write the [L, 720] rows once
+__global__ void __launch_bounds__(960)
+feat_write_kernel(const float* __restrict__ mel, const int* __restrict__ frame_off,
+                  const int* __restrict__ featrow_off, Taps taps, int normalise,
+                  const double2* __restrict__ partial, const int* __restrict__ out_rowmap,
+                  float* __restrict__ out) {
+    __shared__ __align__(16) float s_mel[kSubFrames * kMel];
+    __shared__ float s_mean[kFeat], s_den[kFeat];
+    const int u = blockIdx.x;
+    const int x = threadIdx.x, ty = threadIdx.y;
     const int f0 = frame_off[u];
     const int T = frame_off[u + 1] - f0;
     const int r0 = featrow_off[u];
     const int L = featrow_off[u + 1] - r0;
-    const int col = c * 240 + x;
-    const float* tw = taps.w + c * 9;
-    const int i_lo = (c == 0) ? 4 : (c == 1 ? 2 : 0);
-    const int i_hi = (c == 0) ? 5 : (c == 1 ? 7 : 9);
-
-    // the 9-tap correlation is recomputed in the second pass (its log-mel input is L2-resident)
-    // instead of writing raw features and reading them back: the output is written exactly once
-    auto tap = [&](int g) {
-        const int t = 3 * g + j;
-        float acc = 0.f;
-        for (int i = i_lo; i < i_hi; ++i) {
-            const int tt = t + i - 4;
-            if (tt >= 0 && tt < T) acc = fmaf(tw[i], __ldg(mel + (size_t)(f0 + tt) * kMel + m), acc);
+    const int g0 = blockIdx.y * kSubRows;
+    if (g0 >= L) return;
+    if (normalise && ty < 3) {
+        // (x - mean) / (std + 1e-6) per column with the unbiased std (main.py:37)
+        const int col = ty * 240 + x;
+        double tsum = 0.0, tsq = 0.0;
+        for (int ch = 0; ch < kStatChunks; ++ch) {
+            const double2 p = partial[((size_t)u * kStatChunks + ch) * kFeat + col];
+            tsum += p.x;
+            tsq += p.y;
         }
-        return acc;
-    };
-    if (!normalise) {
-        for (int g = ty; g < L; g += 4) {
-            const int row = out_rowmap ? out_rowmap[r0 + g] : (r0 + g);
-            out[(size_t)row * kFeat + col] = tap(g);
-        }
-        return;
+        const double mean = tsum / (double)L;
+        double var = (tsq - tsum * mean) / (double)(L - 1);
+        if (var < 0.0) var = 0.0;
+        s_mean[col] = (float)mean;
+        s_den[col] = (float)sqrt(var) + 1e-6f;
     }
-    double sum = 0.0, sq = 0.0;
-    for (int g = ty; g < L; g += 4) {
-        const float acc = tap(g);
-        sum += (double)acc;
-        sq += (double)acc * (double)acc;
-    }
-    s_sum[ty][x] = sum;
-    s_sq[ty][x] = sq;
-    __syncthreads();
-    const double tsum = s_sum[0][x] + s_sum[1][x] + s_sum[2][x] + s_sum[3][x];
-    const double tsq = s_sq[0][x] + s_sq[1][x] + s_sq[2][x] + s_sq[3][x];
-    const double mean = tsum / (double)L;
-    double var = (tsq - tsum * mean) / (double)(L - 1);     // unbiased, torch.std default
-    if (var < 0.0) var = 0.0;
-    const float meanf = (float)mean;
-    const float denom = (float)sqrt(var) + 1e-6f;
-    for (int g = ty; g < L; g += 4) {
-        const int row = out_rowmap ? out_rowmap[r0 + g] : (r0 + g);
-        out[(size_t)row * kFeat + col] = (tap(g) - meanf) / denom;
-    }
+    // (delta_rows starts with a barrier: s_mean / s_den are visible before the first sink call)
+    delta_rows(mel + (size_t)f0 * kMel, T, g0, min(L, g0 + kSubRows), taps, s_mel,
+               [&](int g, int c, float v) {
+                   const int col = c * 240 + x;
+                   const int row = out_rowmap ? out_rowmap[r0 + g] : (r0 + g);
+                   out[(size_t)row * kFeat + col] = normalise ? (v - s_mean[col]) / s_den[col] : v;
+               });
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -248,7 +304,8 @@ int launch_logmel(asr_handle* h, const float* d_pcm, const long long* d_pcm_off,
                   const int* d_frame_off, int B, int total_frames, float* d_mel, cudaStream_t st) {
     if (total_frames <= 0) return ASR_OK;
     const FeatureConsts& c = h->fc;
-    const int grid = (total_frames + kFramesPerCta - 1) / kFramesPerCta;
+    const int per_cta = kFramesPerCta * kFrameRounds;
+    const int grid = (total_frames + per_cta - 1) / per_cta;
     logmel_kernel<<<grid, 256, 0, st>>>(d_pcm, d_pcm_off, d_frame_off, B, total_frames, c.window,
                                         c.tw256, c.tw512, c.mel_start, c.mel_len, c.mel_w,
                                         c.mel_maxw, c.preemph, d_mel);
@@ -258,13 +315,20 @@ int launch_logmel(asr_handle* h, const float* d_pcm, const long long* d_pcm_off,
 }
 
 int launch_delta_cmvn(asr_handle* h, const float* d_mel, const int* d_frame_off,
-                      const int* d_featrow_off, int B, int normalise, const int* out_rowmap,
-                      float* d_out, cudaStream_t st) {
+                      const int* d_featrow_off, int B, int max_rows_per_utt, int normalise,
+                      const int* out_rowmap, float* d_out, cudaStream_t st) {
     Taps t;
     for (int i = 0; i < 27; ++i) t.w[i] = h->fc.taps[i];
-    dim3 grid(B, 3), block(240, 4);
-    delta_cmvn_kernel<<<grid, block, 0, st>>>(d_mel, d_frame_off, d_featrow_off, t, normalise,
-                                              out_rowmap, d_out);
+    dim3 block(240, 4);
+    if (normalise) {
+        feat_stats_kernel<<<dim3(B, kStatChunks), block, 0, st>>>(d_mel, d_frame_off, d_featrow_off, t,
+                                                                  reinterpret_cast<double2*>(h->ws.feat_partial));
+        ASR_CHECK_LAUNCH();
+        h->launches++;
+    }
+    feat_write_kernel<<<dim3(B, (max_rows_per_utt + kSubRows - 1) / kSubRows), block, 0, st>>>(
+        d_mel, d_frame_off, d_featrow_off, t, normalise, reinterpret_cast<const double2*>(h->ws.feat_partial),
+        out_rowmap, d_out);
     ASR_CHECK_LAUNCH();
     h->launches++;
     return ASR_OK;
