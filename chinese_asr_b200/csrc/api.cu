@@ -246,7 +246,7 @@ static int decoder_step(asr_handle* h, int k, int step, int cur, float temperatu
             A.nseg = 2;
             A.seg[0] = ASeg{w.dctx[cur], w.src_row, kEnc, kEnc};
             A.seg[1] = ASeg{w.dh[cur], w.src_row, kDecH, kProjK};
-            {
+            if (step == 0 || k == 1) {      // later beam steps: gathered by the bookkeeping kernel of the previous step
                 StageScope sc2(h, kStSplit, st);
                 ASR_TRY(split_operand(A, R, kProjK, w.a_hi, w.a_lo, w.ctrl, st, &h->launches));
             }

@@ -508,6 +508,10 @@ struct BookParams {
     int* tr_bp; int* tr_tok;                    // [max_len, B, k]
     int* top_done; int* ctrl;
     int B, k, K, step;
+    // optional: gather the next step's cell-GEMM operand [ctx[src] | h[src]] (already split, from the
+    // [h | ctx] rows the cell epilogue / attention kernel wrote) - replaces a gather + split launch
+    const float* split_hi; const float* split_lo;   // [R, 1024] = [h | ctx]
+    float* next_hi; float* next_lo;                 // [R, 1024] = [ctx | h]
 };
 
 struct RowTopkParams {
@@ -545,6 +549,7 @@ __device__ __forceinline__ float block_reduce_sum(float v, float* s_red) {
 // Merge of the k rows' top-K lists of utterance u and the beam bookkeeping of one step
 // (model.py:862-929).  Runs in the LAST row CTA of the utterance to publish its candidates.
 __device__ void beam_bookkeep(const BookParams& p, int u, float* s_s, int* s_f, float* s_cs, int* s_cf) {
+    __shared__ int s_src[kMaxBeam];
     const int tid = threadIdx.x;
     const int k = p.k, K = p.K, R = p.B * k;
     const int nrow = p.step == 0 ? 1 : k;
@@ -591,6 +596,7 @@ __device__ void beam_bookkeep(const BookParams& p, int u, float* s_s, int* s_f, 
         const int i = __popc(live & ((1u << j) - 1u));
         if (valid && !eos && i < k) {
             const int r = u * k + i;
+            s_src[i] = u * k + beam;
             p.src_row[r] = u * k + beam;
             p.beam_score[r] = s_cs[j];
             p.tok_hist[(size_t)(p.step + 1) * R + r] = tok;
@@ -612,6 +618,18 @@ __device__ void beam_bookkeep(const BookParams& p, int u, float* s_s, int* s_f, 
                 p.ctrl[3] = p.step + 1;
                 if (all) p.ctrl[0] = p.step;
             }
+        }
+    }
+    if (p.next_hi) {
+        __syncthreads();
+        // k rows x 1024 floats x (hi, cross): 16-byte copies, halves swapped ([h | ctx] -> [ctx | h])
+        const int per_row = kProjK / 4;                      // float4 per row
+        for (int idx = tid; idx < k * per_row; idx += 256) {
+            const int i = idx / per_row, c4 = idx - i * per_row;
+            const int s4 = c4 < kEnc / 4 ? c4 + kDecH / 4 : c4 - kEnc / 4;
+            const size_t so = (size_t)s_src[i] * kProjK + 4 * s4, d = (size_t)(u * k + i) * kProjK + 4 * c4;
+            *reinterpret_cast<float4*>(p.next_hi + d) = __ldcg(reinterpret_cast<const float4*>(p.split_hi + so));
+            *reinterpret_cast<float4*>(p.next_lo + d) = __ldcg(reinterpret_cast<const float4*>(p.split_lo + so));
         }
     }
 }
@@ -774,7 +792,8 @@ int launch_row_topk(asr_handle* h, int k, int step, cudaStream_t st) {
     float* bs_nxt = w.beam_score;
     BookParams b{w.rowcand_s, w.rowcand_t, bs_nxt, w.src_row, w.tok_hist, w.prev_hist,
                  w.fin_score, w.fin_row, w.tr_cand_s, w.tr_cand_b, w.tr_cand_t, w.tr_bp, w.tr_tok,
-                 w.top_done, w.ctrl, h->meta.B, k, 2 * k, step};
+                 w.top_done, w.ctrl, h->meta.B, k, 2 * k, step,
+                 h->fused_dec ? w.dec_split_hi : nullptr, w.dec_split_lo, h->fused_dec ? w.a_hi : nullptr, w.a_lo};
     static const int fuse = getenv("ASR_B200_FUSE_BOOK") ? atoi(getenv("ASR_B200_FUSE_BOOK")) : 0;
     RowTopkParams p{w.logits, bs_cur, w.rowcand_s, w.rowcand_t, w.row_ticket, w.ctrl, k, 2 * k, step, fuse, b};
     row_topk_kernel<<<h->meta.B * k, 256, 0, st>>>(p);
