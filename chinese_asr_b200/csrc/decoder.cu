@@ -428,6 +428,328 @@ attention_kernel(AttnParams p) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Streaming (single pass) attention: the two-phase kernel above runs its MUFU-bound score phase and its
+// HBM-bound context phase one after the other, and since every CTA of the grid starts at the same time
+// the whole GPU alternates between the two limits.  Here warps 0-3 of a CTA produce softmax numerators
+// chunk by chunk (64 frames) while warps 4-7 stream the encoder rows of the previous chunk, so both
+// limits are worked on at once.  Softmax is "online": numerators are taken against the running
+// maximum M and the accumulators are rescaled by exp(M_old - M_new) when a chunk raises it
+// (same value as softmax-then-sum up to fp32 rounding of the rescale factors).
+// Hand-off through named barriers: full[b] (producers arrive, consumers sync), empty[b] (the reverse).
+constexpr int kAttChunk = 64;
+
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int count) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void att_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void att_mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void att_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void att_mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    unsigned spins = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_addr(bar)), "r"(parity)
+            : "memory");
+        if (!done && ++spins > (1u << 28)) __trap();
+    }
+}
+// contiguous global -> shared bulk copy (TMA engine, no registers), completion on an mbarrier
+__device__ __forceinline__ void att_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+
+constexpr int kAttRows = 8;        // encoder rows per ring stage (16 KB)
+constexpr int kAttStages = 3;
+
+template <int K>
+__global__ void __launch_bounds__(256, K <= 8 ? 4 : 2)
+attention_stream_kernel(AttnParams p) {
+    if (p.ctrl[0] >= 0) return;
+    constexpr int C = kAttChunk;
+    constexpr int kGroup = 32 / K;                 // lanes that end up holding the same beam
+    constexpr int FPW = C / 4;                     // frames per producer warp per chunk
+    extern __shared__ __align__(128) uint8_t att_smem[];
+    // ring of encoder rows | numerators (aliased by the queries during the prologue) | small state
+    float* s_ring = reinterpret_cast<float*>(att_smem);                          // [stages][8][512]
+    float* s_p = s_ring + kAttStages * kAttRows * kEnc;                           // [2][K][C]
+    float* s_q = s_p;                                                             // [K][128] (prologue only)
+    float* s_scale = s_p + 2 * K * C;                                             // [2][K]
+    float* s_wmax = s_scale + 2 * K;                                              // [2][4][K]
+    float* s_wsum = s_wmax + 2 * 4 * K;                                           // [4][K]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_wsum + 4 * K);                 // full[stages], empty[stages]
+    static_assert(2 * C >= kAtt, "queries alias the numerator buffers");
+
+    const int u = blockIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int k = p.k;
+    const int row0 = p.uoff[u];
+    const int nl = p.uoff[u + 1] - row0;
+    const int nchunk = (nl + C - 1) / C;
+    const int nstage = (nl + kAttRows - 1) / kAttRows;
+    uint64_t* full_e = bars;
+    uint64_t* empty_e = bars + kAttStages;
+
+    bool q_big = false;
+    for (int i = tid; i < k * kAtt; i += 256) {
+        const float qv = p.q[(size_t)u * k * kAtt + i];
+        s_q[i] = qv;
+        q_big |= !(fabsf(qv * kAttScale) <= kAttRange);
+    }
+    if (tid == 0) {
+        for (int i = 0; i < kAttStages; ++i) { att_mbar_init(&full_e[i], 1); att_mbar_init(&empty_e[i], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    const bool product_form = !__syncthreads_or(q_big) && p.keys_big[u] == 0;
+
+    if (warp < 4) {
+        // ---------------- producers: scores -> numerators ------------------------------------------
+        const float4 v4 = *reinterpret_cast<const float4*>(p.v + 4 * lane);
+        const float vsum = (v4.x + v4.y) + (v4.z + v4.w);
+        float4 q4[K];
+#pragma unroll
+        for (int kb = 0; kb < K; ++kb) {
+            q4[kb] = kb < k ? *reinterpret_cast<const float4*>(s_q + kb * kAtt + 4 * lane)
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+            q4[kb].x *= kAttScale; q4[kb].y *= kAttScale; q4[kb].z *= kAttScale; q4[kb].w *= kAttScale;
+            if (product_form) {
+                q4[kb].x = exp2f(q4[kb].x); q4[kb].y = exp2f(q4[kb].y);
+                q4[kb].z = exp2f(q4[kb].z); q4[kb].w = exp2f(q4[kb].w);
+            }
+        }
+        const float* kbase = product_form ? p.keys_exp : p.keys;
+        const int my_kb = lane / kGroup;
+        const bool leader = (lane % kGroup) == 0 && my_kb < k;
+        float run_max = -CUDART_INF_F, run_sum = 0.f;      // leader lanes: state of beam my_kb
+        for (int c = 0; c < nchunk; ++c) {
+            const int buf = c & 1;
+            const int c0 = c * C;
+            float* pb = s_p + (buf * K + my_kb) * C;       // this lane's beam row of the chunk
+            // the first barrier of chunk 0 also orders every producer's query reads before the
+            // numerator stores that overwrite them
+            named_bar_sync(c >= 2 ? 3 + buf : 5, c >= 2 ? 256 : 128);     // buffer drained by the consumers
+            float cmax = -CUDART_INF_F;
+            // the key row of the next frame is in flight while one frame is evaluated
+            auto load_key = [&](int f) {
+                const int l = min(c0 + warp + 4 * f, nl - 1);
+                return __ldg(reinterpret_cast<const float4*>(kbase + (size_t)(row0 + l) * kAtt) + lane);
+            };
+            float4 key_n1 = load_key(0);
+#pragma unroll 1
+            for (int f = 0; f < FPW; ++f) {
+                const int l = c0 + warp + 4 * f;
+                float ev = -CUDART_INF_F;
+                float4 key = key_n1;
+                if (f + 1 < FPW) key_n1 = load_key(f + 1);
+                if (l < nl) {                              // warp-uniform
+                    float e[K];
+                    if (product_form) {
+                        if (K >= 2) {
+                            // two beams per packed FFMA2: d = key * q + 1, then t += v * rcp(d)
+#pragma unroll
+                            for (int kb = 0; kb < K; kb += 2) {
+                                const int k1 = kb + 1 < K ? kb + 1 : kb;
+                                const float2 one = make_float2(1.f, 1.f);
+                                const float2 dx = __ffma2_rn(make_float2(key.x, key.x), make_float2(q4[kb].x, q4[k1].x), one);
+                                const float2 dy = __ffma2_rn(make_float2(key.y, key.y), make_float2(q4[kb].y, q4[k1].y), one);
+                                const float2 dz = __ffma2_rn(make_float2(key.z, key.z), make_float2(q4[kb].z, q4[k1].z), one);
+                                const float2 dw = __ffma2_rn(make_float2(key.w, key.w), make_float2(q4[kb].w, q4[k1].w), one);
+                                float2 t = __fmul2_rn(make_float2(v4.x, v4.x), make_float2(rcp_approx(dx.x), rcp_approx(dx.y)));
+                                t = __ffma2_rn(make_float2(v4.y, v4.y), make_float2(rcp_approx(dy.x), rcp_approx(dy.y)), t);
+                                t = __ffma2_rn(make_float2(v4.z, v4.z), make_float2(rcp_approx(dz.x), rcp_approx(dz.y)), t);
+                                t = __ffma2_rn(make_float2(v4.w, v4.w), make_float2(rcp_approx(dw.x), rcp_approx(dw.y)), t);
+                                const float2 ee = __ffma2_rn(make_float2(-2.f, -2.f), t, make_float2(vsum, vsum));
+                                e[kb] = ee.x;
+                                e[k1] = ee.y;
+                            }
+                        } else {
+                            float t = v4.x * rcp_approx(fmaf(key.x, q4[0].x, 1.f));
+                            t = fmaf(v4.y, rcp_approx(fmaf(key.y, q4[0].y, 1.f)), t);
+                            t = fmaf(v4.z, rcp_approx(fmaf(key.z, q4[0].z, 1.f)), t);
+                            t = fmaf(v4.w, rcp_approx(fmaf(key.w, q4[0].w, 1.f)), t);
+                            e[0] = fmaf(-2.f, t, vsum);
+                        }
+                    } else {
+                        key.x *= kAttScale; key.y *= kAttScale; key.z *= kAttScale; key.w *= kAttScale;
+#pragma unroll
+                        for (int kb = 0; kb < K; ++kb) {
+                            float t = v4.x * rcp1p_ex2(key.x + q4[kb].x);
+                            t = fmaf(v4.y, rcp1p_ex2(key.y + q4[kb].y), t);
+                            t = fmaf(v4.z, rcp1p_ex2(key.z + q4[kb].z), t);
+                            t = fmaf(v4.w, rcp1p_ex2(key.w + q4[kb].w), t);
+                            e[kb] = fmaf(-2.f, t, vsum);
+                        }
+                    }
+                    int off = 16;
+#pragma unroll
+                    for (int n = K; n > 1; n >>= 1) {
+                        const int half = n >> 1;
+                        const bool up = (lane & off) != 0;
+#pragma unroll
+                        for (int j = 0; j < half; ++j) {
+                            const float send = up ? e[j] : e[j + half];
+                            const float keep = up ? e[j + half] : e[j];
+                            e[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                        }
+                        off >>= 1;
+                    }
+                    for (; off > 0; off >>= 1) e[0] += __shfl_xor_sync(0xffffffffu, e[0], off);
+                    ev = e[0];
+                }
+                if (leader) pb[warp + 4 * f] = ev;         // raw score, turned into a numerator below
+                cmax = fmaxf(cmax, ev);
+            }
+            if (leader) s_wmax[(buf * 4 + warp) * K + my_kb] = cmax;
+            named_bar_sync(5, 128);                        // chunk maxima of the 4 producer warps
+            if (leader) {
+                const float* wm = s_wmax + buf * 4 * K + my_kb;
+                const float new_max = fmaxf(run_max, fmaxf(fmaxf(wm[0], wm[K]), fmaxf(wm[2 * K], wm[3 * K])));
+                const float scale = __expf(run_max - new_max);     // first chunk: exp(-inf) = 0 (accumulators are 0)
+                run_max = new_max;
+                float csum = 0.f;
+#pragma unroll
+                for (int f = 0; f < FPW; ++f) {
+                    const float pe = __expf(pb[warp + 4 * f] - run_max);      // frames past the end: exp(-inf) = 0
+                    pb[warp + 4 * f] = pe;
+                    csum += pe;
+                }
+                run_sum = fmaf(run_sum, scale, csum);
+                if (warp == 0) s_scale[buf * K + my_kb] = scale;
+            }
+            __threadfence_block();
+            named_bar_arrive(1 + buf, 256);
+        }
+        if (leader) s_wsum[warp * K + my_kb] = run_sum;
+    } else {
+        // ---------------- consumers: context accumulation -------------------------------------------
+        const int cg4 = tid - 128;                         // 4 of the 512 encoder columns
+        float2 a01[K], a23[K];
+#pragma unroll
+        for (int kb = 0; kb < K; ++kb) { a01[kb] = make_float2(0.f, 0.f); a23[kb] = a01[kb]; }
+        const float* enc_u = p.enc + (size_t)row0 * kEnc;
+        auto issue = [&](int st) {                         // rows [8 st, 8 st + 8) of the utterance -> ring slot
+            const int slot = st % kAttStages;
+            const int rows = min(kAttRows, nl - st * kAttRows);
+            const uint32_t bytes = (uint32_t)rows * kEnc * 4u;
+            att_mbar_expect_tx(&full_e[slot], bytes);
+            att_bulk_g2s(s_ring + slot * kAttRows * kEnc, enc_u + (size_t)st * kAttRows * kEnc, bytes, &full_e[slot]);
+        };
+        if (tid == 128) for (int st = 0; st < min(kAttStages, nstage); ++st) issue(st);
+        for (int st = 0; st < nstage; ++st) {
+            const int slot = st % kAttStages;
+            const int l0 = st * kAttRows;
+            const int buf = (l0 / C) & 1;
+            const int lc = l0 % C;
+            if (lc == 0) {
+                named_bar_sync(1 + buf, 256);              // this chunk's numerators are ready
+#pragma unroll
+                for (int kb = 0; kb < K; ++kb) {
+                    if (kb < k) {
+                        const float sc = s_scale[buf * K + kb];
+                        a01[kb].x *= sc; a01[kb].y *= sc; a23[kb].x *= sc; a23[kb].y *= sc;
+                    }
+                }
+            }
+            att_mbar_wait(&full_e[slot], (uint32_t)((st / kAttStages) & 1));
+            const int rows = min(kAttRows, nl - l0);
+            const float4* er = reinterpret_cast<const float4*>(s_ring + slot * kAttRows * kEnc) + cg4;
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {               // 4 rows at a time: 16 registers of encoder data
+                float4 e[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    e[i] = 4 * hf + i < rows ? er[(4 * hf + i) * (kEnc / 4)] : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (hf == 1) {
+                    __syncwarp();
+                    if (lane == 0) att_mbar_arrive(&empty_e[slot]);    // this warp has read the slot
+                }
+#pragma unroll
+                for (int kb = 0; kb < K; ++kb) {
+                    if (kb < k) {
+                        const float4 w4 = *reinterpret_cast<const float4*>(s_p + (buf * K + kb) * C + lc + 4 * hf);
+                        const float w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            a01[kb] = __ffma2_rn(make_float2(w[i], w[i]), make_float2(e[i].x, e[i].y), a01[kb]);
+                            a23[kb] = __ffma2_rn(make_float2(w[i], w[i]), make_float2(e[i].z, e[i].w), a23[kb]);
+                        }
+                    }
+                }
+            }
+            if (lc + kAttRows == C || st + 1 == nstage) {              // last stage of the chunk
+                const int c = l0 / C;
+                if (c + 2 < nchunk) named_bar_arrive(3 + buf, 256);
+            }
+            if (tid == 128 && st + kAttStages < nstage) {
+                att_mbar_wait(&empty_e[slot], (uint32_t)((st / kAttStages) & 1));   // all 4 warps have read it
+                issue(st + kAttStages);
+            }
+        }
+        __syncthreads();                                   // producers' sums
+#pragma unroll
+        for (int kb = 0; kb < K; ++kb) {
+            if (kb < k) {
+                const float inv = (s_wsum[kb] + s_wsum[K + kb]) + (s_wsum[2 * K + kb] + s_wsum[3 * K + kb]);
+                const float4 o = make_float4(a01[kb].x / inv, a01[kb].y / inv, a23[kb].x / inv, a23[kb].y / inv);
+                const int row = u * k + kb;
+                *reinterpret_cast<float4*>(p.ctx_out + (size_t)row * kEnc + 4 * cg4) = o;
+                if (p.split_hi) {
+                    // operand split of ctx for the vocabulary GEMM (gemm_tc.cu kSplitAct): this thread
+                    // owns half of an 8-float block
+                    uint32_t u0, u1, u2, u3;
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u0) : "f"(o.x));
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u1) : "f"(o.y));
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u2) : "f"(o.z));
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u3) : "f"(o.w));
+                    const float4 hi = make_float4(__uint_as_float(u0), __uint_as_float(u1), __uint_as_float(u2), __uint_as_float(u3));
+                    *reinterpret_cast<float4*>(p.split_hi + (size_t)row * p.split_ld + kDecH + 4 * cg4) = hi;
+                    uint2 lo2, xx2;
+                    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo2.x) : "f"(o.y - hi.y), "f"(o.x - hi.x));
+                    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo2.y) : "f"(o.w - hi.w), "f"(o.z - hi.z));
+                    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(xx2.x) : "f"(o.y), "f"(o.x));
+                    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(xx2.y) : "f"(o.w), "f"(o.z));
+                    uint32_t* blk = reinterpret_cast<uint32_t*>(p.split_lo + (size_t)row * p.split_ld + kDecH) + (cg4 >> 1) * 8;
+                    *reinterpret_cast<uint2*>(blk + 2 * (cg4 & 1)) = lo2;
+                    *reinterpret_cast<uint2*>(blk + 4 + 2 * (cg4 & 1)) = xx2;
+                }
+            }
+        }
+        return;
+    }
+    __syncthreads();                                       // matches the consumers' barrier above
+}
+
+template <int K>
+static int launch_attention_stream(const AttnParams& p, int B, cudaStream_t st) {
+    const size_t smem = sizeof(float) * ((size_t)kAttStages * kAttRows * kEnc + 2 * K * kAttChunk + 2 * K + 8 * K + 4 * K) +
+                        sizeof(uint64_t) * 2 * kAttStages + 16;
+    static bool attr = false;
+    if (!attr) {
+        ASR_CUDA(cudaFuncSetAttribute(attention_stream_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    attention_stream_kernel<K><<<B, 256, smem, st>>>(p);
+    return ASR_OK;
+}
+
 int launch_attention(asr_handle* h, int k, int step, int nxt, float* d_align_step, cudaStream_t st) {
     (void)step;
     Workspace& w = h->ws;
@@ -463,6 +785,18 @@ int launch_attention(asr_handle* h, int k, int step, int nxt, float* d_align_ste
     p.align_out = d_align_step;
     p.raw_score = (d_align_step && S > 1) ? w.att_score : nullptr;
     const int K = k == 1 ? 1 : (k <= 4 ? 4 : (k <= 8 ? 8 : 16));
+    static const bool stream_env = !(getenv("ASR_B200_ATT_STREAM") && atoi(getenv("ASR_B200_ATT_STREAM")) == 0);
+    if (stream_env && S == 1 && !d_align_step) {
+        switch (K) {
+            case 1: ASR_TRY(launch_attention_stream<1>(p, m.B, st)); break;
+            case 4: ASR_TRY(launch_attention_stream<4>(p, m.B, st)); break;
+            case 8: ASR_TRY(launch_attention_stream<8>(p, m.B, st)); break;
+            default: ASR_TRY(launch_attention_stream<16>(p, m.B, st)); break;
+        }
+        ASR_CHECK_LAUNCH();
+        h->launches++;
+        return ASR_OK;
+    }
     const size_t smem = sizeof(float) * ((size_t)K * kAtt + (size_t)K * p.sc_ld + (size_t)K * kEnc);
     dim3 grid(m.B, S);
 #define ASR_LAUNCH_ATT(KK)                                                                      \
