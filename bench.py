@@ -38,7 +38,7 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=512, help="utterances per GPU per step")
     ap.add_argument("--bw", type=int, default=8)
     ap.add_argument("--seconds", type=float, default=SECONDS)
-    ap.add_argument("--cpu-sample", type=int, default=16, help="utterances in the CPU baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=64, help="utterances per batch of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -258,16 +258,21 @@ def run_native(args):
     R = B * k
     n_gemm = 4 + 1 + 3 * MAX_LEN
     kernel_ms = dict(stages)
-    kernel_ms["gemm_tf32x3_kernel (all GEMM stages)"] = gemm_ms
-    dom = max(("gemm_tf32x3_kernel (all GEMM stages)", "enc_recurrence", "attention", "topk_bookkeep", "features"),
+    kernel_ms["gemm engine (all GEMM stages)"] = gemm_ms
+    dom = max(("gemm engine (all GEMM stages)", "enc_recurrence", "attention", "topk_bookkeep", "features"),
               key=lambda kk: kernel_ms[kk])
     if dom.startswith("gemm"):
         ach = gemm_gflop / gemm_ms                        # GFLOP / ms = TFLOP/s (algorithmic fp32 2*M*N*K)
-        roof = {"kernel": "tc::gemm_tf32x3_kernel", "bound": "tensor", "achieved": ach, "peak": tf_peak,
-                "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": None,
-                "peak_source": peak_src + " cuBLAS bf16 sustained; the kernel executes 3 tf32 MMAs per fp32 product "
-                               "(3xTF32), i.e. 6x the bf16 tensor-pipe time per algorithmic FLOP",
-                "executed_tf32_tflops": 3.0 * ach, "algorithmic_gflop_per_step": gemm_gflop,
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the 125 launches of a pass
+        # (4 encoder projections 8.59 GB, keys 0.77 GB, 40 x (vocabulary 166 MB + cell 65 MB + query 17 MB)):
+        # profiles/r01_kernels.csv, one `ncu --set full` capture of this workload
+        traffic = 19.33e9 / 125 if (B, k, L) == (512, 8, 332) else None
+        roof = {"kernel": "tc::gemm_tf32x3_persistent_kernel", "bound": "tensor", "achieved": ach, "peak": tf_peak,
+                "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": traffic,
+                "peak_source": peak_src + " cuBLAS bf16 sustained.  Per fp32 product the kernel issues one tf32 MMA "
+                               "(a_hi*w_hi) and one bf16 MMA over 2K (a_lo*w + a*w_lo): 4x the bf16 tensor-pipe time "
+                               "per algorithmic FLOP, so tensor_pipe_frac = 4 * frac is the share of the pipe's peak",
+                "tensor_pipe_frac": 4.0 * ach / tf_peak, "algorithmic_gflop_per_step": gemm_gflop,
                 "ms_per_launch": gemm_ms / n_gemm, "launches_per_step": n_gemm, "ms_per_step": gemm_ms}
     elif dom == "enc_recurrence":
         fl = 2.0 * B * L * 4 * 2 * 1024 * 256
@@ -297,10 +302,10 @@ def run_native(args):
 
     cpu = None
     if not args.no_cpu_baseline:
-        rate, dt, threads = cpu_port_rate(args.cpu_sample, k, args.seconds)
+        rate, dt, threads = cpu_port_rate(args.cpu_sample, k, args.seconds, reps=3)
         cpu = {"value": rate, "unit": "utt/s", "cores": threads, "kind": "port", "host_cpus": os.cpu_count(),
-               "sample": f"{args.cpu_sample} utterances x {args.seconds:g} s, one batch, features+encoder+beam "
-                         f"bw={k}, {dt:.1f} s wall"}
+               "sample": f"3 batches of {args.cpu_sample} utterances x {args.seconds:g} s, features+encoder+beam "
+                         f"bw={k}, best batch {dt:.1f} s wall"}
     line = {
         "metric": "utterances_per_sec_beam8", "value": value, "unit": "utt/s", "rtfx": value * args.seconds,
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,

@@ -280,6 +280,36 @@ def check_batch_invariance(B=12, k=4, seconds=3.0, seed=900):
     return {"single_eq_batch": same, "of": 3, "perm_invariant": perm_ok}
 
 
+def check_attention_range(which, scale=400.0, k=4):
+    """Attention pre-activations outside the product form's range (|x| > 20.8): scaling W_enc makes
+    the keys large (flagged per utterance by keys_exp_kernel), scaling W_hidden the queries (flagged
+    per step); both must fall back to the exact sum-then-exp scores and still match the oracle."""
+    weights = O.make_weights(1234, "sharp", eos_bias=8.0)
+    name = {"keys": "attn_mechanism.W_enc", "queries": "attn_mechanism.W_hidden"}[which]
+    weights["decoder_state_dict"][name] = weights["decoder_state_dict"][name] * scale
+    m = get_model((1234, "sharp", 8.0, which, scale), weights)
+    _, i2w = vocab()
+    pcms = [O.synth_pcm(5100 + i, n) for i, n in enumerate((40000, 33000, 26000))]
+    feats = [O.features(p) for p in pcms]
+    lens = torch.tensor([f.size(0) for f in feats])
+    enc = O.encoder_forward(weights, feats, lens)
+    tr = {}
+    o = O.beam_decode(weights, k, feats, lens, i2w, trace=tr)
+    out = m.eval_one_batch_with_beam(m.device, k, feats, lens, None, i2w, second_pass=False)
+    og = O.greedy_decode(weights, feats, lens, i2w)
+    gr = m.eval_one_batch_with_greedy(m.device, feats, lens, i2w, None)
+    off = np.zeros(len(pcms) + 1, dtype=np.int64)
+    off[1:] = np.cumsum([len(p) for p in pcms])
+    tok, ln, sc, texts = m.transcribe(np.concatenate(pcms), off, bw=None, int2word=i2w)
+    keys = O.attention_keys(weights, enc[0] if isinstance(enc, tuple) else enc)
+    return {"beam_tokens_vs_oracle": int(m.last_beam_info["tokens"] == o["tokens"]),
+            "beam_score_rel": float(max(abs(a - b) / max(1e-6, abs(b)) for a, b in zip(out.score, o["score"]))),
+            "greedy_text_vs_oracle": int(list(gr.pred_text) == og["pred_text"]),
+            "stream_greedy_text_vs_oracle": int(texts == og["pred_text"]),
+            "max_abs_key": float(torch.as_tensor(keys).abs().max()),
+            "oracle_min_margin": float(min(tr["min_margin"]))}
+
+
 def check_graph_replay(B=6, k=4, n=40000, seed=700):
     """The beam loop is replayed from a CUDA graph once a batch shape repeats (eager, capture,
     replay on calls 1-3).  Batches with the same shape but different audio must give exactly what

@@ -107,6 +107,15 @@ def test_batch_invariance(G):
     assert r["single_eq_batch"] == r["of"] and r["perm_invariant"] == 1
 
 
+@pytest.mark.parametrize("which", ["keys", "queries"])
+def test_attention_out_of_range_falls_back_to_exact_scores(G, which):
+    r = G.check_attention_range(which)
+    if which == "keys":
+        assert r["max_abs_key"] > 21.0, r          # the case really is outside the product form's range
+    assert r["beam_tokens_vs_oracle"] == 1 and r["greedy_text_vs_oracle"] == 1, r
+    assert r["stream_greedy_text_vs_oracle"] == 1 and r["beam_score_rel"] <= SCORE_RTOL, r
+
+
 def test_graph_replay_equals_eager_loop(G):
     r = G.check_graph_replay()
     assert r["replay_eq_eager"] == r["of"] and r["batches_differ"] == 1, r

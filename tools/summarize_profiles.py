@@ -45,9 +45,10 @@ def launches():
         a[1] += v
     tot = sum(v[1] for v in agg.values())
     with open(os.path.join(out_dir, f"{tag}_launches.md"), "w") as f:
-        f.write(f"# ncu launch list, {tag}: `python tools/prof_step.py 512 8 0` (one pass of the hot path,\n"
-                "# 512 x 10 s utterances, bw=8), `--metrics gpu__time_duration.sum --clock-control none`.\n"
-                "# Per-launch times are cold-cache and serialised: compare SHARES with bench.py's stage_ms.\n\n")
+        f.write(f"# ncu launch list, {tag}: `python bench.py --steps 2 --warmup 1 --no-cpu-baseline` (512 x 10 s\n"
+                "# utterances per pass, bw=8; 3 device-resident passes, 3 end-to-end passes, 1 stage-timed pass),\n"
+                "# `ncu --metrics gpu__time_duration.sum --clock-control none -c 4000` after the same command exited 0\n"
+                "# without ncu.  Per-launch times are cold-cache and serialised: compare SHARES with stage_ms.\n\n")
         f.write("| kernel | launches | total ms | avg us | share |\n|---|---:|---:|---:|---:|\n")
         for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"| `{k}` | {v[0]} | {v[1] / 1e3:.2f} | {v[1] / v[0]:.1f} | {100 * v[1] / tot:.1f}% |\n")
@@ -57,8 +58,13 @@ def launches():
 
 def kernels():
     rows_out = []
-    for rep in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", f"prof_{tag}_*.ncu-rep"))):
-        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    reps = sorted(glob.glob(os.path.join(ROOT, "gpurun_out", f"prof_{tag}_*.ncu-rep")))
+    raws = sorted(glob.glob(os.path.join(ROOT, "gpurun_out", f"prof_{tag}_*_raw.csv")))   # exported on the GPU box
+    for rep in reps + raws:
+        if rep.endswith(".csv"):
+            raw = open(rep).read()
+        else:
+            raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(io.StringIO(raw)))
         if len(rows) < 3:
             continue
