@@ -74,6 +74,7 @@ SIGNATURES = {
     "asr_set_gemm_mode": (C.c_int, [C.c_void_p, C.c_int]),
     "asr_test_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                 C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "asr_prefetch_pcm": (C.c_int, [C.c_void_p, C.c_void_p, c_int64_p, C.c_int]),
     "asr_bench_gemm": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_float_p, C.c_void_p]),
     "asr_launch_count": (C.c_int64, [C.c_void_p, C.c_int]),
     "asr_stage_timing": (C.c_int, [C.c_void_p, C.c_int]),

@@ -710,6 +710,7 @@ int asr_destroy(asr_handle* h) {
     cudaDeviceSynchronize();
     if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
     if (h->graph_stream) cudaStreamDestroy(h->graph_stream);
+    if (h->copy_stream) { cudaStreamDestroy(h->copy_stream); cudaEventDestroy(h->pre_ev[0]); cudaEventDestroy(h->pre_ev[1]); }
     for (void* p : h->weight_allocs) cudaFree(p);
     for (void* p : h->ws.allocs) cudaFree(p);
     if (h->ws.h_stage) cudaFreeHost(h->ws.h_stage);
@@ -731,6 +732,8 @@ int asr_reserve(asr_handle* h, int max_utts, int64_t max_rows, int max_beam, int
     if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }   // captured pointers are stale
     memset(h->graph_key, 0, sizeof(h->graph_key));
     memset(h->graph_seen, 0, sizeof(h->graph_seen));
+    w.pcm_pre[0] = w.pcm_pre[1] = nullptr;       // freed with the pool above
+    h->pre_src[0] = h->pre_src[1] = nullptr;
     if (w.h_stage) { cudaFreeHost(w.h_stage); w.h_stage = nullptr; }
     w.max_utts = max_utts; w.max_rows = max_rows; w.max_beam = max_beam; w.max_len = max_len;
     w.max_samples = max_samples;
@@ -961,6 +964,8 @@ int asr_beam_trace(asr_handle* h, float* h_cand_score, int32_t* h_cand_beam, int
     return ASR_OK;
 }
 
+static int issue_prefetch(asr_handle* h, int slot);
+
 int asr_transcribe_device(asr_handle* h, const float* d_pcm, const int64_t* h_pcm_off, int B, int k, int max_len,
                           float temperature, int second_pass, double lm_weight, double length_weight,
                           int32_t* h_tokens, int32_t* h_len, float* h_score, void* stream) {
@@ -968,6 +973,7 @@ int asr_transcribe_device(asr_handle* h, const float* d_pcm, const int64_t* h_pc
     cudaStream_t st = (cudaStream_t)stream;
     std::vector<int32_t> L(B);
     ASR_TRY(features_device(h, d_pcm, h_pcm_off, B, L.data(), 1, true, h->ws.xpack, st));
+    for (int sl = 0; sl < 2; ++sl) ASR_TRY(issue_prefetch(h, sl));     // next batch's PCM copy overlaps this batch
     ASR_TRY(run_encoder(h, 3, st));
     ASR_TRY(run_keys(h, st));
     h->encoded = true;
@@ -979,6 +985,41 @@ int asr_transcribe_device(asr_handle* h, const float* d_pcm, const int64_t* h_pc
     return fetch_results(h, B, max_len, h_tokens, h_len, h_score, nullptr, st);
 }
 
+// Start the host->device copy of a batch's PCM on the handle's copy stream (double-buffered device
+// staging) so that it overlaps the decode of the batch before it; the asr_transcribe call for the same
+// host buffer then waits on the copy's event instead of copying.
+int asr_prefetch_pcm(asr_handle* h, const float* h_pcm, const int64_t* h_pcm_off, int B) {
+    if (!h || !h_pcm || !h_pcm_off || B <= 0) { set_error("asr_prefetch_pcm: bad argument"); return ASR_ERR_ARG; }
+    Workspace& w = h->ws;
+    const int64_t n = h_pcm_off[B] - h_pcm_off[0];
+    if (!w.pcm || n > w.max_samples) { set_error("batch has more samples than reserved"); return ASR_ERR_CAPACITY; }
+    if (!h->copy_stream) {
+        ASR_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) ASR_CUDA(cudaEventCreateWithFlags(&h->pre_ev[i], cudaEventDisableTiming));
+    }
+    const int slot = (int)(h->pre_count++ & 1);
+    if (!w.pcm_pre[slot]) {
+        ASR_CUDA(cudaMalloc(&w.pcm_pre[slot], sizeof(float) * (size_t)w.max_samples));
+        w.allocs.push_back(w.pcm_pre[slot]);
+    }
+    // The copy itself is issued by the next asr_transcribe call AFTER its own small metadata uploads:
+    // copy engines are FIFO, and a 300 MB copy queued first would hold those (synchronous) uploads - and
+    // with them the whole batch - back by its full duration (measured: no overlap gain at all).
+    h->pre_src[slot] = h_pcm + h_pcm_off[0];
+    h->pre_n[slot] = n;
+    h->pre_issued[slot] = false;
+    return ASR_OK;
+}
+
+static int issue_prefetch(asr_handle* h, int slot) {
+    if (!h->pre_src[slot] || h->pre_issued[slot]) return ASR_OK;
+    ASR_CUDA(cudaMemcpyAsync(h->ws.pcm_pre[slot], h->pre_src[slot], sizeof(float) * (size_t)h->pre_n[slot],
+                             cudaMemcpyHostToDevice, h->copy_stream));
+    ASR_CUDA(cudaEventRecord(h->pre_ev[slot], h->copy_stream));
+    h->pre_issued[slot] = true;
+    return ASR_OK;
+}
+
 int asr_transcribe(asr_handle* h, const float* h_pcm, const int64_t* h_pcm_off, int B, int k, int max_len,
                    float temperature, int second_pass, double lm_weight, double length_weight,
                    int32_t* h_tokens, int32_t* h_len, float* h_score, void* stream) {
@@ -986,10 +1027,26 @@ int asr_transcribe(asr_handle* h, const float* h_pcm, const int64_t* h_pcm_off, 
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t n = h_pcm_off[B] - h_pcm_off[0];
     if (n > h->ws.max_samples) { set_error("batch has more samples than reserved"); return ASR_ERR_CAPACITY; }
-    ASR_CUDA(cudaMemcpyAsync(h->ws.pcm, h_pcm + h_pcm_off[0], sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, st));
     std::vector<int64_t> off(B + 1);
     for (int i = 0; i <= B; ++i) off[i] = h_pcm_off[i] - h_pcm_off[0];
-    return asr_transcribe_device(h, h->ws.pcm, off.data(), B, k, max_len, temperature, second_pass, lm_weight,
+    const float* d_pcm = h->ws.pcm;
+    int hit = -1;
+    for (int sl = 0; sl < 2; ++sl) {          // oldest outstanding prefetch of this buffer first
+        const int c = (int)((h->pre_count + sl) & 1);
+        if (h->pre_src[c] == h_pcm + h_pcm_off[0] && h->pre_n[c] == n) { hit = c; break; }
+    }
+    static const bool dbg_pre = getenv("ASR_B200_PREFETCH_DBG") != nullptr;
+    if (dbg_pre) fprintf(stderr, "[prefetch] transcribe: %s (slot %d, event %s)\n", hit >= 0 ? "hit" : "miss", hit,
+                         hit >= 0 ? (cudaEventQuery(h->pre_ev[hit]) == cudaSuccess ? "done" : "pending") : "-");
+    if (hit >= 0) {
+        ASR_TRY(issue_prefetch(h, hit));          // not started yet if no batch ran since it was registered
+        ASR_CUDA(cudaStreamWaitEvent(st, h->pre_ev[hit], 0));
+        d_pcm = h->ws.pcm_pre[hit];
+        h->pre_src[hit] = nullptr;
+    } else {
+        ASR_CUDA(cudaMemcpyAsync(h->ws.pcm, h_pcm + h_pcm_off[0], sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, st));
+    }
+    return asr_transcribe_device(h, d_pcm, off.data(), B, k, max_len, temperature, second_pass, lm_weight,
                                  length_weight, h_tokens, h_len, h_score, stream);
 }
 

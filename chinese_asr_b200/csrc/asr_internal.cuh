@@ -211,6 +211,7 @@ struct Workspace {
     int64_t max_rows = 0, max_samples = 0, max_frames = 0;
     // features
     float* pcm = nullptr;        // [max_samples] staging for asr_transcribe
+    float* pcm_pre[2] = {};      // [max_samples] x 2, allocated on first asr_prefetch_pcm
     float* mel = nullptr;        // [max_frames, 80]
     float* xpack = nullptr;      // [max_rows, 720] packed time-major encoder input
     double* feat_partial = nullptr;  // [max_utts, 4, 720] (sum, sum of squares) partials of the CMVN statistics
@@ -294,6 +295,12 @@ struct asr_handle {
     long long graph_seen[8] = {};
     int64_t graph_launches = 0;             // kernels inside the captured graph
     cudaStream_t graph_stream = nullptr;    // blocking stream standing in for the legacy stream (not capturable)
+    cudaStream_t copy_stream = nullptr;     // asr_prefetch_pcm: H2D copies overlapping the previous batch
+    cudaEvent_t pre_ev[2] = {};
+    const float* pre_src[2] = {};           // host address a staged copy came from (nullptr = free / consumed)
+    int64_t pre_n[2] = {};
+    bool pre_issued[2] = {};                // the copy has been enqueued (it is issued behind the next batch's uploads)
+    uint64_t pre_count = 0;
     bool enc_split_ready = false;  // ws.a_hi / a_lo hold the split of `enc` (written by the last recurrence)
     bool fused_dec = false;     // decoder step with pre-multiplied embeddings and producer-side operand splits
     double gemm_flops = 0.0;     // algorithmic 2*M*N*K of every GEMM-engine launch since the last reset

@@ -380,6 +380,20 @@ class Model(object):
         return tokens, tlen, score
 
     # ---- GEMM engine ---------------------------------------------------------------------------------
+    def prefetch(self, pcm, offsets, bw=None):
+        """Start the host->device copy of a batch (pinned host tensor / numpy array) so that it
+        overlaps the decode of the previous batch; the next transcribe() call given the same buffer
+        and offsets uses the staged copy.  At most two batches may be in flight.  `bw` sizes the
+        workspace like the transcribe() call that follows (a later re-allocation would drop the copy)."""
+        self._need()
+        off = np.ascontiguousarray(offsets, dtype=np.int64)
+        B = off.shape[0] - 1
+        rows = int(sum(int(lib.asr_num_frames(int(off[i + 1] - off[i]))) for i in range(B)))
+        self.reserve(B, max(rows, 1), max(bw or 1, 1), int(off[-1] - off[0]))
+        ptr = pcm.data_ptr() if isinstance(pcm, torch.Tensor) else pcm.ctypes.data
+        self._keep_prefetch = (pcm, off)           # the copy is asynchronous: keep the host buffer alive
+        check(lib.asr_prefetch_pcm(self._h, C.c_void_p(ptr), off.ctypes.data_as(_cabi.c_int64_p), B), "asr_prefetch_pcm")
+
     def set_gemm_mode(self, mode):
         """'simt' (CUDA-core fp32), 'tc' (GEMM stages on tcgen05 3xTF32), 'rec' (only the encoder
         recurrence on tcgen05) or 'tc+rec' (both)."""

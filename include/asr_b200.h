@@ -165,6 +165,12 @@ int asr_transcribe(asr_handle* h, const float* h_pcm, const int64_t* h_pcm_off, 
                    int max_len, float temperature, int second_pass, double lm_weight,
                    double length_weight, int32_t* h_tokens, int32_t* h_len, float* h_score,
                    void* stream);
+/* Pipelining aid for servers: starts the host->device copy of a batch's PCM (pinned host memory) on
+ * the handle's own copy stream, so it overlaps the decode of the previous batch.  The next
+ * asr_transcribe call given the same h_pcm / offsets consumes the prefetched copy (it waits on the
+ * copy's event instead of copying).  At most two prefetches may be outstanding. */
+int asr_prefetch_pcm(asr_handle* h, const float* h_pcm, const int64_t* h_pcm_off, int B);
+
 /* Same, PCM already resident on the device (d_pcm); used for the HBM-resident throughput. */
 int asr_transcribe_device(asr_handle* h, const float* d_pcm, const int64_t* h_pcm_off, int B,
                           int k, int max_len, float temperature, int second_pass, double lm_weight,

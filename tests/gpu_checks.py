@@ -249,7 +249,19 @@ def check_fused(cname="beam4"):
     tok2, ln2, sc2, texts2 = m.transcribe(dev, off, bw=cs["bw"], int2word=i2w, resident=True)
     tokg, lng, scg, textsg = m.transcribe(pin, off, bw=None, int2word=i2w)
     greedy = m.eval_one_batch_with_greedy(m.device, dfeats, lens, i2w, None)
+    # asr_prefetch_pcm pipeline: batch 2 is registered before batch 1 runs and staged during it
+    pin2 = torch.from_numpy(np.concatenate(pcms[::-1])).pin_memory()
+    off2 = np.zeros(len(pcms) + 1, dtype=np.int64)
+    off2[1:] = np.cumsum([len(p) for p in pcms[::-1]])
+    want2 = m.transcribe(pin2, off2, bw=cs["bw"], int2word=i2w)
+    m.prefetch(pin, off, bw=cs["bw"])
+    m.prefetch(pin2, off2, bw=cs["bw"])
+    got1 = m.transcribe(pin, off, bw=cs["bw"], int2word=i2w)
+    got2 = m.transcribe(pin2, off2, bw=cs["bw"], int2word=i2w)
+    pre_ok = int(got1[3] == texts and np.array_equal(got1[2], sc) and got2[3] == want2[3]
+                 and np.array_equal(got2[2], want2[2]) and got2[3] == texts[::-1])
     return {"fused_eq_staged": int(texts == list(staged.pred_text)),
+            "prefetched_eq_direct": pre_ok,
             "resident_eq_host": int(texts2 == texts and np.array_equal(sc, sc2)),
             "score_eq": int(np.allclose(sc, np.array(staged.score, dtype=np.float32), rtol=0, atol=0)),
             "greedy_fused_eq_staged": int(textsg == list(greedy.pred_text))}
