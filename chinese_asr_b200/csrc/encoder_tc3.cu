@@ -113,7 +113,22 @@ __device__ __forceinline__ void tmem_ld_cols<10>(uint32_t taddr, uint32_t* r) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-constexpr int kThreads = 512;
+template <>
+__device__ __forceinline__ void tmem_ld_cols<20>(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19])
+                 : "r"(taddr + 16));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+constexpr int kThreads = 544;        // 16 gate warps + 1 MMA-issue warp
+constexpr int kIssueWarp = 16;
 
 struct Params {
     const float* xg;            // [rows, 2048] permuted gate pre-activations (bias included)
@@ -142,20 +157,20 @@ constexpr int kStageBytes = 80 * 320;    // per-CTA staging slot (largest NB)
 template <int NB>
 __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(kThreads, 1)
 lstm_rec_tc3_kernel(Params p) {
-    constexpr int NW = kThreads / 32;        // 16 warps: 4 TMEM lane quarters x 4 column groups
-    constexpr int PASSES = NB > 64 ? 2 : 1;
-    constexpr int RB = NB / PASSES;          // rows transposed through `red` per pass
-    constexpr int HC = RB / (NW / 4);        // accumulator columns read per warp per pass
-    constexpr int P = (NB + NW - 1) / NW;    // rows per gate thread (row i = warp + NW * q)
+    // 16 warps: warp = (TMEM lane quarter q = warp & 3, column group warp >> 2).  TMEM lane m of the CTA's
+    // 128 gate rows is (unit m >> 2, gate m & 3): the four gates of a unit sit in 4 adjacent lanes, so a
+    // 4x4 transpose by warp shuffles gives every lane complete (i, f, g, o) pre-activations of P cells
+    // (unit, batch row) - no shared-memory transposition and no block barrier in the gate phase.
+    constexpr int CW = NB / 4;               // accumulator columns (batch rows) per warp
+    constexpr int P = CW / 4;                // cells per lane: rows cg * CW + 4 b + (lane & 3)
     constexpr int kHi = NB * 128;            // bytes of one hi (or lo) slab
     constexpr int kBf = NB * 64;             // bytes of one bf16 slab
     constexpr int kSlab = 2 * kHi + kBf;     // [hi | lo | bf16] of one 32-wide K range
-    static_assert(NB % 16 == 0 && RB % (NW / 4) == 0, "NB");
+    static_assert(NB % 16 == 0, "NB");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* T = smem;                                             // 8 slabs x kSlab
-    float* red = reinterpret_cast<float*>(T + 8 * kSlab);          // [RB][128]
-    uint64_t* mma_done = reinterpret_cast<uint64_t*>(red + RB * 128);
+    uint64_t* mma_done = reinterpret_cast<uint64_t*>(T + 8 * kSlab);
     uint64_t* h_ready = mma_done + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h_ready + 1);
     int* s_len = reinterpret_cast<int*>(tmem_slot + 1);            // [NB]
@@ -187,7 +202,8 @@ lstm_rec_tc3_kernel(Params p) {
     const uint32_t tmem_alo = tmem_base + 256;
     const uint32_t tmem_d = tmem_base + 384;
     if (warp < 4) {
-        const size_t wrow = (size_t)dir * kGates + j * 128 + 32 * warp + lane;   // gate column of this lane
+        const int m = 32 * warp + lane;                                          // TMEM lane = (unit m >> 2, gate m & 3)
+        const size_t wrow = (size_t)dir * kGates + j * 128 + (m & 3) * 32 + (m >> 2);
         const float* whi = p.whh_hi + wrow * kEncH;
 #pragma unroll 1
         for (int c0 = 0; c0 < kEncH; c0 += 32) {
@@ -220,7 +236,9 @@ lstm_rec_tc3_kernel(Params p) {
     tc_fence_after();
     const int Lc = s_len[0];
 
-    const int uu = lane;
+    const int uu = 8 * (warp & 3) + (lane >> 2);      // unit of this lane within the CTA's 32
+    const int jr = lane & 3;
+    const int col0 = (warp >> 2) * CW + jr;           // batch row of cell b: col0 + 4 b
     const int ocol = dir * kEncH + 32 * j + uu;
     float c_reg[P], h_reg[P];
 #pragma unroll
@@ -243,20 +261,21 @@ lstm_rec_tc3_kernel(Params p) {
     auto store_outputs = [&](int t, int row_t, int n_act) {
 #pragma unroll
         for (int q = 0; q < P; ++q) {
-            const int i = warp + NW * q;
-            if (i < n_act) {
+            const int i = col0 + 4 * q;
+            const bool act = i < n_act;
+            // operand split for the consuming GEMM: the lane 4 away holds the neighbouring unit of the
+            // same row; even units pack the two residuals, odd units the two values (bf16 pairs)
+            const float hi = rn_tf32(yv[q]);
+            const float lo = yv[q] - hi;
+            const float lo_n = __shfl_xor_sync(0xffffffffu, lo, 4);
+            const float y_n = __shfl_xor_sync(0xffffffffu, yv[q], 4);
+            if (act) {
                 const size_t row = (size_t)(row_t + i);
                 const size_t urow = p.y_utt ? (size_t)(p.uoff[r0 + i] + t) : 0;
                 if (p.y_packed) p.y_packed[row * kEnc + ocol] = yv[q];
                 if (p.y_utt) p.y_utt[urow * kEnc + ocol] = yv[q];
                 if (p.y_hi) {
-                    // operand split for the consuming GEMM: lane pairs pack two bf16 (even lane:
-                    // residuals, odd lane: values) - all 32 lanes of the warp are in this branch
                     const size_t srow = p.y_utt ? urow : row;      // last layer: rows as `enc`
-                    const float hi = rn_tf32(yv[q]);
-                    const float lo = yv[q] - hi;
-                    const float lo_n = __shfl_xor_sync(0xffffffffu, lo, 1);
-                    const float y_n = __shfl_xor_sync(0xffffffffu, yv[q], 1);
                     p.y_hi[srow * kEnc + ocol] = hi;
                     const bool odd = (ocol & 1) != 0;
                     const __nv_bfloat162 pk = odd ? __floats2bfloat162_rn(y_n, yv[q]) : __floats2bfloat162_rn(lo, lo_n);
@@ -269,7 +288,7 @@ lstm_rec_tc3_kernel(Params p) {
     };
 
     for (int s = 0; s < Lc; ++s) {
-        if (warp == 4) {
+        if (warp == kIssueWarp) {
             if (lane == 0) {
                 if (s > 0) mbar_wait(h_ready, (uint32_t)((s - 1) & 1));
                 tc_fence_after();
@@ -295,16 +314,18 @@ lstm_rec_tc3_kernel(Params p) {
             __syncwarp();
         }
 
-        if (s > 0) store_outputs(prev_t, prev_row_t, prev_nact);
         const int t = dir == 0 ? s : Lc - 1 - s;
         if (dir == 0) { while (nact > 0 && s_len[nact - 1] <= t) --nact; }
         else { while (nact < nrows && s_len[nact] > t) ++nact; }
         const int row_t = p.toff[t] + r0;
 
+        if (warp < kIssueWarp) {
+        // gate warps: the issue warp above does nothing else, so it never arrives late at the step's barrier
+        if (s > 0) store_outputs(prev_t, prev_row_t, prev_nact);
         float xi[P], xf[P], xgg[P], xo[P], xres[P];
 #pragma unroll
         for (int q = 0; q < P; ++q) {
-            const int i = warp + NW * q;
+            const int i = col0 + 4 * q;
             xi[q] = xf[q] = xgg[q] = xo[q] = xres[q] = 0.f;
             if (i < nact) {
                 if (p.x_in) xres[q] = __ldg(p.x_in + (size_t)(row_t + i) * kEnc + ocol);
@@ -319,28 +340,30 @@ lstm_rec_tc3_kernel(Params p) {
         mbar_wait(mma_done, (uint32_t)(s & 1));
         tc_fence_after();
         if (p.dbg && blockIdx.x == 0 && tid == 0) p.dbg[s * 8 + 2] = clock64();
-#pragma unroll
-        for (int pass = 0; pass < PASSES; ++pass) {
-            {
-                // warps w, w+4, w+8, w+12 share a TMEM lane quarter and split the columns 4 ways
-                uint32_t d[HC];
-                const int qd = warp & 3, cg4 = warp >> 2;
-                tmem_ld_cols<HC>(tmem_d + ((uint32_t)(32 * qd) << 16) + (uint32_t)(pass * RB + cg4 * HC), d);
-                const int m = 32 * qd + lane;
-#pragma unroll
-                for (int n = 0; n < HC; ++n) red[(cg4 * HC + n) * 128 + m] = __uint_as_float(d[n]);
-            }
+        {
+            uint32_t d[CW];
+            tmem_ld_cols<CW>(tmem_d + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((warp >> 2) * CW), d);
             tc_fence_before();
-            __syncthreads();
+            const bool o1 = (jr & 1) != 0, o2 = (jr & 2) != 0;
 #pragma unroll
             for (int q = 0; q < P; ++q) {
-                const int i = warp + NW * q;
-                if (i >= pass * RB && i < (pass + 1) * RB && i < nact) {    // rows of this pass
-                    const float* rr = red + (i - pass * RB) * 128 + uu;
-                    const float gi = xi[q] + rr[0];
-                    const float gf = xf[q] + rr[32];
-                    const float gg = xgg[q] + rr[64];
-                    const float go = xo[q] + rr[96];
+                // 4x4 transpose across the 4 lanes of a unit: in = this lane's gate for rows 4q..4q+3,
+                // out = gates i, f, g, o of row 4q + jr
+                const float v0 = __uint_as_float(d[4 * q]), v1 = __uint_as_float(d[4 * q + 1]);
+                const float v2 = __uint_as_float(d[4 * q + 2]), v3 = __uint_as_float(d[4 * q + 3]);
+                const float ra = __shfl_xor_sync(0xffffffffu, o1 ? v0 : v1, 1);
+                const float rb = __shfl_xor_sync(0xffffffffu, o1 ? v2 : v3, 1);
+                const float x0 = o1 ? ra : v0, x1 = o1 ? v1 : ra;
+                const float x2 = o1 ? rb : v2, x3 = o1 ? v3 : rb;
+                const float ua = __shfl_xor_sync(0xffffffffu, o2 ? x0 : x2, 2);
+                const float ub = __shfl_xor_sync(0xffffffffu, o2 ? x1 : x3, 2);
+                const float di = o2 ? ua : x0, df = o2 ? ub : x1, dg = o2 ? x2 : ua, dO = o2 ? x3 : ub;
+                const int i = col0 + 4 * q;
+                if (i < nact) {
+                    const float gi = xi[q] + di;
+                    const float gf = xf[q] + df;
+                    const float gg = xgg[q] + dg;
+                    const float go = xo[q] + dO;
                     const float c = sigmoid_f(gf) * c_reg[q] + sigmoid_f(gi) * tanh_f(gg);
                     const float hh = sigmoid_f(go) * tanh_f(c);
                     c_reg[q] = c;
@@ -357,7 +380,7 @@ lstm_rec_tc3_kernel(Params p) {
                     yv[q] = hh + xres[q];
                 }
             }
-            if (PASSES > 1 && pass + 1 < PASSES) __syncthreads();
+        }
         }
         if (p.dbg && blockIdx.x == 0 && tid == 0) p.dbg[s * 8 + 4] = clock64();
         if (s + 1 < Lc) {
@@ -389,12 +412,12 @@ lstm_rec_tc3_kernel(Params p) {
         }
         prev_t = t; prev_row_t = row_t; prev_nact = nact;
     }
-    if (Lc > 0) store_outputs(prev_t, prev_row_t, prev_nact);
+    if (Lc > 0 && warp < kIssueWarp) store_outputs(prev_t, prev_row_t, prev_nact);
 
 #pragma unroll
     for (int q = 0; q < P; ++q) {
-        const int i = warp + NW * q;
-        if (i < nrows) {
+        const int i = col0 + 4 * q;
+        if (i < nrows && warp < kIssueWarp) {
             p.h_fin[(size_t)(r0 + i) * kEnc + ocol] = h_reg[q];
             p.c_fin[(size_t)(r0 + i) * kEnc + ocol] = c_reg[q];
         }
@@ -418,8 +441,7 @@ __global__ void pack_bf16_pairs_kernel(const float* __restrict__ src, uint32_t* 
 
 template <int NB>
 static int launch(const Params& p, cudaStream_t st) {
-    constexpr int PASSES = NB > 64 ? 2 : 1;
-    const size_t smem = 8 * (size_t)(NB * 320) + (size_t)(NB / PASSES) * 128 * 4 + 1024 + 64 + NB * 4;
+    const size_t smem = 8 * (size_t)(NB * 320) + 1024 + 64 + NB * 4;
     static bool attr = false;
     if (!attr) {
         ASR_CUDA(cudaFuncSetAttribute(lstm_rec_tc3_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
