@@ -437,7 +437,7 @@ attention_kernel(AttnParams p) {
 // maximum M and the accumulators are rescaled by exp(M_old - M_new) when a chunk raises it
 // (same value as softmax-then-sum up to fp32 rounding of the rescale factors).
 // Hand-off through named barriers: full[b] (producers arrive, consumers sync), empty[b] (the reverse).
-constexpr int kAttChunk = 64;
+constexpr int kAttChunk = 32;
 
 __device__ __forceinline__ void named_bar_sync(int id, int count) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
@@ -491,12 +491,11 @@ attention_stream_kernel(AttnParams p) {
     // ring of encoder rows | numerators (aliased by the queries during the prologue) | small state
     float* s_ring = reinterpret_cast<float*>(att_smem);                          // [stages][8][512]
     float* s_p = s_ring + kAttStages * kAttRows * kEnc;                           // [2][K][C]
-    float* s_q = s_p;                                                             // [K][128] (prologue only)
-    float* s_scale = s_p + 2 * K * C;                                             // [2][K]
+    float* s_q = s_p + 2 * K * C;                                                 // [K][128]
+    float* s_scale = s_q + K * kAtt;                                             // [2][K]
     float* s_wmax = s_scale + 2 * K;                                              // [2][4][K]
     float* s_wsum = s_wmax + 2 * 4 * K;                                           // [4][K]
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_wsum + 4 * K);                 // full[stages], empty[stages]
-    static_assert(2 * C >= kAtt, "queries alias the numerator buffers");
 
     const int u = blockIdx.x;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -739,7 +738,7 @@ attention_stream_kernel(AttnParams p) {
 
 template <int K>
 static int launch_attention_stream(const AttnParams& p, int B, cudaStream_t st) {
-    const size_t smem = sizeof(float) * ((size_t)kAttStages * kAttRows * kEnc + 2 * K * kAttChunk + 2 * K + 8 * K + 4 * K) +
+    const size_t smem = sizeof(float) * ((size_t)kAttStages * kAttRows * kEnc + 2 * K * kAttChunk + K * kAtt + 2 * K + 8 * K + 4 * K) +
                         sizeof(uint64_t) * 2 * kAttStages + 16;
     static bool attr = false;
     if (!attr) {
