@@ -311,7 +311,7 @@ def run_native(args):
                 "frac_of_hbm_peak": dec_bytes / (dec_ms / 1000.0) / 1e9 / hbm_peak}
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # reported on rank 0 at N = 1 only
         rate, dt, threads = cpu_port_rate(args.cpu_sample, k, args.seconds, reps=3)
         cpu = {"value": rate, "unit": "utt/s", "cores": threads, "kind": "port", "host_cpus": os.cpu_count(),
                "sample": f"3 batches of {args.cpu_sample} utterances x {args.seconds:g} s, features+encoder+beam "
@@ -345,6 +345,11 @@ def run_native(args):
 
 def main():
     args = parse_args()
+    if int(os.environ.get("RANK", "0")) == 0:
+        # torchrun exports OMP_NUM_THREADS=1; the CPU arms run on rank 0 and must see all host threads.
+        # This has to happen before torch creates its OpenMP pool (set_num_threads later is not enough).
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+        os.environ["MKL_NUM_THREADS"] = str(os.cpu_count() or 1)
     if args.impl == "reference":
         run_reference(args)
     else:
