@@ -174,6 +174,49 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
         ::"r"(smem_u32(bar)), "h"(mask)
         : "memory");
 }
+// ---- CTA-pair (cta_group::2) forms: one MMA over M = 256 spans both CTAs' tensor cores; each CTA holds its
+// 128 rows of A and HALF of the W tile, which the hardware shares between the two SMs.
+__device__ __forceinline__ void umma2_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                           uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                           uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma2_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(smem_u32(bar)), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t local_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+// TMA load into this CTA's shared memory, completion bytes on the mbarrier at cluster address `bar_cluster`
+// (the leader CTA's `full` barrier)
+__device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* map, uint32_t bar_cluster, void* dst, int x, int y) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster), "r"(x), "r"(y)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
+
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -183,10 +226,10 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-template <int BN, int BKF, int STAGES>
+template <int BN, int BKF, int STAGES, bool TWO = false>
 struct SmemLayoutP {
     static constexpr int kATile = BM * BKF * 4;
-    static constexpr int kBTile = BN * BKF * 4;
+    static constexpr int kBTile = (TWO ? BN / 2 : BN) * BKF * 4;      // 2-SM form: each CTA keeps half of the W tile
     static constexpr int kStage = 2 * kATile + 2 * kBTile;
     static constexpr int kScratch = 4 * 32 * 36 * 4;      // per epilogue warp: 32 rows x (32 + 4) floats
     static constexpr int kBytes = STAGES * kStage + kScratch + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -196,13 +239,14 @@ struct SmemLayoutP {
 // each CTA fetches HALF of the W tile and multicasts it into both CTAs' shared memory (the main loop is
 // bound by L2 -> SM traffic, this removes a third of it).  A stage is reused only after the MMA
 // warps of BOTH CTAs have committed it (multicast tcgen05.commit onto both `empty` barriers).
-template <int BN, int BKF, int STAGES, int CL>
+template <int BN, int BKF, int STAGES, int CL, bool TWO = false>
 __global__ void __launch_bounds__(192, 1)
 gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                               const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                               int M, int N, int K, GemmEpilogue epi, int dbg) {
     if (epi.stop_flag && *epi.stop_flag >= 0) return;
-    using L = SmemLayoutP<BN, BKF, STAGES>;
+    static_assert(!TWO || CL == 2, "the 2-SM form is a CTA pair");
+    using L = SmemLayoutP<BN, BKF, STAGES, TWO>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     float* scratch = reinterpret_cast<float*>(smem + STAGES * L::kStage);
@@ -223,8 +267,8 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, cons
     constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1);
 
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], TWO ? 1 : CL); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], TWO ? 8 : 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_hi) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_lo) : "memory");
@@ -232,10 +276,17 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, cons
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w_lo) : "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "n"(2 * BN > 256 ? 512 : 2 * BN)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (TWO) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                         "n"(2 * BN > 256 ? 512 : 2 * BN)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                         "n"(2 * BN > 256 ? 512 : 2 * BN)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     if (CL > 1) cluster_sync_all(); else __syncthreads();       // peer barriers are initialised too
@@ -252,6 +303,17 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, cons
                     const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(&empty[s], ph ^ 1);
                     uint8_t* st = smem + s * L::kStage;
+                    if (TWO) {
+                        // both CTAs' bytes complete on the LEADER's barrier (its MMA warp consumes both halves)
+                        if (crank == 0) mbar_expect_tx(&full[s], 2 * L::kStage);
+                        const uint32_t fb = mapa_rank(smem_u32(&full[s]), 0);
+                        const int nrow = n0 + crank * (BN / 2);
+                        tma_load_2d_2sm(&map_a_hi, fb, st, kb * BKF, m0);
+                        tma_load_2d_2sm(&map_a_lo, fb, st + L::kATile, kb * BKF, m0);
+                        tma_load_2d_2sm(&map_w_hi, fb, st + 2 * L::kATile, kb * BKF, nrow);
+                        tma_load_2d_2sm(&map_w_lo, fb, st + 2 * L::kATile + L::kBTile, kb * BKF, nrow);
+                        continue;
+                    }
                     mbar_expect_tx(&full[s], L::kStage);
                     tma_load_2d(&map_a_hi, &full[s], st, kb * BKF, m0);
                     tma_load_2d(&map_a_lo, &full[s], st + L::kATile, kb * BKF, m0);
@@ -268,9 +330,9 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, cons
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
-            constexpr uint32_t idesc_x = make_idesc_bf16(BM, BN);
+        if (lane == 0 && !(TWO && crank != 0)) {               // 2-SM form: only the leader CTA issues
+            constexpr uint32_t idesc = make_idesc_tf32(TWO ? 2 * BM : BM, BN);
+            constexpr uint32_t idesc_x = make_idesc_bf16(TWO ? 2 * BM : BM, BN);
             int it = 0, lt = 0;
             for (int work = work0; work < nwork; work += work_step, ++lt) {
                 const int acc = lt & 1;
@@ -291,12 +353,19 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, cons
 #pragma unroll
                     for (int kk = 0; kk < BKF / UMMA_K; ++kk) {
                         const uint64_t adv = (uint64_t)((kk * UMMA_K * 4) >> 4);
-                        umma_bf16(tacc, d_al + adv, d_wl + adv, idesc_x, (kb | kk) ? 1u : 0u);   // cross terms
-                        umma_tf32(tacc, d_ah + adv, d_wh + adv, idesc, 1u);
+                        if (TWO) {
+                            umma2_bf16(tacc, d_al + adv, d_wl + adv, idesc_x, (kb | kk) ? 1u : 0u);
+                            umma2_tf32(tacc, d_ah + adv, d_wh + adv, idesc, 1u);
+                        } else {
+                            umma_bf16(tacc, d_al + adv, d_wl + adv, idesc_x, (kb | kk) ? 1u : 0u);   // cross terms
+                            umma_tf32(tacc, d_ah + adv, d_wh + adv, idesc, 1u);
+                        }
                     }
-                    if (CL == 1) umma_commit(&empty[s]); else umma_commit_mc(&empty[s], kMask);
+                    if (TWO) umma2_commit_mc(&empty[s], kMask);
+                    else if (CL == 1) umma_commit(&empty[s]);
+                    else umma_commit_mc(&empty[s], kMask);
                 }
-                umma_commit(&tfull[acc]);
+                if (TWO) umma2_commit_mc(&tfull[acc], kMask); else umma_commit(&tfull[acc]);
             }
         }
     } else {
@@ -427,13 +496,20 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, cons
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (lane == 0) {
+                // 2-SM form: the leader's MMA overwrites both CTAs' accumulators, so both epilogues report to it
+                if (TWO && crank != 0) mbar_arrive_cluster(mapa_rank(smem_u32(&tempty[acc]), 0));
+                else mbar_arrive(&tempty[acc]);
+            }
         }
     }
     if (CL > 1) cluster_sync_all(); else __syncthreads();       // no CTA leaves while its peer may still signal it
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN > 256 ? 512 : 2 * BN) : "memory");
+        if (TWO)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN > 256 ? 512 : 2 * BN) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN > 256 ? 512 : 2 * BN) : "memory");
     }
 }
 
@@ -539,11 +615,11 @@ int split_operand(const AOperand& A, int M, int K, float* hi, float* lo, const i
 }
 
 // CL CTAs of a cluster work on CL vertically adjacent tiles and share the W tile by multicast
-template <int BN, int BKF, int STAGES, int CL>
+template <int BN, int BKF, int STAGES, int CL, bool TWO = false>
 static int launch_tc_cluster(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const float* w_hi, const float* w_lo,
                              int M, int N, int K, const GemmEpilogue& epi, cudaStream_t st, int dbg_p) {
-    auto kern = tc::gemm_tf32x3_persistent_kernel<BN, BKF, STAGES, CL>;
-    const int smem_p = tc::SmemLayoutP<BN, BKF, STAGES>::kBytes;
+    auto kern = tc::gemm_tf32x3_persistent_kernel<BN, BKF, STAGES, CL, TWO>;
+    const int smem_p = tc::SmemLayoutP<BN, BKF, STAGES, TWO>::kBytes;
     const int tiles_m = (M + tc::BM - 1) / tc::BM, tiles_n = (N + BN - 1) / BN;
     static int max_clusters = 0;
     cudaLaunchConfig_t cfg = {};
@@ -581,12 +657,13 @@ static int launch_tc_cfg(const float* a_hi, const float* a_lo, const float* w_hi
     ASR_TRY(tc::make_map(&ma_lo, a_lo, M, K, tc::BM, BKF, epi.lda));
     ASR_TRY(tc::make_map(&mw_hi, w_hi, N, K, BN, BKF, epi.ldw));
     ASR_TRY(tc::make_map(&mw_lo, w_lo, N, K, BN, BKF, epi.ldw));
-    static const int cl = getenv("ASR_B200_GEMM_CLUSTER") ? atoi(getenv("ASR_B200_GEMM_CLUSTER")) : 2;
+    static const int cl = getenv("ASR_B200_GEMM_CLUSTER") ? atoi(getenv("ASR_B200_GEMM_CLUSTER")) : 22;   // 22 = CTA pair with cta_group::2 MMAs
     static const int dbg_p = getenv("ASR_B200_GEMM_DBG") ? atoi(getenv("ASR_B200_GEMM_DBG")) : 0;
     const int smem_p = tc::SmemLayoutP<BN, BKF, STAGES>::kBytes;
     const int tiles_m = (M + tc::BM - 1) / tc::BM, tiles_n = (N + BN - 1) / BN;
     if (cl == 2) return launch_tc_cluster<BN, BKF, STAGES, 2>(ma_hi, ma_lo, w_hi, w_lo, M, N, K, epi, st, dbg_p);
     if (cl == 4) return launch_tc_cluster<BN, BKF, STAGES, 4>(ma_hi, ma_lo, w_hi, w_lo, M, N, K, epi, st, dbg_p);
+    if (cl == 22) return launch_tc_cluster<BN, BKF, STAGES + (BKF == 32 ? 1 : 2), 2, true>(ma_hi, ma_lo, w_hi, w_lo, M, N, K, epi, st, dbg_p);
     {
         static bool attr_p = false;
         static int num_sms = 0;
@@ -622,7 +699,12 @@ int launch_gemm_tc(const float* a_hi, const float* a_lo, const float* w_hi, cons
         if (cost(224) < cost(256)) bn = 224;
     }
     if (env) bn = atoi(env);
-    if (bn == 256) {
+    static const int bk32 = getenv("ASR_B200_GEMM_BK") ? atoi(getenv("ASR_B200_GEMM_BK")) == 32 : 1;   // 128-byte K slabs, 3 stages in the 2-SM form
+    if (bn == 256 && bk32) {
+        ASR_TRY((launch_tc_cfg<256, 32, 2>(a_hi, a_lo, w_hi, w_lo, M, N, K, epi, st)));
+    } else if (bn == 224 && bk32) {
+        ASR_TRY((launch_tc_cfg<224, 32, 2>(a_hi, a_lo, w_hi, w_lo, M, N, K, epi, st)));
+    } else if (bn == 256) {
         // 128 x 256 tile, 64-byte K slabs, 4 stages: twice the MMA work per byte of A in flight
         ASR_TRY((launch_tc_cfg<256, 16, 4>(a_hi, a_lo, w_hi, w_lo, M, N, K, epi, st)));
     } else if (bn == 224) {
