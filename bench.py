@@ -274,9 +274,9 @@ def run_native(args):
     if dom.startswith("gemm"):
         ach = gemm_gflop / gemm_ms                        # GFLOP / ms = TFLOP/s (algorithmic fp32 2*M*N*K)
         # dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the 125 launches of a pass
-        # (4 encoder projections 8.59 GB, keys 0.77 GB, 40 x (vocabulary 166 MB + cell 65 MB + query 17 MB)):
+        # (4 encoder projections 8.55 GB, keys 0.77 GB, 40 x (vocabulary 160 MB + cell 64 MB + query 17 MB)):
         # profiles/r01_kernels.csv, one `ncu --set full` capture of this workload
-        traffic = 19.33e9 / 125 if (B, k, L) == (512, 8, 332) else None
+        traffic = 18.96e9 / 125 if (B, k, L) == (512, 8, 332) else None
         roof = {"kernel": "tc::gemm_tf32x3_persistent_kernel", "bound": "tensor", "achieved": ach, "peak": tf_peak,
                 "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": traffic,
                 "peak_source": peak_src + " cuBLAS bf16 sustained.  Per fp32 product the kernel issues one tf32 MMA "
