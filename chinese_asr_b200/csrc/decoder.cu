@@ -956,13 +956,29 @@ __device__ void beam_bookkeep(const BookParams& p, int u, float* s_s, int* s_f, 
     if (p.next_hi) {
         __syncthreads();
         // k rows x 1024 floats x (hi, cross): 16-byte copies, halves swapped ([h | ctx] -> [ctx | h])
-        const int per_row = kProjK / 4;                      // float4 per row
-        for (int idx = tid; idx < k * per_row; idx += 256) {
-            const int i = idx / per_row, c4 = idx - i * per_row;
-            const int s4 = c4 < kEnc / 4 ? c4 + kDecH / 4 : c4 - kEnc / 4;
-            const size_t so = (size_t)s_src[i] * kProjK + 4 * s4, d = (size_t)(u * k + i) * kProjK + 4 * c4;
-            *reinterpret_cast<float4*>(p.next_hi + d) = __ldcg(reinterpret_cast<const float4*>(p.split_hi + so));
-            *reinterpret_cast<float4*>(p.next_lo + d) = __ldcg(reinterpret_cast<const float4*>(p.split_lo + so));
+        static_assert(kProjK / 4 == 256, "one 16-byte column per thread");
+        // per_row = 256 = blockDim: thread `tid` owns one 16-byte column of every row; all 2k loads of a
+        // thread are issued before the first store
+        const int c4 = tid;
+        const int s4 = c4 < kEnc / 4 ? c4 + kDecH / 4 : c4 - kEnc / 4;
+        for (int i0 = 0; i0 < k; i0 += 4) {          // 8 loads in flight per thread
+            float4 vh[4], vl[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (i0 + i < k) {
+                    const size_t so = (size_t)s_src[i0 + i] * kProjK + 4 * s4;
+                    vh[i] = __ldcg(reinterpret_cast<const float4*>(p.split_hi + so));
+                    vl[i] = __ldcg(reinterpret_cast<const float4*>(p.split_lo + so));
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (i0 + i < k) {
+                    const size_t d = (size_t)(u * k + i0 + i) * kProjK + 4 * c4;
+                    *reinterpret_cast<float4*>(p.next_hi + d) = vh[i];
+                    *reinterpret_cast<float4*>(p.next_lo + d) = vl[i];
+                }
+            }
         }
     }
 }

@@ -698,6 +698,8 @@ int launch_gemm_tc(const float* a_hi, const float* a_lo, const float* w_hi, cons
         auto cost = [&](int w) { return (long long)((mg * ((N + w - 1) / w) + ncl - 1) / ncl) * w; };
         if (cost(224) < cost(256)) bn = 224;
     }
+    static const char* env_cell = getenv("ASR_B200_CELL_TILE");
+    if (env_cell && epi.kind == Epi::kLstmCell) bn = atoi(env_cell);
     if (env) bn = atoi(env);
     static const int bk32 = getenv("ASR_B200_GEMM_BK") ? atoi(getenv("ASR_B200_GEMM_BK")) == 32 : 1;   // 128-byte K slabs, 3 stages in the 2-SM form
     if (bn == 256 && bk32) {
