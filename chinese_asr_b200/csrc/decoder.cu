@@ -134,6 +134,8 @@ struct AttnParams {
     const int* order;       // [B]
     const int* ctrl;
     int k, S, B, Lmax, sc_ld;
+    long long* trace;       // optional clock64 timeline of CTA 0 (ASR_B200_ATT_TRACE)
+    int dbg;                // timing experiments only: 1 = producers skip the score math, 2 = consumers skip the FMAs
     long long score_ld;
 };
 
@@ -487,6 +489,8 @@ attention_stream_kernel(AttnParams p) {
     constexpr int C = kAttChunk;
     constexpr int kGroup = 32 / K;                 // lanes that end up holding the same beam
     constexpr int FPW = C / 4;                     // frames per producer warp per chunk
+    const bool tr = p.trace && blockIdx.x == 0;
+    if (tr && threadIdx.x == 0) p.trace[0] = clock64();
     extern __shared__ __align__(128) uint8_t att_smem[];
     // ring of encoder rows | numerators (aliased by the queries during the prologue) | small state
     float* s_ring = reinterpret_cast<float*>(att_smem);                          // [stages][8][512]
@@ -518,6 +522,7 @@ attention_stream_kernel(AttnParams p) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     const bool product_form = !__syncthreads_or(q_big) && p.keys_big[u] == 0;
+    if (tr && tid == 0) p.trace[1] = clock64();
 
     if (warp < 4) {
         // ---------------- producers: scores -> numerators ------------------------------------------
@@ -544,10 +549,13 @@ attention_stream_kernel(AttnParams p) {
             float* pb = s_p + (buf * K + my_kb) * C;       // this lane's beam row of the chunk
             // the first barrier of chunk 0 also orders every producer's query reads before the
             // numerator stores that overwrite them
+            if (tr && tid == 0 && c < 16) p.trace[8 + c * 8 + 0] = clock64();
             named_bar_sync(c >= 2 ? 3 + buf : 5, c >= 2 ? 256 : 128);     // buffer drained by the consumers
+            if (tr && tid == 0 && c < 16) p.trace[8 + c * 8 + 1] = clock64();
             float cmax = -CUDART_INF_F;
             // the key row of the next frame is in flight while one frame is evaluated
             auto load_key = [&](int f) {
+                if (p.dbg & 4) return make_float4(0.f, 0.f, 0.f, 0.f);
                 const int l = min(c0 + warp + 4 * f, nl - 1);
                 return __ldg(reinterpret_cast<const float4*>(kbase + (size_t)(row0 + l) * kAtt) + lane);
             };
@@ -558,7 +566,8 @@ attention_stream_kernel(AttnParams p) {
                 float ev = -CUDART_INF_F;
                 float4 key = key_n1;
                 if (f + 1 < FPW) key_n1 = load_key(f + 1);
-                if (l < nl) {                              // warp-uniform
+                if (l < nl && (p.dbg & 1)) ev = 0.f;
+                if (l < nl && !(p.dbg & 1)) {              // warp-uniform
                     float e[K];
                     if (product_form) {
                         if (K >= 2) {
@@ -617,7 +626,9 @@ attention_stream_kernel(AttnParams p) {
                 cmax = fmaxf(cmax, ev);
             }
             if (leader) s_wmax[(buf * 4 + warp) * K + my_kb] = cmax;
+            if (tr && tid == 0 && c < 16) p.trace[8 + c * 8 + 2] = clock64();
             named_bar_sync(5, 128);                        // chunk maxima of the 4 producer warps
+            if (tr && tid == 0 && c < 16) p.trace[8 + c * 8 + 3] = clock64();
             if (leader) {
                 const float* wm = s_wmax + buf * 4 * K + my_kb;
                 const float new_max = fmaxf(run_max, fmaxf(fmaxf(wm[0], wm[K]), fmaxf(wm[2 * K], wm[3 * K])));
@@ -635,6 +646,7 @@ attention_stream_kernel(AttnParams p) {
             }
             __threadfence_block();
             named_bar_arrive(1 + buf, 256);
+            if (tr && tid == 0 && c < 16) p.trace[8 + c * 8 + 4] = clock64();
         }
         if (leader) s_wsum[warp * K + my_kb] = run_sum;
     } else {
@@ -647,7 +659,7 @@ attention_stream_kernel(AttnParams p) {
         auto issue = [&](int st) {                         // rows [8 st, 8 st + 8) of the utterance -> ring slot
             const int slot = st % kAttStages;
             const int rows = min(kAttRows, nl - st * kAttRows);
-            const uint32_t bytes = (uint32_t)rows * kEnc * 4u;
+            const uint32_t bytes = (p.dbg & 8) ? 16u : (uint32_t)rows * kEnc * 4u;
             att_mbar_expect_tx(&full_e[slot], bytes);
             att_bulk_g2s(s_ring + slot * kAttRows * kEnc, enc_u + (size_t)st * kAttRows * kEnc, bytes, &full_e[slot]);
         };
@@ -658,7 +670,9 @@ attention_stream_kernel(AttnParams p) {
             const int buf = (l0 / C) & 1;
             const int lc = l0 % C;
             if (lc == 0) {
+                if (tr && tid == 128 && l0 / C < 16) p.trace[8 + (l0 / C) * 8 + 5] = clock64();
                 named_bar_sync(1 + buf, 256);              // this chunk's numerators are ready
+                if (tr && tid == 128 && l0 / C < 16) p.trace[8 + (l0 / C) * 8 + 6] = clock64();
 #pragma unroll
                 for (int kb = 0; kb < K; ++kb) {
                     if (kb < k) {
@@ -672,6 +686,7 @@ attention_stream_kernel(AttnParams p) {
             const float4* er = reinterpret_cast<const float4*>(s_ring + slot * kAttRows * kEnc) + cg4;
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {               // 4 rows at a time: 16 registers of encoder data
+                if (p.dbg & 2) { if (hf == 1) { __syncwarp(); if (lane == 0) att_mbar_arrive(&empty_e[slot]); } continue; }
                 float4 e[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
@@ -695,6 +710,7 @@ attention_stream_kernel(AttnParams p) {
             }
             if (lc + kAttRows == C || st + 1 == nstage) {              // last stage of the chunk
                 const int c = l0 / C;
+                if (tr && tid == 128 && c < 16) p.trace[8 + c * 8 + 7] = clock64();
                 if (c + 2 < nchunk) named_bar_arrive(3 + buf, 256);
             }
             if (tid == 128 && st + kAttStages < nstage) {
@@ -703,6 +719,7 @@ attention_stream_kernel(AttnParams p) {
             }
         }
         __syncthreads();                                   // producers' sums
+        if (tr && tid == 128) p.trace[2] = clock64();
 #pragma unroll
         for (int kb = 0; kb < K; ++kb) {
             if (kb < k) {
@@ -731,6 +748,7 @@ attention_stream_kernel(AttnParams p) {
                 }
             }
         }
+        if (tr && tid == 128) p.trace[3] = clock64();
         return;
     }
     __syncthreads();                                       // matches the consumers' barrier above
@@ -755,6 +773,13 @@ int launch_attention(asr_handle* h, int k, int step, int nxt, float* d_align_ste
     const BatchMeta& m = h->meta;
     AttnParams p{};
     p.q = w.att_q;
+    static const int att_dbg = getenv("ASR_B200_ATT_DBG") ? atoi(getenv("ASR_B200_ATT_DBG")) : 0;
+    p.dbg = att_dbg;
+    static long long* d_trace = nullptr;
+    static int trace_calls = 0;
+    static const bool want_trace = getenv("ASR_B200_ATT_TRACE") != nullptr;
+    if (want_trace && !d_trace) { ASR_CUDA(cudaMalloc(&d_trace, 256 * sizeof(long long))); ASR_CUDA(cudaMemset(d_trace, 0, 256 * sizeof(long long))); }
+    p.trace = d_trace;
     p.keys = w.keys;
     p.keys_exp = w.keys_exp;
     p.keys_big = w.keys_big;
@@ -794,6 +819,18 @@ int launch_attention(asr_handle* h, int k, int step, int nxt, float* d_align_ste
         }
         ASR_CHECK_LAUNCH();
         h->launches++;
+        if (d_trace && ++trace_calls == 50) {
+            long long t[256];
+            cudaStreamSynchronize(st);
+            cudaMemcpy(t, d_trace, sizeof(t), cudaMemcpyDeviceToHost);
+            fprintf(stderr, "[att trace] prologue %lld, loop end %lld, kernel end %lld cycles\n", t[1] - t[0], t[2] - t[0], t[3] - t[0]);
+            for (int c = 0; c < 12; ++c) {
+                const long long* a = t + 8 + c * 8;
+                if (!a[0]) break;
+                fprintf(stderr, "  chunk %2d prod: start %6lld drained %6lld scores %6lld maxbar %6lld published %6lld | cons: wait-from %6lld ready %6lld done %6lld\n",
+                        c, a[0] - t[0], a[1] - t[0], a[2] - t[0], a[3] - t[0], a[4] - t[0], a[5] - t[0], a[6] - t[0], a[7] - t[0]);
+            }
+        }
         return ASR_OK;
     }
     const size_t smem = sizeof(float) * ((size_t)K * kAtt + (size_t)K * p.sc_ld + (size_t)K * kEnc);
