@@ -48,6 +48,11 @@ def synth_batch(B, n, seed):
     return (0.1 * rng.standard_normal((B, n))).astype(np.float32)
 
 
+def synth_batch_s16(B, n, seed):
+    """The same waveforms as 16-bit PCM - what a WAV file holds and what the front end ships to the GPU."""
+    return np.clip(np.round(synth_batch(B, n, seed) * 32768.0), -32768, 32767).astype(np.int16)
+
+
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
@@ -107,7 +112,7 @@ def cpu_port_rate(n_utts, bw, seconds, threads=None, reps=1, warm=0):
     torch.set_num_threads(threads or max(1, os.cpu_count() or 1))
     weights = O.make_weights(1234, "plain")
     n = int(seconds * SR)
-    pcm = synth_batch(n_utts, n, 4242)
+    pcm = O.pcm_from_int16(synth_batch_s16(n_utts, n, 4242))     # fast_read (data.py:109-121) of 16-bit samples
     best = None
     for it in range(warm + reps):
         t0 = time.perf_counter()
@@ -183,7 +188,8 @@ def run_native(args):
     m.load_state(O.make_weights(1234, "plain"))
     m.reserve(B, B * L, k, B * n, MAX_LEN)
     off = (np.arange(B + 1, dtype=np.int64) * n)
-    host = torch.from_numpy(synth_batch(B, n, 1000 + rank).reshape(-1)).pin_memory()
+    # 16-bit PCM (what WAV files hold): converted to float32 by the log-mel kernel (asr_transcribe_pcm, ASR_PCM_S16)
+    host = torch.from_numpy(synth_batch_s16(B, n, 1000 + rank).reshape(-1)).pin_memory()
     host2 = host.clone().pin_memory()          # end-to-end steps alternate between two host buffers
     resident = host.to(dev)
     total = B * world
@@ -324,10 +330,11 @@ def run_native(args):
                                f"(BASELINE.json configs[4]: 4096 utterances over 8 GPUs)",
                    "beam": k, "utts_per_gpu_per_step": B, "utt_seconds": args.seconds, "max_len": MAX_LEN,
                    "enc_frames_per_utt": L, "weights": "random-init (reference initialisers), fp32",
+                   "pcm": "int16 (16-bit WAV samples), converted on the device",
                    "l2_policy": "inputs larger than L2 (PCM %.0f MB, gate pre-activations %.0f MB per step)"
-                                % (B * n * 4 / 1e6, B * L * 8192 / 1e6)},
+                                % (B * n * 2 / 1e6, B * L * 8192 / 1e6)},
         "e2e": {"value": e2e_val, "unit": "utt/s", "rtfx": e2e_val * args.seconds,
-                "h2d_bytes_per_step": int(B * n * 4 + (B + 1) * 16 + 3 * B * L * 4),
+                "h2d_bytes_per_step": int(B * n * 2 + (B + 1) * 16 + 3 * B * L * 4),
                 "d2h_bytes_per_step": int(B * (MAX_LEN + 2) * 4 + 16),
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),

@@ -1,13 +1,38 @@
 #!/bin/bash
 # Build libasr_b200.so (sm_100a only) in-tree.  Usage: ./build.sh [extra nvcc flags]
+# One nvcc -c per source, in parallel; an object is rebuilt when its source, a shared header, the public
+# header or this script is newer.  Extra flags force a full rebuild.
 set -e
 cd "$(dirname "$0")"
 SRC=chinese_asr_b200/csrc
 OUT=chinese_asr_b200/libasr_b200.so
+OBJ=build/obj
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
-$NVCC -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 \
-    -Xcompiler -fPIC -shared -Xptxas -v "$@" \
-    $SRC/api.cu $SRC/features.cu $SRC/gemm.cu $SRC/gemm_tc.cu $SRC/encoder.cu $SRC/encoder_tc.cu $SRC/encoder_tc3.cu $SRC/decoder.cu \
-    -o $OUT 2> build.log || { cat build.log; exit 1; }
+FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xptxas -v"
+mkdir -p $OBJ
+: > build.log
+pids=()
+names=()
+for f in api features gemm gemm_tc encoder encoder_tc encoder_tc3 decoder wer; do
+    o=$OBJ/$f.o
+    stale=0
+    if [ ! -f $o ] || [ $# -gt 0 ]; then stale=1; else
+        for d in $SRC/$f.cu $SRC/*.cuh include/asr_b200.h build.sh; do
+            [ $d -nt $o ] && stale=1
+        done
+    fi
+    if [ $stale = 1 ]; then
+        ( $NVCC $FLAGS "$@" -c $SRC/$f.cu -o $o > $OBJ/$f.log 2>&1 ) &
+        pids+=($!)
+        names+=($f)
+    fi
+done
+fail=0
+for i in "${!pids[@]}"; do
+    if ! wait ${pids[$i]}; then fail=1; echo "nvcc failed on ${names[$i]}.cu"; fi
+    cat $OBJ/${names[$i]}.log >> build.log
+done
+if [ $fail = 1 ]; then rm -f $(for n in "${names[@]}"; do echo $OBJ/$n.o; done); grep -E "error" build.log | head -40; exit 1; fi
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -Xcompiler -fPIC $OBJ/*.o -o $OUT >> build.log 2>&1 || { tail -20 build.log; exit 1; }
 grep -E "error|warning" build.log | grep -v "ptxas info" | head -20 || true
 echo "built $OUT"

@@ -19,6 +19,8 @@ c_float_p = C.POINTER(C.c_float)
 c_int32_p = C.POINTER(C.c_int32)
 c_int64_p = C.POINTER(C.c_int64)
 
+PCM_F32, PCM_S16 = 0, 1          # enum asr_pcm_format
+
 
 class AsrWeights(C.Structure):
     _fields_ = [("enc_w_ih", c_float_p * 8), ("enc_w_hh", c_float_p * 8),
@@ -51,6 +53,19 @@ SIGNATURES = {
     "asr_features": (C.c_int, [C.c_void_p, C.c_void_p, c_int64_p, C.c_int, C.c_void_p, c_int32_p,
                                C.c_int, C.c_void_p]),
     "asr_num_frames": (C.c_int, [C.c_int64]),
+    "asr_features_pcm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, c_int64_p, C.c_int, C.c_void_p, c_int32_p,
+                                   C.c_int, C.c_float, C.c_void_p]),
+    "asr_cmvn": (C.c_int, [C.c_void_p, C.c_void_p, c_int32_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
+    "asr_set_vocab": (C.c_int, [C.c_void_p, c_int32_p, c_int32_p, C.c_int]),
+    "asr_wer": (C.c_int, [C.c_void_p, c_int32_p, c_int32_p, C.c_int, c_int32_p, c_int64_p, C.c_int, c_int32_p,
+                          c_int32_p, C.c_void_p]),
+    "asr_transcribe_pcm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_float, c_int64_p, C.c_int, C.c_int,
+                                     C.c_int, C.c_float, C.c_int, C.c_double, C.c_double, c_int32_p, c_int32_p,
+                                     c_float_p, C.c_void_p]),
+    "asr_transcribe_device_pcm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_float, c_int64_p, C.c_int,
+                                            C.c_int, C.c_int, C.c_float, C.c_int, C.c_double, C.c_double,
+                                            c_int32_p, c_int32_p, c_float_p, C.c_void_p]),
+    "asr_prefetch_pcm_fmt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, c_int64_p, C.c_int]),
     "asr_encode": (C.c_int, [C.c_void_p, C.c_void_p, c_int32_p, C.c_int, C.c_void_p]),
     "asr_export_encoder": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p]),

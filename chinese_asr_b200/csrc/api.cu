@@ -429,6 +429,7 @@ static int beam_decode_device(asr_handle* h, int k, int max_len, float temperatu
     }
     h->last_k = k;
     h->last_B = h->meta.B;
+    h->last_out_ld = max_len;
     return ASR_OK;
 }
 
@@ -450,6 +451,8 @@ static int greedy_decode_device(asr_handle* h, int max_len, float* d_align, floa
         cur ^= 1;
     }
     ASR_TRY(launch_greedy_finalise(h, max_len, st));
+    h->last_B = B;
+    h->last_out_ld = max_len;
     return ASR_OK;
 }
 
@@ -467,9 +470,10 @@ static int fetch_results(asr_handle* h, int B, int max_len, int32_t* h_tokens, i
     return ASR_OK;
 }
 
-static int features_device(asr_handle* h, const float* d_pcm, const int64_t* h_pcm_off, int B,
-                           int32_t* h_L, int normalise, bool packed_out, float* d_out,
+static int features_device(asr_handle* h, const void* d_pcm, int format, const int64_t* h_pcm_off, int B,
+                           int32_t* h_L, int normalise, float eps, bool packed_out, float* d_out,
                            cudaStream_t st) {
+    if (format != ASR_PCM_F32 && format != ASR_PCM_S16) { set_error("unknown PCM format %d", format); return ASR_ERR_ARG; }
     Workspace& w = h->ws;
     if (B <= 0 || B > w.max_utts) { set_error("batch %d outside 1..%d", B, w.max_utts); return ASR_ERR_CAPACITY; }
     if (h_pcm_off[B] - h_pcm_off[0] > w.max_samples) { set_error("batch has more samples than reserved"); return ASR_ERR_CAPACITY; }
@@ -496,10 +500,10 @@ static int features_device(asr_handle* h, const float* d_pcm, const int64_t* h_p
     ASR_CUDA(cudaMemcpyAsync(w.d_featrow_off, hs + sizeof(long long) * (B + 1) + sizeof(int) * (B + 1), sizeof(int) * (B + 1), cudaMemcpyHostToDevice, st));
     ASR_CUDA(cudaStreamSynchronize(st));
     StageScope sc(h, kStFeat, st);
-    ASR_TRY(launch_logmel(h, d_pcm, w.d_pcm_off, w.d_frame_off, B, foff[B], w.mel, st));
+    ASR_TRY(launch_logmel(h, d_pcm, format, w.d_pcm_off, w.d_frame_off, B, foff[B], w.mel, st));
     int lmax = 0;
     for (int i = 0; i < B; ++i) lmax = std::max(lmax, (int)h_L[i]);
-    ASR_TRY(launch_delta_cmvn(h, w.mel, w.d_frame_off, w.d_featrow_off, B, lmax, normalise,
+    ASR_TRY(launch_delta_cmvn(h, w.mel, w.d_frame_off, w.d_featrow_off, B, lmax, normalise, eps,
                               packed_out ? h->meta.d_feat2packed : nullptr, d_out, st));
     return ASR_OK;
 }
@@ -712,6 +716,8 @@ int asr_destroy(asr_handle* h) {
     if (h->graph_stream) cudaStreamDestroy(h->graph_stream);
     if (h->copy_stream) { cudaStreamDestroy(h->copy_stream); cudaEventDestroy(h->pre_ev[0]); cudaEventDestroy(h->pre_ev[1]); }
     for (void* p : h->weight_allocs) cudaFree(p);
+    if (h->vocab.d_cp) cudaFree(h->vocab.d_cp);
+    if (h->vocab.d_off) cudaFree(h->vocab.d_off);
     for (void* p : h->ws.allocs) cudaFree(p);
     if (h->ws.h_stage) cudaFreeHost(h->ws.h_stage);
     for (cudaEvent_t e : h->ev) if (e) cudaEventDestroy(e);
@@ -821,12 +827,38 @@ int asr_reserve(asr_handle* h, int max_utts, int64_t max_rows, int max_beam, int
     return ASR_OK;
 }
 
-int asr_features(asr_handle* h, const float* d_pcm, const int64_t* h_pcm_off, int B, float* d_feats,
-                 int32_t* h_L, int normalise, void* stream) {
+int asr_features_pcm(asr_handle* h, const void* d_pcm, int format, const int64_t* h_pcm_off, int B,
+                     float* d_feats, int32_t* h_L, int normalise, float cmvn_eps, void* stream) {
     if (!h || !d_pcm || !h_pcm_off || !d_feats || !h_L) { set_error("asr_features: NULL argument"); return ASR_ERR_ARG; }
     if (h->ws.max_samples <= 0) { set_error("asr_features: reserve with max_samples > 0"); return ASR_ERR_STATE; }
     cudaStream_t st = (cudaStream_t)stream;
-    ASR_TRY(features_device(h, d_pcm, h_pcm_off, B, h_L, normalise, false, d_feats, st));
+    ASR_TRY(features_device(h, d_pcm, format, h_pcm_off, B, h_L, normalise, cmvn_eps, false, d_feats, st));
+    ASR_CUDA(cudaStreamSynchronize(st));
+    return ASR_OK;
+}
+
+int asr_features(asr_handle* h, const float* d_pcm, const int64_t* h_pcm_off, int B, float* d_feats,
+                 int32_t* h_L, int normalise, void* stream) {
+    return asr_features_pcm(h, d_pcm, ASR_PCM_F32, h_pcm_off, B, d_feats, h_L, normalise, 1e-6f, stream);
+}
+
+int asr_cmvn(asr_handle* h, const float* d_feats, const int32_t* h_L, int B, float eps, float* d_out, void* stream) {
+    if (!h || !d_feats || !h_L || !d_out) { set_error("asr_cmvn: NULL argument"); return ASR_ERR_ARG; }
+    Workspace& w = h->ws;
+    if (!w.feat_partial) { set_error("asr_cmvn: call asr_reserve first"); return ASR_ERR_STATE; }
+    if (B <= 0 || B > w.max_utts) { set_error("batch %d outside 1..%d", B, w.max_utts); return ASR_ERR_CAPACITY; }
+    cudaStream_t st = (cudaStream_t)stream;
+    int* roff = reinterpret_cast<int*>(w.h_stage);
+    int lmax = 0;
+    roff[0] = 0;
+    for (int i = 0; i < B; ++i) {
+        if (h_L[i] < 1) { set_error("asr_cmvn: utterance %d has no rows", i); return ASR_ERR_ARG; }
+        roff[i + 1] = roff[i] + h_L[i];
+        lmax = std::max(lmax, (int)h_L[i]);
+    }
+    ASR_CUDA(cudaMemcpyAsync(w.d_featrow_off, roff, sizeof(int) * (B + 1), cudaMemcpyHostToDevice, st));
+    ASR_CUDA(cudaStreamSynchronize(st));                       // the staging area is reused
+    ASR_TRY(launch_cmvn(h, d_feats, w.d_featrow_off, B, lmax, eps, d_out, st));
     ASR_CUDA(cudaStreamSynchronize(st));
     return ASR_OK;
 }
@@ -966,13 +998,13 @@ int asr_beam_trace(asr_handle* h, float* h_cand_score, int32_t* h_cand_beam, int
 
 static int issue_prefetch(asr_handle* h, int slot);
 
-int asr_transcribe_device(asr_handle* h, const float* d_pcm, const int64_t* h_pcm_off, int B, int k, int max_len,
-                          float temperature, int second_pass, double lm_weight, double length_weight,
-                          int32_t* h_tokens, int32_t* h_len, float* h_score, void* stream) {
+int asr_transcribe_device_pcm(asr_handle* h, const void* d_pcm, int format, float cmvn_eps, const int64_t* h_pcm_off,
+                              int B, int k, int max_len, float temperature, int second_pass, double lm_weight,
+                              double length_weight, int32_t* h_tokens, int32_t* h_len, float* h_score, void* stream) {
     if (!h || !d_pcm || !h_pcm_off) { set_error("asr_transcribe: NULL argument"); return ASR_ERR_ARG; }
     cudaStream_t st = (cudaStream_t)stream;
     std::vector<int32_t> L(B);
-    ASR_TRY(features_device(h, d_pcm, h_pcm_off, B, L.data(), 1, true, h->ws.xpack, st));
+    ASR_TRY(features_device(h, d_pcm, format, h_pcm_off, B, L.data(), 1, cmvn_eps, true, h->ws.xpack, st));
     for (int sl = 0; sl < 2; ++sl) ASR_TRY(issue_prefetch(h, sl));     // next batch's PCM copy overlaps this batch
     ASR_TRY(run_encoder(h, 3, st));
     ASR_TRY(run_keys(h, st));
@@ -985,11 +1017,21 @@ int asr_transcribe_device(asr_handle* h, const float* d_pcm, const int64_t* h_pc
     return fetch_results(h, B, max_len, h_tokens, h_len, h_score, nullptr, st);
 }
 
+int asr_transcribe_device(asr_handle* h, const float* d_pcm, const int64_t* h_pcm_off, int B, int k, int max_len,
+                          float temperature, int second_pass, double lm_weight, double length_weight,
+                          int32_t* h_tokens, int32_t* h_len, float* h_score, void* stream) {
+    return asr_transcribe_device_pcm(h, d_pcm, ASR_PCM_F32, 1e-6f, h_pcm_off, B, k, max_len, temperature, second_pass,
+                                     lm_weight, length_weight, h_tokens, h_len, h_score, stream);
+}
+
+static inline size_t pcm_sample_bytes(int format) { return format == ASR_PCM_S16 ? 2 : 4; }
+
 // Start the host->device copy of a batch's PCM on the handle's copy stream (double-buffered device
 // staging) so that it overlaps the decode of the batch before it; the asr_transcribe call for the same
 // host buffer then waits on the copy's event instead of copying.
-int asr_prefetch_pcm(asr_handle* h, const float* h_pcm, const int64_t* h_pcm_off, int B) {
+int asr_prefetch_pcm_fmt(asr_handle* h, const void* h_pcm, int format, const int64_t* h_pcm_off, int B) {
     if (!h || !h_pcm || !h_pcm_off || B <= 0) { set_error("asr_prefetch_pcm: bad argument"); return ASR_ERR_ARG; }
+    if (format != ASR_PCM_F32 && format != ASR_PCM_S16) { set_error("unknown PCM format %d", format); return ASR_ERR_ARG; }
     Workspace& w = h->ws;
     const int64_t n = h_pcm_off[B] - h_pcm_off[0];
     if (!w.pcm || n > w.max_samples) { set_error("batch has more samples than reserved"); return ASR_ERR_CAPACITY; }
@@ -1005,35 +1047,44 @@ int asr_prefetch_pcm(asr_handle* h, const float* h_pcm, const int64_t* h_pcm_off
     // The copy itself is issued by the next asr_transcribe call AFTER its own small metadata uploads:
     // copy engines are FIFO, and a 300 MB copy queued first would hold those (synchronous) uploads - and
     // with them the whole batch - back by its full duration (measured: no overlap gain at all).
-    h->pre_src[slot] = h_pcm + h_pcm_off[0];
+    h->pre_src[slot] = static_cast<const char*>(h_pcm) + pcm_sample_bytes(format) * (size_t)h_pcm_off[0];
     h->pre_n[slot] = n;
+    h->pre_fmt[slot] = format;
     h->pre_issued[slot] = false;
     return ASR_OK;
 }
 
+int asr_prefetch_pcm(asr_handle* h, const float* h_pcm, const int64_t* h_pcm_off, int B) {
+    return asr_prefetch_pcm_fmt(h, h_pcm, ASR_PCM_F32, h_pcm_off, B);
+}
+
 static int issue_prefetch(asr_handle* h, int slot) {
     if (!h->pre_src[slot] || h->pre_issued[slot]) return ASR_OK;
-    ASR_CUDA(cudaMemcpyAsync(h->ws.pcm_pre[slot], h->pre_src[slot], sizeof(float) * (size_t)h->pre_n[slot],
+    ASR_CUDA(cudaMemcpyAsync(h->ws.pcm_pre[slot], h->pre_src[slot],
+                             pcm_sample_bytes(h->pre_fmt[slot]) * (size_t)h->pre_n[slot],
                              cudaMemcpyHostToDevice, h->copy_stream));
     ASR_CUDA(cudaEventRecord(h->pre_ev[slot], h->copy_stream));
     h->pre_issued[slot] = true;
     return ASR_OK;
 }
 
-int asr_transcribe(asr_handle* h, const float* h_pcm, const int64_t* h_pcm_off, int B, int k, int max_len,
-                   float temperature, int second_pass, double lm_weight, double length_weight,
-                   int32_t* h_tokens, int32_t* h_len, float* h_score, void* stream) {
+int asr_transcribe_pcm(asr_handle* h, const void* h_pcm, int format, float cmvn_eps, const int64_t* h_pcm_off, int B,
+                       int k, int max_len, float temperature, int second_pass, double lm_weight,
+                       double length_weight, int32_t* h_tokens, int32_t* h_len, float* h_score, void* stream) {
     if (!h || !h_pcm || !h_pcm_off) { set_error("asr_transcribe: NULL argument"); return ASR_ERR_ARG; }
+    if (format != ASR_PCM_F32 && format != ASR_PCM_S16) { set_error("unknown PCM format %d", format); return ASR_ERR_ARG; }
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t n = h_pcm_off[B] - h_pcm_off[0];
     if (n > h->ws.max_samples) { set_error("batch has more samples than reserved"); return ASR_ERR_CAPACITY; }
     std::vector<int64_t> off(B + 1);
     for (int i = 0; i <= B; ++i) off[i] = h_pcm_off[i] - h_pcm_off[0];
-    const float* d_pcm = h->ws.pcm;
+    const size_t sb = pcm_sample_bytes(format);
+    const char* src = static_cast<const char*>(h_pcm) + sb * (size_t)h_pcm_off[0];
+    const void* d_pcm = h->ws.pcm;
     int hit = -1;
     for (int sl = 0; sl < 2; ++sl) {          // oldest outstanding prefetch of this buffer first
         const int c = (int)((h->pre_count + sl) & 1);
-        if (h->pre_src[c] == h_pcm + h_pcm_off[0] && h->pre_n[c] == n) { hit = c; break; }
+        if (h->pre_src[c] == src && h->pre_n[c] == n && h->pre_fmt[c] == format) { hit = c; break; }
     }
     static const bool dbg_pre = getenv("ASR_B200_PREFETCH_DBG") != nullptr;
     if (dbg_pre) fprintf(stderr, "[prefetch] transcribe: %s (slot %d, event %s)\n", hit >= 0 ? "hit" : "miss", hit,
@@ -1044,10 +1095,17 @@ int asr_transcribe(asr_handle* h, const float* h_pcm, const int64_t* h_pcm_off, 
         d_pcm = h->ws.pcm_pre[hit];
         h->pre_src[hit] = nullptr;
     } else {
-        ASR_CUDA(cudaMemcpyAsync(h->ws.pcm, h_pcm + h_pcm_off[0], sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, st));
+        ASR_CUDA(cudaMemcpyAsync(h->ws.pcm, src, sb * (size_t)n, cudaMemcpyHostToDevice, st));
     }
-    return asr_transcribe_device(h, d_pcm, off.data(), B, k, max_len, temperature, second_pass, lm_weight,
-                                 length_weight, h_tokens, h_len, h_score, stream);
+    return asr_transcribe_device_pcm(h, d_pcm, format, cmvn_eps, off.data(), B, k, max_len, temperature, second_pass,
+                                     lm_weight, length_weight, h_tokens, h_len, h_score, stream);
+}
+
+int asr_transcribe(asr_handle* h, const float* h_pcm, const int64_t* h_pcm_off, int B, int k, int max_len,
+                   float temperature, int second_pass, double lm_weight, double length_weight,
+                   int32_t* h_tokens, int32_t* h_len, float* h_score, void* stream) {
+    return asr_transcribe_pcm(h, h_pcm, ASR_PCM_F32, 1e-6f, h_pcm_off, B, k, max_len, temperature, second_pass,
+                              lm_weight, length_weight, h_tokens, h_len, h_score, stream);
 }
 
 int64_t asr_launch_count(asr_handle* h, int reset) {

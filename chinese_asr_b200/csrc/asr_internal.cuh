@@ -171,6 +171,13 @@ struct PackedWeights {
     float* emb_proj = nullptr;           // [5004, 2048] E' = embedding * W_ih[:, :256]^T (gate-interleaved columns)
 };
 
+// token id -> Unicode code points of int2word[id] (asr_set_vocab), for the device edit distance (wer.cu)
+struct VocabChars {
+    int* d_cp = nullptr;
+    int* d_off = nullptr;
+    int V = 0, max_chars = 0;
+};
+
 struct LmTables {
     float* uni_logp = nullptr;
     float* uni_bo = nullptr;
@@ -282,10 +289,12 @@ struct asr_handle {
     asr::FeatureConsts fc;
     asr::PackedWeights w;
     asr::LmTables lm;
+    asr::VocabChars vocab;
     asr::Workspace ws;
     asr::BatchMeta meta;
     bool encoded = false;
     int last_k = 0, last_steps = 0, last_B = 0;
+    int last_out_ld = 0;         // row stride of ws.out_tokens after the last decode (its max_len)
     int64_t launches = 0;
     bool timing = false;
     int gemm_mode = 0;           // 0 = CUDA-core fp32 FMA, 1 = tcgen05 3xTF32
@@ -297,8 +306,9 @@ struct asr_handle {
     cudaStream_t graph_stream = nullptr;    // blocking stream standing in for the legacy stream (not capturable)
     cudaStream_t copy_stream = nullptr;     // asr_prefetch_pcm: H2D copies overlapping the previous batch
     cudaEvent_t pre_ev[2] = {};
-    const float* pre_src[2] = {};           // host address a staged copy came from (nullptr = free / consumed)
+    const void* pre_src[2] = {};            // host address a staged copy came from (nullptr = free / consumed)
     int64_t pre_n[2] = {};
+    int pre_fmt[2] = {};                    // asr_pcm_format of the staged samples
     bool pre_issued[2] = {};                // the copy has been enqueued (it is issued behind the next batch's uploads)
     uint64_t pre_count = 0;
     bool enc_split_ready = false;  // ws.a_hi / a_lo hold the split of `enc` (written by the last recurrence)
@@ -315,12 +325,15 @@ namespace asr {
 
 // ---- features.cu -----------------------------------------------------------------------------
 int build_feature_consts(asr_handle* h, const asr_feature_consts* fc);
-int launch_logmel(asr_handle* h, const float* d_pcm, const long long* d_pcm_off,
+int launch_logmel(asr_handle* h, const void* d_pcm, int format, const long long* d_pcm_off,
                   const int* d_frame_off, int B, int total_frames, float* d_mel, cudaStream_t st);
 // out_rowmap: feature row (utterance-major, original order) -> output row; nullptr = identity
 int launch_delta_cmvn(asr_handle* h, const float* d_mel, const int* d_frame_off,
-                      const int* d_featrow_off, int B, int max_rows_per_utt, int normalise,
+                      const int* d_featrow_off, int B, int max_rows_per_utt, int normalise, float eps,
                       const int* out_rowmap, float* d_out, cudaStream_t st);
+// AudioLoader.batch_audio (data.py:513-518) on features that already exist
+int launch_cmvn(asr_handle* h, const float* d_in, const int* d_featrow_off, int B, int max_rows_per_utt,
+                float eps, float* d_out, cudaStream_t st);
 
 // ---- encoder.cu ------------------------------------------------------------------------------
 int launch_pack_rows(asr_handle* h, const float* src, const int* rowmap, int64_t rows, int width,

@@ -28,8 +28,14 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
 constexpr int kFramesPerCta = 8;      // one warp per frame
 constexpr int kFrameRounds = 4;       // frames per warp: the twiddle / window tables are staged once per 32 frames
 
+// PCM sample as the float32 soundfile.read(dtype='float32') hands the reference (data.py:111): float32 files as
+// stored, 16-bit files as x / 32768 (exact: a power of two), so both sample types give bit-identical frames.
+__device__ __forceinline__ float pcm_sample(const float* x, int i) { return x[i]; }
+__device__ __forceinline__ float pcm_sample(const short* x, int i) { return (float)x[i] * (1.0f / 32768.0f); }
+
+template <typename S>
 __global__ void __launch_bounds__(256)
-logmel_kernel(const float* __restrict__ pcm, const long long* __restrict__ pcm_off,
+logmel_kernel(const S* __restrict__ pcm, const long long* __restrict__ pcm_off,
               const int* __restrict__ frame_off, int B, int total_frames,
               const float* __restrict__ g_window, const float2* __restrict__ g_tw256,
               const float2* __restrict__ g_tw512, const int* __restrict__ mel_start,
@@ -61,7 +67,7 @@ logmel_kernel(const float* __restrict__ pcm, const long long* __restrict__ pcm_o
     }
     const int u = lo;
     const int t = gf - frame_off[u];
-    const float* x = pcm + pcm_off[u] + (long long)t * kHop;
+    const S* x = pcm + pcm_off[u] + (long long)t * kHop;
 
     float2* a = s_a[warp];
     float2* b = s_b[warp];
@@ -73,7 +79,7 @@ logmel_kernel(const float* __restrict__ pcm, const long long* __restrict__ pcm_o
         const int s = 2 * n;
         float2 z = make_float2(0.f, 0.f);
         if (s >= kWinOff && s < kWinOff + kWin) {   // kWinOff, kWin even -> both samples inside
-            const float x0 = x[s], x1 = x[s + 1], x2 = x[s + 2];
+            const float x0 = pcm_sample(x, s), x1 = pcm_sample(x, s + 1), x2 = pcm_sample(x, s + 2);
             const float y0 = __fsub_rn(x1, __fmul_rn(preemph, x0));
             const float y1 = __fsub_rn(x2, __fmul_rn(preemph, x1));
             z.x = y0 * s_win[s - kWinOff];
@@ -220,7 +226,7 @@ feat_stats_kernel(const float* __restrict__ mel, const int* __restrict__ frame_o
 // pass 2: recompute the taps from the staged log-mel rows, normalise, write the [L, 720] rows once
 __global__ void __launch_bounds__(960)
 feat_write_kernel(const float* __restrict__ mel, const int* __restrict__ frame_off,
-                  const int* __restrict__ featrow_off, Taps taps, int normalise,
+                  const int* __restrict__ featrow_off, Taps taps, int normalise, float eps,
                   const double2* __restrict__ partial, const int* __restrict__ out_rowmap,
                   float* __restrict__ out) {
     __shared__ __align__(16) float s_mel[kSubFrames * kMel];
@@ -234,7 +240,7 @@ feat_write_kernel(const float* __restrict__ mel, const int* __restrict__ frame_o
     const int g0 = blockIdx.y * kSubRows;
     if (g0 >= L) return;
     if (normalise && ty < 3) {
-        // (x - mean) / (std + 1e-6) per column with the unbiased std (main.py:37)
+        // (x - mean) / (std + eps) per column with the unbiased std (eps 1e-6 main.py:37, 1e-7 data.py:517)
         const int col = ty * 240 + x;
         double tsum = 0.0, tsq = 0.0;
         for (int ch = 0; ch < kStatChunks; ++ch) {
@@ -246,7 +252,7 @@ feat_write_kernel(const float* __restrict__ mel, const int* __restrict__ frame_o
         double var = (tsq - tsum * mean) / (double)(L - 1);
         if (var < 0.0) var = 0.0;
         s_mean[col] = (float)mean;
-        s_den[col] = (float)sqrt(var) + 1e-6f;
+        s_den[col] = (float)sqrt(var) + eps;
     }
     // (delta_rows starts with a barrier: s_mean / s_den are visible before the first sink call)
     delta_rows(mel + (size_t)f0 * kMel, T, g0, min(L, g0 + kSubRows), taps, s_mel,
@@ -255,6 +261,69 @@ feat_write_kernel(const float* __restrict__ mel, const int* __restrict__ frame_o
                    const int row = out_rowmap ? out_rowmap[r0 + g] : (r0 + g);
                    out[(size_t)row * kFeat + col] = normalise ? (v - s_mean[col]) / s_den[col] : v;
                });
+}
+
+// ---------------------------------------------------------------------------------------------
+// AudioLoader.batch_audio (data.py:513-518): instance normalisation of features that already exist
+// ([sum L, 720], utterance-major), eps = 1e-7.  Same two-pass shape as above: fixed-order double
+// partial sums per quarter of the rows (deterministic), then one read + one write of every row.
+__global__ void __launch_bounds__(720)
+cmvn_stats_kernel(const float* __restrict__ x, const int* __restrict__ featrow_off,
+                  double2* __restrict__ partial) {
+    const int u = blockIdx.x, ch = blockIdx.y, col = threadIdx.x;
+    const int r0 = featrow_off[u];
+    const int L = featrow_off[u + 1] - r0;
+    const int per = (L + kStatChunks - 1) / kStatChunks;
+    const int ga = min(L, ch * per), gb = min(L, ga + per);
+    double s = 0.0, q = 0.0;
+    const float* p = x + (size_t)(r0 + ga) * kFeat + col;
+    int g = ga;
+    for (; g + 4 <= gb; g += 4, p += 4 * kFeat) {       // 4 independent loads in flight per thread
+        const float a = p[0], b = p[kFeat], c = p[2 * kFeat], d = p[3 * kFeat];
+        s += (double)a; q += (double)a * a;
+        s += (double)b; q += (double)b * b;
+        s += (double)c; q += (double)c * c;
+        s += (double)d; q += (double)d * d;
+    }
+    for (; g < gb; ++g, p += kFeat) { const float a = p[0]; s += (double)a; q += (double)a * a; }
+    partial[((size_t)u * kStatChunks + ch) * kFeat + col] = make_double2(s, q);
+}
+
+__global__ void __launch_bounds__(720)
+cmvn_apply_kernel(const float* __restrict__ x, const int* __restrict__ featrow_off, float eps,
+                  const double2* __restrict__ partial, float* __restrict__ out) {
+    const int u = blockIdx.x, col = threadIdx.x;
+    const int r0 = featrow_off[u];
+    const int L = featrow_off[u + 1] - r0;
+    const int g0 = blockIdx.y * kSubRows;
+    if (g0 >= L) return;
+    double tsum = 0.0, tsq = 0.0;
+    for (int ch = 0; ch < kStatChunks; ++ch) {
+        const double2 pr = partial[((size_t)u * kStatChunks + ch) * kFeat + col];
+        tsum += pr.x;
+        tsq += pr.y;
+    }
+    const double mean_d = tsum / (double)L;
+    double var = (tsq - tsum * mean_d) / (double)(L - 1);      // L == 1 -> NaN, like torch.std
+    if (var < 0.0) var = 0.0;
+    const float mean = (float)mean_d, den = (float)sqrt(var) + eps;
+    const int g1 = min(L, g0 + kSubRows);
+    for (int g = g0; g < g1; ++g) {
+        const size_t i = (size_t)(r0 + g) * kFeat + col;
+        out[i] = (x[i] - mean) / den;
+    }
+}
+
+int launch_cmvn(asr_handle* h, const float* d_in, const int* d_featrow_off, int B, int max_rows_per_utt,
+                float eps, float* d_out, cudaStream_t st) {
+    cmvn_stats_kernel<<<dim3(B, kStatChunks), kFeat, 0, st>>>(d_in, d_featrow_off,
+                                                              reinterpret_cast<double2*>(h->ws.feat_partial));
+    ASR_CHECK_LAUNCH();
+    cmvn_apply_kernel<<<dim3(B, (max_rows_per_utt + kSubRows - 1) / kSubRows), kFeat, 0, st>>>(
+        d_in, d_featrow_off, eps, reinterpret_cast<const double2*>(h->ws.feat_partial), d_out);
+    ASR_CHECK_LAUNCH();
+    h->launches += 2;
+    return ASR_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -300,22 +369,27 @@ int build_feature_consts(asr_handle* h, const asr_feature_consts* fc) {
     return ASR_OK;
 }
 
-int launch_logmel(asr_handle* h, const float* d_pcm, const long long* d_pcm_off,
+int launch_logmel(asr_handle* h, const void* d_pcm, int format, const long long* d_pcm_off,
                   const int* d_frame_off, int B, int total_frames, float* d_mel, cudaStream_t st) {
     if (total_frames <= 0) return ASR_OK;
     const FeatureConsts& c = h->fc;
     const int per_cta = kFramesPerCta * kFrameRounds;
     const int grid = (total_frames + per_cta - 1) / per_cta;
-    logmel_kernel<<<grid, 256, 0, st>>>(d_pcm, d_pcm_off, d_frame_off, B, total_frames, c.window,
-                                        c.tw256, c.tw512, c.mel_start, c.mel_len, c.mel_w,
-                                        c.mel_maxw, c.preemph, d_mel);
+    if (format == ASR_PCM_S16)
+        logmel_kernel<short><<<grid, 256, 0, st>>>(static_cast<const short*>(d_pcm), d_pcm_off, d_frame_off, B,
+                                                   total_frames, c.window, c.tw256, c.tw512, c.mel_start,
+                                                   c.mel_len, c.mel_w, c.mel_maxw, c.preemph, d_mel);
+    else
+        logmel_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(d_pcm), d_pcm_off, d_frame_off, B,
+                                                   total_frames, c.window, c.tw256, c.tw512, c.mel_start,
+                                                   c.mel_len, c.mel_w, c.mel_maxw, c.preemph, d_mel);
     ASR_CHECK_LAUNCH();
     h->launches++;
     return ASR_OK;
 }
 
 int launch_delta_cmvn(asr_handle* h, const float* d_mel, const int* d_frame_off,
-                      const int* d_featrow_off, int B, int max_rows_per_utt, int normalise,
+                      const int* d_featrow_off, int B, int max_rows_per_utt, int normalise, float eps,
                       const int* out_rowmap, float* d_out, cudaStream_t st) {
     Taps t;
     for (int i = 0; i < 27; ++i) t.w[i] = h->fc.taps[i];
@@ -327,7 +401,7 @@ int launch_delta_cmvn(asr_handle* h, const float* d_mel, const int* d_frame_off,
         h->launches++;
     }
     feat_write_kernel<<<dim3(B, (max_rows_per_utt + kSubRows - 1) / kSubRows), block, 0, st>>>(
-        d_mel, d_frame_off, d_featrow_off, t, normalise, reinterpret_cast<const double2*>(h->ws.feat_partial),
+        d_mel, d_frame_off, d_featrow_off, t, normalise, eps, reinterpret_cast<const double2*>(h->ws.feat_partial),
         out_rowmap, d_out);
     ASR_CHECK_LAUNCH();
     h->launches++;

@@ -3,7 +3,12 @@
 Same names and argument meaning as the reference (data.py:21-57 create_fb_matrix, :84-106 MelScale,
 :109-121 fast_read, :167-280 get_log_mel, :371-382 AudioBase), but get_log_mel runs the fused
 CUDA kernels (csrc/features.cu) through the C ABI and returns a CUDA tensor.  The host only builds
-the constant tables (filterbank, window, delta taps) once, exactly as AudioBase does."""
+the constant tables (filterbank, window, delta taps) once, exactly as AudioBase does.
+
+Batched front end: AudioDst / AudioLoader (data.py:385-540, eval and
+infer modes) hand whole batches of 16-bit PCM to the device - the samples travel as int16 and the
+log-mel kernel converts them, the instance normalisation of batch_audio (eps 1e-7, data.py:517) is
+fused into the feature kernels."""
 import math
 import os
 import pickle
@@ -74,6 +79,20 @@ def fast_read(path):
     return data
 
 
+def read_pcm(path):
+    """WAV samples as stored: int16 for 16-bit files (converted to float on the device, same values
+    as fast_read's x / 32768), float32 otherwise.  Channel 0 of multi-channel files."""
+    with wave.open(path, 'rb') as w:
+        rate, width, ch, n = w.getframerate(), w.getsampwidth(), w.getnchannels(), w.getnframes()
+        raw = w.readframes(n)
+    if rate != gpd['sample_rate']:
+        print(f'[WARN] rate={rate}, path={path}')
+    if width == 2:
+        data = np.frombuffer(raw, dtype='<i2')
+        return data.reshape(-1, ch)[:, 0].copy() if ch > 1 else data
+    return fast_read(path)
+
+
 class AudioBase(object):
     """Vocabulary + feature constants (data.py:371-382).  dict.pkl is read from `dict_path`
     (default: ./dict.pkl like the reference, then $ASR_DICT_PKL)."""
@@ -118,5 +137,106 @@ def get_log_mel(training, file_path, ms, window, data_aug=False, engine=None):
     eng = engine or _default_engine
     if eng is None:
         raise RuntimeError("get_log_mel needs a loaded Model (Model.load) to own the device handle")
-    pcm = fast_read(file_path) if isinstance(file_path, str) else np.asarray(file_path, dtype=np.float32)
-    return eng.features([pcm], normalise=False)[0]
+    return eng.features([_waveform(file_path)], normalise=False)[0]
+
+
+def _waveform(src):
+    """WAV path or array -> int16 (as stored; converted on the device) or float32 samples."""
+    if isinstance(src, str):
+        return read_pcm(src)
+    a = np.asarray(src)
+    return a if a.dtype == np.int16 else a.astype(np.float32)
+
+
+# ---------------------------------------------------------------------------------------------
+# batched front end: AudioDst / AudioLoader (data.py:385-540), eval and infer modes
+
+class AudioDst(object):
+    """data.py:392-459 without the training branch.  Items are (waveform, text_int) or (waveform,):
+    the waveform stays raw (int16 as stored) because the features of a whole batch are computed in
+    one pass on the device by AudioLoader; `feature(idx)` gives the reference's per-item result."""
+
+    def __init__(self, audio_base, mode='infer', dev_or_test=None, path_list=None, text_list=None):
+        assert mode in ('train', 'eval', 'infer'), "mode must be train, eval or infer"
+        if mode == 'train':
+            raise NotImplementedError("training data pipeline (augmentation, TrainSampler) is outside the inference path")
+        if path_list is None:
+            raise ValueError("path_list is required (the AISHELL manifests of AudioBase are not part of this package)")
+        if text_list is not None:
+            assert len(text_list) == len(path_list)
+        else:
+            assert mode == 'infer'
+        self.path_list = path_list
+        self.text_list = text_list
+        self.word2int = audio_base.word2int
+        self.data_aug = False
+        self.audio_base = audio_base
+        self.mode = mode
+
+    def __len__(self):
+        return len(self.path_list)
+
+    def _text_int(self, idx):
+        text = self.text_list[idx]
+        return [self.word2int.get(ele, self.word2int['<unk>']) for ele in text]      # data.py:455
+
+    def __getitem__(self, idx):
+        p = self.path_list[idx]
+        pcm = _waveform(p)
+        if self.text_list is not None:
+            return pcm, self._text_int(idx)
+        return (pcm,)
+
+    def feature(self, idx, engine=None):
+        """What the reference's __getitem__ returns first: get_log_mel of item idx (un-normalised)."""
+        return get_log_mel(False, self.path_list[idx], self.audio_base.ms, self.audio_base.window, False, engine)
+
+
+class AudioLoader(object):
+    """data.py:462-540 for eval / infer: `.loader` iterates (t, lens, text) batches of
+    gpd['eval_batch_size'] items in order - t: list of normalised [L_i, 720] CUDA tensors,
+    lens: IntTensor, text: list of int lists or None."""
+
+    def __init__(self, dst, engine=None, batch_size=None):
+        self.dst = dst
+        self.mode = dst.mode
+        self.bsz = batch_size or gpd.get('eval_batch_size', 256)
+        self.engine = engine
+        self.loader = self
+
+    def __len__(self):
+        return (len(self.dst) + self.bsz - 1) // self.bsz
+
+    def __iter__(self):
+        eng = self.engine or _default_engine
+        if eng is None:
+            raise RuntimeError("AudioLoader needs a loaded Model (Model.load) to own the device handle")
+        for b0 in range(0, len(self.dst), self.bsz):
+            items = [self.dst[i] for i in range(b0, min(len(self.dst), b0 + self.bsz))]
+            pcms = [it[0] for it in items]
+            if not all(p.dtype == np.int16 for p in pcms):
+                pcms = [p.astype(np.float32) / 32768.0 if p.dtype == np.int16 else np.asarray(p, np.float32) for p in pcms]
+            # get_log_mel of every item + batch_audio's normalisation (eps 1e-7), one pass on the device
+            t = eng.features(pcms, normalise=bool(gpd['normalize']), eps=1e-7)
+            lens = torch.IntTensor([x.size(0) for x in t])
+            text = [it[1] for it in items] if len(items[0]) == 2 else None
+            yield t, lens, text
+
+    @staticmethod
+    def collate_fn(batch, engine=None):
+        """data.py:496-507 on items that already carry features: [(feature, text_int)] | [(feature,)]."""
+        t, lens = AudioLoader.batch_audio([ele[0] for ele in batch], engine)
+        if len(batch[0]) == 2:
+            return t, lens, [ele[1] for ele in batch]
+        return t, lens, None
+
+    @staticmethod
+    def batch_audio(batch, engine=None):
+        """data.py:509-518 (RNN encoders: the batch stays a list): instance normalisation on the device."""
+        eng = engine or _default_engine
+        if eng is None:
+            raise RuntimeError("batch_audio needs a loaded Model (Model.load) to own the device handle")
+        lens = torch.IntTensor([t.size(0) for t in batch])
+        if gpd['normalize']:
+            batch = eng.cmvn(batch, eps=1e-7)
+        return batch, lens

@@ -46,6 +46,7 @@ gpd = {
     # added at run time by main.py:123-124
     'use_cuda': True,
     'eval_num_workers': 0,
+    'eval_batch_size': 256,      # gpd.py:118
 }
 
 _FROZEN = {

@@ -12,7 +12,7 @@ import torch
 
 import numpy as np
 
-from .data import AudioBase, fast_read
+from .data import AudioBase, _waveform
 from .gpd import gpd
 from .lm import NGramLM
 from .model import Model
@@ -20,7 +20,7 @@ from .model import Model
 
 def parse(path, model, audio_base, lm_model, bw):
     """main.py:27-65.  `path`: 16 kHz mono WAV file (or a float32 waveform array)."""
-    pcm = fast_read(path) if isinstance(path, str) else np.asarray(path, dtype=np.float32)
+    pcm = _waveform(path)        # fast_read (data.py:109): 16-bit samples are converted on the device
     # get_log_mel + per-utterance CMVN (main.py:36-37), fused in the feature kernels
     data = model.features([pcm], normalise=True)[0]
     lens = torch.tensor([data.shape[0]])

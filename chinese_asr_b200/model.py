@@ -144,10 +144,12 @@ class Model(object):
         self._reserved = want
 
     # ---- features (data.py:167-280 + main.py:37) -------------------------------------------------
-    def features(self, pcms, normalise=True):
-        """list of float32 waveforms -> list of CUDA tensors [L_i, 720]."""
+    def features(self, pcms, normalise=True, eps=1e-6):
+        """list of waveforms (float32, or int16 as stored in 16-bit WAV files) -> list of CUDA tensors
+        [L_i, 720].  eps: CMVN epsilon, 1e-6 = main.py:37, 1e-7 = AudioLoader.batch_audio (data.py:517)."""
         self._need()
-        pcms = [np.ascontiguousarray(p, dtype=np.float32) for p in pcms]
+        s16 = len(pcms) > 0 and all(isinstance(p, np.ndarray) and p.dtype == np.int16 for p in pcms)
+        pcms = [np.ascontiguousarray(p, dtype=np.int16 if s16 else np.float32) for p in pcms]
         B = len(pcms)
         off = np.zeros(B + 1, dtype=np.int64)
         off[1:] = np.cumsum([len(p) for p in pcms])
@@ -157,14 +159,83 @@ class Model(object):
         d_pcm = torch.from_numpy(np.concatenate(pcms)).to(self.device)
         d_feats = torch.empty(max(rows, 1), 720, dtype=torch.float32, device=self.device)
         h_L = np.zeros(B, dtype=np.int32)
-        check(lib.asr_features(self._h, C.c_void_p(d_pcm.data_ptr()), off.ctypes.data_as(_cabi.c_int64_p), B,
-                               C.c_void_p(d_feats.data_ptr()), h_L.ctypes.data_as(_cabi.c_int32_p),
-                               1 if normalise else 0, self._stream()), "asr_features")
+        check(lib.asr_features_pcm(self._h, C.c_void_p(d_pcm.data_ptr()), _cabi.PCM_S16 if s16 else _cabi.PCM_F32,
+                                   off.ctypes.data_as(_cabi.c_int64_p), B, C.c_void_p(d_feats.data_ptr()),
+                                   h_L.ctypes.data_as(_cabi.c_int32_p), 1 if normalise else 0, float(eps),
+                                   self._stream()), "asr_features_pcm")
         out, r = [], 0
         for n in h_L.tolist():
             out.append(d_feats[r:r + n])
             r += n
         return out
+
+    def cmvn(self, feats, eps=1e-7):
+        """AudioLoader.batch_audio's instance normalisation (data.py:513-518) on the device:
+        list of [L_i, 720] tensors -> list of normalised CUDA tensors (views of one buffer)."""
+        self._need()
+        B = len(feats)
+        lens = np.ascontiguousarray([int(t.size(0)) for t in feats], dtype=np.int32)
+        for t in feats:
+            if t.dim() != 2 or t.size(1) != 720:
+                raise ValueError(f"feature tensor {tuple(t.shape)} is not [L, 720]")
+        self.reserve(B, int(lens.sum()), self._reserved[2] if self._reserved else 1,
+                     self._reserved[3] if self._reserved else 0)
+        x = torch.cat([t.to(self.device, torch.float32) for t in feats], dim=0).contiguous()
+        out = torch.empty_like(x)
+        check(lib.asr_cmvn(self._h, C.c_void_p(x.data_ptr()), lens.ctypes.data_as(_cabi.c_int32_p), B, float(eps),
+                           C.c_void_p(out.data_ptr()), self._stream()), "asr_cmvn")
+        res, r = [], 0
+        for n in lens.tolist():
+            res.append(out[r:r + n])
+            r += n
+        return res
+
+    # ---- character error rate (util.py:237-262) ----------------------------------------------------
+    def set_vocab(self, int2word):
+        """Upload int2word as code-point strings (asr_set_vocab) for the device edit distance."""
+        self._need()
+        if getattr(self, '_vocab_src', None) is int2word:
+            return
+        V = max(int2word) + 1
+        off = np.zeros(V + 1, dtype=np.int32)
+        cps = []
+        for t in range(V):
+            w = int2word.get(t, '')
+            cps.extend(ord(ch) for ch in w)
+            off[t + 1] = len(cps)
+        cp = np.ascontiguousarray(cps if cps else [0], dtype=np.int32)
+        check(lib.asr_set_vocab(self._h, cp.ctypes.data_as(_cabi.c_int32_p), off.ctypes.data_as(_cabi.c_int32_p), V),
+              "asr_set_vocab")
+        self._vocab_src = int2word
+
+    def wer(self, text, int2word, hyp=None):
+        """Per-utterance get_wer(pred, ref) (util.py:237-262, normalised by the reference length in
+        characters) on the device.  text: reference transcripts as token-id lists (what collate_fn
+        yields, data.py:503-504) or as strings; hyp: list of token-id lists, or None = the hypotheses
+        of the last decode call, where they lie on the device."""
+        self.set_vocab(int2word)
+        B = len(text)
+        refs = [t if isinstance(t, str) else ''.join(int2word[e] for e in t) for t in text]
+        roff = np.zeros(B + 1, dtype=np.int64)
+        roff[1:] = np.cumsum([len(t) for t in refs])
+        ref = np.ascontiguousarray([ord(ch) for t in refs for ch in t] or [0], dtype=np.int32)
+        dist = np.zeros(B, dtype=np.int32)
+        hch = np.zeros(B, dtype=np.int32)
+        i32 = _cabi.c_int32_p
+        if hyp is None:
+            hp, hl, ld = None, None, 0
+        else:
+            ld = max(1, max(len(x) for x in hyp))
+            ha = np.zeros((B, ld), dtype=np.int32)
+            hn = np.zeros(B, dtype=np.int32)
+            for i, x in enumerate(hyp):
+                ha[i, :len(x)] = x
+                hn[i] = len(x)
+            hp, hl = ha.ctypes.data_as(i32), hn.ctypes.data_as(i32)
+        check(lib.asr_wer(self._h, hp, hl, ld, ref.ctypes.data_as(i32), roff.ctypes.data_as(_cabi.c_int64_p), B,
+                          dist.ctypes.data_as(i32), hch.ctypes.data_as(i32), self._stream()), "asr_wer")
+        # an empty reference divides by zero in the reference; here: 1.0 if anything was predicted
+        return [d / len(r) if len(r) > 0 else float(n > 0) for d, r, n in zip(dist.tolist(), refs, hch.tolist())]
 
     # ---- encoder -----------------------------------------------------------------------------
     def _encode(self, data, lens, max_beam):
@@ -243,8 +314,8 @@ class Model(object):
                 score.append(float(accum[i]) / (int(tlen[i]) + int(fin[i])))      # model.py:593
         wer = None
         if text is not None:
-            text = [''.join([int2word[e] for e in ele]) for ele in text]
-            wer = np.mean([get_wer(pred, ref) for pred, ref in zip(pred_text, text)])
+            wer = np.mean(self.wer(text, int2word))        # hypotheses are scored where they lie (asr_wer)
+            text = [t if isinstance(t, str) else ''.join([int2word[e] for e in t]) for t in text]
         out = EvalOutput(pred_text=pred_text, score=score, text=text, wer=wer, n=B,
                          alignment=[align[s] for s in range(nsteps)],
                          audio_feat_len=torch.as_tensor(lens), text_len=torch.from_numpy(tlen.copy()))
@@ -308,11 +379,10 @@ class Model(object):
         tokens, tlen, score, info = self._beam(B, bmsz, second_pass, lm_weight, length_weight)
         outputs = [tokens[i, :tlen[i]].tolist() for i in range(B)]
         pred_text = [''.join([int2word[idx] for idx in ele]) for ele in outputs]
-        if text is not None:
-            text = [''.join([int2word[idx] for idx in ele]) for ele in text]
         wer = None
         if text is not None:
-            wer = np.mean([get_wer(pred, ref) for pred, ref in zip(pred_text, text)])
+            wer = np.mean(self.wer(text, int2word))        # hypotheses are scored where they lie (asr_wer)
+            text = [t if isinstance(t, str) else ''.join([int2word[e] for e in t]) for t in text]
         self.last_beam_info = dict(steps=int(info[0]), stopped_at=int(info[1]), fallback=int(info[2]),
                                    finished=int(info[3]), tokens=outputs)
         return EvalOutput(pred_text=pred_text, score=[float(s) for s in score], text=text, wer=wer, n=B,
@@ -346,13 +416,38 @@ class Model(object):
                                  bp.ctypes.data_as(i32), at.ctypes.data_as(i32), _cabi.fptr(fs)), "asr_beam_trace")
         return dict(cand_scores=cs, cand_beams=cb, cand_tokens=ct, backptr=bp, active_tokens=at, fin_scores=fs)
 
+    # ---- dataset loop (model.py:1370-1439 test_model) ------------------------------------------------
+    def test_model(self, loader, int2word, bw=None, second_pass=False, lm_model=None, lm_weight=0.0,
+                   length_weight=0.0):
+        """The reference's evaluation loop over an AudioLoader: per-batch WER weighted by batch size
+        (model.py:1411-1430), plus the sentence error rate it prints at the end (:1432-1437)."""
+        total_pred_text, total_text, wer_list = [], [], []
+        eval_nb, eval_wer = 0, 0.
+        for data, lens, text in getattr(loader, 'loader', loader):
+            if bw is None:
+                output = self.eval_one_batch_with_greedy(self.device, data, lens, int2word, text)
+            else:
+                output = self.eval_one_batch_with_beam(self.device, bw, data, lens, text, int2word,
+                                                       second_pass=second_pass, lm_model=lm_model,
+                                                       lm_weight=lm_weight, length_weight=length_weight)
+            eval_nb += lens.size(0)
+            eval_wer += output.wer * lens.size(0)
+            wer_list.append(output.wer)
+            total_pred_text.extend(output.pred_text)
+            total_text.extend(output.text)
+        eval_wer /= max(eval_nb, 1)
+        wrong = sum(1 for a, b in zip(total_pred_text, total_text) if a != b)
+        return dict(wer=float(eval_wer), n=eval_nb, wer_list=[float(w) for w in wer_list],
+                    error_rate=wrong / max(eval_nb, 1), pred_text=total_pred_text, text=total_text)
+
     # ---- fused path: PCM in, hypotheses out ---------------------------------------------------------
     def transcribe(self, pcm, offsets, bw=None, second_pass=False, lm_model=None, lm_weight=0.0,
-                   length_weight=0.0, int2word=None, resident=False):
+                   length_weight=0.0, int2word=None, resident=False, cmvn_eps=1e-6):
         """Whole path for a batch (parse() of main.py:27-65, batched): `pcm` is one float32 buffer
         (pinned host tensor / numpy array, or a CUDA tensor when resident=True) holding the
-        concatenated waveforms, `offsets` [B+1] sample offsets.  Returns (tokens, lens, scores)
-        numpy arrays, plus texts when int2word is given."""
+        concatenated waveforms, `offsets` [B+1] sample offsets.  An int16 buffer (16-bit WAV samples
+        as stored) is converted on the device.  Returns (tokens, lens, scores) numpy arrays, plus texts
+        when int2word is given."""
         self._need()
         off = np.ascontiguousarray(offsets, dtype=np.int64)
         B = off.shape[0] - 1
@@ -364,13 +459,15 @@ class Model(object):
         tokens = np.zeros((B, max_len), dtype=np.int32)
         tlen = np.zeros(B, dtype=np.int32)
         score = np.zeros(B, dtype=np.float32)
+        fmt = self._pcm_format(pcm)
         if resident:
-            fn, ptr = lib.asr_transcribe_device, pcm.data_ptr()
-            assert pcm.is_cuda and pcm.dtype == torch.float32
+            fn, ptr = lib.asr_transcribe_device_pcm, pcm.data_ptr()
+            assert pcm.is_cuda
         else:
-            fn = lib.asr_transcribe
+            fn = lib.asr_transcribe_pcm
             ptr = pcm.data_ptr() if isinstance(pcm, torch.Tensor) else pcm.ctypes.data
-        check(fn(self._h, C.c_void_p(ptr), off.ctypes.data_as(_cabi.c_int64_p), B, int(bw or 0), max_len,
+        check(fn(self._h, C.c_void_p(ptr), fmt, float(cmvn_eps), off.ctypes.data_as(_cabi.c_int64_p), B,
+                 int(bw or 0), max_len,
                  float(gpd['temperature']), 1 if second_pass else 0, float(lm_weight), float(length_weight),
                  tokens.ctypes.data_as(_cabi.c_int32_p), tlen.ctypes.data_as(_cabi.c_int32_p),
                  _cabi.fptr(score), self._stream()), "asr_transcribe")
@@ -392,7 +489,17 @@ class Model(object):
         self.reserve(B, max(rows, 1), max(bw or 1, 1), int(off[-1] - off[0]))
         ptr = pcm.data_ptr() if isinstance(pcm, torch.Tensor) else pcm.ctypes.data
         self._keep_prefetch = (pcm, off)           # the copy is asynchronous: keep the host buffer alive
-        check(lib.asr_prefetch_pcm(self._h, C.c_void_p(ptr), off.ctypes.data_as(_cabi.c_int64_p), B), "asr_prefetch_pcm")
+        check(lib.asr_prefetch_pcm_fmt(self._h, C.c_void_p(ptr), self._pcm_format(pcm),
+                                       off.ctypes.data_as(_cabi.c_int64_p), B), "asr_prefetch_pcm_fmt")
+
+    @staticmethod
+    def _pcm_format(pcm):
+        dt = str(pcm.dtype).replace('torch.', '')
+        if dt == 'float32':
+            return _cabi.PCM_F32
+        if dt == 'int16':
+            return _cabi.PCM_S16
+        raise TypeError(f"PCM buffer must be float32 or int16, not {dt}")
 
     def set_gemm_mode(self, mode):
         """'simt' (CUDA-core fp32), 'tc' (GEMM stages on tcgen05 3xTF32), 'rec' (only the encoder

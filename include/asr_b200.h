@@ -98,6 +98,24 @@ int asr_features(asr_handle* h, const float* d_pcm, const int64_t* h_pcm_off, in
 /* frame count helper: L for an utterance of n samples */
 int asr_num_frames(int64_t n_samples);
 
+/* Batched front end.  The reference reads every WAV with
+ * soundfile.read(path, dtype='float32') (fast_read, data.py:109-121), i.e. 16-bit files become
+ * x / 32768 on the host; here the 16-bit samples travel to the device as they are (half the
+ * host->device bytes) and the log-mel kernel converts them while loading - bit-identical frames. */
+enum asr_pcm_format {
+    ASR_PCM_F32 = 0,   /* float32 in [-1, 1) */
+    ASR_PCM_S16 = 1    /* little-endian int16, value / 32768 */
+};
+/* asr_features with a sample format and the CMVN epsilon spelled out: 1e-6 is main.py:37 (parse),
+ * 1e-7 is AudioLoader.batch_audio (data.py:517).  Offsets count samples, not bytes. */
+int asr_features_pcm(asr_handle* h, const void* d_pcm, int format, const int64_t* h_pcm_off, int B,
+                     float* d_feats, int32_t* h_L, int normalise, float cmvn_eps, void* stream);
+/* AudioLoader.batch_audio (data.py:509-518) for features that already exist on the device:
+ * d_out[r, c] = (d_feats[r, c] - mean_u[c]) / (std_u[c] + eps), per utterance u and column c,
+ * unbiased std.  d_feats / d_out: [sum h_L, 720] utterance-major; in-place is allowed. */
+int asr_cmvn(asr_handle* h, const float* d_feats, const int32_t* h_L, int B, float eps, float* d_out,
+             void* stream);
+
 /* RNNEncoder.forward + get_mask_for_softmax + get_initial_state + compute_key_value
  * (encoder.py:36-81, util.py:131-142, decoder.py:56-59, attention.py:67-78).
  * d_feats as produced by asr_features (utterance-major, original order).  The encoder memory,
@@ -158,6 +176,21 @@ int asr_decode_beam(asr_handle* h, int k, int max_len, float temperature, int se
 int asr_beam_trace(asr_handle* h, float* h_cand_score, int32_t* h_cand_beam, int32_t* h_cand_tok,
                    int32_t* h_backptr, int32_t* h_active_tok, float* h_fin_score);
 
+/* get_wer (util.py:237-262) as the decode drivers use it when `text` is given (model.py:595-598,
+ * 982-985): Levenshtein distance between the predicted and the reference STRING.  Strings are code
+ * point sequences: token t stands for h_codepoints[h_tok_off[t] .. h_tok_off[t+1]) (int2word[t];
+ * "<unk>" is five characters).  asr_set_vocab copies the table (dict.pkl, data.py:373). */
+int asr_set_vocab(asr_handle* h, const int32_t* h_codepoints, const int32_t* h_tok_off, int V);
+/* h_dist[B] = edit distance of every utterance; WER of the batch = mean over u of
+ * h_dist[u] / (h_ref_off[u+1] - h_ref_off[u]).  h_ref: the reference strings as code points,
+ * concatenated; h_ref_off[B+1].  h_hyp [B, hyp_ld] + h_hyp_len[B]: hypotheses as token ids, or
+ * h_hyp = NULL to score the hypotheses of the last decode / transcribe call on this handle where
+ * they lie on the device (no host round trip of the tokens).  h_hyp_chars (optional): length of
+ * every hypothesis string in characters. */
+int asr_wer(asr_handle* h, const int32_t* h_hyp, const int32_t* h_hyp_len, int hyp_ld,
+            const int32_t* h_ref, const int64_t* h_ref_off, int B, int32_t* h_dist,
+            int32_t* h_hyp_chars, void* stream);
+
 /* Whole path for one batch, host buffers in / host buffers out (parse() in main.py:27-65 for a
  * batch): H2D copy of the PCM, features, encoder, greedy (k = 0) or beam decode, D2H of the
  * hypotheses.  h_pcm should be pinned for the copy to be asynchronous. */
@@ -170,6 +203,18 @@ int asr_transcribe(asr_handle* h, const float* h_pcm, const int64_t* h_pcm_off, 
  * asr_transcribe call given the same h_pcm / offsets consumes the prefetched copy (it waits on the
  * copy's event instead of copying).  At most two prefetches may be outstanding. */
 int asr_prefetch_pcm(asr_handle* h, const float* h_pcm, const int64_t* h_pcm_off, int B);
+
+/* asr_transcribe / asr_prefetch_pcm / asr_transcribe_device with a sample format (enum asr_pcm_format)
+ * and the CMVN epsilon as arguments; the float32 entry points are these with ASR_PCM_F32, 1e-6. */
+int asr_transcribe_pcm(asr_handle* h, const void* h_pcm, int format, float cmvn_eps,
+                       const int64_t* h_pcm_off, int B, int k, int max_len, float temperature,
+                       int second_pass, double lm_weight, double length_weight, int32_t* h_tokens,
+                       int32_t* h_len, float* h_score, void* stream);
+int asr_prefetch_pcm_fmt(asr_handle* h, const void* h_pcm, int format, const int64_t* h_pcm_off, int B);
+int asr_transcribe_device_pcm(asr_handle* h, const void* d_pcm, int format, float cmvn_eps,
+                              const int64_t* h_pcm_off, int B, int k, int max_len, float temperature,
+                              int second_pass, double lm_weight, double length_weight,
+                              int32_t* h_tokens, int32_t* h_len, float* h_score, void* stream);
 
 /* Same, PCM already resident on the device (d_pcm); used for the HBM-resident throughput. */
 int asr_transcribe_device(asr_handle* h, const float* d_pcm, const int64_t* h_pcm_off, int B,

@@ -648,3 +648,90 @@ def beam_decode(weights, k, feats, lens, int2word=None, second_pass=False, lm_mo
         text = ["".join(int2word[t] for t in s) for s in tokens]
     return {"tokens": tokens, "score": scores, "pred_text": text, "nbest": nbest,
             "steps": step + 1, "stopped_at": stopped_at, "fallback": missing}
+
+
+# ----------------------------------------------------------------------------------------------
+# batched front end and error rate: the callers either side of
+# the hot path.  Pinned by tests/golden/ref_frontend.npz (tools/make_golden_frontend.py).
+
+def pcm_from_int16(x: np.ndarray) -> np.ndarray:
+    """fast_read (data.py:109-121): soundfile.read(path, dtype='float32') on a 16-bit PCM file.
+    soundfile is a third-party dependency absent from the reference tree and from this image
+    (unpinned, no requirements file); libsndfile's documented int16 -> float conversion is
+    x / 32768 (exact in float32)."""
+    return np.asarray(x, dtype=np.int16).astype(np.float32) / np.float32(32768.0)
+
+
+def synth_pcm_int16(seed: int, n_samples: int) -> np.ndarray:
+    """16-bit synthetic waveform: the float waveform of synth_pcm quantised like a WAV writer does."""
+    x = synth_pcm(seed, n_samples)
+    return np.clip(np.round(x * 32768.0), -32768, 32767).astype(np.int16)
+
+
+def batch_audio(batch: list, eps: float = 1e-7):
+    """AudioLoader.batch_audio (data.py:509-518) for the RNN encoders: instance normalisation of every
+    [L, 720] feature matrix with eps 1e-7 (main.py:37 uses 1e-6), lens as IntTensor."""
+    lens = torch.IntTensor([t.size(0) for t in batch])
+    return [cmvn(t, eps) for t in batch], lens
+
+
+def collate_fn(batch: list):
+    """AudioLoader.collate_fn (data.py:496-507): [(feature, text_int)] or [(feature,)] -> (t, lens, text)."""
+    t, lens = batch_audio([ele[0] for ele in batch])
+    text = [ele[1] for ele in batch] if len(batch[0]) == 2 else None
+    return t, lens, text
+
+
+def edit_distance(pred, ref) -> int:
+    """Unit-cost Levenshtein distance between two sequences: what get_wer (util.py:237-262) obtains
+    from python-Levenshtein's distance() (third party, absent, unpinned) and what the reference's own
+    get_wer_python (util.py:186-234) computes with one DP row."""
+    n, m = len(pred), len(ref)
+    if m == 0:
+        return n
+    if n == 0:
+        return m
+    dist = list(range(n + 1))
+    for i in range(1, m + 1):
+        pre = i
+        for j in range(1, n + 1):
+            if pred[j - 1] == ref[i - 1]:
+                cur = dist[j - 1]
+            else:
+                cur = min(pre, dist[j], dist[j - 1]) + 1
+            dist[j - 1] = pre
+            pre = cur
+        dist[n] = pre
+    return dist[n]
+
+
+def get_wer(pred: str, ref: str, normalize: bool = True):
+    """util.py:237-246 (return_tuple=False): distance / len(ref) over the characters of the strings."""
+    r = edit_distance(pred, ref)
+    return r / (len(ref) * 1.) if normalize else r
+
+
+def batch_wer(pred_tokens, ref_tokens, int2word):
+    """The decode drivers' WER (model.py:595-598, 982-985): strings are ''.join(int2word[t]); mean of
+    get_wer over the batch.  Returns (mean, per-utterance list)."""
+    per = []
+    for p, r in zip(pred_tokens, ref_tokens):
+        per.append(get_wer("".join(int2word[t] for t in p), "".join(int2word[t] for t in r)))
+    return float(np.mean(per)), per
+
+
+def synth_reference_text(seed: int, hyp_tokens, n_vocab: int = VOCAB):
+    """Seeded 'reference transcript' for WER tests: the hypothesis with random substitutions,
+    deletions and insertions (token ids >= 3 so that '<unk>' - five characters - occurs)."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for t in hyp_tokens:
+        r = rng.random()
+        if r < 0.15:
+            continue
+        out.append(int(rng.integers(3, n_vocab)) if r < 0.35 else int(t))
+        if rng.random() < 0.15:
+            out.append(int(rng.integers(3, n_vocab)))
+    if not out:
+        out.append(int(rng.integers(3, n_vocab)))
+    return out

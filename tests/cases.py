@@ -55,3 +55,34 @@ def load_golden():
     import os
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_golden.npz")
     return np.load(path, allow_pickle=False)
+
+
+# ---- rows either side of the hot path: 16-bit ingest, batch_audio, WER ----
+FRONTEND = dict(seeds=[801, 802, 803, 804], nsamp=[24000, 16001, 31000, 8000])
+
+
+def load_frontend_golden():
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_frontend.npz")
+    return np.load(path, allow_pickle=False)
+
+
+def wer_token_pairs():
+    """Seeded (hypothesis tokens, reference tokens) pairs: identical, edited, empty hypothesis,
+    specials ('<unk>' = five characters), the ' ' token, and a long reference."""
+    rng = np.random.default_rng(4321)
+    pairs = []
+    for i in range(10):
+        hyp = [int(t) for t in rng.integers(4, 5004, size=int(rng.integers(1, 41)))]
+        pairs.append((hyp, O.synth_reference_text(100 + i, hyp)))
+    pairs.append(([10, 11, 12], [10, 11, 12]))
+    pairs.append(([], [20, 21, 22, 23]))
+    pairs.append(([3, 30, 3, 31], [30, 3, 31, 781, 32]))
+    pairs.append(([40, 781, 41], [40, 41]))
+    pairs.append(([50, 51], [int(t) for t in rng.integers(4, 5004, size=150)]))
+    pairs.append(([int(t) for t in rng.integers(4, 5004, size=40)], [60]))
+    return pairs
+
+
+def wer_pairs(int2word):
+    return [("".join(int2word[t] for t in h), "".join(int2word[t] for t in r)) for h, r in wer_token_pairs()]

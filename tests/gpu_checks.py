@@ -384,3 +384,109 @@ def check_config_shape(B, k, seconds_list, lm_seed=None, wseed=1234, eos_bias=8.
         res["oracle_min_margin"] = float(min(tr["min_margin"]))
         res["nonempty"] = int(sum(1 for t in otexts if len(t) > 0))
     return res
+
+
+# ---------------------------------------------------------------------------------------------
+# rows either side of the hot path
+def check_frontend():
+    """16-bit ingest, loader CMVN (eps 1e-7), batch_audio / collate_fn, the AudioLoader pipeline."""
+    import wave
+    import tempfile
+    from tests.cases import FRONTEND, load_frontend_golden
+    from chinese_asr_b200 import data
+    g = load_frontend_golden()
+    w = O.make_weights(1234, "plain")
+    m = get_model((1234, "plain", None), w)
+    pcm16 = [O.synth_pcm_int16(s, n) for s, n in zip(FRONTEND["seeds"], FRONTEND["nsamp"])]
+    res = {}
+    raw16 = m.features(pcm16, normalise=False)                                  # int16 converted on the device
+    raw32 = m.features([O.pcm_from_int16(x) for x in pcm16], normalise=False)   # host conversion (fast_read)
+    res["s16_eq_f32_bitwise"] = int(all(torch.equal(a, b) for a, b in zip(raw16, raw32)))
+    fused = m.features(pcm16, normalise=True, eps=1e-7)                         # loader path: features + CMVN fused
+    normed, lens = data.AudioLoader.batch_audio([r.clone() for r in raw16], m)  # batch_audio on existing features
+    res["lens_ok"] = int(lens.dtype == torch.int32 and lens.tolist() == g["fe_lens"].tolist())
+    for i in range(len(pcm16)):
+        rows = g[f"fe{i}_rows"]
+        res[f"fe{i}_raw_vs_ref"] = maxabs(raw16[i][rows], g[f"fe{i}_raw"])
+        res[f"fe{i}_fused_vs_ref"] = maxabs(fused[i][rows], g[f"fe{i}_norm"])
+        res[f"fe{i}_batch_audio_vs_ref"] = maxabs(normed[i][rows], g[f"fe{i}_norm"])
+        res[f"fe{i}_batch_audio_vs_oracle"] = maxabs(normed[i], O.batch_audio([raw16[i].cpu()])[0][0])
+    t, l2, text = data.AudioLoader.collate_fn([(r, [1, 2]) for r in raw16], m)
+    res["collate_ok"] = int(text == [[1, 2]] * len(raw16) and all(torch.equal(a, b) for a, b in zip(t, normed)))
+    # eps really is an argument: 1e-6 (main.py:37) differs from 1e-7 and matches the oracle's cmvn
+    e6 = m.features(pcm16[:1], normalise=True, eps=1e-6)[0]
+    res["eps6_vs_oracle"] = maxabs(e6, O.cmvn(O.features(O.pcm_from_int16(pcm16[0]), normalise=False), 1e-6))
+    # the loader: WAV files on disk -> batches of (t, lens, text)
+    _, i2w = vocab()
+    w2i = vocab()[0]
+
+    class AB:
+        word2int, int2word = w2i, i2w
+    with tempfile.TemporaryDirectory() as d:
+        paths = []
+        for i, x in enumerate(pcm16):
+            p = os.path.join(d, f"u{i}.wav")
+            with wave.open(p, "wb") as wf:
+                wf.setnchannels(1)
+                wf.setsampwidth(2)
+                wf.setframerate(16000)
+                wf.writeframes(x.tobytes())
+            paths.append(p)
+        texts = [[i2w[10 + i], i2w[20 + i]] for i in range(len(paths))]
+        ld = data.AudioLoader(data.AudioDst(AB, "eval", "dev", path_list=paths, text_list=texts), m, batch_size=3)
+        got = list(ld.loader)
+    ok = len(got) == 2 and [len(b[0]) for b in got] == [3, 1] and got[0][2] == [[10, 20], [11, 21], [12, 22]]
+    flat = [t for b in got for t in b[0]]
+    res["loader_ok"] = int(ok and all(torch.equal(a, b) for a, b in zip(flat, fused)))
+    return res
+
+
+def check_wer():
+    from tests.cases import load_frontend_golden, wer_token_pairs
+    g = load_frontend_golden()
+    _, i2w = vocab()
+    m = get_model((1234, "plain", None), O.make_weights(1234, "plain"))
+    pairs = wer_token_pairs()
+    hyp = [h for h, _ in pairs]
+    ref = [r for _, r in pairs]
+    per = m.wer(ref, i2w, hyp=hyp)
+    want = g["wer_norm"]
+    res = {"per_utt_max_abs": float(np.abs(np.asarray(per) - want).max())}
+    dist = [round(p * len("".join(i2w[t] for t in r))) for p, r in zip(per, ref)]
+    res["dist_mismatch"] = int(sum(int(a != b) for a, b in zip(dist, g["wer_dist"].tolist())))
+    # references given as strings
+    per_s = m.wer(["".join(i2w[t] for t in r) for r in ref], i2w, hyp=hyp)
+    res["string_refs_same"] = int(per_s == per)
+    return res
+
+
+def check_driver_wer(cname):
+    """WER reported by the decode drivers when `text` is given (model.py:595-598, 982-985): the
+    hypotheses are scored on the device where the decode left them."""
+    from tests.cases import load_frontend_golden
+    g = load_frontend_golden()
+    cs = CASES[cname]
+    weights = case_weights(cs)
+    m = get_model(wkey(cs), weights)
+    _, i2w = vocab()
+    _, feats, lens = case_inputs(cs)
+    if cs["bw"] is None:
+        hyp = O.greedy_decode(weights, feats, lens, i2w)["tokens"]
+    else:
+        hyp = O.beam_decode(weights, cs["bw"], feats, lens, i2w)["tokens"]
+    refs = [O.synth_reference_text(7000 + i, h) for i, h in enumerate(hyp)]
+    if cs["bw"] is None:
+        out = m.eval_one_batch_with_greedy(m.device, feats, lens, i2w, refs)
+    else:
+        out = m.eval_one_batch_with_beam(m.device, cs["bw"], feats, lens, refs, i2w, second_pass=False)
+    res = {"wer": float(out.wer), "ref_wer": float(g[cname + "_wer"]),
+           "text_ok": int(list(out.text) == g[cname + "_wer_text"].tolist())}
+
+    class OneBatch:
+        loader = [(feats, torch.IntTensor(lens.tolist()), refs)] * 2
+    tm = m.test_model(OneBatch, i2w, bw=cs["bw"])
+    res["test_model_wer"] = tm["wer"]
+    res["test_model_n"] = tm["n"]
+    res["test_model_error_rate"] = tm["error_rate"]
+    res["oracle_error_rate"] = float(np.mean([h != r for h, r in zip(hyp, refs)]))
+    return res

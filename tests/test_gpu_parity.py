@@ -178,3 +178,46 @@ def test_config4_beam8_lm_batch32_10s(G):
     r = G.check_config_shape(32, 8, [10.0] * 32, lm_seed=7, seed0=3600)
     assert r["exact"] >= 31, r
     assert r["score_rel_max"] <= SCORE_RTOL
+
+
+# ---- rows either side of the hot path -----------------------------
+def test_frontend_int16_ingest_and_batch_audio(G):
+    r = G.check_frontend()
+    assert r["s16_eq_f32_bitwise"] == 1 and r["lens_ok"] == 1 and r["collate_ok"] == 1 and r["loader_ok"] == 1, r
+    for k, v in r.items():
+        if "_vs_" in k:
+            assert v <= FEAT_TOL, (k, v)
+
+
+def test_device_wer_bit_exact(G):
+    r = G.check_wer()
+    assert r["dist_mismatch"] == 0 and r["per_utt_max_abs"] <= 1e-12 and r["string_refs_same"] == 1, r
+
+
+@pytest.mark.parametrize("cname", ["greedy3", "beam4"])
+def test_driver_wer_matches_reference(G, cname):
+    r = G.check_driver_wer(cname)
+    assert abs(r["wer"] - r["ref_wer"]) < 1e-9 and r["text_ok"] == 1, r
+    assert abs(r["test_model_wer"] - r["ref_wer"]) < 1e-9 and r["test_model_n"] == 2 * len(G.CASES[cname]["seeds"])
+    assert r["test_model_error_rate"] == r["oracle_error_rate"]
+
+
+def test_transcribe_int16_equals_float32(G):
+    """asr_transcribe_pcm with 16-bit samples (half the host->device bytes) decodes exactly what the
+    float32 path decodes from the same samples / 32768, resident or through the prefetch pipeline."""
+    from oracle import asr_oracle as O
+    m = G.get_model((1234, "sharp", 8.0), O.make_weights(1234, "sharp", eos_bias=8.0))
+    B, n = 6, 48000
+    x16 = np.stack([O.synth_pcm_int16(8100 + i, n) for i in range(B)]).reshape(-1)
+    x32 = O.pcm_from_int16(x16)
+    off = np.arange(B + 1, dtype=np.int64) * n
+    a = m.transcribe(x32, off, bw=4)
+    b = m.transcribe(x16, off, bw=4)
+    assert all(np.array_equal(p, q) for p, q in zip(a, b))
+    h16 = torch.from_numpy(x16).pin_memory()
+    m.prefetch(h16, off, bw=4)
+    c = m.transcribe(h16, off, bw=4)
+    d = m.transcribe(torch.from_numpy(x16).cuda(), off, bw=4, resident=True)
+    assert all(np.array_equal(p, q) for p, q in zip(a, c)) and all(np.array_equal(p, q) for p, q in zip(a, d))
+    with pytest.raises(TypeError):
+        m.transcribe(x16.astype(np.int32), off, bw=4)
