@@ -283,12 +283,12 @@ def run_native(args):
         # (4 encoder projections 8.55 GB, keys 0.77 GB, 40 x (vocabulary 160 MB + cell 64 MB + query 17 MB)):
         # profiles/r01_kernels.csv, one `ncu --set full` capture of this workload
         traffic = 18.96e9 / 125 if (B, k, L) == (512, 8, 332) else None
-        roof = {"kernel": "tc::gemm_tf32x3_persistent_kernel", "bound": "tensor", "achieved": ach, "peak": tf_peak,
+        roof = {"kernel": "tc::gemm_split_persistent_kernel", "bound": "tensor", "achieved": ach, "peak": tf_peak,
                 "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": traffic,
-                "peak_source": peak_src + " cuBLAS bf16 sustained.  Per fp32 product the kernel issues one tf32 MMA "
-                               "(a_hi*w_hi) and one bf16 MMA over 2K (a_lo*w + a*w_lo): 4x the bf16 tensor-pipe time "
-                               "per algorithmic FLOP, so tensor_pipe_frac = 4 * frac is the share of the pipe's peak",
-                "tensor_pipe_frac": 4.0 * ach / tf_peak, "algorithmic_gflop_per_step": gemm_gflop,
+                "peak_source": peak_src + " cuBLAS bf16 sustained.  Per 16 values of k the kernel issues one fp16 MMA "
+                               "(a_hi*w_hi) and two bf16 MMAs (a_lo*w + a*w_lo over 2K): 3x the bf16 tensor-pipe time "
+                               "per algorithmic FLOP, so tensor_pipe_frac = 3 * frac is the share of the pipe's peak",
+                "tensor_pipe_frac": 3.0 * ach / tf_peak, "algorithmic_gflop_per_step": gemm_gflop,
                 "ms_per_launch": gemm_ms / n_gemm, "launches_per_step": n_gemm, "ms_per_step": gemm_ms}
     elif dom == "enc_recurrence":
         fl = 2.0 * B * L * 4 * 2 * 1024 * 256

@@ -126,7 +126,7 @@ static int prepare_batch(asr_handle* h, const int32_t* h_L, int B, cudaStream_t 
 
 // GEMM dispatch: CUDA-core fp32 (mode 0) or tcgen05 3xTF32 with a fused gather + hi/lo split of
 // the A operand (mode 1).  Both produce fp32-faithful results; mode 1 runs on the tensor cores.
-static int gemm(asr_handle* h, const AOperand& A, const float* W, const float* W_hi, const float* W_lo,
+static int gemm(asr_handle* h, const AOperand& A, const float* W, const hi_t* W_hi, const float* W_lo,
                 int M, int N, int K, const GemmEpilogue& epi, cudaStream_t st) {
     if (h->gemm_mode == 1 && W_hi && W_lo && h->ws.a_hi) {
         {
@@ -142,11 +142,19 @@ static int gemm(asr_handle* h, const AOperand& A, const float* W, const float* W
     return launch_gemm(A, W, M, N, K, epi, st, &h->launches);
 }
 
-static int split_weight(asr_handle* h, const float* w, int N, int K, float** hi, float** lo,
+static int split_weight(asr_handle* h, const float* w, int N, int K, hi_t** hi, float** lo,
                         int fmt = kSplitWeight) {
     ASR_TRY(dev_alloc_t(h->weight_allocs, hi, (size_t)N * K));
     ASR_TRY(dev_alloc_t(h->weight_allocs, lo, (size_t)N * K));
     ASR_TRY(split_operand(plain_a(w, K, K), N, K, *hi, *lo, nullptr, 0, nullptr, fmt));
+    ASR_CUDA(cudaDeviceSynchronize());
+    return ASR_OK;
+}
+// tf32 hi / lo, both fp32: the encoder recurrence engines pack their own operands from these
+static int split_weight_legacy(asr_handle* h, const float* w, int N, int K, float** hi, float** lo) {
+    ASR_TRY(dev_alloc_t(h->weight_allocs, hi, (size_t)N * K));
+    ASR_TRY(dev_alloc_t(h->weight_allocs, lo, (size_t)N * K));
+    ASR_TRY(split_operand_legacy(plain_a(w, K, K), N, K, *hi, *lo, 0));
     ASR_CUDA(cudaDeviceSynchronize());
     return ASR_OK;
 }
@@ -597,7 +605,7 @@ int asr_create(asr_handle** out, const asr_weights* wt, const asr_feature_consts
     for (int layer = 0; layer < 4; ++layer) {
         const int K = layer == 0 ? kFeat : kEnc;
         if ((rc = split_weight(h, h->w.enc_w_ih[layer], 2 * kGates, K, &h->w.enc_w_ih_hi[layer], &h->w.enc_w_ih_lo[layer])) != ASR_OK) return rc;
-        if ((rc = split_weight(h, h->w.enc_w_hh[layer], 2 * kGates, kEncH, &h->w.enc_w_hh_hi[layer], &h->w.enc_w_hh_lo[layer], kSplitLegacy)) != ASR_OK) return rc;
+        if ((rc = split_weight_legacy(h, h->w.enc_w_hh[layer], 2 * kGates, kEncH, &h->w.enc_w_hh_hi[layer], &h->w.enc_w_hh_lo[layer])) != ASR_OK) return rc;
         if ((rc = dev_alloc_t(pool, &h->w.enc_w_hh_lo_bf[layer], (size_t)2 * kGates * kEncH / 2)) != ASR_OK) return rc;
         if ((rc = pack_bf16_pairs(h->w.enc_w_hh_lo[layer], h->w.enc_w_hh_lo_bf[layer], (long long)2 * kGates * kEncH / 2)) != ASR_OK) return rc;
     }
@@ -607,7 +615,8 @@ int asr_create(asr_handle** out, const asr_weights* wt, const asr_feature_consts
     {
         // E' = embedding * W_ih[:, :256]^T (gate-interleaved columns): the embedding part of the decoder
         // LSTM input projection is a table lookup added in the cell GEMM's epilogue, K drops 1280 -> 1024
-        float *e_hi = nullptr, *e_lo = nullptr;
+        hi_t* e_hi = nullptr;
+        float* e_lo = nullptr;
         if ((rc = split_weight(h, h->w.emb, kVocab, kEmb, &e_hi, &e_lo, kSplitAct)) != ASR_OK) return rc;
         if ((rc = dev_alloc_t(pool, &h->w.emb_proj, (size_t)kVocab * 4 * kDecH)) != ASR_OK) return rc;
         GemmEpilogue e{};
@@ -650,7 +659,8 @@ int asr_test_gemm(asr_handle* h, const float* d_A, const float* d_W, const float
     if (mode == 0) {
         ASR_TRY(launch_gemm(plain_a(d_A, K, K), d_W, M, N, K, e, st, &h->launches));
     } else {
-        float *a_hi, *a_lo, *w_hi, *w_lo;
+        hi_t *a_hi, *w_hi;
+        float *a_lo, *w_lo;
         ASR_CUDA(cudaMalloc(&a_hi, sizeof(float) * (size_t)M * K));
         ASR_CUDA(cudaMalloc(&a_lo, sizeof(float) * (size_t)M * K));
         ASR_CUDA(cudaMalloc(&w_hi, sizeof(float) * (size_t)N * K));
@@ -672,7 +682,8 @@ int asr_test_gemm(asr_handle* h, const float* d_A, const float* d_W, const float
 int asr_bench_gemm(asr_handle* h, int M, int N, int K, int iters, float* ms_out, void* stream) {
     if (!h || !ms_out || M < 1 || N < 1 || K < 8 || iters < 1) { set_error("asr_bench_gemm: bad argument"); return ASR_ERR_ARG; }
     cudaStream_t st = (cudaStream_t)stream;
-    float *a, *a_hi, *a_lo, *w, *w_hi, *w_lo, *c, *bias;
+    float *a, *a_lo, *w, *w_lo, *c, *bias;
+    hi_t *a_hi, *w_hi;
     ASR_CUDA(cudaMalloc(&a, sizeof(float) * (size_t)M * K));
     ASR_CUDA(cudaMalloc(&a_hi, sizeof(float) * (size_t)M * K));
     ASR_CUDA(cudaMalloc(&a_lo, sizeof(float) * (size_t)M * K));

@@ -1,5 +1,6 @@
 // Internal declarations shared by the translation units of libasr_b200.so (sm_100a only).
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -28,6 +29,21 @@ constexpr int kNumSMs = 148;
 constexpr int kStages = 12;       // 8 pipeline stages + kernel-level timers (GEMM kernel, operand split)
 
 void set_error(const char* fmt, ...);
+
+// ---- split-precision operands of the tcgen05 GEMM engine (gemm_tc.cu) ---------------------------
+// x = hi + lo with hi = fp16(x) (11 significant bits, like tf32, but half the bytes and the full-rate
+// kind::f16 MMA) and lo = x - hi exact in fp32.  |x| > 65504 saturates hi; the residual carries the rest.
+typedef __half hi_t;
+#ifdef __CUDACC__
+__device__ __forceinline__ float hi_part(float x) {
+    return __half2float(__float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f)));
+}
+// two hi parts (already fp16-representable) -> packed half2, first argument in the low half-word
+__device__ __forceinline__ uint32_t pack_hi2(float a, float b) {
+    const __half2 v = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&v);
+}
+#endif
 
 #define ASR_CUDA(call)                                                                        \
     do {                                                                                      \
@@ -100,7 +116,7 @@ struct GemmEpilogue {
     const float* addrow;   // kLstmCell: gate pre-activations += addrow[addrow_idx[row]][n] (the
     const int* addrow_idx; //   pre-multiplied embedding table E' = emb * W_ih[:, :256]^T, row = token)
     int addrow_ld;
-    float* split_hi;       // kLstmCell: also write rn_tf32(h) / residual into [M, split_ld] at column u,
+    hi_t* split_hi;        // kLstmCell: also write fp16(h) / the cross operand into [M, split_ld] at column u,
     float* split_lo;       //   the A operand of the query / vocabulary GEMMs (no separate split pass)
     int split_ld;
 };
@@ -108,12 +124,15 @@ struct GemmEpilogue {
 // C[M,N] = A[M,K] * W[N,K]^T (+ epilogue).  fp32 in, fp32 accumulate.
 int launch_gemm(const AOperand& A, const float* W, int M, int N, int K, const GemmEpilogue& epi,
                 cudaStream_t st, int64_t* launches);
-// tcgen05 split-precision path (gemm_tc.cu): operands pre-split into a tf32 `hi` part and a `lo`
-// buffer of the same byte size holding the bf16 cross-term operand (layout: see split_operand_kernel)
+// tcgen05 split-precision path (gemm_tc.cu): operands pre-split into an fp16 `hi` part ([rows, K] halves)
+// and a `lo` buffer ([rows, K] 4-byte words) holding the bf16 cross-term operand (layout: see
+// split_operand_kernel).  kSplitLegacy (encoder recurrence weights): hi = rn_tf32(x), lo = rn_tf32(x - hi),
+// both fp32, `hi` then points to floats.
 enum { kSplitLegacy = 0, kSplitAct = 1, kSplitWeight = 2 };
-int split_operand(const AOperand& A, int M, int K, float* hi, float* lo, const int* stop_flag,
+int split_operand(const AOperand& A, int M, int K, hi_t* hi, float* lo, const int* stop_flag,
                   cudaStream_t st, int64_t* launches, int fmt = kSplitAct);
-int launch_gemm_tc(const float* a_hi, const float* a_lo, const float* w_hi, const float* w_lo, int M,
+int split_operand_legacy(const AOperand& A, int M, int K, float* hi, float* lo, cudaStream_t st);
+int launch_gemm_tc(const hi_t* a_hi, const float* a_lo, const hi_t* w_hi, const float* w_lo, int M,
                    int N, int K, const GemmEpilogue& epi, cudaStream_t st, int64_t* launches);
 // a weight matrix with its pre-split copies
 struct SplitW {
@@ -152,20 +171,20 @@ struct PackedWeights {
     float* att_b = nullptr;          // [128]
     float* att_w_hidden = nullptr;   // [512, 128]  as stored (k-major rows, coalesced over d)
     float* att_v = nullptr;          // [128]
-    // tf32 hi / lo splits of the GEMM weights (tcgen05 3xTF32 path), same shapes as the originals
-    float* enc_w_ih_hi[4] = {};
+    // fp16 hi / bf16 cross splits of the GEMM weights (tcgen05 split-precision path), same shapes as the originals
+    hi_t* enc_w_ih_hi[4] = {};
     float* enc_w_ih_lo[4] = {};
-    float* dec_w_hi = nullptr;
+    hi_t* dec_w_hi = nullptr;
     float* dec_w_lo = nullptr;
-    float* proj_w_hi = nullptr;
+    hi_t* proj_w_hi = nullptr;
     float* proj_w_lo = nullptr;
-    float* att_w_enc_t_hi = nullptr;
+    hi_t* att_w_enc_t_hi = nullptr;
     float* att_w_enc_t_lo = nullptr;
     float* enc_w_hh_hi[4] = {};          // [2, 1024, 256] tf32 split of enc_w_hh (tensor-core recurrence)
     float* enc_w_hh_lo[4] = {};
     uint32_t* enc_w_hh_lo_bf[4] = {};    // [2, 1024, 128] bf16 pairs of the residual (TMEM-resident recurrence)
     float* att_w_hidden_t = nullptr;     // [128, 512] (W_hidden transposed -> [N, K]) for the query GEMM
-    float* att_w_hidden_t_hi = nullptr;
+    hi_t* att_w_hidden_t_hi = nullptr;
     float* att_w_hidden_t_lo = nullptr;
     float* zero_bias = nullptr;          // [2048] zeros
     float* emb_proj = nullptr;           // [5004, 2048] E' = embedding * W_ih[:, :256]^T (gate-interleaved columns)
@@ -240,7 +259,7 @@ struct Workspace {
     float* dctx[2] = {};
     float* logits = nullptr;     // [R, 5004]
     float* att_q = nullptr;      // [R, 128] query projection of the current step
-    float* dec_split_hi = nullptr;   // [R, 1024] tf32 hi of [h_new | ctx_new], written by the producing kernels
+    hi_t* dec_split_hi = nullptr;    // [R, 1024] fp16 hi of [h_new | ctx_new], written by the producing kernels
     float* dec_split_lo = nullptr;
     float* att_part = nullptr;   // [B, S, k, 2 + 512] partial (max, sum, ctx)
     float* att_score = nullptr;  // [R, Lmax_cap] raw scores (alignment export)
@@ -277,7 +296,7 @@ struct Workspace {
     // pinned host staging
     void* h_stage = nullptr;
     size_t h_stage_bytes = 0;
-    float* a_hi = nullptr;       // split A operand of the tcgen05 GEMMs: max(rows*720, R*1280) floats
+    hi_t* a_hi = nullptr;        // split A operand of the tcgen05 GEMMs: max(rows*720, R*1280) elements
     float* a_lo = nullptr;
     std::vector<void*> allocs;
 };
@@ -352,7 +371,7 @@ int launch_lstm_recurrence_tc(asr_handle* h, int layer, const float* xg, const f
 // layout, same row order as y_packed - or as y_utt when y_packed is nullptr)
 int launch_lstm_recurrence_tc3(asr_handle* h, int layer, const float* xg, const float* x_in,
                                float* y_packed, float* y_utt, float* h_fin, float* c_fin,
-                               cudaStream_t st, float* split_hi = nullptr, float* split_lo = nullptr);
+                               cudaStream_t st, hi_t* split_hi = nullptr, float* split_lo = nullptr);
 int pack_bf16_pairs(const float* src, uint32_t* dst, long long n_pairs);
 size_t rec3_stage_bytes_per_cta();
 int launch_export_padded(asr_handle* h, const float* src_utt, int width, float* dst, int Lmax, int B,

@@ -124,7 +124,7 @@ struct AttnParams {
     const float* v;         // [128]
     const int* uoff;        // [B + 1]
     float* ctx_out;         // [R, 512]
-    float* split_hi;        // optional: tf32 hi / lo split of ctx written at column 512 of the
+    hi_t* split_hi;         // optional: fp16 hi / bf16 cross split of ctx written at column 512 of the
     float* split_lo;        //   [R, split_ld] A operand of the vocabulary GEMM
     int split_ld;
     float* part;            // [B, S, k, 514]
@@ -141,15 +141,15 @@ struct AttnParams {
 
 __device__ __forceinline__ void write_ctx_split(const AttnParams& p, int row, int tid, float2 o) {
     if (!p.split_hi) return;
-    // thread `tid` owns ctx[2 tid], ctx[2 tid + 1].  hi = rn_tf32(x); the cross operand holds, per
+    // thread `tid` owns ctx[2 tid], ctx[2 tid + 1].  hi = fp16(x); the cross operand holds, per
     // 8-float block, 8 x bf16(x - hi) then 8 x bf16(x) (gemm_tc.cu: kSplitAct)
     float2 hi;
-    uint32_t u, xl, xx;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(o.x)); hi.x = __uint_as_float(u);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(o.y)); hi.y = __uint_as_float(u);
+    uint32_t xl, xx;
+    hi.x = hi_part(o.x);
+    hi.y = hi_part(o.y);
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(xl) : "f"(o.y - hi.y), "f"(o.x - hi.x));
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(xx) : "f"(o.y), "f"(o.x));
-    reinterpret_cast<float2*>(p.split_hi + (size_t)row * p.split_ld + kDecH)[tid] = hi;
+    reinterpret_cast<uint32_t*>(p.split_hi + (size_t)row * p.split_ld + kDecH)[tid] = pack_hi2(hi.x, hi.y);
     uint32_t* cross = reinterpret_cast<uint32_t*>(p.split_lo + (size_t)row * p.split_ld + kDecH) + (tid >> 2) * 8 + (tid & 3);
     cross[0] = xl;
     cross[4] = xx;
@@ -730,13 +730,9 @@ attention_stream_kernel(AttnParams p) {
                 if (p.split_hi) {
                     // operand split of ctx for the vocabulary GEMM (gemm_tc.cu kSplitAct): this thread
                     // owns half of an 8-float block
-                    uint32_t u0, u1, u2, u3;
-                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u0) : "f"(o.x));
-                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u1) : "f"(o.y));
-                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u2) : "f"(o.z));
-                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u3) : "f"(o.w));
-                    const float4 hi = make_float4(__uint_as_float(u0), __uint_as_float(u1), __uint_as_float(u2), __uint_as_float(u3));
-                    *reinterpret_cast<float4*>(p.split_hi + (size_t)row * p.split_ld + kDecH + 4 * cg4) = hi;
+                    const float4 hi = make_float4(hi_part(o.x), hi_part(o.y), hi_part(o.z), hi_part(o.w));
+                    *reinterpret_cast<uint2*>(p.split_hi + (size_t)row * p.split_ld + kDecH + 4 * cg4) =
+                        make_uint2(pack_hi2(hi.x, hi.y), pack_hi2(hi.z, hi.w));
                     uint2 lo2, xx2;
                     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo2.x) : "f"(o.y - hi.y), "f"(o.x - hi.x));
                     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo2.y) : "f"(o.w - hi.w), "f"(o.z - hi.z));
@@ -880,8 +876,8 @@ struct BookParams {
     int B, k, K, step;
     // optional: gather the next step's cell-GEMM operand [ctx[src] | h[src]] (already split, from the
     // [h | ctx] rows the cell epilogue / attention kernel wrote) - replaces a gather + split launch
-    const float* split_hi; const float* split_lo;   // [R, 1024] = [h | ctx]
-    float* next_hi; float* next_lo;                 // [R, 1024] = [ctx | h]
+    const hi_t* split_hi; const float* split_lo;    // [R, 1024] = [h | ctx]: fp16 hi, 4-byte cross words
+    hi_t* next_hi; float* next_lo;                  // [R, 1024] = [ctx | h]
 };
 
 struct RowTopkParams {
@@ -992,28 +988,33 @@ __device__ void beam_bookkeep(const BookParams& p, int u, float* s_s, int* s_f, 
     }
     if (p.next_hi) {
         __syncthreads();
-        // k rows x 1024 floats x (hi, cross): 16-byte copies, halves swapped ([h | ctx] -> [ctx | h])
-        static_assert(kProjK / 4 == 256, "one 16-byte column per thread");
-        // per_row = 256 = blockDim: thread `tid` owns one 16-byte column of every row; all 2k loads of a
-        // thread are issued before the first store
+        // k rows x 1024 values x (2-byte hi, 4-byte cross): 16-byte copies, halves swapped ([h | ctx] -> [ctx | h])
+        static_assert(kProjK / 4 == 256, "one 16-byte cross column per thread");
+        // thread `tid` owns one 16-byte column of the cross operand of every row (4 values of k) and, for
+        // tid < 128, one 16-byte column of the hi operand (8 values of k); all loads of a group of 4 rows
+        // are issued before the first store
         const int c4 = tid;
         const int s4 = c4 < kEnc / 4 ? c4 + kDecH / 4 : c4 - kEnc / 4;
-        for (int i0 = 0; i0 < k; i0 += 4) {          // 8 loads in flight per thread
-            float4 vh[4], vl[4];
+        const bool has_hi = tid < kProjK / 8;
+        const int c8 = tid & (kProjK / 8 - 1);
+        const int s8 = c8 < kEnc / 8 ? c8 + kDecH / 8 : c8 - kEnc / 8;
+        for (int i0 = 0; i0 < k; i0 += 4) {          // up to 8 loads in flight per thread
+            uint4 vh[4];
+            float4 vl[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 if (i0 + i < k) {
-                    const size_t so = (size_t)s_src[i0 + i] * kProjK + 4 * s4;
-                    vh[i] = __ldcg(reinterpret_cast<const float4*>(p.split_hi + so));
-                    vl[i] = __ldcg(reinterpret_cast<const float4*>(p.split_lo + so));
+                    const size_t so = (size_t)s_src[i0 + i] * kProjK;
+                    vl[i] = __ldcg(reinterpret_cast<const float4*>(p.split_lo + so + 4 * s4));
+                    if (has_hi) vh[i] = __ldcg(reinterpret_cast<const uint4*>(p.split_hi + so + 8 * s8));
                 }
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 if (i0 + i < k) {
-                    const size_t d = (size_t)(u * k + i0 + i) * kProjK + 4 * c4;
-                    *reinterpret_cast<float4*>(p.next_hi + d) = vh[i];
-                    *reinterpret_cast<float4*>(p.next_lo + d) = vl[i];
+                    const size_t d = (size_t)(u * k + i0 + i) * kProjK;
+                    *reinterpret_cast<float4*>(p.next_lo + d + 4 * c4) = vl[i];
+                    if (has_hi) *reinterpret_cast<uint4*>(p.next_hi + d + 8 * c8) = vh[i];
                 }
             }
         }

@@ -138,7 +138,7 @@ struct Params {
     int xchg_dsmem;         // 1: exchange h through distributed shared memory, 0: through global staging
     float* y_packed;
     float* y_utt;
-    float* y_hi;            // optional [rows, 512]: rn_tf32(y), rows as y_utt when that is written, else as y_packed
+    hi_t* y_hi;             // optional [rows, 512]: fp16(y), rows as y_utt when that is written, else as y_packed
     uint32_t* y_cross;      // optional: per 8-float block 8 x bf16(y - hi) then 8 x bf16(y)  (gemm_tc.cu kSplitAct)
     float* h_fin;
     float* c_fin;
@@ -265,7 +265,7 @@ lstm_rec_tc3_kernel(Params p) {
             const bool act = i < n_act;
             // operand split for the consuming GEMM: the lane 4 away holds the neighbouring unit of the
             // same row; even units pack the two residuals, odd units the two values (bf16 pairs)
-            const float hi = rn_tf32(yv[q]);
+            const float hi = hi_part(yv[q]);
             const float lo = yv[q] - hi;
             const float lo_n = __shfl_xor_sync(0xffffffffu, lo, 4);
             const float y_n = __shfl_xor_sync(0xffffffffu, yv[q], 4);
@@ -276,7 +276,7 @@ lstm_rec_tc3_kernel(Params p) {
                 if (p.y_utt) p.y_utt[urow * kEnc + ocol] = yv[q];
                 if (p.y_hi) {
                     const size_t srow = p.y_utt ? urow : row;      // last layer: rows as `enc`
-                    p.y_hi[srow * kEnc + ocol] = hi;
+                    p.y_hi[srow * kEnc + ocol] = __float2half_rn(hi);
                     const bool odd = (ocol & 1) != 0;
                     const __nv_bfloat162 pk = odd ? __floats2bfloat162_rn(y_n, yv[q]) : __floats2bfloat162_rn(lo, lo_n);
                     // block of 8 floats -> 8 words: words 0-3 residual pairs, words 4-7 value pairs
@@ -464,7 +464,7 @@ int pack_bf16_pairs(const float* src, uint32_t* dst, long long n_pairs) {
 size_t rec3_stage_bytes_per_cta() { return rec3::kStageBytes; }
 
 int launch_lstm_recurrence_tc3(asr_handle* h, int layer, const float* xg, const float* x_in, float* y_packed,
-                               float* y_utt, float* h_fin, float* c_fin, cudaStream_t st, float* split_hi,
+                               float* y_utt, float* h_fin, float* c_fin, cudaStream_t st, hi_t* split_hi,
                                float* split_lo) {
     const BatchMeta& m = h->meta;
     rec3::Params p{};

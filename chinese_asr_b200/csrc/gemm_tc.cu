@@ -3,20 +3,22 @@
 // Why split precision: parity with the fp32 reference must be token-exact (BASELINE.json north_star),
 // and bf16 / single-pass tf32 tensor-core products (8 / 11 significant bits) flip beam decisions
 // (hard part 1).  Every fp32 operand x is split once into
-//     x_hi = rn_tf32(x)          (cvt.rna.tf32.f32, exact in tf32)
-//     x_lo = x - x_hi            (the residual, |x_lo| <= 2^-11 |x|)
+//     x_hi = fp16(x)             (round to nearest even: 11 significant bits like tf32, but 2 bytes and
+//                                 the full-rate kind::f16 MMA; saturating, see hi_part())
+//     x_lo = x - x_hi            (the residual, exact in fp32, |x_lo| <= 2^-11 |x|)
 // and the product is accumulated in fp32 in TMEM as
-//     a_hi*w_hi                  one tcgen05.mma.kind::tf32 (K = 8)
-//   + (a_lo*w + a*w_lo)          ONE tcgen05.mma.kind::f16 on bf16 operands (K = 16): the "cross" operand
-//                                holds, per 8 values of k, [8 x bf16(a_lo) | 8 x bf16(a)] on the A side
-//                                and [8 x bf16(w) | 8 x bf16(w_lo)] on the W side.
+//     a_hi*w_hi                  one tcgen05.mma.kind::f16 on fp16 operands per 16 values of k
+//   + (a_lo*w + a*w_lo)          one tcgen05.mma.kind::f16 on bf16 operands (K = 16) per 8 values of k: the
+//                                "cross" operand holds, per 8 values of k, [8 x bf16(a_lo) | 8 x bf16(a)] on
+//                                the A side and [8 x bf16(w) | 8 x bf16(w_lo)] on the W side.
 // The cross terms are 2^-11 of the product, so bf16's 2^-9 relative accuracy leaves ~2^-20; measured
 // 2-5e-6 relative error against fp64, the same as three tf32 MMAs (the tensor core's truncating
-// accumulation dominates).  Two MMAs per 8 values of k.
+// accumulation dominates).  Three MMA issue slots per 16 values of k (the tf32 hi form needed four: a
+// kind::tf32 MMA covers only 8 values of k in the time a 16-bit MMA covers 16).
 //
 // Kernel anatomy (persistent, one CTA per SM, cta_group::1, optionally a cluster of 2 CTAs):
-//   warp 0   : TMA producer - cp.async.bulk.tensor.2d of the A_hi / A_cross / W_hi / W_cross K-slabs
-//              (64- or 128-byte rows, SWIZZLE_64B / 128B) into a 3/4-stage shared-memory ring,
+//   warp 0   : TMA producer - cp.async.bulk.tensor.2d of the A_cross / W_cross (128-byte rows, SWIZZLE_128B)
+//              and A_hi / W_hi (64-byte rows, SWIZZLE_64B) K-slabs of 32 values of k into a 4-stage ring,
 //              completion on `full` mbarriers (expect_tx); out-of-bounds rows / K are zero-filled by
 //              TMA, so M, N and K tails need no special code.  In a CTA pair each CTA fetches half of
 //              the W tile and multicasts it into both CTAs.
@@ -132,6 +134,10 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// kind::f16 with fp16 operands: D=f32 (1<<4), A=B=F16 (0<<7, 0<<10)
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 // two floats -> packed bf16x2 (first argument in the low half-word), round to nearest even
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo_half, float hi_half) {
     uint32_t u;
@@ -228,9 +234,15 @@ __device__ __forceinline__ void cluster_sync_all() {
 
 template <int BN, int BKF, int STAGES, bool TWO = false>
 struct SmemLayoutP {
-    static constexpr int kATile = BM * BKF * 4;
+    static_assert(BKF == 32, "K slabs of 32 values: 128-byte cross rows, 64-byte fp16 hi rows");
+    static constexpr int kATile = BM * BKF * 4;                       // cross operand, 4 bytes per value of k
     static constexpr int kBTile = (TWO ? BN / 2 : BN) * BKF * 4;      // 2-SM form: each CTA keeps half of the W tile
-    static constexpr int kStage = 2 * kATile + 2 * kBTile;
+    static constexpr int kAHi = kATile / 2;                           // fp16 hi operand, 2 bytes per value of k
+    static constexpr int kBHi = kBTile / 2;
+    // stage = [A_cross | W_cross | A_hi | W_hi]; every tile is a multiple of 1024 bytes (swizzle atoms)
+    static constexpr int kOffAX = 0, kOffWX = kATile, kOffAH = kATile + kBTile, kOffWH = kATile + kBTile + kAHi;
+    static constexpr int kStage = kATile + kBTile + kAHi + kBHi;
+    static_assert(kBTile % 1024 == 0 && kBHi % 512 == 0, "tile alignment");
     static constexpr int kScratch = 4 * 32 * 36 * 4;      // per epilogue warp: 32 rows x (32 + 4) floats
     static constexpr int kBytes = STAGES * kStage + kScratch + 1024 /*align slack*/ + 256 /*barriers*/;
 };
@@ -241,7 +253,7 @@ struct SmemLayoutP {
 // warps of BOTH CTAs have committed it (multicast tcgen05.commit onto both `empty` barriers).
 template <int BN, int BKF, int STAGES, int CL, bool TWO = false>
 __global__ void __launch_bounds__(192, 1)
-gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+gemm_split_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                               const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                               int M, int N, int K, GemmEpilogue epi, int dbg) {
     if (epi.stop_flag && *epi.stop_flag >= 0) return;
@@ -308,30 +320,29 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, cons
                         if (crank == 0) mbar_expect_tx(&full[s], 2 * L::kStage);
                         const uint32_t fb = mapa_rank(smem_u32(&full[s]), 0);
                         const int nrow = n0 + crank * (BN / 2);
-                        tma_load_2d_2sm(&map_a_hi, fb, st, kb * BKF, m0);
-                        tma_load_2d_2sm(&map_a_lo, fb, st + L::kATile, kb * BKF, m0);
-                        tma_load_2d_2sm(&map_w_hi, fb, st + 2 * L::kATile, kb * BKF, nrow);
-                        tma_load_2d_2sm(&map_w_lo, fb, st + 2 * L::kATile + L::kBTile, kb * BKF, nrow);
+                        tma_load_2d_2sm(&map_a_lo, fb, st + L::kOffAX, kb * BKF, m0);
+                        tma_load_2d_2sm(&map_w_lo, fb, st + L::kOffWX, kb * BKF, nrow);
+                        tma_load_2d_2sm(&map_a_hi, fb, st + L::kOffAH, kb * BKF, m0);
+                        tma_load_2d_2sm(&map_w_hi, fb, st + L::kOffWH, kb * BKF, nrow);
                         continue;
                     }
                     mbar_expect_tx(&full[s], L::kStage);
-                    tma_load_2d(&map_a_hi, &full[s], st, kb * BKF, m0);
-                    tma_load_2d(&map_a_lo, &full[s], st + L::kATile, kb * BKF, m0);
+                    tma_load_2d(&map_a_lo, &full[s], st + L::kOffAX, kb * BKF, m0);
+                    tma_load_2d(&map_a_hi, &full[s], st + L::kOffAH, kb * BKF, m0);
                     if (CL == 1) {
-                        tma_load_2d(&map_w_hi, &full[s], st + 2 * L::kATile, kb * BKF, n0);
-                        tma_load_2d(&map_w_lo, &full[s], st + 2 * L::kATile + L::kBTile, kb * BKF, n0);
+                        tma_load_2d(&map_w_lo, &full[s], st + L::kOffWX, kb * BKF, n0);
+                        tma_load_2d(&map_w_hi, &full[s], st + L::kOffWH, kb * BKF, n0);
                     } else {
-                        const int part = crank * (L::kBTile / CL);
                         const int nrow = n0 + crank * (BN / CL);
-                        tma_load_2d_mc(&map_w_hi, &full[s], st + 2 * L::kATile + part, kb * BKF, nrow, kMask);
-                        tma_load_2d_mc(&map_w_lo, &full[s], st + 2 * L::kATile + L::kBTile + part, kb * BKF, nrow, kMask);
+                        tma_load_2d_mc(&map_w_lo, &full[s], st + L::kOffWX + crank * (L::kBTile / CL), kb * BKF, nrow, kMask);
+                        tma_load_2d_mc(&map_w_hi, &full[s], st + L::kOffWH + crank * (L::kBHi / CL), kb * BKF, nrow, kMask);
                     }
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0 && !(TWO && crank != 0)) {               // 2-SM form: only the leader CTA issues
-            constexpr uint32_t idesc = make_idesc_tf32(TWO ? 2 * BM : BM, BN);
+            constexpr uint32_t idesc_h = make_idesc_f16(TWO ? 2 * BM : BM, BN);
             constexpr uint32_t idesc_x = make_idesc_bf16(TWO ? 2 * BM : BM, BN);
             int it = 0, lt = 0;
             for (int work = work0; work < nwork; work += work_step, ++lt) {
@@ -346,20 +357,22 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, cons
                     mbar_wait(&full[s], ph);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     uint8_t* st = smem + s * L::kStage;
-                    const uint64_t d_ah = make_kmajor_desc<BKF>(st);
-                    const uint64_t d_al = make_kmajor_desc<BKF>(st + L::kATile);
-                    const uint64_t d_wh = make_kmajor_desc<BKF>(st + 2 * L::kATile);
-                    const uint64_t d_wl = make_kmajor_desc<BKF>(st + 2 * L::kATile + L::kBTile);
+                    const uint64_t d_ax = make_kmajor_desc<32>(st + L::kOffAX);     // 128-byte rows, SWIZZLE_128B
+                    const uint64_t d_wx = make_kmajor_desc<32>(st + L::kOffWX);
+                    const uint64_t d_ah = make_kmajor_desc<16>(st + L::kOffAH);     // 64-byte rows, SWIZZLE_64B
+                    const uint64_t d_wh = make_kmajor_desc<16>(st + L::kOffWH);
+                    // every MMA consumes 32 bytes of K per row: 8 values of k of the cross operand, 16 of the hi operand
 #pragma unroll
-                    for (int kk = 0; kk < BKF / UMMA_K; ++kk) {
-                        const uint64_t adv = (uint64_t)((kk * UMMA_K * 4) >> 4);
-                        if (TWO) {
-                            umma2_bf16(tacc, d_al + adv, d_wl + adv, idesc_x, (kb | kk) ? 1u : 0u);
-                            umma2_tf32(tacc, d_ah + adv, d_wh + adv, idesc, 1u);
-                        } else {
-                            umma_bf16(tacc, d_al + adv, d_wl + adv, idesc_x, (kb | kk) ? 1u : 0u);   // cross terms
-                            umma_tf32(tacc, d_ah + adv, d_wh + adv, idesc, 1u);
-                        }
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const uint64_t adv = (uint64_t)((kk * 32) >> 4);
+                        if (TWO) umma2_bf16(tacc, d_ax + adv, d_wx + adv, idesc_x, (kb | kk) ? 1u : 0u);
+                        else umma_bf16(tacc, d_ax + adv, d_wx + adv, idesc_x, (kb | kk) ? 1u : 0u);
+                    }
+#pragma unroll
+                    for (int kk = 0; kk < 2; ++kk) {
+                        const uint64_t adv = (uint64_t)((kk * 32) >> 4);
+                        if (TWO) umma2_bf16(tacc, d_ah + adv, d_wh + adv, idesc_h, 1u);
+                        else umma_bf16(tacc, d_ah + adv, d_wh + adv, idesc_h, 1u);
                     }
                     if (TWO) umma2_commit_mc(&empty[s], kMask);
                     else if (CL == 1) umma_commit(&empty[s]);
@@ -437,11 +450,11 @@ gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, cons
                         // the 8 hidden units of this thread are one 8-float block of the split operand
                         float hh[8], hl[8];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) { hh[j] = rn_tf32_e(hv[j]); hl[j] = hv[j] - hh[j]; }
-                        float4* sh = reinterpret_cast<float4*>(epi.split_hi + (size_t)row * epi.split_ld + (n >> 2));
+                        for (int j = 0; j < 8; ++j) { hh[j] = hi_part(hv[j]); hl[j] = hv[j] - hh[j]; }
+                        uint4* sh = reinterpret_cast<uint4*>(epi.split_hi + (size_t)row * epi.split_ld + (n >> 2));
                         uint4* sx = reinterpret_cast<uint4*>(epi.split_lo + (size_t)row * epi.split_ld + (n >> 2));
-                        sh[0] = make_float4(hh[0], hh[1], hh[2], hh[3]);
-                        sh[1] = make_float4(hh[4], hh[5], hh[6], hh[7]);
+                        sh[0] = make_uint4(pack_hi2(hh[0], hh[1]), pack_hi2(hh[2], hh[3]), pack_hi2(hh[4], hh[5]),
+                                           pack_hi2(hh[6], hh[7]));
                         sx[0] = make_uint4(pack_bf16x2(hl[0], hl[1]), pack_bf16x2(hl[2], hl[3]),
                                            pack_bf16x2(hl[4], hl[5]), pack_bf16x2(hl[6], hl[7]));
                         sx[1] = make_uint4(pack_bf16x2(hv[0], hv[1]), pack_bf16x2(hv[2], hv[3]),
@@ -521,11 +534,13 @@ __device__ __forceinline__ float rn_tf32(float x) {
     return __uint_as_float(u);
 }
 
-// fmt: kSplitLegacy  lo = rn_tf32(x - hi) as fp32 (the encoder recurrence packs its own W_lo from it)
+// LEGACY (kSplitLegacy): hi = rn_tf32(x), lo = rn_tf32(x - hi), both fp32 (the encoder recurrence packs its own
+//      operands from them); otherwise hi = fp16(x) and
 //      kSplitAct / kSplitWeight  "cross" operand: per 8-float block 16 bf16 values,
 //          activations [bf16(x - hi) x8 | bf16(x) x8],  weights [bf16(w) x8 | bf16(w - hi) x8],
 //      so one kind::f16 MMA (K = 16) over a block adds  x_lo*w + x*w_lo  for 8 values of k.
-__global__ void split_operand_kernel(AOperand A, int M, int K, float* __restrict__ hi, float* __restrict__ lo,
+template <bool LEGACY>
+__global__ void split_operand_kernel(AOperand A, int M, int K, void* __restrict__ hi_out, float* __restrict__ lo,
                                      const int* stop_flag, int fmt) {
     if (stop_flag && *stop_flag >= 0) return;
     const int k8n = K >> 3;
@@ -544,16 +559,20 @@ __global__ void split_operand_kernel(AOperand A, int M, int K, float* __restrict
         const float4 v0 = src[0], v1 = src[1];
         const float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
         float h[8], l[8];
+        if (LEGACY) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { h[j] = rn_tf32(x[j]); l[j] = x[j] - h[j]; }
-        float4* ph = reinterpret_cast<float4*>(hi + (size_t)row * K + k);
-        ph[0] = make_float4(h[0], h[1], h[2], h[3]);
-        ph[1] = make_float4(h[4], h[5], h[6], h[7]);
-        if (fmt == kSplitLegacy) {
+            for (int j = 0; j < 8; ++j) { h[j] = rn_tf32(x[j]); l[j] = x[j] - h[j]; }
+            float4* ph = reinterpret_cast<float4*>(static_cast<float*>(hi_out) + (size_t)row * K + k);
+            ph[0] = make_float4(h[0], h[1], h[2], h[3]);
+            ph[1] = make_float4(h[4], h[5], h[6], h[7]);
             float4* pl = reinterpret_cast<float4*>(lo + (size_t)row * K + k);
             pl[0] = make_float4(rn_tf32(l[0]), rn_tf32(l[1]), rn_tf32(l[2]), rn_tf32(l[3]));
             pl[1] = make_float4(rn_tf32(l[4]), rn_tf32(l[5]), rn_tf32(l[6]), rn_tf32(l[7]));
         } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { h[j] = hi_part(x[j]); l[j] = x[j] - h[j]; }
+            *reinterpret_cast<uint4*>(static_cast<hi_t*>(hi_out) + (size_t)row * K + k) =
+                make_uint4(pack_hi2(h[0], h[1]), pack_hi2(h[2], h[3]), pack_hi2(h[4], h[5]), pack_hi2(h[6], h[7]));
             const uint4 pl = make_uint4(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]),
                                         pack_bf16x2(l[4], l[5]), pack_bf16x2(l[6], l[7]));
             const uint4 px = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]),
@@ -582,43 +601,67 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
-// 2-D fp32 tensor [rows, K] row-major -> box [box_rows, 32] with 128-byte swizzle
-static int make_map(CUtensorMap* map, const float* base, int rows, int K, int box_rows, int BKF, int ld = 0) {
+// cross operand: 2-D tensor [rows, K] of 4-byte words (two bf16 each), row-major -> box [box_rows, 32] = 128-byte
+// rows with 128-byte swizzle.  hi operand: [rows, K] fp16 -> box [box_rows, 32] = 64-byte rows, 64-byte swizzle.
+static int make_map_t(CUtensorMap* map, const void* base, int rows, int K, int box_rows, int ld, bool hi) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return ASR_ERR_CUDA; }
+    const size_t esz = hi ? sizeof(hi_t) : sizeof(float);
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)(ld > 0 ? ld : K) * sizeof(float)};
-    cuuint32_t box[2] = {(cuuint32_t)BKF, (cuuint32_t)box_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)(ld > 0 ? ld : K) * esz};
+    cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, BKF == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+    CUresult r = enc(map, hi ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                     const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     hi ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) rows=%d K=%d", (int)r, rows, K); return ASR_ERR_CUDA; }
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) rows=%d K=%d hi=%d", (int)r, rows, K, (int)hi); return ASR_ERR_CUDA; }
     return ASR_OK;
+}
+static int make_map(CUtensorMap* map, const float* base, int rows, int K, int box_rows, int, int ld = 0) {
+    return make_map_t(map, base, rows, K, box_rows, ld, false);
+}
+static int make_map(CUtensorMap* map, const hi_t* base, int rows, int K, int box_rows, int, int ld = 0) {
+    return make_map_t(map, base, rows, K, box_rows, ld, true);
 }
 
 }  // namespace tc
 
-int split_operand(const AOperand& A, int M, int K, float* hi, float* lo, const int* stop_flag, cudaStream_t st,
-                  int64_t* launches, int fmt) {
-    if (M <= 0) return ASR_OK;
+static int check_split_args(const AOperand& A, int K) {
     if (K % 8) { set_error("split: K %% 8"); return ASR_ERR_ARG; }
     for (int g = 0; g + 1 < A.nseg; ++g)
         if (A.seg[g].kend % 8) { set_error("split: segment boundary %% 8"); return ASR_ERR_ARG; }
+    return ASR_OK;
+}
+
+int split_operand(const AOperand& A, int M, int K, hi_t* hi, float* lo, const int* stop_flag, cudaStream_t st,
+                  int64_t* launches, int fmt) {
+    if (M <= 0) return ASR_OK;
+    ASR_TRY(check_split_args(A, K));
+    if (fmt == kSplitLegacy) { set_error("split: use split_operand_legacy"); return ASR_ERR_ARG; }
     long long total = (long long)M * (K / 8);
     int grid = (int)std::min<long long>((total + 255) / 256, (long long)kNumSMs * 16);
-    tc::split_operand_kernel<<<grid, 256, 0, st>>>(A, M, K, hi, lo, stop_flag, fmt);
+    tc::split_operand_kernel<false><<<grid, 256, 0, st>>>(A, M, K, hi, lo, stop_flag, fmt);
     ASR_CHECK_LAUNCH();
     if (launches) ++*launches;
     return ASR_OK;
 }
 
+int split_operand_legacy(const AOperand& A, int M, int K, float* hi, float* lo, cudaStream_t st) {
+    if (M <= 0) return ASR_OK;
+    ASR_TRY(check_split_args(A, K));
+    long long total = (long long)M * (K / 8);
+    int grid = (int)std::min<long long>((total + 255) / 256, (long long)kNumSMs * 16);
+    tc::split_operand_kernel<true><<<grid, 256, 0, st>>>(A, M, K, hi, lo, nullptr, kSplitLegacy);
+    ASR_CHECK_LAUNCH();
+    return ASR_OK;
+}
+
 // CL CTAs of a cluster work on CL vertically adjacent tiles and share the W tile by multicast
 template <int BN, int BKF, int STAGES, int CL, bool TWO = false>
-static int launch_tc_cluster(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const float* w_hi, const float* w_lo,
+static int launch_tc_cluster(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const hi_t* w_hi, const float* w_lo,
                              int M, int N, int K, const GemmEpilogue& epi, cudaStream_t st, int dbg_p) {
-    auto kern = tc::gemm_tf32x3_persistent_kernel<BN, BKF, STAGES, CL, TWO>;
+    auto kern = tc::gemm_split_persistent_kernel<BN, BKF, STAGES, CL, TWO>;
     const int smem_p = tc::SmemLayoutP<BN, BKF, STAGES, TWO>::kBytes;
     const int tiles_m = (M + tc::BM - 1) / tc::BM, tiles_n = (N + BN - 1) / BN;
     static int max_clusters = 0;
@@ -650,7 +693,7 @@ static int launch_tc_cluster(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo,
 
 // C = A * W^T with pre-split operands (a_hi/a_lo [M,K], w_hi/w_lo [N,K], all dense row-major)
 template <int BN, int BKF, int STAGES>
-static int launch_tc_cfg(const float* a_hi, const float* a_lo, const float* w_hi, const float* w_lo, int M, int N,
+static int launch_tc_cfg(const hi_t* a_hi, const float* a_lo, const hi_t* w_hi, const float* w_lo, int M, int N,
                          int K, const GemmEpilogue& epi, cudaStream_t st) {
     CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
     ASR_TRY(tc::make_map(&ma_hi, a_hi, M, K, tc::BM, BKF, epi.lda));
@@ -663,7 +706,7 @@ static int launch_tc_cfg(const float* a_hi, const float* a_lo, const float* w_hi
     const int tiles_m = (M + tc::BM - 1) / tc::BM, tiles_n = (N + BN - 1) / BN;
     if (cl == 2) return launch_tc_cluster<BN, BKF, STAGES, 2>(ma_hi, ma_lo, w_hi, w_lo, M, N, K, epi, st, dbg_p);
     if (cl == 4) return launch_tc_cluster<BN, BKF, STAGES, 4>(ma_hi, ma_lo, w_hi, w_lo, M, N, K, epi, st, dbg_p);
-    if (cl == 22) return launch_tc_cluster<BN, BKF, STAGES + (BKF == 32 ? 1 : 2), 2, true>(ma_hi, ma_lo, w_hi, w_lo, M, N, K, epi, st, dbg_p);
+    if (cl == 22) return launch_tc_cluster<BN, BKF, STAGES + 2, 2, true>(ma_hi, ma_lo, w_hi, w_lo, M, N, K, epi, st, dbg_p);
     {
         static bool attr_p = false;
         static int num_sms = 0;
@@ -671,19 +714,19 @@ static int launch_tc_cfg(const float* a_hi, const float* a_lo, const float* w_hi
             int dev = 0;
             ASR_CUDA(cudaGetDevice(&dev));
             ASR_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-            ASR_CUDA(cudaFuncSetAttribute(tc::gemm_tf32x3_persistent_kernel<BN, BKF, STAGES, 1>,
+            ASR_CUDA(cudaFuncSetAttribute(tc::gemm_split_persistent_kernel<BN, BKF, STAGES, 1>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, smem_p));
             attr_p = true;
         }
         const int ntiles = tiles_n * tiles_m;
         const int grid_p = ntiles < num_sms ? ntiles : num_sms;
-        tc::gemm_tf32x3_persistent_kernel<BN, BKF, STAGES, 1><<<grid_p, 192, smem_p, st>>>(ma_hi, ma_lo, mw_hi, mw_lo, M, N, K, epi, dbg_p);
+        tc::gemm_split_persistent_kernel<BN, BKF, STAGES, 1><<<grid_p, 192, smem_p, st>>>(ma_hi, ma_lo, mw_hi, mw_lo, M, N, K, epi, dbg_p);
         ASR_CHECK_LAUNCH();
         return ASR_OK;
     }
 }
 
-int launch_gemm_tc(const float* a_hi, const float* a_lo, const float* w_hi, const float* w_lo, int M, int N, int K,
+int launch_gemm_tc(const hi_t* a_hi, const float* a_lo, const hi_t* w_hi, const float* w_lo, int M, int N, int K,
                    const GemmEpilogue& epi, cudaStream_t st, int64_t* launches) {
     if (M <= 0) return ASR_OK;
     if (K % 8) { set_error("gemm_tc: K must be a multiple of 8"); return ASR_ERR_ARG; }
@@ -701,16 +744,10 @@ int launch_gemm_tc(const float* a_hi, const float* a_lo, const float* w_hi, cons
     static const char* env_cell = getenv("ASR_B200_CELL_TILE");
     if (env_cell && epi.kind == Epi::kLstmCell) bn = atoi(env_cell);
     if (env) bn = atoi(env);
-    static const int bk32 = getenv("ASR_B200_GEMM_BK") ? atoi(getenv("ASR_B200_GEMM_BK")) == 32 : 1;   // 128-byte K slabs, 3 stages in the 2-SM form
-    if (bn == 256 && bk32) {
+    if (bn == 256) {
         ASR_TRY((launch_tc_cfg<256, 32, 2>(a_hi, a_lo, w_hi, w_lo, M, N, K, epi, st)));
-    } else if (bn == 224 && bk32) {
-        ASR_TRY((launch_tc_cfg<224, 32, 2>(a_hi, a_lo, w_hi, w_lo, M, N, K, epi, st)));
-    } else if (bn == 256) {
-        // 128 x 256 tile, 64-byte K slabs, 4 stages: twice the MMA work per byte of A in flight
-        ASR_TRY((launch_tc_cfg<256, 16, 4>(a_hi, a_lo, w_hi, w_lo, M, N, K, epi, st)));
     } else if (bn == 224) {
-        ASR_TRY((launch_tc_cfg<224, 16, 4>(a_hi, a_lo, w_hi, w_lo, M, N, K, epi, st)));
+        ASR_TRY((launch_tc_cfg<224, 32, 2>(a_hi, a_lo, w_hi, w_lo, M, N, K, epi, st)));
     } else {
         ASR_TRY((launch_tc_cfg<128, 32, 3>(a_hi, a_lo, w_hi, w_lo, M, N, K, epi, st)));
     }
