@@ -606,6 +606,7 @@ int asr_create(asr_handle** out, const asr_weights* wt, const asr_feature_consts
         const int K = layer == 0 ? kFeat : kEnc;
         if ((rc = split_weight(h, h->w.enc_w_ih[layer], 2 * kGates, K, &h->w.enc_w_ih_hi[layer], &h->w.enc_w_ih_lo[layer])) != ASR_OK) return rc;
         if ((rc = split_weight_legacy(h, h->w.enc_w_hh[layer], 2 * kGates, kEncH, &h->w.enc_w_hh_hi[layer], &h->w.enc_w_hh_lo[layer])) != ASR_OK) return rc;
+        if ((rc = split_weight(h, h->w.enc_w_hh[layer], 2 * kGates, kEncH, &h->w.enc_w_hh_hi16[layer], &h->w.enc_w_hh_x[layer])) != ASR_OK) return rc;
         if ((rc = dev_alloc_t(pool, &h->w.enc_w_hh_lo_bf[layer], (size_t)2 * kGates * kEncH / 2)) != ASR_OK) return rc;
         if ((rc = pack_bf16_pairs(h->w.enc_w_hh_lo[layer], h->w.enc_w_hh_lo_bf[layer], (long long)2 * kGates * kEncH / 2)) != ASR_OK) return rc;
     }

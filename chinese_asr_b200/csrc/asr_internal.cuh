@@ -182,7 +182,9 @@ struct PackedWeights {
     float* att_w_enc_t_lo = nullptr;
     float* enc_w_hh_hi[4] = {};          // [2, 1024, 256] tf32 split of enc_w_hh (tensor-core recurrence)
     float* enc_w_hh_lo[4] = {};
-    uint32_t* enc_w_hh_lo_bf[4] = {};    // [2, 1024, 128] bf16 pairs of the residual (TMEM-resident recurrence)
+    uint32_t* enc_w_hh_lo_bf[4] = {};    // [2, 1024, 128] bf16 pairs of the residual (smem-resident tensor-core recurrence)
+    hi_t* enc_w_hh_hi16[4] = {};         // [2, 1024, 256] fp16 hi + cross words of enc_w_hh (kSplitWeight): the
+    float* enc_w_hh_x[4] = {};           //   TMEM-resident recurrence (encoder_tc3.cu)
     float* att_w_hidden_t = nullptr;     // [128, 512] (W_hidden transposed -> [N, K]) for the query GEMM
     hi_t* att_w_hidden_t_hi = nullptr;
     float* att_w_hidden_t_lo = nullptr;

@@ -3,17 +3,18 @@
 // encoder_tc.cu keeps W_hi in shared memory and re-reads its 128 KB through the UMMA operand path
 // every step (measured: the 64 MMAs of a step are bound by ~64 B/clk of shared-memory operand
 // fetch, ~3.9k cycles).  Here the whole recurrent weight slice of a CTA lives in TMEM:
-//     columns [  0,256) : W_hi  = rn_tf32(W_hh slice)            128 lanes x 256 tf32
-//     columns [256,384) : W_lo  = bf16(W_hh - W_hi), 2 per column 128 lanes x 256 bf16
+//     columns [  0,128) : W_hi  = fp16(W_hh slice), 2 per column             128 lanes x 256 fp16
+//     columns [128,384) : W cross, per 8 values of k [8 x bf16(w) | 8 x bf16(w - w_hi)]   (4 bytes per k)
 //     columns [384,512) : fp32 accumulator D[128 gate cols, NB rows]
-// so shared memory only holds the h operand tiles, which lets one cluster carry up to NB = 80
-// sequences (one round of <= 15 clusters covers 2 directions x 512 sequences).  Per K-step:
-//     D += W_hi (TMEM, tf32) * h_hi^T        tcgen05.mma kind::tf32, A from TMEM
-//     D += W_hi (TMEM, tf32) * h_lo^T        tcgen05.mma kind::tf32, A from TMEM
-//     D += W_lo (TMEM, bf16) * bf16(h)^T     tcgen05.mma kind::f16  (K = 16 per instruction)
-// The W_lo term only needs ~2^-9 relative accuracy (it is 2^-11 of the product), which bf16 gives.
+// (the split-precision operands of gemm_tc.cu: kSplitWeight on the A side, kSplitAct on the h side), so
+// shared memory only holds the h operand tiles, which lets one cluster carry up to NB = 80 sequences
+// (one round of <= 15 clusters covers 2 directions x 512 sequences).  Per step 48 MMAs, all kind::f16:
+//     D += W_hi (TMEM, fp16) * h_hi^T                          16 x (K = 16 values of k)
+//     D += W_x  (TMEM, bf16) * [bf16(h_lo) | bf16(h)]^T        32 x (K = 16 = 8 values of k): w*h_lo + w_lo*h
+// (the tf32 form issued 80: an MMA costs ~65 cycles here whatever its shape).  The cross terms are 2^-11
+// of the product, which bf16's 2^-9 relative accuracy carries to ~2^-20.
 // Exchange of h_{t+1}: as in encoder_tc.cu - each CTA writes the image of its 32-unit slice
-// ([hi | lo | bf16] rows, already in the swizzled UMMA layouts) to global staging and multicasts it
+// ([cross | hi] rows, already in the swizzled UMMA layouts) to global staging and multicasts it
 // with one cp.async.bulk into the tiles of all 8 CTAs; mbarriers only, no cluster barrier per step.
 #include <cooperative_groups.h>
 #include <cuda_bf16.h>
@@ -89,6 +90,14 @@ __device__ __forceinline__ uint32_t sw64_offset(int row, int kk) {
 __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// kind::f16 with fp16 operands (format 0)
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// byte offset of byte `b` (0..127) of row `row` inside a [rows x 128 B] SWIZZLE_128B K-major slab
+__device__ __forceinline__ uint32_t sw128_byte(int row, int b) {
+    return (uint32_t)(row * 128 + ((((b >> 4) ^ (row & 7)) << 4) | (b & 15)));
+}
 template <int N>
 __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t* r);
 template <>
@@ -132,8 +141,8 @@ constexpr int kIssueWarp = 16;
 
 struct Params {
     const float* xg;            // [rows, 2048] permuted gate pre-activations (bias included)
-    const float* whh_hi;        // [2, 1024, 256] permuted, rn_tf32(W_hh)
-    const uint32_t* whh_lo_bf;  // [2, 1024, 128] permuted, bf16 pairs of (W_hh - hi)
+    const hi_t* whh_hi;         // [2, 1024, 256] permuted, fp16(W_hh)                       (gemm_tc.cu kSplitWeight)
+    const uint32_t* whh_x;      // [2, 1024, 256] words: per 8 k, 8 x bf16(w) then 8 x bf16(w - hi)
     const float* x_in;
     int xchg_dsmem;         // 1: exchange h through distributed shared memory, 0: through global staging
     float* y_packed;
@@ -152,7 +161,7 @@ struct Params {
     long long* dbg;
 };
 
-constexpr int kStageBytes = 80 * 320;    // per-CTA staging slot (largest NB)
+constexpr int kStageBytes = 80 * 192;    // per-CTA staging slot (largest NB)
 
 template <int NB>
 __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(kThreads, 1)
@@ -163,9 +172,9 @@ lstm_rec_tc3_kernel(Params p) {
     // (unit, batch row) - no shared-memory transposition and no block barrier in the gate phase.
     constexpr int CW = NB / 4;               // accumulator columns (batch rows) per warp
     constexpr int P = CW / 4;                // cells per lane: rows cg * CW + 4 b + (lane & 3)
-    constexpr int kHi = NB * 128;            // bytes of one hi (or lo) slab
-    constexpr int kBf = NB * 64;             // bytes of one bf16 slab
-    constexpr int kSlab = 2 * kHi + kBf;     // [hi | lo | bf16] of one 32-wide K range
+    constexpr int kX = NB * 128;             // bytes of one cross slab: 32 values of k x [bf16(h_lo) | bf16(h)]
+    constexpr int kHi = NB * 64;             // bytes of one fp16 hi slab
+    constexpr int kSlab = kX + kHi;          // [cross | hi] of one 32-wide K range
     static_assert(NB % 16 == 0, "NB");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -199,33 +208,32 @@ lstm_rec_tc3_kernel(Params p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_alo = tmem_base + 256;
+    const uint32_t tmem_ax = tmem_base + 128;
     const uint32_t tmem_d = tmem_base + 384;
     if (warp < 4) {
         const int m = 32 * warp + lane;                                          // TMEM lane = (unit m >> 2, gate m & 3)
         const size_t wrow = (size_t)dir * kGates + j * 128 + (m & 3) * 32 + (m >> 2);
-        const float* whi = p.whh_hi + wrow * kEncH;
-#pragma unroll 1
-        for (int c0 = 0; c0 < kEncH; c0 += 32) {
-            uint32_t r[32];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const float4 v = *reinterpret_cast<const float4*>(whi + c0 + 4 * q);
-                r[4 * q] = __float_as_uint(v.x); r[4 * q + 1] = __float_as_uint(v.y);
-                r[4 * q + 2] = __float_as_uint(v.z); r[4 * q + 3] = __float_as_uint(v.w);
-            }
-            tmem_st32(tmem_base + ((uint32_t)(32 * warp) << 16) + (uint32_t)c0, r);
-        }
-        const uint32_t* wlo = p.whh_lo_bf + wrow * (kEncH / 2);
+        const uint32_t* whi = reinterpret_cast<const uint32_t*>(p.whh_hi + wrow * kEncH);     // 128 words of fp16 pairs
 #pragma unroll 1
         for (int c0 = 0; c0 < kEncH / 2; c0 += 32) {
             uint32_t r[32];
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-                const uint4 v = *reinterpret_cast<const uint4*>(wlo + c0 + 4 * q);
+                const uint4 v = *reinterpret_cast<const uint4*>(whi + c0 + 4 * q);
                 r[4 * q] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
             }
-            tmem_st32(tmem_alo + ((uint32_t)(32 * warp) << 16) + (uint32_t)c0, r);
+            tmem_st32(tmem_base + ((uint32_t)(32 * warp) << 16) + (uint32_t)c0, r);
+        }
+        const uint32_t* wx = p.whh_x + wrow * kEncH;                                          // 256 words
+#pragma unroll 1
+        for (int c0 = 0; c0 < kEncH; c0 += 32) {
+            uint32_t r[32];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const uint4 v = *reinterpret_cast<const uint4*>(wx + c0 + 4 * q);
+                r[4 * q] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
+            }
+            tmem_st32(tmem_ax + ((uint32_t)(32 * warp) << 16) + (uint32_t)c0, r);
         }
         tmem_wait_st();
     }
@@ -247,7 +255,7 @@ lstm_rec_tc3_kernel(Params p) {
     cluster.sync();
 
     const uint32_t t_base = smem_u32(T);
-    constexpr uint32_t idesc_t = idesc_tf32(128, NB);
+    constexpr uint32_t idesc_h = idesc_f16(128, NB);
     constexpr uint32_t idesc_b = idesc_bf16(128, NB);
 
     // rows are sorted by decreasing length: the active count follows t incrementally
@@ -293,20 +301,18 @@ lstm_rec_tc3_kernel(Params p) {
                 if (s > 0) mbar_wait(h_ready, (uint32_t)((s - 1) & 1));
                 tc_fence_after();
                 if (p.dbg && blockIdx.x == 0) p.dbg[s * 8 + 0] = clock64();
-                const uint64_t dHi0 = kmajor_sw128_desc(t_base);
-                const uint64_t dLo0 = kmajor_sw128_desc(t_base + kHi);
-                const uint64_t dBf0 = kmajor_sw64_desc(t_base + 2 * kHi);
+                const uint64_t dX0 = kmajor_sw128_desc(t_base);
+                const uint64_t dHi0 = kmajor_sw64_desc(t_base + kX);
+                // every MMA consumes 8 TMEM columns of A and 32 bytes of a B row
 #pragma unroll
-                for (int kk = 0; kk < 32; ++kk) {
-                    const uint64_t adv = (uint64_t)(((kk >> 2) * kSlab + (kk & 3) * 32) >> 4);
-                    umma_tf32_ts(tmem_d, tmem_base + (uint32_t)(8 * kk), dHi0 + adv, idesc_t, kk > 0 ? 1u : 0u);
-                    umma_tf32_ts(tmem_d, tmem_base + (uint32_t)(8 * kk), dLo0 + adv, idesc_t, 1u);
-                    if ((kk & 1) == 0) {
-                        // bf16 K-step kb = kk/2: 16 k's = 8 TMEM columns, 32 bytes of the 64-byte row
-                        const int kb = kk >> 1;
-                        const uint64_t advb = (uint64_t)(((kb >> 1) * kSlab + (kb & 1) * 32) >> 4);
-                        umma_bf16_ts(tmem_d, tmem_alo + (uint32_t)(8 * kb), dBf0 + advb, idesc_b, 1u);
-                    }
+                for (int kh = 0; kh < 16; ++kh) {        // 16 values of k each
+                    const uint64_t adv = (uint64_t)(((kh >> 1) * kSlab + (kh & 1) * 32) >> 4);
+                    umma_bf16_ts(tmem_d, tmem_base + (uint32_t)(8 * kh), dHi0 + adv, idesc_h, kh > 0 ? 1u : 0u);
+                }
+#pragma unroll
+                for (int kb = 0; kb < 32; ++kb) {        // 8 values of k each: w * h_lo + w_lo * h
+                    const uint64_t adv = (uint64_t)(((kb >> 2) * kSlab + (kb & 3) * 32) >> 4);
+                    umma_bf16_ts(tmem_d, tmem_ax + (uint32_t)(8 * kb), dX0 + adv, idesc_b, 1u);
                 }
                 umma_commit_mc(mma_done, (uint16_t)0xFF);
                 if (p.dbg && blockIdx.x == 0) p.dbg[s * 8 + 1] = clock64();
@@ -368,15 +374,16 @@ lstm_rec_tc3_kernel(Params p) {
                     const float hh = sigmoid_f(go) * tanh_f(c);
                     c_reg[q] = c;
                     h_reg[q] = hh;
-                    const float hi = rn_tf32(hh);
-                    const float lo = rn_tf32(hh - hi);
+                    const float hi = hi_part(hh);
+                    const float lo = hh - hi;
                     // image of this CTA's 32-unit slab of the next B operand: into global staging, or (all
                     // 8 CTAs' MMAs of this step are complete - mma_done counts 8 commits) straight into
                     // the slab's place in the local operand tile
                     uint8_t* img = p.xchg_dsmem ? T + j * kSlab : stage;
-                    *reinterpret_cast<float*>(img + sw128_offset(i, uu)) = hi;
-                    *reinterpret_cast<float*>(img + kHi + sw128_offset(i, uu)) = lo;
-                    *reinterpret_cast<__nv_bfloat16*>(img + 2 * kHi + sw64_offset(i, uu)) = __float2bfloat16_rn(hh);
+                    const int xb = (uu >> 3) * 32 + (uu & 7) * 2;       // 8-k block: 16 bytes of bf16(h_lo), 16 of bf16(h)
+                    *reinterpret_cast<__nv_bfloat16*>(img + sw128_byte(i, xb)) = __float2bfloat16_rn(lo);
+                    *reinterpret_cast<__nv_bfloat16*>(img + sw128_byte(i, xb + 16)) = __float2bfloat16_rn(hh);
+                    *reinterpret_cast<__half*>(img + kX + sw64_offset(i, uu)) = __float2half_rn(hi);
                     yv[q] = hh + xres[q];
                 }
             }
@@ -441,7 +448,7 @@ __global__ void pack_bf16_pairs_kernel(const float* __restrict__ src, uint32_t* 
 
 template <int NB>
 static int launch(const Params& p, cudaStream_t st) {
-    const size_t smem = 8 * (size_t)(NB * 320) + 1024 + 64 + NB * 4;
+    const size_t smem = 8 * (size_t)(NB * 192) + 1024 + 64 + NB * 4;
     static bool attr = false;
     if (!attr) {
         ASR_CUDA(cudaFuncSetAttribute(lstm_rec_tc3_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -473,8 +480,8 @@ int launch_lstm_recurrence_tc3(asr_handle* h, int layer, const float* xg, const 
     p.y_hi = split_hi;
     p.y_cross = reinterpret_cast<uint32_t*>(split_lo);
     p.xg = xg;
-    p.whh_hi = h->w.enc_w_hh_hi[layer];
-    p.whh_lo_bf = h->w.enc_w_hh_lo_bf[layer];
+    p.whh_hi = h->w.enc_w_hh_hi16[layer];
+    p.whh_x = reinterpret_cast<const uint32_t*>(h->w.enc_w_hh_x[layer]);
     p.x_in = x_in;
     p.y_packed = y_packed;
     p.y_utt = y_utt;
