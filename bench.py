@@ -271,6 +271,7 @@ def run_native(args):
     gemm_ms = stages.pop("gemm_kernel_ms")
     split_ms = stages.pop("operand_split_ms")
     gemm_gflop = stages.pop("gemm_gflop")
+    att_ms = stages.pop("attention_kernel_ms")
     R = B * k
     n_gemm = 4 + 1 + 3 * MAX_LEN
     kernel_ms = dict(stages)
@@ -280,9 +281,10 @@ def run_native(args):
     if dom.startswith("gemm"):
         ach = gemm_gflop / gemm_ms                        # GFLOP / ms = TFLOP/s (algorithmic fp32 2*M*N*K)
         # dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the 125 launches of a pass
-        # (4 encoder projections 8.55 GB, keys 0.77 GB, 40 x (vocabulary 160 MB + cell 64 MB + query 17 MB)):
-        # profiles/r01_kernels.csv, one `ncu --set full` capture of this workload
-        traffic = 18.96e9 / 125 if (B, k, L) == (512, 8, 332) else None
+        # (encoder projections 2.10 + 3 x 1.87 GB, keys 0.61 GB (not captured: operand + output bytes),
+        # 40 x (vocabulary 109 MB + cell 51 MB + query 13 MB)): profiles/r01_kernels.csv, one `ncu --set full`
+        # capture of this workload
+        traffic = 15.24e9 / 125 if (B, k, L) == (512, 8, 332) else None
         roof = {"kernel": "tc::gemm_split_persistent_kernel", "bound": "tensor", "achieved": ach, "peak": tf_peak,
                 "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": traffic,
                 "peak_source": peak_src + " cuBLAS bf16 sustained.  Per 16 values of k the kernel issues one fp16 MMA "
@@ -309,12 +311,25 @@ def run_native(args):
                 "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src}
     stages["gemm_kernel_ms"] = gemm_ms
     stages["operand_split_ms"] = split_ms
+    stages["attention_kernel_ms"] = att_ms
     # the north-star group: one decoder step (cell + attention + projection + top-k) vs HBM roofline
     dec_ms = (stages["dec_cell"] + stages["attention"] + stages["vocab_proj"] + stages["topk_bookkeep"]) / MAX_LEN
     dec_bytes = decoder_step_bytes(B, k, L)
+    # the memory-bound kernel of that group: attention scores + context over the encoder memory.  Per launch it
+    # must read keys_exp (128 floats) + memory (512 floats) of every frame once per utterance, the queries, and
+    # write ctx + its split operand
+    att_bytes = B * L * 2560 + R * (4 * 128 + 4 * 512 + 6 * 512)
+    att_us = 1000.0 * att_ms / MAX_LEN
     dec_roof = {"ms_per_decoder_step": dec_ms, "algorithmic_bytes": dec_bytes,
                 "achieved_gbs": dec_bytes / (dec_ms / 1000.0) / 1e9,
-                "frac_of_hbm_peak": dec_bytes / (dec_ms / 1000.0) / 1e9 / hbm_peak}
+                "frac_of_hbm_peak": dec_bytes / (dec_ms / 1000.0) / 1e9 / hbm_peak,
+                "memory_bound_kernel": {"kernel": "attention_stream_kernel", "bound": "hbm", "us_per_launch": att_us,
+                                        "algorithmic_bytes": att_bytes, "achieved": att_bytes / att_us / 1e3,
+                                        "peak": hbm_peak, "unit": "GB/s", "frac": att_bytes / att_us / 1e3 / hbm_peak,
+                                        "peak_source": peak_src},
+                "note": "the GEMMs of the step (cell, query, vocabulary) are tensor-bound in fp32-faithful "
+                        "split precision, so the whole step sits below the HBM roofline; the attention kernel is "
+                        "the memory-bound part"}
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:      # reported on rank 0 at N = 1 only

@@ -39,7 +39,8 @@ static int dev_upload(std::vector<void*>& pool, T** p, const std::vector<T>& v) 
 
 // ---- stage timing ----------------------------------------------------------------------------
 enum Stage { kStFeat = 0, kStEncGemm, kStEncRec, kStKeys, kStCell, kStAttn, kStProj, kStTopk,
-             kStGemmKernel /* every GEMM-engine launch, nested in the stages above */, kStSplit /* operand split */ };
+             kStGemmKernel /* every GEMM-engine launch, nested in the stages above */, kStSplit /* operand split */,
+             kStAttnKernel = 11 /* the attention kernel alone (nested in kStAttn; slot 10 reports the GEMM GFLOP) */ };
 
 struct StageScope {
     asr_handle* h; cudaStream_t st; int idx;
@@ -294,7 +295,10 @@ static int decoder_step(asr_handle* h, int k, int step, int cur, float temperatu
                 ASR_TRY(launch_gemm_tc(w.dec_split_hi, w.dec_split_lo, h->w.att_w_hidden_t_hi, h->w.att_w_hidden_t_lo, R, kAtt,
                                        kDecH, e, st, &h->launches));
             }
-            ASR_TRY(launch_attention(h, k, step, nxt, d_align_step, st));
+            {
+                StageScope sc4(h, kStAttnKernel, st);
+                ASR_TRY(launch_attention(h, k, step, nxt, d_align_step, st));
+            }
         }
         {
             StageScope sc(h, kStProj, st);

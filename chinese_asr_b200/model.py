@@ -528,9 +528,10 @@ class Model(object):
     def stage_times(self):
         """ms per pipeline stage (CUDA events on the launch stream) + kernel-level timers:
         `gemm_kernel_ms` = all GEMM-engine launches (nested in the stages), `operand_split_ms`,
-        `gemm_gflop` = their algorithmic 2*M*N*K."""
+        `gemm_gflop` = their algorithmic 2*M*N*K, `attention_kernel_ms` = the attention kernel alone."""
         ms = np.zeros(12, dtype=np.float32)
         check(lib.asr_stage_times(self._h, _cabi.fptr(ms), 12), "asr_stage_times")
         names = ("features", "enc_input_gemm", "enc_recurrence", "attn_keys", "dec_cell", "attention",
-                 "vocab_proj", "topk_bookkeep", "gemm_kernel_ms", "operand_split_ms", "gemm_gflop")
+                 "vocab_proj", "topk_bookkeep", "gemm_kernel_ms", "operand_split_ms", "gemm_gflop",
+                 "attention_kernel_ms")
         return dict(zip(names, ms.tolist()))

@@ -240,7 +240,9 @@ int64_t asr_launch_count(asr_handle* h, int reset);
 
 /* Stage timing with CUDA events on `stream` for the next transcribe/decode call:
  * h_ms[8] = {features, encoder input GEMMs, encoder recurrence, keys+init, decoder cell,
- * attention, vocab projection, top-k + bookkeeping + finalise}.  enable=1 records events
+ * attention, vocab projection, top-k + bookkeeping + finalise}; h_ms[8..11] = {all GEMM-engine
+ * launches, operand splits, algorithmic GFLOP of those GEMMs, the attention kernel alone} (nested in
+ * the stages).  enable=1 records events
  * around every stage (adds event overhead); asr_stage_times reads them after a sync. */
 int asr_stage_timing(asr_handle* h, int enable);
 int asr_stage_times(asr_handle* h, float* h_ms, int n);
