@@ -788,9 +788,9 @@ int asr_reserve(asr_handle* h, int max_utts, int64_t max_rows, int max_beam, int
     }
     {
         // tensor-core recurrence staging: 2 directions x ceil(max_utts / 16) chunks x 8 CTAs x 8 KB
-        // (encoder_tc.cu), or 2 x max(7, ceil(max_utts / 80)) chunks x 8 CTAs x 25 KB (encoder_tc3.cu)
+        // (encoder_tc.cu), or 2 x max(7, ceil(max_utts / 128)) chunks x 8 CTAs x 24 KB (encoder_tc3.cu)
         const size_t v2 = (size_t)2 * ((max_utts + 15) / 16) * 8 * 8192;
-        const size_t v3 = (size_t)2 * std::max(7, (max_utts + 79) / 80) * 8 * rec3_stage_bytes_per_cta();
+        const size_t v3 = (size_t)2 * std::max(7, (max_utts + 127) / 128) * 8 * rec3_stage_bytes_per_cta();
         w.rec_stage_ctas = (std::max(v2, v3) + 8191) / 8192;      // capacity in 8 KB units
         ASR_TRY(dev_alloc_t(pool, &w.rec_stage, w.rec_stage_ctas * 2048));
     }

@@ -123,6 +123,19 @@ __device__ __forceinline__ void tmem_ld_cols<10>(uint32_t taddr, uint32_t* r) {
 }
 
 template <>
+__device__ __forceinline__ void tmem_ld_cols<24>(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23])
+                 : "r"(taddr + 16));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+template <>
 __device__ __forceinline__ void tmem_ld_cols<20>(uint32_t taddr, uint32_t* r) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -161,7 +174,8 @@ struct Params {
     long long* dbg;
 };
 
-constexpr int kStageBytes = 80 * 192;    // per-CTA staging slot (largest NB)
+constexpr int kMaxNB = 128;              // sequences per cluster: the accumulator takes TMEM columns [384, 384 + NB)
+constexpr int kStageBytes = kMaxNB * 192;    // per-CTA staging slot (largest NB)
 
 template <int NB>
 __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(kThreads, 1)
@@ -493,10 +507,11 @@ int launch_lstm_recurrence_tc3(asr_handle* h, int layer, const float* xg, const 
     p.uoff = m.d_uoff_sorted;
     p.B = m.B;
     // <= 15 clusters of 8 CTAs are co-resident on a B200 (measured): aim at one round, i.e. at most
-    // 7 chunks per direction, with the smallest operand tile that holds the chunk.
+    // 7 chunks per direction, with the smallest operand tile that holds the chunk (up to 7 x 128 = 896
+    // sequences in one round; the step time grows with NB only through the gate phase and the exchange).
     int rows = (m.B + 6) / 7;
-    int NB = rows <= 16 ? 16 : rows <= 32 ? 32 : rows <= 64 ? 64 : 80;
-    if (rows > 80) rows = 80;
+    int NB = rows <= 16 ? 16 : rows <= 32 ? 32 : rows <= 64 ? 64 : rows <= 80 ? 80 : rows <= 96 ? 96 : 128;
+    if (rows > rec3::kMaxNB) rows = rec3::kMaxNB;
     p.rows_per_chunk = rows;
     p.nchunks = (m.B + rows - 1) / rows;
     if ((size_t)2 * p.nchunks * 8 * rec3::kStageBytes > h->ws.rec_stage_ctas * 8192) {
@@ -511,7 +526,9 @@ int launch_lstm_recurrence_tc3(asr_handle* h, int layer, const float* xg, const 
         case 16: ASR_TRY(rec3::launch<16>(p, st)); break;
         case 32: ASR_TRY(rec3::launch<32>(p, st)); break;
         case 64: ASR_TRY(rec3::launch<64>(p, st)); break;
-        default: ASR_TRY(rec3::launch<80>(p, st)); break;
+        case 80: ASR_TRY(rec3::launch<80>(p, st)); break;
+        case 96: ASR_TRY(rec3::launch<96>(p, st)); break;
+        default: ASR_TRY(rec3::launch<128>(p, st)); break;
     }
     if (dbg) {
         std::vector<long long> hb(8 * 4096);

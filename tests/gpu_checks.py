@@ -490,3 +490,24 @@ def check_driver_wer(cname):
     res["test_model_error_rate"] = tm["error_rate"]
     res["oracle_error_rate"] = float(np.mean([h != r for h, r in zip(hyp, refs)]))
     return res
+
+
+def check_wide_recurrence(B, k=4, group=40, seed=5200):
+    """Batches of 561..896 utterances run the recurrence with 96 / 128 sequences per cluster (one round of 14
+    clusters).  Size-independent property: every hypothesis equals the one decoded in a batch of `group`
+    (16 sequences per cluster)."""
+    weights = O.make_weights(1234, "sharp", eos_bias=8.0)
+    m = get_model((1234, "sharp", 8.0), weights)
+    rng = np.random.default_rng(seed)
+    ns = [int(16000 * (1.2 + 1.3 * rng.random())) for _ in range(B)]
+    pcm = np.concatenate([O.synth_pcm_int16(seed + i, n) for i, n in enumerate(ns)])
+    off = np.zeros(B + 1, dtype=np.int64)
+    off[1:] = np.cumsum(ns)
+    tok, ln, sc = m.transcribe(pcm, off, bw=k)
+    same, score_rel = 0, 0.0
+    for g0 in range(0, B, group):
+        g1 = min(B, g0 + group)
+        t1, l1, s1 = m.transcribe(pcm[off[g0]:off[g1]], off[g0:g1 + 1] - off[g0], bw=k)
+        same += int(sum(int(l1[i] == ln[g0 + i] and (t1[i] == tok[g0 + i]).all()) for i in range(g1 - g0)))
+        score_rel = max(score_rel, float(np.max(np.abs(s1 - sc[g0:g1]) / np.maximum(1.0, np.abs(sc[g0:g1])))))
+    return {"same": same, "of": B, "score_rel": score_rel, "len_spread": int(ln.max() - ln.min())}

@@ -221,3 +221,10 @@ def test_transcribe_int16_equals_float32(G):
     assert all(np.array_equal(p, q) for p, q in zip(a, c)) and all(np.array_equal(p, q) for p, q in zip(a, d))
     with pytest.raises(TypeError):
         m.transcribe(x16.astype(np.int32), off, bw=4)
+
+
+@pytest.mark.parametrize("B", [600, 700])
+def test_wide_recurrence_batches_are_batch_invariant(G, B):
+    """96 (B = 600) and 128 (B = 700) sequences per recurrence cluster against 16 per cluster."""
+    r = G.check_wide_recurrence(B)
+    assert r["same"] >= r["of"] - 1 and r["score_rel"] <= SCORE_RTOL and r["len_spread"] > 0, r
