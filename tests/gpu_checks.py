@@ -206,6 +206,29 @@ def check_gemm(mode):
         out = m.test_gemm(A.cuda(), W.cuda(), b.cuda(), mode).cpu().double()
         scale = float(ref.abs().max())
         res[f"{M}x{N}x{K}_relerr"] = float((out - ref).abs().max()) / scale
+    # dynamic range of the fp16 hi part, per ROW of A so that every output row is dominated by its own magnitude.
+    # fp16's normal range (6.1e-5 ... 65504): full relative accuracy, measured per row against the row's largest |C|
+    M, N, K = 384, 256, 512
+    W = torch.randn(N, K, generator=g) * 0.05
+    b = torch.zeros(N)
+    mag = 10.0 ** torch.linspace(-4.0, 4.0, M)            # 6 sigma of the largest row stays below 65504
+    A = torch.randn(M, K, generator=g) * mag[:, None]
+    ref = A.double() @ W.double().t()
+    out = m.test_gemm(A.cuda(), W.cuda(), b.cuda(), mode).cpu().double()
+    res["normal_range_rowwise_relerr"] = float(((out - ref).abs().max(dim=1).values / ref.abs().max(dim=1).values).max())
+    # below it (down to values whose hi part is 0): the cross operand carries what hi dropped, so the ABSOLUTE error
+    # stays ~2^-34 |w| per term (outputs here are ~1e-6; the bound asserted is 1e-8 for the tensor-core engine)
+    mag = 10.0 ** torch.linspace(-8.0, -5.0, M)
+    A = torch.randn(M, K, generator=g) * mag[:, None]
+    ref = A.double() @ W.double().t()
+    out = m.test_gemm(A.cuda(), W.cuda(), b.cuda(), mode).cpu().double()
+    res["tiny_abs_err_x1e3"] = float((out - ref).abs().max()) * 1e3
+    # beyond fp16's range the hi part saturates and the residual is carried at bf16 accuracy only: still finite
+    A2 = torch.randn(128, K, generator=g) * 3e5
+    out2 = m.test_gemm(A2.cuda(), W.cuda(), b.cuda(), mode).cpu().double()
+    ref2 = A2.double() @ W.double().t()
+    res["saturated_finite"] = 0.0 if bool(torch.isfinite(out2).all()) else 1.0
+    res["saturated_relerr_x1e-3"] = float((out2 - ref2).abs().max() / ref2.abs().max()) * 1e-3
     return res
 
 

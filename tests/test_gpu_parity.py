@@ -49,8 +49,10 @@ def test_encoder(G, cname):
 
 @pytest.mark.parametrize("mode", ["simt", "tc"])
 def test_gemm_engines_fp32_faithful(G, mode):
-    # max |C - C_fp64| / max |C_fp64|.  CUDA-core fp32 FMA: ~1e-6.  tcgen05 3xTF32: the products are
-    # fp32-exact but the tensor core accumulates with truncation, measured 3-7e-6 at K <= 1024.
+    # max |C - C_fp64| / max |C_fp64|.  CUDA-core fp32 FMA: ~1e-6.  tcgen05 split precision (fp16 hi + bf16
+    # cross terms): the products are fp32-faithful but the tensor core accumulates with truncation, measured
+    # 3-7e-6 at K <= 1024.  Also: row-wise accuracy over fp16's normal range (1e-4 ... 1e4 row magnitudes),
+    # the absolute error bound below it, and finite results (bf16-accurate residual) when |a| > 65504.
     r = G.check_gemm(mode)
     tol = 2e-6 if mode == "simt" else 1e-5
     for k, v in r.items():
@@ -228,3 +230,29 @@ def test_wide_recurrence_batches_are_batch_invariant(G, B):
     """96 (B = 600) and 128 (B = 700) sequences per recurrence cluster against 16 per cluster."""
     r = G.check_wide_recurrence(B)
     assert r["same"] >= r["of"] - 1 and r["score_rel"] <= SCORE_RTOL and r["len_spread"] > 0, r
+
+
+def test_frontend_and_wer_errors_are_loud(G):
+    import ctypes as C
+    from chinese_asr_b200 import _cabi
+    from chinese_asr_b200._cabi import AsrError
+    from chinese_asr_b200.model import Model
+    from oracle import asr_oracle as O
+    m = Model()
+    m.load_state(O.make_weights(1234, "plain"))
+    i2w = G.vocab()[1]
+    with pytest.raises(AsrError):                                   # no resident hypotheses yet, no vocabulary
+        _cabi.check(_cabi.lib.asr_wer(m._h, None, None, 0, (C.c_int32 * 1)(65), (C.c_int64 * 2)(0, 1), 1,
+                                      (C.c_int32 * 1)(), None, None), "asr_wer")
+    with pytest.raises(AsrError):                                   # decode first: nothing resident for B = 3
+        m.wer([[10], [11], [12]], i2w)
+    with pytest.raises(AsrError):                                   # unknown sample format
+        m.reserve(1, 100, 4, 32000)
+        x = torch.zeros(32000, device="cuda")
+        _cabi.check(_cabi.lib.asr_features_pcm(m._h, C.c_void_p(x.data_ptr()), 7, (C.c_int64 * 2)(0, 32000), 1,
+                                               C.c_void_p(x.data_ptr()), (C.c_int32 * 1)(), 1, 1e-6, None), "asr_features_pcm")
+    with pytest.raises(ValueError):
+        m.cmvn([torch.zeros(5, 100)])
+    one = m.cmvn([torch.ones(1, 720, device="cuda")])[0]           # a single row: unbiased std is NaN, like torch.std
+    assert bool(torch.isnan(one).all())
+    m.close()
