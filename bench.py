@@ -32,7 +32,7 @@ V = 5004
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--batch", type=int, default=512,
@@ -42,6 +42,9 @@ def parse_args():
     ap.add_argument("--seconds", type=float, default=SECONDS)
     ap.add_argument("--cpu-sample", type=int, default=64, help="utterances per batch of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pipeline", type=int, default=2,
+                    help="engines (handles) per GPU with batches in flight: the latency-bound encoder of one batch "
+                         "overlaps the decoder of another (chinese_asr_b200.parallel.BatchPipeline); 1 = one handle")
     return ap.parse_args()
 
 
@@ -186,28 +189,40 @@ def run_native(args):
     n = int(args.seconds * SR)
     L = (1 + (n - 1 - 512) // 160) // 3
 
-    m = Model()
-    m.load_state(O.make_weights(1234, "plain"))
-    m.reserve(B, B * L, k, B * n, MAX_LEN)
+    S = max(1, args.pipeline)
+    weights = O.make_weights(1234, "plain")
+    models = []
+    for _ in range(S):
+        mm = Model()
+        mm.load_state(weights)
+        mm.reserve(B, B * L, k, B * n, MAX_LEN)
+        models.append(mm)
+    m = models[0]
+    pipe = parallel.BatchPipeline(models)
     off = (np.arange(B + 1, dtype=np.int64) * n)
-    # 16-bit PCM (what WAV files hold): converted to float32 by the log-mel kernel (asr_transcribe_pcm, ASR_PCM_S16)
-    host = torch.from_numpy(synth_batch_s16(B, n, 1000 + rank).reshape(-1)).pin_memory()
-    host2 = host.clone().pin_memory()          # end-to-end steps alternate between two host buffers
-    resident = host.to(dev)
+    # 16-bit PCM (what WAV files hold): converted to float32 by the log-mel kernel (asr_transcribe_pcm, ASR_PCM_S16).
+    # End-to-end steps cycle through 2 pinned host buffers per engine.
+    hosts = [torch.from_numpy(synth_batch_s16(B, n, 1000 + rank + 17 * i).reshape(-1)).pin_memory()
+             for i in range(2 * S)]
+    resident = hosts[0].to(dev)
     total = B * world
 
-    def step(e2e):
+    def run_steps(e2e, steps, first=0):
+        """`steps` batches of B utterances per GPU, handed round-robin to the S engines (each on its own host
+        thread and stream).  e2e: every batch starts in pinned host memory (its H2D copy is inside the call) and
+        ends with the hypotheses on the host; otherwise the PCM is resident in HBM."""
         if e2e:
-            # a server's pipeline: the copy of the next batch overlaps this batch's decode
-            if e2e > 1:
-                m.prefetch(host2 if (e2e & 1) else host, off, bw=k)
-            tok, ln, sc = m.transcribe(host if (e2e & 1) else host2, off, bw=k)
+            # a server's pipeline: every engine stages its next batch's PCM while it decodes the current one
+            results = pipe.map([(hosts[(first + i) % (2 * S)], off) for i in range(steps)], prefetch=True, bw=k)
         else:
-            tok, ln, sc = m.transcribe(resident, off, bw=k, resident=True)
-        if world > 1:   # the one collective of the path: gather the hypotheses
-            rec = parallel.pack_records(np.arange(B) + rank * B, tok, ln, sc, MAX_LEN)
-            tok, ln, sc = parallel.gather_hypotheses(rec, total, MAX_LEN, device=dev)
-        return tok, ln, sc
+            results = pipe.map([(resident, off)] * steps, bw=k, resident=True)
+        out = None
+        for tok, ln, sc in results:
+            if world > 1:   # the one collective of the path: gather the hypotheses (same order on every rank)
+                rec = parallel.pack_records(np.arange(B) + rank * B, tok, ln, sc, MAX_LEN)
+                tok, ln, sc = parallel.gather_hypotheses(rec, total, MAX_LEN, device=dev)
+            out = (tok, ln, sc)
+        return out
 
     def timed(e2e, steps):
         if world > 1:
@@ -215,14 +230,7 @@ def run_native(args):
         torch.cuda.synchronize()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-        if e2e:
-            # e2e codes: odd / even = which host buffer this step reads; > 1 = prefetch the next step's
-            m.prefetch(host, off, bw=k)
-            for i in range(steps):
-                step((1 if i % 2 == 0 else 2) + (2 if i + 1 < steps else 0))
-        else:
-            for _ in range(steps):
-                step(0)
+        run_steps(e2e, steps)          # returns when every batch's results are on the host
         ev1.record()
         torch.cuda.synchronize()
         ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
@@ -231,23 +239,29 @@ def run_native(args):
             dist.barrier()
         return float(ms.item())
 
-    for _ in range(max(args.warmup, 3)):
-        step(0)
-    timed(True, 2)          # untimed here: first use of the prefetch staging buffers allocates them
+    # warm-up: every engine alone first (workspaces, launch-time statics, graph capture on its second batch) ...
+    pipe.each(lambda mm: [mm.transcribe(resident, off, bw=k, resident=True) for _ in range(2)])
+    pipe.each(lambda mm: mm.transcribe(hosts[0], off, bw=k))
+    # ... then W untimed steps through the pipeline
+    run_steps(False, max(args.warmup, 3))
+    run_steps(True, S)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    m.launch_count(reset=True)
+    for mm in models:
+        mm.launch_count(reset=True)
     ms_dev = timed(False, args.steps)
-    launches = m.launch_count(reset=True)
+    launches = sum(mm.launch_count(reset=True) for mm in models)
     ms_e2e = timed(True, args.steps)
     clocks = sampler.stop() if rank == 0 else None
 
     # instrumented repeat of the same step: per-stage CUDA-event durations on the launch stream
+    # (one engine alone: the stage durations of a solo batch)
     m.stage_timing(True)
-    step(0)
+    pipe.each(lambda mm: mm.transcribe(resident, off, bw=k, resident=True) if mm is m else None)
     stages = m.stage_times()
     m.stage_timing(False)
+    pipe.close()
 
     if rank != 0:
         if world > 1:
@@ -347,6 +361,9 @@ def run_native(args):
         "config": {"workload": f"bw={k} beam decode of {args.seconds:g} s 16 kHz utterances, {B} per GPU per step "
                                f"(BASELINE.json configs[4]: 4096 utterances over 8 GPUs)",
                    "beam": k, "utts_per_gpu_per_step": B, "utt_seconds": args.seconds, "max_len": MAX_LEN,
+                   "engines_per_gpu": S,
+                   "pipeline": ("%d handles per GPU, batches handed round-robin, each engine on its own host thread and "
+                                "stream: one batch's encoder overlaps another's decoder" % S) if S > 1 else "one handle",
                    "enc_frames_per_utt": L, "weights": "random-init (reference initialisers), fp32",
                    "pcm": "int16 (16-bit WAV samples), converted on the device",
                    "l2_policy": "inputs larger than L2 (PCM %.0f MB, gate pre-activations %.0f MB per step)"

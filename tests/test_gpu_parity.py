@@ -256,3 +256,37 @@ def test_frontend_and_wer_errors_are_loud(G):
     one = m.cmvn([torch.ones(1, 720, device="cuda")])[0]           # a single row: unbiased std is NaN, like torch.std
     assert bool(torch.isnan(one).all())
     m.close()
+
+
+def test_batch_pipeline_two_engines_equal_one(G):
+    """Two handles on one GPU with batches in flight on two host threads / streams (BatchPipeline) decode
+    exactly what one handle decodes, batch by batch, in submission order."""
+    from chinese_asr_b200.model import Model
+    from chinese_asr_b200.parallel import BatchPipeline
+    from oracle import asr_oracle as O
+    w = O.make_weights(1234, "sharp", eos_bias=8.0)
+    one = G.get_model((1234, "sharp", 8.0), w)
+    B, n = 24, 40000
+    batches = []
+    for j in range(5):
+        x = np.stack([O.synth_pcm_int16(9100 + 100 * j + i, n) for i in range(B)]).reshape(-1)
+        batches.append((x, np.arange(B + 1, dtype=np.int64) * n))
+    want = [one.transcribe(x, off, bw=4) for x, off in batches]
+    engines = []
+    for _ in range(2):
+        m = Model()
+        m.load_state(w)
+        engines.append(m)
+    pipe = BatchPipeline(engines)
+    for rounds in range(2):                     # second round: both engines replay their captured graphs
+        got = pipe.map(batches, bw=4)
+        for a, b in zip(want, got):
+            assert all(np.array_equal(p, q) for p, q in zip(a, b))
+    # every engine stages its next batch on its copy stream while it decodes the current one
+    pinned = [(torch.from_numpy(x).pin_memory(), off) for x, off in batches]
+    got = pipe.map(pinned, prefetch=True, bw=4)
+    for a, b in zip(want, got):
+        assert all(np.array_equal(p, q) for p, q in zip(a, b))
+    pipe.close()
+    for m in engines:
+        m.close()

@@ -96,3 +96,34 @@ def test_gather_hypotheses_gloo(world):
     for p in procs:
         p.join(timeout=60)
     assert all(ok for _, ok in res) and len(res) == world
+
+
+def test_batch_pipeline_round_robin_and_order():
+    """BatchPipeline hands batches to its engines in round-robin order, one worker thread per engine, and the
+    futures keep submission order (host-only fake engines: no device involved)."""
+    import threading
+    import time
+    from chinese_asr_b200.parallel import BatchPipeline
+
+    class Fake:
+        device = None
+
+        def __init__(self, name, delay):
+            self.name, self.delay, self.threads, self.seen = name, delay, set(), []
+
+        def transcribe(self, pcm, offsets, **kw):
+            self.threads.add(threading.get_ident())
+            self.seen.append(pcm)
+            time.sleep(self.delay)
+            return (self.name, pcm, kw.get("bw"))
+
+    a, b = Fake("a", 0.03), Fake("b", 0.0)
+    pipe = BatchPipeline([a, b])
+    res = pipe.map([(i, None) for i in range(6)], bw=8)
+    assert res == [("a", 0, 8), ("b", 1, 8), ("a", 2, 8), ("b", 3, 8), ("a", 4, 8), ("b", 5, 8)]
+    assert a.seen == [0, 2, 4] and b.seen == [1, 3, 5]
+    assert len(a.threads) == 1 and len(b.threads) == 1 and a.threads != b.threads
+    assert pipe.each(lambda m: m.name) == ["a", "b"]
+    pipe.close()
+    with pytest.raises(ValueError):
+        BatchPipeline([])
