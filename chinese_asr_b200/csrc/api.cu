@@ -1076,9 +1076,17 @@ int asr_prefetch_pcm(asr_handle* h, const float* h_pcm, const int64_t* h_pcm_off
 
 static int issue_prefetch(asr_handle* h, int slot) {
     if (!h->pre_src[slot] || h->pre_issued[slot]) return ASR_OK;
-    ASR_CUDA(cudaMemcpyAsync(h->ws.pcm_pre[slot], h->pre_src[slot],
-                             pcm_sample_bytes(h->pre_fmt[slot]) * (size_t)h->pre_n[slot],
-                             cudaMemcpyHostToDevice, h->copy_stream));
+    // In pieces: a copy engine serves its queue in order, so one 160 MB operation would hold back every small
+    // (synchronous) metadata upload issued meanwhile - by this handle or by another engine of the same GPU
+    // (BatchPipeline) - for its whole duration; between pieces other streams' copies get their turn.
+    {
+        const size_t bytes = pcm_sample_bytes(h->pre_fmt[slot]) * (size_t)h->pre_n[slot];
+        static const size_t piece = getenv("ASR_B200_PREFETCH_PIECE") ? (size_t)atoll(getenv("ASR_B200_PREFETCH_PIECE")) : ((size_t)4 << 20);
+        const char* src = static_cast<const char*>(h->pre_src[slot]);
+        char* dst = reinterpret_cast<char*>(h->ws.pcm_pre[slot]);
+        for (size_t o = 0; o < bytes; o += piece)
+            ASR_CUDA(cudaMemcpyAsync(dst + o, src + o, std::min(piece, bytes - o), cudaMemcpyHostToDevice, h->copy_stream));
+    }
     ASR_CUDA(cudaEventRecord(h->pre_ev[slot], h->copy_stream));
     h->pre_issued[slot] = true;
     return ASR_OK;

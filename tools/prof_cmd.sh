@@ -2,8 +2,8 @@
 # The .ncu-rep stays on the box (/tmp: gpurun_out/ is capped at 64 MiB); its raw page comes back as CSV.
 set -x
 rm -f gpurun_out/*.ncu-rep
-python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/plain_bench.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches_r01.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
+python bench.py --steps 2 --warmup 3 --no-cpu-baseline --pipeline 1 > gpurun_out/plain_bench.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches_r01.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --pipeline 1 > gpurun_out/ncu_bench.log 2>&1
 echo "launch list rc=$?"
 python tools/prof_step.py 512 8 1 > gpurun_out/plain_prof.log 2>&1 &&
 ncu --set full --clock-control none --launch-skip 258 --launch-count 28 -f -o /tmp/prof_r01_all python tools/prof_step.py 512 8 1 > gpurun_out/ncu_prof.log 2>&1

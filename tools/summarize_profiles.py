@@ -45,8 +45,9 @@ def launches():
         a[1] += v
     tot = sum(v[1] for v in agg.values())
     with open(os.path.join(out_dir, f"{tag}_launches.md"), "w") as f:
-        f.write(f"# ncu launch list, {tag}: `python bench.py --steps 2 --warmup 3 --no-cpu-baseline` (512 x 10 s\n"
-                "# utterances per pass, bw=8; 5 device-resident passes, 4 end-to-end passes, 1 stage-timed pass; tools/prof_cmd.sh),\n"
+        f.write(f"# ncu launch list, {tag}: `python bench.py --steps 2 --warmup 3 --no-cpu-baseline --pipeline 1` (one engine;\n"
+                "# 512 x 10 s utterances per pass, bw=8; 5 device-resident passes, 4 end-to-end passes, 1 stage-timed pass;\n"
+                "# tools/prof_cmd.sh.  With the default two engines the same kernels run, interleaved from two streams),\n"
                 "# `ncu --metrics gpu__time_duration.sum --clock-control none -c 4000` after the same command exited 0\n"
                 "# without ncu.  Per-launch times are cold-cache and serialised: compare SHARES with stage_ms.\n\n")
         f.write("| kernel | launches | total ms | avg us | share |\n|---|---:|---:|---:|---:|\n")
