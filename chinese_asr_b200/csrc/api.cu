@@ -171,7 +171,8 @@ static int run_encoder(asr_handle* h, int upto_layer, cudaStream_t st) {
     // separate split pass (read 4 B, write 8 B per element, 4 x 170k x 512 per batch) disappears.
     static const bool fuse_env = !(getenv("ASR_B200_FUSED_ENC_SPLIT") && atoi(getenv("ASR_B200_FUSED_ENC_SPLIT")) == 0);
     const bool fuse = fuse_env && h->gemm_mode == 1 && h->rec_mode == 2 && w.a_hi;
-    bool presplit = false;
+    bool presplit = h->feat_split_ready;      // layer 0: the feature kernel wrote the split operand
+    h->feat_split_ready = false;
     h->enc_split_ready = false;
     for (int layer = 0; layer <= upto_layer; ++layer) {
         {
@@ -515,8 +516,14 @@ static int features_device(asr_handle* h, const void* d_pcm, int format, const i
     ASR_TRY(launch_logmel(h, d_pcm, format, w.d_pcm_off, w.d_frame_off, B, foff[B], w.mel, st));
     int lmax = 0;
     for (int i = 0; i < B; ++i) lmax = std::max(lmax, (int)h_L[i]);
+    // Fused path (PCM -> hypotheses): the features are only ever read by the layer-0 input GEMM, so they are written
+    // straight as its split A operand (6 bytes per value) instead of fp32 + a split pass (4 + 4 + 6 bytes)
+    static const bool fuse_env = !(getenv("ASR_B200_FUSED_FEAT_SPLIT") && atoi(getenv("ASR_B200_FUSED_FEAT_SPLIT")) == 0);
+    const bool fuse = packed_out && fuse_env && h->gemm_mode == 1 && w.a_hi != nullptr;
     ASR_TRY(launch_delta_cmvn(h, w.mel, w.d_frame_off, w.d_featrow_off, B, lmax, normalise, eps,
-                              packed_out ? h->meta.d_feat2packed : nullptr, d_out, st));
+                              packed_out ? h->meta.d_feat2packed : nullptr, fuse ? nullptr : d_out, st,
+                              fuse ? w.a_hi : nullptr, fuse ? w.a_lo : nullptr));
+    h->feat_split_ready = fuse;
     return ASR_OK;
 }
 
@@ -884,6 +891,7 @@ int asr_encode(asr_handle* h, const float* d_feats, const int32_t* h_L, int B, v
     cudaStream_t st = (cudaStream_t)stream;
     ASR_TRY(prepare_batch(h, h_L, B, st));
     ASR_TRY(launch_pack_rows(h, d_feats, h->meta.d_pack_src, h->meta.rows, kFeat, h->ws.xpack, st));
+    h->feat_split_ready = false;          // the caller's features: layer 0 splits xpack itself
     ASR_TRY(run_encoder(h, 3, st));
     ASR_TRY(run_keys(h, st));
     h->encoded = true;
@@ -896,6 +904,7 @@ int asr_encode_layers(asr_handle* h, const float* d_feats, const int32_t* h_L, i
     cudaStream_t st = (cudaStream_t)stream;
     ASR_TRY(prepare_batch(h, h_L, B, st));
     ASR_TRY(launch_pack_rows(h, d_feats, h->meta.d_pack_src, h->meta.rows, kFeat, h->ws.xpack, st));
+    h->feat_split_ready = false;
     ASR_TRY(run_encoder(h, upto_layer, st));
     ASR_TRY(launch_export_packed_padded(h, h->ws.act[upto_layer & 1], kEnc, d_layer_out, st));
     ASR_CUDA(cudaStreamSynchronize(st));

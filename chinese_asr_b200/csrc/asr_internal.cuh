@@ -332,6 +332,7 @@ struct asr_handle {
     int pre_fmt[2] = {};                    // asr_pcm_format of the staged samples
     bool pre_issued[2] = {};                // the copy has been enqueued (it is issued behind the next batch's uploads)
     uint64_t pre_count = 0;
+    bool feat_split_ready = false;  // ws.a_hi / a_lo hold the split of the packed features (written by feat_write_kernel)
     bool enc_split_ready = false;  // ws.a_hi / a_lo hold the split of `enc` (written by the last recurrence)
     bool fused_dec = false;     // decoder step with pre-multiplied embeddings and producer-side operand splits
     double gemm_flops = 0.0;     // algorithmic 2*M*N*K of every GEMM-engine launch since the last reset
@@ -351,7 +352,8 @@ int launch_logmel(asr_handle* h, const void* d_pcm, int format, const long long*
 // out_rowmap: feature row (utterance-major, original order) -> output row; nullptr = identity
 int launch_delta_cmvn(asr_handle* h, const float* d_mel, const int* d_frame_off,
                       const int* d_featrow_off, int B, int max_rows_per_utt, int normalise, float eps,
-                      const int* out_rowmap, float* d_out, cudaStream_t st);
+                      const int* out_rowmap, float* d_out, cudaStream_t st, hi_t* split_hi = nullptr,
+                      float* split_x = nullptr);   // optional: also (or only, d_out = nullptr) the split GEMM operand
 // AudioLoader.batch_audio (data.py:513-518) on features that already exist
 int launch_cmvn(asr_handle* h, const float* d_in, const int* d_featrow_off, int B, int max_rows_per_utt,
                 float eps, float* d_out, cudaStream_t st);

@@ -12,6 +12,7 @@
 //                        with column c*240 + j*80 + m (data.py:244-249), then (x-mean)/(std+1e-6)
 //                        per column with the unbiased std (main.py:37).
 // Both are HBM/L2-bound streaming kernels: algorithmic bytes per utterance 4N + 4*720*L.
+#include <cuda_bf16.h>
 #include <math.h>
 
 #include <vector>
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(960)
 feat_write_kernel(const float* __restrict__ mel, const int* __restrict__ frame_off,
                   const int* __restrict__ featrow_off, Taps taps, int normalise, float eps,
                   const double2* __restrict__ partial, const int* __restrict__ out_rowmap,
-                  float* __restrict__ out) {
+                  float* __restrict__ out, hi_t* __restrict__ split_hi, uint32_t* __restrict__ split_x) {
     __shared__ __align__(16) float s_mel[kSubFrames * kMel];
     __shared__ float s_mean[kFeat], s_den[kFeat];
     const int u = blockIdx.x;
@@ -259,7 +260,17 @@ feat_write_kernel(const float* __restrict__ mel, const int* __restrict__ frame_o
                [&](int g, int c, float v) {
                    const int col = c * 240 + x;
                    const int row = out_rowmap ? out_rowmap[r0 + g] : (r0 + g);
-                   out[(size_t)row * kFeat + col] = normalise ? (v - s_mean[col]) / s_den[col] : v;
+                   const float val = normalise ? (v - s_mean[col]) / s_den[col] : v;
+                   if (out) out[(size_t)row * kFeat + col] = val;
+                   if (split_hi) {
+                       // the A operand of the layer-0 input GEMM, already split (gemm_tc.cu kSplitAct): fp16 hi and,
+                       // per 8 values, 8 x bf16(x - hi) then 8 x bf16(x) - no separate split pass over the features
+                       const float hi = hi_part(val);
+                       split_hi[(size_t)row * kFeat + col] = __float2half_rn(hi);
+                       __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(split_x + (size_t)row * kFeat + (col & ~7));
+                       xb[col & 7] = __float2bfloat16_rn(val - hi);
+                       xb[8 + (col & 7)] = __float2bfloat16_rn(val);
+                   }
                });
 }
 
@@ -390,7 +401,7 @@ int launch_logmel(asr_handle* h, const void* d_pcm, int format, const long long*
 
 int launch_delta_cmvn(asr_handle* h, const float* d_mel, const int* d_frame_off,
                       const int* d_featrow_off, int B, int max_rows_per_utt, int normalise, float eps,
-                      const int* out_rowmap, float* d_out, cudaStream_t st) {
+                      const int* out_rowmap, float* d_out, cudaStream_t st, hi_t* split_hi, float* split_x) {
     Taps t;
     for (int i = 0; i < 27; ++i) t.w[i] = h->fc.taps[i];
     dim3 block(240, 4);
@@ -402,7 +413,7 @@ int launch_delta_cmvn(asr_handle* h, const float* d_mel, const int* d_frame_off,
     }
     feat_write_kernel<<<dim3(B, (max_rows_per_utt + kSubRows - 1) / kSubRows), block, 0, st>>>(
         d_mel, d_frame_off, d_featrow_off, t, normalise, eps, reinterpret_cast<const double2*>(h->ws.feat_partial),
-        out_rowmap, d_out);
+        out_rowmap, d_out, split_hi, reinterpret_cast<uint32_t*>(split_x));
     ASR_CHECK_LAUNCH();
     h->launches++;
     return ASR_OK;

@@ -290,3 +290,30 @@ def test_batch_pipeline_two_engines_equal_one(G):
     pipe.close()
     for m in engines:
         m.close()
+
+
+def test_config3_full_size_properties(G):
+    """BASELINE.json configs[2] at its full size: bw=16, 256 utterances of mixed 2-20 s (padding / masking / EOS
+    handling).  The oracle cannot finish this in seconds, so the size-independent properties are checked:
+    bit-reproducible, lengths within bounds, and batch-invariant - the shortest, the longest and four other
+    utterances decode to the same tokens alone (B = 1) as inside the batch of 256."""
+    from oracle import asr_oracle as O
+    m = G.get_model((77, "sharp", 9.0), O.make_weights(77, "sharp", eos_bias=9.0))
+    rng = np.random.default_rng(2600)
+    B = 256
+    secs = rng.integers(2, 21, size=B)
+    ns = [int(16000 * s) for s in secs]
+    pcms = [O.synth_pcm_int16(26000 + i, n) for i, n in enumerate(ns)]
+    off = np.zeros(B + 1, dtype=np.int64)
+    off[1:] = np.cumsum(ns)
+    x = np.concatenate(pcms)
+    t1, l1, s1 = m.transcribe(x, off, bw=16)
+    t2, l2, s2 = m.transcribe(x, off, bw=16)
+    assert np.array_equal(t1, t2) and np.array_equal(l1, l2) and np.array_equal(s1, s2)
+    assert l1.min() >= 0 and l1.max() <= 40 and np.isfinite(s1).all() and len(set(l1.tolist())) > 3
+    picks = [int(np.argmin(ns)), int(np.argmax(ns)), 7, 100, 180, 255]
+    same = 0
+    for i in picks:
+        ta, la, sa = m.transcribe(pcms[i], np.array([0, ns[i]], dtype=np.int64), bw=16)
+        same += int(la[0] == l1[i] and np.array_equal(ta[0], t1[i]) and abs(float(sa[0]) - float(s1[i])) <= SCORE_RTOL * max(1.0, abs(float(s1[i]))))
+    assert same == len(picks), (same, picks)
