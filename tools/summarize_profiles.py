@@ -46,7 +46,7 @@ def launches():
     tot = sum(v[1] for v in agg.values())
     with open(os.path.join(out_dir, f"{tag}_launches.md"), "w") as f:
         f.write(f"# ncu launch list, {tag}: `python bench.py --steps 2 --warmup 3 --no-cpu-baseline --pipeline 1` (one engine;\n"
-                "# 512 x 10 s utterances per pass, bw=8; 5 device-resident passes, 4 end-to-end passes, 1 stage-timed pass;\n"
+                "# 512 x 10 s utterances per pass, bw=8; 7 device-resident passes, 4 end-to-end passes, 1 stage-timed pass;\n"
                 "# tools/prof_cmd.sh.  With the default two engines the same kernels run, interleaved from two streams),\n"
                 "# `ncu --metrics gpu__time_duration.sum --clock-control none -c 4000` after the same command exited 0\n"
                 "# without ncu.  Per-launch times are cold-cache and serialised: compare SHARES with stage_ms.\n\n")
@@ -70,15 +70,29 @@ def kernels():
         if len(rows) < 3:
             continue
         hdr = rows[0]
+        units = rows[1]
         idx = {h: i for i, h in enumerate(hdr)}
+        # ncu picks a unit per report: normalise durations to ms and DRAM bytes to GB
+        scale = {"ns": 1e-6, "us": 1e-3, "usecond": 1e-3, "ms": 1.0, "msecond": 1.0, "s": 1e3, "second": 1e3,
+                 "byte": 1e-9, "Kbyte": 1e-6, "Mbyte": 1e-3, "Gbyte": 1.0}
         for r in rows[2:]:
             d = {"report": os.path.basename(rep), "kernel": r[idx["Kernel Name"]].split("(")[0].replace("void ", "")}
             for k in KEEP:
-                d[k] = r[idx[k]] if k in idx else ""
+                v = r[idx[k]] if k in idx else ""
+                if k in idx and (k.startswith("gpu__time_duration") or k.startswith("dram__bytes")) and v:
+                    u = units[idx[k]]
+                    if u in scale:
+                        v = "%.6f" % (float(v.replace(",", "")) * scale[u])
+                d[k] = v
             rows_out.append(d)
     if not rows_out:
         return
     with open(os.path.join(out_dir, f"{tag}_kernels.csv"), "w", newline="") as f:
+        f.write("# units: gpu__time_duration.sum ms, dram__bytes_* GB, the rest as named (pct / counts)\n")
+        if tag == "r01":
+            f.write("# prof_r01_all_raw: one pass captured before feat_write_kernel wrote the split operand itself - its\n"
+                    "# feat_write_kernel and 0.23 ms split_operand_kernel<0> rows are that earlier pair; prof_r01_fw_raw is the\n"
+                    "# fused feat_write_kernel (6 B per value written, no split pass).  All other kernels are unchanged.\n")
         w = csv.DictWriter(f, fieldnames=["report", "kernel"] + KEEP)
         w.writeheader()
         w.writerows(rows_out)
