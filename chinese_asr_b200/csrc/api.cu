@@ -125,7 +125,7 @@ static int prepare_batch(asr_handle* h, const int32_t* h_L, int B, cudaStream_t 
     return ASR_OK;
 }
 
-// GEMM dispatch: CUDA-core fp32 (mode 0) or tcgen05 3xTF32 with a fused gather + hi/lo split of
+// GEMM dispatch: CUDA-core fp32 (mode 0) or tcgen05 split precision with a fused gather + hi/cross split of
 // the A operand (mode 1).  Both produce fp32-faithful results; mode 1 runs on the tensor cores.
 static int gemm(asr_handle* h, const AOperand& A, const float* W, const hi_t* W_hi, const float* W_lo,
                 int M, int N, int K, const GemmEpilogue& epi, cudaStream_t st) {
@@ -248,7 +248,7 @@ static int decoder_step(asr_handle* h, int k, int step, int cur, float temperatu
         // Tensor-core decoder step with producer-side operand preparation:
         //   * the embedding part of the LSTM input projection is the pre-multiplied table E' (added in the
         //     cell GEMM's epilogue), so the cell GEMM runs over K = 1024 = [ctx[src] | h[src]];
-        //   * the cell epilogue and the attention kernel write the tf32 hi / lo splits of h_new / ctx_new
+        //   * the cell epilogue and the attention kernel write the fp16 hi / bf16 cross splits of h_new / ctx_new
         //     straight into the [R, 1024] A operand of the query and vocabulary GEMMs.
         {
             StageScope sc(h, kStCell, st);
@@ -612,7 +612,7 @@ int asr_create(asr_handle** out, const asr_weights* wt, const asr_feature_consts
         if ((rc = dev_upload(pool, &h->w.zero_bias, z)) != ASR_OK) return rc;
     }
     if ((rc = split_weight(h, h->w.att_w_hidden_t, kAtt, kDecH, &h->w.att_w_hidden_t_hi, &h->w.att_w_hidden_t_lo)) != ASR_OK) return rc;
-    // tf32 hi / lo copies for the tcgen05 path
+    // fp16 hi / bf16 cross copies for the tcgen05 path
     for (int layer = 0; layer < 4; ++layer) {
         const int K = layer == 0 ? kFeat : kEnc;
         if ((rc = split_weight(h, h->w.enc_w_ih[layer], 2 * kGates, K, &h->w.enc_w_ih_hi[layer], &h->w.enc_w_ih_lo[layer])) != ASR_OK) return rc;
@@ -641,7 +641,7 @@ int asr_create(asr_handle** out, const asr_weights* wt, const asr_feature_consts
         ASR_CUDA(cudaDeviceSynchronize());
     }
     const char* env = getenv("ASR_B200_GEMM");
-    // defaults: every GEMM-shaped stage and the recurrence on the tcgen05 tensor cores (3xTF32);
+    // defaults: every GEMM-shaped stage and the recurrence on the tcgen05 tensor cores (split precision);
     // ASR_B200_GEMM=simt / ASR_B200_REC=simt|tc select the CUDA-core / smem-resident variants
     h->gemm_mode = (env && strcmp(env, "simt") == 0) ? 0 : 1;
     const char* env_rec = getenv("ASR_B200_REC");

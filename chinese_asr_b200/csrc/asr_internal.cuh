@@ -137,7 +137,7 @@ int launch_gemm_tc(const hi_t* a_hi, const float* a_lo, const hi_t* w_hi, const 
 // a weight matrix with its pre-split copies
 struct SplitW {
     float* w = nullptr;    // [N, K] fp32
-    float* hi = nullptr;   // rn_tf32(w)
+    float* hi = nullptr;   // rn_tf32(w)         (legacy fp32 pair of the smem-resident recurrence engine)
     float* lo = nullptr;   // rn_tf32(w - hi)
 };
 
@@ -318,7 +318,7 @@ struct asr_handle {
     int last_out_ld = 0;         // row stride of ws.out_tokens after the last decode (its max_len)
     int64_t launches = 0;
     bool timing = false;
-    int gemm_mode = 0;           // 0 = CUDA-core fp32 FMA, 1 = tcgen05 3xTF32
+    int gemm_mode = 0;           // 0 = CUDA-core fp32 FMA, 1 = tcgen05 split precision (fp16 hi + bf16 cross)
     int rec_mode = 0;            // encoder recurrence: 0 = CUDA-core (register-stationary W_hh), 1 = tcgen05
     cudaGraphExec_t graph_exec = nullptr;   // captured beam-decode loop for the shape in graph_key
     long long graph_key[8] = {};

@@ -41,7 +41,6 @@ namespace asr {
 namespace tc {
 
 constexpr int BM = 128;
-constexpr int UMMA_K = 8;
 constexpr unsigned kSpinLimit = 1u << 28;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -74,15 +73,7 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y)
         : "memory");
 }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                          uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
+// kind::f16 covers both operand formats of the engine: fp16 (hi) and bf16 (cross), chosen by the descriptor
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                           uint32_t accumulate) {
     asm volatile(
@@ -124,12 +115,6 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(const void* smem) {
     return d;
 }
 
-// instruction descriptor, kind::tf32: D=f32 (1<<4), A=B=TF32 (2<<7, 2<<10), both K-major,
-// N>>3 at [17,23), M>>4 at [24,29)
-__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
 // kind::f16 with bf16 operands: D=f32 (1<<4), A=B=BF16 (1<<7, 1<<10)
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -150,12 +135,6 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo_half, float hi_half) {
 // chunk).  ex2.approx / rcp.approx forms (2 ulp) are branch-free; the encoder recurrence uses the same.
 __device__ __forceinline__ float sigm(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float tanh_e(float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); }
-__device__ __forceinline__ float rn_tf32_e(float x) {
-    uint32_t u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-    return __uint_as_float(u);
-}
-
 // ---------------------------------------------------------------------------------------------
 // Persistent variant: one CTA per SM loops over output tiles; the TMA producer and the MMA issuer run
 // ahead across tile boundaries and the accumulator is DOUBLE-BUFFERED in TMEM (2 x BN columns), so
@@ -182,15 +161,6 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
 }
 // ---- CTA-pair (cta_group::2) forms: one MMA over M = 256 spans both CTAs' tensor cores; each CTA holds its
 // 128 rows of A and HALF of the W tile, which the hardware shares between the two SMs.
-__device__ __forceinline__ void umma2_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                           uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
 __device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                            uint32_t accumulate) {
     asm volatile(
@@ -527,7 +497,7 @@ gemm_split_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, const
 }
 
 // ---------------------------------------------------------------------------------------------
-// operand split: x -> (rn_tf32(x), rn_tf32(x - rn_tf32(x))), with the AOperand gather fused
+// operand split with the AOperand gather fused (rn_tf32 only serves the legacy recurrence format)
 __device__ __forceinline__ float rn_tf32(float x) {
     uint32_t u;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));

@@ -502,7 +502,7 @@ class Model(object):
         raise TypeError(f"PCM buffer must be float32 or int16, not {dt}")
 
     def set_gemm_mode(self, mode):
-        """'simt' (CUDA-core fp32), 'tc' (GEMM stages on tcgen05 3xTF32), 'rec' (only the encoder
+        """'simt' (CUDA-core fp32), 'tc' (GEMM stages on tcgen05, split precision), 'rec' (only the encoder
         recurrence on tcgen05) or 'tc+rec' (both)."""
         self._need()
         check(lib.asr_set_gemm_mode(self._h, {'simt': 0, 'tc': 1, 'rec': 2, 'tc+rec': 3, 'rec3': 4, 'tc+rec3': 5}[mode]), "asr_set_gemm_mode")

@@ -224,7 +224,8 @@ int asr_transcribe_device(asr_handle* h, const float* d_pcm, const int64_t* h_pc
 
 /* GEMM engine of the four GEMM-shaped stages (nn.LSTM input projections util.py:1259, attention
  * keys attention.py:77, nn.LSTMCell util.py:1650-1661, vocabulary projection decoder.py:133):
- * 0 = CUDA-core fp32 FMA, 1 = tcgen05/TMEM/TMA tensor cores, split precision (fp32-faithful).  The
+ * 0 = CUDA-core fp32 FMA, 1 = tcgen05/TMEM/TMA tensor cores, split precision (fp16 hi + bf16 cross
+ * terms, fp32-faithful: ~2^-20 relative per product; operands beyond +-65504 fall back to bf16 accuracy).  The
  * default can also be chosen with the environment variable ASR_B200_GEMM=simt|tc. */
 int asr_set_gemm_mode(asr_handle* h, int mode);
 /* Standalone GEMM for tests: d_C[M,N] = d_A[M,K] * d_W[N,K]^T + d_bias[N] through engine `mode`. */
