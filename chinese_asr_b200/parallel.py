@@ -107,6 +107,8 @@ class BatchPipeline(object):
         memory, all batches known in advance): every engine stages its NEXT batch's PCM on its copy stream
         (Model.prefetch / asr_prefetch_pcm) while it decodes the current one."""
         batches = list(batches)
+        if kw.get("resident"):
+            prefetch = False                                # the PCM is already in HBM: nothing to stage
         if not prefetch:
             futs = [self.submit(p, o, **kw) for p, o in batches]
             return [f.result() for f in futs]
