@@ -156,8 +156,12 @@ class AudioDst(object):
     the waveform stays raw (int16 as stored) because the features of a whole batch are computed in
     one pass on the device by AudioLoader; `feature(idx)` gives the reference's per-item result."""
 
-    def __init__(self, audio_base, mode='infer', dev_or_test=None, path_list=None, text_list=None):
+    def __init__(self, audio_base, mode='train', dev_or_test='dev', path_list=None, text_list=None):
+        # same signature and defaults as the reference (data.py:393); the default mode is the one this package
+        # does not implement, so it has to be spelled out: AudioDst(ab, 'eval', 'dev', paths, texts) / 'infer'
         assert mode in ('train', 'eval', 'infer'), "mode must be train, eval or infer"
+        if dev_or_test is not None:
+            assert dev_or_test in ('dev', 'test'), "dev_or_test must be dev or test"
         if mode == 'train':
             raise NotImplementedError("training data pipeline (augmentation, TrainSampler) is outside the inference path")
         if path_list is None:

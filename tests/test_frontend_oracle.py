@@ -90,6 +90,11 @@ def test_read_pcm_and_dataset_items(tmp_path):
     assert len(infer[0]) == 1
     ld = data.AudioLoader(dst, batch_size=1)
     assert len(ld) == 2 and ld.loader is ld
+    import pytest
+    with pytest.raises(NotImplementedError):                 # the reference's default mode is 'train' (data.py:393)
+        data.AudioDst(AB)
+    with pytest.raises(ValueError):
+        data.AudioDst(AB, "infer")                           # no manifests here: paths must be given
 
 
 def test_wer_pairs_cover_edge_cases():
