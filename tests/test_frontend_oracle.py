@@ -102,3 +102,31 @@ def test_wer_pairs_cover_edge_cases():
     assert any(len(h) == 0 for h, _ in pairs) and any(h == r for h, r in pairs)
     assert any(3 in h for h, _ in pairs) and any(781 in r for _, r in pairs)
     assert max(len(r) for _, r in pairs) >= 150
+
+
+def test_edit_distance_properties():
+    """Metric properties of the oracle's edit distance (the checker of asr_wer): identity, symmetry, the
+    length bounds and the triangle inequality, on seeded random strings over a small alphabet."""
+    rng = np.random.default_rng(99)
+
+    def rand_s():
+        return "".join(chr(97 + int(c)) for c in rng.integers(0, 4, size=int(rng.integers(0, 12))))
+
+    for _ in range(200):
+        a, b, c = rand_s(), rand_s(), rand_s()
+        dab, dba = O.edit_distance(a, b), O.edit_distance(b, a)
+        assert dab == dba and (dab == 0) == (a == b)
+        assert abs(len(a) - len(b)) <= dab <= max(len(a), len(b))
+        assert O.edit_distance(a, c) <= dab + O.edit_distance(b, c)
+        assert O.edit_distance(a + "x", b + "x") == dab            # a common suffix changes nothing
+
+
+def test_batch_audio_statistics():
+    """batch_audio's instance normalisation: zero mean, unbiased unit std per column (up to eps), per utterance."""
+    g = torch.Generator().manual_seed(5)
+    feats = [torch.randn(n, 720, generator=g) * 3 + 1 for n in (7, 40)]
+    out, lens = O.batch_audio(feats)
+    assert lens.tolist() == [7, 40]
+    for y in out:
+        assert float(y.mean(dim=0).abs().max()) < 1e-5
+        assert float((y.std(dim=0) - 1).abs().max()) < 1e-5
