@@ -40,7 +40,7 @@ class AsrLmTables(C.Structure):
     _fields_ = [("uni_logp", c_float_p), ("uni_bo", c_float_p), ("bi_keys", c_int64_p),
                 ("bi_vals", c_float_p), ("bi_cap", C.c_int64), ("tri_keys", c_int64_p),
                 ("tri_vals", c_float_p), ("tri_cap", C.c_int64), ("vocab", C.c_int32),
-                ("skip_id", C.c_int32)]
+                ("skip_id", C.c_int32), ("id_map", c_int32_p)]
 
 
 # every symbol include/asr_b200.h declares, with its signature
@@ -80,6 +80,8 @@ SIGNATURES = {
                                   C.c_double, c_int32_p, c_int32_p, c_float_p, c_int32_p, C.c_void_p]),
     "asr_beam_trace": (C.c_int, [C.c_void_p, c_float_p, c_int32_p, c_int32_p, c_int32_p, c_int32_p,
                                  c_float_p]),
+    "asr_decode_info": (C.c_int, [C.c_void_p, c_int32_p]),
+    "asr_beam_nbest": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_int32_p, c_int32_p, c_int32_p, c_float_p]),
     "asr_transcribe": (C.c_int, [C.c_void_p, C.c_void_p, c_int64_p, C.c_int, C.c_int, C.c_int,
                                  C.c_float, C.c_int, C.c_double, C.c_double, c_int32_p, c_int32_p,
                                  c_float_p, C.c_void_p]),

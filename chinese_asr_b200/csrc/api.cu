@@ -464,6 +464,7 @@ static int greedy_decode_device(asr_handle* h, int max_len, float* d_align, floa
         cur ^= 1;
     }
     ASR_TRY(launch_greedy_finalise(h, max_len, st));
+    h->last_k = 0;               // no beam history: asr_beam_trace / asr_beam_nbest refuse
     h->last_B = B;
     h->last_out_ld = max_len;
     return ASR_OK;
@@ -479,6 +480,7 @@ static int fetch_results(asr_handle* h, int B, int max_len, int32_t* h_tokens, i
     ASR_CUDA(cudaMemcpyAsync(info, w.out_info, sizeof(info), cudaMemcpyDeviceToHost, st));
     ASR_CUDA(cudaStreamSynchronize(st));
     h->last_steps = info[0];
+    memcpy(h->last_info, info, sizeof(info));
     if (h_info) memcpy(h_info, info, sizeof(info));
     return ASR_OK;
 }
@@ -757,22 +759,22 @@ int asr_reserve(asr_handle* h, int max_utts, int64_t max_rows, int max_beam, int
     Workspace& w = h->ws;
     cudaDeviceSynchronize();
     for (void* p : w.allocs) cudaFree(p);
-    w.allocs.clear();
+    if (w.h_stage) cudaFreeHost(w.h_stage);
+    w = Workspace();                             // every pointer null, every capacity 0 until ALL allocations succeed
+    h->meta.d_order = nullptr;
+    h->encoded = false;
     if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }   // captured pointers are stale
     memset(h->graph_key, 0, sizeof(h->graph_key));
     memset(h->graph_seen, 0, sizeof(h->graph_seen));
-    w.pcm_pre[0] = w.pcm_pre[1] = nullptr;       // freed with the pool above
-    h->pre_src[0] = h->pre_src[1] = nullptr;
-    if (w.h_stage) { cudaFreeHost(w.h_stage); w.h_stage = nullptr; }
-    w.max_utts = max_utts; w.max_rows = max_rows; w.max_beam = max_beam; w.max_len = max_len;
-    w.max_samples = max_samples;
-    w.max_frames = 3 * max_rows + 2 * (int64_t)max_utts;
+    h->pre_src[0] = h->pre_src[1] = nullptr;      // the staged PCM copies went with the pool
+    const int64_t max_frames = 3 * max_rows + 2 * (int64_t)max_utts;
+    auto allocate = [&]() -> int {
     std::vector<void*>& pool = w.allocs;
     const size_t R = (size_t)max_utts * max_beam;
     const size_t K2 = 2 * (size_t)max_beam;
     if (max_samples > 0) {
         ASR_TRY(dev_alloc_t(pool, &w.pcm, (size_t)max_samples));
-        ASR_TRY(dev_alloc_t(pool, &w.mel, (size_t)w.max_frames * kMel));
+        ASR_TRY(dev_alloc_t(pool, &w.mel, (size_t)max_frames * kMel));
     }
     ASR_TRY(dev_alloc_t(pool, &w.xpack, (size_t)max_rows * kFeat));
     ASR_TRY(dev_alloc_t(pool, &w.feat_partial, (size_t)max_utts * 4 * kFeat * 2));     // [B, 4, 720] double2
@@ -846,6 +848,19 @@ int asr_reserve(asr_handle* h, int max_utts, int64_t max_rows, int max_beam, int
     h->meta.d_order = meta_block;
     w.h_stage_bytes = std::max(meta_ints * sizeof(int), (size_t)(max_utts + 1) * 16 + 64);
     ASR_CUDA(cudaMallocHost(&w.h_stage, w.h_stage_bytes));
+    return ASR_OK;
+    };
+    const int rc = allocate();
+    if (rc != ASR_OK) {                          // leave an empty, consistent workspace behind (capacities 0)
+        for (void* p : w.allocs) cudaFree(p);
+        if (w.h_stage) cudaFreeHost(w.h_stage);
+        w = Workspace();
+        h->meta.d_order = nullptr;
+        return rc;
+    }
+    w.max_utts = max_utts; w.max_rows = max_rows; w.max_beam = max_beam; w.max_len = max_len;
+    w.max_samples = max_samples;
+    w.max_frames = max_frames;
     h->encoded = false;
     return ASR_OK;
 }
@@ -950,6 +965,13 @@ int asr_set_lm(asr_handle* h, const asr_lm_tables* t) {
     ASR_TRY(upf(&lm.bi_vals, t->bi_vals, 2 * (size_t)t->bi_cap));
     ASR_TRY(upl(&lm.tri_keys, t->tri_keys, t->tri_cap));
     ASR_TRY(upf(&lm.tri_vals, t->tri_vals, t->tri_cap));
+    lm.id_map = nullptr;
+    if (t->id_map) {
+        std::vector<int> v(t->id_map, t->id_map + t->vocab);
+        for (int x : v)
+            if (x < 0 || x >= t->vocab) { set_error("asr_set_lm: id_map entry %d outside the vocabulary", x); return ASR_ERR_ARG; }
+        ASR_TRY(dev_upload(pool, &lm.id_map, v));
+    }
     lm.bi_cap = t->bi_cap; lm.tri_cap = t->tri_cap; lm.vocab = t->vocab; lm.skip_id = t->skip_id;
     lm.loaded = true;
     return ASR_OK;
@@ -981,6 +1003,13 @@ int asr_decode_beam(asr_handle* h, int k, int max_len, float temperature, int se
     cudaStream_t st = (cudaStream_t)stream;
     ASR_TRY(beam_decode_device(h, k, max_len, temperature, second_pass, lm_weight, length_weight, st));
     return fetch_results(h, h->meta.B, max_len, h_tokens, h_len, h_score, h_info, st);
+}
+
+int asr_decode_info(asr_handle* h, int32_t* h_info) {
+    if (!h || !h_info) { set_error("asr_decode_info: NULL argument"); return ASR_ERR_ARG; }
+    if (h->last_B <= 0) { set_error("asr_decode_info: nothing decoded yet"); return ASR_ERR_STATE; }
+    memcpy(h_info, h->last_info, sizeof(h->last_info));
+    return ASR_OK;
 }
 
 int asr_beam_trace(asr_handle* h, float* h_cand_score, int32_t* h_cand_beam, int32_t* h_cand_tok,
@@ -1017,6 +1046,51 @@ int asr_beam_trace(asr_handle* h, float* h_cand_score, int32_t* h_cand_beam, int
                     const size_t i = ((size_t)s * B + u) * k + j;
                     h_fin_score[((size_t)s * B + order[u]) * k + j] = fr[i] >= 0 ? fs[i] : NAN;
                 }
+    }
+    return ASR_OK;
+}
+
+// parse_finished_tensors' list (model.py:708-747) for a caller that rescores on the host: every finished
+// hypothesis of the last beam decode per utterance in (step, rank) order, back-traced on the host from the
+// history the decode left on the device.  Not on the hot path (the device finaliser picks / rescores itself).
+int asr_beam_nbest(asr_handle* h, int cap, int tok_ld, int32_t* h_count, int32_t* h_tokens, int32_t* h_len,
+                   float* h_score) {
+    if (!h || h->last_k <= 0) { set_error("asr_beam_nbest: no beam decode yet"); return ASR_ERR_STATE; }
+    if (!h_count || cap < 0 || (cap > 0 && (!h_tokens || !h_len || !h_score || tok_ld < 1))) {
+        set_error("asr_beam_nbest: bad argument");
+        return ASR_ERR_ARG;
+    }
+    ASR_CUDA(cudaDeviceSynchronize());
+    const int B = h->last_B, k = h->last_k, R = B * k, steps = h->last_steps;
+    const Workspace& w = h->ws;
+    std::vector<float> fs((size_t)std::max(steps, 1) * R);
+    std::vector<int> fr(fs.size()), tok((size_t)(steps + 1) * R), prev(tok.size());
+    ASR_CUDA(cudaMemcpy(fs.data(), w.fin_score, sizeof(float) * (size_t)steps * R, cudaMemcpyDeviceToHost));
+    ASR_CUDA(cudaMemcpy(fr.data(), w.fin_row, sizeof(int) * (size_t)steps * R, cudaMemcpyDeviceToHost));
+    ASR_CUDA(cudaMemcpy(tok.data(), w.tok_hist, sizeof(int) * tok.size(), cudaMemcpyDeviceToHost));
+    ASR_CUDA(cudaMemcpy(prev.data(), w.prev_hist, sizeof(int) * prev.size(), cudaMemcpyDeviceToHost));
+    for (int u = 0; u < B; ++u) {
+        const int uo = h->meta.order[u];
+        int n = 0;
+        for (int l = 0; l < steps; ++l)
+            for (int j = 0; j < k; ++j) {
+                const size_t o = ((size_t)l * B + u) * k + j;
+                if (fr[o] < 0) continue;
+                if (n < cap) {
+                    if (l > tok_ld) { set_error("asr_beam_nbest: hypothesis of %d tokens > tok_ld %d", l, tok_ld); return ASR_ERR_ARG; }
+                    int32_t* dst = h_tokens + ((size_t)uo * cap + n) * tok_ld;
+                    int row = fr[o];
+                    for (int pos = l; pos >= 1; --pos) {          // the same chain beam_finalise_kernel walks
+                        dst[pos - 1] = tok[(size_t)pos * R + row];
+                        row = prev[(size_t)pos * R + row];
+                    }
+                    for (int i = l; i < tok_ld; ++i) dst[i] = kPad;
+                    h_len[(size_t)uo * cap + n] = l;
+                    h_score[(size_t)uo * cap + n] = fs[o];
+                }
+                ++n;
+            }
+        h_count[uo] = n;
     }
     return ASR_OK;
 }

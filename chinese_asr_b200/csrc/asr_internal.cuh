@@ -210,6 +210,7 @@ struct LmTables {
     long long tri_cap = 0;
     int vocab = 0;
     int skip_id = -1;
+    int* id_map = nullptr;       // [vocab] token -> LM word (tokens without a unigram -> <unk>), nullptr = identity
     bool loaded = false;
 };
 
@@ -315,6 +316,7 @@ struct asr_handle {
     asr::BatchMeta meta;
     bool encoded = false;
     int last_k = 0, last_steps = 0, last_B = 0;
+    int last_info[4] = {};       // {steps, stop step or -1, fallbacks, finished hypotheses} of the last decode
     int last_out_ld = 0;         // row stride of ws.out_tokens after the last decode (its max_len)
     int64_t launches = 0;
     bool timing = false;

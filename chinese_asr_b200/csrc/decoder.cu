@@ -1203,6 +1203,7 @@ struct LmDev {
     const long long* bi_keys; const float* bi_vals; long long bi_cap;
     const long long* tri_keys; const float* tri_vals; long long tri_cap;
     int vocab, skip_id;
+    const int* id_map;
 };
 
 __device__ __forceinline__ long long hash_slot(long long key, long long cap) {
@@ -1243,8 +1244,9 @@ __device__ float lm_score_ids(const LmDev& lm, const int* ids, int n) {
     int c0 = 0, c1 = kSos, nctx = 1;
     float total = 0.f;
     for (int i = 0; i <= n; ++i) {
-        const int w = i < n ? ids[i] : kEos;
+        int w = i < n ? ids[i] : kEos;
         if (i < n && w == lm.skip_id) continue;
+        if (lm.id_map) w = lm.id_map[w];
         total = __fadd_rn(total, lm_word(lm, c0, c1, nctx, w));
         c0 = c1; c1 = w; nctx = 2;
     }
@@ -1261,7 +1263,7 @@ __global__ void lm_score_kernel(LmDev lm, const int* __restrict__ ids, const int
 static LmDev lm_dev(const asr_handle* h) {
     const LmTables& t = h->lm;
     return LmDev{t.uni_logp, t.uni_bo, t.bi_keys, t.bi_vals, t.bi_cap, t.tri_keys, t.tri_vals,
-                 t.tri_cap, t.vocab, t.skip_id};
+                 t.tri_cap, t.vocab, t.skip_id, t.id_map};
 }
 
 int launch_lm_score(asr_handle* h, const int* d_ids, const int* d_n, int n, int max_n,

@@ -61,8 +61,8 @@ def delta_filter_stack():
 
 
 def fast_read(path):
-    """16-bit PCM / float32 WAV -> float32 in [-1, 1) (data.py:109-121; soundfile is replaced by
-    the stdlib wave module)."""
+    """16-bit or 32-bit integer PCM WAV -> float32 in [-1, 1) (data.py:109-121; soundfile is replaced by
+    the stdlib wave module, which reads integer PCM only: an IEEE-float WAV raises wave.Error)."""
     with wave.open(path, 'rb') as w:
         rate, width, ch, n = w.getframerate(), w.getsampwidth(), w.getnchannels(), w.getnframes()
         raw = w.readframes(n)
@@ -144,8 +144,12 @@ def _waveform(src):
     """WAV path or array -> int16 (as stored; converted on the device) or float32 samples."""
     if isinstance(src, str):
         return read_pcm(src)
-    a = np.asarray(src)
-    return a if a.dtype == np.int16 else a.astype(np.float32)
+    a = src.detach().cpu().numpy() if isinstance(src, torch.Tensor) else np.asarray(src)
+    if a.dtype == np.int16:
+        return a
+    if not np.issubdtype(a.dtype, np.floating):
+        raise TypeError(f"waveform dtype {a.dtype}: only float (in [-1, 1)) or int16 PCM is accepted")
+    return a.astype(np.float32)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -3,7 +3,9 @@
 The reference calls kenlm.LanguageModel(lm_path).score(' '.join(chars), bos=True).  KenLM and its
 binary model are not available here, so the B200 path takes a back-off n-gram (order <= 3) in ARPA
 semantics: log10 probabilities, back-off weights, <s> context when bos, </s> appended when eos,
-OOV -> <unk>.  Scoring of the finished hypotheses runs on the GPU (csrc/decoder.cu); this class
+a word the LM does not know scores as <unk> (kenlm maps it to its <unk> index before every lookup:
+dict.pkl tokens missing from an ARPA file go through `id_map`; n-grams over words that dict.pkl does
+not have can never be asked for and are dropped).  Scoring of the finished hypotheses runs on the GPU (csrc/decoder.cu); this class
 only builds / uploads the tables.  `.score()` is provided for API compatibility and evaluates the
 same tables through the device kernel (asr_lm_score) - there is no host scoring path."""
 import numpy as np
@@ -46,6 +48,8 @@ class NGramLM:
         self.word2int = word2int
         self.skip_id = skip_id
         self._engine = None
+        if "id_map" in self.t:
+            self.t["id_map"] = self.t["id_map"].astype(np.int32)
 
     def tables(self):
         return self.t
@@ -57,6 +61,7 @@ class NGramLM:
         uni_logp = np.full(V, -99.0, dtype=np.float32)
         uni_bo = np.zeros(V, dtype=np.float32)
         bi, tri = [], []
+        seen = np.zeros(V, dtype=bool)
         order = 0
         with open(path, encoding='utf-8') as f:
             for line in f:
@@ -79,18 +84,30 @@ class NGramLM:
                 if len(words) != order:
                     continue
                 lp = float(parts[0])
-                ids = [word2int.get(w, UNK) for w in words]
+                # "<unk>" itself is dict.pkl id 3; any other word dict.pkl lacks can never be produced by the
+                # decoder, so n-grams containing it are unreachable (mapping them onto <unk> would overwrite
+                # <unk>'s own entries)
+                if any(w not in word2int for w in words):
+                    continue
+                ids = [word2int[w] for w in words]
                 if order == 1:
+                    seen[ids[0]] = True
                     uni_logp[ids[0]] = lp
                     uni_bo[ids[0]] = bo
                 elif order == 2:
                     bi.append((ids[0] * V + ids[1], (lp, bo)))
                 elif order == 3:
                     tri.append(((ids[0] * V + ids[1]) * V + ids[2], (lp,)))
+        # later duplicates of an n-gram must not shadow the first (kenlm rejects them; first one wins here)
+        bi = list({k: v for k, v in reversed(bi)}.items())
+        tri = list({k: v for k, v in reversed(tri)}.items())
         bk, bv = _build_table(bi, 2)
         tk, tv = _build_table(tri, 1)
+        # dict.pkl tokens the ARPA file has no unigram for are out-of-vocabulary for the LM: kenlm looks them
+        # up as <unk>, in every position of an n-gram
+        id_map = np.where(seen, np.arange(V), UNK).astype(np.int32)
         return cls({"uni_logp": uni_logp, "uni_bo": uni_bo, "bi_keys": bk, "bi_vals": bv,
-                    "tri_keys": tk, "tri_vals": tv.reshape(-1)}, word2int, skip_id)
+                    "tri_keys": tk, "tri_vals": tv.reshape(-1), "id_map": id_map}, word2int, skip_id)
 
     def bind(self, engine):
         self._engine = engine

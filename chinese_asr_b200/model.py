@@ -11,7 +11,6 @@ Python only marshals buffers: features, encoder, the whole autoregressive loop, 
 finalisation and LM rescoring run in libasr_b200.so (CUDA, sm_100a) without per-step host syncs.
 torch tensors are buffer carriers (data_ptr()).  There is no CPU path: use_cuda=False raises."""
 import ctypes as C
-from operator import itemgetter
 
 import numpy as np
 import torch
@@ -19,7 +18,7 @@ import torch
 from . import _cabi
 from ._cabi import lib, check
 from .gpd import gpd, check_frozen
-from .util import EvalOutput, get_wer
+from .util import EvalOutput
 from . import data as _data
 
 VOCAB = 5004
@@ -42,6 +41,7 @@ class Model(object):
         self._keep = []            # host arrays that must outlive asr_create
         self._reserved = None
         self._lm = None
+        self._vocab_src = None
         self.optimizer = None
         self.logger = None
 
@@ -101,12 +101,17 @@ class Model(object):
             check(lib.asr_create(C.byref(h), C.byref(w), C.byref(fc)), "asr_create")
         self._h = h
         self._reserved = None
+        self._lm = None                # the new handle has no LM tables / vocabulary yet
+        self._vocab_src = None
         _data.set_default_engine(self)
 
     def close(self):
         if self._h is not None:
             lib.asr_destroy(self._h)
             self._h = None
+        self._reserved = None
+        self._lm = None
+        self._vocab_src = None
 
     def __del__(self):
         try:
@@ -148,8 +153,16 @@ class Model(object):
         """list of waveforms (float32, or int16 as stored in 16-bit WAV files) -> list of CUDA tensors
         [L_i, 720].  eps: CMVN epsilon, 1e-6 = main.py:37, 1e-7 = AudioLoader.batch_audio (data.py:517)."""
         self._need()
-        s16 = len(pcms) > 0 and all(isinstance(p, np.ndarray) and p.dtype == np.int16 for p in pcms)
-        pcms = [np.ascontiguousarray(p, dtype=np.int16 if s16 else np.float32) for p in pcms]
+        pcms = [p.detach().cpu().numpy() if isinstance(p, torch.Tensor) else np.asarray(p) for p in pcms]
+        for p in pcms:
+            if p.dtype != np.int16 and not np.issubdtype(p.dtype, np.floating):
+                raise TypeError(f"waveform dtype {p.dtype}: only float (in [-1, 1)) or int16 PCM is accepted")
+        s16 = len(pcms) > 0 and all(p.dtype == np.int16 for p in pcms)
+        if s16:
+            pcms = [np.ascontiguousarray(p) for p in pcms]
+        else:       # a mixed batch: 16-bit items become x / 32768 like fast_read (data.py:111), exact in float32
+            pcms = [p.astype(np.float32) / np.float32(32768.0) if p.dtype == np.int16
+                    else np.ascontiguousarray(p, dtype=np.float32) for p in pcms]
         B = len(pcms)
         off = np.zeros(B + 1, dtype=np.int64)
         off[1:] = np.cumsum([len(p) for p in pcms])
@@ -329,8 +342,8 @@ class Model(object):
         kenlm object the reference passes as lm_model (model.py:755)."""
         self._need()
         if not hasattr(lm_model, 'tables'):
-            raise TypeError("lm_model must provide .tables() (chinese_asr_b200.lm.NGramLM); "
-                            "host-side LM scoring is not part of the B200 path")
+            raise TypeError("set_lm needs .tables() (chinese_asr_b200.lm.NGramLM); an lm_model that only offers "
+                            ".score() is rescored on the host from asr_beam_nbest (see _host_rescore)")
         if self._lm is lm_model:
             return
         t = lm_model.tables()
@@ -342,11 +355,14 @@ class Model(object):
         tri_keys = np.ascontiguousarray(t["tri_keys"], dtype=np.int64)
         tri_vals = np.ascontiguousarray(t["tri_vals"], dtype=np.float32).reshape(-1)
         assert bi_vals.shape[0] == 2 * bi_keys.shape[0] and tri_vals.shape[0] == tri_keys.shape[0]
+        id_map = np.ascontiguousarray(t["id_map"], dtype=np.int32) if t.get("id_map") is not None else None
+        assert id_map is None or id_map.shape[0] == uni_logp.shape[0]
         tb = _cabi.AsrLmTables(
             _cabi.fptr(uni_logp), _cabi.fptr(uni_bo),
             bi_keys.ctypes.data_as(_cabi.c_int64_p), _cabi.fptr(bi_vals), int(bi_keys.shape[0]),
             tri_keys.ctypes.data_as(_cabi.c_int64_p), _cabi.fptr(tri_vals), int(tri_keys.shape[0]),
-            int(uni_logp.shape[0]), int(getattr(lm_model, 'skip_id', 781)))
+            int(uni_logp.shape[0]), int(getattr(lm_model, 'skip_id', 781)),
+            id_map.ctypes.data_as(_cabi.c_int32_p) if id_map is not None else None)
         check(lib.asr_set_lm(self._h, C.byref(tb)), "asr_set_lm")
         self._lm = lm_model
         if hasattr(lm_model, 'bind'):
@@ -371,12 +387,11 @@ class Model(object):
     def eval_one_batch_with_beam(self, device, bmsz, data, lens, text, int2word,
                                  second_pass=gpd['second_pass'], lm_model=None,
                                  lm_weight=gpd['lm_weight'], length_weight=gpd['length_weight']):
-        if second_pass:
-            if lm_model is None:
-                raise ValueError("second_pass=True needs lm_model")
-            self.set_lm(lm_model)
+        host_lm = self._prepare_lm(second_pass, lm_model)
         B, lens_np = self._encode(data, lens, bmsz)
-        tokens, tlen, score, info = self._beam(B, bmsz, second_pass, lm_weight, length_weight)
+        tokens, tlen, score, info = self._beam(B, bmsz, second_pass and not host_lm, lm_weight, length_weight)
+        if host_lm:
+            self._host_rescore(B, tokens, tlen, score, lm_model, lm_weight, length_weight, int2word)
         outputs = [tokens[i, :tlen[i]].tolist() for i in range(B)]
         pred_text = [''.join([int2word[idx] for idx in ele]) for ele in outputs]
         wer = None
@@ -401,9 +416,66 @@ class Model(object):
               "asr_decode_beam")
         return tokens, tlen, score, info
 
+    def _prepare_lm(self, second_pass, lm_model):
+        """Device tables when the LM offers them (NGramLM.tables()); any other object with the reference's
+        duck-typed `.score(sentence, bos=True)` (model.py:755; main.py:82 passes a kenlm.LanguageModel) is
+        rescored on the host from the device's n-best list.  Returns True for the host route."""
+        if not second_pass:
+            return False
+        if lm_model is None:
+            raise ValueError("second_pass=True needs lm_model")
+        if hasattr(lm_model, 'tables'):
+            self.set_lm(lm_model)
+            return False
+        if not hasattr(lm_model, 'score'):
+            raise TypeError("lm_model needs .score(sentence, bos=True) (model.py:755)")
+        return True
+
+    def beam_nbest(self, B, cap=None):
+        """parse_finished_tensors' per-utterance lists (model.py:708-747) of the last beam decode:
+        [[(tokens, score), ...] in (step, rank) order] per utterance (asr_beam_nbest)."""
+        self._need()
+        i32 = _cabi.c_int32_p
+        max_len = gpd['max_len']
+        count = np.zeros(B, dtype=np.int32)
+        if cap is None:
+            check(lib.asr_beam_nbest(self._h, 0, max_len, count.ctypes.data_as(i32), None, None, None), "asr_beam_nbest")
+            cap = max(1, int(count.max()))
+        toks = np.zeros((B, cap, max_len), dtype=np.int32)
+        lens = np.zeros((B, cap), dtype=np.int32)
+        sc = np.zeros((B, cap), dtype=np.float32)
+        check(lib.asr_beam_nbest(self._h, cap, max_len, count.ctypes.data_as(i32), toks.ctypes.data_as(i32),
+                                 lens.ctypes.data_as(i32), _cabi.fptr(sc)), "asr_beam_nbest")
+        return [[(toks[u, i, :lens[u, i]].tolist(), float(sc[u, i])) for i in range(min(int(count[u]), cap))]
+                for u in range(B)]
+
+    def _host_rescore(self, B, tokens, tlen, score, lm_model, lm_weight, length_weight, int2word):
+        """model.py:749-763 with the caller's own lm_model: for every utterance with more than one finished
+        hypothesis, argmax (first wins) of logp + lm_weight * lm_model.score(' '.join(chars), bos=True) +
+        length_weight * len; the returned score stays the un-rescored logp (:762).  Utterances with one
+        finished hypothesis or none (fallback, :961-972) keep what the device finaliser chose."""
+        if int2word is None:
+            raise ValueError("host LM rescoring needs int2word (the LM scores strings, model.py:755)")
+        for u, hyps in enumerate(self.beam_nbest(B)):
+            if len(hyps) < 2:
+                continue
+            total = [s + lm_weight * lm_model.score(' '.join(int2word[t] for t in toks), bos=True)
+                     + length_weight * len(toks) for toks, s in hyps]
+            best_toks, best_s = hyps[int(np.argmax(total))]
+            tokens[u, :] = 0
+            tokens[u, :len(best_toks)] = best_toks
+            tlen[u] = len(best_toks)
+            score[u] = best_s
+
+    def decode_info(self):
+        """{steps, stopped_at (-1 = ran to max_len), fallback, finished} of the last decode (asr_decode_info)."""
+        info = np.zeros(4, dtype=np.int32)
+        check(lib.asr_decode_info(self._h, info.ctypes.data_as(_cabi.c_int32_p)), "asr_decode_info")
+        return dict(steps=int(info[0]), stopped_at=int(info[1]), fallback=int(info[2]), finished=int(info[3]))
+
     def beam_trace(self, B, bmsz):
         """Per-step internals of the last beam decode (parity tests): dict of numpy arrays."""
-        steps = self.last_beam_info['steps']
+        steps = self.decode_info()['steps']
         K = 2 * bmsz
         cs = np.zeros((steps, B, K), dtype=np.float32)
         cb = np.zeros((steps, B, K), dtype=np.int32)
@@ -451,8 +523,7 @@ class Model(object):
         self._need()
         off = np.ascontiguousarray(offsets, dtype=np.int64)
         B = off.shape[0] - 1
-        if second_pass:
-            self.set_lm(lm_model)
+        host_lm = self._prepare_lm(second_pass, lm_model)
         max_len = gpd['max_len']
         rows = int(sum(int(lib.asr_num_frames(int(off[i + 1] - off[i]))) for i in range(B)))
         self.reserve(B, max(rows, 1), max(bw or 1, 1), int(off[-1] - off[0]))
@@ -468,9 +539,12 @@ class Model(object):
             ptr = pcm.data_ptr() if isinstance(pcm, torch.Tensor) else pcm.ctypes.data
         check(fn(self._h, C.c_void_p(ptr), fmt, float(cmvn_eps), off.ctypes.data_as(_cabi.c_int64_p), B,
                  int(bw or 0), max_len,
-                 float(gpd['temperature']), 1 if second_pass else 0, float(lm_weight), float(length_weight),
+                 float(gpd['temperature']), 1 if (second_pass and not host_lm) else 0, float(lm_weight),
+                 float(length_weight),
                  tokens.ctypes.data_as(_cabi.c_int32_p), tlen.ctypes.data_as(_cabi.c_int32_p),
                  _cabi.fptr(score), self._stream()), "asr_transcribe")
+        if host_lm:
+            self._host_rescore(B, tokens, tlen, score, lm_model, lm_weight, length_weight, int2word)
         if int2word is not None:
             texts = [''.join(int2word[t] for t in tokens[i, :tlen[i]].tolist()) for i in range(B)]
             return tokens, tlen, score, texts

@@ -153,6 +153,8 @@ typedef struct asr_lm_tables {
     int64_t tri_cap;          /* power of two                  */
     int32_t vocab;
     int32_t skip_id;          /* token that vanishes under str.split(): id 781 ' ' */
+    const int32_t* id_map;    /* [vocab] token id -> LM word id, NULL = identity: tokens the LM has
+                                 no unigram for score as <unk> in every n-gram position, like kenlm */
 } asr_lm_tables;
 int asr_set_lm(asr_handle* h, const asr_lm_tables* t);
 /* kenlm-style score of token-id sequences on the device (tests): h_ids [n, max_n], h_n[n] */
@@ -168,6 +170,11 @@ int asr_decode_beam(asr_handle* h, int k, int max_len, float temperature, int se
                     double lm_weight, double length_weight, int32_t* h_tokens, int32_t* h_len,
                     float* h_score, int32_t* h_info, void* stream);
 
+/* h_info[4] of the last decode on this handle (asr_decode_beam, asr_decode_greedy or asr_transcribe*):
+ * {steps executed, stop step or -1 (model.py:578, 897-901), #utterances that took the un-finished
+ * fallback, #finished hypotheses}. */
+int asr_decode_info(asr_handle* h, int32_t* h_info);
+
 /* Per-step internals of the last asr_decode_beam call (parity tests; original utterance order):
  * h_cand_score/h_cand_beam/h_cand_tok [steps, B, 2k] (model.py:863-867),
  * h_backptr/h_active_tok [steps, B, k] (model.py:907-909),
@@ -175,6 +182,16 @@ int asr_decode_beam(asr_handle* h, int k, int max_len, float temperature, int se
  * Any pointer may be NULL. */
 int asr_beam_trace(asr_handle* h, float* h_cand_score, int32_t* h_cand_beam, int32_t* h_cand_tok,
                    int32_t* h_backptr, int32_t* h_active_tok, float* h_fin_score);
+
+/* The finished hypotheses of the last asr_decode_beam / asr_transcribe* (k >= 1) call, per utterance in
+ * the (step, rank) order in which parse_finished_tensors (model.py:708-747) lists them - what a caller
+ * needs to rescore with its OWN lm_model.score (model.py:749-763; main.py:79-85 loads a KenLM binary):
+ * h_count[B] = number of finished hypotheses of every utterance (0 = it took the un-finished fallback);
+ * the first min(count, cap) of them in h_tokens [B, cap, tok_ld] (padded with <pad>), h_len [B, cap],
+ * h_score [B, cap] (accumulated log-prob including the </s> step, no length normalisation).
+ * cap = 0 only counts.  Original utterance order. */
+int asr_beam_nbest(asr_handle* h, int cap, int tok_ld, int32_t* h_count, int32_t* h_tokens,
+                   int32_t* h_len, float* h_score);
 
 /* get_wer (util.py:237-262) as the decode drivers use it when `text` is given (model.py:595-598,
  * 982-985): Levenshtein distance between the predicted and the reference STRING.  Strings are code

@@ -524,10 +524,19 @@ def _topk_sorted(scores, k):
 
 @torch.no_grad()
 def beam_decode(weights, k, feats, lens, int2word=None, second_pass=False, lm_model=None,
-                lm_weight=0.0, length_weight=0.0, temperature=1.0, max_len=MAX_LEN, trace=None):
+                lm_weight=0.0, length_weight=0.0, temperature=1.0, max_len=MAX_LEN, trace=None,
+                batch_stop_step=None):
     """Restatement of Model.eval_one_batch_with_beam.  `trace` (dict) receives per-step
     internals: cand_scores/cand_beams/cand_tokens [B,2k], backptr/active_tokens [B,k],
-    finished records, stop step."""
+    finished records, stop step, and per utterance the decision margins (`margin_utt`) and the
+    first step whose rank-0 candidate was </s> (`top_done_step`, -1 = never).
+
+    batch_stop_step: utterances interact only through the early stop (model.py:897-901: the loop
+    ends at the first step where EVERY utterance of the batch has had </s> at rank 0).  To decode
+    a few utterances of a large batch alone and still get what the reference returns for them
+    inside that batch, the stop step of the whole batch is passed in: an int S ends the loop at
+    step S, -1 never ends it early (some other utterance of the batch never finishes); None is
+    the reference's own rule for the utterances given."""
     bsz = len(feats)
     R = bsz * k
     c2 = 2 * k
@@ -576,6 +585,8 @@ def beam_decode(weights, k, feats, lens, int2word=None, second_pass=False, lm_mo
             gaps = srt[:, :-1] - srt[:, 1:]
             used = torch.arange(c2).view(1, -1) <= deepest.view(-1, 1)
             trace.setdefault("min_margin", []).append(float(gaps[used].min()))
+            trace.setdefault("margin_utt", []).append(
+                torch.where(used, gaps, torch.full_like(gaps, float("inf"))).min(dim=1)[0])
         # finished set: EOS among the top-k candidates (model.py:876-889)
         top_beam = cand_beam[:, :k] + base.view(-1, 1)
         is_eos_k = cand_tok[:, :k] == EOS
@@ -584,8 +595,11 @@ def beam_decode(weights, k, feats, lens, int2word=None, second_pass=False, lm_mo
         fin_utt = torch.div(fin_rows, k, rounding_mode="floor")
         fin_scores = cand_s[:, :k].masked_select(is_eos_k)
         finished.append((fin_tokens, fin_utt, fin_scores))
+        if trace is not None:
+            first = trace.setdefault("top_done_step", torch.full((bsz,), -1, dtype=torch.long))
+            first[(cand_tok[:, 0] == EOS) & ~top_done] = step
         top_done = top_done | (cand_tok[:, 0] == EOS)
-        if bool(top_done.all()):
+        if bool(top_done.all()) if batch_stop_step is None else step == batch_stop_step:
             stopped_at = step
             break
         # active set: first k non-EOS candidates in rank order (model.py:904-909)

@@ -50,7 +50,8 @@ def check_features():
     m = get_model((1234, "plain", None), w)
     res = {}
     pcms = {"feat_2s": O.synth_pcm(11, 32000), "feat_5s": O.synth_pcm(12, 80000),
-            "feat_odd": O.synth_pcm(13, 20011)}
+            "feat_odd": O.synth_pcm(13, 20011), "feat_10s": O.synth_pcm(14, 160000),
+            "feat_20s": O.synth_pcm(15, 320000)}
     names = list(pcms)
     raw = m.features([pcms[n] for n in names], normalise=False)
     nrm = m.features([pcms[n] for n in names], normalise=True)
@@ -177,7 +178,24 @@ def check_beam(cname):
     res["cand_scores_vs_ref"] = float(np.abs(t["cand_scores"][:ns] - ref_cs).max())
     res["cand_scores_rel_vs_ref"] = float((np.abs(t["cand_scores"][:ns] - ref_cs) / np.maximum(1.0, np.abs(ref_cs))).max())
     flat = t["cand_beams"][:ns].astype(np.int64) * O.VOCAB + t["cand_tokens"][:ns]
-    res["cand_index_mismatch_vs_ref"] = int((flat != g[cname + "_cand_index"][:ns]).sum())
+    ref_idx = g[cname + "_cand_index"][:ns]
+    res["cand_index_mismatch_vs_ref"] = int((flat != ref_idx).sum())
+    # consumed candidates: ranks < k (finished set) and, while an active set is formed, everything up to the
+    # k-th non-</s> candidate; mismatches beyond are reported with the oracle's gap at that rank
+    consumed_bad, tail_margins = 0, []
+    n_act = g[cname + "_active"].shape[0]
+    for s_, u, r_ in np.argwhere(flat != ref_idx):
+        ref_tok = ref_idx[s_, u] % O.VOCAB
+        used = k if s_ >= n_act else max(k, int(np.searchsorted(np.cumsum(ref_tok != O.EOS), k)) + 1)
+        if r_ < used:
+            consumed_bad += 1
+        else:
+            sc_ref = g[cname + "_cand_scores"][s_, u]
+            lo, hi = max(0, r_ - 1), min(2 * k - 1, r_ + 1)
+            tail_margins.append(float(min(abs(sc_ref[lo] - sc_ref[r_]) if lo != r_ else np.inf,
+                                          abs(sc_ref[hi] - sc_ref[r_]) if hi != r_ else np.inf)))
+    res["cand_index_consumed_mismatch_vs_ref"] = consumed_bad
+    res["cand_index_tail_mismatch_margins"] = tail_margins
     nb = len(tr.get("backptr", []))
     if nb:
         bp = torch.stack(tr["backptr"]).numpy()
@@ -370,43 +388,182 @@ def check_graph_replay(B=6, k=4, n=40000, seed=700):
     return {"replay_eq_eager": same, "of": len(batches), "batches_differ": distinct}
 
 
+NEAR_TIE = 2e-6     # a decision may differ from the oracle's only where the oracle's own margin is below this
+
+
+def _rel(a, b):
+    return abs(float(a) - float(b)) / max(1.0, abs(float(b)))
+
+
+def compare_with_oracle(m, weights, pcms, k, picks=None, lm_seed=None, lm_weight=0.0, length_weight=0.0,
+                        temperature=1.0, group=32, label=""):
+    """Decode ALL of `pcms` as one batch through the fused C-ABI path (PCM in, hypotheses out), then decode
+    the PICKED utterances with the CPU oracle and compare, per utterance and per step: the consumed
+    candidates of the top-2k list (token, source beam, score), back-pointers, active tokens, the whole list
+    of finished hypotheses in (step, rank) order (asr_beam_nbest) and the final pick.
+
+    Utterances of a batch interact only through the early stop (model.py:897-901), so the oracle decodes the
+    picks alone with the batch's stop step passed in (`batch_stop_step`) and the check verifies that this
+    stop step is consistent with every pick (its rank-0 </s> came no later).
+
+    A difference is tolerated ONLY as a proven near-tie: the oracle's own decision margin at the first
+    differing step must be < NEAR_TIE (fp32 noise); it is reported in `flips`.  Anything else lands in `bad`."""
+    from chinese_asr_b200.gpd import gpd
+    from chinese_asr_b200.lm import NGramLM
+    w2i, i2w = vocab()
+    B = len(pcms)
+    picks = list(range(B)) if picks is None else sorted(set(int(i) for i in picks))
+    s16 = pcms[0].dtype == np.int16
+    lm_o = O.NGramLM(seed=lm_seed, word2int=w2i) if lm_seed else None
+    lm_d = NGramLM(lm_o.tables(), w2i) if lm_o else None
+    off = np.zeros(B + 1, dtype=np.int64)
+    off[1:] = np.cumsum([len(p) for p in pcms])
+    gpd['temperature'] = temperature
+    try:
+        tok, ln, sc = m.transcribe(np.concatenate(pcms), off, bw=k, second_pass=lm_d is not None, lm_model=lm_d,
+                                   lm_weight=lm_weight, length_weight=length_weight)
+    finally:
+        gpd['temperature'] = 1.
+    info = m.decode_info()
+    t = m.beam_trace(B, k)
+    nbest = m.beam_nbest(B)
+    S = info["stopped_at"]
+    res = {"B": B, "picks": len(picks), "steps": info["steps"], "stopped_at": S, "exact": 0, "flips": [], "bad": [],
+           "nonempty": 0, "finished_hyps": 0, "score_rel_max": 0.0, "cand_score_rel_max": 0.0,
+           "min_margin": float("inf"), "lens": sorted({int(x) for x in ln[picks]})}
+    K = 2 * k
+    for g0 in range(0, len(picks), group):
+        ids = picks[g0:g0 + group]
+        feats = [O.features(O.pcm_from_int16(pcms[i]) if s16 else pcms[i]) for i in ids]
+        lens = torch.tensor([f.size(0) for f in feats])
+        tr = {}
+        o = O.beam_decode(weights, k, feats, lens, i2w, second_pass=lm_o is not None, lm_model=lm_o,
+                          lm_weight=lm_weight, length_weight=length_weight, temperature=temperature, trace=tr,
+                          batch_stop_step=S)
+        if o["steps"] != info["steps"]:
+            res["bad"].append(("steps", ids[0], o["steps"], info["steps"]))
+            continue
+        n_act = len(tr.get("backptr", []))
+        for j, i in enumerate(ids):
+            tds = int(tr["top_done_step"][j])
+            if (S >= 0 and not 0 <= tds <= S):
+                res["bad"].append(("stop step inconsistent", i, tds, S))
+                continue
+            div = None
+            for s in range(info["steps"]):
+                o_tok, o_beam = tr["cand_tokens"][s][j].numpy(), tr["cand_beams"][s][j].numpy()
+                o_sc = tr["cand_scores"][s][j].numpy()
+                res["min_margin"] = min(res["min_margin"], float(tr["margin_utt"][s][j]))
+                # consumed ranks: the top k (finished set, model.py:876-889) and, when the step forms an active
+                # set, everything up to the k-th non-</s> candidate (model.py:904-909)
+                used = k
+                if s < n_act:
+                    used = max(k, int(np.searchsorted(np.cumsum(o_tok != O.EOS), k)) + 1)
+                same = (np.array_equal(t["cand_tokens"][s, i, :used], o_tok[:used])
+                        and np.array_equal(t["cand_beams"][s, i, :used], o_beam[:used]))
+                if same and s < n_act:
+                    same = (np.array_equal(t["backptr"][s, i], tr["backptr"][s][j].numpy())
+                            and np.array_equal(t["active_tokens"][s, i], tr["active_tokens"][s][j].numpy()))
+                if not same:
+                    div = (s, float(tr["margin_utt"][s][j]))
+                    break
+                res["cand_score_rel_max"] = max(res["cand_score_rel_max"],
+                                                float(np.max(np.abs(t["cand_scores"][s, i, :used] - o_sc[:used])
+                                                             / np.maximum(1.0, np.abs(o_sc[:used])))))
+            if div is not None:
+                (res["flips"] if div[1] < NEAR_TIE else res["bad"]).append(("diverged", i, div[0], div[1]))
+                continue
+            o_nb = o["nbest"].get(j, [])
+            g_nb = nbest[i]
+            nb_ok = len(o_nb) == len(g_nb) and all(a[0] == b[0] and _rel(a[1], b[1]) <= 1e-3 for a, b in zip(g_nb, o_nb))
+            final_ok = tok[i, :ln[i]].tolist() == o["tokens"][j] and _rel(sc[i], o["score"][j]) <= 1e-3
+            if not (nb_ok and final_ok):
+                res["bad"].append(("nbest" if not nb_ok else "final", i, len(g_nb), len(o_nb)))
+                continue
+            res["exact"] += 1
+            res["nonempty"] += int(ln[i] > 0)
+            res["finished_hyps"] += len(o_nb)
+            res["score_rel_max"] = max(res["score_rel_max"], _rel(sc[i], o["score"][j]))
+    print(f"[parity {label}] B={B} k={k} picks={len(picks)} exact={res['exact']} flips={res['flips']} "
+          f"bad={res['bad']} steps={info['steps']} stop={S} finished_hyps={res['finished_hyps']} "
+          f"min_margin={res['min_margin']:.2e} score_rel={res['score_rel_max']:.1e} "
+          f"cand_score_rel={res['cand_score_rel_max']:.1e}")
+    return res
+
+
+def synth_batch(secs, seed0, int16=True):
+    mk = O.synth_pcm_int16 if int16 else O.synth_pcm
+    return [mk(seed0 + i, int(16000 * s)) for i, s in enumerate(secs)]
+
+
 def check_config_shape(B, k, seconds_list, lm_seed=None, wseed=1234, eos_bias=8.0, seed0=3000, lm_weight=0.3,
                        length_weight=2.0):
-    """BASELINE.json configs at their real utterance lengths, fused path (PCM in) vs the oracle on
-    the same seeded inputs.  Returns exact-match statistics (near-ties below fp32 noise may flip)."""
-    from chinese_asr_b200.lm import NGramLM
+    """BASELINE.json configs at their real utterance lengths, fused path (PCM in) vs the oracle on the same
+    seeded inputs, every utterance compared step by step (compare_with_oracle); greedy: texts."""
     weights = O.make_weights(wseed, "sharp", eos_bias=eos_bias)
     m = get_model((wseed, "sharp", eos_bias), weights)
     w2i, i2w = vocab()
+    if k is not None:
+        pcms = synth_batch(seconds_list, seed0, int16=False)
+        return compare_with_oracle(m, weights, pcms, k, lm_seed=lm_seed, lm_weight=lm_weight if lm_seed else 0.0,
+                                   length_weight=length_weight if lm_seed else 0.0, label=f"config B={B} k={k}")
     ns = [int(16000 * s) for s in seconds_list]
     pcms = [O.synth_pcm(seed0 + i, n) for i, n in enumerate(ns)]
     feats = [O.features(p) for p in pcms]
     lens = torch.tensor([f.size(0) for f in feats])
-    lm_o = O.NGramLM(seed=lm_seed, word2int=w2i) if lm_seed else None
-    lm_d = NGramLM(lm_o.tables(), w2i) if lm_o else None
     off = np.zeros(B + 1, dtype=np.int64)
     off[1:] = np.cumsum(ns)
-    pcm = np.concatenate(pcms)
-    if k is None:
-        o = O.greedy_decode(weights, feats, lens, i2w)
-        tok, ln, sc, texts = m.transcribe(pcm, off, bw=None, int2word=i2w)
-        otexts, oscores = o["pred_text"], None
-    else:
-        tr = {}
-        o = O.beam_decode(weights, k, feats, lens, i2w, second_pass=lm_o is not None, lm_model=lm_o,
-                          lm_weight=lm_weight if lm_o else 0.0, length_weight=length_weight if lm_o else 0.0, trace=tr)
-        tok, ln, sc, texts = m.transcribe(pcm, off, bw=k, second_pass=lm_d is not None, lm_model=lm_d,
-                                          lm_weight=lm_weight if lm_o else 0.0,
-                                          length_weight=length_weight if lm_o else 0.0, int2word=i2w)
-        otexts, oscores = o["pred_text"], o["score"]
-    same = [a == b for a, b in zip(texts, otexts)]
-    res = {"B": B, "exact": int(sum(same)), "lens_min": int(lens.min()), "lens_max": int(lens.max())}
-    if oscores is not None:
-        rel = [abs(float(a) - b) / max(1e-6, abs(b)) for a, b, s in zip(sc, oscores, same) if s]
-        res["score_rel_max"] = float(max(rel)) if rel else 0.0
-        res["oracle_min_margin"] = float(min(tr["min_margin"]))
-        res["nonempty"] = int(sum(1 for t in otexts if len(t) > 0))
-    return res
+    o = O.greedy_decode(weights, feats, lens, i2w)
+    tok, ln, sc, texts = m.transcribe(np.concatenate(pcms), off, bw=None, int2word=i2w)
+    same = [a == b for a, b in zip(texts, o["pred_text"])]
+    return {"B": B, "exact": int(sum(same)), "lens_min": int(lens.min()), "lens_max": int(lens.max())}
+
+
+def rec_chunk_edges(B):
+    """First / last sorted rank of every recurrence chunk (encoder_tc3.cu: NB = 16..128 sequences per
+    cluster, at least 7 chunks per direction) - equal-length batches keep their order when sorted."""
+    nb = 16
+    while 7 * nb < B and nb < 128:
+        nb += 16
+    edges = set()
+    for c0 in range(0, B, nb):
+        edges.update((c0, min(B, c0 + nb) - 1))
+    return sorted(edges)
+
+
+def check_bench_shape(B=512, k=8, seconds=10.0, n_picks=32, seed0=41000):
+    """The bench workload (BASELINE.json configs[4] per GPU: 512 x 10 s, bw=8) with sharp weights so that
+    decisions are well separated: 32 picked utterances (first / last of every recurrence chunk + random)
+    against the oracle."""
+    weights = O.make_weights(1234, "sharp", eos_bias=8.0)
+    m = get_model((1234, "sharp", 8.0), weights)
+    pcms = synth_batch([seconds] * B, seed0)
+    picks = rec_chunk_edges(B)
+    rng = np.random.default_rng(seed0)
+    while len(set(picks)) < n_picks:
+        picks.append(int(rng.integers(0, B)))
+    return compare_with_oracle(m, weights, pcms, k, picks=picks, label="bench shape")
+
+
+def check_config3_full(B=256, k=16, n_picks=24, seed0=26000):
+    """BASELINE.json configs[2] at full size: bw=16, 256 utterances of mixed 2-20 s; 24 picks including the
+    shortest and the longest against the oracle, plus bit-reproducibility of the whole batch."""
+    weights = O.make_weights(77, "sharp", eos_bias=9.0)
+    m = get_model((77, "sharp", 9.0), weights)
+    rng = np.random.default_rng(2600)
+    secs = rng.integers(2, 21, size=B).tolist()
+    pcms = synth_batch(secs, seed0)
+    picks = [int(np.argmin(secs)), int(np.argmax(secs)), 0, B - 1]
+    while len(set(picks)) < n_picks:
+        picks.append(int(rng.integers(0, B)))
+    r = compare_with_oracle(m, weights, pcms, k, picks=picks, group=12, label="config 3 full")
+    off = np.zeros(B + 1, dtype=np.int64)
+    off[1:] = np.cumsum([len(p) for p in pcms])
+    x = np.concatenate(pcms)
+    a, b = m.transcribe(x, off, bw=k), m.transcribe(x, off, bw=k)
+    r["reproducible"] = int(all(np.array_equal(p, q) for p, q in zip(a, b)))
+    r["secs_min"], r["secs_max"] = int(min(secs)), int(max(secs))
+    return r
 
 
 # ---------------------------------------------------------------------------------------------
@@ -515,22 +672,146 @@ def check_driver_wer(cname):
     return res
 
 
-def check_wide_recurrence(B, k=4, group=40, seed=5200):
+def check_wide_recurrence(B, k=4, group=40, seed=5200, n_picks=16):
     """Batches of 561..896 utterances run the recurrence with 96 / 128 sequences per cluster (one round of 14
-    clusters).  Size-independent property: every hypothesis equals the one decoded in a batch of `group`
-    (16 sequences per cluster)."""
+    clusters).  Picked utterances (first / last sorted rank of every chunk + random) against the oracle, and the
+    size-independent property: every hypothesis is bit-identical to the one decoded in a batch of `group`."""
     weights = O.make_weights(1234, "sharp", eos_bias=8.0)
     m = get_model((1234, "sharp", 8.0), weights)
     rng = np.random.default_rng(seed)
     ns = [int(16000 * (1.2 + 1.3 * rng.random())) for _ in range(B)]
-    pcm = np.concatenate([O.synth_pcm_int16(seed + i, n) for i, n in enumerate(ns)])
+    pcms = [O.synth_pcm_int16(seed + i, n) for i, n in enumerate(ns)]
+    order = np.argsort(-np.array([int(O.num_frames(n)) // 3 for n in ns]), kind="stable")     # the library's sort
+    picks = [int(order[r]) for r in rec_chunk_edges(B)][:n_picks]
+    while len(set(picks)) < n_picks:
+        picks.append(int(rng.integers(0, B)))
+    res = compare_with_oracle(m, weights, pcms, k, picks=picks, label=f"wide recurrence B={B}")
+    pcm = np.concatenate(pcms)
     off = np.zeros(B + 1, dtype=np.int64)
     off[1:] = np.cumsum(ns)
     tok, ln, sc = m.transcribe(pcm, off, bw=k)
-    same, score_rel = 0, 0.0
+    stop = m.decode_info()["stopped_at"]
+    same = compared = 0
     for g0 in range(0, B, group):
         g1 = min(B, g0 + group)
         t1, l1, s1 = m.transcribe(pcm[off[g0]:off[g1]], off[g0:g1 + 1] - off[g0], bw=k)
-        same += int(sum(int(l1[i] == ln[g0 + i] and (t1[i] == tok[g0 + i]).all()) for i in range(g1 - g0)))
-        score_rel = max(score_rel, float(np.max(np.abs(s1 - sc[g0:g1]) / np.maximum(1.0, np.abs(sc[g0:g1])))))
-    return {"same": same, "of": B, "score_rel": score_rel, "len_spread": int(ln.max() - ln.min())}
+        if m.decode_info()["stopped_at"] != stop:
+            continue            # utterances interact through the early stop: only equal stop steps are comparable
+        compared += g1 - g0
+        same += int(sum(int(l1[i] == ln[g0 + i] and (t1[i] == tok[g0 + i]).all() and s1[i] == sc[g0 + i])
+                        for i in range(g1 - g0)))
+    res.update({"same": same, "of": compared, "len_spread": int(ln.max() - ln.min())})
+    return res
+
+
+# ---------------------------------------------------------------------------------------------
+# boundary: lm_model duck typing (model.py:749-763, main.py:79-85) and ARPA vocabularies
+class ScoreOnlyLM:
+    """What the reference is handed: any object with .score(sentence, bos=True) (a kenlm.LanguageModel)."""
+
+    def __init__(self, lm):
+        self._lm = lm
+        self.calls = 0
+
+    def score(self, sentence, bos=True):
+        self.calls += 1
+        return self._lm.score(sentence, bos=bos)
+
+
+def check_host_lm(cname="beam8lm"):
+    """An lm_model offering only .score() is rescored on the host from asr_beam_nbest with the rule of
+    model.py:749-763 and must pick exactly what the device tables pick (and what the reference picked)."""
+    from chinese_asr_b200.lm import NGramLM
+    g = load_golden()
+    cs = CASES[cname]
+    weights = case_weights(cs)
+    m = get_model(wkey(cs), weights)
+    w2i, i2w = vocab()
+    _, feats, lens = case_inputs(cs)
+    lm_o = O.NGramLM(seed=cs["lm"], word2int=w2i)
+    kw = dict(second_pass=True, lm_weight=cs["lm_weight"], length_weight=cs["length_weight"])
+    dev = m.eval_one_batch_with_beam(m.device, cs["bw"], feats, lens, None, i2w, lm_model=NGramLM(lm_o.tables(), w2i), **kw)
+    plain = ScoreOnlyLM(lm_o)
+    host = m.eval_one_batch_with_beam(m.device, cs["bw"], feats, lens, None, i2w, lm_model=plain, **kw)
+    none = m.eval_one_batch_with_beam(m.device, cs["bw"], feats, lens, None, i2w, second_pass=False)
+    off = np.zeros(len(feats) + 1, dtype=np.int64)
+    pcms = [O.synth_pcm(s_, n) for s_, n in zip(cs["seeds"], cs["nsamp"])]
+    off[1:] = np.cumsum([len(p) for p in pcms])
+    fused = m.transcribe(np.concatenate(pcms), off, bw=cs["bw"], lm_model=ScoreOnlyLM(lm_o), int2word=i2w, **kw)
+    nb = m.beam_nbest(len(feats))
+    return {"host_eq_device": int(list(host.pred_text) == list(dev.pred_text) and list(host.score) == list(dev.score)),
+            "host_eq_ref": int(list(host.pred_text) == list(g[cname + "_text"])),
+            "fused_eq_device": int(fused[3] == list(dev.pred_text)),
+            "lm_changes_a_pick": int(list(none.pred_text) != list(dev.pred_text)),
+            "lm_calls": plain.calls, "ref_lm_calls": int(len(g[cname + "_lm_seen"])),
+            "nbest_counts": [len(x) for x in nb]}
+
+
+ARPA = """\\data\\
+ngram 1={n1}
+ngram 2={n2}
+ngram 3={n3}
+
+\\1-grams:
+{uni}
+
+\\2-grams:
+{bi}
+
+\\3-grams:
+{tri}
+
+\\end\\
+"""
+
+
+def arpa_backoff_score(grams, sentence):
+    """kenlm's .score(sentence, bos=True, eos=True) restated on the ARPA entries themselves (dicts keyed by word
+    tuples -> (log10 p, backoff)); words without a unigram score as <unk>."""
+    def p(ctx, w):
+        if not ctx:
+            return grams[1][(w,)][0]
+        key = tuple(ctx) + (w,)
+        if key in grams[len(key)]:
+            return grams[len(key)][key][0]
+        return grams[len(ctx)].get(tuple(ctx), (0.0, 0.0))[1] + p(ctx[1:], w)
+    ctx, total = ["<s>"], 0.0
+    for w in sentence.split() + ["</s>"]:
+        w = w if (w,) in grams[1] else "<unk>"
+        total += p(ctx[-2:], w)
+        ctx.append(w)
+    return total
+
+
+def check_arpa_oov():
+    """ARPA file whose vocabulary differs from dict.pkl in both directions: a word dict.pkl lacks
+    must not overwrite <unk>; a dict.pkl token the ARPA lacks scores as <unk> in every n-gram position."""
+    import tempfile
+    from chinese_asr_b200.lm import NGramLM
+    w2i, i2w = vocab()
+    a, b, c, d, miss = (i2w[i] for i in (10, 11, 12, 13, 14))        # `miss` has no unigram in the ARPA
+    grams = {1: {("<unk>",): (-2.5, -0.3), ("<s>",): (-99.0, -0.4), ("</s>",): (-1.1, 0.0), (a,): (-1.3, -0.2),
+                 (b,): (-1.6, -0.25), (c,): (-1.9, -0.1), (d,): (-2.1, 0.0), ("ZZZ",): (-0.7, -0.9)},
+             2: {("<s>", a): (-0.5, -0.15), (a, b): (-0.6, -0.05), (b, "<unk>"): (-0.9, -0.07), ("<unk>", c): (-0.8, -0.02),
+                 (a, "ZZZ"): (-0.1, -0.6), ("ZZZ", b): (-0.2, 0.0), (c, "</s>"): (-0.3, 0.0)},
+             3: {("<s>", a, b): (-0.25, 0.0), (a, b, "<unk>"): (-0.35, 0.0), (b, "<unk>", c): (-0.45, 0.0),
+                 (a, "ZZZ", b): (-0.05, 0.0)}}
+    fmt = lambda n: "\n".join(f"{v[0]}\t{' '.join(k)}" + (f"\t{v[1]}" if n < 3 else "") for k, v in grams[n].items())
+    text = ARPA.format(n1=len(grams[1]), n2=len(grams[2]), n3=len(grams[3]), uni=fmt(1), bi=fmt(2), tri=fmt(3))
+    with tempfile.NamedTemporaryFile("w", suffix=".arpa", delete=False, encoding="utf-8") as f:
+        f.write(text)
+    lm = NGramLM.from_arpa(f.name, w2i)
+    os.unlink(f.name)
+    m = get_model((1234, "plain", None), O.make_weights(1234, "plain"))
+    m._lm = None
+    m.set_lm(lm)
+    sents = [f"{a} {b} {miss} {c}", f"{miss}", f"{a} {b}", f"{d} {miss} {miss} {a}", f"{c}", "", f"{a} {b} {i2w[3]} {c}",
+             f"{b} {miss} {c} {a} {b} {miss}"]
+    dev = [lm.score(s_) for s_ in sents]
+    ref = [arpa_backoff_score({n: {k: v for k, v in gs.items() if "ZZZ" not in k} for n, gs in grams.items()}, s_)
+           for s_ in sents]
+    t = lm.tables()
+    m._lm = None                       # the next caller uploads its own tables
+    return {"max_abs": float(np.max(np.abs(np.array(dev) - np.array(ref)))),
+            "unk_kept": int(t["uni_logp"][3] == np.float32(-2.5) and t["uni_bo"][3] == np.float32(-0.3)),
+            "missing_maps_to_unk": int(t["id_map"][14] == 3 and t["id_map"][10] == 10)}

@@ -127,3 +127,27 @@ def test_batch_pipeline_round_robin_and_order():
     pipe.close()
     with pytest.raises(ValueError):
         BatchPipeline([])
+
+
+def test_arpa_vocabulary_mismatch_tables(tmp_path):
+    """an ARPA word missing from dict.pkl must not be folded onto <unk> (it would overwrite <unk>'s
+    own unigram and duplicate n-gram keys); a dict.pkl token missing from the ARPA maps to <unk> (id_map)."""
+    from chinese_asr_b200.lm import NGramLM, _hash_slot
+    import pickle
+    w2i, i2w = pickle.load(open(os.path.join(os.path.dirname(__file__), "golden", "dict.pkl"), "rb"))
+    a, b = i2w[10], i2w[11]
+    arpa = tmp_path / "oov.arpa"
+    arpa.write_text("\\data\\\nngram 1=5\nngram 2=3\n\n\\1-grams:\n"
+                    f"-2.5\t<unk>\t-0.3\n-99\t<s>\t-0.4\n-1.1\t</s>\n-1.3\t{a}\t-0.2\n-0.7\tZZZ\t-0.9\n\n"
+                    f"\\2-grams:\n-0.5\t<s> {a}\t-0.1\n-0.1\t{a} ZZZ\t-0.6\n-0.6\t{a} <unk>\t-0.05\n\n\\end\\\n",
+                    encoding="utf-8")
+    lm = NGramLM.from_arpa(str(arpa), w2i)
+    t = lm.tables()
+    assert t["uni_logp"][3] == np.float32(-2.5) and t["uni_bo"][3] == np.float32(-0.3)      # <unk> kept
+    assert t["id_map"][10] == 10 and t["id_map"][11] == 3 and t["id_map"][3] == 3 and t["id_map"][1] == 1
+    V = len(w2i)
+    assert int((t["bi_keys"] >= 0).sum()) == 2                                               # "a ZZZ" dropped
+    s = _hash_slot(10 * V + 3, len(t["bi_keys"]))
+    while t["bi_keys"][s] != 10 * V + 3:
+        s = (s + 1) & (len(t["bi_keys"]) - 1)
+    assert t["bi_vals"][s][0] == np.float32(-0.6)                                            # the literal "a <unk>" entry

@@ -96,7 +96,9 @@ def main():
     out["window"] = ref.audio_base.window.numpy()
 
     # ---- features ---------------------------------------------------------------------------
-    for name, seed, n in (("feat_2s", 11, 32000), ("feat_5s", 12, 80000), ("feat_odd", 13, 20011)):
+    # 10 s and 20 s are the utterance lengths of BASELINE.json's configs (332 / 665 encoder frames)
+    for name, seed, n in (("feat_2s", 11, 32000), ("feat_5s", 12, 80000), ("feat_odd", 13, 20011),
+                          ("feat_10s", 14, 160000), ("feat_20s", 15, 320000)):
         pcm = O.synth_pcm(seed, n)
         f_raw = ref_features(ref, pcm, normalise=False)
         f = ref_features(ref, pcm, normalise=True)
