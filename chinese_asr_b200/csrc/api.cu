@@ -5,6 +5,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <map>
+#include <mutex>
 #include <numeric>
 
 #include "asr_internal.cuh"
@@ -18,6 +20,23 @@ void set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device property of a kernel: handles on several GPUs of
+// one process (and several host threads, parallel.BatchPipeline) all come through here.
+int ensure_dynamic_smem(const void* func, size_t bytes) {
+    if (bytes <= 48 * 1024) return ASR_OK;
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, size_t> set;
+    int dev = 0;
+    ASR_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& cur = set[{func, dev}];
+    if (bytes > cur) {
+        ASR_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        cur = bytes;
+    }
+    return ASR_OK;
 }
 
 static int dev_alloc(std::vector<void*>& pool, void** p, size_t bytes) {
@@ -125,22 +144,17 @@ static int prepare_batch(asr_handle* h, const int32_t* h_L, int B, cudaStream_t 
     return ASR_OK;
 }
 
-// GEMM dispatch: CUDA-core fp32 (mode 0) or tcgen05 split precision with a fused gather + hi/cross split of
-// the A operand (mode 1).  Both produce fp32-faithful results; mode 1 runs on the tensor cores.
-static int gemm(asr_handle* h, const AOperand& A, const float* W, const hi_t* W_hi, const float* W_lo,
-                int M, int N, int K, const GemmEpilogue& epi, cudaStream_t st) {
-    if (h->gemm_mode == 1 && W_hi && W_lo && h->ws.a_hi) {
-        {
-            StageScope sc(h, kStSplit, st);
-            ASR_TRY(split_operand(A, M, K, h->ws.a_hi, h->ws.a_lo, epi.stop_flag, st, &h->launches));
-        }
-        StageScope sc(h, kStGemmKernel, st);
-        h->gemm_flops += 2.0 * M * N * K;
-        return launch_gemm_tc(h->ws.a_hi, h->ws.a_lo, W_hi, W_lo, M, N, K, epi, st, &h->launches);
+// GEMM on the tcgen05 split-precision engine with a gather + hi/cross split pass of the A operand in front
+// (only operands no producer kernel pre-splits: caller-supplied features, decode step 0).
+static int gemm(asr_handle* h, const AOperand& A, const hi_t* W_hi, const float* W_lo, int M, int N, int K,
+                const GemmEpilogue& epi, cudaStream_t st) {
+    {
+        StageScope sc(h, kStSplit, st);
+        ASR_TRY(split_operand(A, M, K, h->ws.a_hi, h->ws.a_lo, epi.stop_flag, st, &h->launches));
     }
     StageScope sc(h, kStGemmKernel, st);
     h->gemm_flops += 2.0 * M * N * K;
-    return launch_gemm(A, W, M, N, K, epi, st, &h->launches);
+    return launch_gemm_tc(h->ws.a_hi, h->ws.a_lo, W_hi, W_lo, M, N, K, epi, st, &h->launches);
 }
 
 static int split_weight(asr_handle* h, const float* w, int N, int K, hi_t** hi, float** lo,
@@ -151,14 +165,6 @@ static int split_weight(asr_handle* h, const float* w, int N, int K, hi_t** hi, 
     ASR_CUDA(cudaDeviceSynchronize());
     return ASR_OK;
 }
-// tf32 hi / lo, both fp32: the encoder recurrence engines pack their own operands from these
-static int split_weight_legacy(asr_handle* h, const float* w, int N, int K, float** hi, float** lo) {
-    ASR_TRY(dev_alloc_t(h->weight_allocs, hi, (size_t)N * K));
-    ASR_TRY(dev_alloc_t(h->weight_allocs, lo, (size_t)N * K));
-    ASR_TRY(split_operand_legacy(plain_a(w, K, K), N, K, *hi, *lo, 0));
-    ASR_CUDA(cudaDeviceSynchronize());
-    return ASR_OK;
-}
 
 static int run_encoder(asr_handle* h, int upto_layer, cudaStream_t st) {
     Workspace& w = h->ws;
@@ -166,11 +172,8 @@ static int run_encoder(asr_handle* h, int upto_layer, cudaStream_t st) {
     const int M = (int)m.rows;
     const float* x = w.xpack;
     int K = kFeat;
-    // With both engines on the tensor cores the recurrence kernel also emits its output as the
-    // pre-split A operand of the next GEMM (next layer's input projection / attention keys): the
-    // separate split pass (read 4 B, write 8 B per element, 4 x 170k x 512 per batch) disappears.
-    static const bool fuse_env = !(getenv("ASR_B200_FUSED_ENC_SPLIT") && atoi(getenv("ASR_B200_FUSED_ENC_SPLIT")) == 0);
-    const bool fuse = fuse_env && h->gemm_mode == 1 && h->rec_mode == 2 && w.a_hi;
+    // The recurrence kernel also emits its output as the pre-split A operand of the next GEMM (next layer's
+    // input projection / attention keys): no separate split pass (read 4 B, write 6 B per element).
     bool presplit = h->feat_split_ready;      // layer 0: the feature kernel wrote the split operand
     h->feat_split_ready = false;
     h->enc_split_ready = false;
@@ -188,27 +191,18 @@ static int run_encoder(asr_handle* h, int upto_layer, cudaStream_t st) {
                 ASR_TRY(launch_gemm_tc(w.a_hi, w.a_lo, h->w.enc_w_ih_hi[layer], h->w.enc_w_ih_lo[layer], M, 2 * kGates,
                                        K, e, st, &h->launches));
             } else {
-                ASR_TRY(gemm(h, plain_a(x, K, K), h->w.enc_w_ih[layer], h->w.enc_w_ih_hi[layer],
-                             h->w.enc_w_ih_lo[layer], M, 2 * kGates, K, e, st));
+                ASR_TRY(gemm(h, plain_a(x, K, K), h->w.enc_w_ih_hi[layer], h->w.enc_w_ih_lo[layer], M, 2 * kGates, K,
+                             e, st));
             }
         }
         {
             StageScope sc(h, kStEncRec, st);
             const bool last = layer == 3;
             float* y = w.act[layer & 1];
-            if (h->rec_mode == 2) {
-                ASR_TRY(launch_lstm_recurrence_tc3(h, layer, w.xg, layer == 0 ? nullptr : x, y,
-                                                   last ? w.enc : nullptr, w.h0, w.c0, st,
-                                                   fuse ? w.a_hi : nullptr, fuse ? w.a_lo : nullptr));
-                presplit = fuse;
-                if (last) h->enc_split_ready = fuse;      // utterance-major split of `enc` for the keys GEMM
-            } else if (h->rec_mode == 1) {
-                ASR_TRY(launch_lstm_recurrence_tc(h, layer, w.xg, layer == 0 ? nullptr : x, y,
-                                                  last ? w.enc : nullptr, w.h0, w.c0, st));
-            } else {
-                ASR_TRY(launch_lstm_recurrence(h, layer, w.xg, layer == 0 ? nullptr : x, y,
-                                               last ? w.enc : nullptr, w.h0, w.c0, st));
-            }
+            ASR_TRY(launch_lstm_recurrence_tc3(h, layer, w.xg, layer == 0 ? nullptr : x, y, last ? w.enc : nullptr,
+                                               w.h0, w.c0, st, w.a_hi, w.a_lo));
+            presplit = true;
+            if (last) h->enc_split_ready = true;       // utterance-major split of `enc` for the keys GEMM
             x = y;
             K = kEnc;
         }
@@ -224,106 +218,42 @@ static int run_keys(asr_handle* h, cudaStream_t st) {
     e.bias = h->w.att_b;
     e.C = w.keys;
     e.ldc = kAtt;
-    if (h->enc_split_ready && h->gemm_mode == 1) {
+    if (h->enc_split_ready) {
         h->enc_split_ready = false;
         StageScope sc2(h, kStGemmKernel, st);
         h->gemm_flops += 2.0 * (double)h->meta.rows * kAtt * kEnc;
         ASR_TRY(launch_gemm_tc(w.a_hi, w.a_lo, h->w.att_w_enc_t_hi, h->w.att_w_enc_t_lo, (int)h->meta.rows, kAtt, kEnc,
                                e, st, &h->launches));
     } else {
-        ASR_TRY(gemm(h, plain_a(w.enc, kEnc, kEnc), h->w.att_w_enc_t, h->w.att_w_enc_t_hi, h->w.att_w_enc_t_lo,
-                     (int)h->meta.rows, kAtt, kEnc, e, st));
+        ASR_TRY(gemm(h, plain_a(w.enc, kEnc, kEnc), h->w.att_w_enc_t_hi, h->w.att_w_enc_t_lo, (int)h->meta.rows, kAtt,
+                     kEnc, e, st));
     }
     return launch_keys_exp(h, st);
 }
 
-// one decoder step up to the logits: LSTM cell -> attention -> vocabulary projection
-static int decoder_step(asr_handle* h, int k, int step, int cur, float temperature,
-                        float* d_align_step, cudaStream_t st) {
+// One decoder step up to the vocabulary projection: LSTM cell -> attention -> projection (decoder.py:94-137),
+// with producer-side operand preparation:
+//   * the embedding part of the LSTM input projection is the pre-multiplied table E' (added in the cell GEMM's
+//     epilogue), so the cell GEMM runs over K = 1024 = [ctx[src] | h[src]];
+//   * the cell epilogue and the attention kernel write the fp16 hi / bf16 cross splits of h_new / ctx_new
+//     straight into the [R, 1024] A operand of the query and vocabulary GEMMs;
+//   * the vocabulary GEMM's epilogue keeps, per 224-column tile and row, the log-sum-exp partial and the top
+//     candidates (KP slots); logits are written to HBM only for the greedy driver's logits export.
+static int decoder_step(asr_handle* h, int k, int step, int cur, float temperature, float* d_align_step,
+                        bool materialise_logits, cudaStream_t st) {
     Workspace& w = h->ws;
     const int R = h->meta.B * k;
     const int nxt = cur ^ 1;
-    h->fused_dec = h->gemm_mode == 1 && !(getenv("ASR_B200_FUSED_DEC") && atoi(getenv("ASR_B200_FUSED_DEC")) == 0);
-    if (h->fused_dec) {
-        // Tensor-core decoder step with producer-side operand preparation:
-        //   * the embedding part of the LSTM input projection is the pre-multiplied table E' (added in the
-        //     cell GEMM's epilogue), so the cell GEMM runs over K = 1024 = [ctx[src] | h[src]];
-        //   * the cell epilogue and the attention kernel write the fp16 hi / bf16 cross splits of h_new / ctx_new
-        //     straight into the [R, 1024] A operand of the query and vocabulary GEMMs.
-        {
-            StageScope sc(h, kStCell, st);
+    {
+        StageScope sc(h, kStCell, st);
+        if (step == 0 || k == 1) {      // later beam steps: gathered by the bookkeeping of the previous step
             AOperand A{};
             A.nseg = 2;
             A.seg[0] = ASeg{w.dctx[cur], w.src_row, kEnc, kEnc};
             A.seg[1] = ASeg{w.dh[cur], w.src_row, kDecH, kProjK};
-            if (step == 0 || k == 1) {      // later beam steps: gathered by the bookkeeping kernel of the previous step
-                StageScope sc2(h, kStSplit, st);
-                ASR_TRY(split_operand(A, R, kProjK, w.a_hi, w.a_lo, w.ctrl, st, &h->launches));
-            }
-            GemmEpilogue e{};
-            e.kind = Epi::kLstmCell;
-            e.bias = h->w.dec_b;
-            e.c_prev = w.dc[cur];
-            e.c_rowidx = w.src_row;
-            e.h_out = w.dh[nxt];
-            e.c_out = w.dc[nxt];
-            e.H = kDecH;
-            e.stop_flag = w.ctrl;
-            e.ldw = kDecK;
-            e.addrow = h->w.emb_proj;
-            e.addrow_idx = w.tok_hist + (size_t)step * R;
-            e.addrow_ld = 4 * kDecH;
-            e.split_hi = w.dec_split_hi;
-            e.split_lo = w.dec_split_lo;
-            e.split_ld = kProjK;
-            StageScope sc3(h, kStGemmKernel, st);
-            h->gemm_flops += 2.0 * R * 4 * kDecH * kProjK;
-            ASR_TRY(launch_gemm_tc(w.a_hi, w.a_lo, h->w.dec_w_hi + kEmb, h->w.dec_w_lo + kEmb, R, 4 * kDecH, kProjK, e, st,
-                                   &h->launches));
+            StageScope sc2(h, kStSplit, st);
+            ASR_TRY(split_operand(A, R, kProjK, w.a_hi, w.a_lo, w.ctrl, st, &h->launches));
         }
-        {
-            StageScope sc(h, kStAttn, st);
-            GemmEpilogue e{};
-            e.kind = Epi::kBias;
-            e.bias = h->w.zero_bias;
-            e.C = w.att_q;
-            e.ldc = kAtt;
-            e.stop_flag = w.ctrl;
-            e.lda = kProjK;
-            {
-                StageScope sc3(h, kStGemmKernel, st);
-                h->gemm_flops += 2.0 * R * kAtt * kDecH;
-                ASR_TRY(launch_gemm_tc(w.dec_split_hi, w.dec_split_lo, h->w.att_w_hidden_t_hi, h->w.att_w_hidden_t_lo, R, kAtt,
-                                       kDecH, e, st, &h->launches));
-            }
-            {
-                StageScope sc4(h, kStAttnKernel, st);
-                ASR_TRY(launch_attention(h, k, step, nxt, d_align_step, st));
-            }
-        }
-        {
-            StageScope sc(h, kStProj, st);
-            GemmEpilogue e{};
-            e.kind = temperature == 1.f ? Epi::kBias : Epi::kBiasScale;
-            e.bias = h->w.proj_b;
-            e.C = w.logits;
-            e.ldc = kVocab;
-            e.scale = temperature;
-            e.stop_flag = w.ctrl;
-            StageScope sc3(h, kStGemmKernel, st);
-            h->gemm_flops += 2.0 * R * kVocab * kProjK;
-            ASR_TRY(launch_gemm_tc(w.dec_split_hi, w.dec_split_lo, h->w.proj_w_hi, h->w.proj_w_lo, R, kVocab, kProjK, e, st,
-                                   &h->launches));
-        }
-        return ASR_OK;
-    }
-    {
-        StageScope sc(h, kStCell, st);
-        AOperand A{};
-        A.nseg = 3;
-        A.seg[0] = ASeg{h->w.emb, w.tok_hist + (size_t)step * R, kEmb, kEmb};
-        A.seg[1] = ASeg{w.dctx[cur], w.src_row, kEnc, kEmb + kEnc};
-        A.seg[2] = ASeg{w.dh[cur], w.src_row, kDecH, kDecK};
         GemmEpilogue e{};
         e.kind = Epi::kLstmCell;
         e.bias = h->w.dec_b;
@@ -333,35 +263,57 @@ static int decoder_step(asr_handle* h, int k, int step, int cur, float temperatu
         e.c_out = w.dc[nxt];
         e.H = kDecH;
         e.stop_flag = w.ctrl;
-        ASR_TRY(gemm(h, A, h->w.dec_w, h->w.dec_w_hi, h->w.dec_w_lo, R, 4 * kDecH, kDecK, e, st));
+        e.ldw = kDecK;
+        e.addrow = h->w.emb_proj;
+        e.addrow_idx = w.tok_hist + (size_t)step * R;
+        e.addrow_ld = 4 * kDecH;
+        e.split_hi = w.dec_split_hi;
+        e.split_lo = w.dec_split_lo;
+        e.split_ld = kProjK;
+        StageScope sc3(h, kStGemmKernel, st);
+        h->gemm_flops += 2.0 * R * 4 * kDecH * kProjK;
+        ASR_TRY(launch_gemm_tc(w.a_hi, w.a_lo, h->w.dec_w_hi + kEmb, h->w.dec_w_lo + kEmb, R, 4 * kDecH, kProjK, e, st,
+                               &h->launches));
     }
     {
         StageScope sc(h, kStAttn, st);
-        // query projection q = h_new * W_hidden (attention.py:92) on the GEMM engine
         GemmEpilogue e{};
         e.kind = Epi::kBias;
         e.bias = h->w.zero_bias;
         e.C = w.att_q;
         e.ldc = kAtt;
         e.stop_flag = w.ctrl;
-        ASR_TRY(gemm(h, plain_a(w.dh[nxt], kDecH, kDecH), h->w.att_w_hidden_t, h->w.att_w_hidden_t_hi,
-                     h->w.att_w_hidden_t_lo, R, kAtt, kDecH, e, st));
-        ASR_TRY(launch_attention(h, k, step, nxt, d_align_step, st));
+        e.lda = kProjK;
+        {
+            StageScope sc3(h, kStGemmKernel, st);
+            h->gemm_flops += 2.0 * R * kAtt * kDecH;
+            ASR_TRY(launch_gemm_tc(w.dec_split_hi, w.dec_split_lo, h->w.att_w_hidden_t_hi, h->w.att_w_hidden_t_lo, R, kAtt,
+                                   kDecH, e, st, &h->launches));
+        }
+        {
+            StageScope sc4(h, kStAttnKernel, st);
+            ASR_TRY(launch_attention(h, k, step, nxt, d_align_step, st));
+        }
     }
     {
         StageScope sc(h, kStProj, st);
-        AOperand A{};
-        A.nseg = 2;
-        A.seg[0] = ASeg{w.dh[nxt], nullptr, kDecH, kDecH};
-        A.seg[1] = ASeg{w.dctx[nxt], nullptr, kEnc, kProjK};
         GemmEpilogue e{};
         e.kind = temperature == 1.f ? Epi::kBias : Epi::kBiasScale;
         e.bias = h->w.proj_b;
-        e.C = w.logits;
-        e.ldc = kVocab;
         e.scale = temperature;
         e.stop_flag = w.ctrl;
-        ASR_TRY(gemm(h, A, h->w.proj_w, h->w.proj_w_hi, h->w.proj_w_lo, R, kVocab, kProjK, e, st));
+        if (materialise_logits) {
+            e.C = w.logits;
+            e.ldc = kVocab;
+        } else {
+            e.topk_slots = vocab_topk_slots(k);
+            e.topk_part = w.topk_part;
+            e.topk_ms = w.topk_ms;
+        }
+        StageScope sc3(h, kStGemmKernel, st);
+        h->gemm_flops += 2.0 * R * kVocab * kProjK;
+        ASR_TRY(launch_gemm_tc(w.dec_split_hi, w.dec_split_lo, h->w.proj_w_hi, h->w.proj_w_lo, R, kVocab, kProjK, e, st,
+                               &h->launches));
     }
     return ASR_OK;
 }
@@ -384,7 +336,7 @@ static int beam_decode_device(asr_handle* h, int k, int max_len, float temperatu
     // The legacy default stream cannot be captured: a blocking stream of the handle stands in for it
     // (implicitly ordered with the legacy stream on both sides, so callers see the same semantics).
     cudaStream_t caller_st = st;
-    static const bool use_graph = !(getenv("ASR_B200_GRAPH") && atoi(getenv("ASR_B200_GRAPH")) == 0);
+    const bool use_graph = true;
     if (use_graph && !h->timing && (st == nullptr || st == cudaStreamLegacy)) {
         if (!h->graph_stream) ASR_CUDA(cudaStreamCreate(&h->graph_stream));
         st = h->graph_stream;
@@ -393,10 +345,9 @@ static int beam_decode_device(asr_handle* h, int k, int max_len, float temperatu
         ASR_TRY(decode_init(h, k, max_len, false, st));
         int cur = 0;
         for (int step = 0; step < max_len; ++step) {
-            ASR_TRY(decoder_step(h, k, step, cur, temperature, nullptr, st));
+            ASR_TRY(decoder_step(h, k, step, cur, temperature, nullptr, false, st));
             StageScope sc(h, kStTopk, st);
-            ASR_TRY(launch_row_topk(h, k, step, st));
-            ASR_TRY(launch_beam_bookkeep(h, k, step, max_len, st));
+            ASR_TRY(launch_beam_merge(h, k, step, st));
             cur ^= 1;
         }
         return ASR_OK;
@@ -407,8 +358,7 @@ static int beam_decode_device(asr_handle* h, int k, int max_len, float temperatu
     // (B, k, max_len, Lmax, frames, temperature, engines) keys the graph.
     int temp_bits = 0;
     memcpy(&temp_bits, &temperature, sizeof(int));
-    const long long key[8] = {h->meta.B, k, max_len, h->meta.Lmax, (long long)h->meta.rows, temp_bits,
-                              h->gemm_mode, h->rec_mode};
+    const long long key[8] = {h->meta.B, k, max_len, h->meta.Lmax, (long long)h->meta.rows, temp_bits, 0, 0};
     if (use_graph && !h->timing) {
         if (h->graph_exec && memcmp(key, h->graph_key, sizeof(key)) == 0) {
             ASR_CUDA(cudaGraphLaunch(h->graph_exec, st));
@@ -454,13 +404,13 @@ static int greedy_decode_device(asr_handle* h, int max_len, float* d_align, floa
     int cur = 0;
     for (int step = 0; step < max_len; ++step) {
         float* al = d_align ? d_align + (size_t)step * h->meta.Lmax * B : nullptr;
-        ASR_TRY(decoder_step(h, 1, step, cur, 1.f, al, st));
+        ASR_TRY(decoder_step(h, 1, step, cur, 1.f, al, d_logits != nullptr, st));
         if (d_logits) {
             // logits are in sorted order; export in original order
             ASR_TRY(launch_unsort_rows(h, h->ws.logits, kVocab, d_logits + (size_t)step * B * kVocab, st));
         }
         StageScope sc(h, kStTopk, st);
-        ASR_TRY(launch_greedy_pick(h, step, max_len, st));
+        ASR_TRY(launch_greedy_pick(h, step, d_logits != nullptr, st));
         cur ^= 1;
     }
     ASR_TRY(launch_greedy_finalise(h, max_len, st));
@@ -520,8 +470,7 @@ static int features_device(asr_handle* h, const void* d_pcm, int format, const i
     for (int i = 0; i < B; ++i) lmax = std::max(lmax, (int)h_L[i]);
     // Fused path (PCM -> hypotheses): the features are only ever read by the layer-0 input GEMM, so they are written
     // straight as its split A operand (6 bytes per value) instead of fp32 + a split pass (4 + 4 + 6 bytes)
-    static const bool fuse_env = !(getenv("ASR_B200_FUSED_FEAT_SPLIT") && atoi(getenv("ASR_B200_FUSED_FEAT_SPLIT")) == 0);
-    const bool fuse = packed_out && fuse_env && h->gemm_mode == 1 && w.a_hi != nullptr;
+    const bool fuse = packed_out;
     ASR_TRY(launch_delta_cmvn(h, w.mel, w.d_frame_off, w.d_featrow_off, B, lmax, normalise, eps,
                               packed_out ? h->meta.d_feat2packed : nullptr, fuse ? nullptr : d_out, st,
                               fuse ? w.a_hi : nullptr, fuse ? w.a_lo : nullptr));
@@ -618,10 +567,7 @@ int asr_create(asr_handle** out, const asr_weights* wt, const asr_feature_consts
     for (int layer = 0; layer < 4; ++layer) {
         const int K = layer == 0 ? kFeat : kEnc;
         if ((rc = split_weight(h, h->w.enc_w_ih[layer], 2 * kGates, K, &h->w.enc_w_ih_hi[layer], &h->w.enc_w_ih_lo[layer])) != ASR_OK) return rc;
-        if ((rc = split_weight_legacy(h, h->w.enc_w_hh[layer], 2 * kGates, kEncH, &h->w.enc_w_hh_hi[layer], &h->w.enc_w_hh_lo[layer])) != ASR_OK) return rc;
         if ((rc = split_weight(h, h->w.enc_w_hh[layer], 2 * kGates, kEncH, &h->w.enc_w_hh_hi16[layer], &h->w.enc_w_hh_x[layer])) != ASR_OK) return rc;
-        if ((rc = dev_alloc_t(pool, &h->w.enc_w_hh_lo_bf[layer], (size_t)2 * kGates * kEncH / 2)) != ASR_OK) return rc;
-        if ((rc = pack_bf16_pairs(h->w.enc_w_hh_lo[layer], h->w.enc_w_hh_lo_bf[layer], (long long)2 * kGates * kEncH / 2)) != ASR_OK) return rc;
     }
     if ((rc = split_weight(h, h->w.dec_w, 4 * kDecH, kDecK, &h->w.dec_w_hi, &h->w.dec_w_lo)) != ASR_OK) return rc;
     if ((rc = split_weight(h, h->w.proj_w, kVocab, kProjK, &h->w.proj_w_hi, &h->w.proj_w_lo)) != ASR_OK) return rc;
@@ -642,27 +588,13 @@ int asr_create(asr_handle** out, const asr_weights* wt, const asr_feature_consts
         if ((rc = launch_gemm_tc(e_hi, e_lo, h->w.dec_w_hi, h->w.dec_w_lo, kVocab, 4 * kDecH, kEmb, e, 0, nullptr)) != ASR_OK) return rc;
         ASR_CUDA(cudaDeviceSynchronize());
     }
-    const char* env = getenv("ASR_B200_GEMM");
-    // defaults: every GEMM-shaped stage and the recurrence on the tcgen05 tensor cores (split precision);
-    // ASR_B200_GEMM=simt / ASR_B200_REC=simt|tc select the CUDA-core / smem-resident variants
-    h->gemm_mode = (env && strcmp(env, "simt") == 0) ? 0 : 1;
-    const char* env_rec = getenv("ASR_B200_REC");
-    h->rec_mode = (env_rec && strcmp(env_rec, "simt") == 0) ? 0 : (env_rec && strcmp(env_rec, "tc") == 0) ? 1 : 2;
     *out = h;
     return ASR_OK;
 }
 
-int asr_set_gemm_mode(asr_handle* h, int mode) {
-    if (!h || mode < 0 || mode > 7) { set_error("asr_set_gemm_mode: bad argument"); return ASR_ERR_ARG; }
-    h->gemm_mode = mode & 1;          // bit 0: GEMM stages on tcgen05
-    // bit 1: encoder recurrence on tcgen05 (W_hi in smem); bit 2: weights fully TMEM-resident
-    h->rec_mode = (mode & 4) ? 2 : ((mode & 2) ? 1 : 0);
-    return ASR_OK;
-}
-
-// Standalone GEMM for tests: d_C[M,N] = d_A[M,K] * d_W[N,K]^T + d_bias[N] with either path.
+// Standalone GEMM for tests: d_C[M,N] = d_A[M,K] * d_W[N,K]^T + d_bias[N] through the split-precision engine.
 int asr_test_gemm(asr_handle* h, const float* d_A, const float* d_W, const float* d_bias, float* d_C, int M,
-                  int N, int K, int mode, void* stream) {
+                  int N, int K, void* stream) {
     if (!h || !d_A || !d_W || !d_bias || !d_C) { set_error("asr_test_gemm: NULL argument"); return ASR_ERR_ARG; }
     cudaStream_t st = (cudaStream_t)stream;
     GemmEpilogue e{};
@@ -670,24 +602,19 @@ int asr_test_gemm(asr_handle* h, const float* d_A, const float* d_W, const float
     e.bias = d_bias;
     e.C = d_C;
     e.ldc = N;
-    if (mode == 0) {
-        ASR_TRY(launch_gemm(plain_a(d_A, K, K), d_W, M, N, K, e, st, &h->launches));
-    } else {
-        hi_t *a_hi, *w_hi;
-        float *a_lo, *w_lo;
-        ASR_CUDA(cudaMalloc(&a_hi, sizeof(float) * (size_t)M * K));
-        ASR_CUDA(cudaMalloc(&a_lo, sizeof(float) * (size_t)M * K));
-        ASR_CUDA(cudaMalloc(&w_hi, sizeof(float) * (size_t)N * K));
-        ASR_CUDA(cudaMalloc(&w_lo, sizeof(float) * (size_t)N * K));
-        int rc = split_operand(plain_a(d_A, K, K), M, K, a_hi, a_lo, nullptr, st, &h->launches);
-        if (rc == ASR_OK) rc = split_operand(plain_a(d_W, K, K), N, K, w_hi, w_lo, nullptr, st, &h->launches, kSplitWeight);
-        if (rc == ASR_OK) rc = launch_gemm_tc(a_hi, a_lo, w_hi, w_lo, M, N, K, e, st, &h->launches);
-        cudaError_t ce = cudaStreamSynchronize(st);
-        cudaFree(a_hi); cudaFree(a_lo); cudaFree(w_hi); cudaFree(w_lo);
-        if (rc != ASR_OK) return rc;
-        if (ce != cudaSuccess) { set_error("asr_test_gemm: %s", cudaGetErrorString(ce)); return ASR_ERR_CUDA; }
-    }
-    ASR_CUDA(cudaStreamSynchronize(st));
+    hi_t *a_hi, *w_hi;
+    float *a_lo, *w_lo;
+    ASR_CUDA(cudaMalloc(&a_hi, sizeof(float) * (size_t)M * K));
+    ASR_CUDA(cudaMalloc(&a_lo, sizeof(float) * (size_t)M * K));
+    ASR_CUDA(cudaMalloc(&w_hi, sizeof(float) * (size_t)N * K));
+    ASR_CUDA(cudaMalloc(&w_lo, sizeof(float) * (size_t)N * K));
+    int rc = split_operand(plain_a(d_A, K, K), M, K, a_hi, a_lo, nullptr, st, &h->launches);
+    if (rc == ASR_OK) rc = split_operand(plain_a(d_W, K, K), N, K, w_hi, w_lo, nullptr, st, &h->launches, kSplitWeight);
+    if (rc == ASR_OK) rc = launch_gemm_tc(a_hi, a_lo, w_hi, w_lo, M, N, K, e, st, &h->launches);
+    cudaError_t ce = cudaStreamSynchronize(st);
+    cudaFree(a_hi); cudaFree(a_lo); cudaFree(w_hi); cudaFree(w_lo);
+    if (rc != ASR_OK) return rc;
+    if (ce != cudaSuccess) { set_error("asr_test_gemm: %s", cudaGetErrorString(ce)); return ASR_ERR_CUDA; }
     return ASR_OK;
 }
 
@@ -796,14 +723,14 @@ int asr_reserve(asr_handle* h, int max_utts, int64_t max_rows, int max_beam, int
         ASR_TRY(dev_alloc_t(pool, &w.dctx[i], R * kEnc));
     }
     {
-        // tensor-core recurrence staging: 2 directions x ceil(max_utts / 16) chunks x 8 CTAs x 8 KB
-        // (encoder_tc.cu), or 2 x max(7, ceil(max_utts / 128)) chunks x 8 CTAs x 24 KB (encoder_tc3.cu)
-        const size_t v2 = (size_t)2 * ((max_utts + 15) / 16) * 8 * 8192;
+        // recurrence exchange staging: 2 directions x max(7, ceil(max_utts / 128)) chunks x 8 CTAs (encoder_tc3.cu)
         const size_t v3 = (size_t)2 * std::max(7, (max_utts + 127) / 128) * 8 * rec3_stage_bytes_per_cta();
-        w.rec_stage_ctas = (std::max(v2, v3) + 8191) / 8192;      // capacity in 8 KB units
+        w.rec_stage_ctas = (v3 + 8191) / 8192;      // capacity in 8 KB units
         ASR_TRY(dev_alloc_t(pool, &w.rec_stage, w.rec_stage_ctas * 2048));
     }
-    ASR_TRY(dev_alloc_t(pool, &w.logits, R * kVocab));
+    ASR_TRY(dev_alloc_t(pool, &w.logits, (size_t)max_utts * kVocab));
+    ASR_TRY(dev_alloc_t(pool, &w.topk_part, (size_t)kVocabTiles * R * vocab_topk_slots(max_beam)));
+    ASR_TRY(dev_alloc_t(pool, &w.topk_ms, (size_t)kVocabTiles * R));
     ASR_TRY(dev_alloc_t(pool, &w.att_q, R * kAtt));
     ASR_TRY(dev_alloc_t(pool, &w.dec_split_hi, R * kProjK));
     ASR_TRY(dev_alloc_t(pool, &w.dec_split_lo, R * kProjK));
@@ -812,13 +739,10 @@ int asr_reserve(asr_handle* h, int max_utts, int64_t max_rows, int max_beam, int
     w.att_score_ld = std::min<int64_t>(max_rows, 4096);
     ASR_TRY(dev_alloc_t(pool, &w.att_score, (size_t)max_utts * w.att_score_ld));
     ASR_TRY(dev_alloc_t(pool, &w.att_ticket, (size_t)max_utts));
-    ASR_TRY(dev_alloc_t(pool, &w.row_ticket, (size_t)max_utts));
     ASR_TRY(dev_alloc_t(pool, &w.tok_hist, (size_t)(max_len + 1) * R));
     ASR_TRY(dev_alloc_t(pool, &w.prev_hist, (size_t)(max_len + 1) * R));
     ASR_TRY(dev_alloc_t(pool, &w.src_row, R));
     ASR_TRY(dev_alloc_t(pool, &w.beam_score, R));
-    ASR_TRY(dev_alloc_t(pool, &w.rowcand_s, R * K2));
-    ASR_TRY(dev_alloc_t(pool, &w.rowcand_t, R * K2));
     ASR_TRY(dev_alloc_t(pool, &w.fin_score, (size_t)max_len * R));
     ASR_TRY(dev_alloc_t(pool, &w.fin_row, (size_t)max_len * R));
     ASR_TRY(dev_alloc_t(pool, &w.tr_cand_s, (size_t)max_len * max_utts * K2));
@@ -1164,7 +1088,7 @@ static int issue_prefetch(asr_handle* h, int slot) {
     // (BatchPipeline) - for its whole duration; between pieces other streams' copies get their turn.
     {
         const size_t bytes = pcm_sample_bytes(h->pre_fmt[slot]) * (size_t)h->pre_n[slot];
-        static const size_t piece = getenv("ASR_B200_PREFETCH_PIECE") ? (size_t)atoll(getenv("ASR_B200_PREFETCH_PIECE")) : ((size_t)4 << 20);
+        const size_t piece = (size_t)4 << 20;
         const char* src = static_cast<const char*>(h->pre_src[slot]);
         char* dst = reinterpret_cast<char*>(h->ws.pcm_pre[slot]);
         for (size_t o = 0; o < bytes; o += piece)
@@ -1193,9 +1117,6 @@ int asr_transcribe_pcm(asr_handle* h, const void* h_pcm, int format, float cmvn_
         const int c = (int)((h->pre_count + sl) & 1);
         if (h->pre_src[c] == src && h->pre_n[c] == n && h->pre_fmt[c] == format) { hit = c; break; }
     }
-    static const bool dbg_pre = getenv("ASR_B200_PREFETCH_DBG") != nullptr;
-    if (dbg_pre) fprintf(stderr, "[prefetch] transcribe: %s (slot %d, event %s)\n", hit >= 0 ? "hit" : "miss", hit,
-                         hit >= 0 ? (cudaEventQuery(h->pre_ev[hit]) == cudaSuccess ? "done" : "pending") : "-");
     if (hit >= 0) {
         ASR_TRY(issue_prefetch(h, hit));          // not started yet if no batch ran since it was registered
         ASR_CUDA(cudaStreamWaitEvent(st, h->pre_ev[hit], 0));
@@ -1224,7 +1145,8 @@ int64_t asr_launch_count(asr_handle* h, int reset) {
 
 int asr_stage_timing(asr_handle* h, int enable) {
     if (!h) return ASR_ERR_ARG;
-    h->timing = enable != 0;
+    h->timing = (enable & 1) != 0;
+    h->rec_timeline = (enable & 2) != 0;
     h->n_ev = 0;
     h->gemm_flops = 0.0;
     return ASR_OK;

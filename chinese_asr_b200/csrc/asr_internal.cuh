@@ -27,8 +27,13 @@ constexpr int kNfft = 512, kHop = 160, kWin = 400, kBins = 257, kWinOff = 56;
 constexpr int kMaxBeam = ASR_MAX_BEAM;
 constexpr int kNumSMs = 148;
 constexpr int kStages = 12;       // 8 pipeline stages + kernel-level timers (GEMM kernel, operand split)
+// vocabulary projection with fused log-sum-exp / top-k partials (gemm_tc.cu): 224-column tiles, 5004 = 22 x 224 + 76
+constexpr int kVocabTileN = 224;
+constexpr int kVocabTiles = (kVocab + kVocabTileN - 1) / kVocabTileN;     // 23
 
 void set_error(const char* fmt, ...);
+// raise a kernel's dynamic shared-memory limit on the current device (once per kernel and device)
+int ensure_dynamic_smem(const void* func, size_t bytes);
 
 // ---- split-precision operands of the tcgen05 GEMM engine (gemm_tc.cu) ---------------------------
 // x = hi + lo with hi = fp16(x) (11 significant bits, like tf32, but half the bytes and the full-rate
@@ -119,27 +124,22 @@ struct GemmEpilogue {
     hi_t* split_hi;        // kLstmCell: also write fp16(h) / the cross operand into [M, split_ld] at column u,
     float* split_lo;       //   the A operand of the query / vocabulary GEMMs (no separate split pass)
     int split_ld;
+    // vocabulary epilogue (kBias / kBiasScale with topk_slots = KP > 0): nothing is written to C; per 224-column
+    // tile tn and row r the KP largest logits (value bits, token id) and the (max, sum of exp) of the tile
+    int topk_slots;
+    uint2* topk_part;      // [kVocabTiles, M, KP]
+    float2* topk_ms;       // [kVocabTiles, M]
 };
 
-// C[M,N] = A[M,K] * W[N,K]^T (+ epilogue).  fp32 in, fp32 accumulate.
-int launch_gemm(const AOperand& A, const float* W, int M, int N, int K, const GemmEpilogue& epi,
-                cudaStream_t st, int64_t* launches);
-// tcgen05 split-precision path (gemm_tc.cu): operands pre-split into an fp16 `hi` part ([rows, K] halves)
-// and a `lo` buffer ([rows, K] 4-byte words) holding the bf16 cross-term operand (layout: see
-// split_operand_kernel).  kSplitLegacy (encoder recurrence weights): hi = rn_tf32(x), lo = rn_tf32(x - hi),
-// both fp32, `hi` then points to floats.
-enum { kSplitLegacy = 0, kSplitAct = 1, kSplitWeight = 2 };
+// C[M,N] = A[M,K] * W[N,K]^T (+ epilogue) on the tcgen05 split-precision engine (gemm_tc.cu): operands
+// pre-split into an fp16 `hi` part ([rows, K] halves) and a `lo` buffer ([rows, K] 4-byte words) holding the
+// bf16 cross-term operand (layout: see split_operand_kernel).
+enum { kSplitAct = 1, kSplitWeight = 2 };
 int split_operand(const AOperand& A, int M, int K, hi_t* hi, float* lo, const int* stop_flag,
                   cudaStream_t st, int64_t* launches, int fmt = kSplitAct);
-int split_operand_legacy(const AOperand& A, int M, int K, float* hi, float* lo, cudaStream_t st);
 int launch_gemm_tc(const hi_t* a_hi, const float* a_lo, const hi_t* w_hi, const float* w_lo, int M,
                    int N, int K, const GemmEpilogue& epi, cudaStream_t st, int64_t* launches);
-// a weight matrix with its pre-split copies
-struct SplitW {
-    float* w = nullptr;    // [N, K] fp32
-    float* hi = nullptr;   // rn_tf32(w)         (legacy fp32 pair of the smem-resident recurrence engine)
-    float* lo = nullptr;   // rn_tf32(w - hi)
-};
+int vocab_topk_slots(int k);      // KP of the vocabulary epilogue for beam width k (>= 2k): 2, 8, 16 or 32
 
 // ---------------------------------------------------------------------------------------------
 struct FeatureConsts {
@@ -180,9 +180,6 @@ struct PackedWeights {
     float* proj_w_lo = nullptr;
     hi_t* att_w_enc_t_hi = nullptr;
     float* att_w_enc_t_lo = nullptr;
-    float* enc_w_hh_hi[4] = {};          // [2, 1024, 256] tf32 split of enc_w_hh (tensor-core recurrence)
-    float* enc_w_hh_lo[4] = {};
-    uint32_t* enc_w_hh_lo_bf[4] = {};    // [2, 1024, 128] bf16 pairs of the residual (smem-resident tensor-core recurrence)
     hi_t* enc_w_hh_hi16[4] = {};         // [2, 1024, 256] fp16 hi + cross words of enc_w_hh (kSplitWeight): the
     float* enc_w_hh_x[4] = {};           //   TMEM-resident recurrence (encoder_tc3.cu)
     float* att_w_hidden_t = nullptr;     // [128, 512] (W_hidden transposed -> [N, K]) for the query GEMM
@@ -260,20 +257,19 @@ struct Workspace {
     float* dh[2] = {};           // [R, 512]
     float* dc[2] = {};
     float* dctx[2] = {};
-    float* logits = nullptr;     // [R, 5004]
+    float* logits = nullptr;     // [max_utts, 5004]: only the greedy driver's logits export (tests) materialises them
+    uint2* topk_part = nullptr;  // [23, R, KP] per vocabulary tile and row: top-KP (logit bits, token id)
+    float2* topk_ms = nullptr;   // [23, R] per vocabulary tile and row: (max logit, sum of exp(logit - max))
     float* att_q = nullptr;      // [R, 128] query projection of the current step
     hi_t* dec_split_hi = nullptr;    // [R, 1024] fp16 hi of [h_new | ctx_new], written by the producing kernels
     float* dec_split_lo = nullptr;
     float* att_part = nullptr;   // [B, S, k, 2 + 512] partial (max, sum, ctx)
     float* att_score = nullptr;  // [R, Lmax_cap] raw scores (alignment export)
     int* att_ticket = nullptr;   // [B]
-    int* row_ticket = nullptr;   // [B] rows of the utterance whose top-K is published (row_topk_kernel)
     int* tok_hist = nullptr;     // [max_len + 1, R]
     int* prev_hist = nullptr;    // [max_len + 1, R]
     int* src_row = nullptr;      // [R] source row of the current step's state
     float* beam_score = nullptr; // [R]
-    float* rowcand_s = nullptr;  // [R, 2k]
-    int* rowcand_t = nullptr;    // [R, 2k]
     float* fin_score = nullptr;  // [max_len, B, k]  (NaN = none)
     int* fin_row = nullptr;      // [max_len, B, k]
     float* tr_cand_s = nullptr;  // [max_len, B, 2k]
@@ -283,8 +279,8 @@ struct Workspace {
     int* tr_tok = nullptr;       // [max_len, B, k]
     int* top_done = nullptr;     // [B]
     int* ctrl = nullptr;         // [8]: 0 stop_step(-1), 1 done_count, 2 ticket, 3 steps_run
-    float* rec_stage = nullptr;  // tensor-core recurrence: per CTA 8 KB image of its new h slice (hi | lo)
-    size_t rec_stage_ctas = 0;
+    float* rec_stage = nullptr;  // recurrence: per CTA the exchange image of its new h slice (encoder_tc3.cu)
+    size_t rec_stage_ctas = 0;   // capacity in 8 KB units
     // greedy
     float* g_accum = nullptr;    // [B]
     int* g_finished = nullptr;   // [B]
@@ -320,8 +316,7 @@ struct asr_handle {
     int last_out_ld = 0;         // row stride of ws.out_tokens after the last decode (its max_len)
     int64_t launches = 0;
     bool timing = false;
-    int gemm_mode = 0;           // 0 = CUDA-core fp32 FMA, 1 = tcgen05 split precision (fp16 hi + bf16 cross)
-    int rec_mode = 0;            // encoder recurrence: 0 = CUDA-core (register-stationary W_hh), 1 = tcgen05
+    bool rec_timeline = false;   // print the recurrence kernel's clock64 step timeline (asr_stage_timing(h, 2))
     cudaGraphExec_t graph_exec = nullptr;   // captured beam-decode loop for the shape in graph_key
     long long graph_key[8] = {};
     long long graph_seen[8] = {};
@@ -336,7 +331,6 @@ struct asr_handle {
     uint64_t pre_count = 0;
     bool feat_split_ready = false;  // ws.a_hi / a_lo hold the split of the packed features (written by feat_write_kernel)
     bool enc_split_ready = false;  // ws.a_hi / a_lo hold the split of `enc` (written by the last recurrence)
-    bool fused_dec = false;     // decoder step with pre-multiplied embeddings and producer-side operand splits
     double gemm_flops = 0.0;     // algorithmic 2*M*N*K of every GEMM-engine launch since the last reset
     cudaEvent_t ev[2 * 1024] = {};
     int n_ev = 0;
@@ -363,22 +357,14 @@ int launch_cmvn(asr_handle* h, const float* d_in, const int* d_featrow_off, int 
 // ---- encoder.cu ------------------------------------------------------------------------------
 int launch_pack_rows(asr_handle* h, const float* src, const int* rowmap, int64_t rows, int width,
                      float* dst, cudaStream_t st);
-// one bidirectional layer recurrence.  xg [rows, 2048]; x_in residual input (nullptr for layer 0)
-// y_packed: packed time-major output (or nullptr); y_utt: utterance-major output (or nullptr)
-int launch_lstm_recurrence(asr_handle* h, int layer, const float* xg, const float* x_in,
-                           float* y_packed, float* y_utt, float* h_fin, float* c_fin,
-                           cudaStream_t st);
-// tensor-core (tcgen05 3xTF32) variant, encoder_tc.cu
-int launch_lstm_recurrence_tc(asr_handle* h, int layer, const float* xg, const float* x_in,
-                              float* y_packed, float* y_utt, float* h_fin, float* c_fin,
-                              cudaStream_t st);
-// weights fully TMEM-resident variant, encoder_tc3.cu.  split_hi / split_lo (optional, [rows, 512]):
-// the layer output is also written as the pre-split A operand of the GEMM that consumes it (kSplitAct
-// layout, same row order as y_packed - or as y_utt when y_packed is nullptr)
+// One bidirectional layer recurrence on the tensor cores, weights TMEM-resident (encoder_tc3.cu).
+// xg [rows, 2048]; x_in residual input (nullptr for layer 0); y_packed: packed time-major output (or nullptr);
+// y_utt: utterance-major output (or nullptr).  split_hi / split_lo (optional, [rows, 512]): the layer output is
+// also written as the pre-split A operand of the GEMM that consumes it (kSplitAct layout, same row order as
+// y_packed - or as y_utt when y_packed is nullptr)
 int launch_lstm_recurrence_tc3(asr_handle* h, int layer, const float* xg, const float* x_in,
                                float* y_packed, float* y_utt, float* h_fin, float* c_fin,
                                cudaStream_t st, hi_t* split_hi = nullptr, float* split_lo = nullptr);
-int pack_bf16_pairs(const float* src, uint32_t* dst, long long n_pairs);
 size_t rec3_stage_bytes_per_cta();
 int launch_export_padded(asr_handle* h, const float* src_utt, int width, float* dst, int Lmax, int B,
                          const float* pad_row, cudaStream_t st);
@@ -390,11 +376,12 @@ int launch_unsort_rows(asr_handle* h, const float* src, int width, float* dst, c
 int decode_init(asr_handle* h, int k, int max_len, bool greedy, cudaStream_t st);
 int launch_keys_exp(asr_handle* h, cudaStream_t st);
 int launch_attention(asr_handle* h, int k, int step, int cur, float* d_align_step, cudaStream_t st);
-int launch_row_topk(asr_handle* h, int k, int step, cudaStream_t st);
-int launch_beam_bookkeep(asr_handle* h, int k, int step, int max_len, cudaStream_t st);
+// per utterance: log-sum-exp and top-2k over the k rows' vocabulary-tile partials, then the beam bookkeeping
+int launch_beam_merge(asr_handle* h, int k, int step, cudaStream_t st);
 int launch_beam_finalise(asr_handle* h, int k, int max_len, int second_pass, double lm_weight,
                          double length_weight, cudaStream_t st);
-int launch_greedy_pick(asr_handle* h, int step, int max_len, cudaStream_t st);
+// from_logits: argmax / log-sum-exp over materialised logits (export path); else over the tile partials
+int launch_greedy_pick(asr_handle* h, int step, bool from_logits, cudaStream_t st);
 int launch_greedy_finalise(asr_handle* h, int max_len, cudaStream_t st);
 int launch_lm_score(asr_handle* h, const int* d_ids, const int* d_n, int n, int max_n,
                     float* d_scores, cudaStream_t st);

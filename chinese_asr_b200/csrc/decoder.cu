@@ -9,13 +9,13 @@
 //                        and re-gathers them every step, model.py:660-669, 913-916).  Long
 //                        utterances are split over several CTAs (flash-decoding style partial
 //                        softmax), the last CTA to finish combines the partials.
-//   row_topk_kernel    : per row: logsumexp (model.py:835), log-prob + beam score (model.py:836)
-//                        and an exact top-2k by 4-pass radix select on registers.
-//   beam_bookkeep_kernel: per utterance: merge the k rows' candidates into the top-2k over k*V
-//                        (model.py:860-867), EOS/finished bookkeeping (model.py:876-889), early
-//                        stop flag (model.py:897-901), active-set selection, back-pointers and
-//                        history (model.py:904-929).  No host sync: the stop decision is a device
-//                        flag every later kernel checks.
+//   beam_merge_kernel  : per utterance: logsumexp of its k rows from the vocabulary GEMM's per-tile
+//                        (max, sum) partials (model.py:835), log-prob + beam score (model.py:836) of the
+//                        per-tile top candidates, exact top-2k over k*V (model.py:860-867), then
+//                        EOS/finished bookkeeping (model.py:876-889), early stop flag (model.py:897-901),
+//                        active-set selection, back-pointers and history (model.py:904-929) and the gather
+//                        of the next step's cell-GEMM operand.  The logits themselves never reach HBM.  No
+//                        host sync: the stop decision is a device flag every later kernel checks.
 //   beam_finalise_kernel: parse_finished_tensors + second-pass LM rescoring + un-finished
 //                        fallback (model.py:708-765, 945-987), n-gram LM lookups on device.
 //   greedy_pick_kernel : argmax / score / length bookkeeping of the greedy loop (model.py:554-578).
@@ -62,7 +62,7 @@ struct InitParams {
     const float* h0; const float* c0;
     float* dh; float* dc; float* dctx;
     int* src_row; float* beam_score; int* tok_hist; int* prev_hist; int* top_done;
-    int* ctrl; int* att_ticket; int* row_ticket;
+    int* ctrl; int* att_ticket;
     float* g_accum; int* g_finished; int* g_len;
     int B, k, R;
 };
@@ -83,7 +83,6 @@ __global__ void decode_init_kernel(InitParams p) {
         if (r % p.k == 0) {
             p.top_done[u] = 0;
             p.att_ticket[u] = 0;
-            p.row_ticket[u] = 0;
             p.g_accum[u] = 0.f;
             p.g_finished[u] = 0;
             p.g_len[u] = 0;
@@ -101,7 +100,7 @@ int decode_init(asr_handle* h, int k, int max_len, bool greedy, cudaStream_t st)
     Workspace& w = h->ws;
     const int B = h->meta.B, R = B * k;
     InitParams p{w.h0, w.c0, w.dh[0], w.dc[0], w.dctx[0], w.src_row, w.beam_score, w.tok_hist,
-                 w.prev_hist, w.top_done, w.ctrl, w.att_ticket, w.row_ticket, w.g_accum, w.g_finished, w.g_len,
+                 w.prev_hist, w.top_done, w.ctrl, w.att_ticket, w.g_accum, w.g_finished, w.g_len,
                  B, k, R};
     ASR_CUDA(cudaMemsetAsync(w.tok_hist, 0, sizeof(int) * (size_t)(max_len + 1) * R, st));
     decode_init_kernel<<<R, 128, 0, st>>>(p);
@@ -754,11 +753,7 @@ template <int K>
 static int launch_attention_stream(const AttnParams& p, int B, cudaStream_t st) {
     const size_t smem = sizeof(float) * ((size_t)kAttStages * kAttRows * kEnc + 2 * K * kAttChunk + K * kAtt + 2 * K + 8 * K + 4 * K) +
                         sizeof(uint64_t) * 2 * kAttStages + 16;
-    static bool attr = false;
-    if (!attr) {
-        ASR_CUDA(cudaFuncSetAttribute(attention_stream_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
-    }
+    ASR_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&attention_stream_kernel<K>), smem));
     attention_stream_kernel<K><<<B, 256, smem, st>>>(p);
     return ASR_OK;
 }
@@ -769,13 +764,8 @@ int launch_attention(asr_handle* h, int k, int step, int nxt, float* d_align_ste
     const BatchMeta& m = h->meta;
     AttnParams p{};
     p.q = w.att_q;
-    static const int att_dbg = getenv("ASR_B200_ATT_DBG") ? atoi(getenv("ASR_B200_ATT_DBG")) : 0;
-    p.dbg = att_dbg;
-    static long long* d_trace = nullptr;
-    static int trace_calls = 0;
-    static const bool want_trace = getenv("ASR_B200_ATT_TRACE") != nullptr;
-    if (want_trace && !d_trace) { ASR_CUDA(cudaMalloc(&d_trace, 256 * sizeof(long long))); ASR_CUDA(cudaMemset(d_trace, 0, 256 * sizeof(long long))); }
-    p.trace = d_trace;
+    p.dbg = 0;
+    p.trace = nullptr;
     p.keys = w.keys;
     p.keys_exp = w.keys_exp;
     p.keys_big = w.keys_big;
@@ -783,7 +773,7 @@ int launch_attention(asr_handle* h, int k, int step, int nxt, float* d_align_ste
     p.v = h->w.att_v;
     p.uoff = m.d_uoff_sorted;
     p.ctx_out = w.dctx[nxt];
-    p.split_hi = h->fused_dec ? w.dec_split_hi : nullptr;
+    p.split_hi = w.dec_split_hi;
     p.split_lo = w.dec_split_lo;
     p.split_ld = kProjK;
     p.part = w.att_part;
@@ -796,8 +786,6 @@ int launch_attention(asr_handle* h, int k, int step, int nxt, float* d_align_ste
     int S = (2 * kNumSMs + m.B - 1) / m.B;
     if (S > 8) S = 8;
     if (S < 1) S = 1;
-    static const int env_split = getenv("ASR_B200_ATT_SPLIT") ? atoi(getenv("ASR_B200_ATT_SPLIT")) : 0;
-    if (env_split > 0) S = env_split;
     while (S > 1 && (m.Lmax + S - 1) / S < 16) --S;
     p.S = S;
     p.sc_ld = ((m.Lmax + S - 1) / S + 3) & ~3;
@@ -805,8 +793,7 @@ int launch_attention(asr_handle* h, int k, int step, int nxt, float* d_align_ste
     p.align_out = d_align_step;
     p.raw_score = (d_align_step && S > 1) ? w.att_score : nullptr;
     const int K = k == 1 ? 1 : (k <= 4 ? 4 : (k <= 8 ? 8 : 16));
-    static const bool stream_env = !(getenv("ASR_B200_ATT_STREAM") && atoi(getenv("ASR_B200_ATT_STREAM")) == 0);
-    if (stream_env && S == 1 && !d_align_step) {
+    if (S == 1 && !d_align_step) {
         switch (K) {
             case 1: ASR_TRY(launch_attention_stream<1>(p, m.B, st)); break;
             case 4: ASR_TRY(launch_attention_stream<4>(p, m.B, st)); break;
@@ -815,30 +802,13 @@ int launch_attention(asr_handle* h, int k, int step, int nxt, float* d_align_ste
         }
         ASR_CHECK_LAUNCH();
         h->launches++;
-        if (d_trace && ++trace_calls == 50) {
-            long long t[256];
-            cudaStreamSynchronize(st);
-            cudaMemcpy(t, d_trace, sizeof(t), cudaMemcpyDeviceToHost);
-            fprintf(stderr, "[att trace] prologue %lld, loop end %lld, kernel end %lld cycles\n", t[1] - t[0], t[2] - t[0], t[3] - t[0]);
-            for (int c = 0; c < 12; ++c) {
-                const long long* a = t + 8 + c * 8;
-                if (!a[0]) break;
-                fprintf(stderr, "  chunk %2d prod: start %6lld drained %6lld scores %6lld maxbar %6lld published %6lld | cons: wait-from %6lld ready %6lld done %6lld\n",
-                        c, a[0] - t[0], a[1] - t[0], a[2] - t[0], a[3] - t[0], a[4] - t[0], a[5] - t[0], a[6] - t[0], a[7] - t[0]);
-            }
-        }
         return ASR_OK;
     }
     const size_t smem = sizeof(float) * ((size_t)K * kAtt + (size_t)K * p.sc_ld + (size_t)K * kEnc);
     dim3 grid(m.B, S);
 #define ASR_LAUNCH_ATT(KK)                                                                      \
     do {                                                                                        \
-        static size_t cur_max = 48 * 1024;                                                      \
-        if (smem > cur_max) {                                                                   \
-            ASR_CUDA(cudaFuncSetAttribute(attention_kernel<KK>,                                 \
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            cur_max = smem;                                                                     \
-        }                                                                                       \
+        ASR_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&attention_kernel<KK>), smem)); \
         attention_kernel<KK><<<grid, 256, smem, st>>>(p);                                       \
     } while (0)
     if (smem > 200 * 1024) { set_error("attention: utterance too long (%d frames)", m.Lmax); return ASR_ERR_CAPACITY; }
@@ -855,18 +825,15 @@ int launch_attention(asr_handle* h, int k, int step, int nxt, float* d_align_ste
 }
 
 // ---------------------------------------------------------------------------------------------
-// per-row logsumexp + exact top-K (K = 2k <= 32)
+// per-utterance merge of the vocabulary GEMM's tile partials + beam bookkeeping
 __device__ __forceinline__ unsigned ordered_key(float f) {
     const unsigned b = __float_as_uint(f);
     return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 
-constexpr int kRowElems = 20;   // 256 threads * 20 >= 5004
 constexpr int kCandCap = 1024;
 
-// per-utterance merge + beam bookkeeping state (shared by the row kernel's tail)
 struct BookParams {
-    const float* cand_s; const int* cand_t;     // [R, K]
     float* beam_score; int* src_row;            // [R]
     int* tok_hist; int* prev_hist;              // [max_len + 1, R]
     float* fin_score; int* fin_row;             // [max_len, B, k]
@@ -874,69 +841,25 @@ struct BookParams {
     int* tr_bp; int* tr_tok;                    // [max_len, B, k]
     int* top_done; int* ctrl;
     int B, k, K, step;
-    // optional: gather the next step's cell-GEMM operand [ctx[src] | h[src]] (already split, from the
-    // [h | ctx] rows the cell epilogue / attention kernel wrote) - replaces a gather + split launch
+    // gather of the next step's cell-GEMM operand [ctx[src] | h[src]] (already split, from the [h | ctx] rows the
+    // cell epilogue / attention kernel wrote) - replaces a gather + split launch
     const hi_t* split_hi; const float* split_lo;    // [R, 1024] = [h | ctx]: fp16 hi, 4-byte cross words
     hi_t* next_hi; float* next_lo;                  // [R, 1024] = [ctx | h]
 };
 
-struct RowTopkParams {
-    const float* logits;      // [R, V]
-    const float* beam_score;  // [R]
-    float* cand_s;            // [R, K]
-    int* cand_t;              // [R, K]
-    int* row_ticket;          // [B] rows of the utterance that have published their candidates
-    const int* ctrl;
-    int k, K, step, fuse_book;
+struct MergeParams {
+    const uint2* part;        // [kVocabTiles, R, KP] (logit bits, token id)
+    const float2* part_ms;    // [kVocabTiles, R] (tile max, sum of exp(logit - max))
+    int KP;
     BookParams book;
 };
 
-__device__ __forceinline__ float block_reduce_max(float v, float* s_red) {
-    v = warp_max(v);
-    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    float r = s_red[0];
-#pragma unroll
-    for (int i = 1; i < 8; ++i) r = fmaxf(r, s_red[i]);
-    __syncthreads();
-    return r;
-}
-__device__ __forceinline__ float block_reduce_sum(float v, float* s_red) {
-    v = warp_sum(v);
-    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    float r = s_red[0];
-#pragma unroll
-    for (int i = 1; i < 8; ++i) r += s_red[i];
-    __syncthreads();
-    return r;
-}
-
-// Merge of the k rows' top-K lists of utterance u and the beam bookkeeping of one step
-// (model.py:862-929).  Runs in the LAST row CTA of the utterance to publish its candidates.
-__device__ void beam_bookkeep(const BookParams& p, int u, float* s_s, int* s_f, float* s_cs, int* s_cf) {
+// Beam bookkeeping of one step for utterance u from its merged, sorted top-K candidates (model.py:876-929):
+// s_cs[j] = score, s_cf[j] = beam * V + token of rank j.
+__device__ void beam_bookkeep(const BookParams& p, int u, const float* s_cs, const int* s_cf) {
     __shared__ int s_src[kMaxBeam];
     const int tid = threadIdx.x;
     const int k = p.k, K = p.K, R = p.B * k;
-    const int nrow = p.step == 0 ? 1 : k;
-    const int n = nrow * K;                                   // <= 16 * 32 = 512
-    for (int i = tid; i < n; i += 256) {
-        const int b = i / K, j = i - b * K;
-        s_s[i] = __ldcg(p.cand_s + (size_t)(u * k + b) * K + j);
-        s_f[i] = b * kVocab + __ldcg(p.cand_t + (size_t)(u * k + b) * K + j);
-    }
-    __syncthreads();
-    for (int i = tid; i < n; i += 256) {
-        const float si = s_s[i];
-        const int fi = s_f[i];
-        int rank = 0;
-        for (int j = 0; j < n; ++j) {
-            const float sj = s_s[j];
-            rank += (sj > si || (sj == si && s_f[j] < fi)) ? 1 : 0;
-        }
-        if (rank < K) { s_cs[rank] = si; s_cf[rank] = fi; }
-    }
-    __syncthreads();
     if (tid < K) {
         const size_t o = ((size_t)p.step * p.B + u) * K + tid;
         p.tr_cand_s[o] = s_cs[tid];
@@ -986,7 +909,7 @@ __device__ void beam_bookkeep(const BookParams& p, int u, float* s_s, int* s_f, 
             }
         }
     }
-    if (p.next_hi) {
+    if (p.next_hi && k > 1) {
         __syncthreads();
         // k rows x 1024 values x (2-byte hi, 4-byte cross): 16-byte copies, halves swapped ([h | ctx] -> [ctx | h])
         static_assert(kProjK / 4 == 256, "one 16-byte cross column per thread");
@@ -1021,180 +944,139 @@ __device__ void beam_bookkeep(const BookParams& p, int u, float* s_s, int* s_f, 
     }
 }
 
+// One CTA per utterance.  The vocabulary GEMM's epilogue left, per 224-column tile and row, the tile's
+// (max, sum exp) and its KP >= 2k largest logits with token ids; the top 2k of the utterance's k * V scores
+// (model.py:860-867) are among those k * 23 * KP candidates: a logit outside its tile's top KP >= 2k has 2k
+// larger-or-equal ones in its own row, and x -> (x - lse) + beam score is monotone.  Order: score descending,
+// then beam * V + token ascending (torch.topk's tie order is unspecified; the oracle defines the same).
 __global__ void __launch_bounds__(256)
-beam_bookkeep_kernel(BookParams p) {
-    if (p.ctrl[0] >= 0) return;
-    __shared__ float s_s[512];
-    __shared__ int s_f[512];
-    __shared__ float s_cs[32];
-    __shared__ int s_cf[32];
-    beam_bookkeep(p, blockIdx.x, s_s, s_f, s_cs, s_cf);
-}
-
-// One CTA per decoder row: log-softmax statistics, score = logit - lse + beam score (model.py:835-836),
-// exact top-K (K = 2k <= 32, ties by token id), then - in the last row CTA of each utterance - the
-// per-utterance merge and bookkeeping, so a decoder step needs no separate bookkeeping launch.
-__global__ void __launch_bounds__(256, 4)
-row_topk_kernel(RowTopkParams p) {
-    if (p.ctrl[0] >= 0) return;
-    const int r = blockIdx.x;
-    const int u = r / p.k;
-    __shared__ float s_red[8];
-    __shared__ int s_wcnt[8];
-    __shared__ int s_cnt, s_last;
+beam_merge_kernel(MergeParams p) {
+    const BookParams& b = p.book;
+    if (b.ctrl[0] >= 0) return;
+    extern __shared__ __align__(16) uint8_t merge_smem[];
+    __shared__ float s_lse[kMaxBeam], s_bs[kMaxBeam];
     __shared__ float s_gmax[64];
     __shared__ float s_thr;
+    __shared__ int s_cnt;
+    __shared__ int s_wcnt[8];
     __shared__ float s_cs[kCandCap];
-    __shared__ int s_ct[kCandCap];
+    __shared__ int s_cf[kCandCap];
     __shared__ float s_top_s[32];
     __shared__ int s_top_f[32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nrow = p.step == 0 ? 1 : p.k;                // step 0: only the first beam (model.py:862)
-    const bool active = p.step != 0 || (r % p.k) == 0;
+    const int u = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int k = b.k, K = b.K, R = b.B * k, KP = p.KP;
+    const int nrow = b.step == 0 ? 1 : k;                  // step 0: only the first beam (model.py:862)
+    const int total = nrow * kVocabTiles * KP;
+    float* s_lp = reinterpret_cast<float*>(merge_smem);    // [total] log-prob + beam score
+    int* s_fl = reinterpret_cast<int*>(s_lp + total);      // [total] beam * V + token
 
-    if (active) {
-        // row base is 16-byte aligned (5004 * 4 = 1251 * 16): 5 float4 per thread cover the row
-        const float4* row4 = reinterpret_cast<const float4*>(p.logits + (size_t)r * kVocab);
-        float v[kRowElems];
-        float m = -CUDART_INF_F;
+    // log-sum-exp of every row from its tile partials (model.py:835)
+    for (int r = warp; r < nrow; r += 8) {
+        const int row = u * k + r;
+        const float2 ms = lane < kVocabTiles ? __ldcg(p.part_ms + (size_t)lane * R + row) : make_float2(-CUDART_INF_F, 0.f);
+        const float mx = warp_max(ms.x);
+        const float sum = warp_sum(lane < kVocabTiles ? ms.y * __expf(ms.x - mx) : 0.f);
+        if (lane == 0) { s_lse[r] = mx + logf(sum); s_bs[r] = b.beam_score[row]; }
+    }
+    if (tid == 0) s_cnt = 0;
+    __syncthreads();
+    // candidates: i = (tile * nrow + r) * KP + j, so a warp reads consecutive slots of consecutive rows
+    float tmf = -CUDART_INF_F;
+    for (int i = tid; i < total; i += 256) {
+        const int j = i % KP, q = i / KP;
+        const int r = q % nrow, tile = q / nrow;
+        const uint2 c = __ldcg(p.part + ((size_t)tile * R + u * k + r) * KP + j);
+        const float lp = __fadd_rn(__fsub_rn(__uint_as_float(c.x), s_lse[r]), s_bs[r]);      // model.py:835-836
+        s_lp[i] = lp;
+        s_fl[i] = r * kVocab + (int)c.y;
+        tmf = fmaxf(tmf, lp);
+    }
+    // Threshold: the maxima of 64 groups of 4 threads are 64 distinct candidates (at least 23 K / 4 >= K groups
+    // are non-empty), so their K-th largest T has at least K candidates >= T and usually few more.
+    float gm = fmaxf(tmf, __shfl_xor_sync(0xffffffffu, tmf, 1));
+    gm = fmaxf(gm, __shfl_xor_sync(0xffffffffu, gm, 2));
+    if ((tid & 3) == 0) s_gmax[tid >> 2] = gm;
+    __syncthreads();
+    {
+        const int g = tid >> 2, part = tid & 3;
+        int above = 0;
 #pragma unroll
-        for (int i = 0; i < kRowElems / 4; ++i) {
-            const int e4 = tid + 256 * i;
-            float4 x = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
-            if (e4 < kVocab / 4) x = __ldg(row4 + e4);
-            v[4 * i] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
-            m = fmaxf(m, fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w)));
+        for (int i = 0; i < 16; ++i) {
+            const int o = part * 16 + i;
+            const float x = s_gmax[o];
+            above += (x > gm || (x == gm && o < g)) ? 1 : 0;
         }
-        m = block_reduce_max(m, s_red);
-        float s = 0.f;
-#pragma unroll
-        for (int i = 0; i < kRowElems; ++i) s += __expf(v[i] - m);    // exp(-inf) = 0 for padding
-        s = block_reduce_sum(s, s_red);
-        const float lse = m + logf(s);
-        const float bs = p.beam_score[r];
-        float tmf = -CUDART_INF_F;
-#pragma unroll
-        for (int i = 0; i < kRowElems; ++i) {
-            v[i] = __fadd_rn(__fsub_rn(v[i], lse), bs);               // padding stays -inf
-            tmf = fmaxf(tmf, v[i]);
+        above += __shfl_xor_sync(0xffffffffu, above, 1);
+        above += __shfl_xor_sync(0xffffffffu, above, 2);
+        if (part == 0 && above == K - 1) s_thr = gm;
+    }
+    __syncthreads();
+    unsigned kth = ordered_key(s_thr);
+    auto collect = [&]() {
+        for (int i = tid; i < total; i += 256) {
+            const float v = s_lp[i];
+            if (ordered_key(v) >= kth) {
+                const int slot = atomicAdd(&s_cnt, 1);
+                if (slot < kCandCap) { s_cs[slot] = v; s_cf[slot] = s_fl[i]; }
+            }
         }
-        // Threshold: the maxima of 64 groups of 4 threads are 64 distinct row elements, so their K-th
-        // largest T (K <= 32) has at least K elements >= T - and for a non-degenerate row only a few
-        // more (expected 64 (H_64 - H_(64-K)): 18 for K = 16, 44 for K = 32).  Ranks by counting over
-        // the 64 maxima, 2 barriers.  (Measured alternatives: 32-step bisection with
-        // __syncthreads_count over the 256 thread maxima - 32 barriers; min over K group maxima - one
-        // barrier but ~3x the candidates.)
-        float gm = fmaxf(tmf, __shfl_xor_sync(0xffffffffu, tmf, 1));
-        gm = fmaxf(gm, __shfl_xor_sync(0xffffffffu, gm, 2));
-        if ((tid & 3) == 0) s_gmax[tid >> 2] = gm;
+    };
+    collect();
+    __syncthreads();
+    if (s_cnt > kCandCap) {
+        // Degenerate scores (more than kCandCap candidates above the threshold): exact K-th largest by
+        // bisection over all candidates, then collect again (ties beyond the cap are truncated).
+        kth = 0u;
+#pragma unroll 1
+        for (int bit = 31; bit >= 0; --bit) {
+            const unsigned cand = kth | (1u << bit);
+            int c = 0;
+            for (int i = tid; i < total; i += 256) c += ordered_key(s_lp[i]) >= cand ? 1 : 0;
+            c = __reduce_add_sync(0xffffffffu, c);
+            __syncthreads();
+            if (lane == 0) s_wcnt[warp] = c;
+            __syncthreads();
+            int tot = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) tot += s_wcnt[w];
+            if (tot >= K) kth = cand;
+        }
+        __syncthreads();
         if (tid == 0) s_cnt = 0;
         __syncthreads();
-        {
-            const int g = tid >> 2, part = tid & 3;
-            int above = 0;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int o = part * 16 + i;
-                const float x = s_gmax[o];
-                above += (x > gm || (x == gm && o < g)) ? 1 : 0;
-            }
-            above += __shfl_xor_sync(0xffffffffu, above, 1);
-            above += __shfl_xor_sync(0xffffffffu, above, 2);
-            if (part == 0 && above == p.K - 1) s_thr = gm;
-        }
-        __syncthreads();
-        unsigned kth = ordered_key(s_thr);
-        auto collect = [&]() {
-#pragma unroll
-            for (int i = 0; i < kRowElems; ++i) {
-                if (ordered_key(v[i]) >= kth && v[i] != -CUDART_INF_F) {
-                    const int slot = atomicAdd(&s_cnt, 1);
-                    if (slot < kCandCap) { s_cs[slot] = v[i]; s_ct[slot] = 4 * (tid + 256 * (i >> 2)) + (i & 3); }
-                }
-            }
-        };
         collect();
         __syncthreads();
-        if (s_cnt > kCandCap) {
-            // Degenerate row (more than kCandCap values above the threshold): exact K-th largest by
-            // bisection over all elements, then collect again (ties beyond the cap are truncated).
-            kth = 0u;
-#pragma unroll 1
-            for (int bit = 31; bit >= 0; --bit) {
-                const unsigned cand = kth | (1u << bit);
-                int c = 0;
-#pragma unroll
-                for (int i = 0; i < kRowElems; ++i) c += (ordered_key(v[i]) >= cand && v[i] != -CUDART_INF_F) ? 1 : 0;
-                c = __reduce_add_sync(0xffffffffu, c);
-                __syncthreads();
-                if (lane == 0) s_wcnt[warp] = c;
-                __syncthreads();
-                int tot = 0;
-#pragma unroll
-                for (int w = 0; w < 8; ++w) tot += s_wcnt[w];
-                if (tot >= p.K) kth = cand;
-            }
-            __syncthreads();
-            if (tid == 0) s_cnt = 0;
-            __syncthreads();
-            collect();
-            __syncthreads();
-        }
-        const int n = min(s_cnt, kCandCap);
-        // rank by counting: order (score desc, token asc)
-        for (int i = tid; i < n; i += 256) {
-            const float si = s_cs[i];
-            const int ti = s_ct[i];
-            int rank = 0;
-            for (int j = 0; j < n; ++j) {
-                const float sj = s_cs[j];
-                rank += (sj > si || (sj == si && s_ct[j] < ti)) ? 1 : 0;
-            }
-            if (rank < p.K) {
-                p.cand_s[(size_t)r * p.K + rank] = si;
-                p.cand_t[(size_t)r * p.K + rank] = ti;
-            }
-        }
-        if (!p.fuse_book) return;
-        // publish; the last of the utterance's `nrow` rows merges and does the bookkeeping
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) {
-            const int t = atomicAdd(p.row_ticket + u, 1);
-            s_last = (t == nrow - 1);
-            if (s_last) p.row_ticket[u] = 0;
-        }
-        __syncthreads();
-        if (!s_last) return;
-        __threadfence();
-        beam_bookkeep(p.book, u, s_cs, s_ct, s_top_s, s_top_f);
     }
+    const int n = min(s_cnt, kCandCap);
+    // rank by counting: order (score desc, beam * V + token asc)
+    for (int i = tid; i < n; i += 256) {
+        const float si = s_cs[i];
+        const int fi = s_cf[i];
+        int rank = 0;
+        for (int j = 0; j < n; ++j) {
+            const float sj = s_cs[j];
+            rank += (sj > si || (sj == si && s_cf[j] < fi)) ? 1 : 0;
+        }
+        if (rank < K) { s_top_s[rank] = si; s_top_f[rank] = fi; }
+    }
+    __syncthreads();
+    beam_bookkeep(b, u, s_top_s, s_top_f);
 }
 
-int launch_row_topk(asr_handle* h, int k, int step, cudaStream_t st) {
+int launch_beam_merge(asr_handle* h, int k, int step, cudaStream_t st) {
     Workspace& w = h->ws;
-    // the utterance's last row CTA overwrites beam_score for the next step only after every row of that
-    // utterance has read its own entry (they all published before the ticket completes)
-    float* bs_cur = w.beam_score;
-    float* bs_nxt = w.beam_score;
-    BookParams b{w.rowcand_s, w.rowcand_t, bs_nxt, w.src_row, w.tok_hist, w.prev_hist,
-                 w.fin_score, w.fin_row, w.tr_cand_s, w.tr_cand_b, w.tr_cand_t, w.tr_bp, w.tr_tok,
-                 w.top_done, w.ctrl, h->meta.B, k, 2 * k, step,
-                 h->fused_dec ? w.dec_split_hi : nullptr, w.dec_split_lo, h->fused_dec ? w.a_hi : nullptr, w.a_lo};
-    static const int fuse = getenv("ASR_B200_FUSE_BOOK") ? atoi(getenv("ASR_B200_FUSE_BOOK")) : 0;
-    RowTopkParams p{w.logits, bs_cur, w.rowcand_s, w.rowcand_t, w.row_ticket, w.ctrl, k, 2 * k, step, fuse, b};
-    row_topk_kernel<<<h->meta.B * k, 256, 0, st>>>(p);
+    const int KP = vocab_topk_slots(k);
+    MergeParams p{w.topk_part, w.topk_ms, KP,
+                  BookParams{w.beam_score, w.src_row, w.tok_hist, w.prev_hist, w.fin_score, w.fin_row, w.tr_cand_s,
+                             w.tr_cand_b, w.tr_cand_t, w.tr_bp, w.tr_tok, w.top_done, w.ctrl, h->meta.B, k, 2 * k, step,
+                             w.dec_split_hi, w.dec_split_lo, w.a_hi, w.a_lo}};
+    const size_t smem = (size_t)k * kVocabTiles * KP * 8;          // k = 16: 94 KB
+    ASR_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&beam_merge_kernel), smem));
+    beam_merge_kernel<<<h->meta.B, 256, smem, st>>>(p);
     ASR_CHECK_LAUNCH();
     h->launches++;
-    if (!fuse) {
-        beam_bookkeep_kernel<<<h->meta.B, 256, 0, st>>>(b);
-        ASR_CHECK_LAUNCH();
-        h->launches++;
-    }
     return ASR_OK;
 }
-
-int launch_beam_bookkeep(asr_handle*, int, int, int, cudaStream_t) { return ASR_OK; }   // part of launch_row_topk
 
 // ---------------------------------------------------------------------------------------------
 // n-gram LM on device (tables from asr_set_lm; semantics of oracle NGramLM / kenlm .score)
@@ -1396,51 +1278,89 @@ int launch_beam_finalise(asr_handle* h, int k, int max_len, int second_pass, dou
 
 // ---------------------------------------------------------------------------------------------
 // greedy
+constexpr int kRowElems = 20;   // 256 threads * 20 >= 5004
+
 struct GreedyParams {
-    const float* logits;   // [B, V]
-    int* tok_hist;         // [max_len + 1, B]
-    int* g_tokens;         // [max_len, B]
+    const float* logits;      // [B, V] (export path) or nullptr
+    const uint2* part;        // [kVocabTiles, B, 2] tile partials of the vocabulary GEMM (KP = 2)
+    const float2* part_ms;    // [kVocabTiles, B]
+    int* tok_hist;            // [max_len + 1, B]
+    int* g_tokens;            // [max_len, B]
     float* g_accum; int* g_finished; int* g_len;
     int* ctrl;
     int B, step;
 };
 
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ float block_reduce_sum(float v, float* s_red) {
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = s_red[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) r += s_red[i];
+    __syncthreads();
+    return r;
+}
+
+// argmax (first maximum = lowest token id), log-sum-exp and the score / length bookkeeping of one greedy step
+// (model.py:554-578).  FROM_LOGITS: over the materialised row (the driver's logits export); otherwise over the
+// vocabulary GEMM's tile partials - slot 0 of a tile is its maximum with the lowest token id.
+template <bool FROM_LOGITS>
+__global__ void __launch_bounds__(FROM_LOGITS ? 256 : 32)
 greedy_pick_kernel(GreedyParams p) {
     if (p.ctrl[0] >= 0) return;
-    __shared__ float s_red[8];
-    __shared__ float s_v[8];
-    __shared__ int s_i[8];
-    const int u = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const float* row = p.logits + (size_t)u * kVocab;
-    float v[kRowElems];
-    float m = -CUDART_INF_F;
+    const int u = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    float m = -CUDART_INF_F, lse;
     int mi = 0x7fffffff;
+    if (FROM_LOGITS) {
+        __shared__ float s_red[8];
+        __shared__ float s_v[8];
+        __shared__ int s_i[8];
+        const int warp = tid >> 5;
+        const float* row = p.logits + (size_t)u * kVocab;
+        float v[kRowElems];
 #pragma unroll
-    for (int i = 0; i < kRowElems; ++i) {
-        const int e = tid + 256 * i;
-        v[i] = e < kVocab ? row[e] : -CUDART_INF_F;
-        if (v[i] > m) { m = v[i]; mi = e; }          // ascending e per thread: first max kept
+        for (int i = 0; i < kRowElems; ++i) {
+            const int e = tid + 256 * i;
+            v[i] = e < kVocab ? row[e] : -CUDART_INF_F;
+            if (v[i] > m) { m = v[i]; mi = e; }          // ascending e per thread: first max kept
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float m2 = __shfl_xor_sync(0xffffffffu, m, o);
+            const int i2 = __shfl_xor_sync(0xffffffffu, mi, o);
+            if (m2 > m || (m2 == m && i2 < mi)) { m = m2; mi = i2; }
+        }
+        if (lane == 0) { s_v[warp] = m; s_i[warp] = mi; }
+        __syncthreads();
+        m = s_v[0]; mi = s_i[0];
+#pragma unroll
+        for (int i = 1; i < 8; ++i)
+            if (s_v[i] > m || (s_v[i] == m && s_i[i] < mi)) { m = s_v[i]; mi = s_i[i]; }
+        __syncthreads();
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < kRowElems; ++i) s += expf(v[i] - m);
+        s = block_reduce_sum(s, s_red);
+        lse = m + logf(s);
+    } else {
+        float2 ms = make_float2(-CUDART_INF_F, 0.f);
+        if (lane < kVocabTiles) {
+            ms = __ldcg(p.part_ms + (size_t)lane * p.B + u);
+            const uint2 c = __ldcg(p.part + ((size_t)lane * p.B + u) * 2);
+            m = __uint_as_float(c.x);
+            mi = (int)c.y;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float m2 = __shfl_xor_sync(0xffffffffu, m, o);
+            const int i2 = __shfl_xor_sync(0xffffffffu, mi, o);
+            if (m2 > m || (m2 == m && i2 < mi)) { m = m2; mi = i2; }
+        }
+        const float s = warp_sum(lane < kVocabTiles ? ms.y * __expf(ms.x - m) : 0.f);
+        lse = m + logf(s);
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const float m2 = __shfl_xor_sync(0xffffffffu, m, o);
-        const int i2 = __shfl_xor_sync(0xffffffffu, mi, o);
-        if (m2 > m || (m2 == m && i2 < mi)) { m = m2; mi = i2; }
-    }
-    if (lane == 0) { s_v[warp] = m; s_i[warp] = mi; }
-    __syncthreads();
-    m = s_v[0]; mi = s_i[0];
-#pragma unroll
-    for (int i = 1; i < 8; ++i)
-        if (s_v[i] > m || (s_v[i] == m && s_i[i] < mi)) { m = s_v[i]; mi = s_i[i]; }
-    __syncthreads();
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < kRowElems; ++i) s += expf(v[i] - m);
-    s = block_reduce_sum(s, s_red);
     if (tid != 0) return;
-    const float lse = m + logf(s);
     const float logp = __fsub_rn(m, lse);            // model.py:554,563
     const int tok = mi;
     p.g_tokens[(size_t)p.step * p.B + u] = tok;
@@ -1465,12 +1385,12 @@ greedy_pick_kernel(GreedyParams p) {
     }
 }
 
-int launch_greedy_pick(asr_handle* h, int step, int max_len, cudaStream_t st) {
-    (void)max_len;
+int launch_greedy_pick(asr_handle* h, int step, bool from_logits, cudaStream_t st) {
     Workspace& w = h->ws;
-    GreedyParams p{w.logits, w.tok_hist, w.g_tokens, w.g_accum, w.g_finished, w.g_len, w.ctrl,
-                   h->meta.B, step};
-    greedy_pick_kernel<<<h->meta.B, 256, 0, st>>>(p);
+    GreedyParams p{from_logits ? w.logits : nullptr, w.topk_part, w.topk_ms, w.tok_hist, w.g_tokens, w.g_accum,
+                   w.g_finished, w.g_len, w.ctrl, h->meta.B, step};
+    if (from_logits) greedy_pick_kernel<true><<<h->meta.B, 256, 0, st>>>(p);
+    else greedy_pick_kernel<false><<<h->meta.B, 32, 0, st>>>(p);
     ASR_CHECK_LAUNCH();
     h->launches++;
     return ASR_OK;

@@ -451,36 +451,16 @@ lstm_rec_tc3_kernel(Params p) {
     }
 }
 
-// W_lo (fp32 residual) -> bf16 pairs (k even in the low half-word)
-__global__ void pack_bf16_pairs_kernel(const float* __restrict__ src, uint32_t* __restrict__ dst, long long n2) {
-    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i >= n2) return;
-    const __nv_bfloat16 a = __float2bfloat16_rn(src[2 * i]);
-    const __nv_bfloat16 b = __float2bfloat16_rn(src[2 * i + 1]);
-    dst[i] = (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
-}
-
 template <int NB>
 static int launch(const Params& p, cudaStream_t st) {
     const size_t smem = 8 * (size_t)(NB * 192) + 1024 + 64 + NB * 4;
-    static bool attr = false;
-    if (!attr) {
-        ASR_CUDA(cudaFuncSetAttribute(lstm_rec_tc3_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
-    }
+    ASR_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&lstm_rec_tc3_kernel<NB>), smem));
     lstm_rec_tc3_kernel<NB><<<2 * p.nchunks * 8, kThreads, smem, st>>>(p);
     ASR_CHECK_LAUNCH();
     return ASR_OK;
 }
 
 }  // namespace rec3
-
-int pack_bf16_pairs(const float* src, uint32_t* dst, long long n_pairs) {
-    rec3::pack_bf16_pairs_kernel<<<(unsigned)((n_pairs + 255) / 256), 256>>>(src, dst, n_pairs);
-    ASR_CHECK_LAUNCH();
-    ASR_CUDA(cudaDeviceSynchronize());
-    return ASR_OK;
-}
 
 size_t rec3_stage_bytes_per_cta() { return rec3::kStageBytes; }
 
@@ -489,8 +469,7 @@ int launch_lstm_recurrence_tc3(asr_handle* h, int layer, const float* xg, const 
                                float* split_lo) {
     const BatchMeta& m = h->meta;
     rec3::Params p{};
-    static const int xchg = getenv("ASR_B200_REC_XCHG") ? atoi(getenv("ASR_B200_REC_XCHG")) : 0;   // measured: 7 DSMEM bulk copies per CTA per step (10.9 -> 17.9 ms per batch) lose to one multicast from L2
-    p.xchg_dsmem = xchg;
+    p.xchg_dsmem = 0;      // measured: 7 DSMEM bulk copies per CTA per step (10.9 -> 17.9 ms per batch) lose to one multicast from L2
     p.y_hi = split_hi;
     p.y_cross = reinterpret_cast<uint32_t*>(split_lo);
     p.xg = xg;
@@ -518,7 +497,7 @@ int launch_lstm_recurrence_tc3(asr_handle* h, int layer, const float* xg, const 
         set_error("recurrence staging too small");
         return ASR_ERR_CAPACITY;
     }
-    static const bool want_dbg = getenv("ASR_B200_REC_DBG") != nullptr;
+    const bool want_dbg = h->rec_timeline;      // asr_stage_timing(h, 2): clock64 timeline of cluster 0 to stderr
     long long* dbg = nullptr;
     if (want_dbg) { ASR_CUDA(cudaMalloc(&dbg, sizeof(long long) * 8 * 4096)); ASR_CUDA(cudaMemset(dbg, 0, sizeof(long long) * 8 * 4096)); }
     p.dbg = dbg;

@@ -7,32 +7,43 @@
 //                                 the full-rate kind::f16 MMA; saturating, see hi_part())
 //     x_lo = x - x_hi            (the residual, exact in fp32, |x_lo| <= 2^-11 |x|)
 // and the product is accumulated in fp32 in TMEM as
-//     a_hi*w_hi                  one tcgen05.mma.kind::f16 on fp16 operands per 16 values of k
-//   + (a_lo*w + a*w_lo)          one tcgen05.mma.kind::f16 on bf16 operands (K = 16) per 8 values of k: the
-//                                "cross" operand holds, per 8 values of k, [8 x bf16(a_lo) | 8 x bf16(a)] on
-//                                the A side and [8 x bf16(w) | 8 x bf16(w_lo)] on the W side.
-// The cross terms are 2^-11 of the product, so bf16's 2^-9 relative accuracy leaves ~2^-20; measured
-// 2-5e-6 relative error against fp64, the same as three tf32 MMAs (the tensor core's truncating
-// accumulation dominates).  Three MMA issue slots per 16 values of k (the tf32 hi form needed four: a
-// kind::tf32 MMA covers only 8 values of k in the time a 16-bit MMA covers 16).
+//     (a_lo*w + a*w_lo)          "cross" pass: one tcgen05.mma.kind::f16 on bf16 operands (K = 16) per 8
+//                                values of k; the cross operand holds, per 8 values of k,
+//                                [8 x bf16(a_lo) | 8 x bf16(a)] on the A side and [8 x bf16(w) | 8 x bf16(w_lo)]
+//                                on the W side
+//   + a_hi*w_hi                  "hi" pass: one tcgen05.mma.kind::f16 on fp16 operands per 16 values of k.
+// The cross terms are 2^-11 of the product, so bf16's 2^-9 relative accuracy leaves ~2^-20.
 //
-// Kernel anatomy (persistent, one CTA per SM, cta_group::1, optionally a cluster of 2 CTAs):
-//   warp 0   : TMA producer - cp.async.bulk.tensor.2d of the A_cross / W_cross (128-byte rows, SWIZZLE_128B)
-//              and A_hi / W_hi (64-byte rows, SWIZZLE_64B) K-slabs of 32 values of k into a 4-stage ring,
-//              completion on `full` mbarriers (expect_tx); out-of-bounds rows / K are zero-filled by
-//              TMA, so M, N and K tails need no special code.  In a CTA pair each CTA fetches half of
-//              the W tile and multicasts it into both CTAs.
-//   warp 1   : allocates TMEM (2 accumulators of BN fp32 columns), issues the MMAs (M=128, N=BN) from
-//              one elected lane, tcgen05.commit releases the stage (`empty` mbarrier, of both CTAs of
-//              a pair) and signals `tfull[acc]`.
+// Order of accumulation.  The tensor core adds every MMA into the fp32 accumulator with TRUNCATION, so each
+// MMA costs up to one ulp of the accumulator's magnitude, biased towards zero.  The first engine
+// interleaved cross and hi MMAs per K slab: 3*K/16 truncations at full magnitude (192 for K = 1024, measured
+// 2-5e-6 of max |C| against fp64).  Here a tile runs ALL of its cross MMAs first, while the accumulator only
+// holds the 2^-11-sized cross sum (their truncations are 2^-11 smaller too), then the K/16 hi MMAs: a third of
+// the full-magnitude truncations for the same operand bytes and MMA count.  Both operand kinds are 128-byte
+// K-major rows with SWIZZLE_128B (cross: 32 values of k per row, hi: 64), so a stage of the ring is the same
+// [A 16 KB | W half-tile] in both passes.
+//
+// Kernel anatomy (persistent; CTA PAIRS with tcgen05.mma.cta_group::2: one MMA of M = 256 spans both SMs'
+// tensor cores, each CTA holds its 128 rows of A and HALF of the W tile, a third less operand traffic per SM
+// than one CTA per tile):
+//   warp 0   : TMA producer - cp.async.bulk.tensor.2d of the A / W K-slabs into a 6..8-stage ring; both CTAs'
+//              bytes complete on the LEADER's `full` mbarrier (expect_tx); out-of-bounds rows / K are
+//              zero-filled by TMA, so M, N and K tails need no special code.
+//   warp 1   : allocates TMEM (2 accumulators of BN fp32 columns); in the leader CTA one elected lane issues
+//              the MMAs, tcgen05.commit (multicast) releases the stage in both CTAs and signals `tfull[acc]`.
 //   warps 2-5: epilogue of tile i while the main loop of tile i+1 runs - tcgen05.ld 32x32b.x32 of the
-//              accumulator rows, smem transpose, coalesced stores with fused bias / temperature, or
-//              the fused LSTM cell (gates, E'[token] lookup, h/c and the split of h for the next GEMM).
-// SASS evidence: UTCHMMA-class (UTC*MMA), UTMALDG, LDTM, UTCBAR in `cuobjdump -sass`.
+//              accumulator rows, then one of
+//                * bias (/ temperature) -> smem transpose -> coalesced stores,
+//                * the fused LSTM cell (gates, E'[token] lookup, h/c and the split of h for the next GEMM),
+//                * the vocabulary epilogue (KP > 0): per (row, tile) the log-sum-exp partial (max, sum) and
+//                  the top-KP logits with their token ids - the logits never reach HBM (decoder.py:133,
+//                  model.py:835-836, 863-867 up to the per-utterance merge in decoder.cu).
+// SASS evidence: UTCHMMA.2CTA, UTMALDG, LDTM, UTCBAR in `cuobjdump -sass` (profiles/r02_sass.txt).
 #include <cuda.h>
-#include <stdlib.h>
+#include <math_constants.h>
 
 #include <algorithm>
+#include <atomic>
 
 #include "asr_internal.cuh"
 
@@ -67,25 +78,48 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (!done && ++spins > kSpinLimit) __trap();      // turn a protocol bug into an error, not a hang
     }
 }
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int x, int y) {
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t local_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load into this CTA's shared memory, completion bytes on the mbarrier at cluster address `bar_cluster`
+// (the leader CTA's `full` barrier)
+__device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* map, uint32_t bar_cluster, void* dst, int x, int y) {
     asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y)
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster), "r"(x), "r"(y)
         : "memory");
 }
 // kind::f16 covers both operand formats of the engine: fp16 (hi) and bf16 (cross), chosen by the descriptor
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+__device__ __forceinline__ void umma2_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                           uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
+__device__ __forceinline__ void umma2_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(smem_u32(bar)), "h"(mask)
+        : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
     asm volatile(
@@ -100,21 +134,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (one 128-byte swizzle atom along K):
-// start address >> 4 | SBO (8 rows * 128 B = 1024 B) >> 4 at [32,46) | version 1 at [46,48) |
-// layout SWIZZLE_128B (2) at [61,64).  LBO is unused for swizzled K-major operands.
-template <int BKF>
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (128-byte rows, 8-row / 1024-byte atoms):
+// start address >> 4 | SBO 1024 >> 4 at [32,46) | version 1 at [46,48) | layout SWIZZLE_128B (2) at [61,64).
+// LBO is unused for swizzled K-major operands.
 __device__ __forceinline__ uint64_t make_kmajor_desc(const void* smem) {
-    // BKF = 32: 128-byte rows, SWIZZLE_128B (2), 1024-byte atoms; BKF = 16: 64-byte rows, SWIZZLE_64B (4),
-    // 512-byte atoms
     uint64_t d = 0;
     d |= (uint64_t)((smem_u32(smem) & 0x3FFFF) >> 4);
-    d |= (uint64_t)((BKF == 32 ? 1024 : 512) >> 4) << 32;
+    d |= (uint64_t)(1024 >> 4) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)(BKF == 32 ? 2 : 4) << 61;
+    d |= (uint64_t)2 << 61;
     return d;
 }
-
 // kind::f16 with bf16 operands: D=f32 (1<<4), A=B=BF16 (1<<7, 1<<10)
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -135,143 +165,65 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo_half, float hi_half) {
 // chunk).  ex2.approx / rcp.approx forms (2 ulp) are branch-free; the encoder recurrence uses the same.
 __device__ __forceinline__ float sigm(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float tanh_e(float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); }
-// ---------------------------------------------------------------------------------------------
-// Persistent variant: one CTA per SM loops over output tiles; the TMA producer and the MMA issuer run
-// ahead across tile boundaries and the accumulator is DOUBLE-BUFFERED in TMEM (2 x BN columns), so
-// the epilogue of tile i (TMEM -> smem transpose -> coalesced stores) overlaps the main loop of tile
-// i+1.  Measured on the one-tile-per-CTA kernel: main loop 27.4k cycles at 90 % tensor-pipe
-// efficiency, but 2.6k cycles of prologue and 7.7k cycles of epilogue per tile were exposed.
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 
-__device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* map, uint64_t* bar, void* dst, int x, int y,
-                                               uint16_t mask) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
-        "[%0], [%1, {%3, %4}], [%2], %5;"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "h"(mask)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
-    asm volatile(
-        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-        ::"r"(smem_u32(bar)), "h"(mask)
-        : "memory");
-}
-// ---- CTA-pair (cta_group::2) forms: one MMA over M = 256 spans both CTAs' tensor cores; each CTA holds its
-// 128 rows of A and HALF of the W tile, which the hardware shares between the two SMs.
-__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                           uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma2_commit_mc(uint64_t* bar, uint16_t mask) {
-    asm volatile(
-        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-        ::"r"(smem_u32(bar)), "h"(mask)
-        : "memory");
-}
-__device__ __forceinline__ uint32_t mapa_rank(uint32_t local_addr, uint32_t rank) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
-    return r;
-}
-// TMA load into this CTA's shared memory, completion bytes on the mbarrier at cluster address `bar_cluster`
-// (the leader CTA's `full` barrier)
-__device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* map, uint32_t bar_cluster, void* dst, int x, int y) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster), "r"(x), "r"(y)
-        : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
-    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
-}
-
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-
-template <int BN, int BKF, int STAGES, bool TWO = false>
-struct SmemLayoutP {
-    static_assert(BKF == 32, "K slabs of 32 values: 128-byte cross rows, 64-byte fp16 hi rows");
-    static constexpr int kATile = BM * BKF * 4;                       // cross operand, 4 bytes per value of k
-    static constexpr int kBTile = (TWO ? BN / 2 : BN) * BKF * 4;      // 2-SM form: each CTA keeps half of the W tile
-    static constexpr int kAHi = kATile / 2;                           // fp16 hi operand, 2 bytes per value of k
-    static constexpr int kBHi = kBTile / 2;
-    // stage = [A_cross | W_cross | A_hi | W_hi]; every tile is a multiple of 1024 bytes (swizzle atoms)
-    static constexpr int kOffAX = 0, kOffWX = kATile, kOffAH = kATile + kBTile, kOffWH = kATile + kBTile + kAHi;
-    static constexpr int kStage = kATile + kBTile + kAHi + kBHi;
-    static_assert(kBTile % 1024 == 0 && kBHi % 512 == 0, "tile alignment");
-    static constexpr int kScratch = 4 * 32 * 36 * 4;      // per epilogue warp: 32 rows x (32 + 4) floats
+template <int BN, int STAGES>
+struct SmemLayout {
+    static constexpr int kATile = BM * 128;             // 128 rows x 128 bytes (32 cross words or 64 fp16 values of k)
+    static constexpr int kWTile = (BN / 2) * 128;       // this CTA's half of the W tile
+    static constexpr int kStage = kATile + kWTile;
+    static_assert(kWTile % 1024 == 0, "swizzle atoms");
+    static constexpr int kScratch = 4 * 32 * 36 * 4;    // per epilogue warp: 32 rows x (32 + 4) floats
     static constexpr int kBytes = STAGES * kStage + kScratch + 1024 /*align slack*/ + 256 /*barriers*/;
+    static_assert((2 * STAGES + 4) * 8 + 8 <= 256, "barrier block");
+    static_assert(kBytes <= 232448, "shared memory per CTA");
 };
 
-// CL = 2: the CTA pair of a cluster works on two vertically adjacent 128-row tiles of the same N tile;
-// each CTA fetches HALF of the W tile and multicasts it into both CTAs' shared memory (the main loop is
-// bound by L2 -> SM traffic, this removes a third of it).  A stage is reused only after the MMA
-// warps of BOTH CTAs have committed it (multicast tcgen05.commit onto both `empty` barriers).
-template <int BN, int BKF, int STAGES, int CL, bool TWO = false>
+// KP = 0: bias / LSTM-cell epilogues (epi.kind); KP > 0: the vocabulary epilogue keeping the top-KP logits of
+// every (row, tile).  A separate instantiation keeps its 2 x KP + 32 live registers away from the others.
+template <int BN, int STAGES, int KP>
 __global__ void __launch_bounds__(192, 1)
-gemm_split_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-                              const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
-                              int M, int N, int K, GemmEpilogue epi, int dbg) {
+gemm_split_pair_kernel(const __grid_constant__ CUtensorMap map_a_x, const __grid_constant__ CUtensorMap map_a_h,
+                       const __grid_constant__ CUtensorMap map_w_x, const __grid_constant__ CUtensorMap map_w_h,
+                       int M, int N, int K, GemmEpilogue epi) {
     if (epi.stop_flag && *epi.stop_flag >= 0) return;
-    static_assert(!TWO || CL == 2, "the 2-SM form is a CTA pair");
-    using L = SmemLayoutP<BN, BKF, STAGES, TWO>;
+    using L = SmemLayout<BN, STAGES>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     float* scratch = reinterpret_cast<float*>(smem + STAGES * L::kStage);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * L::kStage + L::kScratch);
-    uint64_t* full = bars;                     // [STAGES]
+    uint64_t* full = bars;                     // [STAGES]  (used in the leader CTA)
     uint64_t* empty = bars + STAGES;           // [STAGES]
     uint64_t* tfull = bars + 2 * STAGES;       // [2] accumulator ready for the epilogue
-    uint64_t* tempty = bars + 2 * STAGES + 2;  // [2] accumulator drained by the 4 epilogue warps
+    uint64_t* tempty = bars + 2 * STAGES + 2;  // [2] accumulator drained by the 8 epilogue warps of the pair
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    constexpr int kTmemCols = 2 * BN > 256 ? 512 : 2 * BN;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_n = (N + BN - 1) / BN;
-    const int mgroups = ((M + BM - 1) / BM + CL - 1) / CL;        // groups of CL vertically adjacent tiles
+    const int mgroups = ((M + BM - 1) / BM + 1) / 2;          // pairs of vertically adjacent 128-row tiles
     const int nwork = mgroups * tiles_n;
-    const int nkb = (K + BKF - 1) / BKF;
-    const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
-    const int work0 = blockIdx.x / CL, work_step = gridDim.x / CL;
-    constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1);
+    const int nkx = (K + 31) / 32;                            // cross slabs: 32 values of k per 128-byte row
+    const int nkh = (K + 63) / 64;                            // hi slabs: 64 values of k per 128-byte row
+    const int crank = (int)cluster_ctarank();
+    const int work0 = blockIdx.x >> 1, work_step = gridDim.x >> 1;
 
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], TWO ? 1 : CL); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], TWO ? 8 : 4); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_hi) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_lo) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w_hi) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w_lo) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_x) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_h) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w_x) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w_h) : "memory");
     }
     if (warp == 1) {
-        if (TWO) {
-            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                         "n"(2 * BN > 256 ? 512 : 2 * BN)
-                         : "memory");
-            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-        } else {
-            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                         "n"(2 * BN > 256 ? 512 : 2 * BN)
-                         : "memory");
-            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-        }
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "n"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    if (CL > 1) cluster_sync_all(); else __syncthreads();       // peer barriers are initialised too
+    cluster_sync_all();                                        // the peer's barriers are initialised too
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
@@ -279,76 +231,59 @@ gemm_split_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, const
         if (lane == 0) {
             int it = 0;
             for (int work = work0; work < nwork; work += work_step) {
-                const int m0 = ((work / tiles_n) * CL + crank) * BM, n0 = (work % tiles_n) * BN;
-                for (int kb = 0; kb < nkb; ++kb, ++it) {
-                    const int s = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1;
-                    mbar_wait(&empty[s], ph ^ 1);
-                    uint8_t* st = smem + s * L::kStage;
-                    if (TWO) {
+                const int m0 = ((work / tiles_n) * 2 + crank) * BM;
+                const int nrow = (work % tiles_n) * BN + crank * (BN / 2);
+#pragma unroll 1
+                for (int pass = 0; pass < 2; ++pass) {
+                    const CUtensorMap* ma = pass == 0 ? &map_a_x : &map_a_h;
+                    const CUtensorMap* mw = pass == 0 ? &map_w_x : &map_w_h;
+                    const int nk = pass == 0 ? nkx : nkh, kstep = pass == 0 ? 32 : 64;
+                    for (int kb = 0; kb < nk; ++kb, ++it) {
+                        const int s = it % STAGES;
+                        mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+                        uint8_t* st = smem + s * L::kStage;
                         // both CTAs' bytes complete on the LEADER's barrier (its MMA warp consumes both halves)
                         if (crank == 0) mbar_expect_tx(&full[s], 2 * L::kStage);
                         const uint32_t fb = mapa_rank(smem_u32(&full[s]), 0);
-                        const int nrow = n0 + crank * (BN / 2);
-                        tma_load_2d_2sm(&map_a_lo, fb, st + L::kOffAX, kb * BKF, m0);
-                        tma_load_2d_2sm(&map_w_lo, fb, st + L::kOffWX, kb * BKF, nrow);
-                        tma_load_2d_2sm(&map_a_hi, fb, st + L::kOffAH, kb * BKF, m0);
-                        tma_load_2d_2sm(&map_w_hi, fb, st + L::kOffWH, kb * BKF, nrow);
-                        continue;
-                    }
-                    mbar_expect_tx(&full[s], L::kStage);
-                    tma_load_2d(&map_a_lo, &full[s], st + L::kOffAX, kb * BKF, m0);
-                    tma_load_2d(&map_a_hi, &full[s], st + L::kOffAH, kb * BKF, m0);
-                    if (CL == 1) {
-                        tma_load_2d(&map_w_lo, &full[s], st + L::kOffWX, kb * BKF, n0);
-                        tma_load_2d(&map_w_hi, &full[s], st + L::kOffWH, kb * BKF, n0);
-                    } else {
-                        const int nrow = n0 + crank * (BN / CL);
-                        tma_load_2d_mc(&map_w_lo, &full[s], st + L::kOffWX + crank * (L::kBTile / CL), kb * BKF, nrow, kMask);
-                        tma_load_2d_mc(&map_w_hi, &full[s], st + L::kOffWH + crank * (L::kBHi / CL), kb * BKF, nrow, kMask);
+                        tma_load_2d_2sm(ma, fb, st, kb * kstep, m0);
+                        tma_load_2d_2sm(mw, fb, st + L::kATile, kb * kstep, nrow);
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && !(TWO && crank != 0)) {               // 2-SM form: only the leader CTA issues
-            constexpr uint32_t idesc_h = make_idesc_f16(TWO ? 2 * BM : BM, BN);
-            constexpr uint32_t idesc_x = make_idesc_bf16(TWO ? 2 * BM : BM, BN);
+        if (lane == 0 && crank == 0) {                         // only the leader CTA issues
+            constexpr uint32_t idesc_h = make_idesc_f16(2 * BM, BN);
+            constexpr uint32_t idesc_x = make_idesc_bf16(2 * BM, BN);
             int it = 0, lt = 0;
             for (int work = work0; work < nwork; work += work_step, ++lt) {
                 const int acc = lt & 1;
-                const uint32_t aph = (lt >> 1) & 1;
-                mbar_wait(&tempty[acc], aph ^ 1);          // the epilogue has drained this accumulator
+                mbar_wait(&tempty[acc], ((lt >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t tacc = tmem_base + (uint32_t)(acc * BN);
-                for (int kb = 0; kb < nkb; ++kb, ++it) {
-                    const int s = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1;
-                    mbar_wait(&full[s], ph);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    uint8_t* st = smem + s * L::kStage;
-                    const uint64_t d_ax = make_kmajor_desc<32>(st + L::kOffAX);     // 128-byte rows, SWIZZLE_128B
-                    const uint64_t d_wx = make_kmajor_desc<32>(st + L::kOffWX);
-                    const uint64_t d_ah = make_kmajor_desc<16>(st + L::kOffAH);     // 64-byte rows, SWIZZLE_64B
-                    const uint64_t d_wh = make_kmajor_desc<16>(st + L::kOffWH);
-                    // every MMA consumes 32 bytes of K per row: 8 values of k of the cross operand, 16 of the hi operand
+                uint32_t first = 0u;                            // the tile's first MMA overwrites the accumulator
+#pragma unroll 1
+                for (int pass = 0; pass < 2; ++pass) {
+                    const int nk = pass == 0 ? nkx : nkh;
+                    const uint32_t idesc = pass == 0 ? idesc_x : idesc_h;
+                    for (int kb = 0; kb < nk; ++kb, ++it) {
+                        const int s = it % STAGES;
+                        mbar_wait(&full[s], (it / STAGES) & 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        uint8_t* st = smem + s * L::kStage;
+                        const uint64_t d_a = make_kmajor_desc(st);
+                        const uint64_t d_w = make_kmajor_desc(st + L::kATile);
+                        // every MMA consumes 32 bytes of K per row: 8 values of k of the cross operand, 16 of hi
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        const uint64_t adv = (uint64_t)((kk * 32) >> 4);
-                        if (TWO) umma2_bf16(tacc, d_ax + adv, d_wx + adv, idesc_x, (kb | kk) ? 1u : 0u);
-                        else umma_bf16(tacc, d_ax + adv, d_wx + adv, idesc_x, (kb | kk) ? 1u : 0u);
+                        for (int kk = 0; kk < 4; ++kk) {
+                            const uint64_t adv = (uint64_t)((kk * 32) >> 4);
+                            umma2_f16(tacc, d_a + adv, d_w + adv, idesc, first);
+                            first = 1u;
+                        }
+                        umma2_commit_mc(&empty[s], 3);
                     }
-#pragma unroll
-                    for (int kk = 0; kk < 2; ++kk) {
-                        const uint64_t adv = (uint64_t)((kk * 32) >> 4);
-                        if (TWO) umma2_bf16(tacc, d_ah + adv, d_wh + adv, idesc_h, 1u);
-                        else umma_bf16(tacc, d_ah + adv, d_wh + adv, idesc_h, 1u);
-                    }
-                    if (TWO) umma2_commit_mc(&empty[s], kMask);
-                    else if (CL == 1) umma_commit(&empty[s]);
-                    else umma_commit_mc(&empty[s], kMask);
                 }
-                if (TWO) umma2_commit_mc(&tfull[acc], kMask); else umma_commit(&tfull[acc]);
+                umma2_commit_mc(&tfull[acc], 3);
             }
         }
     } else {
@@ -356,12 +291,75 @@ gemm_split_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, const
         float* scr = scratch + q * (32 * 36);
         int lt = 0;
         for (int work = work0; work < nwork; work += work_step, ++lt) {
-            const int m0 = ((work / tiles_n) * CL + crank) * BM, n0 = (work % tiles_n) * BN;
+            const int m0 = ((work / tiles_n) * 2 + crank) * BM, n0 = (work % tiles_n) * BN;
             const int acc = lt & 1;
             const uint32_t aph = (lt >> 1) & 1;
             const uint32_t tacc = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
             const int rbase = m0 + q * 32;
-            if (epi.kind == Epi::kLstmCell) {
+            if constexpr (KP > 0) {
+                // ---- vocabulary epilogue: one accumulator row per thread ------------------------------------
+                // pass 1: sorted insertion of all BN logits of the row into t[0..KP) (values only: 2 FMNMX per
+                // slot); pass 2 (the accumulator is read again from TMEM): sum of exp against the tile maximum
+                // t[0], and every logit above the KP-th value - plus as many equal to it as still fit, in
+                // column order - goes out with its token id.  Ties therefore resolve towards lower token ids.
+                static_assert(BN % 32 == 0 && BN <= 32 * 36, "bias tile lives in the warp's scratch");
+                const int row = rbase + lane;
+                const bool row_ok = row < M;
+                const bool sc = epi.kind == Epi::kBiasScale;
+                const int tn = work % tiles_n;
+                for (int c = lane; c < BN; c += 32) scr[c] = n0 + c < N ? __ldg(epi.bias + n0 + c) : 0.f;
+                __syncwarp();
+                const int nvalid = N - n0;                      // columns of this tile inside the vocabulary
+                mbar_wait(&tfull[acc], aph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                float t[KP];
+#pragma unroll
+                for (int s = 0; s < KP; ++s) t[s] = -CUDART_INF_F;
+                auto logit = [&](uint32_t raw, int c) {
+                    float v = __uint_as_float(raw) + scr[c];
+                    if (sc) v = v / epi.scale;                  // logit /= temperature (model.py:834)
+                    return c < nvalid ? v : -CUDART_INF_F;
+                };
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    uint32_t r[32];
+                    tmem_ld32(tacc + (uint32_t)c0, r);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float v = logit(r[j], c0 + j);
+#pragma unroll
+                        for (int s = 0; s < KP; ++s) {
+                            const float hi = fmaxf(t[s], v);
+                            v = fminf(t[s], v);
+                            t[s] = hi;
+                        }
+                    }
+                }
+                const float thr = t[KP - 1], mx = t[0];
+                int cg = 0, ce = 0;
+#pragma unroll
+                for (int s = 0; s < KP; ++s) ce += t[s] > thr ? 1 : 0;     // slots [0, ce): above thr; [ce, KP): equal
+                float ssum = 0.f;
+                uint2* out = epi.topk_part + ((size_t)tn * M + (row_ok ? row : 0)) * KP;
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    uint32_t r[32];
+                    tmem_ld32(tacc + (uint32_t)c0, r);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float v = logit(r[j], c0 + j);
+                        ssum += __expf(v - mx);                 // columns past the vocabulary: exp(-inf) = 0
+                        if (row_ok) {
+                            if (v > thr) {
+                                out[cg++] = make_uint2(__float_as_uint(v), (uint32_t)(n0 + c0 + j));
+                            } else if (v == thr && ce < KP && c0 + j < nvalid) {
+                                out[ce++] = make_uint2(__float_as_uint(v), (uint32_t)(n0 + c0 + j));
+                            }
+                        }
+                    }
+                }
+                if (row_ok) epi.topk_ms[(size_t)tn * M + row] = make_float2(mx, ssum);
+            } else if (epi.kind == Epi::kLstmCell) {
                 // One accumulator row per thread, 32 columns (8 hidden units x i,f,g,o) per chunk.  The
                 // per-row operands of chunk c+1 (previous cell state of the source beam, the E'[token]
                 // row segment) are fetched while chunk c is computed, and those of chunk 0 before the
@@ -449,7 +447,7 @@ gemm_split_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, const
                     // all shared-memory loads are issued before the stores (independent, unrolled)
                     const int cq = lane & 7, rq = lane >> 3;
                     const int n = n0 + c0 + 4 * cq;
-                    if (n + 3 < N && !(dbg & 8)) {
+                    if (n + 3 < N) {
                         const float4 b4 = __ldg(reinterpret_cast<const float4*>(epi.bias + n));
                         float4 v[8];
 #pragma unroll
@@ -463,7 +461,7 @@ gemm_split_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, const
                                 *reinterpret_cast<float4*>(epi.C + (size_t)row * epi.ldc + n) = o;
                             }
                         }
-                    } else if (n < N && !(dbg & 8)) {
+                    } else if (n < N) {
                         for (int i = 0; i < 8; ++i) {
                             const int row = rbase + 4 * i + rq;
                             for (int jj = 0; jj < 4 && row < M; ++jj)
@@ -480,37 +478,24 @@ gemm_split_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, const
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) {
-                // 2-SM form: the leader's MMA overwrites both CTAs' accumulators, so both epilogues report to it
-                if (TWO && crank != 0) mbar_arrive_cluster(mapa_rank(smem_u32(&tempty[acc]), 0));
+                // the leader's MMA overwrites both CTAs' accumulators, so both epilogues report to it
+                if (crank != 0) mbar_arrive_cluster(mapa_rank(smem_u32(&tempty[acc]), 0));
                 else mbar_arrive(&tempty[acc]);
             }
         }
     }
-    if (CL > 1) cluster_sync_all(); else __syncthreads();       // no CTA leaves while its peer may still signal it
+    cluster_sync_all();                                        // no CTA leaves while its peer may still signal it
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (TWO)
-            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN > 256 ? 512 : 2 * BN) : "memory");
-        else
-            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN > 256 ? 512 : 2 * BN) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// operand split with the AOperand gather fused (rn_tf32 only serves the legacy recurrence format)
-__device__ __forceinline__ float rn_tf32(float x) {
-    uint32_t u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-    return __uint_as_float(u);
-}
-
-// LEGACY (kSplitLegacy): hi = rn_tf32(x), lo = rn_tf32(x - hi), both fp32 (the encoder recurrence packs its own
-//      operands from them); otherwise hi = fp16(x) and
-//      kSplitAct / kSplitWeight  "cross" operand: per 8-float block 16 bf16 values,
-//          activations [bf16(x - hi) x8 | bf16(x) x8],  weights [bf16(w) x8 | bf16(w - hi) x8],
-//      so one kind::f16 MMA (K = 16) over a block adds  x_lo*w + x*w_lo  for 8 values of k.
-template <bool LEGACY>
-__global__ void split_operand_kernel(AOperand A, int M, int K, void* __restrict__ hi_out, float* __restrict__ lo,
+// operand split with the AOperand gather fused: hi = fp16(x) and the "cross" operand, per 8-float block 16
+// bf16 values - activations [bf16(x - hi) x8 | bf16(x) x8], weights [bf16(w) x8 | bf16(w - hi) x8] - so one
+// kind::f16 MMA (K = 16) over a block adds  x_lo*w + x*w_lo  for 8 values of k.
+__global__ void split_operand_kernel(AOperand A, int M, int K, hi_t* __restrict__ hi_out, float* __restrict__ lo,
                                      const int* stop_flag, int fmt) {
     if (stop_flag && *stop_flag >= 0) return;
     const int k8n = K >> 3;
@@ -529,28 +514,17 @@ __global__ void split_operand_kernel(AOperand A, int M, int K, void* __restrict_
         const float4 v0 = src[0], v1 = src[1];
         const float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
         float h[8], l[8];
-        if (LEGACY) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { h[j] = rn_tf32(x[j]); l[j] = x[j] - h[j]; }
-            float4* ph = reinterpret_cast<float4*>(static_cast<float*>(hi_out) + (size_t)row * K + k);
-            ph[0] = make_float4(h[0], h[1], h[2], h[3]);
-            ph[1] = make_float4(h[4], h[5], h[6], h[7]);
-            float4* pl = reinterpret_cast<float4*>(lo + (size_t)row * K + k);
-            pl[0] = make_float4(rn_tf32(l[0]), rn_tf32(l[1]), rn_tf32(l[2]), rn_tf32(l[3]));
-            pl[1] = make_float4(rn_tf32(l[4]), rn_tf32(l[5]), rn_tf32(l[6]), rn_tf32(l[7]));
-        } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { h[j] = hi_part(x[j]); l[j] = x[j] - h[j]; }
-            *reinterpret_cast<uint4*>(static_cast<hi_t*>(hi_out) + (size_t)row * K + k) =
-                make_uint4(pack_hi2(h[0], h[1]), pack_hi2(h[2], h[3]), pack_hi2(h[4], h[5]), pack_hi2(h[6], h[7]));
-            const uint4 pl = make_uint4(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]),
-                                        pack_bf16x2(l[4], l[5]), pack_bf16x2(l[6], l[7]));
-            const uint4 px = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]),
-                                        pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
-            uint4* pc = reinterpret_cast<uint4*>(lo + (size_t)row * K + k);
-            pc[0] = fmt == kSplitAct ? pl : px;
-            pc[1] = fmt == kSplitAct ? px : pl;
-        }
+        for (int j = 0; j < 8; ++j) { h[j] = hi_part(x[j]); l[j] = x[j] - h[j]; }
+        *reinterpret_cast<uint4*>(hi_out + (size_t)row * K + k) =
+            make_uint4(pack_hi2(h[0], h[1]), pack_hi2(h[2], h[3]), pack_hi2(h[4], h[5]), pack_hi2(h[6], h[7]));
+        const uint4 pl = make_uint4(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]),
+                                    pack_bf16x2(l[4], l[5]), pack_bf16x2(l[6], l[7]));
+        const uint4 px = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]),
+                                    pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
+        uint4* pc = reinterpret_cast<uint4*>(lo + (size_t)row * K + k);
+        pc[0] = fmt == kSplitAct ? pl : px;
+        pc[1] = fmt == kSplitAct ? px : pl;
     }
 }
 
@@ -560,39 +534,34 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static EncodeTiledFn get_encode() {
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
+    static std::atomic<EncodeTiledFn> fn{nullptr};
+    EncodeTiledFn f = fn.load(std::memory_order_acquire);
+    if (!f) {
         void* p = nullptr;
         cudaDriverEntryPointQueryResult q;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
             q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
+            f = reinterpret_cast<EncodeTiledFn>(p);
+        fn.store(f, std::memory_order_release);
     }
-    return fn;
+    return f;
 }
 
-// cross operand: 2-D tensor [rows, K] of 4-byte words (two bf16 each), row-major -> box [box_rows, 32] = 128-byte
-// rows with 128-byte swizzle.  hi operand: [rows, K] fp16 -> box [box_rows, 32] = 64-byte rows, 64-byte swizzle.
-static int make_map_t(CUtensorMap* map, const void* base, int rows, int K, int box_rows, int ld, bool hi) {
+// Both operand kinds are 2-D row-major tensors read as boxes of 128-byte rows with 128-byte swizzle:
+// cross [rows, K] 4-byte words (two bf16 each) -> box [box_rows, 32]; hi [rows, K] fp16 -> box [box_rows, 64].
+static int make_map(CUtensorMap* map, const void* base, int rows, int K, int box_rows, int ld, bool hi) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return ASR_ERR_CUDA; }
     const size_t esz = hi ? sizeof(hi_t) : sizeof(float);
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)(ld > 0 ? ld : K) * esz};
-    cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {hi ? 64u : 32u, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, hi ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                      const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     hi ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) rows=%d K=%d hi=%d", (int)r, rows, K, (int)hi); return ASR_ERR_CUDA; }
     return ASR_OK;
-}
-static int make_map(CUtensorMap* map, const float* base, int rows, int K, int box_rows, int, int ld = 0) {
-    return make_map_t(map, base, rows, K, box_rows, ld, false);
-}
-static int make_map(CUtensorMap* map, const hi_t* base, int rows, int K, int box_rows, int, int ld = 0) {
-    return make_map_t(map, base, rows, K, box_rows, ld, true);
 }
 
 }  // namespace tc
@@ -608,118 +577,88 @@ int split_operand(const AOperand& A, int M, int K, hi_t* hi, float* lo, const in
                   int64_t* launches, int fmt) {
     if (M <= 0) return ASR_OK;
     ASR_TRY(check_split_args(A, K));
-    if (fmt == kSplitLegacy) { set_error("split: use split_operand_legacy"); return ASR_ERR_ARG; }
     long long total = (long long)M * (K / 8);
     int grid = (int)std::min<long long>((total + 255) / 256, (long long)kNumSMs * 16);
-    tc::split_operand_kernel<false><<<grid, 256, 0, st>>>(A, M, K, hi, lo, stop_flag, fmt);
+    tc::split_operand_kernel<<<grid, 256, 0, st>>>(A, M, K, hi, lo, stop_flag, fmt);
     ASR_CHECK_LAUNCH();
     if (launches) ++*launches;
     return ASR_OK;
 }
 
-int split_operand_legacy(const AOperand& A, int M, int K, float* hi, float* lo, cudaStream_t st) {
-    if (M <= 0) return ASR_OK;
-    ASR_TRY(check_split_args(A, K));
-    long long total = (long long)M * (K / 8);
-    int grid = (int)std::min<long long>((total + 255) / 256, (long long)kNumSMs * 16);
-    tc::split_operand_kernel<true><<<grid, 256, 0, st>>>(A, M, K, hi, lo, nullptr, kSplitLegacy);
-    ASR_CHECK_LAUNCH();
-    return ASR_OK;
-}
-
-// CL CTAs of a cluster work on CL vertically adjacent tiles and share the W tile by multicast
-template <int BN, int BKF, int STAGES, int CL, bool TWO = false>
-static int launch_tc_cluster(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const hi_t* w_hi, const float* w_lo,
-                             int M, int N, int K, const GemmEpilogue& epi, cudaStream_t st, int dbg_p) {
-    auto kern = tc::gemm_split_persistent_kernel<BN, BKF, STAGES, CL, TWO>;
-    const int smem_p = tc::SmemLayoutP<BN, BKF, STAGES, TWO>::kBytes;
-    const int tiles_m = (M + tc::BM - 1) / tc::BM, tiles_n = (N + BN - 1) / BN;
-    static int max_clusters = 0;
+template <int BN, int STAGES, int KP>
+static int launch_pair(const hi_t* a_hi, const float* a_lo, const hi_t* w_hi, const float* w_lo, int M, int N, int K,
+                       const GemmEpilogue& epi, cudaStream_t st) {
+    auto kern = tc::gemm_split_pair_kernel<BN, STAGES, KP>;
+    constexpr int smem = tc::SmemLayout<BN, STAGES>::kBytes;
+    CUtensorMap ma_x, ma_h, mw_x, mw_h;          // each CTA of the pair fetches its 128 rows of A, half of the W tile rows
+    ASR_TRY(tc::make_map(&ma_x, a_lo, M, K, tc::BM, epi.lda, false));
+    ASR_TRY(tc::make_map(&ma_h, a_hi, M, K, tc::BM, epi.lda, true));
+    ASR_TRY(tc::make_map(&mw_x, w_lo, N, K, BN / 2, epi.ldw, false));
+    ASR_TRY(tc::make_map(&mw_h, w_hi, N, K, BN / 2, epi.ldw, true));
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.blockDim = dim3(192);
-    cfg.dynamicSmemBytes = smem_p;
+    cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    if (!max_clusters) {
-        ASR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_p));
-        cfg.gridDim = dim3(CL * kNumSMs);
-        ASR_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
-        if (max_clusters < 1) { set_error("gemm_tc: no co-resident cluster of %d CTAs", CL); return ASR_ERR_CUDA; }
-        if (dbg_p & 16) fprintf(stderr, "[gemm_tc] BN=%d cluster %d: %d co-resident clusters\n", BN, CL, max_clusters);
+    // function attributes and cluster occupancy are per device: one slot per device id, set on first use there
+    static std::atomic<int> max_clusters[64];
+    int dev = 0;
+    ASR_CUDA(cudaGetDevice(&dev));
+    int mc = max_clusters[dev & 63].load(std::memory_order_acquire);
+    if (!mc) {
+        ASR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        cfg.gridDim = dim3(2 * kNumSMs);
+        ASR_CUDA(cudaOccupancyMaxActiveClusters(&mc, kern, &cfg));
+        if (mc < 1) { set_error("gemm_tc: no co-resident CTA pair (BN = %d)", BN); return ASR_ERR_CUDA; }
+        max_clusters[dev & 63].store(mc, std::memory_order_release);
     }
-    CUtensorMap mw_hi, mw_lo;       // each CTA of the cluster fetches 1/CL of the W tile rows
-    ASR_TRY(tc::make_map(&mw_hi, w_hi, N, K, BN / CL, BKF, epi.ldw));
-    ASR_TRY(tc::make_map(&mw_lo, w_lo, N, K, BN / CL, BKF, epi.ldw));
-    const int nwork = ((tiles_m + CL - 1) / CL) * tiles_n;
-    cfg.gridDim = dim3(CL * std::min(nwork, max_clusters));
-    ASR_CUDA(cudaLaunchKernelEx(&cfg, kern, ma_hi, ma_lo, mw_hi, mw_lo, M, N, K, epi, dbg_p));
+    const int tiles_m = (M + tc::BM - 1) / tc::BM, tiles_n = (N + BN - 1) / BN;
+    const int nwork = ((tiles_m + 1) / 2) * tiles_n;
+    cfg.gridDim = dim3(2 * std::min(nwork, mc));
+    ASR_CUDA(cudaLaunchKernelEx(&cfg, kern, ma_x, ma_h, mw_x, mw_h, M, N, K, epi));
     ASR_CHECK_LAUNCH();
     return ASR_OK;
 }
 
-// C = A * W^T with pre-split operands (a_hi/a_lo [M,K], w_hi/w_lo [N,K], all dense row-major)
-template <int BN, int BKF, int STAGES>
-static int launch_tc_cfg(const hi_t* a_hi, const float* a_lo, const hi_t* w_hi, const float* w_lo, int M, int N,
-                         int K, const GemmEpilogue& epi, cudaStream_t st) {
-    CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
-    ASR_TRY(tc::make_map(&ma_hi, a_hi, M, K, tc::BM, BKF, epi.lda));
-    ASR_TRY(tc::make_map(&ma_lo, a_lo, M, K, tc::BM, BKF, epi.lda));
-    ASR_TRY(tc::make_map(&mw_hi, w_hi, N, K, BN, BKF, epi.ldw));
-    ASR_TRY(tc::make_map(&mw_lo, w_lo, N, K, BN, BKF, epi.ldw));
-    static const int cl = getenv("ASR_B200_GEMM_CLUSTER") ? atoi(getenv("ASR_B200_GEMM_CLUSTER")) : 22;   // 22 = CTA pair with cta_group::2 MMAs
-    static const int dbg_p = getenv("ASR_B200_GEMM_DBG") ? atoi(getenv("ASR_B200_GEMM_DBG")) : 0;
-    const int smem_p = tc::SmemLayoutP<BN, BKF, STAGES>::kBytes;
-    const int tiles_m = (M + tc::BM - 1) / tc::BM, tiles_n = (N + BN - 1) / BN;
-    if (cl == 2) return launch_tc_cluster<BN, BKF, STAGES, 2>(ma_hi, ma_lo, w_hi, w_lo, M, N, K, epi, st, dbg_p);
-    if (cl == 4) return launch_tc_cluster<BN, BKF, STAGES, 4>(ma_hi, ma_lo, w_hi, w_lo, M, N, K, epi, st, dbg_p);
-    if (cl == 22) return launch_tc_cluster<BN, BKF, STAGES + 2, 2, true>(ma_hi, ma_lo, w_hi, w_lo, M, N, K, epi, st, dbg_p);
-    {
-        static bool attr_p = false;
-        static int num_sms = 0;
-        if (!attr_p) {
-            int dev = 0;
-            ASR_CUDA(cudaGetDevice(&dev));
-            ASR_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-            ASR_CUDA(cudaFuncSetAttribute(tc::gemm_split_persistent_kernel<BN, BKF, STAGES, 1>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem_p));
-            attr_p = true;
-        }
-        const int ntiles = tiles_n * tiles_m;
-        const int grid_p = ntiles < num_sms ? ntiles : num_sms;
-        tc::gemm_split_persistent_kernel<BN, BKF, STAGES, 1><<<grid_p, 192, smem_p, st>>>(ma_hi, ma_lo, mw_hi, mw_lo, M, N, K, epi, dbg_p);
-        ASR_CHECK_LAUNCH();
-        return ASR_OK;
-    }
-}
+int vocab_topk_slots(int k) { return k <= 1 ? 2 : (k <= 4 ? 8 : (k <= 8 ? 16 : 32)); }
 
+// C = A * W^T with pre-split operands (a_hi/a_lo [M,K], w_hi/w_lo [N,K], row strides epi.lda / epi.ldw or K)
 int launch_gemm_tc(const hi_t* a_hi, const float* a_lo, const hi_t* w_hi, const float* w_lo, int M, int N, int K,
                    const GemmEpilogue& epi, cudaStream_t st, int64_t* launches) {
     if (M <= 0) return ASR_OK;
     if (K % 8) { set_error("gemm_tc: K must be a multiple of 8"); return ASR_ERR_ARG; }
     if (epi.kind == Epi::kLstmCell && (N % 32)) { set_error("gemm_tc: LSTM epilogue needs N %% 32 == 0"); return ASR_ERR_ARG; }
-    static const char* env = getenv("ASR_B200_GEMM_TILE");
+    if (epi.topk_slots) {
+        // vocabulary projection with the fused log-sum-exp / top-k partials: 224-wide tiles (kVocabTiles = 23)
+        if (N != kVocab || !epi.topk_part || !epi.topk_ms || epi.kind == Epi::kLstmCell) { set_error("gemm_tc: bad top-k epilogue"); return ASR_ERR_ARG; }
+        switch (epi.topk_slots) {
+            case 2: ASR_TRY((launch_pair<kVocabTileN, 6, 2>(a_hi, a_lo, w_hi, w_lo, M, N, K, epi, st))); break;
+            case 8: ASR_TRY((launch_pair<kVocabTileN, 6, 8>(a_hi, a_lo, w_hi, w_lo, M, N, K, epi, st))); break;
+            case 16: ASR_TRY((launch_pair<kVocabTileN, 6, 16>(a_hi, a_lo, w_hi, w_lo, M, N, K, epi, st))); break;
+            case 32: ASR_TRY((launch_pair<kVocabTileN, 6, 32>(a_hi, a_lo, w_hi, w_lo, M, N, K, epi, st))); break;
+            default: set_error("gemm_tc: top-k slots %d", epi.topk_slots); return ASR_ERR_ARG;
+        }
+        if (launches) ++*launches;
+        return ASR_OK;
+    }
     // tile width: 128 for narrow outputs; otherwise 256 or 224 columns, whichever leaves the smaller
-    // last wave over the 74 CTA pairs (vocabulary GEMM: 5004 = 23 x 224 -> 368 pair tiles = 4.97 waves of
-    // 224 columns instead of 320 = 4.32 -> 5 waves of 256)
+    // last wave over the 74 CTA pairs
     int bn = N >= 1024 ? 256 : 128;
     if (bn == 256 && epi.kind != Epi::kLstmCell) {
         const int mg = ((M + tc::BM - 1) / tc::BM + 1) / 2, ncl = kNumSMs / 2;
         auto cost = [&](int w) { return (long long)((mg * ((N + w - 1) / w) + ncl - 1) / ncl) * w; };
         if (cost(224) < cost(256)) bn = 224;
     }
-    static const char* env_cell = getenv("ASR_B200_CELL_TILE");
-    if (env_cell && epi.kind == Epi::kLstmCell) bn = atoi(env_cell);
-    if (env) bn = atoi(env);
     if (bn == 256) {
-        ASR_TRY((launch_tc_cfg<256, 32, 2>(a_hi, a_lo, w_hi, w_lo, M, N, K, epi, st)));
+        ASR_TRY((launch_pair<256, 6, 0>(a_hi, a_lo, w_hi, w_lo, M, N, K, epi, st)));
     } else if (bn == 224) {
-        ASR_TRY((launch_tc_cfg<224, 32, 2>(a_hi, a_lo, w_hi, w_lo, M, N, K, epi, st)));
+        ASR_TRY((launch_pair<224, 6, 0>(a_hi, a_lo, w_hi, w_lo, M, N, K, epi, st)));
     } else {
-        ASR_TRY((launch_tc_cfg<128, 32, 3>(a_hi, a_lo, w_hi, w_lo, M, N, K, epi, st)));
+        ASR_TRY((launch_pair<128, 8, 0>(a_hi, a_lo, w_hi, w_lo, M, N, K, epi, st)));
     }
     if (launches) ++*launches;
     return ASR_OK;

@@ -575,29 +575,23 @@ class Model(object):
             return _cabi.PCM_S16
         raise TypeError(f"PCM buffer must be float32 or int16, not {dt}")
 
-    def set_gemm_mode(self, mode):
-        """'simt' (CUDA-core fp32), 'tc' (GEMM stages on tcgen05, split precision), 'rec' (only the encoder
-        recurrence on tcgen05) or 'tc+rec' (both)."""
-        self._need()
-        check(lib.asr_set_gemm_mode(self._h, {'simt': 0, 'tc': 1, 'rec': 2, 'tc+rec': 3, 'rec3': 4, 'tc+rec3': 5}[mode]), "asr_set_gemm_mode")
-
-    def test_gemm(self, A, W, bias, mode):
-        """C = A @ W.T + bias on the device through one GEMM engine (tests)."""
+    def test_gemm(self, A, W, bias):
+        """C = A @ W.T + bias on the device through the split-precision tensor-core engine (tests)."""
         self._need()
         M, K = A.shape
         N = W.shape[0]
         Cout = torch.empty(M, N, dtype=torch.float32, device=self.device)
         check(lib.asr_test_gemm(self._h, C.c_void_p(A.data_ptr()), C.c_void_p(W.data_ptr()),
                                 C.c_void_p(bias.data_ptr()), C.c_void_p(Cout.data_ptr()), M, N, K,
-                                {'simt': 0, 'tc': 1}[mode], self._stream()), "asr_test_gemm")
+                                self._stream()), "asr_test_gemm")
         return Cout
 
     # ---- instrumentation ---------------------------------------------------------------------------
     def launch_count(self, reset=False):
         return int(lib.asr_launch_count(self._h, 1 if reset else 0))
 
-    def stage_timing(self, enable=True):
-        check(lib.asr_stage_timing(self._h, 1 if enable else 0), "asr_stage_timing")
+    def stage_timing(self, enable=True, recurrence_timeline=False):
+        check(lib.asr_stage_timing(self._h, (1 if enable else 0) | (2 if recurrence_timeline else 0)), "asr_stage_timing")
 
     def stage_times(self):
         """ms per pipeline stage (CUDA events on the launch stream) + kernel-level timers:

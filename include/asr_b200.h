@@ -239,15 +239,13 @@ int asr_transcribe_device(asr_handle* h, const float* d_pcm, const int64_t* h_pc
                           double length_weight, int32_t* h_tokens, int32_t* h_len, float* h_score,
                           void* stream);
 
-/* GEMM engine of the four GEMM-shaped stages (nn.LSTM input projections util.py:1259, attention
- * keys attention.py:77, nn.LSTMCell util.py:1650-1661, vocabulary projection decoder.py:133):
- * 0 = CUDA-core fp32 FMA, 1 = tcgen05/TMEM/TMA tensor cores, split precision (fp16 hi + bf16 cross
- * terms, fp32-faithful: ~2^-20 relative per product; operands beyond +-65504 fall back to bf16 accuracy).  The
- * default can also be chosen with the environment variable ASR_B200_GEMM=simt|tc. */
-int asr_set_gemm_mode(asr_handle* h, int mode);
-/* Standalone GEMM for tests: d_C[M,N] = d_A[M,K] * d_W[N,K]^T + d_bias[N] through engine `mode`. */
+/* The GEMM engine of the GEMM-shaped stages (nn.LSTM input projections util.py:1259, attention keys
+ * attention.py:77, query attention.py:92, nn.LSTMCell util.py:1650-1661, vocabulary projection decoder.py:133):
+ * tcgen05 / TMEM / TMA tensor cores in split precision (fp16 hi + bf16 cross terms, fp32-faithful: ~2^-20
+ * relative per product; operands beyond +-65504 fall back to bf16 accuracy).  Standalone entry for tests:
+ * d_C[M,N] = d_A[M,K] * d_W[N,K]^T + d_bias[N]. */
 int asr_test_gemm(asr_handle* h, const float* d_A, const float* d_W, const float* d_bias, float* d_C,
-                  int M, int N, int K, int mode, void* stream);
+                  int M, int N, int K, void* stream);
 
 /* Tuning aid: average ms per launch of the tensor-core GEMM engine on an [M,K] x [N,K]^T problem
  * (operands already split, CUDA events on `stream`, `iters` timed launches after 2 warm-ups). */
@@ -260,8 +258,9 @@ int64_t asr_launch_count(asr_handle* h, int reset);
  * h_ms[8] = {features, encoder input GEMMs, encoder recurrence, keys+init, decoder cell,
  * attention, vocab projection, top-k + bookkeeping + finalise}; h_ms[8..11] = {all GEMM-engine
  * launches, operand splits, algorithmic GFLOP of those GEMMs, the attention kernel alone} (nested in
- * the stages).  enable=1 records events
- * around every stage (adds event overhead); asr_stage_times reads them after a sync. */
+ * the stages).  enable bit 0 records events around every stage (adds event overhead; the decode loop then runs
+ * eagerly instead of from its CUDA graph); asr_stage_times reads them after a sync.  enable bit 1 prints the
+ * recurrence kernel's per-step clock64 timeline (phases of cluster 0) to stderr. */
 int asr_stage_timing(asr_handle* h, int enable);
 int asr_stage_times(asr_handle* h, float* h_ms, int n);
 

@@ -47,16 +47,16 @@ def test_encoder(G, cname):
             assert v <= ENC_TOL, (k, v)
 
 
-@pytest.mark.parametrize("mode", ["simt", "tc"])
-def test_gemm_engines_fp32_faithful(G, mode):
-    # max |C - C_fp64| / max |C_fp64|.  CUDA-core fp32 FMA: ~1e-6.  tcgen05 split precision (fp16 hi + bf16
-    # cross terms): the products are fp32-faithful but the tensor core accumulates with truncation, measured
-    # 3-7e-6 at K <= 1024.  Also: row-wise accuracy over fp16's normal range (1e-4 ... 1e4 row magnitudes),
-    # the absolute error bound below it, and finite results (bf16-accurate residual) when |a| > 65504.
-    r = G.check_gemm(mode)
-    tol = 2e-6 if mode == "simt" else 1e-5
+def test_gemm_engine_fp32_faithful(G):
+    # max |C - C_fp64| / max |C_fp64| of the tcgen05 split-precision engine (fp16 hi + bf16 cross terms).  The
+    # products are fp32-faithful; the tensor core accumulates with truncation, which the cross-first / hi-second
+    # pass order keeps to K / 16 full-magnitude steps (a CUDA-core fp32 FMA loop measures ~1e-6 here).  Also:
+    # row-wise accuracy over fp16's normal range (1e-4 ... 1e4 row magnitudes), the absolute error bound below it,
+    # and finite results (bf16-accurate residual) when |a| > 65504.
+    r = G.check_gemm()
+    print("[gemm accuracy]", r)
     for k, v in r.items():
-        assert v <= tol, (mode, k, v)
+        assert v <= 5e-6, (k, v)
 
 
 def test_lm_scores_bit_exact(G):

@@ -20,8 +20,7 @@ def main():
               ("encoder_kat", G.check_encoder_kat, ()),
               ("encoder_greedy3", G.check_encoder, ("greedy3",)),
               ("encoder_beam4", G.check_encoder, ("beam4",)),
-              ("gemm_simt", G.check_gemm, ("simt",)),
-              ("gemm_tc", G.check_gemm, ("tc",)),
+              ("gemm_tc", G.check_gemm, ()),
               ("lm", G.check_lm, ()),
               ("greedy1", G.check_greedy, ("greedy1",)),
               ("greedy3", G.check_greedy, ("greedy3",)),
