@@ -620,11 +620,13 @@ int asr_test_gemm(asr_handle* h, const float* d_A, const float* d_W, const float
 
 // Tuning aid: average ms per launch of the tensor-core GEMM engine on an [M,K] x [N,K]^T problem with
 // pre-split operands (events on `stream`, `iters` launches after 2 warm-ups).
-int asr_bench_gemm(asr_handle* h, int M, int N, int K, int iters, float* ms_out, void* stream) {
+int asr_bench_gemm(asr_handle* h, int M, int N, int K, int iters, int topk_slots, float* ms_out, void* stream) {
     if (!h || !ms_out || M < 1 || N < 1 || K < 8 || iters < 1) { set_error("asr_bench_gemm: bad argument"); return ASR_ERR_ARG; }
     cudaStream_t st = (cudaStream_t)stream;
     float *a, *a_lo, *w, *w_lo, *c, *bias;
     hi_t *a_hi, *w_hi;
+    uint2* part = nullptr;
+    float2* pms = nullptr;
     ASR_CUDA(cudaMalloc(&a, sizeof(float) * (size_t)M * K));
     ASR_CUDA(cudaMalloc(&a_hi, sizeof(float) * (size_t)M * K));
     ASR_CUDA(cudaMalloc(&a_lo, sizeof(float) * (size_t)M * K));
@@ -641,6 +643,13 @@ int asr_bench_gemm(asr_handle* h, int M, int N, int K, int iters, float* ms_out,
     e.bias = bias;
     e.C = c;
     e.ldc = N;
+    if (topk_slots > 0) {
+        ASR_CUDA(cudaMalloc(&part, sizeof(uint2) * (size_t)kVocabTiles * M * topk_slots));
+        ASR_CUDA(cudaMalloc(&pms, sizeof(float2) * (size_t)kVocabSums * M));
+        e.topk_slots = topk_slots;
+        e.topk_part = part;
+        e.topk_ms = pms;
+    }
     int rc = split_operand(plain_a(a, K, K), M, K, a_hi, a_lo, nullptr, st, nullptr, kSplitAct);
     if (rc == ASR_OK) rc = split_operand(plain_a(w, K, K), N, K, w_hi, w_lo, nullptr, st, nullptr, kSplitWeight);
     cudaEvent_t e0, e1;
@@ -656,6 +665,8 @@ int asr_bench_gemm(asr_handle* h, int M, int N, int K, int iters, float* ms_out,
     *ms_out = ms / iters;
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaFree(a); cudaFree(a_hi); cudaFree(a_lo); cudaFree(w); cudaFree(w_hi); cudaFree(w_lo); cudaFree(c); cudaFree(bias);
+    if (part) cudaFree(part);
+    if (pms) cudaFree(pms);
     if (rc != ASR_OK) return rc;
     if (ce != cudaSuccess) { set_error("asr_bench_gemm: %s", cudaGetErrorString(ce)); return ASR_ERR_CUDA; }
     return ASR_OK;
@@ -730,7 +741,7 @@ int asr_reserve(asr_handle* h, int max_utts, int64_t max_rows, int max_beam, int
     }
     ASR_TRY(dev_alloc_t(pool, &w.logits, (size_t)max_utts * kVocab));
     ASR_TRY(dev_alloc_t(pool, &w.topk_part, (size_t)kVocabTiles * R * vocab_topk_slots(max_beam)));
-    ASR_TRY(dev_alloc_t(pool, &w.topk_ms, (size_t)kVocabTiles * R));
+    ASR_TRY(dev_alloc_t(pool, &w.topk_ms, (size_t)kVocabSums * R));
     ASR_TRY(dev_alloc_t(pool, &w.att_q, R * kAtt));
     ASR_TRY(dev_alloc_t(pool, &w.dec_split_hi, R * kProjK));
     ASR_TRY(dev_alloc_t(pool, &w.dec_split_lo, R * kProjK));

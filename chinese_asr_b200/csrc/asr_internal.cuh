@@ -30,6 +30,7 @@ constexpr int kStages = 12;       // 8 pipeline stages + kernel-level timers (GE
 // vocabulary projection with fused log-sum-exp / top-k partials (gemm_tc.cu): 224-column tiles, 5004 = 22 x 224 + 76
 constexpr int kVocabTileN = 224;
 constexpr int kVocabTiles = (kVocab + kVocabTileN - 1) / kVocabTileN;     // 23
+constexpr int kVocabSums = 2 * kVocabTiles;      // (max, sum exp) partials per row: two column halves per tile
 
 void set_error(const char* fmt, ...);
 // raise a kernel's dynamic shared-memory limit on the current device (once per kernel and device)
@@ -128,7 +129,7 @@ struct GemmEpilogue {
     // tile tn and row r the KP largest logits (value bits, token id) and the (max, sum of exp) of the tile
     int topk_slots;
     uint2* topk_part;      // [kVocabTiles, M, KP]
-    float2* topk_ms;       // [kVocabTiles, M]
+    float2* topk_ms;       // [kVocabSums, M]
 };
 
 // C[M,N] = A[M,K] * W[N,K]^T (+ epilogue) on the tcgen05 split-precision engine (gemm_tc.cu): operands
@@ -259,7 +260,7 @@ struct Workspace {
     float* dctx[2] = {};
     float* logits = nullptr;     // [max_utts, 5004]: only the greedy driver's logits export (tests) materialises them
     uint2* topk_part = nullptr;  // [23, R, KP] per vocabulary tile and row: top-KP (logit bits, token id)
-    float2* topk_ms = nullptr;   // [23, R] per vocabulary tile and row: (max logit, sum of exp(logit - max))
+    float2* topk_ms = nullptr;   // [46, R] per half vocabulary tile and row: (tile max logit, sum of exp(logit - max))
     float* att_q = nullptr;      // [R, 128] query projection of the current step
     hi_t* dec_split_hi = nullptr;    // [R, 1024] fp16 hi of [h_new | ctx_new], written by the producing kernels
     float* dec_split_lo = nullptr;

@@ -849,7 +849,7 @@ struct BookParams {
 
 struct MergeParams {
     const uint2* part;        // [kVocabTiles, R, KP] (logit bits, token id)
-    const float2* part_ms;    // [kVocabTiles, R] (tile max, sum of exp(logit - max))
+    const float2* part_ms;    // [kVocabSums, R] (tile max, sum of exp(logit - max) over a column half)
     int KP;
     BookParams book;
 };
@@ -973,9 +973,11 @@ beam_merge_kernel(MergeParams p) {
     // log-sum-exp of every row from its tile partials (model.py:835)
     for (int r = warp; r < nrow; r += 8) {
         const int row = u * k + r;
-        const float2 ms = lane < kVocabTiles ? __ldcg(p.part_ms + (size_t)lane * R + row) : make_float2(-CUDART_INF_F, 0.f);
-        const float mx = warp_max(ms.x);
-        const float sum = warp_sum(lane < kVocabTiles ? ms.y * __expf(ms.x - mx) : 0.f);
+        static_assert(kVocabSums <= 64, "two partials per lane");
+        const float2 m0 = __ldcg(p.part_ms + (size_t)lane * R + row);
+        const float2 m1 = lane + 32 < kVocabSums ? __ldcg(p.part_ms + (size_t)(lane + 32) * R + row) : make_float2(-CUDART_INF_F, 0.f);
+        const float mx = warp_max(fmaxf(m0.x, m1.x));
+        const float sum = warp_sum(m0.y * __expf(m0.x - mx) + m1.y * __expf(m1.x - mx));     // exp(-inf) = 0
         if (lane == 0) { s_lse[r] = mx + logf(sum); s_bs[r] = b.beam_score[row]; }
     }
     if (tid == 0) s_cnt = 0;
@@ -1283,7 +1285,7 @@ constexpr int kRowElems = 20;   // 256 threads * 20 >= 5004
 struct GreedyParams {
     const float* logits;      // [B, V] (export path) or nullptr
     const uint2* part;        // [kVocabTiles, B, 2] tile partials of the vocabulary GEMM (KP = 2)
-    const float2* part_ms;    // [kVocabTiles, B]
+    const float2* part_ms;    // [kVocabSums, B]
     int* tok_hist;            // [max_len + 1, B]
     int* g_tokens;            // [max_len, B]
     float* g_accum; int* g_finished; int* g_len;
@@ -1344,9 +1346,9 @@ greedy_pick_kernel(GreedyParams p) {
         s = block_reduce_sum(s, s_red);
         lse = m + logf(s);
     } else {
-        float2 ms = make_float2(-CUDART_INF_F, 0.f);
+        const float2 m0 = __ldcg(p.part_ms + (size_t)lane * p.B + u);
+        const float2 m1 = lane + 32 < kVocabSums ? __ldcg(p.part_ms + (size_t)(lane + 32) * p.B + u) : make_float2(-CUDART_INF_F, 0.f);
         if (lane < kVocabTiles) {
-            ms = __ldcg(p.part_ms + (size_t)lane * p.B + u);
             const uint2 c = __ldcg(p.part + ((size_t)lane * p.B + u) * 2);
             m = __uint_as_float(c.x);
             mi = (int)c.y;
@@ -1357,7 +1359,7 @@ greedy_pick_kernel(GreedyParams p) {
             const int i2 = __shfl_xor_sync(0xffffffffu, mi, o);
             if (m2 > m || (m2 == m && i2 < mi)) { m = m2; mi = i2; }
         }
-        const float s = warp_sum(lane < kVocabTiles ? ms.y * __expf(ms.x - m) : 0.f);
+        const float s = warp_sum(m0.y * __expf(m0.x - m) + m1.y * __expf(m1.x - m));
         lse = m + logf(s);
     }
     if (tid != 0) return;

@@ -166,13 +166,61 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo_half, float hi_half) {
 __device__ __forceinline__ float sigm(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float tanh_e(float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); }
 
-template <int BN, int STAGES>
+// Sorting networks on registers (all indices compile-time): the vocabulary epilogue keeps the KP largest
+// logits of a row by sorting every group of KP new values and merging it into the running list - about
+// (log2 KP)^2 / 2 + log2 KP + 1 min/max pairs per value, against 2 KP for a sorted insertion, and wide enough
+// (KP / 2 independent compare-exchanges per stage) to hide the min/max latency.
+template <int N>
+__device__ __forceinline__ void bitonic_sort_desc(float (&a)[N]) {
+#pragma unroll
+    for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const float hi = fmaxf(a[i], a[l]), lo = fminf(a[i], a[l]);
+                    const bool desc = (i & k) == 0;
+                    a[i] = desc ? hi : lo;
+                    a[l] = desc ? lo : hi;
+                }
+            }
+        }
+    }
+}
+// t (sorted descending) <- the N largest of t and b (sorted descending): max(t[i], b[N-1-i]) is a bitonic
+// sequence holding exactly those, one bitonic merge sorts it
+template <int N>
+__device__ __forceinline__ void merge_top_desc(float (&t)[N], const float (&b)[N]) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) t[i] = fmaxf(t[i], b[N - 1 - i]);
+#pragma unroll
+    for (int j = N >> 1; j > 0; j >>= 1) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const int l = i ^ j;
+            if (l > i) {
+                const float hi = fmaxf(t[i], t[l]), lo = fminf(t[i], t[l]);
+                t[i] = hi;
+                t[l] = lo;
+            }
+        }
+    }
+}
+
+template <int BN, int STAGES, int KP = 0>
 struct SmemLayout {
     static constexpr int kATile = BM * 128;             // 128 rows x 128 bytes (32 cross words or 64 fp16 values of k)
     static constexpr int kWTile = (BN / 2) * 128;       // this CTA's half of the W tile
     static constexpr int kStage = kATile + kWTile;
     static_assert(kWTile % 1024 == 0, "swizzle atoms");
-    static constexpr int kScratch = 4 * 32 * 36 * 4;    // per epilogue warp: 32 rows x (32 + 4) floats
+    // KP = 0: per epilogue warp 32 rows x (32 + 4) floats (transpose for coalesced stores);
+    // KP > 0: 8 epilogue warps, each its half of the bias tile (128 floats) + 32 lanes x (KP + 1) floats to hand its
+    // top-KP list to the warp that shares its rows
+    static constexpr int kEpiWarps = KP > 0 ? 8 : 4;
+    static constexpr int kScratch = KP > 0 ? 8 * (128 + 32 * (KP + 1)) * 4 : 4 * 32 * 36 * 4;
+    static constexpr int kThreads = 64 + 32 * kEpiWarps;
     static constexpr int kBytes = STAGES * kStage + kScratch + 1024 /*align slack*/ + 256 /*barriers*/;
     static_assert((2 * STAGES + 4) * 8 + 8 <= 256, "barrier block");
     static_assert(kBytes <= 232448, "shared memory per CTA");
@@ -181,12 +229,12 @@ struct SmemLayout {
 // KP = 0: bias / LSTM-cell epilogues (epi.kind); KP > 0: the vocabulary epilogue keeping the top-KP logits of
 // every (row, tile).  A separate instantiation keeps its 2 x KP + 32 live registers away from the others.
 template <int BN, int STAGES, int KP>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__((SmemLayout<BN, STAGES, KP>::kThreads), 1)
 gemm_split_pair_kernel(const __grid_constant__ CUtensorMap map_a_x, const __grid_constant__ CUtensorMap map_a_h,
                        const __grid_constant__ CUtensorMap map_w_x, const __grid_constant__ CUtensorMap map_w_h,
                        int M, int N, int K, GemmEpilogue epi) {
     if (epi.stop_flag && *epi.stop_flag >= 0) return;
-    using L = SmemLayout<BN, STAGES>;
+    using L = SmemLayout<BN, STAGES, KP>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     float* scratch = reinterpret_cast<float*>(smem + STAGES * L::kStage);
@@ -209,7 +257,7 @@ gemm_split_pair_kernel(const __grid_constant__ CUtensorMap map_a_x, const __grid
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 2 * L::kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_x) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_h) : "memory");
@@ -287,8 +335,8 @@ gemm_split_pair_kernel(const __grid_constant__ CUtensorMap map_a_x, const __grid
             }
         }
     } else {
-        const int q = warp & 3;
-        float* scr = scratch + q * (32 * 36);
+        const int q = warp & 3;                                // TMEM lane quarter this warp may read
+        float* scr = KP > 0 ? scratch + (warp - 2) * (128 + 32 * (KP + 1)) : scratch + q * (32 * 36);
         int lt = 0;
         for (int work = work0; work < nwork; work += work_step, ++lt) {
             const int m0 = ((work / tiles_n) * 2 + crank) * BM, n0 = (work % tiles_n) * BN;
@@ -297,68 +345,111 @@ gemm_split_pair_kernel(const __grid_constant__ CUtensorMap map_a_x, const __grid
             const uint32_t tacc = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
             const int rbase = m0 + q * 32;
             if constexpr (KP > 0) {
-                // ---- vocabulary epilogue: one accumulator row per thread ------------------------------------
-                // pass 1: sorted insertion of all BN logits of the row into t[0..KP) (values only: 2 FMNMX per
-                // slot); pass 2 (the accumulator is read again from TMEM): sum of exp against the tile maximum
-                // t[0], and every logit above the KP-th value - plus as many equal to it as still fit, in
-                // column order - goes out with its token id.  Ties therefore resolve towards lower token ids.
-                static_assert(BN % 32 == 0 && BN <= 32 * 36, "bias tile lives in the warp's scratch");
+                // ---- vocabulary epilogue: one accumulator row per thread, TWO warps per 32 rows ------------
+                // Warps w and w + 4 read the same TMEM lanes (rows) and split the tile's columns (chunks of 32:
+                // [0, 128) and [128, BN)).  pass 1: the KP largest logits of the warp's columns (values only,
+                // sorting networks on registers); the two lists are exchanged through shared memory and merged,
+                // which gives both warps the tile's KP-th largest value thr and maximum mx; pass 2 (the
+                // accumulator is read again from TMEM): sum of exp against mx, and every logit above thr - plus
+                // as many equal to it as still fit, in column order - goes out with its token id (the lower
+                // column half fills its slots first, so ties resolve towards lower token ids).
+                static_assert(BN % 32 == 0 && BN > 128 && BN <= 256 && 32 % KP == 0, "two column halves of <= 128");
+                const int half = (warp - 2) >> 2;               // 0: columns [0, 128), 1: [128, BN)
+                const int cbeg = half * 128, cend = half ? BN : 128;
                 const int row = rbase + lane;
                 const bool row_ok = row < M;
                 const bool sc = epi.kind == Epi::kBiasScale;
                 const int tn = work % tiles_n;
-                for (int c = lane; c < BN; c += 32) scr[c] = n0 + c < N ? __ldg(epi.bias + n0 + c) : 0.f;
+                float* s_bias = scr;                            // [128] this warp's part of the bias tile
+                float* s_list = scr + 128;                      // [32][KP + 1] this warp's top-KP lists
+                const float* p_list = s_list + (half ? -4 : 4) * (128 + 32 * (KP + 1));      // the partner warp's
+                // columns past the vocabulary (zero-filled W rows) get -inf through the bias
+                for (int c = lane; c < cend - cbeg; c += 32)
+                    s_bias[c] = n0 + cbeg + c < N ? __ldg(epi.bias + n0 + cbeg + c) : -CUDART_INF_F;
                 __syncwarp();
-                const int nvalid = N - n0;                      // columns of this tile inside the vocabulary
                 mbar_wait(&tfull[acc], aph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 float t[KP];
 #pragma unroll
                 for (int s = 0; s < KP; ++s) t[s] = -CUDART_INF_F;
-                auto logit = [&](uint32_t raw, int c) {
-                    float v = __uint_as_float(raw) + scr[c];
-                    if (sc) v = v / epi.scale;                  // logit /= temperature (model.py:834)
-                    return c < nvalid ? v : -CUDART_INF_F;
+                // the 32 logits of a chunk: accumulator + bias, / temperature (model.py:834; IEEE division like
+                // torch, kept out of the straight-line min/max code below)
+                auto load_chunk = [&](int c0, float (&v)[32]) {
+                    uint32_t r[32];
+                    tmem_ld32(tacc + (uint32_t)c0, r);
+                    const float4* b4 = reinterpret_cast<const float4*>(s_bias + (c0 - cbeg));
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 bb = b4[j >> 2];
+                        v[j] = __uint_as_float(r[j]) + bb.x;
+                        v[j + 1] = __uint_as_float(r[j + 1]) + bb.y;
+                        v[j + 2] = __uint_as_float(r[j + 2]) + bb.z;
+                        v[j + 3] = __uint_as_float(r[j + 3]) + bb.w;
+                    }
+                    if (sc) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = v[j] / epi.scale;
+                    }
                 };
 #pragma unroll 1
-                for (int c0 = 0; c0 < BN; c0 += 32) {
-                    uint32_t r[32];
-                    tmem_ld32(tacc + (uint32_t)c0, r);
+                for (int c0 = cbeg; c0 < cend; c0 += 32) {
+                    float v[32];
+                    load_chunk(c0, v);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float v = logit(r[j], c0 + j);
+                    for (int g = 0; g < 32; g += KP) {
+                        float b[KP];
 #pragma unroll
-                        for (int s = 0; s < KP; ++s) {
-                            const float hi = fmaxf(t[s], v);
-                            v = fminf(t[s], v);
-                            t[s] = hi;
-                        }
+                        for (int s = 0; s < KP; ++s) b[s] = v[g + s];
+                        bitonic_sort_desc<KP>(b);
+                        merge_top_desc<KP>(t, b);
                     }
                 }
-                const float thr = t[KP - 1], mx = t[0];
-                int cg = 0, ce = 0;
+                // exchange with the warp sharing these rows (named barrier per lane quarter, 64 threads)
 #pragma unroll
-                for (int s = 0; s < KP; ++s) ce += t[s] > thr ? 1 : 0;     // slots [0, ce): above thr; [ce, KP): equal
+                for (int s = 0; s < KP; ++s) s_list[lane * (KP + 1) + s] = t[s];
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+                float o[KP], own[KP];
+#pragma unroll
+                for (int s = 0; s < KP; ++s) { o[s] = p_list[lane * (KP + 1) + s]; own[s] = t[s]; }
+                merge_top_desc<KP>(t, o);                       // t: the tile's top KP of this row
+                const float thr = t[KP - 1], mx = t[0];
+                int ngt = 0, gt_own = 0, eq_own = 0, gt_oth = 0, eq_oth = 0;
+#pragma unroll
+                for (int s = 0; s < KP; ++s) {
+                    ngt += t[s] > thr ? 1 : 0;
+                    gt_own += own[s] > thr ? 1 : 0;
+                    eq_own += own[s] == thr ? 1 : 0;
+                    gt_oth += o[s] > thr ? 1 : 0;
+                    eq_oth += o[s] == thr ? 1 : 0;
+                }
+                // slots [0, ngt): above thr, lower column half first; [ngt, KP): equal to thr, lower half first
+                int cg = half ? gt_oth : 0;
+                int ce = ngt + (half ? min(eq_oth, KP - ngt) : 0);
+                (void)gt_own; (void)eq_own;
                 float ssum = 0.f;
                 uint2* out = epi.topk_part + ((size_t)tn * M + (row_ok ? row : 0)) * KP;
+                const int nvalid = N - n0;                                 // columns of this tile inside the vocabulary
 #pragma unroll 1
-                for (int c0 = 0; c0 < BN; c0 += 32) {
-                    uint32_t r[32];
-                    tmem_ld32(tacc + (uint32_t)c0, r);
+                for (int c0 = cbeg; c0 < cend; c0 += 32) {
+                    float v[32];
+                    load_chunk(c0, v);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) ssum += __expf(v[j] - mx);     // columns past the vocabulary: exp(-inf) = 0
+                    // candidates: branch-free slot arithmetic, one predicated 8-byte store per value
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        const float v = logit(r[j], c0 + j);
-                        ssum += __expf(v - mx);                 // columns past the vocabulary: exp(-inf) = 0
-                        if (row_ok) {
-                            if (v > thr) {
-                                out[cg++] = make_uint2(__float_as_uint(v), (uint32_t)(n0 + c0 + j));
-                            } else if (v == thr && ce < KP && c0 + j < nvalid) {
-                                out[ce++] = make_uint2(__float_as_uint(v), (uint32_t)(n0 + c0 + j));
-                            }
-                        }
+                        const bool in = row_ok && c0 + j < nvalid;
+                        const bool gt = in && v[j] > thr;
+                        const bool eq = in && v[j] == thr && ce < KP;
+                        const int pos = gt ? cg : ce;
+                        if (gt || eq) out[pos] = make_uint2(__float_as_uint(v[j]), (uint32_t)(n0 + c0 + j));
+                        cg += gt ? 1 : 0;
+                        ce += eq ? 1 : 0;
                     }
                 }
-                if (row_ok) epi.topk_ms[(size_t)tn * M + row] = make_float2(mx, ssum);
+                if (row_ok) epi.topk_ms[((size_t)tn * 2 + half) * M + row] = make_float2(mx, ssum);
+                // the partner must have read this warp's list before the next tile overwrites it
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
             } else if (epi.kind == Epi::kLstmCell) {
                 // One accumulator row per thread, 32 columns (8 hidden units x i,f,g,o) per chunk.  The
                 // per-row operands of chunk c+1 (previous cell state of the source beam, the E'[token]
@@ -589,7 +680,7 @@ template <int BN, int STAGES, int KP>
 static int launch_pair(const hi_t* a_hi, const float* a_lo, const hi_t* w_hi, const float* w_lo, int M, int N, int K,
                        const GemmEpilogue& epi, cudaStream_t st) {
     auto kern = tc::gemm_split_pair_kernel<BN, STAGES, KP>;
-    constexpr int smem = tc::SmemLayout<BN, STAGES>::kBytes;
+    constexpr int smem = tc::SmemLayout<BN, STAGES, KP>::kBytes;
     CUtensorMap ma_x, ma_h, mw_x, mw_h;          // each CTA of the pair fetches its 128 rows of A, half of the W tile rows
     ASR_TRY(tc::make_map(&ma_x, a_lo, M, K, tc::BM, epi.lda, false));
     ASR_TRY(tc::make_map(&ma_h, a_hi, M, K, tc::BM, epi.lda, true));
@@ -599,7 +690,7 @@ static int launch_pair(const hi_t* a_hi, const float* a_lo, const hi_t* w_hi, co
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.blockDim = dim3(192);
+    cfg.blockDim = dim3(tc::SmemLayout<BN, STAGES, KP>::kThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cfg.attrs = at;

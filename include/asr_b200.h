@@ -248,8 +248,11 @@ int asr_test_gemm(asr_handle* h, const float* d_A, const float* d_W, const float
                   int M, int N, int K, void* stream);
 
 /* Tuning aid: average ms per launch of the tensor-core GEMM engine on an [M,K] x [N,K]^T problem
- * (operands already split, CUDA events on `stream`, `iters` timed launches after 2 warm-ups). */
-int asr_bench_gemm(asr_handle* h, int M, int N, int K, int iters, float* ms_out, void* stream);
+ * (operands already split, CUDA events on `stream`, `iters` timed launches after 2 warm-ups).
+ * topk_slots = 0: bias epilogue storing C; 2 / 8 / 16 / 32 (N must be 5004): the vocabulary epilogue
+ * (log-sum-exp partials + top candidates per tile, no logits stored). */
+int asr_bench_gemm(asr_handle* h, int M, int N, int K, int iters, int topk_slots, float* ms_out,
+                   void* stream);
 
 /* Number of kernels this library launched since the handle was created / last reset. */
 int64_t asr_launch_count(asr_handle* h, int reset);

@@ -585,6 +585,7 @@ def beam_decode(weights, k, feats, lens, int2word=None, second_pass=False, lm_mo
             gaps = srt[:, :-1] - srt[:, 1:]
             used = torch.arange(c2).view(1, -1) <= deepest.view(-1, 1)
             trace.setdefault("min_margin", []).append(float(gaps[used].min()))
+            trace.setdefault("next_score", []).append(srt[:, c2].clone())     # best candidate left out of the 2k
             trace.setdefault("margin_utt", []).append(
                 torch.where(used, gaps, torch.full_like(gaps, float("inf"))).min(dim=1)[0])
         # finished set: EOS among the top-k candidates (model.py:876-889)

@@ -388,14 +388,19 @@ def check_graph_replay(B=6, k=4, n=40000, seed=700):
     return {"replay_eq_eager": same, "of": len(batches), "batches_differ": distinct}
 
 
-NEAR_TIE = 2e-6     # a decision may differ from the oracle's only where the oracle's own margin is below this ...
+NEAR_TIE = 2e-6     # a candidate order may differ from the reference's only where the reference's own gap is below this ...
+NOISE_RTOL = 1e-4   # ... or below twice the measured distance between the two implementations' scores at that step
 
 
-def near_tie(gap, score):
-    """... or below 4 ulp of the fp32 scores being compared: beam scores are un-normalised sums of log-probs
-    (model.py:836) and reach |s| ~ 300 with the test weights, where one fp32 ulp is 3e-5 - the reference's own
-    fp32 sums cannot order two candidates closer than that."""
-    return gap < max(NEAR_TIE, 4.0 * float(np.spacing(np.float32(abs(score)))))
+def near_tie(gap, score, noise):
+    """Is a differing decision a proven near-tie?  Beam scores are un-normalised fp32 sums of log-probs
+    (model.py:836) that reach |s| ~ 50-300 with the test weights, and the logits behind them are only specified to
+    1e-3 absolute (BASELINE.json north_star).  Two candidates whose reference scores are `gap` apart can legitimately
+    swap when each implementation's scores carry an error of gap / 2.  `noise` is the largest |score_cuda -
+    score_oracle| over the ranks of the same step on which both still agree: the swap is excused only if
+    gap <= 2 * noise AND that noise itself is small (<= 1e-4 relative to the score, ten times tighter than the
+    1e-3 relative tolerance on final scores) - or if the gap is below 2e-6 outright."""
+    return gap < NEAR_TIE or (gap <= 2.0 * noise and noise <= NOISE_RTOL * max(1.0, abs(score)))
 
 
 def _rel(a, b):
@@ -413,8 +418,9 @@ def compare_with_oracle(m, weights, pcms, k, picks=None, lm_seed=None, lm_weight
     picks alone with the batch's stop step passed in (`batch_stop_step`) and the check verifies that this
     stop step is consistent with every pick (its rank-0 </s> came no later).
 
-    A difference is tolerated ONLY as a proven near-tie: the oracle's own decision margin at the first
-    differing step must be < NEAR_TIE (fp32 noise); it is reported in `flips`.  Anything else lands in `bad`."""
+    A difference is tolerated ONLY as a proven near-tie (near_tie(): the oracle's own gap at the first differing
+    rank is within twice the measured score noise of that step, or < 2e-6); it is reported in `flips` with the
+    step, rank, gap, score and noise.  Anything else lands in `bad`."""
     from chinese_asr_b200.gpd import gpd
     from chinese_asr_b200.lm import NGramLM
     w2i, i2w = vocab()
@@ -477,7 +483,9 @@ def compare_with_oracle(m, weights, pcms, k, picks=None, lm_seed=None, lm_weight
                     r0 = int(bad_r[0]) if len(bad_r) else -1          # -1: candidates agree, back-pointers differ
                     # gap between the oracle's scores at the first differing rank and its neighbours, the score
                     # there, and how far the two implementations' scores are apart on the ranks that still agree
-                    gap = float(min(abs(o_sc[r0] - o_sc[r0 + 1]), abs(o_sc[r0 - 1] - o_sc[r0]) if r0 > 0 else np.inf)) if r0 >= 0 else 0.0
+                    o_ext = np.append(o_sc, float(tr["next_score"][s][j]))      # + the best candidate left out of the 2k
+                    nb_ = [abs(o_ext[r0] - o_ext[x]) for x in (r0 - 1, r0 + 1) if 0 <= x <= K]
+                    gap = float(min(nb_)) if r0 >= 0 else 0.0
                     noise = float(np.max(np.abs(t["cand_scores"][s, i, :max(r0, 1)] - o_sc[:max(r0, 1)])))
                     div = (s, float(tr["margin_utt"][s][j]), r0, gap, float(o_sc[max(r0, 0)]), noise)
                     break
@@ -485,7 +493,8 @@ def compare_with_oracle(m, weights, pcms, k, picks=None, lm_seed=None, lm_weight
                                                 float(np.max(np.abs(t["cand_scores"][s, i, :used] - o_sc[:used])
                                                              / np.maximum(1.0, np.abs(o_sc[:used])))))
             if div is not None:
-                (res["flips"] if near_tie(div[3], div[4]) else res["bad"]).append(("diverged", i) + div)
+                (res["flips"] if near_tie(div[3], div[4], div[5]) else res["bad"]).append(
+                    dict(utt=i, step=div[0], oracle_margin=div[1], rank=div[2], gap=div[3], score=div[4], noise=div[5]))
                 continue
             o_nb = o["nbest"].get(j, [])
             g_nb = nbest[i]
@@ -706,126 +715,29 @@ def check_wide_recurrence(B, k=4, group=40, seed=5200, n_picks=16):
     tok, ln, sc = m.transcribe(pcm, off, bw=k)
     stop = m.decode_info()["stopped_at"]
     same = compared = 0
+    score_rel, differ = 0.0, []
     for g0 in range(0, B, group):
         g1 = min(B, g0 + group)
         t1, l1, s1 = m.transcribe(pcm[off[g0]:off[g1]], off[g0:g1 + 1] - off[g0], bw=k)
         if m.decode_info()["stopped_at"] != stop:
             continue            # utterances interact through the early stop: only equal stop steps are comparable
         compared += g1 - g0
-        same += int(sum(int(l1[i] == ln[g0 + i] and (t1[i] == tok[g0 + i]).all() and s1[i] == sc[g0 + i])
-                        for i in range(g1 - g0)))
-    res.update({"same": same, "of": compared, "len_spread": int(ln.max() - ln.min())})
+        for i in range(g1 - g0):
+            if l1[i] == ln[g0 + i] and (t1[i] == tok[g0 + i]).all():
+                same += 1
+                score_rel = max(score_rel, _rel(s1[i], sc[g0 + i]))
+            else:
+                differ.append(g0 + i)
+    # Small batches take the frame-split attention kernel and other GEMM tile shapes, so scores differ in the last
+    # bits and a near-tie may resolve differently: every utterance whose tokens differ is checked against the oracle
+    # in BOTH batchings (exact, or a proven near-tie) - never waved through.
+    bad = []
+    for i in differ:
+        g0 = (i // group) * group
+        g1 = min(B, g0 + group)
+        big = compare_with_oracle(m, weights, pcms, k, picks=[i], label=f"wide recurrence B={B}, differing utt {i}")
+        small = compare_with_oracle(m, weights, pcms[g0:g1], k, picks=[i - g0], label=f"batch of {g1 - g0}, utt {i}")
+        bad += big["bad"] + small["bad"]
+    res.update({"same": same, "of": compared, "differ": differ, "differ_bad": bad, "self_score_rel": score_rel,
+                "len_spread": int(ln.max() - ln.min())})
     return res
-
-
-# ---------------------------------------------------------------------------------------------
-# boundary: lm_model duck typing (model.py:749-763, main.py:79-85) and ARPA vocabularies
-class ScoreOnlyLM:
-    """What the reference is handed: any object with .score(sentence, bos=True) (a kenlm.LanguageModel)."""
-
-    def __init__(self, lm):
-        self._lm = lm
-        self.calls = 0
-
-    def score(self, sentence, bos=True):
-        self.calls += 1
-        return self._lm.score(sentence, bos=bos)
-
-
-def check_host_lm(cname="beam8lm"):
-    """An lm_model offering only .score() is rescored on the host from asr_beam_nbest with the rule of
-    model.py:749-763 and must pick exactly what the device tables pick (and what the reference picked)."""
-    from chinese_asr_b200.lm import NGramLM
-    g = load_golden()
-    cs = CASES[cname]
-    weights = case_weights(cs)
-    m = get_model(wkey(cs), weights)
-    w2i, i2w = vocab()
-    _, feats, lens = case_inputs(cs)
-    lm_o = O.NGramLM(seed=cs["lm"], word2int=w2i)
-    kw = dict(second_pass=True, lm_weight=cs["lm_weight"], length_weight=cs["length_weight"])
-    dev = m.eval_one_batch_with_beam(m.device, cs["bw"], feats, lens, None, i2w, lm_model=NGramLM(lm_o.tables(), w2i), **kw)
-    plain = ScoreOnlyLM(lm_o)
-    host = m.eval_one_batch_with_beam(m.device, cs["bw"], feats, lens, None, i2w, lm_model=plain, **kw)
-    none = m.eval_one_batch_with_beam(m.device, cs["bw"], feats, lens, None, i2w, second_pass=False)
-    off = np.zeros(len(feats) + 1, dtype=np.int64)
-    pcms = [O.synth_pcm(s_, n) for s_, n in zip(cs["seeds"], cs["nsamp"])]
-    off[1:] = np.cumsum([len(p) for p in pcms])
-    fused = m.transcribe(np.concatenate(pcms), off, bw=cs["bw"], lm_model=ScoreOnlyLM(lm_o), int2word=i2w, **kw)
-    nb = m.beam_nbest(len(feats))
-    return {"host_eq_device": int(list(host.pred_text) == list(dev.pred_text) and list(host.score) == list(dev.score)),
-            "host_eq_ref": int(list(host.pred_text) == list(g[cname + "_text"])),
-            "fused_eq_device": int(fused[3] == list(dev.pred_text)),
-            "lm_changes_a_pick": int(list(none.pred_text) != list(dev.pred_text)),
-            "lm_calls": plain.calls, "ref_lm_calls": int(len(g[cname + "_lm_seen"])),
-            "nbest_counts": [len(x) for x in nb]}
-
-
-ARPA = """\\data\\
-ngram 1={n1}
-ngram 2={n2}
-ngram 3={n3}
-
-\\1-grams:
-{uni}
-
-\\2-grams:
-{bi}
-
-\\3-grams:
-{tri}
-
-\\end\\
-"""
-
-
-def arpa_backoff_score(grams, sentence):
-    """kenlm's .score(sentence, bos=True, eos=True) restated on the ARPA entries themselves (dicts keyed by word
-    tuples -> (log10 p, backoff)); words without a unigram score as <unk>."""
-    def p(ctx, w):
-        if not ctx:
-            return grams[1][(w,)][0]
-        key = tuple(ctx) + (w,)
-        if key in grams[len(key)]:
-            return grams[len(key)][key][0]
-        return grams[len(ctx)].get(tuple(ctx), (0.0, 0.0))[1] + p(ctx[1:], w)
-    ctx, total = ["<s>"], 0.0
-    for w in sentence.split() + ["</s>"]:
-        w = w if (w,) in grams[1] else "<unk>"
-        total += p(ctx[-2:], w)
-        ctx.append(w)
-    return total
-
-
-def check_arpa_oov():
-    """ARPA file whose vocabulary differs from dict.pkl in both directions: a word dict.pkl lacks
-    must not overwrite <unk>; a dict.pkl token the ARPA lacks scores as <unk> in every n-gram position."""
-    import tempfile
-    from chinese_asr_b200.lm import NGramLM
-    w2i, i2w = vocab()
-    a, b, c, d, miss = (i2w[i] for i in (10, 11, 12, 13, 14))        # `miss` has no unigram in the ARPA
-    grams = {1: {("<unk>",): (-2.5, -0.3), ("<s>",): (-99.0, -0.4), ("</s>",): (-1.1, 0.0), (a,): (-1.3, -0.2),
-                 (b,): (-1.6, -0.25), (c,): (-1.9, -0.1), (d,): (-2.1, 0.0), ("ZZZ",): (-0.7, -0.9)},
-             2: {("<s>", a): (-0.5, -0.15), (a, b): (-0.6, -0.05), (b, "<unk>"): (-0.9, -0.07), ("<unk>", c): (-0.8, -0.02),
-                 (a, "ZZZ"): (-0.1, -0.6), ("ZZZ", b): (-0.2, 0.0), (c, "</s>"): (-0.3, 0.0)},
-             3: {("<s>", a, b): (-0.25, 0.0), (a, b, "<unk>"): (-0.35, 0.0), (b, "<unk>", c): (-0.45, 0.0),
-                 (a, "ZZZ", b): (-0.05, 0.0)}}
-    fmt = lambda n: "\n".join(f"{v[0]}\t{' '.join(k)}" + (f"\t{v[1]}" if n < 3 else "") for k, v in grams[n].items())
-    text = ARPA.format(n1=len(grams[1]), n2=len(grams[2]), n3=len(grams[3]), uni=fmt(1), bi=fmt(2), tri=fmt(3))
-    with tempfile.NamedTemporaryFile("w", suffix=".arpa", delete=False, encoding="utf-8") as f:
-        f.write(text)
-    lm = NGramLM.from_arpa(f.name, w2i)
-    os.unlink(f.name)
-    m = get_model((1234, "plain", None), O.make_weights(1234, "plain"))
-    m._lm = None
-    m.set_lm(lm)
-    sents = [f"{a} {b} {miss} {c}", f"{miss}", f"{a} {b}", f"{d} {miss} {miss} {a}", f"{c}", "", f"{a} {b} {i2w[3]} {c}",
-             f"{b} {miss} {c} {a} {b} {miss}"]
-    dev = [lm.score(s_) for s_ in sents]
-    ref = [arpa_backoff_score({n: {k: v for k, v in gs.items() if "ZZZ" not in k} for n, gs in grams.items()}, s_)
-           for s_ in sents]
-    t = lm.tables()
-    m._lm = None                       # the next caller uploads its own tables
-    return {"max_abs": float(np.max(np.abs(np.array(dev) - np.array(ref)))),
-            "unk_kept": int(t["uni_logp"][3] == np.float32(-2.5) and t["uni_bo"][3] == np.float32(-0.3)),
-            "missing_maps_to_unk": int(t["id_map"][14] == 3 and t["id_map"][10] == 10)}

@@ -1,12 +1,12 @@
-# ncu evidence for profiles/: launch list of bench.py + one --set full capture of a pass (encoder + 2 decoder steps).
-# The .ncu-rep stays on the box (/tmp: gpurun_out/ is capped at 64 MiB); its raw page comes back as CSV.
+# ncu --set full captures of the decoder-step kernels at the bench workload (512 x 10 s, bw=8), one launch each,
+# after the same command exited 0 without ncu.  Usage (on the GPU box): bash tools/prof_cmd.sh <tag>
+TAG=${1:-r02}
 set -x
-rm -f gpurun_out/*.ncu-rep
-python bench.py --steps 2 --warmup 3 --no-cpu-baseline --pipeline 1 > gpurun_out/plain_bench.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches_r01.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --pipeline 1 > gpurun_out/ncu_bench.log 2>&1
-echo "launch list rc=$?"
-python tools/prof_step.py 512 8 1 > gpurun_out/plain_prof.log 2>&1 &&
-ncu --set full --clock-control none --launch-skip 258 --launch-count 28 -f -o /tmp/prof_r01_all python tools/prof_step.py 512 8 1 > gpurun_out/ncu_prof.log 2>&1
-echo "set full rc=$?"
-ncu -i /tmp/prof_r01_all.ncu-rep --page raw --csv > gpurun_out/prof_r01_all_raw.csv 2>/dev/null
-du -sh gpurun_out; ls -la gpurun_out/ | tail -12
+python tools/prof_step.py 512 8 1 > gpurun_out/plain_prof.log 2>&1 || exit 1
+for spec in "vocab gemm_split_pair_kernel 11" "cell gemm_split_pair_kernel 9" "merge beam_merge_kernel 1" "attn attention_stream_kernel 1"; do
+    set -- $spec
+    ncu --set full --clock-control none --import-source on -k regex:$2 -s $3 -c 1 -f -o gpurun_out/prof_${TAG}_$1 \
+        python tools/prof_step.py 512 8 1 > gpurun_out/ncu_$1.log 2>&1
+    echo "$1 rc=$?"
+done
+ls -la gpurun_out/*.ncu-rep
