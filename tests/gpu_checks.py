@@ -741,3 +741,116 @@ def check_wide_recurrence(B, k=4, group=40, seed=5200, n_picks=16):
     res.update({"same": same, "of": compared, "differ": differ, "differ_bad": bad, "self_score_rel": score_rel,
                 "len_spread": int(ln.max() - ln.min())})
     return res
+
+
+# ---------------------------------------------------------------------------------------------
+# boundary: lm_model duck typing (model.py:749-763, main.py:79-85) and ARPA vocabularies
+class ScoreOnlyLM:
+    """What the reference is handed: any object with .score(sentence, bos=True) (a kenlm.LanguageModel)."""
+
+    def __init__(self, lm):
+        self._lm = lm
+        self.calls = 0
+
+    def score(self, sentence, bos=True):
+        self.calls += 1
+        return self._lm.score(sentence, bos=bos)
+
+
+def check_host_lm(cname="beam8lm"):
+    """An lm_model offering only .score() is rescored on the host from asr_beam_nbest with the rule of
+    model.py:749-763 and must pick exactly what the device tables pick (and what the reference picked)."""
+    from chinese_asr_b200.lm import NGramLM
+    g = load_golden()
+    cs = CASES[cname]
+    weights = case_weights(cs)
+    m = get_model(wkey(cs), weights)
+    w2i, i2w = vocab()
+    _, feats, lens = case_inputs(cs)
+    lm_o = O.NGramLM(seed=cs["lm"], word2int=w2i)
+    kw = dict(second_pass=True, lm_weight=cs["lm_weight"], length_weight=cs["length_weight"])
+    dev = m.eval_one_batch_with_beam(m.device, cs["bw"], feats, lens, None, i2w, lm_model=NGramLM(lm_o.tables(), w2i), **kw)
+    plain = ScoreOnlyLM(lm_o)
+    host = m.eval_one_batch_with_beam(m.device, cs["bw"], feats, lens, None, i2w, lm_model=plain, **kw)
+    none = m.eval_one_batch_with_beam(m.device, cs["bw"], feats, lens, None, i2w, second_pass=False)
+    off = np.zeros(len(feats) + 1, dtype=np.int64)
+    pcms = [O.synth_pcm(s_, n) for s_, n in zip(cs["seeds"], cs["nsamp"])]
+    off[1:] = np.cumsum([len(p) for p in pcms])
+    fused = m.transcribe(np.concatenate(pcms), off, bw=cs["bw"], lm_model=ScoreOnlyLM(lm_o), int2word=i2w, **kw)
+    nb = m.beam_nbest(len(feats))
+    return {"host_eq_device": int(list(host.pred_text) == list(dev.pred_text) and list(host.score) == list(dev.score)),
+            "host_eq_ref": int(list(host.pred_text) == list(g[cname + "_text"])),
+            "fused_eq_device": int(fused[3] == list(dev.pred_text)),
+            "lm_changes_a_pick": int(list(none.pred_text) != list(dev.pred_text)),
+            "lm_calls": plain.calls, "ref_lm_calls": int(len(g[cname + "_lm_seen"])),
+            "nbest_counts": [len(x) for x in nb]}
+
+
+ARPA = """\\data\\
+ngram 1={n1}
+ngram 2={n2}
+ngram 3={n3}
+
+\\1-grams:
+{uni}
+
+\\2-grams:
+{bi}
+
+\\3-grams:
+{tri}
+
+\\end\\
+"""
+
+
+def arpa_backoff_score(grams, sentence):
+    """kenlm's .score(sentence, bos=True, eos=True) restated on the ARPA entries themselves (dicts keyed by word
+    tuples -> (log10 p, backoff)); words without a unigram score as <unk>."""
+    def p(ctx, w):
+        if not ctx:
+            return grams[1][(w,)][0]
+        key = tuple(ctx) + (w,)
+        if key in grams[len(key)]:
+            return grams[len(key)][key][0]
+        return grams[len(ctx)].get(tuple(ctx), (0.0, 0.0))[1] + p(ctx[1:], w)
+    ctx, total = ["<s>"], 0.0
+    for w in sentence.split() + ["</s>"]:
+        w = w if (w,) in grams[1] else "<unk>"
+        total += p(ctx[-2:], w)
+        ctx.append(w)
+    return total
+
+
+def check_arpa_oov():
+    """ARPA file whose vocabulary differs from dict.pkl in both directions: a word dict.pkl lacks
+    must not overwrite <unk>; a dict.pkl token the ARPA lacks scores as <unk> in every n-gram position."""
+    import tempfile
+    from chinese_asr_b200.lm import NGramLM
+    w2i, i2w = vocab()
+    a, b, c, d, miss = (i2w[i] for i in (10, 11, 12, 13, 14))        # `miss` has no unigram in the ARPA
+    grams = {1: {("<unk>",): (-2.5, -0.3), ("<s>",): (-99.0, -0.4), ("</s>",): (-1.1, 0.0), (a,): (-1.3, -0.2),
+                 (b,): (-1.6, -0.25), (c,): (-1.9, -0.1), (d,): (-2.1, 0.0), ("ZZZ",): (-0.7, -0.9)},
+             2: {("<s>", a): (-0.5, -0.15), (a, b): (-0.6, -0.05), (b, "<unk>"): (-0.9, -0.07), ("<unk>", c): (-0.8, -0.02),
+                 (a, "ZZZ"): (-0.1, -0.6), ("ZZZ", b): (-0.2, 0.0), (c, "</s>"): (-0.3, 0.0)},
+             3: {("<s>", a, b): (-0.25, 0.0), (a, b, "<unk>"): (-0.35, 0.0), (b, "<unk>", c): (-0.45, 0.0),
+                 (a, "ZZZ", b): (-0.05, 0.0)}}
+    fmt = lambda n: "\n".join(f"{v[0]}\t{' '.join(k)}" + (f"\t{v[1]}" if n < 3 else "") for k, v in grams[n].items())
+    text = ARPA.format(n1=len(grams[1]), n2=len(grams[2]), n3=len(grams[3]), uni=fmt(1), bi=fmt(2), tri=fmt(3))
+    with tempfile.NamedTemporaryFile("w", suffix=".arpa", delete=False, encoding="utf-8") as f:
+        f.write(text)
+    lm = NGramLM.from_arpa(f.name, w2i)
+    os.unlink(f.name)
+    m = get_model((1234, "plain", None), O.make_weights(1234, "plain"))
+    m._lm = None
+    m.set_lm(lm)
+    sents = [f"{a} {b} {miss} {c}", f"{miss}", f"{a} {b}", f"{d} {miss} {miss} {a}", f"{c}", "", f"{a} {b} {i2w[3]} {c}",
+             f"{b} {miss} {c} {a} {b} {miss}"]
+    dev = [lm.score(s_) for s_ in sents]
+    ref = [arpa_backoff_score({n: {k: v for k, v in gs.items() if "ZZZ" not in k} for n, gs in grams.items()}, s_)
+           for s_ in sents]
+    t = lm.tables()
+    m._lm = None                       # the next caller uploads its own tables
+    return {"max_abs": float(np.max(np.abs(np.array(dev) - np.array(ref)))),
+            "unk_kept": int(t["uni_logp"][3] == np.float32(-2.5) and t["uni_bo"][3] == np.float32(-0.3)),
+            "missing_maps_to_unk": int(t["id_map"][14] == 3 and t["id_map"][10] == 10)}
