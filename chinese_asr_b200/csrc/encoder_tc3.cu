@@ -1,7 +1,7 @@
-// Tensor-core LSTM recurrence, weights fully resident in TENSOR MEMORY (rec_mode 2).
+// Tensor-core LSTM recurrence, weights fully resident in TENSOR MEMORY.
 //
-// encoder_tc.cu keeps W_hi in shared memory and re-reads its 128 KB through the UMMA operand path
-// every step (measured: the 64 MMAs of a step are bound by ~64 B/clk of shared-memory operand
+// An earlier engine kept W_hi in shared memory and re-read its 128 KB through the UMMA operand path
+// every step (measured: the 64 MMAs of a step were bound by ~64 B/clk of shared-memory operand
 // fetch, ~3.9k cycles).  Here the whole recurrent weight slice of a CTA lives in TMEM:
 //     columns [  0,128) : W_hi  = fp16(W_hh slice), 2 per column             128 lanes x 256 fp16
 //     columns [128,384) : W cross, per 8 values of k [8 x bf16(w) | 8 x bf16(w - w_hi)]   (4 bytes per k)
@@ -13,7 +13,7 @@
 //     D += W_x  (TMEM, bf16) * [bf16(h_lo) | bf16(h)]^T        32 x (K = 16 = 8 values of k): w*h_lo + w_lo*h
 // (the tf32 form issued 80: an MMA costs ~65 cycles here whatever its shape).  The cross terms are 2^-11
 // of the product, which bf16's 2^-9 relative accuracy carries to ~2^-20.
-// Exchange of h_{t+1}: as in encoder_tc.cu - each CTA writes the image of its 32-unit slice
+// Exchange of h_{t+1}: each CTA writes the image of its 32-unit slice
 // ([cross | hi] rows, already in the swizzled UMMA layouts) to global staging and multicasts it
 // with one cp.async.bulk into the tiles of all 8 CTAs; mbarriers only, no cluster barrier per step.
 #include <cooperative_groups.h>
@@ -31,8 +31,28 @@ using namespace tcx;
 
 namespace rec3 {
 
-__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
-__device__ __forceinline__ float tanh_f(float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); }
+__device__ __forceinline__ float rcp_f(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+// One LSTM cell (nn.LSTM: c' = s(f) c + s(i) tanh(g), h' = s(o) tanh(c')) on ex2.approx / rcp.approx.  The gate
+// phase of a recurrence step is paced by the MUFU pipe (16 lanes per clock), so reciprocals are shared:
+// 1/A and 1/G from one rcp(A G), and s(o) tanh(c') = (C - 2) / (O C) with C = e^(2c') + 1 from one rcp(O C) -
+// 5 ex2 + 3 rcp per cell instead of 5 + 5.  Arguments are clamped to +-40 (s, tanh are saturated to fp32 there) so
+// that no product of two denominators overflows.  Relative error ~3 ulp per factor, like the unshared form.
+__device__ __forceinline__ void lstm_cell(float gi, float gf, float gg, float go, float c_prev, float& c, float& h) {
+    const float A = 1.f + __expf(-fmaxf(gi, -40.f));
+    const float Bf = 1.f + __expf(-fmaxf(gf, -40.f));
+    const float G = __expf(2.f * fminf(gg, 20.f)) + 1.f;
+    const float O = 1.f + __expf(-fmaxf(go, -40.f));
+    const float r = rcp_f(A * G);
+    const float si = r * G;                       // 1 / A
+    const float tg = 1.f - 2.f * (r * A);         // 1 - 2 / G
+    c = rcp_f(Bf) * c_prev + si * tg;
+    const float C = __expf(2.f * fminf(c, 20.f)) + 1.f;
+    h = (C - 2.f) * rcp_f(O * C);
+}
 
 __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
     asm volatile(
@@ -278,29 +298,30 @@ lstm_rec_tc3_kernel(Params p) {
     float yv[P];
 #pragma unroll
     for (int q = 0; q < P; ++q) yv[q] = 0.f;
-    // layer output of one step: y (+ residual), and optionally its operand split for the next GEMM.
-    // Called one step late (after the next step's MMAs are issued) so that it never delays them.
+    // layer output of one step: y = h + residual input (util.py:1284-1291), and optionally its operand split
+    // for the next GEMM.  Called one step late (after the next step's MMAs are issued) so that it never delays them.
     auto store_outputs = [&](int t, int row_t, int n_act) {
 #pragma unroll
         for (int q = 0; q < P; ++q) {
             const int i = col0 + 4 * q;
             const bool act = i < n_act;
+            const float y = yv[q];
             // operand split for the consuming GEMM: the lane 4 away holds the neighbouring unit of the
             // same row; even units pack the two residuals, odd units the two values (bf16 pairs)
-            const float hi = hi_part(yv[q]);
-            const float lo = yv[q] - hi;
+            const float hi = hi_part(y);
+            const float lo = y - hi;
             const float lo_n = __shfl_xor_sync(0xffffffffu, lo, 4);
-            const float y_n = __shfl_xor_sync(0xffffffffu, yv[q], 4);
+            const float y_n = __shfl_xor_sync(0xffffffffu, y, 4);
             if (act) {
                 const size_t row = (size_t)(row_t + i);
                 const size_t urow = p.y_utt ? (size_t)(p.uoff[r0 + i] + t) : 0;
-                if (p.y_packed) p.y_packed[row * kEnc + ocol] = yv[q];
-                if (p.y_utt) p.y_utt[urow * kEnc + ocol] = yv[q];
+                if (p.y_packed) p.y_packed[row * kEnc + ocol] = y;
+                if (p.y_utt) p.y_utt[urow * kEnc + ocol] = y;
                 if (p.y_hi) {
                     const size_t srow = p.y_utt ? urow : row;      // last layer: rows as `enc`
                     p.y_hi[srow * kEnc + ocol] = __float2half_rn(hi);
                     const bool odd = (ocol & 1) != 0;
-                    const __nv_bfloat162 pk = odd ? __floats2bfloat162_rn(y_n, yv[q]) : __floats2bfloat162_rn(lo, lo_n);
+                    const __nv_bfloat162 pk = odd ? __floats2bfloat162_rn(y_n, y) : __floats2bfloat162_rn(lo, lo_n);
                     // block of 8 floats -> 8 words: words 0-3 residual pairs, words 4-7 value pairs
                     uint32_t* blk = p.y_cross + srow * kEnc + (size_t)(ocol & ~7);
                     blk[(odd ? 4 : 0) + ((ocol & 7) >> 1)] = *reinterpret_cast<const uint32_t*>(&pk);
@@ -317,16 +338,19 @@ lstm_rec_tc3_kernel(Params p) {
                 if (p.dbg && blockIdx.x == 0) p.dbg[s * 8 + 0] = clock64();
                 const uint64_t dX0 = kmajor_sw128_desc(t_base);
                 const uint64_t dHi0 = kmajor_sw64_desc(t_base + kX);
-                // every MMA consumes 8 TMEM columns of A and 32 bytes of a B row
-#pragma unroll
-                for (int kh = 0; kh < 16; ++kh) {        // 16 values of k each
-                    const uint64_t adv = (uint64_t)(((kh >> 1) * kSlab + (kh & 1) * 32) >> 4);
-                    umma_bf16_ts(tmem_d, tmem_base + (uint32_t)(8 * kh), dHi0 + adv, idesc_h, kh > 0 ? 1u : 0u);
-                }
+                // every MMA consumes 8 TMEM columns of A and 32 bytes of a B row.  The cross terms go first: the
+                // tensor core truncates every accumulation, and while the accumulator only holds the 2^-11-sized
+                // cross sum those 32 truncations are 2^-11 smaller; only the 16 hi MMAs truncate at full magnitude
+                // (measured on the GEMM engine: 3x less error than interleaving, gemm_tc.cu).
 #pragma unroll
                 for (int kb = 0; kb < 32; ++kb) {        // 8 values of k each: w * h_lo + w_lo * h
                     const uint64_t adv = (uint64_t)(((kb >> 2) * kSlab + (kb & 3) * 32) >> 4);
-                    umma_bf16_ts(tmem_d, tmem_ax + (uint32_t)(8 * kb), dX0 + adv, idesc_b, 1u);
+                    umma_bf16_ts(tmem_d, tmem_ax + (uint32_t)(8 * kb), dX0 + adv, idesc_b, kb > 0 ? 1u : 0u);
+                }
+#pragma unroll
+                for (int kh = 0; kh < 16; ++kh) {        // 16 values of k each
+                    const uint64_t adv = (uint64_t)(((kh >> 1) * kSlab + (kh & 1) * 32) >> 4);
+                    umma_bf16_ts(tmem_d, tmem_base + (uint32_t)(8 * kh), dHi0 + adv, idesc_h, 1u);
                 }
                 umma_commit_mc(mma_done, (uint16_t)0xFF);
                 if (p.dbg && blockIdx.x == 0) p.dbg[s * 8 + 1] = clock64();
@@ -341,6 +365,9 @@ lstm_rec_tc3_kernel(Params p) {
 
         if (warp < kIssueWarp) {
         // gate warps: the issue warp above does nothing else, so it never arrives late at the step's barrier
+        // the stores of the previous step first (registers only), then this step's loads: their latency is
+        // covered by the MMAs in flight (measured: loading the residual inside the deferred store instead makes
+        // the gate warps arrive ~500 cycles late at mma_done)
         if (s > 0) store_outputs(prev_t, prev_row_t, prev_nact);
         float xi[P], xf[P], xgg[P], xo[P], xres[P];
 #pragma unroll
@@ -384,8 +411,8 @@ lstm_rec_tc3_kernel(Params p) {
                     const float gf = xf[q] + df;
                     const float gg = xgg[q] + dg;
                     const float go = xo[q] + dO;
-                    const float c = sigmoid_f(gf) * c_reg[q] + sigmoid_f(gi) * tanh_f(gg);
-                    const float hh = sigmoid_f(go) * tanh_f(c);
+                    float c, hh;
+                    lstm_cell(gi, gf, gg, go, c_reg[q], c, hh);
                     c_reg[q] = c;
                     h_reg[q] = hh;
                     const float hi = hi_part(hh);
