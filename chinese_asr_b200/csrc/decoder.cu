@@ -133,8 +133,6 @@ struct AttnParams {
     const int* order;       // [B]
     const int* ctrl;
     int k, S, B, Lmax, sc_ld;
-    long long* trace;       // optional clock64 timeline of CTA 0 (ASR_B200_ATT_TRACE)
-    int dbg;                // timing experiments only: 1 = producers skip the score math, 2 = consumers skip the FMAs
     long long score_ld;
 };
 
@@ -479,7 +477,28 @@ __device__ __forceinline__ void att_bulk_g2s(void* dst, const void* src, uint32_
 }
 
 constexpr int kAttRows = 8;        // encoder rows per ring stage (16 KB)
-constexpr int kAttStages = 3;
+constexpr int kAttStages = 2;      // the consumers drain a stage much faster than HBM delivers one: two keep a copy in flight
+constexpr int kAttBufs = 4;        // numerator chunks the producers may run ahead of the consumers
+
+// per-lane asynchronous copy of 16 bytes global -> shared (LDGSTS): the producers' key prefetch, no registers held
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Shared memory of the streaming kernel (floats): encoder ring | per-warp key ring (aliased by the queries during
+// the prologue) | numerator buffers | per-buffer rescale factors | chunk maxima | sums | mbarriers
+template <int K>
+struct AttSmem {
+    static constexpr int kRing = kAttStages * kAttRows * kEnc;
+    static constexpr int kKeys = 4 * (kAttChunk / 4) * kAtt;            // 4 producer warps x 8 frames x 128
+    static_assert(K * kAtt <= kKeys, "queries alias the key ring");
+    static constexpr int kP = kAttBufs * K * kAttChunk;
+    static constexpr int kSmall = kAttBufs * K + 2 * 4 * K + 4 * K;
+    static constexpr size_t kBytes = sizeof(float) * (kRing + kKeys + kP + kSmall) + sizeof(uint64_t) * 2 * kAttStages + 16;
+};
 
 template <int K>
 __global__ void __launch_bounds__(256, K <= 8 ? 4 : 2)
@@ -488,15 +507,14 @@ attention_stream_kernel(AttnParams p) {
     constexpr int C = kAttChunk;
     constexpr int kGroup = 32 / K;                 // lanes that end up holding the same beam
     constexpr int FPW = C / 4;                     // frames per producer warp per chunk
-    const bool tr = p.trace && blockIdx.x == 0;
-    if (tr && threadIdx.x == 0) p.trace[0] = clock64();
+    using S = AttSmem<K>;
     extern __shared__ __align__(128) uint8_t att_smem[];
-    // ring of encoder rows | numerators (aliased by the queries during the prologue) | small state
     float* s_ring = reinterpret_cast<float*>(att_smem);                          // [stages][8][512]
-    float* s_p = s_ring + kAttStages * kAttRows * kEnc;                           // [2][K][C]
-    float* s_q = s_p + 2 * K * C;                                                 // [K][128]
-    float* s_scale = s_q + K * kAtt;                                             // [2][K]
-    float* s_wmax = s_scale + 2 * K;                                              // [2][4][K]
+    float* s_keys = s_ring + S::kRing;                                            // [4 warps][FPW][128]
+    float* s_q = s_keys;                                                          // [K][128], prologue only
+    float* s_p = s_keys + S::kKeys;                                               // [bufs][K][C]
+    float* s_scale = s_p + S::kP;                                                 // [bufs][K]
+    float* s_wmax = s_scale + kAttBufs * K;                                       // [2][4][K]
     float* s_wsum = s_wmax + 2 * 4 * K;                                           // [4][K]
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_wsum + 4 * K);                 // full[stages], empty[stages]
 
@@ -509,6 +527,8 @@ attention_stream_kernel(AttnParams p) {
     const int nstage = (nl + kAttRows - 1) / kAttRows;
     uint64_t* full_e = bars;
     uint64_t* empty_e = bars + kAttStages;
+    // named barriers: 1 + b: numerators of buffer b published (producers arrive, consumers sync);
+    // 1 + kAttBufs + b: buffer b drained (consumers arrive, producers sync); 1 + 2 kAttBufs: producers only
 
     bool q_big = false;
     for (int i = tid; i < k * kAtt; i += 256) {
@@ -521,7 +541,6 @@ attention_stream_kernel(AttnParams p) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     const bool product_form = !__syncthreads_or(q_big) && p.keys_big[u] == 0;
-    if (tr && tid == 0) p.trace[1] = clock64();
 
     if (warp < 4) {
         // ---------------- producers: scores -> numerators ------------------------------------------
@@ -538,35 +557,38 @@ attention_stream_kernel(AttnParams p) {
                 q4[kb].z = exp2f(q4[kb].z); q4[kb].w = exp2f(q4[kb].w);
             }
         }
+        named_bar_sync(1 + 2 * kAttBufs, 128);             // every producer has its queries: the key ring may be filled
+        // Key rows stream through a per-warp ring of FPW slots: lane copies (and later reads) its own 16 bytes of a
+        // frame's 128-float row.  The slot of frame f is refilled with frame f of the NEXT chunk right after it was
+        // consumed, i.e. one chunk (FPW frames of compute) ahead - the __ldg it replaces was one frame ahead and
+        // left the producers waiting on HBM latency (ncu r02a: 18 % of all stall samples on that load).
         const float* kbase = product_form ? p.keys_exp : p.keys;
+        float* my_keys = s_keys + (warp * FPW) * kAtt + 4 * lane;
+        auto prefetch_key = [&](int c, int f) {
+            if (c < nchunk) {
+                const int l = min(c * C + warp + 4 * f, nl - 1);
+                cp_async16(my_keys + f * kAtt, kbase + (size_t)(row0 + l) * kAtt + 4 * lane);
+            }
+            cp_async_commit();                             // one group per frame, empty past the last chunk
+        };
+#pragma unroll
+        for (int f = 0; f < FPW; ++f) prefetch_key(0, f);
         const int my_kb = lane / kGroup;
         const bool leader = (lane % kGroup) == 0 && my_kb < k;
         float run_max = -CUDART_INF_F, run_sum = 0.f;      // leader lanes: state of beam my_kb
         for (int c = 0; c < nchunk; ++c) {
-            const int buf = c & 1;
+            const int buf = c % kAttBufs;
             const int c0 = c * C;
             float* pb = s_p + (buf * K + my_kb) * C;       // this lane's beam row of the chunk
-            // the first barrier of chunk 0 also orders every producer's query reads before the
-            // numerator stores that overwrite them
-            if (tr && tid == 0 && c < 16) p.trace[8 + c * 8 + 0] = clock64();
-            named_bar_sync(c >= 2 ? 3 + buf : 5, c >= 2 ? 256 : 128);     // buffer drained by the consumers
-            if (tr && tid == 0 && c < 16) p.trace[8 + c * 8 + 1] = clock64();
+            if (c >= kAttBufs) named_bar_sync(1 + kAttBufs + buf, 256);      // buffer drained by the consumers
             float cmax = -CUDART_INF_F;
-            // the key row of the next frame is in flight while one frame is evaluated
-            auto load_key = [&](int f) {
-                if (p.dbg & 4) return make_float4(0.f, 0.f, 0.f, 0.f);
-                const int l = min(c0 + warp + 4 * f, nl - 1);
-                return __ldg(reinterpret_cast<const float4*>(kbase + (size_t)(row0 + l) * kAtt) + lane);
-            };
-            float4 key_n1 = load_key(0);
 #pragma unroll 1
             for (int f = 0; f < FPW; ++f) {
                 const int l = c0 + warp + 4 * f;
                 float ev = -CUDART_INF_F;
-                float4 key = key_n1;
-                if (f + 1 < FPW) key_n1 = load_key(f + 1);
-                if (l < nl && (p.dbg & 1)) ev = 0.f;
-                if (l < nl && !(p.dbg & 1)) {              // warp-uniform
+                cp_async_wait<FPW - 1>();                  // the oldest group = this frame's key row has landed
+                float4 key = *reinterpret_cast<const float4*>(my_keys + f * kAtt);
+                if (l < nl) {                              // warp-uniform
                     float e[K];
                     if (product_form) {
                         if (K >= 2) {
@@ -621,15 +643,15 @@ attention_stream_kernel(AttnParams p) {
                     for (; off > 0; off >>= 1) e[0] += __shfl_xor_sync(0xffffffffu, e[0], off);
                     ev = e[0];
                 }
+                // the slot has been read (its value feeds the arithmetic above): refill it one chunk ahead
+                prefetch_key(c + 1, f);
                 if (leader) pb[warp + 4 * f] = ev;         // raw score, turned into a numerator below
                 cmax = fmaxf(cmax, ev);
             }
-            if (leader) s_wmax[(buf * 4 + warp) * K + my_kb] = cmax;
-            if (tr && tid == 0 && c < 16) p.trace[8 + c * 8 + 2] = clock64();
-            named_bar_sync(5, 128);                        // chunk maxima of the 4 producer warps
-            if (tr && tid == 0 && c < 16) p.trace[8 + c * 8 + 3] = clock64();
+            if (leader) s_wmax[((c & 1) * 4 + warp) * K + my_kb] = cmax;
+            named_bar_sync(1 + 2 * kAttBufs, 128);         // chunk maxima of the 4 producer warps
             if (leader) {
-                const float* wm = s_wmax + buf * 4 * K + my_kb;
+                const float* wm = s_wmax + (c & 1) * 4 * K + my_kb;
                 const float new_max = fmaxf(run_max, fmaxf(fmaxf(wm[0], wm[K]), fmaxf(wm[2 * K], wm[3 * K])));
                 const float scale = __expf(run_max - new_max);     // first chunk: exp(-inf) = 0 (accumulators are 0)
                 run_max = new_max;
@@ -645,8 +667,8 @@ attention_stream_kernel(AttnParams p) {
             }
             __threadfence_block();
             named_bar_arrive(1 + buf, 256);
-            if (tr && tid == 0 && c < 16) p.trace[8 + c * 8 + 4] = clock64();
         }
+        cp_async_wait<0>();
         if (leader) s_wsum[warp * K + my_kb] = run_sum;
     } else {
         // ---------------- consumers: context accumulation -------------------------------------------
@@ -658,7 +680,7 @@ attention_stream_kernel(AttnParams p) {
         auto issue = [&](int st) {                         // rows [8 st, 8 st + 8) of the utterance -> ring slot
             const int slot = st % kAttStages;
             const int rows = min(kAttRows, nl - st * kAttRows);
-            const uint32_t bytes = (p.dbg & 8) ? 16u : (uint32_t)rows * kEnc * 4u;
+            const uint32_t bytes = (uint32_t)rows * kEnc * 4u;
             att_mbar_expect_tx(&full_e[slot], bytes);
             att_bulk_g2s(s_ring + slot * kAttRows * kEnc, enc_u + (size_t)st * kAttRows * kEnc, bytes, &full_e[slot]);
         };
@@ -666,12 +688,10 @@ attention_stream_kernel(AttnParams p) {
         for (int st = 0; st < nstage; ++st) {
             const int slot = st % kAttStages;
             const int l0 = st * kAttRows;
-            const int buf = (l0 / C) & 1;
+            const int buf = (l0 / C) % kAttBufs;
             const int lc = l0 % C;
             if (lc == 0) {
-                if (tr && tid == 128 && l0 / C < 16) p.trace[8 + (l0 / C) * 8 + 5] = clock64();
                 named_bar_sync(1 + buf, 256);              // this chunk's numerators are ready
-                if (tr && tid == 128 && l0 / C < 16) p.trace[8 + (l0 / C) * 8 + 6] = clock64();
 #pragma unroll
                 for (int kb = 0; kb < K; ++kb) {
                     if (kb < k) {
@@ -685,7 +705,6 @@ attention_stream_kernel(AttnParams p) {
             const float4* er = reinterpret_cast<const float4*>(s_ring + slot * kAttRows * kEnc) + cg4;
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {               // 4 rows at a time: 16 registers of encoder data
-                if (p.dbg & 2) { if (hf == 1) { __syncwarp(); if (lane == 0) att_mbar_arrive(&empty_e[slot]); } continue; }
                 float4 e[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
@@ -709,8 +728,7 @@ attention_stream_kernel(AttnParams p) {
             }
             if (lc + kAttRows == C || st + 1 == nstage) {              // last stage of the chunk
                 const int c = l0 / C;
-                if (tr && tid == 128 && c < 16) p.trace[8 + c * 8 + 7] = clock64();
-                if (c + 2 < nchunk) named_bar_arrive(3 + buf, 256);
+                if (c + kAttBufs < nchunk) named_bar_arrive(1 + kAttBufs + buf, 256);
             }
             if (tid == 128 && st + kAttStages < nstage) {
                 att_mbar_wait(&empty_e[slot], (uint32_t)((st / kAttStages) & 1));   // all 4 warps have read it
@@ -718,7 +736,6 @@ attention_stream_kernel(AttnParams p) {
             }
         }
         __syncthreads();                                   // producers' sums
-        if (tr && tid == 128) p.trace[2] = clock64();
 #pragma unroll
         for (int kb = 0; kb < K; ++kb) {
             if (kb < k) {
@@ -743,7 +760,6 @@ attention_stream_kernel(AttnParams p) {
                 }
             }
         }
-        if (tr && tid == 128) p.trace[3] = clock64();
         return;
     }
     __syncthreads();                                       // matches the consumers' barrier above
@@ -751,8 +767,7 @@ attention_stream_kernel(AttnParams p) {
 
 template <int K>
 static int launch_attention_stream(const AttnParams& p, int B, cudaStream_t st) {
-    const size_t smem = sizeof(float) * ((size_t)kAttStages * kAttRows * kEnc + 2 * K * kAttChunk + K * kAtt + 2 * K + 8 * K + 4 * K) +
-                        sizeof(uint64_t) * 2 * kAttStages + 16;
+    constexpr size_t smem = AttSmem<K>::kBytes;
     ASR_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&attention_stream_kernel<K>), smem));
     attention_stream_kernel<K><<<B, 256, smem, st>>>(p);
     return ASR_OK;
@@ -764,8 +779,6 @@ int launch_attention(asr_handle* h, int k, int step, int nxt, float* d_align_ste
     const BatchMeta& m = h->meta;
     AttnParams p{};
     p.q = w.att_q;
-    p.dbg = 0;
-    p.trace = nullptr;
     p.keys = w.keys;
     p.keys_exp = w.keys_exp;
     p.keys_big = w.keys_big;
