@@ -152,7 +152,8 @@ def run_reference(args):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"bw={args.bw} beam decode of {args.seconds:g} s 16 kHz utterances "
                                f"(BASELINE.json configs[4]); CPU arm runs a bounded sample per step",
-                   "beam": args.bw, "utt_seconds": args.seconds, "max_len": MAX_LEN},
+                   "beam": args.bw, "utt_seconds": args.seconds, "max_len": MAX_LEN,
+                   "utts_per_step": n_utts, "cpu_baseline_sample": sample},
         "cpu_baseline": {"value": value, "unit": "utt/s", "cores": threads, "kind": "port", "sample": sample,
                          "host_cpus": cores},
         "e2e": {"value": value, "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -163,9 +164,12 @@ def run_reference(args):
 
 # ---------------------------------------------------------------------------------------------
 def decoder_step_bytes(B, k, L):
-    """algorithmic HBM bytes of one decoder step (fp32 storage)."""
+    """algorithmic HBM bytes of one decoder step (fp32 storage): decoder weights once,
+    keys + encoder memory of every frame once per utterance (shared by its k beams), read + write of h / c / ctx per
+    row, one embedding row per row.  The logits are NOT in this number: they no longer reach HBM (the vocabulary
+    GEMM's epilogue keeps log-sum-exp partials and the top candidates per tile instead)."""
     w_dec = 4 * (2625536 + 65536 + 128 + 5129100)
-    return w_dec + B * L * 2560 + B * k * 12288 + B * k * 1024 + 2 * 4 * B * k * V
+    return w_dec + B * L * 2560 + B * k * 12288 + B * k * 1024
 
 
 def run_native(args):
@@ -179,6 +183,9 @@ def run_native(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    cores = None
+    if world > 1:     # before any engine / NCCL thread exists: this rank's own cores next to its GPU
+        cores = parallel.pin_rank_to_local_cores(local, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -216,13 +223,13 @@ def run_native(args):
             results = pipe.map([(hosts[(first + i) % (2 * S)], off) for i in range(steps)], prefetch=True, bw=k)
         else:
             results = pipe.map([(resident, off)] * steps, bw=k, resident=True)
-        out = None
-        for tok, ln, sc in results:
-            if world > 1:   # the one collective of the path: gather the hypotheses (same order on every rank)
-                rec = parallel.pack_records(np.arange(B) + rank * B, tok, ln, sc, MAX_LEN)
-                tok, ln, sc = parallel.gather_hypotheses(rec, total, MAX_LEN, device=dev)
-            out = (tok, ln, sc)
-        return out
+        if world == 1:
+            return results[-1]
+        # the one collective of the path: a single gather of the hypotheses of every batch
+        # this rank decoded, at the end of the run (utterance id = (step * world + rank) * B + i)
+        rec = np.concatenate([parallel.pack_records(np.arange(B) + (s_ * world + rank) * B, tok, ln, sc, MAX_LEN)
+                              for s_, (tok, ln, sc) in enumerate(results)])
+        return parallel.gather_hypotheses(rec, steps * total, MAX_LEN, device=dev)
 
     def timed(e2e, steps):
         if world > 1:
@@ -290,19 +297,23 @@ def run_native(args):
     att_ms = stages.pop("attention_kernel_ms")
     R = B * k
     n_gemm = 4 + 1 + 3 * MAX_LEN
+    roof_src = {}
+    try:        # ncu DRAM bytes per GEMM-engine launch of this workload (tools/prof_cmd.sh -> profiles/r02_roofline.json)
+        roof_src = json.load(open(os.path.join(ROOT, "profiles", "r02_roofline.json")))
+    except Exception:
+        pass
     kernel_ms = dict(stages)
     kernel_ms["gemm engine (all GEMM stages)"] = gemm_ms
     dom = max(("gemm engine (all GEMM stages)", "enc_recurrence", "attention", "topk_bookkeep", "features"),
               key=lambda kk: kernel_ms[kk])
     if dom.startswith("gemm"):
         ach = gemm_gflop / gemm_ms                        # GFLOP / ms = TFLOP/s (algorithmic fp32 2*M*N*K)
-        # dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the 125 launches of a pass
-        # (encoder projections 2.10 + 3 x 1.87 GB, keys 0.61 GB (not captured: operand + output bytes),
-        # 40 x (vocabulary 109 MB + cell 51 MB + query 13 MB)): profiles/r01_kernels.csv, one `ncu --set full`
-        # capture of this workload
-        # (captured at 512 utterances per step; the operand / output bytes scale with the rows)
-        traffic = 15.24e9 / 125 * B / 512 if (k, L) == (8, 332) else None
-        roof = {"kernel": "tc::gemm_split_persistent_kernel", "bound": "tensor", "achieved": ach, "peak": tf_peak,
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the 125 GEMM-engine launches of one
+        # pass of this workload (ncu, profiles/r02_pass_metrics.csv; captured at 512 utterances per step - the
+        # operand / output bytes scale with the rows)
+        gb = roof_src.get("gemm_dram_bytes_per_pass")
+        traffic = gb / n_gemm * B / 512 if gb and (k, L) == (8, 332) else None
+        roof = {"kernel": "tc::gemm_split_pair_kernel", "bound": "tensor", "achieved": ach, "peak": tf_peak,
                 "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": traffic,
                 "peak_source": peak_src + " cuBLAS bf16 sustained.  Per 16 values of k the kernel issues one fp16 MMA "
                                "(a_hi*w_hi) and two bf16 MMAs (a_lo*w + a*w_lo over 2K): 3x the bf16 tensor-pipe time "
@@ -344,9 +355,11 @@ def run_native(args):
                                         "algorithmic_bytes": att_bytes, "achieved": att_bytes / att_us / 1e3,
                                         "peak": hbm_peak, "unit": "GB/s", "frac": att_bytes / att_us / 1e3 / hbm_peak,
                                         "peak_source": peak_src},
-                "note": "the GEMMs of the step (cell, query, vocabulary) are tensor-bound in fp32-faithful "
-                        "split precision, so the whole step sits below the HBM roofline; the attention kernel is "
-                        "the memory-bound part"}
+                "kernels_per_step": ["cell GEMM (LSTM epilogue)", "query GEMM", "attention_stream_kernel",
+                                     "vocabulary GEMM (LSE + top-k epilogue)", "beam_merge_kernel"],
+                "note": "algorithmic bytes exclude logits (not materialised). The GEMMs of the step (cell, query, "
+                        "vocabulary) are tensor-bound in fp32-faithful split precision (3 MMA slots per product), so "
+                        "the whole step sits below the HBM roofline; the attention kernel is the memory-bound part"}
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:      # reported on rank 0 at N = 1 only
@@ -365,6 +378,8 @@ def run_native(args):
                    "pipeline": ("%d handles per GPU, batches handed round-robin, each engine on its own host thread and "
                                 "stream: one batch's encoder overlaps another's decoder" % S) if S > 1 else "one handle",
                    "enc_frames_per_utt": L, "weights": "random-init (reference initialisers), fp32",
+                   "cpu_baseline_sample": f"{args.cpu_sample} utterances per CPU batch (the GPU arm: {B} per step)",
+                   "rank_cores": cores,
                    "pcm": "int16 (16-bit WAV samples), converted on the device",
                    "l2_policy": "inputs larger than L2 (PCM %.0f MB, gate pre-activations %.0f MB per step)"
                                 % (B * n * 2 / 1e6, B * L * 8192 / 1e6)},

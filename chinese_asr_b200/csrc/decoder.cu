@@ -495,7 +495,8 @@ struct AttSmem {
     static constexpr int kRing = kAttStages * kAttRows * kEnc;
     static constexpr int kKeys = 4 * (kAttChunk / 4) * kAtt;            // 4 producer warps x 8 frames x 128
     static_assert(K * kAtt <= kKeys, "queries alias the key ring");
-    static constexpr int kP = kAttBufs * K * kAttChunk;
+    static constexpr int kPStride = kAttChunk + 4;      // beam rows 36 floats apart: the K leader lanes of a warp hit K different banks
+    static constexpr int kP = kAttBufs * K * kPStride;
     static constexpr int kSmall = kAttBufs * K + 2 * 4 * K + 4 * K;
     static constexpr size_t kBytes = sizeof(float) * (kRing + kKeys + kP + kSmall) + sizeof(uint64_t) * 2 * kAttStages + 16;
 };
@@ -512,7 +513,8 @@ attention_stream_kernel(AttnParams p) {
     float* s_ring = reinterpret_cast<float*>(att_smem);                          // [stages][8][512]
     float* s_keys = s_ring + S::kRing;                                            // [4 warps][FPW][128]
     float* s_q = s_keys;                                                          // [K][128], prologue only
-    float* s_p = s_keys + S::kKeys;                                               // [bufs][K][C]
+    float* s_p = s_keys + S::kKeys;                                               // [bufs][K][C + 4]
+    constexpr int CP = S::kPStride;
     float* s_scale = s_p + S::kP;                                                 // [bufs][K]
     float* s_wmax = s_scale + kAttBufs * K;                                       // [2][4][K]
     float* s_wsum = s_wmax + 2 * 4 * K;                                           // [4][K]
@@ -579,7 +581,7 @@ attention_stream_kernel(AttnParams p) {
         for (int c = 0; c < nchunk; ++c) {
             const int buf = c % kAttBufs;
             const int c0 = c * C;
-            float* pb = s_p + (buf * K + my_kb) * C;       // this lane's beam row of the chunk
+            float* pb = s_p + (buf * K + my_kb) * CP;      // this lane's beam row of the chunk
             if (c >= kAttBufs) named_bar_sync(1 + kAttBufs + buf, 256);      // buffer drained by the consumers
             float cmax = -CUDART_INF_F;
 #pragma unroll 1
@@ -716,7 +718,7 @@ attention_stream_kernel(AttnParams p) {
 #pragma unroll
                 for (int kb = 0; kb < K; ++kb) {
                     if (kb < k) {
-                        const float4 w4 = *reinterpret_cast<const float4*>(s_p + (buf * K + kb) * C + lc + 4 * hf);
+                        const float4 w4 = *reinterpret_cast<const float4*>(s_p + (buf * K + kb) * CP + lc + 4 * hf);
                         const float w[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {

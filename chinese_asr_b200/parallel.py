@@ -35,19 +35,21 @@ def pack_records(indices, tokens, lens, scores, max_len):
 
 
 def gather_hypotheses(rec, total, max_len, device=None, group=None):
-    """All-gather the per-rank records (padded to the largest shard) and scatter them back into
-    original utterance order.  Returns (tokens [total, max_len], lens [total], scores [total])."""
+    """THE collective of the path: one all-gather of the per-rank records (padded to the
+    largest shard) at the end of a run, scattered back into original utterance order.  Call it once with the
+    records of every batch a rank decoded, not once per batch.  Returns (tokens [total, max_len], lens [total],
+    scores [total])."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     per = (total + world - 1) // world
     buf = np.full((per, max_len + 3), -1, dtype=np.int32)
     buf[:rec.shape[0]] = rec
     t = torch.from_numpy(buf)
     if device is not None:
-        t = t.to(device)
+        t = t.pin_memory().to(device, non_blocking=True)
     if world > 1:
-        out = [torch.empty_like(t) for _ in range(world)]
-        dist.all_gather(out, t, group=group)
-        allrec = torch.cat(out, dim=0).cpu().numpy()
+        out = torch.empty((world * per, max_len + 3), dtype=torch.int32, device=t.device)
+        dist.all_gather_into_tensor(out, t, group=group)
+        allrec = out.cpu().numpy()
     else:
         allrec = t.cpu().numpy()
     allrec = allrec[allrec[:, 0] >= 0]
@@ -59,6 +61,31 @@ def gather_hypotheses(rec, total, max_len, device=None, group=None):
     lens[idx] = allrec[:, 1]
     scores[idx] = allrec[:, 2].copy().view(np.float32)
     return tokens, lens, scores
+
+
+def pin_rank_to_local_cores(local_rank, local_world):
+    """Give every rank of a node its own slice of the CPU cores next to its GPU (NVML's ideal affinity of the
+    device, split evenly between the ranks that share it), so that 8 ranks x (engine threads + NCCL proxy) do not
+    migrate over all cores of the box.  Call before any worker thread exists; returns the cores or None when NVML
+    or sched_setaffinity is unavailable (nothing is changed then)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        words = (os.cpu_count() + 63) // 64
+        sets = []
+        for j in range(local_world):
+            mask = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(j), words)
+            sets.append(tuple(c for c in range(os.cpu_count()) if (mask[c // 64] >> (c % 64)) & 1))
+        allowed = set(os.sched_getaffinity(0))
+        mine = [c for c in sets[local_rank] if c in allowed] or sorted(allowed)
+        sharing = [j for j in range(local_world) if sets[j] == sets[local_rank]]
+        pos, n = sharing.index(local_rank), len(sharing)
+        cores = mine[pos * len(mine) // n:(pos + 1) * len(mine) // n] or mine
+        os.sched_setaffinity(0, cores)
+        return cores
+    except Exception:
+        return None
 
 
 class BatchPipeline(object):
