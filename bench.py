@@ -42,6 +42,8 @@ def parse_args():
     ap.add_argument("--seconds", type=float, default=SECONDS)
     ap.add_argument("--cpu-sample", type=int, default=64, help="utterances per batch of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--rec-chunks", type=int, default=0,
+                    help="recurrence chunks per direction (asr_set_recurrence_chunks, experiments); 0 = the default 7")
     ap.add_argument("--pipeline", type=int, default=2,
                     help="engines (handles) per GPU with batches in flight: the latency-bound encoder of one batch "
                          "overlaps the decoder of another (chinese_asr_b200.parallel.BatchPipeline); 1 = one handle")
@@ -203,6 +205,8 @@ def run_native(args):
         mm = Model()
         mm.load_state(weights)
         mm.reserve(B, B * L, k, B * n, MAX_LEN)
+        if args.rec_chunks:
+            mm.set_recurrence_chunks(args.rec_chunks)
         models.append(mm)
     m = models[0]
     pipe = parallel.BatchPipeline(models)
@@ -213,6 +217,8 @@ def run_native(args):
              for i in range(2 * S)]
     resident = hosts[0].to(dev)
     total = B * world
+
+    gather_s = []        # host seconds of every end-of-run gather (pack + H2D + all_gather + D2H + scatter)
 
     def run_steps(e2e, steps, first=0):
         """`steps` batches of B utterances per GPU, handed round-robin to the S engines (each on its own host
@@ -225,11 +231,14 @@ def run_native(args):
             results = pipe.map([(resident, off)] * steps, bw=k, resident=True)
         if world == 1:
             return results[-1]
+        t_g = time.perf_counter()
         # the one collective of the path: a single gather of the hypotheses of every batch
         # this rank decoded, at the end of the run (utterance id = (step * world + rank) * B + i)
         rec = np.concatenate([parallel.pack_records(np.arange(B) + (s_ * world + rank) * B, tok, ln, sc, MAX_LEN)
                               for s_, (tok, ln, sc) in enumerate(results)])
-        return parallel.gather_hypotheses(rec, steps * total, MAX_LEN, device=dev)
+        out = parallel.gather_hypotheses(rec, steps * total, MAX_LEN, device=dev)
+        gather_s.append(time.perf_counter() - t_g)
+        return out
 
     def timed(e2e, steps):
         if world > 1:
@@ -380,6 +389,7 @@ def run_native(args):
                    "enc_frames_per_utt": L, "weights": "random-init (reference initialisers), fp32",
                    "cpu_baseline_sample": f"{args.cpu_sample} utterances per CPU batch (the GPU arm: {B} per step)",
                    "rank_cores": cores,
+                   "final_gather_ms": [round(1e3 * g, 3) for g in gather_s[-2:]],
                    "pcm": "int16 (16-bit WAV samples), converted on the device",
                    "l2_policy": "inputs larger than L2 (PCM %.0f MB, gate pre-activations %.0f MB per step)"
                                 % (B * n * 2 / 1e6, B * L * 8192 / 1e6)},

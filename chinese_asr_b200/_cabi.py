@@ -88,6 +88,7 @@ SIGNATURES = {
     "asr_transcribe_device": (C.c_int, [C.c_void_p, C.c_void_p, c_int64_p, C.c_int, C.c_int, C.c_int,
                                         C.c_float, C.c_int, C.c_double, C.c_double, c_int32_p,
                                         c_int32_p, c_float_p, C.c_void_p]),
+    "asr_set_recurrence_chunks": (C.c_int, [C.c_void_p, C.c_int]),
     "asr_test_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                 C.c_int, C.c_int, C.c_void_p]),
     "asr_prefetch_pcm": (C.c_int, [C.c_void_p, C.c_void_p, c_int64_p, C.c_int]),

@@ -592,6 +592,13 @@ int asr_create(asr_handle** out, const asr_weights* wt, const asr_feature_consts
     return ASR_OK;
 }
 
+int asr_set_recurrence_chunks(asr_handle* h, int chunks_per_direction) {
+    if (!h || chunks_per_direction < 1 || chunks_per_direction > 7) { set_error("asr_set_recurrence_chunks: 1..7"); return ASR_ERR_ARG; }
+    h->rec_chunks = chunks_per_direction;
+    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+    return ASR_OK;
+}
+
 // Standalone GEMM for tests: d_C[M,N] = d_A[M,K] * d_W[N,K]^T + d_bias[N] through the split-precision engine.
 int asr_test_gemm(asr_handle* h, const float* d_A, const float* d_W, const float* d_bias, float* d_C, int M,
                   int N, int K, void* stream) {

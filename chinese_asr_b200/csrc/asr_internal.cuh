@@ -316,6 +316,7 @@ struct asr_handle {
     int last_info[4] = {};       // {steps, stop step or -1, fallbacks, finished hypotheses} of the last decode
     int last_out_ld = 0;         // row stride of ws.out_tokens after the last decode (its max_len)
     int64_t launches = 0;
+    int rec_chunks = 7;          // recurrence chunks per direction (clusters = 2 x chunks), asr_set_recurrence_chunks
     bool timing = false;
     bool rec_timeline = false;   // print the recurrence kernel's clock64 step timeline (asr_stage_timing(h, 2))
     cudaGraphExec_t graph_exec = nullptr;   // captured beam-decode loop for the shape in graph_key

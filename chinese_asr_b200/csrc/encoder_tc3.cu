@@ -515,7 +515,12 @@ int launch_lstm_recurrence_tc3(asr_handle* h, int layer, const float* xg, const 
     // <= 15 clusters of 8 CTAs are co-resident on a B200 (measured): aim at one round, i.e. at most
     // 7 chunks per direction, with the smallest operand tile that holds the chunk (up to 7 x 128 = 896
     // sequences in one round; the step time grows with NB only through the gate phase and the exchange).
-    int rows = (m.B + 6) / 7;
+    // h->rec_chunks < 7 (asr_set_recurrence_chunks) trades a longer step for fewer SMs.  Measured at 512 x 10 s
+    // (ms per batch, SMs): 7 chunks 7.2 on 112; 6 chunks (96 sequences per cluster) 8.0 on 96; 4 chunks (128 per
+    // cluster) 10.8 - 13.6 on 64: the gate phase is issue-bound and grows faster than the chunk, so 7 stays the
+    // default and the knob is for experiments only.
+    const int chunks = h->rec_chunks < 1 ? 1 : (h->rec_chunks > 7 ? 7 : h->rec_chunks);
+    int rows = (m.B + chunks - 1) / chunks;
     int NB = rows <= 16 ? 16 : rows <= 32 ? 32 : rows <= 64 ? 64 : rows <= 80 ? 80 : rows <= 96 ? 96 : 128;
     if (rows > rec3::kMaxNB) rows = rec3::kMaxNB;
     p.rows_per_chunk = rows;

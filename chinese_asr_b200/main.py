@@ -4,8 +4,10 @@
 Knobs kept: greedy (bw=None) vs beam (bw=4/8/16), lm_path -> second pass with lm_weight=1.5 /
 length_weight=1.5 (main.py:45-51), gpd['temperature' | 'max_len' | 'verbose'], dict.pkl vocab.
 Differences, by necessity: convert_audio (main.py:19-24 shells out to ffmpeg + sox) is out of scope,
-so `path` must already be 16 kHz mono PCM WAV; lm_path is an ARPA file (order <= 3) instead of a
-KenLM binary, because the second pass runs on the device from flat tables."""
+so `path` must already be 16 kHz mono PCM WAV.  lm_path: an ARPA file (order <= 3) is loaded into
+device tables and the second pass runs on the GPU; anything else is handed to kenlm.LanguageModel like
+main.py:82 does (when the kenlm module is installed) and the finished hypotheses are rescored on the host
+with its .score() (Model._host_rescore, from asr_beam_nbest)."""
 from time import time
 
 import torch
@@ -42,7 +44,11 @@ class ASR:
         if lm_path is not None and bw is not None and bw > 1:
             print('loading language model...')
             ts = time()
-            lm_model = NGramLM.from_arpa(lm_path, audio_base.word2int)
+            if str(lm_path).endswith('.arpa'):
+                lm_model = NGramLM.from_arpa(lm_path, audio_base.word2int)
+            else:
+                import kenlm                      # main.py:82 (not part of this image; the caller's environment)
+                lm_model = kenlm.LanguageModel(lm_path)
             print('loading cost %.3fs' % (time() - ts))
         else:
             lm_model = None

@@ -575,6 +575,11 @@ class Model(object):
             return _cabi.PCM_S16
         raise TypeError(f"PCM buffer must be float32 or int16, not {dt}")
 
+    def set_recurrence_chunks(self, chunks_per_direction):
+        """asr_set_recurrence_chunks: 7 (default) = lowest latency for one batch; fewer = wider chunks on fewer SMs."""
+        self._need()
+        check(lib.asr_set_recurrence_chunks(self._h, int(chunks_per_direction)), "asr_set_recurrence_chunks")
+
     def test_gemm(self, A, W, bias):
         """C = A @ W.T + bias on the device through the split-precision tensor-core engine (tests)."""
         self._need()

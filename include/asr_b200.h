@@ -239,6 +239,13 @@ int asr_transcribe_device(asr_handle* h, const float* d_pcm, const int64_t* h_pc
                           double length_weight, int32_t* h_tokens, int32_t* h_len, float* h_score,
                           void* stream);
 
+/* Scheduling knob of the encoder recurrence (the nn.LSTM time loop, util.py:1259): a batch is split into
+ * `chunks_per_direction` (1..7, default 7) chunks of sequences per direction, each run by one cluster of 8 SMs.
+ * 7 = shortest latency for one batch (14 clusters = 112 SMs); fewer, wider chunks leave more SMs to other handles'
+ * work on the same GPU at the price of a longer step (measured at 512 x 10 s: 7.2 ms on 112 SMs, 8.0 ms on 96,
+ * 10.8 ms on 64).  Results do not depend on it. */
+int asr_set_recurrence_chunks(asr_handle* h, int chunks_per_direction);
+
 /* The GEMM engine of the GEMM-shaped stages (nn.LSTM input projections util.py:1259, attention keys
  * attention.py:77, query attention.py:92, nn.LSTMCell util.py:1650-1661, vocabulary projection decoder.py:133):
  * tcgen05 / TMEM / TMA tensor cores in split precision (fp16 hi + bf16 cross terms, fp32-faithful: ~2^-20
