@@ -270,6 +270,7 @@ static int decoder_step(asr_handle* h, int k, int step, int cur, float temperatu
         e.split_hi = w.dec_split_hi;
         e.split_lo = w.dec_split_lo;
         e.split_ld = kProjK;
+        e.pdl = true;
         StageScope sc3(h, kStGemmKernel, st);
         h->gemm_flops += 2.0 * R * 4 * kDecH * kProjK;
         ASR_TRY(launch_gemm_tc(w.a_hi, w.a_lo, h->w.dec_w_hi + kEmb, h->w.dec_w_lo + kEmb, R, 4 * kDecH, kProjK, e, st,
@@ -284,6 +285,7 @@ static int decoder_step(asr_handle* h, int k, int step, int cur, float temperatu
         e.ldc = kAtt;
         e.stop_flag = w.ctrl;
         e.lda = kProjK;
+        e.pdl = true;
         {
             StageScope sc3(h, kStGemmKernel, st);
             h->gemm_flops += 2.0 * R * kAtt * kDecH;
@@ -302,6 +304,7 @@ static int decoder_step(asr_handle* h, int k, int step, int cur, float temperatu
         e.bias = h->w.proj_b;
         e.scale = temperature;
         e.stop_flag = w.ctrl;
+        e.pdl = true;
         if (materialise_logits) {
             e.C = w.logits;
             e.ldc = kVocab;

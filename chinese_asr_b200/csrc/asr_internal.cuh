@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/asr_b200.h"
@@ -49,6 +50,17 @@ __device__ __forceinline__ uint32_t pack_hi2(float a, float b) {
     const __half2 v = __floats2half2_rn(a, b);
     return *reinterpret_cast<const uint32_t*>(&v);
 }
+#endif
+
+#ifdef __CUDACC__
+// Programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// start while its predecessor in the stream still runs.  Every kernel of the decoder step calls
+// griddep_launch_dependents() first (the next kernel's CTAs may take SMs as soon as this grid's CTAs leave them
+// and run their own prologue) and griddep_wait() before it reads or writes ANY global memory (the wait returns
+// once the predecessor grid has completed and its writes are visible) - on every path, so that completion stays
+// transitive along the chain.  Both are no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 #endif
 
 #define ASR_CUDA(call)                                                                        \
@@ -117,6 +129,7 @@ struct GemmEpilogue {
     float* c_out;          // [M, H]
     int H;
     const int* stop_flag;  // optional: kernel returns immediately when *stop_flag >= 0
+    bool pdl;              // launch with programmatic stream serialization (kernels of the decoder step)
     // tcgen05 engine only:
     int lda, ldw;          // row strides (floats) of the pre-split A / W operands; 0 = K (dense)
     const float* addrow;   // kLstmCell: gate pre-activations += addrow[addrow_idx[row]][n] (the
@@ -342,6 +355,23 @@ struct asr_handle {
 };
 
 namespace asr {
+
+// launch a plain (non-cluster) kernel, optionally with programmatic stream serialization
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                                 Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 // ---- features.cu -----------------------------------------------------------------------------
 int build_feature_consts(asr_handle* h, const asr_feature_consts* fc);

@@ -504,7 +504,7 @@ struct AttSmem {
 template <int K>
 __global__ void __launch_bounds__(256, K <= 8 ? 4 : 2)
 attention_stream_kernel(AttnParams p) {
-    if (p.ctrl[0] >= 0) return;
+    griddep_launch_dependents();
     constexpr int C = kAttChunk;
     constexpr int kGroup = 32 / K;                 // lanes that end up holding the same beam
     constexpr int FPW = C / 4;                     // frames per producer warp per chunk
@@ -532,15 +532,17 @@ attention_stream_kernel(AttnParams p) {
     // named barriers: 1 + b: numerators of buffer b published (producers arrive, consumers sync);
     // 1 + kAttBufs + b: buffer b drained (consumers arrive, producers sync); 1 + 2 kAttBufs: producers only
 
+    if (tid == 0) {
+        for (int i = 0; i < kAttStages; ++i) { att_mbar_init(&full_e[i], 1); att_mbar_init(&empty_e[i], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    griddep_wait();                                        // the query GEMM has finished: global memory may be touched
+    if (p.ctrl[0] >= 0) return;
     bool q_big = false;
     for (int i = tid; i < k * kAtt; i += 256) {
         const float qv = p.q[(size_t)u * k * kAtt + i];
         s_q[i] = qv;
         q_big |= !(fabsf(qv * kAttScale) <= kAttRange);
-    }
-    if (tid == 0) {
-        for (int i = 0; i < kAttStages; ++i) { att_mbar_init(&full_e[i], 1); att_mbar_init(&empty_e[i], 4); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     const bool product_form = !__syncthreads_or(q_big) && p.keys_big[u] == 0;
 
@@ -771,7 +773,7 @@ template <int K>
 static int launch_attention_stream(const AttnParams& p, int B, cudaStream_t st) {
     constexpr size_t smem = AttSmem<K>::kBytes;
     ASR_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&attention_stream_kernel<K>), smem));
-    attention_stream_kernel<K><<<B, 256, smem, st>>>(p);
+    ASR_CUDA(launch_kernel(attention_stream_kernel<K>, dim3(B), dim3(256), smem, st, true, p));
     return ASR_OK;
 }
 
@@ -966,7 +968,9 @@ __device__ void beam_bookkeep(const BookParams& p, int u, const float* s_cs, con
 // then beam * V + token ascending (torch.topk's tie order is unspecified; the oracle defines the same).
 __global__ void __launch_bounds__(256)
 beam_merge_kernel(MergeParams p) {
+    griddep_launch_dependents();
     const BookParams& b = p.book;
+    griddep_wait();                                        // the vocabulary GEMM has finished
     if (b.ctrl[0] >= 0) return;
     extern __shared__ __align__(16) uint8_t merge_smem[];
     __shared__ float s_lse[kMaxBeam], s_bs[kMaxBeam];
@@ -1089,7 +1093,7 @@ int launch_beam_merge(asr_handle* h, int k, int step, cudaStream_t st) {
                              w.dec_split_hi, w.dec_split_lo, w.a_hi, w.a_lo}};
     const size_t smem = (size_t)k * kVocabTiles * KP * 8;          // k = 16: 94 KB
     ASR_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&beam_merge_kernel), smem));
-    beam_merge_kernel<<<h->meta.B, 256, smem, st>>>(p);
+    ASR_CUDA(launch_kernel(beam_merge_kernel, dim3(h->meta.B), dim3(256), smem, st, true, p));
     ASR_CHECK_LAUNCH();
     h->launches++;
     return ASR_OK;

@@ -233,7 +233,7 @@ __global__ void __launch_bounds__((SmemLayout<BN, STAGES, KP>::kThreads), 1)
 gemm_split_pair_kernel(const __grid_constant__ CUtensorMap map_a_x, const __grid_constant__ CUtensorMap map_a_h,
                        const __grid_constant__ CUtensorMap map_w_x, const __grid_constant__ CUtensorMap map_w_h,
                        int M, int N, int K, GemmEpilogue epi) {
-    if (epi.stop_flag && *epi.stop_flag >= 0) return;
+    griddep_launch_dependents();
     using L = SmemLayout<BN, STAGES, KP>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -274,8 +274,13 @@ gemm_split_pair_kernel(const __grid_constant__ CUtensorMap map_a_x, const __grid
     cluster_sync_all();                                        // the peer's barriers are initialised too
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    // everything above touched no global memory: it overlaps the tail of the previous kernel in the stream
+    griddep_wait();
+    const bool stopped = epi.stop_flag && *epi.stop_flag >= 0;      // early stop of the decode loop (model.py:578, 897)
 
-    if (warp == 0) {
+    if (stopped) {
+        // nothing to do: fall through to the common exit (cluster barrier, TMEM release)
+    } else if (warp == 0) {
         if (lane == 0) {
             int it = 0;
             for (int work = work0; work < nwork; work += work_step) {
@@ -687,9 +692,11 @@ static int launch_pair(const hi_t* a_hi, const float* a_lo, const hi_t* w_hi, co
     ASR_TRY(tc::make_map(&mw_x, w_lo, N, K, BN / 2, epi.ldw, false));
     ASR_TRY(tc::make_map(&mw_h, w_hi, N, K, BN / 2, epi.ldw, true));
     cudaLaunchConfig_t cfg = {};
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // decoder-step launches: see griddep_wait()
+    at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.blockDim = dim3(tc::SmemLayout<BN, STAGES, KP>::kThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
@@ -710,6 +717,7 @@ static int launch_pair(const hi_t* a_hi, const float* a_lo, const hi_t* w_hi, co
     const int tiles_m = (M + tc::BM - 1) / tc::BM, tiles_n = (N + BN - 1) / BN;
     const int nwork = ((tiles_m + 1) / 2) * tiles_n;
     cfg.gridDim = dim3(2 * std::min(nwork, mc));
+    cfg.numAttrs = epi.pdl ? 2 : 1;
     ASR_CUDA(cudaLaunchKernelEx(&cfg, kern, ma_x, ma_h, mw_x, mw_h, M, N, K, epi));
     ASR_CHECK_LAUNCH();
     return ASR_OK;
