@@ -80,6 +80,7 @@ SIGNATURES = {
                                   C.c_double, c_int32_p, c_int32_p, c_float_p, c_int32_p, C.c_void_p]),
     "asr_beam_trace": (C.c_int, [C.c_void_p, c_float_p, c_int32_p, c_int32_p, c_int32_p, c_int32_p,
                                  c_float_p]),
+    "asr_check_guards": (C.c_int, [C.c_void_p]),
     "asr_decode_info": (C.c_int, [C.c_void_p, c_int32_p]),
     "asr_beam_nbest": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_int32_p, c_int32_p, c_int32_p, c_float_p]),
     "asr_transcribe": (C.c_int, [C.c_void_p, C.c_void_p, c_int64_p, C.c_int, C.c_int, C.c_int,

@@ -39,18 +39,20 @@ int ensure_dynamic_smem(const void* func, size_t bytes) {
     return ASR_OK;
 }
 
-static int dev_alloc(std::vector<void*>& pool, void** p, size_t bytes) {
+static int dev_alloc(DevicePool& pool, void** p, size_t bytes) {
     if (bytes == 0) bytes = 16;
-    ASR_CUDA(cudaMalloc(p, bytes));
-    pool.push_back(*p);
+    ASR_CUDA(cudaMalloc(p, bytes + kGuardBytes));
+    ASR_CUDA(cudaMemset(static_cast<char*>(*p) + bytes, kGuardByte, kGuardBytes));
+    pool.ptrs.push_back(*p);
+    pool.bytes.push_back(bytes);
     return ASR_OK;
 }
 template <typename T>
-static int dev_alloc_t(std::vector<void*>& pool, T** p, size_t count) {
+static int dev_alloc_t(DevicePool& pool, T** p, size_t count) {
     return dev_alloc(pool, reinterpret_cast<void**>(p), count * sizeof(T));
 }
 template <typename T>
-static int dev_upload(std::vector<void*>& pool, T** p, const std::vector<T>& v) {
+static int dev_upload(DevicePool& pool, T** p, const std::vector<T>& v) {
     ASR_TRY(dev_alloc_t(pool, p, v.size()));
     ASR_CUDA(cudaMemcpy(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
     return ASR_OK;
@@ -505,7 +507,7 @@ int asr_create(asr_handle** out, const asr_weights* wt, const asr_feature_consts
     if (cc_major != 10) { set_error("asr_b200 requires an sm_100 device (found sm_%d x)", cc_major); return ASR_ERR_CUDA; }
     asr_handle* h = new asr_handle();
     h->device = dev;
-    std::vector<void*>& pool = h->weight_allocs;
+    DevicePool& pool = h->weight_allocs;
     int rc = build_feature_consts(h, fc);
     if (rc != ASR_OK) { delete h; return rc; }
 
@@ -717,7 +719,7 @@ int asr_reserve(asr_handle* h, int max_utts, int64_t max_rows, int max_beam, int
     h->pre_src[0] = h->pre_src[1] = nullptr;      // the staged PCM copies went with the pool
     const int64_t max_frames = 3 * max_rows + 2 * (int64_t)max_utts;
     auto allocate = [&]() -> int {
-    std::vector<void*>& pool = w.allocs;
+    DevicePool& pool = w.allocs;
     const size_t R = (size_t)max_utts * max_beam;
     const size_t K2 = 2 * (size_t)max_beam;
     if (max_samples > 0) {
@@ -900,7 +902,7 @@ int asr_set_lm(asr_handle* h, const asr_lm_tables* t) {
         set_error("asr_set_lm: bad tables");
         return ASR_ERR_ARG;
     }
-    std::vector<void*>& pool = h->weight_allocs;
+    DevicePool& pool = h->weight_allocs;
     LmTables& lm = h->lm;
     auto upf = [&](float** d, const float* s, size_t n) { std::vector<float> v(s, s + n); return dev_upload(pool, d, v); };
     auto upl = [&](long long** d, const int64_t* s, size_t n) { std::vector<long long> v(s, s + n); return dev_upload(pool, d, v); };
@@ -948,6 +950,27 @@ int asr_decode_beam(asr_handle* h, int k, int max_len, float temperature, int se
     cudaStream_t st = (cudaStream_t)stream;
     ASR_TRY(beam_decode_device(h, k, max_len, temperature, second_pass, lm_weight, length_weight, st));
     return fetch_results(h, h->meta.B, max_len, h_tokens, h_len, h_score, h_info, st);
+}
+
+int asr_check_guards(asr_handle* h) {
+    if (!h) { set_error("asr_check_guards: NULL handle"); return ASR_ERR_ARG; }
+    ASR_CUDA(cudaDeviceSynchronize());
+    std::vector<unsigned char> g(kGuardBytes);
+    int bad = 0;
+    const DevicePool* pools[2] = {&h->weight_allocs, &h->ws.allocs};
+    for (int pi = 0; pi < 2; ++pi)
+        for (size_t i = 0; i < pools[pi]->ptrs.size(); ++i) {
+            const size_t n = pools[pi]->bytes[i];
+            if (n == 0) continue;
+            ASR_CUDA(cudaMemcpy(g.data(), static_cast<const char*>(pools[pi]->ptrs[i]) + n, kGuardBytes, cudaMemcpyDeviceToHost));
+            for (size_t b = 0; b < kGuardBytes; ++b)
+                if (g[b] != kGuardByte) {
+                    if (!bad) set_error("guard of %s buffer %zu (%zu bytes) overwritten at +%zu", pi ? "workspace" : "weight", i, n, b);
+                    ++bad;
+                    break;
+                }
+        }
+    return bad;
 }
 
 int asr_decode_info(asr_handle* h, int32_t* h_info) {

@@ -246,6 +246,20 @@ struct BatchMeta {
     int* d_feat2packed = nullptr;     // [rows] row of d_feats -> packed row
 };
 
+// Device allocations of a handle.  Every buffer is followed by a guard of kGuardBytes filled with a pattern that
+// asr_check_guards() verifies: compute-sanitizer is closed on the B200 pool, so writes past the end of a buffer are
+// caught by the library's own canaries (checked by the GPU tests and by smoke()).
+constexpr size_t kGuardBytes = 256;
+constexpr unsigned char kGuardByte = 0xA5;
+struct DevicePool {
+    std::vector<void*> ptrs;
+    std::vector<size_t> bytes;       // payload bytes of ptrs[i] (the guard follows); 0 = no guard (registered buffer)
+    void push_back(void* p) { ptrs.push_back(p); bytes.push_back(0); }
+    void clear() { ptrs.clear(); bytes.clear(); }
+    std::vector<void*>::const_iterator begin() const { return ptrs.begin(); }
+    std::vector<void*>::const_iterator end() const { return ptrs.end(); }
+};
+
 struct Workspace {
     int max_utts = 0, max_beam = 0, max_len = 0;
     int64_t max_rows = 0, max_samples = 0, max_frames = 0;
@@ -311,7 +325,7 @@ struct Workspace {
     size_t h_stage_bytes = 0;
     hi_t* a_hi = nullptr;        // split A operand of the tcgen05 GEMMs: max(rows*720, R*1280) elements
     float* a_lo = nullptr;
-    std::vector<void*> allocs;
+    DevicePool allocs;
 };
 
 }  // namespace asr
@@ -351,7 +365,7 @@ struct asr_handle {
     int n_ev = 0;
     int ev_stage[1024] = {};
     float stage_ms[asr::kStages] = {};
-    std::vector<void*> weight_allocs;
+    asr::DevicePool weight_allocs;
 };
 
 namespace asr {

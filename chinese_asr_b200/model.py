@@ -467,6 +467,14 @@ class Model(object):
             tlen[u] = len(best_toks)
             score[u] = best_s
 
+    def check_guards(self):
+        """asr_check_guards: raises if a kernel wrote past the end of any device buffer of this engine."""
+        self._need()
+        bad = int(lib.asr_check_guards(self._h))
+        if bad != 0:
+            msg = lib.asr_last_error()
+            raise _cabi.AsrError(f"{bad} device buffer guard(s) overwritten: {msg.decode() if msg else ''}")
+
     def decode_info(self):
         """{steps, stopped_at (-1 = ran to max_len), fallback, finished} of the last decode (asr_decode_info)."""
         info = np.zeros(4, dtype=np.int32)

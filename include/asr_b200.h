@@ -170,6 +170,11 @@ int asr_decode_beam(asr_handle* h, int k, int max_len, float temperature, int se
                     double lm_weight, double length_weight, int32_t* h_tokens, int32_t* h_len,
                     float* h_score, int32_t* h_info, void* stream);
 
+/* Every device buffer of a handle (weights, workspaces) ends in a 256-byte canary.  Returns the number of buffers
+ * whose canary was overwritten (0 = intact; asr_last_error() names the first one), negative on a CUDA error.
+ * Synchronises the device.  The GPU tests and smoke() call it: compute-sanitizer is not available on the B200 pool. */
+int asr_check_guards(asr_handle* h);
+
 /* h_info[4] of the last decode on this handle (asr_decode_beam, asr_decode_greedy or asr_transcribe*):
  * {steps executed, stop step or -1 (model.py:578, 897-901), #utterances that took the un-finished
  * fallback, #finished hypotheses}. */
