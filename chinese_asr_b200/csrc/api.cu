@@ -511,7 +511,8 @@ int asr_create(asr_handle** out, const asr_weights* wt, const asr_feature_consts
     int rc = build_feature_consts(h, fc);
     if (rc != ASR_OK) { delete h; return rc; }
 
-    // encoder weights, permuted: n' = dir*1024 + j*128 + gate*32 + uu  <-  gate*256 + 32*j + uu
+    // encoder weights, permuted: n' = dir*1024 + j*128 + 4*uu + gate  <-  gate*256 + 32*j + uu  (the 128 gate rows of
+    // recurrence CTA j are contiguous, and the four gates of a unit adjacent: one 16-byte load of xg per cell)
     for (int layer = 0; layer < 4; ++layer) {
         const int K = layer == 0 ? kFeat : kEnc;
         std::vector<float> wih((size_t)2 * kGates * K), bias(2 * kGates), whh((size_t)2 * kGates * kEncH);
@@ -521,7 +522,7 @@ int asr_create(asr_handle** out, const asr_weights* wt, const asr_feature_consts
                 for (int g = 0; g < 4; ++g)
                     for (int uu = 0; uu < 32; ++uu) {
                         const int src = g * kEncH + 32 * j + uu;
-                        const int dst = dir * kGates + j * 128 + g * 32 + uu;
+                        const int dst = dir * kGates + j * 128 + 4 * uu + g;
                         memcpy(&wih[(size_t)dst * K], wt->enc_w_ih[s] + (size_t)src * K, sizeof(float) * K);
                         memcpy(&whh[(size_t)dst * kEncH], wt->enc_w_hh[s] + (size_t)src * kEncH, sizeof(float) * kEncH);
                         bias[dst] = wt->enc_b_ih[s][src] + wt->enc_b_hh[s][src];
@@ -572,7 +573,6 @@ int asr_create(asr_handle** out, const asr_weights* wt, const asr_feature_consts
     for (int layer = 0; layer < 4; ++layer) {
         const int K = layer == 0 ? kFeat : kEnc;
         if ((rc = split_weight(h, h->w.enc_w_ih[layer], 2 * kGates, K, &h->w.enc_w_ih_hi[layer], &h->w.enc_w_ih_lo[layer])) != ASR_OK) return rc;
-        if ((rc = split_weight(h, h->w.enc_w_hh[layer], 2 * kGates, kEncH, &h->w.enc_w_hh_hi16[layer], &h->w.enc_w_hh_x[layer])) != ASR_OK) return rc;
     }
     if ((rc = split_weight(h, h->w.dec_w, 4 * kDecH, kDecK, &h->w.dec_w_hi, &h->w.dec_w_lo)) != ASR_OK) return rc;
     if ((rc = split_weight(h, h->w.proj_w, kVocab, kProjK, &h->w.proj_w_hi, &h->w.proj_w_lo)) != ASR_OK) return rc;

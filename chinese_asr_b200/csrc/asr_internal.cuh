@@ -171,10 +171,10 @@ struct FeatureConsts {
 struct PackedWeights {
     // encoder: per layer, both directions concatenated along N and permuted so that the 128
     // gate pre-activations a recurrence CTA needs are contiguous:
-    //   n' = dir*1024 + j*128 + gate*32 + uu   <->  reference row gate*256 + 32*j + uu
+    //   n' = dir*1024 + j*128 + 4*uu + gate   <->  reference row gate*256 + 32*j + uu
     float* enc_w_ih[4] = {};     // [2048, K_l]
     float* enc_bias[4] = {};     // [2048]  b_ih + b_hh, same permutation
-    float* enc_w_hh[4] = {};     // [2, 1024, 256] same permutation per direction
+    float* enc_w_hh[4] = {};     // [2, 1024, 256] same permutation per direction (split on the fly by encoder_tc3.cu)
     // decoder cell: [2048, 1280] = [W_ih | W_hh], rows interleaved n' = 4*u + gate
     float* dec_w = nullptr;
     float* dec_b = nullptr;      // [2048] b_ih + b_hh interleaved
@@ -194,8 +194,6 @@ struct PackedWeights {
     float* proj_w_lo = nullptr;
     hi_t* att_w_enc_t_hi = nullptr;
     float* att_w_enc_t_lo = nullptr;
-    hi_t* enc_w_hh_hi16[4] = {};         // [2, 1024, 256] fp16 hi + cross words of enc_w_hh (kSplitWeight): the
-    float* enc_w_hh_x[4] = {};           //   TMEM-resident recurrence (encoder_tc3.cu)
     float* att_w_hidden_t = nullptr;     // [128, 512] (W_hidden transposed -> [N, K]) for the query GEMM
     hi_t* att_w_hidden_t_hi = nullptr;
     float* att_w_hidden_t_lo = nullptr;

@@ -1,21 +1,24 @@
 // Tensor-core LSTM recurrence, weights fully resident in TENSOR MEMORY.
 //
-// An earlier engine kept W_hi in shared memory and re-read its 128 KB through the UMMA operand path
-// every step (measured: the 64 MMAs of a step were bound by ~64 B/clk of shared-memory operand
-// fetch, ~3.9k cycles).  Here the whole recurrent weight slice of a CTA lives in TMEM:
-//     columns [  0,128) : W_hi  = fp16(W_hh slice), 2 per column             128 lanes x 256 fp16
-//     columns [128,384) : W cross, per 8 values of k [8 x bf16(w) | 8 x bf16(w - w_hi)]   (4 bytes per k)
-//     columns [384,512) : fp32 accumulator D[128 gate cols, NB rows]
-// (the split-precision operands of gemm_tc.cu: kSplitWeight on the A side, kSplitAct on the h side), so
-// shared memory only holds the h operand tiles, which lets one cluster carry up to NB = 80 sequences
-// (one round of <= 15 clusters covers 2 directions x 512 sequences).  Per step 48 MMAs, all kind::f16:
-//     D += W_hi (TMEM, fp16) * h_hi^T                          16 x (K = 16 values of k)
-//     D += W_x  (TMEM, bf16) * [bf16(h_lo) | bf16(h)]^T        32 x (K = 16 = 8 values of k): w*h_lo + w_lo*h
-// (the tf32 form issued 80: an MMA costs ~65 cycles here whatever its shape).  The cross terms are 2^-11
-// of the product, which bf16's 2^-9 relative accuracy carries to ~2^-20.
-// Exchange of h_{t+1}: each CTA writes the image of its 32-unit slice
-// ([cross | hi] rows, already in the swizzled UMMA layouts) to global staging and multicasts it
-// with one cp.async.bulk into the tiles of all 8 CTAs; mbarriers only, no cluster barrier per step.
+// The whole recurrent weight slice of a CTA (128 gate rows x 256 k) lives in TMEM, split on the fly at kernel
+// start (gemm_tc.cu's fp16 hi part; the residual is carried as a second fp16, scaled by 2^11 into the range of
+// the value itself):
+//     columns [  0,128) : W_hi  = fp16(w), 2 per column                       128 lanes x 256 fp16
+//     columns [128,256) : W_lo' = fp16((w - W_hi) * 2^11)
+//     columns [256,256 + 2 NB) : fp32 accumulators D_hi[128 gate rows, NB sequences] | D_lo[128, NB]
+// Shared memory holds the h operand tile: per 32-wide K range a slab of 2 NB rows x 64 bytes (SWIZZLE_64B,
+// K-major), rows [0, NB) = fp16(h_hi), rows [NB, 2 NB) = fp16(h_lo * 2^11).  Per step 32 kind::f16 MMAs (two per
+// 16 values of k):
+//     [D_hi | D_lo] += W_hi  (TMEM) * [h_hi ; h_lo']^T      N = 2 NB  : w_hi h_hi  and  w_hi h_lo'
+//          D_lo     += W_lo' (TMEM) * h_hi^T                N = NB    : w_lo' h_hi
+// and the gate warps read  D_hi + 2^-11 D_lo.  An MMA with A in TMEM is paced by the fetch of its 128 lanes x
+// 32 bytes of A (~74 cycles whatever N is), so sharing one fetch of W_hi between the h_hi and h_lo' products
+// costs 32 A fetches per step where the [hi | bf16 cross] operand form (round 1 / early round 2: 16 fp16 + 32
+// bf16 MMAs over K = 8) paid 48; the exchanged image of h shrinks from 6 to 4 bytes per value, and the residual
+// products are rounded to 2^-11 relative (fp16) instead of 2^-9 (bf16): 2^-23 of the product.
+// Exchange of h_{t+1}: each CTA writes the image of its 32-unit slab (already in the swizzled UMMA layout) to
+// global staging and multicasts it with one cp.async.bulk into the tiles of all 8 CTAs; mbarriers only, no
+// cluster barrier per step.
 #include <cooperative_groups.h>
 #include <cuda_bf16.h>
 #include <stdlib.h>
@@ -72,19 +75,7 @@ __device__ __forceinline__ void bulk_g2s_multicast(void* dst_smem, const void* s
         ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
         : "memory");
 }
-// shared memory of this CTA -> shared memory of cluster CTA `rank` (same offsets), completion on the
-// destination CTA's mbarrier
-__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
-    return r;
-}
-__device__ __forceinline__ void bulk_s2s(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t bar_cluster) {
-    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst_cluster), "r"(src_cta), "r"(bytes), "r"(bar_cluster)
-                 : "memory");
-}
-// D[tmem] += A[tmem, bf16] * B[smem desc, bf16]
+// D[tmem] += A[tmem] * B[smem desc], kind::f16 (operand formats from the instruction descriptor)
 __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
                                              uint32_t accumulate) {
     asm volatile(
@@ -103,81 +94,56 @@ __device__ __forceinline__ uint64_t kmajor_sw64_desc(uint32_t smem_addr) {
     d |= (uint64_t)4 << 61;
     return d;
 }
-// byte offset of bf16 element (row, kk in 0..31) inside a [rows x 32 bf16] SWIZZLE_64B K-major slab
+// byte offset of 16-bit element (row, kk in 0..31) inside a [rows x 32] SWIZZLE_64B K-major slab
 __device__ __forceinline__ uint32_t sw64_offset(int row, int kk) {
     return (uint32_t)(row * 64 + ((((kk >> 3) ^ ((row >> 1) & 3)) << 4) | ((kk & 7) << 1)));
-}
-__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 // kind::f16 with fp16 operands (format 0)
 __host__ __device__ constexpr uint32_t idesc_f16(int M, int N) {
     return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-// byte offset of byte `b` (0..127) of row `row` inside a [rows x 128 B] SWIZZLE_128B K-major slab
-__device__ __forceinline__ uint32_t sw128_byte(int row, int b) {
-    return (uint32_t)(row * 128 + ((((b >> 4) ^ (row & 7)) << 4) | (b & 15)));
-}
-template <int N>
-__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t* r);
-template <>
-__device__ __forceinline__ void tmem_ld_cols<8>(uint32_t taddr, uint32_t* r) { tmem_ld8(taddr, r); }
-template <>
-__device__ __forceinline__ void tmem_ld_cols<16>(uint32_t taddr, uint32_t* r) { tmem_ld16(taddr, r); }
-template <>
-__device__ __forceinline__ void tmem_ld_cols<32>(uint32_t taddr, uint32_t* r) { tmem_ld32(taddr, r); }
-template <>
-__device__ __forceinline__ void tmem_ld_cols<4>(uint32_t taddr, uint32_t* r) {
+// tcgen05.ld of N consecutive accumulator columns (one TMEM lane per thread) WITHOUT the wait: several loads are
+// issued back to back and tmem_wait_ld() follows once.  The registers are defined only after that wait.
+__device__ __forceinline__ void tmem_ld4_nw(uint32_t taddr, uint32_t* r) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
                  : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-template <>
-__device__ __forceinline__ void tmem_ld_cols<10>(uint32_t taddr, uint32_t* r) {
-    tmem_ld8(taddr, r);
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];"
-                 : "=r"(r[8]), "=r"(r[9])
-                 : "r"(taddr + 8));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-template <>
-__device__ __forceinline__ void tmem_ld_cols<24>(uint32_t taddr, uint32_t* r) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
+__device__ __forceinline__ void tmem_ld8_nw(uint32_t taddr, uint32_t* r) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23])
-                 : "r"(taddr + 16));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
 }
-template <>
-__device__ __forceinline__ void tmem_ld_cols<20>(uint32_t taddr, uint32_t* r) {
+__device__ __forceinline__ void tmem_ld16_nw(uint32_t taddr, uint32_t* r) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr));
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19])
-                 : "r"(taddr + 16));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+template <int N>
+__device__ __forceinline__ void tmem_ld_cols_nowait(uint32_t taddr, uint32_t* r) {
+    static_assert(N % 4 == 0 && N >= 4 && N <= 32, "columns per warp");
+    if constexpr (N >= 16) {
+        tmem_ld16_nw(taddr, r);
+        if constexpr (N > 16) tmem_ld_cols_nowait<N - 16>(taddr + 16, r + 16);
+    } else if constexpr (N >= 8) {
+        tmem_ld8_nw(taddr, r);
+        if constexpr (N > 8) tmem_ld_cols_nowait<N - 8>(taddr + 8, r + 8);
+    } else {
+        tmem_ld4_nw(taddr, r);
+    }
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 constexpr int kThreads = 544;        // 16 gate warps + 1 MMA-issue warp
 constexpr int kIssueWarp = 16;
 
 struct Params {
-    const float* xg;            // [rows, 2048] permuted gate pre-activations (bias included)
-    const hi_t* whh_hi;         // [2, 1024, 256] permuted, fp16(W_hh)                       (gemm_tc.cu kSplitWeight)
-    const uint32_t* whh_x;      // [2, 1024, 256] words: per 8 k, 8 x bf16(w) then 8 x bf16(w - hi)
+    const float* xg;            // [rows, 2048] permuted gate pre-activations (bias included): column dir*1024 + j*128 + 4u + gate
+    const float* whh;           // [2, 1024, 256] fp32 W_hh, rows permuted like the xg columns
     const float* x_in;
-    int xchg_dsmem;         // 1: exchange h through distributed shared memory, 0: through global staging
     float* y_packed;
     float* y_utt;
     hi_t* y_hi;             // optional [rows, 512]: fp16(y), rows as y_utt when that is written, else as y_packed
@@ -194,8 +160,10 @@ struct Params {
     long long* dbg;
 };
 
-constexpr int kMaxNB = 128;              // sequences per cluster: the accumulator takes TMEM columns [384, 384 + NB)
-constexpr int kStageBytes = kMaxNB * 192;    // per-CTA staging slot (largest NB)
+constexpr int kMaxNB = 128;              // sequences per cluster: the accumulator takes TMEM columns [256, 256 + 2 NB)
+constexpr int kStageBytes = kMaxNB * 128;    // per-CTA staging slot (largest NB)
+constexpr float kLoScale = 2048.f;       // residuals are carried as fp16(lo * 2^11): |lo * 2^11| <= |x|, so they share x's range
+constexpr float kLoUnscale = 1.f / 2048.f;
 
 template <int NB>
 __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(kThreads, 1)
@@ -206,10 +174,8 @@ lstm_rec_tc3_kernel(Params p) {
     // (unit, batch row) - no shared-memory transposition and no block barrier in the gate phase.
     constexpr int CW = NB / 4;               // accumulator columns (batch rows) per warp
     constexpr int P = CW / 4;                // cells per lane: rows cg * CW + 4 b + (lane & 3)
-    constexpr int kX = NB * 128;             // bytes of one cross slab: 32 values of k x [bf16(h_lo) | bf16(h)]
-    constexpr int kHi = NB * 64;             // bytes of one fp16 hi slab
-    constexpr int kSlab = kX + kHi;          // [cross | hi] of one 32-wide K range
-    static_assert(NB % 16 == 0, "NB");
+    constexpr int kSlab = NB * 128;          // one 32-wide K range: [NB rows fp16(h_hi) | NB rows fp16(h_lo')] x 64 bytes
+    static_assert(NB % 16 == 0 && NB <= kMaxNB, "NB");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* T = smem;                                             // 8 slabs x kSlab
@@ -242,32 +208,26 @@ lstm_rec_tc3_kernel(Params p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_ax = tmem_base + 128;
-    const uint32_t tmem_d = tmem_base + 384;
+    const uint32_t tmem_alo = tmem_base + 128;
+    const uint32_t tmem_d = tmem_base + 256;
     if (warp < 4) {
-        const int m = 32 * warp + lane;                                          // TMEM lane = (unit m >> 2, gate m & 3)
-        const size_t wrow = (size_t)dir * kGates + j * 128 + (m & 3) * 32 + (m >> 2);
-        const uint32_t* whi = reinterpret_cast<const uint32_t*>(p.whh_hi + wrow * kEncH);     // 128 words of fp16 pairs
+        // TMEM lane m <- row dir*1024 + j*128 + m of the permuted W_hh, split on the fly: columns [0, 128) fp16(w)
+        // pairs, columns [128, 256) fp16((w - fp16(w)) * 2^11) pairs
+        const int m = 32 * warp + lane;
+        const float4* wrow = reinterpret_cast<const float4*>(p.whh + ((size_t)dir * kGates + j * 128 + m) * kEncH);
 #pragma unroll 1
-        for (int c0 = 0; c0 < kEncH / 2; c0 += 32) {
+        for (int c0 = 0; c0 < kEncH; c0 += 32) {           // c0 < 128: hi columns, else the residual columns
+            const bool lo = c0 >= kEncH / 2;
+            const int f0 = lo ? c0 - kEncH / 2 : c0;        // first fp16 pair column = float 2 f0
             uint32_t r[32];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const uint4 v = *reinterpret_cast<const uint4*>(whi + c0 + 4 * q);
-                r[4 * q] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
+            for (int q = 0; q < 16; ++q) {
+                const float4 v = __ldg(wrow + f0 / 2 + q);
+                const float h0 = hi_part(v.x), h1 = hi_part(v.y), h2 = hi_part(v.z), h3 = hi_part(v.w);
+                r[2 * q] = lo ? pack_hi2((v.x - h0) * kLoScale, (v.y - h1) * kLoScale) : pack_hi2(h0, h1);
+                r[2 * q + 1] = lo ? pack_hi2((v.z - h2) * kLoScale, (v.w - h3) * kLoScale) : pack_hi2(h2, h3);
             }
             tmem_st32(tmem_base + ((uint32_t)(32 * warp) << 16) + (uint32_t)c0, r);
-        }
-        const uint32_t* wx = p.whh_x + wrow * kEncH;                                          // 256 words
-#pragma unroll 1
-        for (int c0 = 0; c0 < kEncH; c0 += 32) {
-            uint32_t r[32];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const uint4 v = *reinterpret_cast<const uint4*>(wx + c0 + 4 * q);
-                r[4 * q] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
-            }
-            tmem_st32(tmem_ax + ((uint32_t)(32 * warp) << 16) + (uint32_t)c0, r);
         }
         tmem_wait_st();
     }
@@ -283,14 +243,20 @@ lstm_rec_tc3_kernel(Params p) {
     const int col0 = (warp >> 2) * CW + jr;           // batch row of cell b: col0 + 4 b
     const int ocol = dir * kEncH + 32 * j + uu;
     float c_reg[P], h_reg[P];
+    // byte offset of (row col0 + 4 q, unit) in the fp16 hi rows of the slab image: the swizzle phase repeats every
+    // 8 rows, so two bases (even / odd q) + 256 q
+    const uint32_t img_e = sw64_offset(col0, uu), img_o = sw64_offset(col0 + 4, uu) - 256u;
 #pragma unroll
-    for (int q = 0; q < P; ++q) { c_reg[q] = 0.f; h_reg[q] = 0.f; }
+    for (int q = 0; q < P; ++q) {
+        c_reg[q] = 0.f;
+        h_reg[q] = 0.f;
+    }
 
     cluster.sync();
 
     const uint32_t t_base = smem_u32(T);
-    constexpr uint32_t idesc_h = idesc_f16(128, NB);
-    constexpr uint32_t idesc_b = idesc_bf16(128, NB);
+    constexpr uint32_t idesc_2n = idesc_f16(128, 2 * NB);
+    constexpr uint32_t idesc_n = idesc_f16(128, NB);
 
     // rows are sorted by decreasing length: the active count follows t incrementally
     int nact = dir == 0 ? nrows : 0;
@@ -336,21 +302,16 @@ lstm_rec_tc3_kernel(Params p) {
                 if (s > 0) mbar_wait(h_ready, (uint32_t)((s - 1) & 1));
                 tc_fence_after();
                 if (p.dbg && blockIdx.x == 0) p.dbg[s * 8 + 0] = clock64();
-                const uint64_t dX0 = kmajor_sw128_desc(t_base);
-                const uint64_t dHi0 = kmajor_sw64_desc(t_base + kX);
-                // every MMA consumes 8 TMEM columns of A and 32 bytes of a B row.  The cross terms go first: the
-                // tensor core truncates every accumulation, and while the accumulator only holds the 2^-11-sized
-                // cross sum those 32 truncations are 2^-11 smaller; only the 16 hi MMAs truncate at full magnitude
-                // (measured on the GEMM engine: 3x less error than interleaving, gemm_tc.cu).
+                const uint64_t d0 = kmajor_sw64_desc(t_base);
+                // Per 16 values of k two MMAs, each reading 8 TMEM columns of A (the A fetch paces an MMA here, not
+                // its N): W_hi against both row blocks of the tile at once (N = 2 NB: accumulator columns [0, NB)
+                // += w_hi h_hi, [NB, 2 NB) += w_hi h_lo'), and W_lo' against the h_hi rows into [NB, 2 NB).  The full-
+                // magnitude sum sees 16 truncating accumulations, the 2^-11-sized cross sum its own 32.
 #pragma unroll
-                for (int kb = 0; kb < 32; ++kb) {        // 8 values of k each: w * h_lo + w_lo * h
-                    const uint64_t adv = (uint64_t)(((kb >> 2) * kSlab + (kb & 3) * 32) >> 4);
-                    umma_bf16_ts(tmem_d, tmem_ax + (uint32_t)(8 * kb), dX0 + adv, idesc_b, kb > 0 ? 1u : 0u);
-                }
-#pragma unroll
-                for (int kh = 0; kh < 16; ++kh) {        // 16 values of k each
-                    const uint64_t adv = (uint64_t)(((kh >> 1) * kSlab + (kh & 1) * 32) >> 4);
-                    umma_bf16_ts(tmem_d, tmem_base + (uint32_t)(8 * kh), dHi0 + adv, idesc_h, 1u);
+                for (int kh = 0; kh < 16; ++kh) {
+                    const uint64_t db = d0 + (uint64_t)(((kh >> 1) * kSlab + (kh & 1) * 32) >> 4);
+                    umma_bf16_ts(tmem_d, tmem_base + (uint32_t)(8 * kh), db, idesc_2n, kh > 0 ? 1u : 0u);
+                    umma_bf16_ts(tmem_d + (uint32_t)NB, tmem_alo + (uint32_t)(8 * kh), db, idesc_n, 1u);
                 }
                 umma_commit_mc(mma_done, (uint16_t)0xFF);
                 if (p.dbg && blockIdx.x == 0) p.dbg[s * 8 + 1] = clock64();
@@ -369,18 +330,16 @@ lstm_rec_tc3_kernel(Params p) {
         // covered by the MMAs in flight (measured: loading the residual inside the deferred store instead makes
         // the gate warps arrive ~500 cycles late at mma_done)
         if (s > 0) store_outputs(prev_t, prev_row_t, prev_nact);
-        float xi[P], xf[P], xgg[P], xo[P], xres[P];
+        float4 xg4[P];
+        float xres[P];
 #pragma unroll
         for (int q = 0; q < P; ++q) {
             const int i = col0 + 4 * q;
-            xi[q] = xf[q] = xgg[q] = xo[q] = xres[q] = 0.f;
+            xg4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            xres[q] = 0.f;
             if (i < nact) {
                 if (p.x_in) xres[q] = __ldg(p.x_in + (size_t)(row_t + i) * kEnc + ocol);
-                const float* g = p.xg + (size_t)(row_t + i) * (2 * kGates) + dir * kGates + j * 128 + uu;
-                xi[q] = __ldg(g);
-                xf[q] = __ldg(g + 32);
-                xgg[q] = __ldg(g + 64);
-                xo[q] = __ldg(g + 96);
+                xg4[q] = __ldg(reinterpret_cast<const float4*>(p.xg + (size_t)(row_t + i) * (2 * kGates) + dir * kGates + j * 128) + uu);
             }
         }
 
@@ -388,16 +347,40 @@ lstm_rec_tc3_kernel(Params p) {
         tc_fence_after();
         if (p.dbg && blockIdx.x == 0 && tid == 0) p.dbg[s * 8 + 2] = clock64();
         {
-            uint32_t d[CW];
-            tmem_ld_cols<CW>(tmem_d + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((warp >> 2) * CW), d);
+            // D_hi + 2^-11 D_lo, read in two column halves (both accumulators of a half in flight, one wait) to
+            // stay inside the 96 registers 17 warps leave per thread
+            constexpr int CA = 4 * ((P + 1) / 2), CB = CW - CA;
+            const uint32_t dcol = tmem_d + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((warp >> 2) * CW);
+            float d[CW];
+            {
+                uint32_t dh[CA], dl[CA];
+                tmem_ld_cols_nowait<CA>(dcol, dh);
+                tmem_ld_cols_nowait<CA>(dcol + (uint32_t)NB, dl);
+                tmem_wait_ld();
+#pragma unroll
+                for (int c = 0; c < CA; ++c) {
+                    asm volatile("" : "+r"(dh[c]), "+r"(dl[c]));      // defined only after the wait above
+                    d[c] = fmaf(__uint_as_float(dl[c]), kLoUnscale, __uint_as_float(dh[c]));
+                }
+            }
+            if constexpr (CB > 0) {
+                uint32_t dh[CB], dl[CB];
+                tmem_ld_cols_nowait<CB>(dcol + (uint32_t)CA, dh);
+                tmem_ld_cols_nowait<CB>(dcol + (uint32_t)(NB + CA), dl);
+                tmem_wait_ld();
+#pragma unroll
+                for (int c = 0; c < CB; ++c) {
+                    asm volatile("" : "+r"(dh[c]), "+r"(dl[c]));
+                    d[CA + c] = fmaf(__uint_as_float(dl[c]), kLoUnscale, __uint_as_float(dh[c]));
+                }
+            }
             tc_fence_before();
             const bool o1 = (jr & 1) != 0, o2 = (jr & 2) != 0;
 #pragma unroll
             for (int q = 0; q < P; ++q) {
                 // 4x4 transpose across the 4 lanes of a unit: in = this lane's gate for rows 4q..4q+3,
                 // out = gates i, f, g, o of row 4q + jr
-                const float v0 = __uint_as_float(d[4 * q]), v1 = __uint_as_float(d[4 * q + 1]);
-                const float v2 = __uint_as_float(d[4 * q + 2]), v3 = __uint_as_float(d[4 * q + 3]);
+                const float v0 = d[4 * q], v1 = d[4 * q + 1], v2 = d[4 * q + 2], v3 = d[4 * q + 3];
                 const float ra = __shfl_xor_sync(0xffffffffu, o1 ? v0 : v1, 1);
                 const float rb = __shfl_xor_sync(0xffffffffu, o1 ? v2 : v3, 1);
                 const float x0 = o1 ? ra : v0, x1 = o1 ? v1 : ra;
@@ -407,24 +390,16 @@ lstm_rec_tc3_kernel(Params p) {
                 const float di = o2 ? ua : x0, df = o2 ? ub : x1, dg = o2 ? x2 : ua, dO = o2 ? x3 : ub;
                 const int i = col0 + 4 * q;
                 if (i < nact) {
-                    const float gi = xi[q] + di;
-                    const float gf = xf[q] + df;
-                    const float gg = xgg[q] + dg;
-                    const float go = xo[q] + dO;
                     float c, hh;
-                    lstm_cell(gi, gf, gg, go, c_reg[q], c, hh);
+                    lstm_cell(xg4[q].x + di, xg4[q].y + df, xg4[q].z + dg, xg4[q].w + dO, c_reg[q], c, hh);
                     c_reg[q] = c;
                     h_reg[q] = hh;
                     const float hi = hi_part(hh);
-                    const float lo = hh - hi;
-                    // image of this CTA's 32-unit slab of the next B operand: into global staging, or (all
-                    // 8 CTAs' MMAs of this step are complete - mma_done counts 8 commits) straight into
-                    // the slab's place in the local operand tile
-                    uint8_t* img = p.xchg_dsmem ? T + j * kSlab : stage;
-                    const int xb = (uu >> 3) * 32 + (uu & 7) * 2;       // 8-k block: 16 bytes of bf16(h_lo), 16 of bf16(h)
-                    *reinterpret_cast<__nv_bfloat16*>(img + sw128_byte(i, xb)) = __float2bfloat16_rn(lo);
-                    *reinterpret_cast<__nv_bfloat16*>(img + sw128_byte(i, xb + 16)) = __float2bfloat16_rn(hh);
-                    *reinterpret_cast<__half*>(img + kX + sw64_offset(i, uu)) = __float2half_rn(hi);
+                    // image of this CTA's 32-unit slab of the next B operand, in global staging: fp16(h_hi) in
+                    // row i, fp16(h_lo * 2^11) in row NB + i (same swizzle phase: NB is a multiple of 8)
+                    uint8_t* img = stage + ((q & 1) ? img_o : img_e) + 256 * q;
+                    *reinterpret_cast<__half*>(img) = __float2half_rn(hi);
+                    *reinterpret_cast<__half*>(img + NB * 64) = __float2half_rn((hh - hi) * kLoScale);
                     yv[q] = hh + xres[q];
                 }
             }
@@ -432,30 +407,14 @@ lstm_rec_tc3_kernel(Params p) {
         }
         if (p.dbg && blockIdx.x == 0 && tid == 0) p.dbg[s * 8 + 4] = clock64();
         if (s + 1 < Lc) {
-            if (p.xchg_dsmem) {
-                // the local slab is in place; push it to the 7 peers with one bulk copy each (issued by 7
-                // different warps), each completing on the receiver's h_ready: no global round trip and
-                // no membar.gl on the step's critical path
-                fence_proxy_async();
-                __syncthreads();
-                if (p.dbg && blockIdx.x == 0 && tid == 0) p.dbg[s * 8 + 5] = clock64();
-                if (tid == 0) mbar_expect_tx(h_ready, 7u * (uint32_t)kSlab);
-                if (lane == 0 && warp >= 1 && warp <= 7) {
-                    const uint32_t peer = (uint32_t)((j + warp) & 7);
-                    const uint32_t src = smem_u32(T + j * kSlab);
-                    bulk_s2s(mapa_u32(src, peer), src, (uint32_t)kSlab, mapa_u32(smem_u32(h_ready), peer));
-                }
-                if (p.dbg && blockIdx.x == 0 && tid == 0) p.dbg[s * 8 + 6] = clock64();
-            } else {
-                __threadfence();
-                fence_proxy_async();
-                __syncthreads();
-                if (p.dbg && blockIdx.x == 0 && tid == 0) p.dbg[s * 8 + 5] = clock64();
-                if (tid == 0) {
-                    mbar_expect_tx(h_ready, 8u * (uint32_t)kSlab);
-                    bulk_g2s_multicast(T + j * kSlab, stage, (uint32_t)kSlab, h_ready, (uint16_t)0xFF);
-                    if (p.dbg && blockIdx.x == 0) p.dbg[s * 8 + 6] = clock64();
-                }
+            __threadfence();
+            fence_proxy_async();
+            __syncthreads();
+            if (p.dbg && blockIdx.x == 0 && tid == 0) p.dbg[s * 8 + 5] = clock64();
+            if (tid == 0) {
+                mbar_expect_tx(h_ready, 8u * (uint32_t)kSlab);
+                bulk_g2s_multicast(T + j * kSlab, stage, (uint32_t)kSlab, h_ready, (uint16_t)0xFF);
+                if (p.dbg && blockIdx.x == 0) p.dbg[s * 8 + 6] = clock64();
             }
         }
         prev_t = t; prev_row_t = row_t; prev_nact = nact;
@@ -480,7 +439,7 @@ lstm_rec_tc3_kernel(Params p) {
 
 template <int NB>
 static int launch(const Params& p, cudaStream_t st) {
-    const size_t smem = 8 * (size_t)(NB * 192) + 1024 + 64 + NB * 4;
+    const size_t smem = 8 * (size_t)(NB * 128) + 1024 + 64 + NB * 4;
     ASR_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&lstm_rec_tc3_kernel<NB>), smem));
     lstm_rec_tc3_kernel<NB><<<2 * p.nchunks * 8, kThreads, smem, st>>>(p);
     ASR_CHECK_LAUNCH();
@@ -496,12 +455,10 @@ int launch_lstm_recurrence_tc3(asr_handle* h, int layer, const float* xg, const 
                                float* split_lo) {
     const BatchMeta& m = h->meta;
     rec3::Params p{};
-    p.xchg_dsmem = 0;      // measured: 7 DSMEM bulk copies per CTA per step (10.9 -> 17.9 ms per batch) lose to one multicast from L2
     p.y_hi = split_hi;
     p.y_cross = reinterpret_cast<uint32_t*>(split_lo);
     p.xg = xg;
-    p.whh_hi = h->w.enc_w_hh_hi16[layer];
-    p.whh_x = reinterpret_cast<const uint32_t*>(h->w.enc_w_hh_x[layer]);
+    p.whh = h->w.enc_w_hh[layer];
     p.x_in = x_in;
     p.y_packed = y_packed;
     p.y_utt = y_utt;
@@ -514,11 +471,8 @@ int launch_lstm_recurrence_tc3(asr_handle* h, int layer, const float* xg, const 
     p.B = m.B;
     // <= 15 clusters of 8 CTAs are co-resident on a B200 (measured): aim at one round, i.e. at most
     // 7 chunks per direction, with the smallest operand tile that holds the chunk (up to 7 x 128 = 896
-    // sequences in one round; the step time grows with NB only through the gate phase and the exchange).
-    // h->rec_chunks < 7 (asr_set_recurrence_chunks) trades a longer step for fewer SMs.  Measured at 512 x 10 s
-    // (ms per batch, SMs): 7 chunks 7.2 on 112; 6 chunks (96 sequences per cluster) 8.0 on 96; 4 chunks (128 per
-    // cluster) 10.8 - 13.6 on 64: the gate phase is issue-bound and grows faster than the chunk, so 7 stays the
-    // default and the knob is for experiments only.
+    // sequences in one round; the step time grows with NB through the gate phase and the exchange).
+    // h->rec_chunks < 7 (asr_set_recurrence_chunks) trades a longer step for fewer SMs.
     const int chunks = h->rec_chunks < 1 ? 1 : (h->rec_chunks > 7 ? 7 : h->rec_chunks);
     int rows = (m.B + chunks - 1) / chunks;
     int NB = rows <= 16 ? 16 : rows <= 32 ? 32 : rows <= 64 ? 64 : rows <= 80 ? 80 : rows <= 96 ? 96 : 128;
