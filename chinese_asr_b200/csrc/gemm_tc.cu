@@ -94,6 +94,20 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
     return r;
 }
+// one lane of a converged warp (the same one every time): the guard of the single-thread TMA / MMA instructions.
+// The loops around them run on all 32 lanes with warp-uniform values so that descriptors, coordinates and barrier
+// addresses live in uniform registers; under `if (lane == 0)` around the whole loop ptxas could not prove that
+// and wrapped every UTCHMMA / UTMALDG in an ELECT + 7 x R2UR + BRA.U.ANY loop (ncu r02c: the MMA issue loop, not
+// the epilogue, paced the vocabulary GEMM).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -246,13 +260,14 @@ gemm_split_pair_kernel(const __grid_constant__ CUtensorMap map_a_x, const __grid
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
     constexpr int kTmemCols = 2 * BN > 256 ? 512 : 2 * BN;
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);      // warp-uniform for the compiler
+    const int lane = threadIdx.x & 31;
     const int tiles_n = (N + BN - 1) / BN;
     const int mgroups = ((M + BM - 1) / BM + 1) / 2;          // pairs of vertically adjacent 128-row tiles
     const int nwork = mgroups * tiles_n;
     const int nkx = (K + 31) / 32;                            // cross slabs: 32 values of k per 128-byte row
     const int nkh = (K + 63) / 64;                            // hi slabs: 64 values of k per 128-byte row
-    const int crank = (int)cluster_ctarank();
+    const int crank = (int)(blockIdx.x & 1);                  // == %cluster_ctarank: 1-D grid of 2-CTA clusters
     const int work0 = blockIdx.x >> 1, work_step = gridDim.x >> 1;
 
     if (warp == 0 && lane == 0) {
@@ -273,7 +288,7 @@ gemm_split_pair_kernel(const __grid_constant__ CUtensorMap map_a_x, const __grid
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     cluster_sync_all();                                        // the peer's barriers are initialised too
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     // everything above touched no global memory: it overlaps the tail of the previous kernel in the stream
     griddep_wait();
     const bool stopped = epi.stop_flag && *epi.stop_flag >= 0;      // early stop of the decode loop (model.py:578, 897)
@@ -281,31 +296,33 @@ gemm_split_pair_kernel(const __grid_constant__ CUtensorMap map_a_x, const __grid
     if (stopped) {
         // nothing to do: fall through to the common exit (cluster barrier, TMEM release)
     } else if (warp == 0) {
-        if (lane == 0) {
-            int it = 0;
-            for (int work = work0; work < nwork; work += work_step) {
-                const int m0 = ((work / tiles_n) * 2 + crank) * BM;
-                const int nrow = (work % tiles_n) * BN + crank * (BN / 2);
+        // all 32 lanes run the loop (uniform values), one elected lane issues the copies
+        int it = 0;
+        for (int work = work0; work < nwork; work += work_step) {
+            const int m0 = ((work / tiles_n) * 2 + crank) * BM;
+            const int nrow = (work % tiles_n) * BN + crank * (BN / 2);
 #pragma unroll 1
-                for (int pass = 0; pass < 2; ++pass) {
-                    const CUtensorMap* ma = pass == 0 ? &map_a_x : &map_a_h;
-                    const CUtensorMap* mw = pass == 0 ? &map_w_x : &map_w_h;
-                    const int nk = pass == 0 ? nkx : nkh, kstep = pass == 0 ? 32 : 64;
-                    for (int kb = 0; kb < nk; ++kb, ++it) {
-                        const int s = it % STAGES;
-                        mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
-                        uint8_t* st = smem + s * L::kStage;
+            for (int pass = 0; pass < 2; ++pass) {
+                const CUtensorMap* ma = pass == 0 ? &map_a_x : &map_a_h;
+                const CUtensorMap* mw = pass == 0 ? &map_w_x : &map_w_h;
+                const int nk = pass == 0 ? nkx : nkh, kstep = pass == 0 ? 32 : 64;
+                for (int kb = 0; kb < nk; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+                    uint8_t* st = smem + s * L::kStage;
+                    const uint32_t fb = mapa_rank(smem_u32(&full[s]), 0);
+                    if (elect_one()) {
                         // both CTAs' bytes complete on the LEADER's barrier (its MMA warp consumes both halves)
                         if (crank == 0) mbar_expect_tx(&full[s], 2 * L::kStage);
-                        const uint32_t fb = mapa_rank(smem_u32(&full[s]), 0);
                         tma_load_2d_2sm(ma, fb, st, kb * kstep, m0);
                         tma_load_2d_2sm(mw, fb, st + L::kATile, kb * kstep, nrow);
                     }
+                    __syncwarp();
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && crank == 0) {                         // only the leader CTA issues
+        if (crank == 0) {                                      // only the leader CTA issues
             constexpr uint32_t idesc_h = make_idesc_f16(2 * BM, BN);
             constexpr uint32_t idesc_x = make_idesc_bf16(2 * BM, BN);
             int it = 0, lt = 0;
@@ -326,17 +343,21 @@ gemm_split_pair_kernel(const __grid_constant__ CUtensorMap map_a_x, const __grid
                         uint8_t* st = smem + s * L::kStage;
                         const uint64_t d_a = make_kmajor_desc(st);
                         const uint64_t d_w = make_kmajor_desc(st + L::kATile);
-                        // every MMA consumes 32 bytes of K per row: 8 values of k of the cross operand, 16 of hi
+                        if (elect_one()) {
+                            // every MMA consumes 32 bytes of K per row: 8 values of k of the cross operand, 16 of hi
 #pragma unroll
-                        for (int kk = 0; kk < 4; ++kk) {
-                            const uint64_t adv = (uint64_t)((kk * 32) >> 4);
-                            umma2_f16(tacc, d_a + adv, d_w + adv, idesc, first);
-                            first = 1u;
+                            for (int kk = 0; kk < 4; ++kk) {
+                                const uint64_t adv = (uint64_t)((kk * 32) >> 4);
+                                umma2_f16(tacc, d_a + adv, d_w + adv, idesc, kk == 0 ? first : 1u);
+                            }
+                            umma2_commit_mc(&empty[s], 3);
                         }
-                        umma2_commit_mc(&empty[s], 3);
+                        __syncwarp();
+                        first = 1u;
                     }
                 }
-                umma2_commit_mc(&tfull[acc], 3);
+                if (elect_one()) umma2_commit_mc(&tfull[acc], 3);
+                __syncwarp();
             }
         }
     } else {
