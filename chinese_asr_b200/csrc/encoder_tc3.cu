@@ -44,19 +44,37 @@ __device__ __forceinline__ float rcp_f(float x) {
 // 1/A and 1/G from one rcp(A G), and s(o) tanh(c') = (C - 2) / (O C) with C = e^(2c') + 1 from one rcp(O C) -
 // 5 ex2 + 3 rcp per cell instead of 5 + 5.  Arguments are clamped to +-40 (s, tanh are saturated to fp32 there) so
 // that no product of two denominators overflows.  Relative error ~3 ulp per factor, like the unshared form.
+__device__ __forceinline__ float ex2_f(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ void lstm_cell(float gi, float gf, float gg, float go, float c_prev, float& c, float& h) {
-    const float A = 1.f + __expf(-fmaxf(gi, -40.f));
-    const float Bf = 1.f + __expf(-fmaxf(gf, -40.f));
-    const float G = __expf(2.f * fminf(gg, 20.f)) + 1.f;
-    const float O = 1.f + __expf(-fmaxf(go, -40.f));
+    // e^x = ex2(x log2 e) without __expf's denormal-range rescaling (a compare and two predicated multiplies per
+    // call): every argument is clamped, so no result is denormal or infinite
+    constexpr float kL2e = 1.4426950408889634f;
+    const float A = 1.f + ex2_f(-kL2e * fmaxf(gi, -40.f));
+    const float Bf = 1.f + ex2_f(-kL2e * fmaxf(gf, -40.f));
+    const float G = ex2_f((2.f * kL2e) * fminf(gg, 20.f)) + 1.f;
+    const float O = 1.f + ex2_f(-kL2e * fmaxf(go, -40.f));
     const float r = rcp_f(A * G);
     const float si = r * G;                       // 1 / A
     const float tg = 1.f - 2.f * (r * A);         // 1 - 2 / G
     c = rcp_f(Bf) * c_prev + si * tg;
-    const float C = __expf(2.f * fminf(c, 20.f)) + 1.f;
+    const float C = ex2_f((2.f * kL2e) * fminf(fmaxf(c, -40.f), 20.f)) + 1.f;
     h = (C - 2.f) * rcp_f(O * C);
 }
 
+// one lane of a converged warp: the guard of the single-thread MMA / commit instructions (see gemm_tc.cu)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
     asm volatile(
         "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -165,7 +183,9 @@ constexpr int kStageBytes = kMaxNB * 128;    // per-CTA staging slot (largest NB
 constexpr float kLoScale = 2048.f;       // residuals are carried as fp16(lo * 2^11): |lo * 2^11| <= |x|, so they share x's range
 constexpr float kLoUnscale = 1.f / 2048.f;
 
-template <int NB>
+// HAS_RES: the layer has a residual input (layers 1-3, util.py:1284-1291).  LAST: the output goes out utterance-major
+// (the encoder memory `enc` and the keys GEMM's split operand); otherwise packed time-major for the next layer.
+template <int NB, bool HAS_RES, bool LAST>
 __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(kThreads, 1)
 lstm_rec_tc3_kernel(Params p) {
     // 16 warps: warp = (TMEM lane quarter q = warp & 3, column group warp >> 2).  TMEM lane m of the CTA's
@@ -175,11 +195,13 @@ lstm_rec_tc3_kernel(Params p) {
     constexpr int CW = NB / 4;               // accumulator columns (batch rows) per warp
     constexpr int P = CW / 4;                // cells per lane: rows cg * CW + 4 b + (lane & 3)
     constexpr int kSlab = NB * 128;          // one 32-wide K range: [NB rows fp16(h_hi) | NB rows fp16(h_lo')] x 64 bytes
+    constexpr int kTrStride = 40;            // floats per transposition row: 32 lanes + 8 (conflict-free 16-byte reads)
     static_assert(NB % 16 == 0 && NB <= kMaxNB, "NB");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* T = smem;                                             // 8 slabs x kSlab
-    uint64_t* mma_done = reinterpret_cast<uint64_t*>(T + 8 * kSlab);
+    float* s_tr = reinterpret_cast<float*>(T + 8 * kSlab);         // [16 gate warps][CW][kTrStride] gate transposition
+    uint64_t* mma_done = reinterpret_cast<uint64_t*>(s_tr + 16 * CW * kTrStride);
     uint64_t* h_ready = mma_done + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h_ready + 1);
     int* s_len = reinterpret_cast<int*>(tmem_slot + 1);            // [NB]
@@ -189,7 +211,8 @@ lstm_rec_tc3_kernel(Params p) {
     const int cid = blockIdx.x / 8;
     const int dir = cid / p.nchunks;
     const int chunk = cid - dir * p.nchunks;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);       // warp-uniform for the compiler (uniform registers)
     const int r0 = chunk * p.rows_per_chunk;
     const int nrows = min(p.rows_per_chunk, p.B - r0);
     uint8_t* stage = p.stage + (size_t)blockIdx.x * kStageBytes;
@@ -207,7 +230,7 @@ lstm_rec_tc3_kernel(Params p) {
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     const uint32_t tmem_alo = tmem_base + 128;
     const uint32_t tmem_d = tmem_base + 256;
     if (warp < 4) {
@@ -246,11 +269,16 @@ lstm_rec_tc3_kernel(Params p) {
     // byte offset of (row col0 + 4 q, unit) in the fp16 hi rows of the slab image: the swizzle phase repeats every
     // 8 rows, so two bases (even / odd q) + 256 q
     const uint32_t img_e = sw64_offset(col0, uu), img_o = sw64_offset(col0 + 4, uu) - 256u;
+    int uo[LAST ? P : 1];                             // LAST: first utterance-major row of the cell's sequence
 #pragma unroll
     for (int q = 0; q < P; ++q) {
         c_reg[q] = 0.f;
         h_reg[q] = 0.f;
+        if (LAST) uo[q] = col0 + 4 * q < nrows ? p.uoff[r0 + col0 + 4 * q] : 0;
     }
+    // this warp's transposition rows (gate warps only), as a shared-window address: the 1024-byte alignment of the
+    // dynamic shared memory hides the address space from the compiler, and generic LD / ST are slower than LDS / STS
+    const uint32_t tr = smem_u32(s_tr) + (uint32_t)(warp * (CW * kTrStride) * 4);
 
     cluster.sync();
 
@@ -264,49 +292,53 @@ lstm_rec_tc3_kernel(Params p) {
     float yv[P];
 #pragma unroll
     for (int q = 0; q < P; ++q) yv[q] = 0.f;
-    // layer output of one step: y = h + residual input (util.py:1284-1291), and optionally its operand split
-    // for the next GEMM.  Called one step late (after the next step's MMAs are issued) so that it never delays them.
+    // word of this unit's bf16 pair inside its 8-float block of the cross operand, relative to the element index:
+    // even units pack the two residuals (words 0-3), odd units the two values (words 4-7)
+    const bool odd = (ocol & 1) != 0;
+    const int cross_adj = (odd ? 4 : 0) + ((ocol & 7) >> 1) - (ocol & 7);
+    // layer output of one step: y = h + residual input (util.py:1284-1291) and its operand split for the next
+    // GEMM.  Called one step late (after the next step's MMAs are issued) so that it never delays them.  Element
+    // indices fit 32 bits (rows x 512 < 2^32 for any batch the workspace holds).
     auto store_outputs = [&](int t, int row_t, int n_act) {
 #pragma unroll
         for (int q = 0; q < P; ++q) {
             const int i = col0 + 4 * q;
-            const bool act = i < n_act;
             const float y = yv[q];
-            // operand split for the consuming GEMM: the lane 4 away holds the neighbouring unit of the
-            // same row; even units pack the two residuals, odd units the two values (bf16 pairs)
-            const float hi = hi_part(y);
+            // the lane 4 away holds the neighbouring unit of the same row
+            const float hi = __half2float(__float2half_rn(y));          // |y| <= 1 + |x|: far inside fp16's range
             const float lo = y - hi;
             const float lo_n = __shfl_xor_sync(0xffffffffu, lo, 4);
             const float y_n = __shfl_xor_sync(0xffffffffu, y, 4);
-            if (act) {
-                const size_t row = (size_t)(row_t + i);
-                const size_t urow = p.y_utt ? (size_t)(p.uoff[r0 + i] + t) : 0;
-                if (p.y_packed) p.y_packed[row * kEnc + ocol] = y;
-                if (p.y_utt) p.y_utt[urow * kEnc + ocol] = y;
-                if (p.y_hi) {
-                    const size_t srow = p.y_utt ? urow : row;      // last layer: rows as `enc`
-                    p.y_hi[srow * kEnc + ocol] = __float2half_rn(hi);
-                    const bool odd = (ocol & 1) != 0;
-                    const __nv_bfloat162 pk = odd ? __floats2bfloat162_rn(y_n, y) : __floats2bfloat162_rn(lo, lo_n);
-                    // block of 8 floats -> 8 words: words 0-3 residual pairs, words 4-7 value pairs
-                    uint32_t* blk = p.y_cross + srow * kEnc + (size_t)(ocol & ~7);
-                    blk[(odd ? 4 : 0) + ((ocol & 7) >> 1)] = *reinterpret_cast<const uint32_t*>(&pk);
+            if (i < n_act) {
+                const uint32_t e = (uint32_t)(row_t + i) * kEnc + ocol;
+                uint32_t se = e;                                         // element index in the split operand
+                if (LAST) {
+                    se = (uint32_t)(uo[q] + t) * kEnc + ocol;            // rows as `enc`
+                    p.y_utt[se] = y;
+                    if (p.y_packed) p.y_packed[e] = y;
+                } else {
+                    p.y_packed[e] = y;
                 }
+                p.y_hi[se] = __float2half_rn(hi);
+                const __nv_bfloat162 pk = odd ? __floats2bfloat162_rn(y_n, y) : __floats2bfloat162_rn(lo, lo_n);
+                p.y_cross[(int)se + cross_adj] = *reinterpret_cast<const uint32_t*>(&pk);
             }
         }
     };
 
     for (int s = 0; s < Lc; ++s) {
         if (warp == kIssueWarp) {
-            if (lane == 0) {
-                if (s > 0) mbar_wait(h_ready, (uint32_t)((s - 1) & 1));
-                tc_fence_after();
-                if (p.dbg && blockIdx.x == 0) p.dbg[s * 8 + 0] = clock64();
-                const uint64_t d0 = kmajor_sw64_desc(t_base);
-                // Per 16 values of k two MMAs, each reading 8 TMEM columns of A (the A fetch paces an MMA here, not
-                // its N): W_hi against both row blocks of the tile at once (N = 2 NB: accumulator columns [0, NB)
-                // += w_hi h_hi, [NB, 2 NB) += w_hi h_lo'), and W_lo' against the h_hi rows into [NB, 2 NB).  The full-
-                // magnitude sum sees 16 truncating accumulations, the 2^-11-sized cross sum its own 32.
+            // all 32 lanes wait (uniform control flow keeps descriptors and TMEM addresses in uniform registers),
+            // one elected lane issues
+            if (s > 0) mbar_wait(h_ready, (uint32_t)((s - 1) & 1));
+            tc_fence_after();
+            if (p.dbg && blockIdx.x == 0 && lane == 0) p.dbg[s * 8 + 0] = clock64();
+            const uint64_t d0 = kmajor_sw64_desc(t_base);
+            if (elect_one()) {
+                // Per 16 values of k two MMAs, each reading 8 TMEM columns of A: W_hi against both row blocks of the
+                // tile at once (N = 2 NB: accumulator columns [0, NB) += w_hi h_hi, [NB, 2 NB) += w_hi h_lo'), and
+                // W_lo' against the h_hi rows into [NB, 2 NB).  The full-magnitude sum sees 16 truncating
+                // accumulations, the 2^-11-sized cross sum its own 32.
 #pragma unroll
                 for (int kh = 0; kh < 16; ++kh) {
                     const uint64_t db = d0 + (uint64_t)(((kh >> 1) * kSlab + (kh & 1) * 32) >> 4);
@@ -314,9 +346,9 @@ lstm_rec_tc3_kernel(Params p) {
                     umma_bf16_ts(tmem_d + (uint32_t)NB, tmem_alo + (uint32_t)(8 * kh), db, idesc_n, 1u);
                 }
                 umma_commit_mc(mma_done, (uint16_t)0xFF);
-                if (p.dbg && blockIdx.x == 0) p.dbg[s * 8 + 1] = clock64();
             }
             __syncwarp();
+            if (p.dbg && blockIdx.x == 0 && lane == 0) p.dbg[s * 8 + 1] = clock64();
         }
 
         const int t = dir == 0 ? s : Lc - 1 - s;
@@ -338,8 +370,9 @@ lstm_rec_tc3_kernel(Params p) {
             xg4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
             xres[q] = 0.f;
             if (i < nact) {
-                if (p.x_in) xres[q] = __ldg(p.x_in + (size_t)(row_t + i) * kEnc + ocol);
-                xg4[q] = __ldg(reinterpret_cast<const float4*>(p.xg + (size_t)(row_t + i) * (2 * kGates) + dir * kGates + j * 128) + uu);
+                const uint32_t r = (uint32_t)(row_t + i);
+                if (HAS_RES) xres[q] = __ldg(p.x_in + r * kEnc + ocol);
+                xg4[q] = __ldg(reinterpret_cast<const float4*>(p.xg + (size_t)r * (2 * kGates) + dir * kGates + j * 128) + uu);
             }
         }
 
@@ -375,26 +408,26 @@ lstm_rec_tc3_kernel(Params p) {
                 }
             }
             tc_fence_before();
-            const bool o1 = (jr & 1) != 0, o2 = (jr & 2) != 0;
+            // 4 x 4 transposition through this warp's shared-memory rows: lane L (unit L >> 2, gate L & 3) writes its
+            // gate of row c to tr[c][L]; the lane of cell (unit, row 4 q + jr) reads gates i, f, g, o as one float4
+            // (20 STS + 5 LDS.128 per lane and step where warp shuffles took 30 SHFL + 60 FSEL)
+#pragma unroll
+            for (int c = 0; c < CW; ++c)
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(tr + (uint32_t)((c * kTrStride + lane) * 4)), "f"(d[c]) : "memory");
+            __syncwarp();
 #pragma unroll
             for (int q = 0; q < P; ++q) {
-                // 4x4 transpose across the 4 lanes of a unit: in = this lane's gate for rows 4q..4q+3,
-                // out = gates i, f, g, o of row 4q + jr
-                const float v0 = d[4 * q], v1 = d[4 * q + 1], v2 = d[4 * q + 2], v3 = d[4 * q + 3];
-                const float ra = __shfl_xor_sync(0xffffffffu, o1 ? v0 : v1, 1);
-                const float rb = __shfl_xor_sync(0xffffffffu, o1 ? v2 : v3, 1);
-                const float x0 = o1 ? ra : v0, x1 = o1 ? v1 : ra;
-                const float x2 = o1 ? rb : v2, x3 = o1 ? v3 : rb;
-                const float ua = __shfl_xor_sync(0xffffffffu, o2 ? x0 : x2, 2);
-                const float ub = __shfl_xor_sync(0xffffffffu, o2 ? x1 : x3, 2);
-                const float di = o2 ? ua : x0, df = o2 ? ub : x1, dg = o2 ? x2 : ua, dO = o2 ? x3 : ub;
+                float di, df, dg, dO;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                             : "=f"(di), "=f"(df), "=f"(dg), "=f"(dO)
+                             : "r"(tr + (uint32_t)(((4 * q + jr) * kTrStride + 4 * (lane >> 2)) * 4)));
                 const int i = col0 + 4 * q;
                 if (i < nact) {
                     float c, hh;
                     lstm_cell(xg4[q].x + di, xg4[q].y + df, xg4[q].z + dg, xg4[q].w + dO, c_reg[q], c, hh);
                     c_reg[q] = c;
                     h_reg[q] = hh;
-                    const float hi = hi_part(hh);
+                    const float hi = __half2float(__float2half_rn(hh));      // |h| < 1
                     // image of this CTA's 32-unit slab of the next B operand, in global staging: fp16(h_hi) in
                     // row i, fp16(h_lo * 2^11) in row NB + i (same swizzle phase: NB is a multiple of 8)
                     uint8_t* img = stage + ((q & 1) ? img_o : img_e) + 256 * q;
@@ -407,8 +440,10 @@ lstm_rec_tc3_kernel(Params p) {
         }
         if (p.dbg && blockIdx.x == 0 && tid == 0) p.dbg[s * 8 + 4] = clock64();
         if (s + 1 < Lc) {
-            __threadfence();
-            fence_proxy_async();
+            // the image stores (generic proxy) must be performed before the bulk copy (async proxy) of thread 0 reads
+            // them: every writer fences generic -> async for global memory, then the CTA barrier orders the copy after
+            // all of them.  (A __threadfence() in front of it, as up to round 2, costs a second MEMBAR.GPU per step.)
+            asm volatile("fence.proxy.async.global;" ::: "memory");
             __syncthreads();
             if (p.dbg && blockIdx.x == 0 && tid == 0) p.dbg[s * 8 + 5] = clock64();
             if (tid == 0) {
@@ -437,13 +472,18 @@ lstm_rec_tc3_kernel(Params p) {
     }
 }
 
-template <int NB>
-static int launch(const Params& p, cudaStream_t st) {
-    const size_t smem = 8 * (size_t)(NB * 128) + 1024 + 64 + NB * 4;
-    ASR_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&lstm_rec_tc3_kernel<NB>), smem));
-    lstm_rec_tc3_kernel<NB><<<2 * p.nchunks * 8, kThreads, smem, st>>>(p);
+template <int NB, bool HAS_RES, bool LAST>
+static int launch_mode(const Params& p, cudaStream_t st) {
+    const size_t smem = 8 * (size_t)(NB * 128) + 1024 + 64 + NB * 4 + 16 * (size_t)(NB / 4) * 40 * 4;
+    ASR_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&lstm_rec_tc3_kernel<NB, HAS_RES, LAST>), smem));
+    lstm_rec_tc3_kernel<NB, HAS_RES, LAST><<<2 * p.nchunks * 8, kThreads, smem, st>>>(p);
     ASR_CHECK_LAUNCH();
     return ASR_OK;
+}
+template <int NB>
+static int launch(const Params& p, cudaStream_t st) {
+    if (p.y_utt) return launch_mode<NB, true, true>(p, st);
+    return p.x_in ? launch_mode<NB, true, false>(p, st) : launch_mode<NB, false, false>(p, st);
 }
 
 }  // namespace rec3
@@ -469,6 +509,7 @@ int launch_lstm_recurrence_tc3(asr_handle* h, int layer, const float* xg, const 
     p.toff = m.d_toff;
     p.uoff = m.d_uoff_sorted;
     p.B = m.B;
+    if (!split_hi || !split_lo || !y_packed || (y_utt && !x_in)) { set_error("recurrence: missing output buffer"); return ASR_ERR_ARG; }
     // <= 15 clusters of 8 CTAs are co-resident on a B200 (measured): aim at one round, i.e. at most
     // 7 chunks per direction, with the smallest operand tile that holds the chunk (up to 7 x 128 = 896
     // sequences in one round; the step time grows with NB through the gate phase and the exchange).
