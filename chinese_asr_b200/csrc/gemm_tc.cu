@@ -177,8 +177,32 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo_half, float hi_half) {
 // The epilogue runs on 4 warps per SM: libm expf / tanhf / IEEE division are long dependent chains with
 // slow-path branches that one warp per scheduler cannot overlap (measured: ~10k cycles per 32-column
 // chunk).  ex2.approx / rcp.approx forms (2 ulp) are branch-free; the encoder recurrence uses the same.
-__device__ __forceinline__ float sigm(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
-__device__ __forceinline__ float tanh_e(float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); }
+// One LSTM cell (nn.LSTMCell: c' = s(f) c + s(i) tanh(g), h' = s(o) tanh(c')) - the form the encoder recurrence uses
+// (encoder_tc3.cu): 5 ex2.approx.ftz + 3 rcp.approx with shared reciprocals (1/A and 1/G from one rcp(A G),
+// s(o) tanh(c') = (C - 2) / (O C)), arguments clamped so that no denominator product overflows.
+__device__ __forceinline__ float ex2_fast(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float rcp_fast(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void lstm_cell_fast(float gi, float gf, float gg, float go, float c_prev, float& c, float& h) {
+    constexpr float kL2e = 1.4426950408889634f;
+    const float A = 1.f + ex2_fast(-kL2e * fmaxf(gi, -40.f));
+    const float Bf = 1.f + ex2_fast(-kL2e * fmaxf(gf, -40.f));
+    const float G = ex2_fast((2.f * kL2e) * fminf(gg, 20.f)) + 1.f;
+    const float O = 1.f + ex2_fast(-kL2e * fmaxf(go, -40.f));
+    const float r = rcp_fast(A * G);
+    const float si = r * G;                       // 1 / A
+    const float tg = 1.f - 2.f * (r * A);         // 1 - 2 / G
+    c = rcp_fast(Bf) * c_prev + si * tg;
+    const float C = ex2_fast((2.f * kL2e) * fminf(fmaxf(c, -40.f), 20.f)) + 1.f;
+    h = (C - 2.f) * rcp_fast(O * C);
+}
 
 // Sorting networks on registers (all indices compile-time): the vocabulary epilogue keeps the KP largest
 // logits of a row by sorting every group of KP new values and merging it into the running list - about
@@ -223,7 +247,7 @@ __device__ __forceinline__ void merge_top_desc(float (&t)[N], const float (&b)[N
     }
 }
 
-template <int BN, int STAGES, int KP = 0>
+template <int BN, int STAGES, int KP = 0, bool LSTM = false>
 struct SmemLayout {
     static constexpr int kATile = BM * 128;             // 128 rows x 128 bytes (32 cross words or 64 fp16 values of k)
     static constexpr int kWTile = (BN / 2) * 128;       // this CTA's half of the W tile
@@ -232,8 +256,11 @@ struct SmemLayout {
     // KP = 0: per epilogue warp 32 rows x (32 + 4) floats (transpose for coalesced stores);
     // KP > 0: 8 epilogue warps, each its half of the bias tile (128 floats) + 32 lanes x (KP + 1) floats to hand its
     // top-KP list to the warp that shares its rows
-    static constexpr int kEpiWarps = KP > 0 ? 8 : 4;
-    static constexpr int kScratch = KP > 0 ? 8 * (128 + 32 * (KP + 1)) * 4 : 4 * 32 * 36 * 4;
+    // the vocabulary and LSTM-cell epilogues run on 8 warps (two per TMEM lane quarter, each half of the columns):
+    // their per-tile work is long enough that, with one warp per scheduler, the epilogue of a CTA's LAST tile - which
+    // nothing overlaps - was as long as the tile's main loop (ncu r02c: cell GEMM 56 us for 31 us of MMAs)
+    static constexpr int kEpiWarps = (KP > 0 || LSTM) ? 8 : 4;
+    static constexpr int kScratch = KP > 0 ? 8 * (128 + 32 * (KP + 1)) * 4 : (LSTM ? 0 : 4 * 32 * 36 * 4);
     static constexpr int kThreads = 64 + 32 * kEpiWarps;
     static constexpr int kBytes = STAGES * kStage + kScratch + 1024 /*align slack*/ + 256 /*barriers*/;
     static_assert((2 * STAGES + 4) * 8 + 8 <= 256, "barrier block");
@@ -242,13 +269,13 @@ struct SmemLayout {
 
 // KP = 0: bias / LSTM-cell epilogues (epi.kind); KP > 0: the vocabulary epilogue keeping the top-KP logits of
 // every (row, tile).  A separate instantiation keeps its 2 x KP + 32 live registers away from the others.
-template <int BN, int STAGES, int KP>
-__global__ void __launch_bounds__((SmemLayout<BN, STAGES, KP>::kThreads), 1)
+template <int BN, int STAGES, int KP, bool LSTM>
+__global__ void __launch_bounds__((SmemLayout<BN, STAGES, KP, LSTM>::kThreads), 1)
 gemm_split_pair_kernel(const __grid_constant__ CUtensorMap map_a_x, const __grid_constant__ CUtensorMap map_a_h,
                        const __grid_constant__ CUtensorMap map_w_x, const __grid_constant__ CUtensorMap map_w_h,
                        int M, int N, int K, GemmEpilogue epi) {
     griddep_launch_dependents();
-    using L = SmemLayout<BN, STAGES, KP>;
+    using L = SmemLayout<BN, STAGES, KP, LSTM>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     float* scratch = reinterpret_cast<float*>(smem + STAGES * L::kStage);
@@ -363,6 +390,7 @@ gemm_split_pair_kernel(const __grid_constant__ CUtensorMap map_a_x, const __grid
     } else {
         const int q = warp & 3;                                // TMEM lane quarter this warp may read
         float* scr = KP > 0 ? scratch + (warp - 2) * (128 + 32 * (KP + 1)) : scratch + q * (32 * 36);
+        (void)scr;
         int lt = 0;
         for (int work = work0; work < nwork; work += work_step, ++lt) {
             const int m0 = ((work / tiles_n) * 2 + crank) * BM, n0 = (work % tiles_n) * BN;
@@ -476,11 +504,13 @@ gemm_split_pair_kernel(const __grid_constant__ CUtensorMap map_a_x, const __grid
                 if (row_ok) epi.topk_ms[((size_t)tn * 2 + half) * M + row] = make_float2(mx, ssum);
                 // the partner must have read this warp's list before the next tile overwrites it
                 asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-            } else if (epi.kind == Epi::kLstmCell) {
-                // One accumulator row per thread, 32 columns (8 hidden units x i,f,g,o) per chunk.  The
-                // per-row operands of chunk c+1 (previous cell state of the source beam, the E'[token]
-                // row segment) are fetched while chunk c is computed, and those of chunk 0 before the
-                // accumulator is even complete: their DRAM latency used to be exposed 8 times per tile.
+            } else if constexpr (LSTM) {
+                // One accumulator row per thread, 32 columns (8 hidden units x i,f,g,o) per chunk; warps w and w + 4
+                // share the rows of a TMEM lane quarter and take half of the tile's columns each.  The per-row
+                // operands of chunk c+1 (previous cell state of the source beam, the E'[token] row segment) are
+                // fetched while chunk c is computed, and those of the first chunk before the accumulator is complete.
+                const int half = (warp - 2) >> 2;
+                const int cbeg = half * (BN / 2), cend = cbeg + BN / 2;
                 const int row = rbase + lane;
                 const bool row_ok = row < M;
                 int crow = row;
@@ -498,17 +528,17 @@ gemm_split_pair_kernel(const __grid_constant__ CUtensorMap map_a_x, const __grid
                         }
                     }
                 };
-                fetch(n0);
+                fetch(n0 + cbeg);
                 mbar_wait(&tfull[acc], aph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 2
-                for (int c0 = 0; c0 < BN; c0 += 32) {
+                for (int c0 = cbeg; c0 < cend; c0 += 32) {
                     const int n = n0 + c0;
                     float4 cpv[2], adv4[8];
                     cpv[0] = cpn[0]; cpv[1] = cpn[1];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) adv4[j] = adn[j];
-                    if (c0 + 32 < BN) fetch(n + 32);
+                    if (c0 + 32 < cend) fetch(n + 32);
                     uint32_t r[32];
                     tmem_ld32(tacc + (uint32_t)c0, r);
                     if (!row_ok || n >= N) continue;
@@ -522,8 +552,7 @@ gemm_split_pair_kernel(const __grid_constant__ CUtensorMap map_a_x, const __grid
                         const float gf = __uint_as_float(r[4 * j + 1]) + b4.y;
                         const float gg = __uint_as_float(r[4 * j + 2]) + b4.z;
                         const float go = __uint_as_float(r[4 * j + 3]) + b4.w;
-                        cv[j] = sigm(gf) * cp[j] + sigm(gi) * tanh_e(gg);
-                        hv[j] = sigm(go) * tanh_e(cv[j]);
+                        lstm_cell_fast(gi, gf, gg, go, cp[j], cv[j], hv[j]);
                     }
                     float4* ho = reinterpret_cast<float4*>(epi.h_out + (size_t)row * epi.H + (n >> 2));
                     float4* co = reinterpret_cast<float4*>(epi.c_out + (size_t)row * epi.H + (n >> 2));
@@ -532,10 +561,10 @@ gemm_split_pair_kernel(const __grid_constant__ CUtensorMap map_a_x, const __grid
                     co[0] = make_float4(cv[0], cv[1], cv[2], cv[3]);
                     co[1] = make_float4(cv[4], cv[5], cv[6], cv[7]);
                     if (epi.split_hi) {
-                        // the 8 hidden units of this thread are one 8-float block of the split operand
+                        // the 8 hidden units of this thread are one 8-float block of the split operand (|h| < 1)
                         float hh[8], hl[8];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) { hh[j] = hi_part(hv[j]); hl[j] = hv[j] - hh[j]; }
+                        for (int j = 0; j < 8; ++j) { hh[j] = __half2float(__float2half_rn(hv[j])); hl[j] = hv[j] - hh[j]; }
                         uint4* sh = reinterpret_cast<uint4*>(epi.split_hi + (size_t)row * epi.split_ld + (n >> 2));
                         uint4* sx = reinterpret_cast<uint4*>(epi.split_lo + (size_t)row * epi.split_ld + (n >> 2));
                         sh[0] = make_uint4(pack_hi2(hh[0], hh[1]), pack_hi2(hh[2], hh[3]), pack_hi2(hh[4], hh[5]),
@@ -702,11 +731,11 @@ int split_operand(const AOperand& A, int M, int K, hi_t* hi, float* lo, const in
     return ASR_OK;
 }
 
-template <int BN, int STAGES, int KP>
+template <int BN, int STAGES, int KP, bool LSTM = false>
 static int launch_pair(const hi_t* a_hi, const float* a_lo, const hi_t* w_hi, const float* w_lo, int M, int N, int K,
                        const GemmEpilogue& epi, cudaStream_t st) {
-    auto kern = tc::gemm_split_pair_kernel<BN, STAGES, KP>;
-    constexpr int smem = tc::SmemLayout<BN, STAGES, KP>::kBytes;
+    auto kern = tc::gemm_split_pair_kernel<BN, STAGES, KP, LSTM>;
+    constexpr int smem = tc::SmemLayout<BN, STAGES, KP, LSTM>::kBytes;
     CUtensorMap ma_x, ma_h, mw_x, mw_h;          // each CTA of the pair fetches its 128 rows of A, half of the W tile rows
     ASR_TRY(tc::make_map(&ma_x, a_lo, M, K, tc::BM, epi.lda, false));
     ASR_TRY(tc::make_map(&ma_h, a_hi, M, K, tc::BM, epi.lda, true));
@@ -718,7 +747,7 @@ static int launch_pair(const hi_t* a_hi, const float* a_lo, const hi_t* w_hi, co
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // decoder-step launches: see griddep_wait()
     at[1].val.programmaticStreamSerializationAllowed = 1;
-    cfg.blockDim = dim3(tc::SmemLayout<BN, STAGES, KP>::kThreads);
+    cfg.blockDim = dim3(tc::SmemLayout<BN, STAGES, KP, LSTM>::kThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cfg.attrs = at;
@@ -773,7 +802,9 @@ int launch_gemm_tc(const hi_t* a_hi, const float* a_lo, const hi_t* w_hi, const 
         auto cost = [&](int w) { return (long long)((mg * ((N + w - 1) / w) + ncl - 1) / ncl) * w; };
         if (cost(224) < cost(256)) bn = 224;
     }
-    if (bn == 256) {
+    if (epi.kind == Epi::kLstmCell) {
+        ASR_TRY((launch_pair<256, 6, 0, true>(a_hi, a_lo, w_hi, w_lo, M, N, K, epi, st)));
+    } else if (bn == 256) {
         ASR_TRY((launch_pair<256, 6, 0>(a_hi, a_lo, w_hi, w_lo, M, N, K, epi, st)));
     } else if (bn == 224) {
         ASR_TRY((launch_pair<224, 6, 0>(a_hi, a_lo, w_hi, w_lo, M, N, K, epi, st)));
