@@ -155,8 +155,12 @@ __device__ __forceinline__ void tmem_ld_cols_nowait(uint32_t taddr, uint32_t* r)
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-constexpr int kThreads = 544;        // 16 gate warps + 1 MMA-issue warp
-constexpr int kIssueWarp = 16;
+// 16 gate warps; the last one also issues the step's MMAs (a few dozen uniform instructions once h has arrived) before
+// it turns to its share of the gate work.  A 17th, issue-only warp (round 1 / 2) put 5 warps on one scheduler and capped
+// every thread at 96 registers: the gate warps spilled, and their local-memory reloads missed L1 behind the streamed xg
+// rows (ncu r02d: 12 % of all stall samples on four LDL).  16 warps get 128 registers.
+constexpr int kThreads = 512;
+constexpr int kIssueWarp = 15;
 
 struct Params {
     const float* xg;            // [rows, 2048] permuted gate pre-activations (bias included): column dir*1024 + j*128 + 4u + gate
@@ -326,7 +330,31 @@ lstm_rec_tc3_kernel(Params p) {
         }
     };
 
+    int toff_t = Lc > 0 ? p.toff[dir == 0 ? 0 : Lc - 1] : 0;
     for (int s = 0; s < Lc; ++s) {
+        const int t = dir == 0 ? s : Lc - 1 - s;
+        if (dir == 0) { while (nact > 0 && s_len[nact - 1] <= t) --nact; }
+        else { while (nact < nrows && s_len[nact] > t) ++nact; }
+        const int row_t = toff_t + r0;
+        if (s + 1 < Lc) toff_t = p.toff[dir == 0 ? s + 1 : Lc - 2 - s];      // next step's row base, a step ahead
+
+        {
+        // this step's loads first (they do not depend on h: issued while the exchange is still in flight), then the
+        // issue warp starts the MMAs, then everybody stores the previous step's outputs under them
+        float4 xg4[P];
+        float xres[P];
+#pragma unroll
+        for (int q = 0; q < P; ++q) {
+            const int i = col0 + 4 * q;
+            xg4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            xres[q] = 0.f;
+            if (i < nact) {
+                const uint32_t r = (uint32_t)(row_t + i);
+                if (HAS_RES) xres[q] = __ldg(p.x_in + r * kEnc + ocol);
+                xg4[q] = __ldg(reinterpret_cast<const float4*>(p.xg + (size_t)r * (2 * kGates) + dir * kGates + j * 128) + uu);
+            }
+        }
+
         if (warp == kIssueWarp) {
             // all 32 lanes wait (uniform control flow keeps descriptors and TMEM addresses in uniform registers),
             // one elected lane issues
@@ -350,31 +378,7 @@ lstm_rec_tc3_kernel(Params p) {
             __syncwarp();
             if (p.dbg && blockIdx.x == 0 && lane == 0) p.dbg[s * 8 + 1] = clock64();
         }
-
-        const int t = dir == 0 ? s : Lc - 1 - s;
-        if (dir == 0) { while (nact > 0 && s_len[nact - 1] <= t) --nact; }
-        else { while (nact < nrows && s_len[nact] > t) ++nact; }
-        const int row_t = p.toff[t] + r0;
-
-        if (warp < kIssueWarp) {
-        // gate warps: the issue warp above does nothing else, so it never arrives late at the step's barrier
-        // the stores of the previous step first (registers only), then this step's loads: their latency is
-        // covered by the MMAs in flight (measured: loading the residual inside the deferred store instead makes
-        // the gate warps arrive ~500 cycles late at mma_done)
         if (s > 0) store_outputs(prev_t, prev_row_t, prev_nact);
-        float4 xg4[P];
-        float xres[P];
-#pragma unroll
-        for (int q = 0; q < P; ++q) {
-            const int i = col0 + 4 * q;
-            xg4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-            xres[q] = 0.f;
-            if (i < nact) {
-                const uint32_t r = (uint32_t)(row_t + i);
-                if (HAS_RES) xres[q] = __ldg(p.x_in + r * kEnc + ocol);
-                xg4[q] = __ldg(reinterpret_cast<const float4*>(p.xg + (size_t)r * (2 * kGates) + dir * kGates + j * 128) + uu);
-            }
-        }
 
         mbar_wait(mma_done, (uint32_t)(s & 1));
         tc_fence_after();
@@ -454,12 +458,12 @@ lstm_rec_tc3_kernel(Params p) {
         }
         prev_t = t; prev_row_t = row_t; prev_nact = nact;
     }
-    if (Lc > 0 && warp < kIssueWarp) store_outputs(prev_t, prev_row_t, prev_nact);
+    if (Lc > 0) store_outputs(prev_t, prev_row_t, prev_nact);
 
 #pragma unroll
     for (int q = 0; q < P; ++q) {
         const int i = col0 + 4 * q;
-        if (i < nrows && warp < kIssueWarp) {
+        if (i < nrows) {
             p.h_fin[(size_t)(r0 + i) * kEnc + ocol] = h_reg[q];
             p.c_fin[(size_t)(r0 + i) * kEnc + ocol] = c_reg[q];
         }
