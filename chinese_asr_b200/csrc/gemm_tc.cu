@@ -510,35 +510,37 @@ gemm_split_pair_kernel(const __grid_constant__ CUtensorMap map_a_x, const __grid
                 // operands of chunk c+1 (previous cell state of the source beam, the E'[token] row segment) are
                 // fetched while chunk c is computed, and those of the first chunk before the accumulator is complete.
                 const int half = (warp - 2) >> 2;
-                const int cbeg = half * (BN / 2), cend = cbeg + BN / 2;
+                const int cbeg = half * (BN / 2);
                 const int row = rbase + lane;
                 const bool row_ok = row < M;
                 int crow = row;
                 if (row_ok && epi.c_rowidx) crow = epi.c_rowidx[row];
                 const float* cbase = epi.c_prev + (size_t)crow * epi.H;
                 const float* abase = (epi.addrow && row_ok) ? epi.addrow + (size_t)epi.addrow_idx[row] * epi.addrow_ld : nullptr;
-                float4 cpn[2], adn[8];
-                auto fetch = [&](int n) {
+                // two chunks of per-row operands in flight (ncu r02d: with one, a quarter of the epilogue's stall
+                // samples sat on the E' rows - every chunk waited out an L2 / DRAM round trip)
+                constexpr int NCH = BN / 64;                     // chunks of this warp's column half
+                float4 cpn[2][2], adn[2][8];
+                auto fetch = [&](int slot, int n) {
                     if (row_ok && n < N) {
-                        cpn[0] = *reinterpret_cast<const float4*>(cbase + (n >> 2));
-                        cpn[1] = *reinterpret_cast<const float4*>(cbase + (n >> 2) + 4);
+                        cpn[slot][0] = *reinterpret_cast<const float4*>(cbase + (n >> 2));
+                        cpn[slot][1] = *reinterpret_cast<const float4*>(cbase + (n >> 2) + 4);
                         if (abase) {
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) adn[j] = __ldg(reinterpret_cast<const float4*>(abase + n + 4 * j));
+                            for (int j = 0; j < 8; ++j) adn[slot][j] = __ldg(reinterpret_cast<const float4*>(abase + n + 4 * j));
                         }
                     }
                 };
-                fetch(n0 + cbeg);
+                fetch(0, n0 + cbeg);
+                if (NCH > 1) fetch(1, n0 + cbeg + 32);
                 mbar_wait(&tfull[acc], aph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 2
-                for (int c0 = cbeg; c0 < cend; c0 += 32) {
-                    const int n = n0 + c0;
-                    float4 cpv[2], adv4[8];
-                    cpv[0] = cpn[0]; cpv[1] = cpn[1];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) adv4[j] = adn[j];
-                    if (c0 + 32 < cend) fetch(n + 32);
+                for (int ch = 0; ch < NCH; ++ch) {
+                    const int c0 = cbeg + 32 * ch;
+                    const int n = n0 + c0;
+                    const float4* cpv = cpn[ch & 1];
+                    const float4* adv4 = adn[ch & 1];
                     uint32_t r[32];
                     tmem_ld32(tacc + (uint32_t)c0, r);
                     if (!row_ok || n >= N) continue;
@@ -554,6 +556,7 @@ gemm_split_pair_kernel(const __grid_constant__ CUtensorMap map_a_x, const __grid
                         const float go = __uint_as_float(r[4 * j + 3]) + b4.w;
                         lstm_cell_fast(gi, gf, gg, go, cp[j], cv[j], hv[j]);
                     }
+                    if (ch + 2 < NCH) fetch(ch & 1, n + 64);     // this slot's operands are consumed: refill it two chunks ahead
                     float4* ho = reinterpret_cast<float4*>(epi.h_out + (size_t)row * epi.H + (n >> 2));
                     float4* co = reinterpret_cast<float4*>(epi.c_out + (size_t)row * epi.H + (n >> 2));
                     ho[0] = make_float4(hv[0], hv[1], hv[2], hv[3]);
