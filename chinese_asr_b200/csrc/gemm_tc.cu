@@ -811,6 +811,10 @@ int launch_gemm_tc(const hi_t* a_hi, const float* a_lo, const hi_t* w_hi, const 
         ASR_TRY((launch_pair<256, 6, 0>(a_hi, a_lo, w_hi, w_lo, M, N, K, epi, st)));
     } else if (bn == 224) {
         ASR_TRY((launch_pair<224, 6, 0>(a_hi, a_lo, w_hi, w_lo, M, N, K, epi, st)));
+    } else if (N <= 128 && ((M + 2 * tc::BM - 1) / (2 * tc::BM)) * 4 <= kNumSMs / 2) {
+        // a narrow output over few rows (the decoder's query projection: 4096 x 128): 32-column tiles put 4x as many
+        // CTA pairs to work - the GEMM is a latency chain (prologue, pipeline fill, epilogue), not a throughput problem
+        ASR_TRY((launch_pair<32, 8, 0>(a_hi, a_lo, w_hi, w_lo, M, N, K, epi, st)));
     } else {
         ASR_TRY((launch_pair<128, 8, 0>(a_hi, a_lo, w_hi, w_lo, M, N, K, epi, st)));
     }
