@@ -470,9 +470,9 @@ static int features_device(asr_handle* h, const void* d_pcm, int format, const i
     ASR_CUDA(cudaMemcpyAsync(w.d_featrow_off, hs + sizeof(long long) * (B + 1) + sizeof(int) * (B + 1), sizeof(int) * (B + 1), cudaMemcpyHostToDevice, st));
     ASR_CUDA(cudaStreamSynchronize(st));
     StageScope sc(h, kStFeat, st);
-    ASR_TRY(launch_logmel(h, d_pcm, format, w.d_pcm_off, w.d_frame_off, B, foff[B], w.mel, st));
-    int lmax = 0;
-    for (int i = 0; i < B; ++i) lmax = std::max(lmax, (int)h_L[i]);
+    int lmax = 0, tmax = 0;
+    for (int i = 0; i < B; ++i) { lmax = std::max(lmax, (int)h_L[i]); tmax = std::max(tmax, foff[i + 1] - foff[i]); }
+    ASR_TRY(launch_logmel(h, d_pcm, format, w.d_pcm_off, w.d_frame_off, B, tmax, w.mel, st));
     // Fused path (PCM -> hypotheses): the features are only ever read by the layer-0 input GEMM, so they are written
     // straight as its split A operand (6 bytes per value) instead of fp32 + a split pass (4 + 4 + 6 bytes)
     const bool fuse = packed_out;

@@ -158,8 +158,7 @@ int vocab_topk_slots(int k);      // KP of the vocabulary epilogue for beam widt
 // ---------------------------------------------------------------------------------------------
 struct FeatureConsts {
     float* window = nullptr;     // [400]
-    float2* tw256 = nullptr;     // [256] exp(-2 pi i k / 256)
-    float2* tw512 = nullptr;     // [257] exp(-2 pi i k / 512)
+    float2* tw512 = nullptr;     // [512] exp(-2 pi i k / 512)
     int* mel_start = nullptr;    // [80]
     int* mel_len = nullptr;      // [80]
     float* mel_w = nullptr;      // [80, mel_maxw]
@@ -388,7 +387,7 @@ inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, 
 // ---- features.cu -----------------------------------------------------------------------------
 int build_feature_consts(asr_handle* h, const asr_feature_consts* fc);
 int launch_logmel(asr_handle* h, const void* d_pcm, int format, const long long* d_pcm_off,
-                  const int* d_frame_off, int B, int total_frames, float* d_mel, cudaStream_t st);
+                  const int* d_frame_off, int B, int max_frames_per_utt, float* d_mel, cudaStream_t st);
 // out_rowmap: feature row (utterance-major, original order) -> output row; nullptr = identity
 int launch_delta_cmvn(asr_handle* h, const float* d_mel, const int* d_frame_off,
                       const int* d_featrow_off, int B, int max_rows_per_utt, int normalise, float eps,

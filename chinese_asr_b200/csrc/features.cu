@@ -25,127 +25,230 @@ namespace asr {
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
+// complex add / subtract as ONE packed fp32x2 instruction each (FADD2 / FFMA2 on sm_100): the butterflies are add-bound
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.f, -1.f), a); }
+__device__ __forceinline__ float2 cmul_negi(float2 a) { return make_float2(a.y, -a.x); }        // a * (-i)
 
-constexpr int kFramesPerCta = 8;      // one warp per frame
-constexpr int kFrameRounds = 4;       // frames per warp: the twiddle / window tables are staged once per 32 frames
+constexpr int kLmFrames = 32;                         // frames per CTA: 16 pairs, two per warp
+constexpr int kLmSpan = (kLmFrames - 1) * kHop + kWinOff + kWin;      // pre-emphasised samples a CTA touches (5416)
+constexpr int kLmSpanPad = (kLmSpan + 7) & ~7;
+constexpr int kLmBuf = 512 + 64;                      // complex points per warp buffer: index i lives at i + (i >> 3)
+constexpr size_t kLmSmem = sizeof(float) * (kLmSpanPad + kWin) + sizeof(float2) * (512 + 8 * kLmBuf);
 
 // PCM sample as the float32 soundfile.read(dtype='float32') hands the reference (data.py:111): float32 files as
 // stored, 16-bit files as x / 32768 (exact: a power of two), so both sample types give bit-identical frames.
-__device__ __forceinline__ float pcm_sample(const float* x, int i) { return x[i]; }
-__device__ __forceinline__ float pcm_sample(const short* x, int i) { return (float)x[i] * (1.0f / 32768.0f); }
+__device__ __forceinline__ float pcm_sample(const float* x, long long i) { return x[i]; }
+__device__ __forceinline__ float pcm_sample(const short* x, long long i) { return (float)x[i] * (1.0f / 32768.0f); }
 
+// 8 consecutive samples starting at a 16-byte aligned address (+ the one after them) -> 9 floats
+__device__ __forceinline__ void pcm_load9(const short* x, float (&v)[9]) {
+    const uint4 r = *reinterpret_cast<const uint4*>(x);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        v[2 * i] = (float)(short)(w[i] & 0xffffu) * (1.0f / 32768.0f);
+        v[2 * i + 1] = (float)(short)(w[i] >> 16) * (1.0f / 32768.0f);
+    }
+    v[8] = (float)x[8] * (1.0f / 32768.0f);
+}
+__device__ __forceinline__ void pcm_load9(const float* x, float (&v)[9]) {
+    const float4 a = *reinterpret_cast<const float4*>(x), b = *reinterpret_cast<const float4*>(x + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    v[8] = x[8];
+}
+
+// forward 8-point DFT in registers (radix-2 decimation in time; w = e^(-2 pi i / 8))
+__device__ __forceinline__ void fft8(float2 (&v)[8]) {
+    const float h = 0.70710678118654752440f;
+    const float2 a0 = cadd(v[0], v[4]), a1 = csub(v[0], v[4]), a2 = cadd(v[2], v[6]), a3 = cmul_negi(csub(v[2], v[6]));
+    const float2 a4 = cadd(v[1], v[5]), a5 = csub(v[1], v[5]), a6 = cadd(v[3], v[7]), a7 = cmul_negi(csub(v[3], v[7]));
+    const float2 b0 = cadd(a0, a2), b1 = cadd(a1, a3), b2 = csub(a0, a2), b3 = csub(a1, a3);
+    const float2 b4 = cadd(a4, a6), b5 = cadd(a5, a7), b6 = csub(a4, a6), b7 = csub(a5, a7);
+    const float2 t5 = make_float2(h * (b5.x + b5.y), h * (b5.y - b5.x));          // b5 * (1 - i) / sqrt 2
+    const float2 t6 = cmul_negi(b6);
+    const float2 t7 = make_float2(h * (b7.y - b7.x), -h * (b7.x + b7.y));         // b7 * (-1 - i) / sqrt 2
+    v[0] = cadd(b0, b4); v[4] = csub(b0, b4);
+    v[1] = cadd(b1, t5); v[5] = csub(b1, t5);
+    v[2] = cadd(b2, t6); v[6] = csub(b2, t6);
+    v[3] = cadd(b3, t7); v[7] = csub(b3, t7);
+}
+
+// One CTA = 32 consecutive frames of one utterance (grid: frame chunks x utterances).
+//   1. the chunk's PCM span is read ONCE with 16-byte loads (8 int16 or 4 + 4 float samples), pre-emphasised
+//      (data.py:201-202) and kept in shared memory (the round-1 kernel fetched every sample ~3.2 times, scalar);
+//   2. each warp transforms TWO real frames per complex FFT: z = frame_a + i frame_b, 512-point Stockham radix-8 in
+//      three passes (64 butterflies per pass = 2 per lane, 16 points in registers; the first pass reads straight from
+//      the pre-emphasised samples x window, torch.stft center=False with the Hann-400 at offset 56, data.py:205-209),
+//      then X_a[k] = (Z[k] + conj Z[-k]) / 2, X_b[k] = (Z[k] - conj Z[-k]) / 2i - no 512-point twiddle pass;
+//   3. power (data.py:221), sparse mel filterbank (data.py:222), zero -> eps, log (data.py:223-224) for both frames.
 template <typename S>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 logmel_kernel(const S* __restrict__ pcm, const long long* __restrict__ pcm_off,
-              const int* __restrict__ frame_off, int B, int total_frames,
-              const float* __restrict__ g_window, const float2* __restrict__ g_tw256,
+              const int* __restrict__ frame_off, const float* __restrict__ g_window,
               const float2* __restrict__ g_tw512, const int* __restrict__ mel_start,
               const int* __restrict__ mel_len, const float* __restrict__ mel_w, int mel_maxw,
               float preemph, float* __restrict__ mel_out) {
-    __shared__ float2 s_tw256[256];
-    __shared__ float2 s_tw512[257];
-    __shared__ float s_win[kWin];
-    __shared__ float2 s_a[kFramesPerCta][256];
-    __shared__ float2 s_b[kFramesPerCta][256 + 2];
+    extern __shared__ __align__(16) uint8_t lm_smem[];
+    float* s_pe = reinterpret_cast<float*>(lm_smem);                   // [kLmSpanPad] pre-emphasised samples
+    float* s_win = s_pe + kLmSpanPad;                                  // [400]
+    float2* s_tw = reinterpret_cast<float2*>(s_win + kWin);            // [512] exp(-2 pi i k / 512)
+    float2* s_buf = s_tw + 512;                                        // [8 warps][kLmBuf]
 
-    const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
-    for (int i = tid; i < 256; i += 256) s_tw256[i] = g_tw256[i];
-    for (int i = tid; i < 257; i += 256) s_tw512[i] = g_tw512[i];
+    const int u = blockIdx.y;
+    const int f0 = frame_off[u];
+    const int T = frame_off[u + 1] - f0;
+    const int t0 = blockIdx.x * kLmFrames;
+    if (t0 >= T) return;
+    const int nf = min(kLmFrames, T - t0);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long x0 = pcm_off[u] + (long long)t0 * kHop;            // first sample of the chunk
+    const int span = (nf - 1) * kHop + kWinOff + kWin;                 // pe[i], i < span, is read below
+
     for (int i = tid; i < kWin; i += 256) s_win[i] = g_window[i];
+    for (int i = tid; i < 512; i += 256) s_tw[i] = g_tw512[i];
+    // pe[i] = x[i + 1] - preemph * x[i]  (two roundings, like the reference's tensor expression)
+    const int per16 = 16 / (int)sizeof(S);
+    if ((x0 % per16) == 0) {
+        for (int g = tid; g * 8 < span; g += 256) {
+            float v[9];
+            pcm_load9(pcm + x0 + 8 * g, v);          // reads x[8 g + 8] at most: inside the utterance (frame layout)
+            float pe[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) pe[i] = __fsub_rn(v[i + 1], __fmul_rn(preemph, v[i]));
+            *reinterpret_cast<float4*>(s_pe + 8 * g) = make_float4(pe[0], pe[1], pe[2], pe[3]);
+            *reinterpret_cast<float4*>(s_pe + 8 * g + 4) = make_float4(pe[4], pe[5], pe[6], pe[7]);
+        }
+    } else {
+        for (int i = tid; i < span; i += 256)
+            s_pe[i] = __fsub_rn(pcm_sample(pcm, x0 + i + 1), __fmul_rn(preemph, pcm_sample(pcm, x0 + i)));
+    }
     __syncthreads();
 
-    for (int round = 0; round < kFrameRounds; ++round) {
-    const int gf = (blockIdx.x * kFrameRounds + round) * kFramesPerCta + warp;
-    if (gf >= total_frames) return;
-    __syncwarp();                       // the previous frame's mel pass has finished reading `power`
-
-    // utterance of this frame: largest u with frame_off[u] <= gf
-    int lo = 0, hi = B;
-    while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (frame_off[mid] <= gf) lo = mid; else hi = mid;
+    // mels of this lane (80 = 32 + 32 + 16)
+    int m_st[3], m_n[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const int m = lane + 32 * r;
+        m_st[r] = m < kMel ? mel_start[m] : 0;
+        m_n[r] = m < kMel ? mel_len[m] : 0;
     }
-    const int u = lo;
-    const int t = gf - frame_off[u];
-    const S* x = pcm + pcm_off[u] + (long long)t * kHop;
-
-    float2* a = s_a[warp];
-    float2* b = s_b[warp];
-
-    // windowed, pre-emphasised frame packed as z[n] = xw[2n] + i xw[2n+1]
+    // Warp buffer of 512 complex points, point i at i + (i >> 3) (one pad per 8: the strided stores of the passes
+    // spread over the banks).  Every access below is (a lane-dependent base) + (a compile-time multiple of i):
+    //   reads of passes 2, 3      point j + 64 i          -> rd[b] + 72 i
+    //   stores of pass 1 (Ns = 1)  point 8 j + i           -> 9 j + i
+    //   stores of pass 2 (Ns = 8)  point 8 (j - k) + k + 8 i -> 9 (j - k) + k + 9 i      (k = j & 7)
+    //   stores of pass 3 (Ns = 64) point j + 64 i          -> rd[b] + 72 i
+    float2* buf = s_buf + warp * kLmBuf;
+    float2* rd[2];
+    float2* w1[2];
+    float2* w2[2];
+    int tws2[2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int n = lane + 32 * i;
-        const int s = 2 * n;
-        float2 z = make_float2(0.f, 0.f);
-        if (s >= kWinOff && s < kWinOff + kWin) {   // kWinOff, kWin even -> both samples inside
-            const float x0 = pcm_sample(x, s), x1 = pcm_sample(x, s + 1), x2 = pcm_sample(x, s + 2);
-            const float y0 = __fsub_rn(x1, __fmul_rn(preemph, x0));
-            const float y1 = __fsub_rn(x2, __fmul_rn(preemph, x1));
-            z.x = y0 * s_win[s - kWinOff];
-            z.y = y1 * s_win[s + 1 - kWinOff];
-        }
-        a[n] = z;
+    for (int b = 0; b < 2; ++b) {
+        const int j = lane + 32 * b;
+        rd[b] = buf + j + (j >> 3);
+        w1[b] = buf + 9 * j;
+        w2[b] = buf + 9 * (j & ~7) + (j & 7);
+        tws2[b] = (j & 7) * 8;
     }
-    __syncwarp();
+    // split: Z[k] at zk + 36 mm, Z[512 - k] at zc - 36 mm for k = lane + 32 mm (k = 0 pairs with itself)
+    const float2* zk = buf + lane + (lane >> 3);
+    const float2* zc = buf + (512 - lane) + ((512 - lane) >> 3);
 
-    // 256-point complex FFT, radix-4 Stockham autosort, 4 passes (Ns = 1, 4, 16, 64)
-    float2* src = a;
-    float2* dst = b;
+    for (int pr = warp; 2 * pr < nf; pr += 8) {
+        const int ta = 2 * pr;                                          // frames ta, ta + 1 of the chunk
+        const bool has_b = ta + 1 < nf;
+        const float* pa = s_pe + ta * kHop;
+        const float* pb = pa + (has_b ? kHop : 0);
+        // ---- pass 1 (Ns = 1): inputs straight from the samples, no twiddles ----------------------------------
 #pragma unroll
-    for (int pass = 0; pass < 4; ++pass) {
-        const int Ns = 1 << (2 * pass);
-        const int tw_stride = 64 >> (2 * pass);
+        for (int b = 0; b < 2; ++b) {
+            const int j = lane + 32 * b;
+            float2 v[8];
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const int j = lane + 32 * i;
-            const int k = j & (Ns - 1);
-            float2 v0 = src[j];
-            float2 v1 = src[j + 64];
-            float2 v2 = src[j + 128];
-            float2 v3 = src[j + 192];
-            if (pass > 0) {
-                v1 = cmul(v1, s_tw256[k * tw_stride]);
-                v2 = cmul(v2, s_tw256[2 * k * tw_stride]);
-                v3 = cmul(v3, s_tw256[3 * k * tw_stride]);
+            for (int i = 0; i < 8; ++i) {
+                const int n = j + 64 * i;
+                v[i] = make_float2(0.f, 0.f);
+                if (n >= kWinOff && n < kWinOff + kWin) {
+                    const float w = s_win[n - kWinOff];
+                    v[i] = make_float2(pa[n] * w, has_b ? pb[n] * w : 0.f);
+                }
             }
-            const float2 s02 = make_float2(v0.x + v2.x, v0.y + v2.y);
-            const float2 d02 = make_float2(v0.x - v2.x, v0.y - v2.y);
-            const float2 s13 = make_float2(v1.x + v3.x, v1.y + v3.y);
-            const float2 d13 = make_float2(v1.x - v3.x, v1.y - v3.y);
-            const int j0 = ((j - k) << 2) + k;
-            dst[j0] = make_float2(s02.x + s13.x, s02.y + s13.y);
-            dst[j0 + Ns] = make_float2(d02.x + d13.y, d02.y - d13.x);      // v0 - i v1 - v2 + i v3
-            dst[j0 + 2 * Ns] = make_float2(s02.x - s13.x, s02.y - s13.y);
-            dst[j0 + 3 * Ns] = make_float2(d02.x - d13.y, d02.y + d13.x);  // v0 + i v1 - v2 - i v3
+            fft8(v);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) w1[b][i] = v[i];
         }
         __syncwarp();
-        float2* tmp = src; src = dst; dst = tmp;
-    }
-    // result in `src` (== a after 4 passes); split into the 257 real-FFT bins, store power in dst
-    float* power = reinterpret_cast<float*>(dst);
-    for (int kbin = lane; kbin <= 256; kbin += 32) {
-        const float2 zk = src[kbin & 255];
-        const float2 zc = src[(256 - kbin) & 255];
-        // E = (zk + conj(zc)) / 2 ; O = (zk - conj(zc)) / (2i)
-        const float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y));
-        const float2 o = make_float2(0.5f * (zk.y + zc.y), -0.5f * (zk.x - zc.x));
-        const float2 wo = cmul(s_tw512[kbin], o);
-        const float re = e.x + wo.x, im = e.y + wo.y;
-        power[kbin] = re * re + im * im;
-    }
-    __syncwarp();
-
-    float* out = mel_out + (size_t)gf * kMel;
-    for (int m = lane; m < kMel; m += 32) {
-        const int st = mel_start[m], n = mel_len[m];
-        const float* w = mel_w + m * mel_maxw;
-        float acc = 0.f;
-        for (int i = 0; i < n; ++i) acc = fmaf(power[st + i], w[i], acc);
-        if (acc == 0.f) acc = 1.1920928955078125e-07f;   // torch.finfo(float32).eps
-        out[m] = logf(acc);
-    }
+        // ---- passes 2, 3 (Ns = 8, 64): in place - all 16 points of a lane are loaded before any is stored --------
+#pragma unroll
+        for (int pass = 1; pass < 3; ++pass) {
+            float2 v[2][8];
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[b][i] = rd[b][72 * i];
+            }
+            __syncwarp();
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                // twiddles exp(-2 pi i * i k / (8 Ns)) = tw512[i * k * 64 / Ns], k = j mod Ns
+                const int tws = pass == 1 ? tws2[b] : lane + 32 * b;
+#pragma unroll
+                for (int i = 1; i < 8; ++i) v[b][i] = cmul(v[b][i], s_tw[i * tws]);
+                fft8(v[b]);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (pass == 1) w2[b][9 * i] = v[b][i];
+                    else rd[b][72 * i] = v[b][i];
+                }
+            }
+            __syncwarp();
+        }
+        // ---- split into the two real spectra, power --------------------------------------------------------
+        float pw_a[9], pw_b[9];
+#pragma unroll
+        for (int mm = 0; mm < 9; ++mm) {
+            const int k = lane + 32 * mm;
+            pw_a[mm] = 0.f; pw_b[mm] = 0.f;
+            if (k <= 256) {
+                const float2 z = zk[36 * mm];
+                const float2 c = k == 0 ? z : zc[-36 * mm];
+                const float ar = 0.5f * (z.x + c.x), ai = 0.5f * (z.y - c.y);
+                const float br = 0.5f * (z.y + c.y), bi = 0.5f * (c.x - z.x);
+                pw_a[mm] = ar * ar + ai * ai;
+                pw_b[mm] = br * br + bi * bi;
+            }
+        }
+        __syncwarp();
+        float* power = reinterpret_cast<float*>(buf);                   // [2][264]
+#pragma unroll
+        for (int mm = 0; mm < 9; ++mm) {
+            const int k = lane + 32 * mm;
+            if (k <= 256) { power[k] = pw_a[mm]; power[264 + k] = pw_b[mm]; }
+        }
+        __syncwarp();
+        // ---- mel filterbank, log ------------------------------------------------------------------------------
+        float* out_a = mel_out + (size_t)(f0 + t0 + ta) * kMel;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const int m = lane + 32 * r;
+            if (m < kMel) {
+                const float* w = mel_w + m * mel_maxw;
+                const float* p0 = power + m_st[r];
+                float acc_a = 0.f, acc_b = 0.f;
+                for (int i = 0; i < m_n[r]; ++i) {
+                    const float wi = __ldg(w + i);
+                    acc_a = fmaf(p0[i], wi, acc_a);
+                    acc_b = fmaf(p0[264 + i], wi, acc_b);
+                }
+                if (acc_a == 0.f) acc_a = 1.1920928955078125e-07f;   // torch.finfo(float32).eps
+                if (acc_b == 0.f) acc_b = 1.1920928955078125e-07f;
+                out_a[m] = logf(acc_a);
+                if (has_b) out_a[kMel + m] = logf(acc_b);
+            }
+        }
+        __syncwarp();                                                   // `power` is read before the next pair's pass 1
     }
 }
 
@@ -353,12 +456,9 @@ int build_feature_consts(asr_handle* h, const asr_feature_consts* fc) {
     std::vector<float> win(fc->window, fc->window + kWin);
     ASR_TRY(upload(h, &c.window, win));
     const double pi = 3.14159265358979323846;
-    std::vector<float2> t256(256), t512(257);
-    for (int k = 0; k < 256; ++k)
-        t256[k] = make_float2((float)cos(-2.0 * pi * k / 256.0), (float)sin(-2.0 * pi * k / 256.0));
-    for (int k = 0; k <= 256; ++k)
+    std::vector<float2> t512(512);
+    for (int k = 0; k < 512; ++k)
         t512[k] = make_float2((float)cos(-2.0 * pi * k / 512.0), (float)sin(-2.0 * pi * k / 512.0));
-    ASR_TRY(upload(h, &c.tw256, t256));
     ASR_TRY(upload(h, &c.tw512, t512));
     // CSR-like band storage of the [257, 80] filterbank
     std::vector<int> start(kMel, 0), len(kMel, 0);
@@ -381,19 +481,21 @@ int build_feature_consts(asr_handle* h, const asr_feature_consts* fc) {
 }
 
 int launch_logmel(asr_handle* h, const void* d_pcm, int format, const long long* d_pcm_off,
-                  const int* d_frame_off, int B, int total_frames, float* d_mel, cudaStream_t st) {
-    if (total_frames <= 0) return ASR_OK;
+                  const int* d_frame_off, int B, int max_frames_per_utt, float* d_mel, cudaStream_t st) {
+    if (max_frames_per_utt <= 0 || B <= 0) return ASR_OK;
     const FeatureConsts& c = h->fc;
-    const int per_cta = kFramesPerCta * kFrameRounds;
-    const int grid = (total_frames + per_cta - 1) / per_cta;
-    if (format == ASR_PCM_S16)
-        logmel_kernel<short><<<grid, 256, 0, st>>>(static_cast<const short*>(d_pcm), d_pcm_off, d_frame_off, B,
-                                                   total_frames, c.window, c.tw256, c.tw512, c.mel_start,
-                                                   c.mel_len, c.mel_w, c.mel_maxw, c.preemph, d_mel);
-    else
-        logmel_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(d_pcm), d_pcm_off, d_frame_off, B,
-                                                   total_frames, c.window, c.tw256, c.tw512, c.mel_start,
-                                                   c.mel_len, c.mel_w, c.mel_maxw, c.preemph, d_mel);
+    const dim3 grid((max_frames_per_utt + kLmFrames - 1) / kLmFrames, B);
+    if (format == ASR_PCM_S16) {
+        ASR_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&logmel_kernel<short>), kLmSmem));
+        logmel_kernel<short><<<grid, 256, kLmSmem, st>>>(static_cast<const short*>(d_pcm), d_pcm_off, d_frame_off, c.window,
+                                                         c.tw512, c.mel_start, c.mel_len, c.mel_w, c.mel_maxw, c.preemph,
+                                                         d_mel);
+    } else {
+        ASR_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&logmel_kernel<float>), kLmSmem));
+        logmel_kernel<float><<<grid, 256, kLmSmem, st>>>(static_cast<const float*>(d_pcm), d_pcm_off, d_frame_off, c.window,
+                                                         c.tw512, c.mel_start, c.mel_len, c.mel_w, c.mel_maxw, c.preemph,
+                                                         d_mel);
+    }
     ASR_CHECK_LAUNCH();
     h->launches++;
     return ASR_OK;
