@@ -33,7 +33,7 @@ __device__ __forceinline__ float2 cmul_negi(float2 a) { return make_float2(a.y, 
 constexpr int kLmFrames = 32;                         // frames per CTA: 16 pairs, two per warp
 constexpr int kLmSpan = (kLmFrames - 1) * kHop + kWinOff + kWin;      // pre-emphasised samples a CTA touches (5416)
 constexpr int kLmSpanPad = (kLmSpan + 7) & ~7;
-constexpr int kLmBuf = 512 + 64;                      // complex points per warp buffer: index i lives at i + (i >> 3)
+constexpr int kLmBuf = 512 + 32;                      // complex points per warp buffer: index i lives at i + (i >> 4)
 constexpr size_t kLmSmem = sizeof(float) * (kLmSpanPad + kWin) + sizeof(float2) * (512 + 8 * kLmBuf);
 
 // PCM sample as the float32 soundfile.read(dtype='float32') hands the reference (data.py:111): float32 files as
@@ -125,20 +125,27 @@ logmel_kernel(const S* __restrict__ pcm, const long long* __restrict__ pcm_off,
     }
     __syncthreads();
 
-    // mels of this lane (80 = 32 + 32 + 16)
-    int m_st[3], m_n[3];
+    // mels of this lane: rounds 0, 1 take mel lane / lane + 32; the 16 widest bands (mels 64..79, up to ~30 bins) are
+    // split in two halves over lane pairs (round 2: mel 64 + lane / 2, half lane & 1) and summed by one shuffle
+    int m_st[3], m_n[3], m_w[3];
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-        const int m = lane + 32 * r;
-        m_st[r] = m < kMel ? mel_start[m] : 0;
-        m_n[r] = m < kMel ? mel_len[m] : 0;
+        const int m = r < 2 ? lane + 32 * r : 64 + (lane >> 1);
+        const int st = mel_start[m], n = mel_len[m];
+        const int n0 = (n + 1) >> 1;
+        const bool second = r == 2 && (lane & 1);
+        m_st[r] = st + (second ? n0 : 0);
+        m_n[r] = r < 2 ? n : (second ? n - n0 : n0);
+        m_w[r] = m * mel_maxw + (second ? n0 : 0);
     }
-    // Warp buffer of 512 complex points, point i at i + (i >> 3) (one pad per 8: the strided stores of the passes
-    // spread over the banks).  Every access below is (a lane-dependent base) + (a compile-time multiple of i):
-    //   reads of passes 2, 3      point j + 64 i          -> rd[b] + 72 i
-    //   stores of pass 1 (Ns = 1)  point 8 j + i           -> 9 j + i
-    //   stores of pass 2 (Ns = 8)  point 8 (j - k) + k + 8 i -> 9 (j - k) + k + 9 i      (k = j & 7)
-    //   stores of pass 3 (Ns = 64) point j + 64 i          -> rd[b] + 72 i
+    // Warp buffer of 512 complex points, point i at i + (i >> 4): one pad per 16 keeps the contiguous 8-byte accesses
+    // of a half-warp inside one 128-byte bank window and spreads the strided stores of passes 1 and 2 (ncu r02d: with a
+    // pad per 8 every access of the transform took twice its ideal wavefronts).  Every access below is (a
+    // lane-dependent base) + (a compile-time function of i):
+    //   reads of passes 2, 3      point j + 64 i            -> rd[b] + 68 i
+    //   stores of pass 1 (Ns = 1)  point 8 j + i             -> 8 j + (j >> 1) + i
+    //   stores of pass 2 (Ns = 8)  point 64 g + k + 8 i      -> 68 g + k + 8 i + (i >> 1)     (j = 8 g + k)
+    //   stores of pass 3 (Ns = 64) point j + 64 i            -> rd[b] + 68 i
     float2* buf = s_buf + warp * kLmBuf;
     float2* rd[2];
     float2* w1[2];
@@ -147,14 +154,14 @@ logmel_kernel(const S* __restrict__ pcm, const long long* __restrict__ pcm_off,
 #pragma unroll
     for (int b = 0; b < 2; ++b) {
         const int j = lane + 32 * b;
-        rd[b] = buf + j + (j >> 3);
-        w1[b] = buf + 9 * j;
-        w2[b] = buf + 9 * (j & ~7) + (j & 7);
+        rd[b] = buf + j + (j >> 4);
+        w1[b] = buf + 8 * j + (j >> 1);
+        w2[b] = buf + 68 * (j >> 3) + (j & 7);
         tws2[b] = (j & 7) * 8;
     }
-    // split: Z[k] at zk + 36 mm, Z[512 - k] at zc - 36 mm for k = lane + 32 mm (k = 0 pairs with itself)
-    const float2* zk = buf + lane + (lane >> 3);
-    const float2* zc = buf + (512 - lane) + ((512 - lane) >> 3);
+    // split: Z[k] at zk + 34 mm, Z[512 - k] at zc - 34 mm for k = lane + 32 mm (k = 0 pairs with itself)
+    const float2* zk = buf + lane + (lane >> 4);
+    const float2* zc = buf + (512 - lane) + ((512 - lane) >> 4);
 
     for (int pr = warp; 2 * pr < nf; pr += 8) {
         const int ta = 2 * pr;                                          // frames ta, ta + 1 of the chunk
@@ -187,7 +194,7 @@ logmel_kernel(const S* __restrict__ pcm, const long long* __restrict__ pcm_off,
 #pragma unroll
             for (int b = 0; b < 2; ++b) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[b][i] = rd[b][72 * i];
+                for (int i = 0; i < 8; ++i) v[b][i] = rd[b][68 * i];
             }
             __syncwarp();
 #pragma unroll
@@ -199,8 +206,8 @@ logmel_kernel(const S* __restrict__ pcm, const long long* __restrict__ pcm_off,
                 fft8(v[b]);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    if (pass == 1) w2[b][9 * i] = v[b][i];
-                    else rd[b][72 * i] = v[b][i];
+                    if (pass == 1) w2[b][8 * i + (i >> 1)] = v[b][i];
+                    else rd[b][68 * i] = v[b][i];
                 }
             }
             __syncwarp();
@@ -212,8 +219,8 @@ logmel_kernel(const S* __restrict__ pcm, const long long* __restrict__ pcm_off,
             const int k = lane + 32 * mm;
             pw_a[mm] = 0.f; pw_b[mm] = 0.f;
             if (k <= 256) {
-                const float2 z = zk[36 * mm];
-                const float2 c = k == 0 ? z : zc[-36 * mm];
+                const float2 z = zk[34 * mm];
+                const float2 c = k == 0 ? z : zc[-34 * mm];
                 const float ar = 0.5f * (z.x + c.x), ai = 0.5f * (z.y - c.y);
                 const float br = 0.5f * (z.y + c.y), bi = 0.5f * (c.x - z.x);
                 pw_a[mm] = ar * ar + ai * ai;
@@ -232,18 +239,25 @@ logmel_kernel(const S* __restrict__ pcm, const long long* __restrict__ pcm_off,
         float* out_a = mel_out + (size_t)(f0 + t0 + ta) * kMel;
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
-            const int m = lane + 32 * r;
-            if (m < kMel) {
-                const float* w = mel_w + m * mel_maxw;
-                const float* p0 = power + m_st[r];
-                float acc_a = 0.f, acc_b = 0.f;
-                for (int i = 0; i < m_n[r]; ++i) {
-                    const float wi = __ldg(w + i);
-                    acc_a = fmaf(p0[i], wi, acc_a);
-                    acc_b = fmaf(p0[264 + i], wi, acc_b);
-                }
-                if (acc_a == 0.f) acc_a = 1.1920928955078125e-07f;   // torch.finfo(float32).eps
-                if (acc_b == 0.f) acc_b = 1.1920928955078125e-07f;
+            const float* w = mel_w + m_w[r];
+            const float* p0 = power + m_st[r];
+            float acc_a = 0.f, acc_b = 0.f;
+            for (int i = 0; i < m_n[r]; ++i) {
+                const float wi = __ldg(w + i);
+                acc_a = fmaf(p0[i], wi, acc_a);
+                acc_b = fmaf(p0[264 + i], wi, acc_b);
+            }
+            int m = lane + 32 * r;
+            bool writer = true;
+            if (r == 2) {
+                acc_a += __shfl_xor_sync(0xffffffffu, acc_a, 1);
+                acc_b += __shfl_xor_sync(0xffffffffu, acc_b, 1);
+                m = 64 + (lane >> 1);
+                writer = (lane & 1) == 0;
+            }
+            if (acc_a == 0.f) acc_a = 1.1920928955078125e-07f;   // torch.finfo(float32).eps
+            if (acc_b == 0.f) acc_b = 1.1920928955078125e-07f;
+            if (writer) {
                 out_a[m] = logf(acc_a);
                 if (has_b) out_a[kMel + m] = logf(acc_b);
             }

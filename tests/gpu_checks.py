@@ -397,9 +397,11 @@ def near_tie(gap, score, noise):
     (model.py:836) that reach |s| ~ 50-300 with the test weights, and the logits behind them are only specified to
     1e-3 absolute (BASELINE.json north_star).  Two candidates whose reference scores are `gap` apart can legitimately
     swap when each implementation's scores carry an error of gap / 2.  `noise` is the largest |score_cuda -
-    score_oracle| over the ranks of the same step on which both still agree: the swap is excused only if
-    gap <= 2 * noise AND that noise itself is small (<= 1e-4 relative to the score, ten times tighter than the
-    1e-3 relative tolerance on final scores) - or if the gap is below 2e-6 outright."""
+    score_oracle| over the candidates (source beam, token) that appear in BOTH top-2k lists of that step, the
+    swapped ones included: the swap is excused only if gap <= 2 * noise AND that noise itself is small (<= 1e-4
+    relative to the score, ten times tighter than the 1e-3 relative tolerance on final scores) - or if the gap is
+    below 2e-6 outright.  In words: the two implementations agree on every candidate's score to 1e-4 relative, and
+    only candidates the oracle itself holds closer together than twice that disagreement may change places."""
     return gap < NEAR_TIE or (gap <= 2.0 * noise and noise <= NOISE_RTOL * max(1.0, abs(score)))
 
 
@@ -486,7 +488,14 @@ def compare_with_oracle(m, weights, pcms, k, picks=None, lm_seed=None, lm_weight
                     o_ext = np.append(o_sc, float(tr["next_score"][s][j]))      # + the best candidate left out of the 2k
                     nb_ = [abs(o_ext[r0] - o_ext[x]) for x in (r0 - 1, r0 + 1) if 0 <= x <= K]
                     gap = float(min(nb_)) if r0 >= 0 else 0.0
-                    noise = float(np.max(np.abs(t["cand_scores"][s, i, :max(r0, 1)] - o_sc[:max(r0, 1)])))
+                    # noise: candidates are matched by IDENTITY (source beam, token) between the two top-2k lists of
+                    # the step - the ranks before the first difference alone are too few samples (one, when the
+                    # lists part at rank 1), and the swapped candidates themselves are the ones whose scores matter
+                    o_id = {(int(b_), int(t_)): float(v_) for b_, t_, v_ in zip(o_beam, o_tok, o_sc)}
+                    d_ = [abs(float(v_) - o_id[(int(b_), int(t_))])
+                          for b_, t_, v_ in zip(t["cand_beams"][s, i], t["cand_tokens"][s, i], t["cand_scores"][s, i])
+                          if (int(b_), int(t_)) in o_id]
+                    noise = float(max(d_)) if d_ else 0.0
                     div = (s, float(tr["margin_utt"][s][j]), r0, gap, float(o_sc[max(r0, 0)]), noise)
                     break
                 res["cand_score_rel_max"] = max(res["cand_score_rel_max"],
