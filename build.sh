@@ -10,7 +10,7 @@ OUT=chinese_asr_b200/libasr_b200.so
 OBJ=build/obj
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xptxas -v"
-SOURCES="api features gemm_tc encoder encoder_tc3 decoder wer"
+SOURCES="api features gemm_tc encoder encoder_tc3 decoder wer resample"
 if [ "$1" = "--clean" ]; then shift; rm -rf $OBJ; fi
 mkdir -p $OBJ
 echo "# build.sh $(date -u +%Y-%m-%dT%H:%M:%SZ)  $($NVCC --version | tail -1)" > build.log

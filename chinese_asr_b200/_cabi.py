@@ -95,6 +95,9 @@ SIGNATURES = {
     "asr_prefetch_pcm": (C.c_int, [C.c_void_p, C.c_void_p, c_int64_p, C.c_int]),
     "asr_bench_gemm": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_float_p, C.c_void_p]),
     "asr_launch_count": (C.c_int64, [C.c_void_p, C.c_int]),
+    "asr_convert_audio_length": (C.c_int64, [C.c_int64, C.c_int]),
+    "asr_convert_audio": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_float,
+                                    C.POINTER(C.c_int16), C.c_int64, c_int64_p, C.c_void_p]),
     "asr_stage_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "asr_stage_times": (C.c_int, [C.c_void_p, c_float_p, C.c_int]),
 }

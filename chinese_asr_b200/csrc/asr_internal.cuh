@@ -25,6 +25,7 @@ constexpr int kDecK = kEmb + kEnc + kDecH;   // 1280: [emb | ctx_prev | h_prev]
 constexpr int kProjK = kDecH + kEnc;    // 1024: [h | ctx]
 constexpr int kPad = 0, kSos = 1, kEos = 2;
 constexpr int kNfft = 512, kHop = 160, kWin = 400, kBins = 257, kWinOff = 56;
+constexpr int kSampleRate = 16000;        // gpd['sample_rate']
 constexpr int kMaxBeam = ASR_MAX_BEAM;
 constexpr int kNumSMs = 148;
 constexpr int kStages = 12;       // 8 pipeline stages + kernel-level timers (GEMM kernel, operand split)

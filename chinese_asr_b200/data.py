@@ -93,6 +93,56 @@ def read_pcm(path):
     return fast_read(path)
 
 
+def convert_pcm(samples, rate, norm_db=-1.0):
+    """The two steps of the reference's convert_audio (main.py:19-24: ffmpeg -ar 16000 -ac 1, sox --norm=-1) on
+    the device: `samples` [n] or [n, channels], int16 or float32 in [-1, 1) at `rate` Hz -> 16 kHz mono int16 with
+    its peak at norm_db dBFS.  Builder-defined filter (include/asr_b200.h: asr_convert_audio)."""
+    import ctypes as C
+    from . import _cabi
+    a = np.asarray(samples)
+    if a.ndim == 1:
+        a = a[:, None]
+    if a.dtype == np.int16:
+        fmt = _cabi.PCM_S16
+    elif np.issubdtype(a.dtype, np.floating):
+        a, fmt = a.astype(np.float32), _cabi.PCM_F32
+    else:
+        raise TypeError(f"waveform dtype {a.dtype}: only float (in [-1, 1)) or int16 PCM is accepted")
+    a = np.ascontiguousarray(a)
+    n, ch = a.shape
+    cap = int(_cabi.lib.asr_convert_audio_length(n, int(rate)))
+    out = np.empty(max(cap, 1), dtype=np.int16)
+    n_out = C.c_int64(0)
+    _cabi.check(_cabi.lib.asr_convert_audio(a.ctypes.data_as(C.c_void_p), fmt, n, ch, int(rate), float(norm_db),
+                                            out.ctypes.data_as(C.POINTER(C.c_int16)), cap, C.byref(n_out), None),
+                "asr_convert_audio")
+    return out[:n_out.value]
+
+
+def convert_audio(path, out_path='tmp.wav'):
+    """main.py:19-24: `path` -> 16 kHz mono 16-bit, peak-normalised to -1 dBFS, written to tmp.wav (the reference's
+    fixed output name); returns that path.  Input: integer-PCM WAV of any rate / channel count - the reference
+    hands `path` to ffmpeg, which also decodes compressed containers; that decoder is not part of this package."""
+    with wave.open(path, 'rb') as w:
+        rate, width, ch, n = w.getframerate(), w.getsampwidth(), w.getnchannels(), w.getnframes()
+        raw = w.readframes(n)
+    if width == 2:
+        a = np.frombuffer(raw, dtype='<i2').reshape(-1, ch)
+    elif width == 4:
+        a = (np.frombuffer(raw, dtype='<i4').astype(np.float32) / 2147483648.0).reshape(-1, ch)
+    else:
+        raise ValueError(f"unsupported sample width {width} in {path}")
+    pcm = convert_pcm(a, rate, -1.0)
+    if os.path.exists(out_path):
+        os.remove(out_path)
+    with wave.open(out_path, 'wb') as w:
+        w.setnchannels(1)
+        w.setsampwidth(2)
+        w.setframerate(gpd['sample_rate'])
+        w.writeframes(pcm.astype('<i2').tobytes())
+    return out_path
+
+
 class AudioBase(object):
     """Vocabulary + feature constants (data.py:371-382).  dict.pkl is read from `dict_path`
     (default: ./dict.pkl like the reference, then $ASR_DICT_PKL)."""

@@ -3,8 +3,10 @@
 
 Knobs kept: greedy (bw=None) vs beam (bw=4/8/16), lm_path -> second pass with lm_weight=1.5 /
 length_weight=1.5 (main.py:45-51), gpd['temperature' | 'max_len' | 'verbose'], dict.pkl vocab.
-Differences, by necessity: convert_audio (main.py:19-24 shells out to ffmpeg + sox) is out of scope,
-so `path` must already be 16 kHz mono PCM WAV.  lm_path: an ARPA file (order <= 3) is loaded into
+convert_audio (main.py:19-24 shells out to ffmpeg + sox) runs on the device (data.convert_audio: down-mix,
+windowed-sinc resampling to 16 kHz, peak normalisation to -1 dBFS; builder-defined, the two programs are not
+part of the reference tree): `path` is an integer-PCM WAV of any rate / channel count - decoding compressed
+containers, which ffmpeg also does for the reference, is not part of this package.  lm_path: an ARPA file (order <= 3) is loaded into
 device tables and the second pass runs on the GPU; anything else is handed to kenlm.LanguageModel like
 main.py:82 does (when the kenlm module is installed) and the finished hypotheses are rescored on the host
 with its .score() (Model._host_rescore, from asr_beam_nbest)."""
@@ -14,14 +16,16 @@ import torch
 
 import numpy as np
 
-from .data import AudioBase, _waveform
+from .data import AudioBase, _waveform, convert_audio
 from .gpd import gpd
 from .lm import NGramLM
 from .model import Model
 
 
 def parse(path, model, audio_base, lm_model, bw):
-    """main.py:27-65.  `path`: 16 kHz mono WAV file (or a float32 waveform array)."""
+    """main.py:27-65.  `path`: WAV file (any rate / channels: converted like main.py:30) or a 16 kHz waveform array."""
+    if isinstance(path, str):
+        path = convert_audio(path)          # main.py:30 -> 'tmp.wav'
     pcm = _waveform(path)        # fast_read (data.py:109): 16-bit samples are converted on the device
     # get_log_mel + per-utterance CMVN (main.py:36-37), fused in the feature kernels
     data = model.features([pcm], normalise=True)[0]

@@ -213,6 +213,18 @@ int asr_wer(asr_handle* h, const int32_t* h_hyp, const int32_t* h_hyp_len, int h
             const int32_t* h_ref, const int64_t* h_ref_off, int B, int32_t* h_dist,
             int32_t* h_hyp_chars, void* stream);
 
+/* convert_audio (main.py:19-24: `ffmpeg -sample_fmt s16 -ar 16000 -ac 1` + `sox --norm=-1`): interleaved PCM of any
+ * rate and channel count (h_pcm [n_frames, channels], enum asr_pcm_format) -> 16 kHz mono int16 whose peak sits at
+ * norm_db dBFS (-1 for the reference's sox call).  Down-mix = channel mean, resampler = Hann-windowed sinc with 16
+ * zero crossings and cutoff 0.97 x the lower Nyquist (16 kHz input passes through), normalisation without dither.
+ * BUILDER-DEFINED: the two external programs are not part of the reference tree, so there is no reference output
+ * to be identical to (parity unpinned; checked against oracle/asr_oracle.py:convert_audio to 1 LSB).  Needs no
+ * handle; runs on the current device.  *n_out = asr_convert_audio_length(n_frames, sample_rate) <= out_cap.
+ * Decoding compressed containers (the reference accepts whatever ffmpeg reads) is not part of it. */
+int64_t asr_convert_audio_length(int64_t n_frames, int sample_rate);
+int asr_convert_audio(const void* h_pcm, int format, int64_t n_frames, int channels, int sample_rate,
+                      float norm_db, int16_t* h_out, int64_t out_cap, int64_t* n_out, void* stream);
+
 /* Whole path for one batch, host buffers in / host buffers out (parse() in main.py:27-65 for a
  * batch): H2D copy of the PCM, features, encoder, greedy (k = 0) or beam decode, D2H of the
  * hypotheses.  h_pcm should be pinned for the copy to be asynchronous. */

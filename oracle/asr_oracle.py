@@ -683,6 +683,44 @@ def synth_pcm_int16(seed: int, n_samples: int) -> np.ndarray:
     return np.clip(np.round(x * 32768.0), -32768, 32767).astype(np.int16)
 
 
+def convert_audio(x, rate: int, norm_db: float = -1.0) -> np.ndarray:
+    """The device resampler's definition (chinese_asr_b200/csrc/resample.cu, include/asr_b200.h:
+    asr_convert_audio) restated in float64 - NOT a restatement of reference code: main.py:19-24 runs ffmpeg
+    (libswresample) and sox, neither of which is in the reference tree (parity unpinned).
+    x: [n] or [n, channels], int16 or float in [-1, 1).  Down-mix = channel mean; y[m] = sum_i x[i] h(m rate /
+    16000 - i) with h(d) = fc sinc(fc d) hann(d / W), fc = 0.97 min(1, 16000 / rate), W = 16 / fc; rate == 16000
+    passes through; out = round(y 10^(dB / 20) / max |y| 32768) clipped to int16."""
+    a = np.asarray(x)
+    if a.dtype == np.int16:
+        a = a.astype(np.float64) / 32768.0
+    a = a.astype(np.float64)
+    if a.ndim == 2:
+        a = a.astype(np.float32).sum(axis=1, dtype=np.float32).astype(np.float64) / a.shape[1] if a.shape[1] > 1 else a[:, 0]
+    n_in = a.shape[0]
+    n_out = n_in * 16000 // rate
+    if rate == 16000:
+        y = a[:n_out].copy()
+    else:
+        fc = 0.97 * min(1.0, 16000.0 / rate)
+        W = 16.0 / fc
+        iw = int(W) + 1
+        y = np.zeros(n_out)
+        m = np.arange(n_out, dtype=np.int64)
+        num = m * rate
+        ip = num // 16000
+        for off in range(-iw, iw + 2):
+            i = ip + off
+            ok = (i >= 0) & (i <= n_in - 1)
+            d = (num - i * 16000) / 16000.0
+            u = d / W
+            ok &= np.abs(u) < 1.0
+            h = fc * np.sinc(fc * d) * (0.5 + 0.5 * np.cos(np.pi * u))
+            y += np.where(ok, a[np.clip(i, 0, n_in - 1)] * h, 0.0)
+    peak = np.max(np.abs(y)) if n_out else 0.0
+    scale = (10.0 ** (norm_db / 20.0)) / peak if peak > 0 else 1.0
+    return np.clip(np.rint(y * scale * 32768.0), -32768, 32767).astype(np.int16)
+
+
 def batch_audio(batch: list, eps: float = 1e-7):
     """AudioLoader.batch_audio (data.py:509-518) for the RNN encoders: instance normalisation of every
     [L, 720] feature matrix with eps 1e-7 (main.py:37 uses 1e-6), lens as IntTensor."""

@@ -863,3 +863,44 @@ def check_arpa_oov():
     return {"max_abs": float(np.max(np.abs(np.array(dev) - np.array(ref)))),
             "unk_kept": int(t["uni_logp"][3] == np.float32(-2.5) and t["uni_bo"][3] == np.float32(-0.3)),
             "missing_maps_to_unk": int(t["id_map"][14] == 3 and t["id_map"][10] == 10)}
+
+
+def check_convert_audio(tmp_dir):
+    """Device resampler (asr_convert_audio through data.convert_pcm / data.convert_audio) vs O.convert_audio."""
+    import wave
+    from chinese_asr_b200 import data as D
+    rng = np.random.default_rng(77)
+    cases = {}
+
+    def speechlike(n, sr):
+        t = np.arange(n) / sr
+        x = sum(a * np.sin(2 * np.pi * f * t + p) for a, f, p in
+                zip((0.3, 0.2, 0.1, 0.05), (180.0, 950.0, 2900.0, 6100.0), (0.1, 1.3, 2.2, 0.7)))
+        return (x + 0.02 * rng.standard_normal(n)).astype(np.float32)
+
+    inputs = {
+        "stereo_44k1_f32": (np.stack([speechlike(44100, 44100), 0.5 * speechlike(44100, 44100)], 1), 44100),
+        "mono_48k_s16": (np.clip(np.rint(speechlike(30011, 48000) * 20000), -32768, 32767).astype(np.int16), 48000),
+        "mono_8k_s16": (np.clip(np.rint(speechlike(9001, 8000) * 12000), -32768, 32767).astype(np.int16), 8000),
+        "mono_22k05_f32": (speechlike(22050, 22050), 22050),
+        "stereo_16k_s16": (np.clip(np.rint(np.stack([speechlike(16000, 16000)] * 2, 1) * 9000), -32768, 32767).astype(np.int16), 16000),
+    }
+    for name, (x, sr) in inputs.items():
+        dev = D.convert_pcm(x, sr)
+        ora = O.convert_audio(x, sr)
+        n = min(len(dev), len(ora))
+        d = np.abs(dev[:n].astype(np.int32) - ora[:n].astype(np.int32))
+        cases[name] = (len(dev), len(ora), int(d.max()) if n else 0, float((d > 0).mean()) if n else 0.0)
+    # WAV round trip like main.py:30
+    x, sr = inputs["stereo_44k1_f32"]
+    src = os.path.join(tmp_dir, "in.wav")
+    with wave.open(src, "wb") as w:
+        w.setnchannels(2); w.setsampwidth(2); w.setframerate(sr)
+        xi = np.clip(np.rint(x * 32767), -32768, 32767).astype("<i2")
+        w.writeframes(xi.tobytes())
+    out = D.convert_audio(src, os.path.join(tmp_dir, "tmp.wav"))
+    with wave.open(out, "rb") as w:
+        rate, ch, raw = w.getframerate(), w.getnchannels(), w.readframes(w.getnframes())
+    got = np.frombuffer(raw, dtype="<i2")
+    want = D.convert_pcm(xi, sr)
+    return {"cases": cases, "wav_rate": rate, "wav_channels": ch, "wav_equal": bool(np.array_equal(got, want))}

@@ -130,3 +130,28 @@ def test_batch_audio_statistics():
     for y in out:
         assert float(y.mean(dim=0).abs().max()) < 1e-5
         assert float((y.std(dim=0) - 1).abs().max()) < 1e-5
+
+
+def test_convert_audio_oracle_properties():
+    """The builder-defined resampler (main.py:19-24 runs ffmpeg + sox, which are not in the reference tree): a tone
+    keeps its frequency and lands at -1 dBFS, content above the new Nyquist is rejected, 16 kHz input passes
+    through, the output length is floor(n * 16000 / rate)."""
+    sr = 48000
+    t = np.arange(sr // 2) / sr
+    tone = (0.3 * np.sin(2 * np.pi * 1000 * t)).astype(np.float32)
+    y = O.convert_audio(np.stack([tone, tone], 1), sr)
+    assert y.dtype == np.int16 and len(y) == len(tone) * 16000 // sr
+    assert int(np.abs(y).max()) == int(np.rint(10 ** (-1 / 20) * 32768))
+    sp = np.abs(np.fft.rfft(y.astype(np.float64)))
+    assert abs(np.argmax(sp) * 16000 / len(y) - 1000) < 4
+    mix = (0.3 * np.sin(2 * np.pi * 10000 * t) + 0.3 * np.sin(2 * np.pi * 500 * t)).astype(np.float32)
+    y2 = O.convert_audio(mix, sr)
+    sp2 = np.abs(np.fft.rfft(y2.astype(np.float64)))
+    f = np.arange(len(sp2)) * 16000 / len(y2)
+    assert sp2[(f > 5500) & (f < 6500)].max() < 1e-3 * sp2.max()          # the 10 kHz tone would alias to 6 kHz
+    x16 = (tone * 32767).astype(np.int16)
+    y3 = O.convert_audio(x16, 16000)
+    assert len(y3) == len(x16)
+    scale = 10 ** (-1 / 20) * 32768 / np.abs(x16).max()
+    assert np.array_equal(y3, np.clip(np.rint(x16 * scale), -32768, 32767).astype(np.int16))
+    assert np.all(O.convert_audio(np.zeros(4000, np.float32), 8000) == 0)  # silence stays silence

@@ -371,3 +371,15 @@ def test_zz_device_buffer_guards_intact(G):
     assert len(G._models) >= 4
     for key, m in G._models.items():
         m.check_guards()
+
+
+def test_convert_audio_vs_oracle(G, tmp_path):
+    """convert_audio (main.py:19-24) on the device against the numpy restatement of the same builder-defined filter:
+    16-bit output within 1 LSB (fp32 taps on the device, float64 in the oracle), lengths equal, 16 kHz pass-through
+    and the WAV round trip through data.convert_audio."""
+    r = G.check_convert_audio(str(tmp_path))
+    for name, (n_dev, n_ora, max_diff, frac_diff) in r["cases"].items():
+        assert n_dev == n_ora, name
+        assert max_diff <= 1, (name, max_diff)
+        assert frac_diff <= 0.02, (name, frac_diff)      # share of samples that differ at all
+    assert r["wav_rate"] == 16000 and r["wav_channels"] == 1 and r["wav_equal"]
