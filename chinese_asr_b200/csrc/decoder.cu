@@ -501,7 +501,8 @@ struct AttSmem {
     static constexpr size_t kBytes = sizeof(float) * (kRing + kKeys + kP + kSmall) + sizeof(uint64_t) * 2 * kAttStages + 16;
 };
 
-template <int K>
+// FULL: k == K (every beam slot of the instantiation is live: no per-beam branches in the consumers' inner loop)
+template <int K, bool FULL>
 __global__ void __launch_bounds__(256, K <= 8 ? 4 : 2)
 attention_stream_kernel(AttnParams p) {
     griddep_launch_dependents();
@@ -676,11 +677,19 @@ attention_stream_kernel(AttnParams p) {
         if (leader) s_wsum[warp * K + my_kb] = run_sum;
     } else {
         // ---------------- consumers: context accumulation -------------------------------------------
+        // All shared-memory traffic of the inner loop goes through 32-bit shared-window addresses computed ONCE and
+        // `ld.shared` with immediate offsets: with generic pointers the compiler rebuilt the window base (S2UR
+        // SR_CgaCtaId + ULEA) and the row offset for every beam - 9 overhead instructions per 8 FFMA2 (ncu r02b:
+        // FFMA2 were 34 % of the consumers' instructions, and the producers spent 43 % of their time waiting for them).
         const int cg4 = tid - 128;                         // 4 of the 512 encoder columns
         float2 a01[K], a23[K];
 #pragma unroll
         for (int kb = 0; kb < K; ++kb) { a01[kb] = make_float2(0.f, 0.f); a23[kb] = a01[kb]; }
         const float* enc_u = p.enc + (size_t)row0 * kEnc;
+        const uint32_t ring_u32 = smem_addr(s_ring) + (uint32_t)cg4 * 16u;
+        const uint32_t p_u32 = smem_addr(s_p);
+        const uint32_t scale_u32 = smem_addr(s_scale);
+        const uint32_t full_u32 = smem_addr(full_e), empty_u32 = smem_addr(empty_e);
         auto issue = [&](int st) {                         // rows [8 st, 8 st + 8) of the utterance -> ring slot
             const int slot = st % kAttStages;
             const int rows = min(kAttRows, nl - st * kAttRows);
@@ -698,29 +707,52 @@ attention_stream_kernel(AttnParams p) {
                 named_bar_sync(1 + buf, 256);              // this chunk's numerators are ready
 #pragma unroll
                 for (int kb = 0; kb < K; ++kb) {
-                    if (kb < k) {
-                        const float sc = s_scale[buf * K + kb];
+                    if (FULL || kb < k) {
+                        float sc;
+                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(sc) : "r"(scale_u32 + (uint32_t)((buf * K + kb) * 4)) : "memory");
                         a01[kb].x *= sc; a01[kb].y *= sc; a23[kb].x *= sc; a23[kb].y *= sc;
                     }
                 }
             }
-            att_mbar_wait(&full_e[slot], (uint32_t)((st / kAttStages) & 1));
+            {   // full[slot]: the stage's rows have landed
+                const uint32_t bar = full_u32 + (uint32_t)slot * 8u, par = (uint32_t)((st / kAttStages) & 1);
+                uint32_t done = 0;
+                unsigned spins = 0;
+                while (!done) {
+                    asm volatile(
+                        "{\n\t.reg .pred p;\n\t"
+                        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                        "selp.u32 %0, 1, 0, p;\n\t}"
+                        : "=r"(done) : "r"(bar), "r"(par) : "memory");
+                    if (!done && ++spins > (1u << 28)) __trap();
+                }
+            }
             const int rows = min(kAttRows, nl - l0);
-            const float4* er = reinterpret_cast<const float4*>(s_ring + slot * kAttRows * kEnc) + cg4;
+            const uint32_t erow = ring_u32 + (uint32_t)(slot * kAttRows * kEnc * 4);
+            const uint32_t wrow = p_u32 + (uint32_t)(((buf * K) * CP + lc) * 4);
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {               // 4 rows at a time: 16 registers of encoder data
                 float4 e[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    e[i] = 4 * hf + i < rows ? er[(4 * hf + i) * (kEnc / 4)] : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int i = 0; i < 4; ++i) {
+                    e[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (4 * hf + i < rows)
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                     : "=f"(e[i].x), "=f"(e[i].y), "=f"(e[i].z), "=f"(e[i].w)
+                                     : "r"(erow + (uint32_t)((4 * hf + i) * kEnc * 4)) : "memory");
+                }
                 if (hf == 1) {
                     __syncwarp();
-                    if (lane == 0) att_mbar_arrive(&empty_e[slot]);    // this warp has read the slot
+                    if (lane == 0)                          // this warp has read the slot
+                        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_u32 + (uint32_t)slot * 8u) : "memory");
                 }
 #pragma unroll
                 for (int kb = 0; kb < K; ++kb) {
-                    if (kb < k) {
-                        const float4 w4 = *reinterpret_cast<const float4*>(s_p + (buf * K + kb) * CP + lc + 4 * hf);
+                    if (FULL || kb < k) {
+                        float4 w4;
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                     : "=f"(w4.x), "=f"(w4.y), "=f"(w4.z), "=f"(w4.w)
+                                     : "r"(wrow + (uint32_t)((kb * CP + 4 * hf) * 4)) : "memory");
                         const float w[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
@@ -772,8 +804,13 @@ attention_stream_kernel(AttnParams p) {
 template <int K>
 static int launch_attention_stream(const AttnParams& p, int B, cudaStream_t st) {
     constexpr size_t smem = AttSmem<K>::kBytes;
-    ASR_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&attention_stream_kernel<K>), smem));
-    ASR_CUDA(launch_kernel(attention_stream_kernel<K>, dim3(B), dim3(256), smem, st, true, p));
+    if (p.k == K) {
+        ASR_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&attention_stream_kernel<K, true>), smem));
+        ASR_CUDA(launch_kernel(attention_stream_kernel<K, true>, dim3(B), dim3(256), smem, st, true, p));
+    } else {
+        ASR_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(&attention_stream_kernel<K, false>), smem));
+        ASR_CUDA(launch_kernel(attention_stream_kernel<K, false>, dim3(B), dim3(256), smem, st, true, p));
+    }
     return ASR_OK;
 }
 
