@@ -307,8 +307,8 @@ def run_native(args):
     R = B * k
     n_gemm = 4 + 1 + 3 * MAX_LEN
     roof_src = {}
-    try:        # ncu DRAM bytes per GEMM-engine launch of this workload (tools/prof_cmd.sh -> profiles/r02_roofline.json)
-        roof_src = json.load(open(os.path.join(ROOT, "profiles", "r02_roofline.json")))
+    try:        # ncu DRAM bytes per GEMM-engine launch of this workload (tools/prof_cmd.sh -> profiles/r02f_roofline.json)
+        roof_src = json.load(open(os.path.join(ROOT, "profiles", "r02f_roofline.json")))
     except Exception:
         pass
     kernel_ms = dict(stages)
@@ -318,7 +318,7 @@ def run_native(args):
     if dom.startswith("gemm"):
         ach = gemm_gflop / gemm_ms                        # GFLOP / ms = TFLOP/s (algorithmic fp32 2*M*N*K)
         # dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the 125 GEMM-engine launches of one
-        # pass of this workload (ncu, profiles/r02_pass_metrics.csv; captured at 512 utterances per step - the
+        # pass of this workload (ncu, profiles/r02f_pass_metrics.csv; captured at 512 utterances per step - the
         # operand / output bytes scale with the rows)
         gb = roof_src.get("gemm_dram_bytes_per_pass")
         traffic = gb / n_gemm * B / 512 if gb and (k, L) == (8, 332) else None

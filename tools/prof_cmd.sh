@@ -14,9 +14,9 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-fi
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --pipeline 1 > gpurun_out/ncu_bench.log 2>&1
 echo "launch list rc=$?"
 python tools/prof_step.py 512 8 1 > gpurun_out/plain_prof.log 2>&1 || exit 1
-# pass 2 of prof_step.py: skip the 1 + 217 launches of handle creation and the warm-up pass
+# pass 2 of prof_step.py: skip the 10 launches of handle creation (9 weight splits, the E' GEMM) and the 216 of the warm-up pass
 M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active
-ncu --metrics $M --clock-control none -s 230 -c 230 --csv --log-file gpurun_out/pass_${TAG}.csv \
+ncu --metrics $M --clock-control none -s 226 -c 216 --csv --log-file gpurun_out/pass_${TAG}.csv \
     python tools/prof_step.py 512 8 1 > gpurun_out/ncu_pass.log 2>&1
 echo "pass metrics rc=$?"
 ncu --set full --clock-control none -k regex:gemm_split_pair_kernel -s 1 -c 11 -f -o /tmp/prof_${TAG}_gemm \
