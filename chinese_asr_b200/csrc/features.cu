@@ -108,8 +108,7 @@ logmel_kernel(const S* __restrict__ pcm, const long long* __restrict__ pcm_off,
     for (int i = tid; i < kWin; i += 256) s_win[i] = g_window[i];
     for (int i = tid; i < 512; i += 256) s_tw[i] = g_tw512[i];
     // pe[i] = x[i + 1] - preemph * x[i]  (two roundings, like the reference's tensor expression)
-    const int per16 = 16 / (int)sizeof(S);
-    if ((x0 % per16) == 0) {
+    if ((reinterpret_cast<uintptr_t>(pcm + x0) & 15) == 0) {        // 16-byte aligned chunk start: vector loads
         for (int g = tid; g * 8 < span; g += 256) {
             float v[9];
             pcm_load9(pcm + x0 + 8 * g, v);          // reads x[8 g + 8] at most: inside the utterance (frame layout)

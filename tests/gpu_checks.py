@@ -577,6 +577,24 @@ def check_bench_shape(B=512, k=8, seconds=10.0, n_picks=32, seed0=41000):
     return compare_with_oracle(m, weights, pcms, k, picks=picks, label="bench shape")
 
 
+def check_odd_beam_widths():
+    """Beam widths that are not an instantiation size (the kernels are built for K = 1, 4, 8, 16 beam slots; bw = 3,
+    6, 11 run them with dead slots): small batches (two-phase attention kernel) with every utterance compared, and
+    one batch of 300 utterances (streaming attention kernel, partial-beam instantiation) with 10 picks."""
+    weights = O.make_weights(1234, "sharp", eos_bias=8.0)
+    m = get_model((1234, "sharp", 8.0), weights)
+    out = {}
+    for k in (3, 6, 11):
+        pcms = synth_batch([2.0, 3.1, 2.4, 4.0, 2.2, 3.6], 52000 + k)
+        out[f"small_k{k}"] = compare_with_oracle(m, weights, pcms, k, label=f"odd beam k={k}")
+    B = 300
+    pcms = synth_batch([2.0] * B, 53000)
+    rng = np.random.default_rng(53)
+    picks = [0, B - 1] + [int(x) for x in rng.integers(0, B, size=8)]
+    out["stream_k6"] = compare_with_oracle(m, weights, pcms, 6, picks=picks, label="odd beam k=6 B=300")
+    return out
+
+
 def check_config3_full(B=256, k=16, n_picks=24, seed0=26000):
     """BASELINE.json configs[2] at full size: bw=16, 256 utterances of mixed 2-20 s; 24 picks including the
     shortest and the longest against the oracle, plus bit-reproducibility of the whole batch."""

@@ -202,6 +202,15 @@ def test_bench_shape_picks_vs_oracle(G):
     assert r["B"] == 512 and r["finished_hyps"] > 32
 
 
+def test_odd_beam_widths_vs_oracle(G):
+    """bw 1...16 (reference main.py knob): widths between the instantiation sizes (3, 6, 11) against the oracle, on
+    the two-phase attention path (small batches) and the streaming path (300 utterances)."""
+    r = G.check_odd_beam_widths()
+    for name, res in r.items():
+        _strict(res, res["picks"])
+        assert res["finished_hyps"] > 0, name
+
+
 def test_config3_full_size_picks_vs_oracle(G):
     """configs[2] at full size: bw=16, 256 mixed 2-20 s utterances; 24 picks incl. shortest / longest."""
     r = G.check_config3_full()
