@@ -259,8 +259,8 @@ int asr_transcribe_device(asr_handle* h, const float* d_pcm, const int64_t* h_pc
 /* Scheduling knob of the encoder recurrence (the nn.LSTM time loop, util.py:1259): a batch is split into
  * `chunks_per_direction` (1..7, default 7) chunks of sequences per direction, each run by one cluster of 8 SMs.
  * 7 = shortest latency for one batch (14 clusters = 112 SMs); fewer, wider chunks leave more SMs to other handles'
- * work on the same GPU at the price of a longer step (measured at 512 x 10 s: 7.2 ms on 112 SMs, 8.0 ms on 96,
- * 10.8 ms on 64).  Results do not depend on it. */
+ * work on the same GPU at the price of a longer step (a step's MMA phase and gate phase both grow with the rows per
+ * cluster; measured at 512 x 10 s: 4.7 ms per batch with 7 chunks).  Results do not depend on it. */
 int asr_set_recurrence_chunks(asr_handle* h, int chunks_per_direction);
 
 /* The GEMM engine of the GEMM-shaped stages (nn.LSTM input projections util.py:1259, attention keys
