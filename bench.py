@@ -188,6 +188,8 @@ def run_native(args):
     cores = None
     if world > 1:     # before any engine / NCCL thread exists: this rank's own cores next to its GPU
         cores = parallel.pin_rank_to_local_cores(local, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
+        if cores:     # host-side torch work (weight initialisation) must not run more threads than this rank has cores
+            torch.set_num_threads(max(1, min(torch.get_num_threads(), len(cores))))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -412,11 +414,21 @@ def run_native(args):
 
 def main():
     args = parse_args()
-    if int(os.environ.get("RANK", "0")) == 0:
-        # torchrun exports OMP_NUM_THREADS=1; the CPU arms run on rank 0 and must see all host threads.
-        # This has to happen before torch creates its OpenMP pool (set_num_threads later is not enough).
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if int(os.environ.get("RANK", "0")) == 0 and (args.impl == "reference" or world == 1):
+        # torchrun exports OMP_NUM_THREADS=1; the CPU arms (the reference arm, and the cpu_baseline leg of the
+        # native arm at N = 1) run on rank 0 and must see all host threads.  This has to happen before torch creates
+        # its OpenMP pool (set_num_threads later is not enough).  NOT for the native arm at N > 1: there rank 0 pins
+        # itself to its own slice of the cores like every other rank (parallel.pin_rank_to_local_cores), and an
+        # OpenMP pool of os.cpu_count() spinning threads on that slice turns the host-side weight initialisation
+        # into minutes (observed: the 8-rank run did not finish in 10 minutes).
         os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
         os.environ["MKL_NUM_THREADS"] = str(os.cpu_count() or 1)
+    if args.impl == "native":
+        # the whole native run takes 1 - 3 minutes: a stuck one dumps every thread's stack and exits instead of
+        # hanging until the caller's timeout
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ.get("ASR_BENCH_WATCHDOG_S", "600")), exit=True)
     if args.impl == "reference":
         run_reference(args)
     else:
