@@ -67,7 +67,9 @@ def pin_rank_to_local_cores(local_rank, local_world):
     """Give every rank of a node its own slice of the CPU cores next to its GPU (NVML's ideal affinity of the
     device, split evenly between the ranks that share it), so that 8 ranks x (engine threads + NCCL proxy) do not
     migrate over all cores of the box.  Call before any worker thread exists; returns the cores or None when NVML
-    or sched_setaffinity is unavailable (nothing is changed then)."""
+    or sched_setaffinity is unavailable or a rank's slice would be smaller than 4 cores (nothing is changed then).
+    The caller must keep its OpenMP / torch thread count within the slice (bench.py: an os.cpu_count()-thread pool
+    on a 1/8 slice made host-side torch work ~100x slower)."""
     import os
     try:
         import pynvml
@@ -82,6 +84,8 @@ def pin_rank_to_local_cores(local_rank, local_world):
         sharing = [j for j in range(local_world) if sets[j] == sets[local_rank]]
         pos, n = sharing.index(local_rank), len(sharing)
         cores = mine[pos * len(mine) // n:(pos + 1) * len(mine) // n] or mine
+        if len(cores) < 4:          # too few cores to be worth fencing in (main + 2 engine threads + NCCL proxy)
+            return None
         os.sched_setaffinity(0, cores)
         return cores
     except Exception:
