@@ -151,3 +151,28 @@ def test_arpa_vocabulary_mismatch_tables(tmp_path):
     while t["bi_keys"][s] != 10 * V + 3:
         s = (s + 1) & (len(t["bi_keys"]) - 1)
     assert t["bi_vals"][s][0] == np.float32(-0.6)                                            # the literal "a <unk>" entry
+
+
+def test_convert_audio_has_no_cpu_fallback_and_checks_arguments():
+    """asr_convert_audio (main.py:19-24 on the device) rejects bad arguments with a message, and on a box without a
+    B200 it fails loudly instead of resampling on the host: the product has no CPU path."""
+    import ctypes as C
+    import torch
+    from chinese_asr_b200 import _cabi, data as D
+    n_out = C.c_int64(0)
+    out = np.zeros(16, dtype=np.int16)
+    x = np.zeros(32, dtype=np.int16)
+    rc = _cabi.lib.asr_convert_audio(x.ctypes.data_as(C.c_void_p), _cabi.PCM_S16, 32, 0, 16000, -1.0,
+                                     out.ctypes.data_as(C.POINTER(C.c_int16)), 16, C.byref(n_out), None)
+    assert rc == -1 and b"asr_convert_audio" in _cabi.lib.asr_last_error()          # channels = 0
+    rc = _cabi.lib.asr_convert_audio(x.ctypes.data_as(C.c_void_p), _cabi.PCM_S16, 32, 1, 32000, -1.0,
+                                     out.ctypes.data_as(C.POINTER(C.c_int16)), 8, C.byref(n_out), None)
+    assert rc == -4 and n_out.value == 16                                            # output buffer too small
+    assert _cabi.lib.asr_convert_audio_length(48000, 48000) == 16000
+    assert _cabi.lib.asr_convert_audio_length(44100, 44100) == 16000
+    assert _cabi.lib.asr_convert_audio_length(8000, 8000) == 16000
+    if not torch.cuda.is_available():
+        with pytest.raises(_cabi.AsrError):
+            D.convert_pcm(np.zeros(16000, dtype=np.int16), 48000)
+    with pytest.raises(TypeError):
+        D.convert_pcm(np.zeros(100, dtype=np.int32), 16000)
