@@ -43,3 +43,36 @@ def test_no_product_import_of_oracle():
                 s = open(os.path.join(dirpath, f), encoding="utf-8").read()
                 assert "import oracle" not in s and "from oracle" not in s, f
                 assert "/root/reference" not in s, f
+
+
+def test_single_thread_instructions_are_issued_from_uniform_code():
+    """Regression guard for the round-2 finding: tcgen05.mma / tcgen05.commit / TMA copies take
+    their operands from uniform registers; when the issue loop sits under a divergent branch ptxas wraps every one
+    of them in an ELECT + R2UR.BROADCAST + BRA.U.ANY loop that paces the tensor pipe.  The GEMM kernels must contain
+    none of those loops, the recurrence kernels at most the one around their multicast copy."""
+    import shutil
+    import subprocess
+    import pytest
+    from chinese_asr_b200 import _cabi
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not installed")
+    sass = subprocess.run(["cuobjdump", "-sass", _cabi.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    counts, mma, name = {}, {}, None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            name = m.group(1)
+            continue
+        if name is None:
+            continue
+        if "BRA.U.ANY" in line:
+            counts[name] = counts.get(name, 0) + 1
+        if "UTCHMMA" in line:
+            mma[name] = mma.get(name, 0) + 1
+    gemm = [n for n in mma if "gemm_split_pair_kernel" in n]
+    rec = [n for n in mma if "lstm_rec_tc3_kernel" in n]
+    assert gemm and rec, "tcgen05 kernels not found in the library"
+    for n in gemm:
+        assert counts.get(n, 0) == 0, (n, counts.get(n))
+    for n in rec:
+        assert counts.get(n, 0) <= 1, (n, counts.get(n))
